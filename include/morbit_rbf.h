@@ -1,0 +1,170 @@
+/* morbit_rbf.h -- C ABI of the B200-native RBF-surrogate hot path of Morbit.jl.
+ *
+ * This is the drop-in boundary: a Julia `GpuRbfConfig <: AbstractSurrogateConfig` (julia/GpuRbf.jl,
+ * INTEGRATION.md) implements Morbit's surrogate plugin interface
+ * (src/AbstractSurrogateInterface.jl:6-79) and reaches CUDA only through these `ccall`-able
+ * entry points.  Plain pointers and sizes only; no torch / CUDA types in any signature.
+ *
+ * Conventions
+ *   - all floating point is IEEE double; all ids are 1-based int32 (Morbit's Int ids, narrowed);
+ *   - "sites" are array-of-structs like the reference's Vector{SVector{n}}: site i of instance b
+ *     starts at sites[(b*stride + i) * n];  this is also Julia's column-major n x stride x B array;
+ *   - every call is batched over B independent instances (multistart runs / objective groups);
+ *     B = 1 is the single-`optimize` case;
+ *   - entry points without suffix take HOST pointers (borrowed for the duration of the call,
+ *     wrap in GC.@preserve) and return after the results are in host memory;
+ *     `_dev` entry points take DEVICE pointers, enqueue on the context's stream and return
+ *     without synchronising (mrbf_sync waits);
+ *   - return value 0 = ok, < 0 = error (mrbf_last_error gives the text); never aborts the process;
+ *     per-instance numerical failures are reported in `status[b]` and do not poison the batch;
+ *   - re-entrant: no global mutable state; one context per (host thread, device).
+ */
+#ifndef MORBIT_RBF_H
+#define MORBIT_RBF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRBF_ABI_VERSION 1
+
+/* src/models/RbfModel.jl:48-54 (RbfKernels), same order */
+enum mrbf_kernel {
+    MRBF_CUBIC = 0,
+    MRBF_INV_MULTIQUADRIC = 1,
+    MRBF_MULTIQUADRIC = 2,
+    MRBF_THIN_PLATE_SPLINE = 3,
+    MRBF_GAUSSIAN = 4
+};
+
+enum mrbf_status {
+    MRBF_OK = 0,
+    MRBF_EINVAL = -1,        /* bad argument */
+    MRBF_ECUDA = -2,         /* CUDA runtime error */
+    MRBF_ENOMEM = -3,
+    MRBF_EUNSUPPORTED = -4,  /* e.g. use_max_points (random sampling), polynomial degree > 1 */
+    MRBF_ENUMERIC = -5       /* at least one instance failed numerically; see status[] */
+};
+
+/* Mirrors RbfConfig, src/models/RbfModel.jl:66-112 (String shape parameters are evaluated on
+ * the Julia side, RbfModel.jl:135-143, and arrive here as numbers via `shape`). */
+typedef struct mrbf_cfg {
+    int32_t kernel;                /* enum mrbf_kernel */
+    int32_t polynomial_degree;     /* -1, 0, 1 */
+    double shape_parameter;        /* NaN => package default (RbfModel.jl:673) */
+    double theta_enlarge_1;
+    double theta_enlarge_2;
+    double theta_pivot;
+    double theta_pivot_cholesky;
+    int32_t max_model_points;      /* <= 0 => (n+1)(n+2)/2  (RbfModel.jl:356) */
+    int32_t use_max_points;        /* must be 0: the reference draws rand() points (RbfModel.jl:409-414) */
+    int32_t optimized_sampling;
+    int32_t reserved;
+} mrbf_cfg;
+
+typedef struct mrbf_ctx mrbf_ctx;
+typedef struct mrbf_model mrbf_model;   /* device-resident batch of fitted models (replaces RbfModel.model,
+                                           src/models/RbfModel.jl:33-38) */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int mrbf_abi_version(void);
+int mrbf_init(int device, mrbf_ctx** ctx);                 /* creates a private non-blocking stream */
+int mrbf_set_stream(mrbf_ctx* ctx, void* cuda_stream);     /* run on the caller's cudaStream_t instead */
+int mrbf_sync(mrbf_ctx* ctx);
+void mrbf_destroy(mrbf_ctx* ctx);
+const char* mrbf_last_error(const mrbf_ctx* ctx);
+/* kernels launched through this context since creation (the bench's gpu_launches counter) */
+int64_t mrbf_launch_count(const mrbf_ctx* ctx);
+
+/* ---- training-set search: replaces prepare_update_model rounds 1-4 --------------------------
+ * src/models/RbfModel.jl:518-655 (_rbf_round1 :242, _rbf_round2 :251, _rbf_round3 :269, _rbf_round4 :352),
+ * src/models/AffinelyIndependentPoints.jl:4-106, src/Databases.jl:324-327, src/utilities.jl:126-221, 437-448.
+ *
+ *   sites      B x db_stride x n   database sites of each instance (scaled space), ids 1..n_db[b]
+ *   n_db       B
+ *   x_index    B                   id of the current iterate in its database
+ *   x          B x n               current scaled iterate
+ *   delta      B                   trust-region radius;  delta_max: algorithm's maximum radius
+ *   glb, gub   n                   global scaled bounds (+-INFINITY when unbounded)
+ *   flags_in   B x 2               [ensure_fully_linear, force_rebuild]
+ *   max_new    B                   evaluation budget for round 3 (RbfModel.jl:613-618, computed by the host)
+ * outputs
+ *   r1, r2     B x n ids           round-1/2 picks in selection order;  n_r1, n_r2: B
+ *   r3_sites   B x n x n           new sites of round 3 (host appends them: new_result!, ids n_db+1..); n_r3: B
+ *   r4         B x r4_stride ids   round-4 picks in acceptance order;  n_r4: B
+ *   dirs       B x n x n           improving directions (column c at dirs[(b*n + c)*n]); n_dirs: B
+ *   flags_out  B x 2               [fully_linear, rebuilt (round 3 fell back to the coordinate rebuild, :634)]
+ *   status     B                   0 ok
+ */
+int mrbf_select_points(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                       const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                       const double* delta, double delta_max, const double* glb, const double* gub,
+                       const int32_t* flags_in, const int32_t* max_new,
+                       int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                       int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                       int32_t* flags_out, int32_t* status);
+int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                           const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                           const double* delta, double delta_max, const double* glb, const double* gub,
+                           const int32_t* flags_in, const int32_t* max_new,
+                           int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                           int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                           int32_t* flags_out, int32_t* status);
+
+/* _rbf_round4 alone with an explicit found set (used after _exploit_other_rbf_metas!, RbfModel.jl:311-342, 562,
+ * and called directly by test/rbf_models.jl:74-86).  found: B x found_stride ids (centre first), n_found: B;
+ * extra_sites: B x extra_stride x n sites that are in the found set but not (yet) in `sites` (may be NULL);
+ * lb2, ub2: B x n box. */
+int mrbf_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                const double* sites, const int32_t* n_db, const double* lb2, const double* ub2,
+                int32_t found_stride, const int32_t* found, const int32_t* n_found,
+                int32_t extra_stride, const double* extra_sites, const int32_t* n_extra,
+                int32_t r4_stride, int32_t* r4, int32_t* n_r4, int32_t* status);
+
+/* Device-side gather of the training set [centre; r1; r2; r3; r4] (_collect_indices, RbfModel.jl:178-186,
+ * and :754-757).  values: B x db_stride x k; r3_values: B x n x k (values of the new round-3 sites).
+ * Outputs train_sites B x train_stride x n, train_values B x train_stride x k, N: B. */
+int mrbf_gather_training_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int32_t db_stride,
+                             const double* sites, const double* values, const int32_t* x_index,
+                             const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                             const double* r3_sites, const double* r3_values, const int32_t* n_r3,
+                             int32_t r4_stride, const int32_t* r4, const int32_t* n_r4,
+                             int32_t train_stride, double* train_sites, double* train_values, int32_t* N);
+
+/* ---- model build: replaces update_model -> RBF.RBFInterpolationModel ---------------------------
+ * src/models/RbfModel.jl:743-767.  sites B x train_stride x n, values B x train_stride x k, N: B (sites used).
+ * shape: B per-instance shape parameters or NULL (then cfg->shape_parameter).  Creates one device-resident
+ * handle for the whole batch.  status[b]: 0 ok, > 0 reduced kernel matrix not positive definite at that column. */
+int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+               const int32_t* N, const double* sites, const double* values, const double* shape,
+               mrbf_model** model, int32_t* status);
+int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+                   const int32_t* N, const double* sites, const double* values, const double* shape,
+                   mrbf_model** model, int32_t* status);
+void mrbf_free_model(mrbf_ctx* ctx, mrbf_model* model);
+/* dimensions: out[0..5] = B, n, k, train_stride, p (polynomial basis size), effective polynomial degree */
+int mrbf_model_dims(const mrbf_model* model, int32_t* out6);
+/* coefficients for parity tests: w B x train_stride x k, lambda B x p x k (row c = basis function c: 1, x_1..x_n) */
+int mrbf_model_coeffs(mrbf_ctx* ctx, const mrbf_model* model, double* w, double* lambda);
+
+/* ---- evaluation: replaces eval_models / get_gradient / get_jacobian -----------------------------
+ * src/models/RbfModel.jl:783-800.  X: B x M x n trial points (M per instance);
+ * Y: B x M x k values; J: B x M x k x n Jacobians (row l = gradient of output l).  Y or J may be NULL. */
+int mrbf_eval(mrbf_ctx* ctx, const mrbf_model* model, int64_t M, const double* X, double* Y, double* J);
+int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* model, int64_t M, const double* X, double* Y, double* J);
+
+/* Armijo backtracking over surrogate values, all step sizes in one launch (src/descent.jl:150-185):
+ * evaluates m(x) and m(x + sigma_i * dir) for sigma_i = step0 * shrink^i (i = 0..max_loops, built by repeated
+ * multiplication like the reference) and returns the first i that satisfies the (strict) Armijo condition
+ * all(mx - mx_i >= sigma_i * c * omega), or the i at which the reference loop would have stopped.
+ * x, dir: B x n;  step0, omega: B;  outputs: step_index B, sigma B, x_plus B x n, mx B x k, mx_plus B x k. */
+int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* model, const double* x, const double* dir, const double* step0,
+                   const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
+                   int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORBIT_RBF_H */

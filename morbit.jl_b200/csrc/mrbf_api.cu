@@ -1,0 +1,508 @@
+// C ABI (include/morbit_rbf.h): context, workspaces, host<->device staging, kernel dispatch.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "mrbf_common.cuh"
+#include "mrbf_kernels.h"
+
+using namespace mrbf;
+
+namespace {
+
+constexpr size_t SMEM_LIMIT = 225 * 1024;   // of the 227 KB a CTA may opt in to on sm_100a
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct mrbf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    char err[512] = {0};
+    DevBuf ws[16];      // kernel workspaces (grow-only)
+    DevBuf hb[32];      // staging for the host-pointer entry points
+};
+
+struct mrbf_model {
+    int B, n, k, train_stride, p, deg;
+    int kernel, ibeta;
+    double sgn;
+    int* N = nullptr;
+    double* centers = nullptr;
+    double* w = nullptr;
+    double* lam = nullptr;
+    double* alpha2 = nullptr;
+};
+
+namespace {
+
+int fail(mrbf_ctx* c, int code, const char* fmt, const char* detail = "") {
+    if (c) snprintf(c->err, sizeof(c->err), fmt, detail);
+    return code;
+}
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return fail(ctx, MRBF_ECUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+int ensure(mrbf_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return MRBF_OK;
+    if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    b.cap = want;
+    return MRBF_OK;
+}
+#define ENSURE(buf, bytes) do { int r_ = ensure(ctx, (buf), (bytes)); if (r_ != MRBF_OK) return r_; } while (0)
+
+// Resolve RbfConfig's kernel parameters (_get_kernel_params, RbfModel.jl:665-690; package defaults for NaN).
+int resolve_radfn(mrbf_ctx* ctx, const mrbf_cfg* cfg, double shape, RadFn* rf, double* alpha, int* cpd) {
+    const bool nan = !(shape == shape);
+    rf->kernel = cfg->kernel; rf->ibeta = 0; rf->sgn = 1.0;
+    double a = 1.0;
+    switch (cfg->kernel) {
+    case MRBF_GAUSSIAN: a = nan ? 1.0 : shape; *cpd = 0; break;
+    case MRBF_INV_MULTIQUADRIC: a = nan ? 1.0 : shape; *cpd = 0; break;
+    case MRBF_MULTIQUADRIC: a = nan ? 1.0 : shape; rf->sgn = -1.0; *cpd = 1; break;        // (-1)^ceil(1/2)
+    case MRBF_CUBIC: {
+        int beta = nan ? 3 : (int)shape;
+        if (beta < 1 || beta % 2 == 0) return fail(ctx, MRBF_EINVAL, "cubic exponent must be a positive odd integer%s");
+        rf->ibeta = beta; *cpd = (beta + 1) / 2;                                            // ceil(beta/2)
+        rf->sgn = ((*cpd) & 1) ? -1.0 : 1.0;
+        break;
+    }
+    case MRBF_THIN_PLATE_SPLINE: {
+        int kk = nan ? 2 : (int)shape;
+        if (kk < 1) return fail(ctx, MRBF_EINVAL, "thin plate spline order must be >= 1%s");
+        rf->ibeta = kk; *cpd = kk + 1; rf->sgn = ((kk + 1) & 1) ? -1.0 : 1.0;
+        break;
+    }
+    default: return fail(ctx, MRBF_EINVAL, "unknown kernel id%s");
+    }
+    if (!(a > 0.0)) return fail(ctx, MRBF_EINVAL, "shape parameter must be strictly positive%s");
+    rf->alpha2 = a * a;
+    *alpha = a;
+    return MRBF_OK;
+}
+
+int check_cfg(mrbf_ctx* ctx, const mrbf_cfg* cfg) {
+    if (!cfg) return fail(ctx, MRBF_EINVAL, "cfg is NULL%s");
+    if (cfg->polynomial_degree < -1 || cfg->polynomial_degree > 1)
+        return fail(ctx, MRBF_EUNSUPPORTED, "polynomial_degree must be -1, 0 or 1%s");
+    if (cfg->use_max_points) return fail(ctx, MRBF_EUNSUPPORTED, "use_max_points draws random points on the host; not supported%s");
+    if (!(cfg->theta_enlarge_1 >= 1.0 && cfg->theta_enlarge_2 >= 1.0)) return fail(ctx, MRBF_EINVAL, "theta_enlarge must be >= 1%s");
+    if (!(cfg->theta_enlarge_1 * cfg->theta_pivot <= 1.0)) return fail(ctx, MRBF_EINVAL, "theta_pivot must be <= 1/theta_enlarge_1%s");
+    return MRBF_OK;
+}
+
+int max_points_of(const mrbf_cfg* cfg, int n) {
+    return cfg->max_model_points <= 0 ? ((n + 1) * (n + 2)) / 2 : cfg->max_model_points;
+}
+
+int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, const double* sites, const int* n_db,
+               const double* lb2, const double* ub2, int found_stride, const int* found, const int* n_found,
+               int extra_stride, const double* extra, const int* n_extra, int n0max, int r4_stride, int* r4, int* n_r4, int* status) {
+    RadFn rf; double alpha; int cpd;
+    int rc = resolve_radfn(ctx, cfg, cfg->shape_parameter, &rf, &alpha, &cpd);
+    if (rc != MRBF_OK) return rc;
+    const int p = poly_dim(n, cfg->polynomial_degree);
+    const int max_points = max_points_of(cfg, n);
+    // N never exceeds max_points (loop bound) nor n0max + #candidates
+    int NM = n0max + db_stride; if (NM > max_points) NM = max_points; if (NM < n0max) NM = n0max;
+    Round4Params R{};
+    R.B = B; R.n = n; R.db_stride = db_stride; R.found_stride = found_stride; R.extra_stride = extra_stride; R.r4_stride = r4_stride;
+    R.NM = NM; R.max_points = max_points;
+    R.cfg.polynomial_degree = cfg->polynomial_degree; R.cfg.optimized_sampling = cfg->optimized_sampling;
+    R.rf = rf;
+    const double t2 = cfg->theta_pivot_cholesky * cfg->theta_pivot_cholesky;
+    R.chol_thr = t2 * t2;
+    R.sites = sites; R.n_db = n_db; R.lb2 = lb2; R.ub2 = ub2; R.found = found; R.n_found = n_found;
+    R.extra_sites = extra; R.n_extra = n_extra; R.r4 = r4; R.n_r4 = n_r4; R.status = status;
+    ENSURE(ctx->ws[6], (size_t)B * db_stride);
+    R.cand = (unsigned char*)ctx->ws[6].p;
+    const size_t vecd = round4_vec_doubles(n, NM, p), wsd = round4_ws_doubles(n, NM, p);
+    size_t smem = vecd * sizeof(double);
+    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) { R.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); R.ws = nullptr; R.ws_stride = 0; }
+    else {
+        if (smem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
+        R.ws_in_smem = 0; R.ws_stride = wsd;
+        ENSURE(ctx->ws[7], (size_t)B * wsd * sizeof(double));
+        R.ws = (double*)ctx->ws[7].p;
+    }
+    CK(launch_round4(R, smem, ctx->stream));
+    ctx->launches += 1;
+    return MRBF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrbf_abi_version(void) { return MRBF_ABI_VERSION; }
+
+int mrbf_init(int device, mrbf_ctx** out) {
+    if (!out) return MRBF_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return MRBF_ECUDA;
+    mrbf_ctx* ctx = new (std::nothrow) mrbf_ctx();
+    if (!ctx) return MRBF_ENOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return MRBF_ECUDA;
+    }
+    ctx->own_stream = true;
+    *out = ctx;
+    return MRBF_OK;
+}
+
+int mrbf_set_stream(mrbf_ctx* ctx, void* s) {
+    if (!ctx) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)s;
+    return MRBF_OK;
+}
+
+int mrbf_sync(mrbf_ctx* ctx) {
+    if (!ctx) return MRBF_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
+void mrbf_destroy(mrbf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->ws) if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->hb) if (b.p) cudaFree(b.p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mrbf_last_error(const mrbf_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+int64_t mrbf_launch_count(const mrbf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ select
+int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                           const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                           const double* delta, double delta_max, const double* glb, const double* gub,
+                           const int32_t* flags_in, const int32_t* max_new,
+                           int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                           int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                           int32_t* flags_out, int32_t* status) {
+    if (!ctx) return MRBF_EINVAL;
+    int rc = check_cfg(ctx, cfg);
+    if (rc != MRBF_OK) return rc;
+    if (B <= 0 || n <= 0 || db_stride <= 0) return fail(ctx, MRBF_EINVAL, "B, n and db_stride must be positive%s");
+    CK(cudaSetDevice(ctx->device));
+    SelectParams S{};
+    S.B = B; S.n = n; S.db_stride = db_stride; S.found_stride = 2 * n + 1;
+    S.cfg.polynomial_degree = cfg->polynomial_degree; S.cfg.optimized_sampling = cfg->optimized_sampling;
+    S.cfg.theta_enlarge_1 = cfg->theta_enlarge_1; S.cfg.theta_enlarge_2 = cfg->theta_enlarge_2; S.cfg.theta_pivot = cfg->theta_pivot;
+    S.delta_max = delta_max;
+    S.sites = sites; S.n_db = n_db; S.x_index = x_index; S.x = x; S.delta = delta; S.glb = glb; S.gub = gub;
+    S.flags_in = flags_in; S.max_new = max_new;
+    S.r1 = r1; S.n_r1 = n_r1; S.r2 = r2; S.n_r2 = n_r2; S.r3_sites = r3_sites; S.n_r3 = n_r3; S.dirs = dirs; S.n_dirs = n_dirs;
+    S.flags_out = flags_out;
+    const size_t seeds = (size_t)B * db_stride * n * sizeof(double);
+    ENSURE(ctx->ws[0], seeds); ENSURE(ctx->ws[1], seeds); ENSURE(ctx->ws[2], (size_t)B * db_stride);
+    S.S = (double*)ctx->ws[0].p; S.T = (double*)ctx->ws[1].p; S.cflags = (unsigned char*)ctx->ws[2].p;
+    const int ldz = n | 1;
+    S.wz_in_smem = select_smem_bytes(n, true) <= SMEM_LIMIT;
+    if (!S.wz_in_smem) { ENSURE(ctx->ws[3], (size_t)B * 2 * n * ldz * sizeof(double)); S.WZ = (double*)ctx->ws[3].p; }
+    ENSURE(ctx->ws[4], (size_t)B * n * 2 * sizeof(double));
+    S.lb2 = (double*)ctx->ws[4].p; S.ub2 = S.lb2 + (size_t)B * n;
+    ENSURE(ctx->ws[5], ((size_t)B * S.found_stride + B) * sizeof(int));
+    S.found = (int*)ctx->ws[5].p; S.n_found = S.found + (size_t)B * S.found_stride;
+    CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem), ctx->stream));
+    ctx->launches += 1;
+    if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
+        rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,
+                        n, r3_sites, n_r3, n + 1, r4_stride, r4, n_r4, status);
+        if (rc != MRBF_OK) return rc;
+    } else {
+        CK(cudaMemsetAsync(n_r4, 0, sizeof(int) * (size_t)B, ctx->stream));
+        if (status) CK(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, ctx->stream));
+    }
+    return MRBF_OK;
+}
+
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+
+int mrbf_select_points(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                       const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                       const double* delta, double delta_max, const double* glb, const double* gub,
+                       const int32_t* flags_in, const int32_t* max_new,
+                       int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                       int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                       int32_t* flags_out, int32_t* status) {
+    if (!ctx) return MRBF_EINVAL;
+    if (B <= 0 || n <= 0 || db_stride <= 0 || r4_stride < 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    const size_t sB = sizeof(int) * (size_t)B, dBn = sizeof(double) * (size_t)B * n;
+    const size_t sites_b = sizeof(double) * (size_t)B * db_stride * n;
+    ENSURE(ctx->hb[0], sites_b); ENSURE(ctx->hb[1], sB * 5 + sB * 2); ENSURE(ctx->hb[2], dBn + sizeof(double) * (size_t)B + 2 * sizeof(double) * n);
+    ENSURE(ctx->hb[3], sizeof(int) * ((size_t)B * n * 2 + (size_t)B * (size_t)(r4_stride > 0 ? r4_stride : 1) + (size_t)B * 8));
+    ENSURE(ctx->hb[4], sizeof(double) * (size_t)B * n * n * 2);
+    double* d_sites = (double*)ctx->hb[0].p;
+    int* d_ndb = (int*)ctx->hb[1].p; int* d_xi = d_ndb + B; int* d_maxnew = d_xi + B; int* d_flags = d_maxnew + B;   // flags: 2B
+    double* d_x = (double*)ctx->hb[2].p; double* d_delta = d_x + (size_t)B * n; double* d_glb = d_delta + B; double* d_gub = d_glb + n;
+    int* d_r1 = (int*)ctx->hb[3].p; int* d_r2 = d_r1 + (size_t)B * n; int* d_r4 = d_r2 + (size_t)B * n;
+    int* d_cnt = d_r4 + (size_t)B * (r4_stride > 0 ? r4_stride : 1);   // n_r1,n_r2,n_r3,n_r4,n_dirs,(flags_out 2),status
+    double* d_r3 = (double*)ctx->hb[4].p; double* d_dirs = d_r3 + (size_t)B * n * n;
+    H2D(d_sites, sites, sites_b); H2D(d_ndb, n_db, sB); H2D(d_xi, x_index, sB); H2D(d_maxnew, max_new, sB); H2D(d_flags, flags_in, 2 * sB);
+    H2D(d_x, x, dBn); H2D(d_delta, delta, sizeof(double) * (size_t)B); H2D(d_glb, glb, sizeof(double) * n); H2D(d_gub, gub, sizeof(double) * n);
+    int rc = mrbf_select_points_dev(ctx, cfg, B, n, db_stride, d_sites, d_ndb, d_xi, d_x, d_delta, delta_max, d_glb, d_gub, d_flags,
+                                    d_maxnew, d_r1, d_cnt, d_r2, d_cnt + B, d_r3, d_cnt + 2 * B, r4_stride, d_r4, d_cnt + 3 * B,
+                                    d_dirs, d_cnt + 4 * B, d_cnt + 5 * B, d_cnt + 7 * B);
+    if (rc != MRBF_OK) return rc;
+    D2H(r1, d_r1, sizeof(int) * (size_t)B * n); D2H(r2, d_r2, sizeof(int) * (size_t)B * n);
+    if (r4_stride > 0) D2H(r4, d_r4, sizeof(int) * (size_t)B * r4_stride);
+    D2H(n_r1, d_cnt, sB); D2H(n_r2, d_cnt + B, sB); D2H(n_r3, d_cnt + 2 * B, sB); D2H(n_r4, d_cnt + 3 * B, sB);
+    D2H(n_dirs, d_cnt + 4 * B, sB); D2H(flags_out, d_cnt + 5 * B, 2 * sB);
+    if (status) D2H(status, d_cnt + 7 * B, sB);
+    D2H(r3_sites, d_r3, sizeof(double) * (size_t)B * n * n); D2H(dirs, d_dirs, sizeof(double) * (size_t)B * n * n);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
+int mrbf_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                const double* sites, const int32_t* n_db, const double* lb2, const double* ub2,
+                int32_t found_stride, const int32_t* found, const int32_t* n_found,
+                int32_t extra_stride, const double* extra_sites, const int32_t* n_extra,
+                int32_t r4_stride, int32_t* r4, int32_t* n_r4, int32_t* status) {
+    if (!ctx) return MRBF_EINVAL;
+    int rc = check_cfg(ctx, cfg);
+    if (rc != MRBF_OK) return rc;
+    if (B <= 0 || n <= 0 || db_stride <= 0 || found_stride <= 0 || r4_stride <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    if (!extra_sites) extra_stride = 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t sB = sizeof(int) * (size_t)B;
+    const size_t sites_b = sizeof(double) * (size_t)B * db_stride * n;
+    const size_t extra_b = sizeof(double) * (size_t)B * extra_stride * n;
+    ENSURE(ctx->hb[0], sites_b);
+    ENSURE(ctx->hb[5], sizeof(double) * (size_t)B * n * 2 + extra_b);
+    ENSURE(ctx->hb[6], sB * 4 + sizeof(int) * (size_t)B * ((size_t)found_stride + r4_stride));
+    double* d_sites = (double*)ctx->hb[0].p;
+    double* d_lb = (double*)ctx->hb[5].p; double* d_ub = d_lb + (size_t)B * n; double* d_extra = d_ub + (size_t)B * n;
+    int* d_ndb = (int*)ctx->hb[6].p; int* d_nf = d_ndb + B; int* d_ne = d_nf + B; int* d_nr4 = d_ne + B;
+    int* d_found = d_nr4 + B; int* d_r4 = d_found + (size_t)B * found_stride;
+    ENSURE(ctx->hb[7], sB);
+    int* d_status = (int*)ctx->hb[7].p;
+    H2D(d_sites, sites, sites_b); H2D(d_lb, lb2, sizeof(double) * (size_t)B * n); H2D(d_ub, ub2, sizeof(double) * (size_t)B * n);
+    H2D(d_ndb, n_db, sB); H2D(d_nf, n_found, sB); H2D(d_found, found, sizeof(int) * (size_t)B * found_stride);
+    if (extra_stride > 0) { H2D(d_extra, extra_sites, extra_b); H2D(d_ne, n_extra, sB); }
+    rc = run_round4(ctx, cfg, B, n, db_stride, d_sites, d_ndb, d_lb, d_ub, found_stride, d_found, d_nf, extra_stride,
+                    extra_stride > 0 ? d_extra : nullptr, extra_stride > 0 ? d_ne : nullptr, found_stride + extra_stride,
+                    r4_stride, d_r4, d_nr4, d_status);
+    if (rc != MRBF_OK) return rc;
+    D2H(r4, d_r4, sizeof(int) * (size_t)B * r4_stride); D2H(n_r4, d_nr4, sB);
+    if (status) D2H(status, d_status, sB);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
+int mrbf_gather_training_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int32_t db_stride,
+                             const double* sites, const double* values, const int32_t* x_index,
+                             const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                             const double* r3_sites, const double* r3_values, const int32_t* n_r3,
+                             int32_t r4_stride, const int32_t* r4, const int32_t* n_r4,
+                             int32_t train_stride, double* train_sites, double* train_values, int32_t* N) {
+    if (!ctx) return MRBF_EINVAL;
+    if (B <= 0 || n <= 0 || k <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    GatherParams G{};
+    G.B = B; G.n = n; G.k = k; G.db_stride = db_stride; G.r4_stride = r4_stride; G.train_stride = train_stride;
+    G.sites = sites; G.values = values; G.x_index = x_index; G.r1 = r1; G.n_r1 = n_r1; G.r2 = r2; G.n_r2 = n_r2;
+    G.r3_sites = r3_sites; G.r3_values = r3_values; G.n_r3 = n_r3; G.r4 = r4; G.n_r4 = n_r4;
+    G.train_sites = train_sites; G.train_values = train_values; G.N = N;
+    CK(launch_gather_training(G, ctx->stream));
+    ctx->launches += 1;
+    return MRBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ build
+void mrbf_free_model(mrbf_ctx* ctx, mrbf_model* m) {
+    if (!m) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(m->N); cudaFree(m->centers); cudaFree(m->w); cudaFree(m->lam); cudaFree(m->alpha2);
+    delete m;
+}
+
+int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+                   const int32_t* N, const double* sites, const double* values, const double* shape,
+                   mrbf_model** out, int32_t* status) {
+    if (!ctx || !out) return MRBF_EINVAL;
+    *out = nullptr;
+    int rc = check_cfg(ctx, cfg);
+    if (rc != MRBF_OK) return rc;
+    if (B <= 0 || n <= 0 || k <= 0 || k > 256 || train_stride <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    RadFn rf; double alpha; int cpd;
+    rc = resolve_radfn(ctx, cfg, cfg->shape_parameter, &rf, &alpha, &cpd);
+    if (rc != MRBF_OK) return rc;
+    int deg = cfg->polynomial_degree;
+    if (deg < cpd - 1) deg = cpd - 1;           // degree raised to cpd_order - 1 (assumption U4)
+    if (deg > 1) return fail(ctx, MRBF_EUNSUPPORTED, "kernel needs a polynomial tail of degree > 1%s");
+    const int p = poly_dim(n, deg), pl = p > 0 ? p : 1;
+    mrbf_model* m = new (std::nothrow) mrbf_model();
+    if (!m) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
+    m->B = B; m->n = n; m->k = k; m->train_stride = train_stride; m->p = p; m->deg = deg;
+    m->kernel = rf.kernel; m->ibeta = rf.ibeta; m->sgn = rf.sgn;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&m->N, sizeof(int) * (size_t)B);
+    if (e == cudaSuccess) e = cudaMalloc(&m->centers, sizeof(double) * (size_t)B * train_stride * n);
+    if (e == cudaSuccess) e = cudaMalloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
+    if (e == cudaSuccess) e = cudaMalloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
+    if (e == cudaSuccess) e = cudaMalloc(&m->alpha2, sizeof(double) * (size_t)B);
+    if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    BuildParams Pb{};
+    Pb.B = B; Pb.n = n; Pb.k = k; Pb.train_stride = train_stride; Pb.p = p; Pb.deg = deg;
+    Pb.kernel = rf.kernel; Pb.ibeta = rf.ibeta; Pb.sgn = rf.sgn; Pb.alpha_default = alpha;
+    Pb.N = N; Pb.sites = sites; Pb.values = values; Pb.shape = shape;
+    Pb.w = m->w; Pb.lam = m->lam; Pb.alpha2_out = m->alpha2; Pb.status = status; Pb.ld = train_stride;
+    const size_t vecd = build_vec_doubles(n, k, Pb.ld, p), wsd = build_ws_doubles(n, k, Pb.ld, p);
+    size_t smem = vecd * sizeof(double);
+    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) { Pb.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); }
+    else {
+        if (smem > SMEM_LIMIT) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_EUNSUPPORTED, "training set too large%s"); }
+        Pb.ws_in_smem = 0; Pb.ws_stride = wsd;
+        int r_ = ensure(ctx, ctx->ws[8], (size_t)B * wsd * sizeof(double));
+        if (r_ != MRBF_OK) { mrbf_free_model(ctx, m); return r_; }
+        Pb.ws = (double*)ctx->ws[8].p;
+    }
+    e = cudaMemcpyAsync(m->N, N, sizeof(int) * (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->centers, sites, sizeof(double) * (size_t)B * train_stride * n, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->w, 0, sizeof(double) * (size_t)B * train_stride * k, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->lam, 0, sizeof(double) * (size_t)B * pl * k, ctx->stream);
+    if (e == cudaSuccess) e = launch_build(Pb, smem, ctx->stream);
+    if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ECUDA, "CUDA error: %s", cudaGetErrorString(e)); }
+    ctx->launches += 1;
+    *out = m;
+    return MRBF_OK;
+}
+
+int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+               const int32_t* N, const double* sites, const double* values, const double* shape,
+               mrbf_model** out, int32_t* status) {
+    if (!ctx || !out) return MRBF_EINVAL;
+    if (B <= 0 || n <= 0 || k <= 0 || train_stride <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    const size_t sb = sizeof(double) * (size_t)B * train_stride * n, vb = sizeof(double) * (size_t)B * train_stride * k;
+    ENSURE(ctx->hb[8], sb); ENSURE(ctx->hb[9], vb); ENSURE(ctx->hb[10], sizeof(int) * (size_t)B * 2 + sizeof(double) * (size_t)B);
+    double* d_s = (double*)ctx->hb[8].p; double* d_v = (double*)ctx->hb[9].p;
+    double* d_shape = (double*)ctx->hb[10].p; int* d_N = (int*)(d_shape + B); int* d_status = d_N + B;
+    H2D(d_s, sites, sb); H2D(d_v, values, vb); H2D(d_N, N, sizeof(int) * (size_t)B);
+    if (shape) H2D(d_shape, shape, sizeof(double) * (size_t)B);
+    int rc = mrbf_build_dev(ctx, cfg, B, n, k, train_stride, d_N, d_s, d_v, shape ? d_shape : nullptr, out, d_status);
+    if (rc != MRBF_OK) return rc;
+    if (status) D2H(status, d_status, sizeof(int) * (size_t)B);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (status) for (int b = 0; b < B; ++b) if (status[b] != 0) return fail(ctx, MRBF_ENUMERIC, "at least one system failed; see status[]%s");
+    return MRBF_OK;
+}
+
+int mrbf_model_dims(const mrbf_model* m, int32_t* out6) {
+    if (!m || !out6) return MRBF_EINVAL;
+    out6[0] = m->B; out6[1] = m->n; out6[2] = m->k; out6[3] = m->train_stride; out6[4] = m->p; out6[5] = m->deg;
+    return MRBF_OK;
+}
+
+int mrbf_model_coeffs(mrbf_ctx* ctx, const mrbf_model* m, double* w, double* lambda) {
+    if (!ctx || !m) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (w) D2H(w, m->w, sizeof(double) * (size_t)m->B * m->train_stride * m->k);
+    if (lambda && m->p > 0) D2H(lambda, m->lam, sizeof(double) * (size_t)m->B * m->p * m->k);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ eval
+static void fill_eval(EvalParams& E, const mrbf_model* m, int64_t M, const double* X, double* Y, double* J) {
+    E.B = m->B; E.n = m->n; E.k = m->k; E.train_stride = m->train_stride; E.p = m->p; E.deg = m->deg;
+    E.kernel = m->kernel; E.ibeta = m->ibeta; E.sgn = m->sgn; E.M = M;
+    E.N = m->N; E.centers = m->centers; E.w = m->w; E.lam = m->lam; E.alpha2 = m->alpha2; E.X = X; E.Y = Y; E.J = J;
+}
+
+int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X, double* Y, double* J) {
+    if (!ctx || !m || !X || M < 0) return MRBF_EINVAL;
+    if (M == 0 || (!Y && !J)) return MRBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    int nl = 0;
+    EvalParams E{};
+    fill_eval(E, m, M, X, Y, J);       // with J the same pass also produces the values
+    CK(launch_eval(E, ctx->stream, &nl));
+    ctx->launches += nl;
+    return MRBF_OK;
+}
+
+int mrbf_eval(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X, double* Y, double* J) {
+    if (!ctx || !m || !X || M < 0) return MRBF_EINVAL;
+    if (M == 0 || (!Y && !J)) return MRBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t xb = sizeof(double) * (size_t)m->B * M * m->n, yb = sizeof(double) * (size_t)m->B * M * m->k;
+    const size_t jb = yb * m->n;
+    ENSURE(ctx->hb[11], xb);
+    if (Y) ENSURE(ctx->hb[12], yb);
+    if (J) ENSURE(ctx->hb[13], jb);
+    double* dX = (double*)ctx->hb[11].p; double* dY = Y ? (double*)ctx->hb[12].p : nullptr; double* dJ = J ? (double*)ctx->hb[13].p : nullptr;
+    H2D(dX, X, xb);
+    int rc = mrbf_eval_dev(ctx, m, M, dX, dY, dJ);
+    if (rc != MRBF_OK) return rc;
+    if (Y) D2H(Y, dY, yb);
+    if (J) D2H(J, dJ, jb);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
+int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const double* dir, const double* step0,
+                   const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
+                   int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus) {
+    if (!ctx || !m || !x || !dir || !step0 || !omega || max_loops < 0) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int B = m->B, n = m->n, k = m->k, ns = max_loops + 1;
+    const size_t dBn = sizeof(double) * (size_t)B * n, dB = sizeof(double) * (size_t)B, dBk = sizeof(double) * (size_t)B * k;
+    ENSURE(ctx->hb[14], 3 * dBn + 3 * dB + 2 * dBk + sizeof(int) * (size_t)B);
+    ENSURE(ctx->hb[15], sizeof(double) * (size_t)B * (ns + 1) * (n + k) + sizeof(double) * (size_t)B * ns);
+    double* d_x = (double*)ctx->hb[14].p; double* d_dir = d_x + (size_t)B * n; double* d_xp = d_dir + (size_t)B * n;
+    double* d_step = d_xp + (size_t)B * n; double* d_om = d_step + B; double* d_sig = d_om + B;
+    double* d_mx = d_sig + B; double* d_mxp = d_mx + (size_t)B * k; int* d_idx = (int*)(d_mxp + (size_t)B * k);
+    double* d_Xall = (double*)ctx->hb[15].p; double* d_Yall = d_Xall + (size_t)B * (ns + 1) * n; double* d_sall = d_Yall + (size_t)B * (ns + 1) * k;
+    H2D(d_x, x, dBn); H2D(d_dir, dir, dBn); H2D(d_step, step0, dB); H2D(d_om, omega, dB);
+    BacktrackParams Q{};
+    Q.B = B; Q.n = n; Q.k = k; Q.nsteps = ns; Q.strict = strict; Q.armijo_c = armijo_c; Q.shrink = shrink;
+    Q.min_stepsize = min_stepsize; Q.max_loops = max_loops;
+    Q.x = d_x; Q.dir = d_dir; Q.step0 = d_step; Q.omega = d_om; Q.Yall = d_Yall; Q.Xall = d_Xall; Q.sig_all = d_sall;
+    Q.step_index = d_idx; Q.sigma = d_sig; Q.x_plus = d_xp; Q.mx = d_mx; Q.mx_plus = d_mxp;
+    CK(launch_backtrack_points(Q, ctx->stream));
+    ctx->launches += 1;
+    int rc = mrbf_eval_dev(ctx, m, ns + 1, d_Xall, d_Yall, nullptr);
+    if (rc != MRBF_OK) return rc;
+    CK(launch_backtrack_pick(Q, ctx->stream));
+    ctx->launches += 1;
+    if (step_index) D2H(step_index, d_idx, sizeof(int) * (size_t)B);
+    if (sigma) D2H(sigma, d_sig, dB);
+    if (x_plus) D2H(x_plus, d_xp, dBn);
+    if (mx) D2H(mx, d_mx, dBk);
+    if (mx_plus) D2H(mx_plus, d_mxp, dBk);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// Batched RBF model build, one CTA per (instance, group) system.
+//
+// Replaces update_model -> RBF.RBFInterpolationModel (src/models/RbfModel.jl:743-767): solve
+//     [Phi Pi; Pi' 0] [w; lambda] = [Y; 0]        for k right-hand sides,
+// Phi_ij = phi(||x_i - x_j||), Pi = [1 x] (polynomial tail of degree <= 1).
+//
+// Route (north star): null-space method instead of the reference's dense LU of the (N+p)^2 saddle matrix.
+//   1. Householder QR of Pi (N x p), LAPACK geqr2 conventions;
+//   2. the same reflectors applied two-sidedly to Phi:  Phi~ = Q' Phi Q  (symmetric rank-2 updates,
+//      ~8 N^2 p flop, instead of forming Z explicitly and two N^2 m GEMMs);
+//   3. Cholesky of the trailing m x m block  Z' Phi Z  (m = N - p; positive definite for the
+//      conditionally positive definite kernels with the signs of mrbf_common.cuh);
+//   4. triangular solves for u, back-substitution with R for lambda, w = Q [0; u].
+// Mathematically the unique solution of the saddle system, so values/Jacobians agree with the reference to
+// O(cond * eps); see DESIGN.md for the measured deltas.
+//
+// The whole system lives in shared memory when (N^2 + N (p + k)) doubles fit, else in an L2-resident
+// global workspace; the code is identical, only the base pointer differs.
+#include "mrbf_common.cuh"
+#include "mrbf_kernels.h"
+
+namespace mrbf {
+
+// Right-looking Cholesky (lower) of the m x m block of A starting at (off, off).  red[74] <- failing column + 1.
+__device__ void chol_lower(double* A, int ld, int off, int m, double* red) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int c = 0; c < m; ++c) {
+        const int pc = off + c;
+        if (tid == 0) {
+            double d = A[pc + (size_t)pc * ld];
+            if (!(d > 0.0)) red[74] = (double)(c + 1);
+            else { d = sqrt(d); A[pc + (size_t)pc * ld] = d; red[75] = d; }
+        }
+        __syncthreads();
+        if (red[74] != 0.0) return;
+        const double dd = red[75];
+        const int rem = m - c - 1;
+        for (int i = tid; i < rem; i += nt) A[pc + 1 + i + (size_t)pc * ld] /= dd;
+        __syncthreads();
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int i = e % rem, l = e / rem;
+            if (i >= l) {
+                const int gi = pc + 1 + i, gl = pc + 1 + l;
+                A[gi + (size_t)gl * ld] = fma(-A[gi + (size_t)pc * ld], A[gl + (size_t)pc * ld], A[gi + (size_t)gl * ld]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Solve L L' U = Y in place for the k columns of Yv (rows off..off+m), L from chol_lower.
+__device__ void chol_solve(const double* A, int ld, int off, int m, double* Yv, int ldy, int k) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int c = 0; c < m; ++c) {                 // forward
+        const int pc = off + c;
+        if (tid < k) Yv[pc + (size_t)tid * ldy] /= A[pc + (size_t)pc * ld];
+        __syncthreads();
+        const int rem = m - c - 1;
+        for (int e = tid; e < rem * k; e += nt) {
+            const int i = pc + 1 + e % rem, q = e / rem;
+            Yv[i + (size_t)q * ldy] = fma(-A[i + (size_t)pc * ld], Yv[pc + (size_t)q * ldy], Yv[i + (size_t)q * ldy]);
+        }
+        __syncthreads();
+    }
+    for (int c = m - 1; c >= 0; --c) {            // backward with L'
+        const int pc = off + c;
+        if (tid < k) Yv[pc + (size_t)tid * ldy] /= A[pc + (size_t)pc * ld];
+        __syncthreads();
+        for (int e = tid; e < c * k; e += nt) {
+            const int l = off + e % c, q = e / c;
+            Yv[l + (size_t)q * ldy] = fma(-A[pc + (size_t)l * ld], Yv[pc + (size_t)q * ldy], Yv[l + (size_t)q * ldy]);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, k = P.k, p = P.p, ld = P.ld;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int pl = p > 0 ? p : 1;
+    double* v = smem;                // ld
+    double* pv = v + ld;             // ld
+    double* tauv = pv + ld;          // pl
+    double* red = tauv + pl;         // 80
+    double* mats = red + 80;
+    double* ws = P.ws_in_smem ? mats : P.ws + (size_t)b * P.ws_stride;
+    double* A = ws;                              // ld x ld
+    double* Pm = A + (size_t)ld * ld;            // ld x pl
+    double* Yv = Pm + (size_t)ld * pl;           // ld x k
+    const int N = P.N[b];
+    double* w_out = P.w + (size_t)b * P.train_stride * k;
+    double* lam_out = P.lam + (size_t)b * pl * k;
+    if (N <= 0 || N > P.train_stride) { if (tid == 0) P.status[b] = -1; return; }
+    const double* sites = P.sites + (size_t)b * P.train_stride * n;
+    const double* values = P.values + (size_t)b * P.train_stride * k;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn;
+    {
+        double a = P.alpha_default;
+        if (P.shape) { double sp = P.shape[b]; if (sp == sp) a = sp; }      // NaN => default
+        rf.alpha2 = a * a;
+        if (tid == 0) P.alpha2_out[b] = rf.alpha2;
+    }
+    if (tid == 0) red[74] = 0.0;
+    // ---- assembly (Gram matrix, polynomial block, right-hand sides)
+    for (int e = tid; e < N * N; e += nt) {
+        const int i = e % N, j = e / N;
+        const double* si = sites + (size_t)i * n; const double* sj = sites + (size_t)j * n;
+        double r2 = 0.0;
+        for (int c = 0; c < n; ++c) { double d = si[c] - sj[c]; r2 = fma(d, d, r2); }
+        A[i + (size_t)j * ld] = rad_phi(rf, r2);
+    }
+    for (int e = tid; e < N * p; e += nt) { const int i = e % N, c = e / N; Pm[i + (size_t)c * ld] = (c == 0) ? 1.0 : sites[(size_t)i * n + c - 1]; }
+    for (int e = tid; e < N * k; e += nt) { const int i = e % N, q = e / N; Yv[i + (size_t)q * ld] = values[(size_t)i * k + q]; }
+    __syncthreads();
+
+    if (N < p) {
+        // fewer sites than polynomial basis functions: w = 0, minimum-norm lambda = Pi' (Pi Pi')^{-1} Y  (U9)
+        for (int e = tid; e < N * N; e += nt) {
+            const int i = e % N, j = e / N;
+            double a = 0.0;
+            for (int c = 0; c < p; ++c) a = fma(Pm[i + (size_t)c * ld], Pm[j + (size_t)c * ld], a);
+            A[i + (size_t)j * ld] = a;
+        }
+        __syncthreads();
+        chol_lower(A, ld, 0, N, red);
+        if (red[74] != 0.0) { if (tid == 0) P.status[b] = (int)red[74]; return; }
+        chol_solve(A, ld, 0, N, Yv, ld, k);
+        for (int e = tid; e < p * k; e += nt) {
+            const int c = e / k, q = e % k;
+            double a = 0.0;
+            for (int i = 0; i < N; ++i) a = fma(Pm[i + (size_t)c * ld], Yv[i + (size_t)q * ld], a);
+            lam_out[(size_t)c * k + q] = a;
+        }
+        for (int e = tid; e < N * k; e += nt) w_out[e] = 0.0;
+        if (tid == 0) P.status[b] = 0;
+        return;
+    }
+
+    // ---- Householder QR of Pi, reflectors applied to Pi, Y and two-sidedly to Phi
+    for (int j = 0; j < p; ++j) {
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < N; i += nt) { double a = Pm[i + (size_t)j * ld]; part = fma(a, a, part); }
+        const double xn2 = block_sum(part, red);
+        if (tid == 0) {
+            double alpha = Pm[j + (size_t)j * ld], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
+            if (xnorm != 0.0) {
+                beta = -copysign(hypot(alpha, xnorm), alpha);
+                tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta);
+            }
+            tauv[j] = tau; red[70] = sc; red[71] = beta;
+        }
+        __syncthreads();
+        const double tau = tauv[j], sc = red[70];
+        for (int i = tid; i < N; i += nt) {
+            double vi = (i < j) ? 0.0 : ((i == j) ? 1.0 : Pm[i + (size_t)j * ld] * sc);
+            v[i] = vi;
+            if (i > j) Pm[i + (size_t)j * ld] = vi;
+        }
+        if (tid == 0) Pm[j + (size_t)j * ld] = red[71];
+        __syncthreads();
+        if (tau == 0.0) continue;
+        // trailing columns of Pi and all columns of Y: warp per column
+        const int ncols = (p - j - 1) + k;
+        for (int cc = warp; cc < ncols; cc += nwarps) {
+            double* col = (cc < p - j - 1) ? Pm + (size_t)(j + 1 + cc) * ld : Yv + (size_t)(cc - (p - j - 1)) * ld;
+            double a = 0.0;
+            for (int i = j + lane; i < N; i += 32) a = fma(v[i], col[i], a);
+            a = warp_sum(a) * tau;
+            for (int i = j + lane; i < N; i += 32) col[i] = fma(-a, v[i], col[i]);
+        }
+        // Phi <- H Phi H :  pv = tau Phi v ; K = tau/2 v'pv ; wv = pv - K v ; Phi -= v wv' + wv v'
+        double part2 = 0.0;
+        for (int i = tid; i < N; i += nt) {
+            double a0 = 0.0, a1 = 0.0;
+            int l = j;
+            for (; l + 2 <= N; l += 2) { a0 = fma(A[i + (size_t)l * ld], v[l], a0); a1 = fma(A[i + (size_t)(l + 1) * ld], v[l + 1], a1); }
+            for (; l < N; ++l) a0 = fma(A[i + (size_t)l * ld], v[l], a0);
+            const double a = tau * (a0 + a1);
+            pv[i] = a;
+            part2 = fma(v[i], a, part2);
+        }
+        const double K = 0.5 * tau * block_sum(part2, red);
+        for (int i = tid; i < N; i += nt) pv[i] = fma(-K, v[i], pv[i]);
+        __syncthreads();
+        for (int e = tid; e < N * N; e += nt) {
+            const int i = e % N, l = e / N;
+            if (i >= j || l >= j) A[i + (size_t)l * ld] -= v[i] * pv[l] + pv[i] * v[l];
+        }
+        __syncthreads();
+    }
+    // ---- Cholesky of Z' Phi Z and the solves
+    const int m = N - p;
+    chol_lower(A, ld, p, m, red);
+    if (red[74] != 0.0) { if (tid == 0) P.status[b] = (int)red[74]; return; }
+    chol_solve(A, ld, p, m, Yv, ld, k);                      // rows p.. of Yv now hold u
+    for (int e = tid; e < p * k; e += nt) {                  // top block: (Q'y)_top - Phi~[top, bottom] u
+        const int r = e % p, q = e / p;
+        double a = Yv[r + (size_t)q * ld];
+        for (int c = 0; c < m; ++c) a = fma(-A[r + (size_t)(p + c) * ld], Yv[p + c + (size_t)q * ld], a);
+        Yv[r + (size_t)q * ld] = a;
+    }
+    __syncthreads();
+    for (int c = p - 1; c >= 0; --c) {                       // R lambda = top
+        if (tid < k) Yv[c + (size_t)tid * ld] /= Pm[c + (size_t)c * ld];
+        __syncthreads();
+        for (int e = tid; e < c * k; e += nt) {
+            const int r = e % c, q = e / c;
+            Yv[r + (size_t)q * ld] = fma(-Pm[r + (size_t)c * ld], Yv[c + (size_t)q * ld], Yv[r + (size_t)q * ld]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < p * k; e += nt) { const int c = e / k, q = e % k; lam_out[(size_t)c * k + q] = Yv[c + (size_t)q * ld]; }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) { const int r = e % p, q = e / p; Yv[r + (size_t)q * ld] = 0.0; }
+    __syncthreads();
+    for (int q = warp; q < k; q += nwarps) {                 // w = H_0 ... H_{p-1} [0; u], warp per right-hand side
+        double* col = Yv + (size_t)q * ld;
+        for (int j = p - 1; j >= 0; --j) {
+            const double tau = tauv[j];
+            if (tau == 0.0) continue;
+            const double* vj = Pm + (size_t)j * ld;
+            double a = 0.0;
+            for (int i = j + 1 + lane; i < N; i += 32) a = fma(vj[i], col[i], a);
+            a = (warp_sum(a) + col[j]) * tau;
+            for (int i = j + 1 + lane; i < N; i += 32) col[i] = fma(-a, vj[i], col[i]);
+            __syncwarp();
+            if (lane == 0) col[j] -= a;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < N * k; e += nt) { const int i = e / k, q = e % k; w_out[e] = Yv[i + (size_t)q * ld]; }
+    if (tid == 0) P.status[b] = 0;
+}
+
+size_t build_vec_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return 2 * (size_t)ld + pl + 80; }
+size_t build_ws_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return (size_t)ld * ld + (size_t)ld * pl + (size_t)ld * k; }
+
+cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    build_kernel<<<P.B, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace mrbf

@@ -1,0 +1,178 @@
+// Shared device helpers for the sm_100a RBF kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/morbit_rbf.h"
+
+namespace mrbf {
+
+// Radial function with resolved parameters (what RBF._get_rad_func returns, RbfModel.jl:692-696).
+struct RadFn {
+    int kernel;      // enum mrbf_kernel
+    int ibeta;       // cubic exponent (1,3,5,..) or thin-plate k
+    double alpha2;   // shape parameter squared
+    double sgn;      // sign making phi conditionally positive definite
+};
+
+// phi as a function of the SQUARED distance (saves the sqrt for gaussian / multiquadrics).
+__device__ __forceinline__ double rad_phi(const RadFn& f, double r2) {
+    switch (f.kernel) {
+    case MRBF_CUBIC: {
+        double r = sqrt(r2);
+        double out = r;
+        for (int e = 2; e < f.ibeta; e += 2) out *= r2;      // r^beta for odd beta
+        return f.sgn * out;
+    }
+    case MRBF_MULTIQUADRIC: return f.sgn * sqrt(fma(f.alpha2, r2, 1.0));
+    case MRBF_INV_MULTIQUADRIC: return 1.0 / sqrt(fma(f.alpha2, r2, 1.0));
+    case MRBF_GAUSSIAN: return exp(-f.alpha2 * r2);
+    default: {   // thin plate spline: sgn * r^(2k) log r
+        if (r2 == 0.0) return 0.0;
+        double p = r2;
+        for (int e = 1; e < f.ibeta; ++e) p *= r2;
+        return f.sgn * p * (0.5 * log(r2));
+    }
+    }
+}
+
+// psi = phi'(r)/r as a function of the squared distance; 0 where singular at r = 0.
+__device__ __forceinline__ double rad_psi(const RadFn& f, double r2) {
+    switch (f.kernel) {
+    case MRBF_CUBIC: {
+        if (r2 == 0.0) return 0.0;
+        double r = sqrt(r2);
+        double out = (f.ibeta == 1) ? 1.0 / r : r;            // beta r^(beta-2)
+        for (int e = 4; e < f.ibeta; e += 2) out *= r2;
+        return f.sgn * (double)f.ibeta * out;
+    }
+    case MRBF_MULTIQUADRIC: return f.sgn * f.alpha2 / sqrt(fma(f.alpha2, r2, 1.0));
+    case MRBF_INV_MULTIQUADRIC: {
+        double t = fma(f.alpha2, r2, 1.0);
+        return -f.alpha2 / (t * sqrt(t));
+    }
+    case MRBF_GAUSSIAN: return -2.0 * f.alpha2 * exp(-f.alpha2 * r2);
+    default: {
+        if (r2 == 0.0) return 0.0;
+        double p = 1.0;
+        for (int e = 1; e < f.ibeta; ++e) p *= r2;
+        return f.sgn * p * ((double)f.ibeta * log(r2) + 1.0);
+    }
+    }
+}
+
+// phi and psi together (shares the transcendental).
+__device__ __forceinline__ void rad_phi_psi(const RadFn& f, double r2, double& phi, double& psi) {
+    switch (f.kernel) {
+    case MRBF_CUBIC: {
+        double r = sqrt(r2);
+        if (f.ibeta == 3) { phi = f.sgn * r2 * r; psi = f.sgn * 3.0 * r; return; }
+        phi = rad_phi(f, r2); psi = rad_psi(f, r2); return;
+    }
+    case MRBF_MULTIQUADRIC: {
+        double s = sqrt(fma(f.alpha2, r2, 1.0));
+        phi = f.sgn * s; psi = f.sgn * f.alpha2 / s; return;
+    }
+    case MRBF_INV_MULTIQUADRIC: {
+        double t = fma(f.alpha2, r2, 1.0);
+        double is = 1.0 / sqrt(t);
+        phi = is; psi = -f.alpha2 * is / t; return;
+    }
+    case MRBF_GAUSSIAN: {
+        double e = exp(-f.alpha2 * r2);
+        phi = e; psi = -2.0 * f.alpha2 * e; return;
+    }
+    default: phi = rad_phi(f, r2); psi = rad_psi(f, r2); return;
+    }
+}
+
+__host__ __device__ inline int poly_dim(int n, int deg) { return deg < 0 ? 0 : (deg == 0 ? 1 : n + 1); }
+
+// ---- block-wide reductions (deterministic order) ----------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum over the block; result returned to every thread.  red: >= 33 doubles of shared scratch.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();                       // protect red[] from the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < nw) ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// Two sums at once.
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { red[warp] = a; red[33 + warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < nw) ? red[lane] : 0.0;
+        double u = (lane < nw) ? red[33 + lane] : 0.0;
+        t = warp_sum(t); u = warp_sum(u);
+        if (lane == 0) { red[32] = t; red[65] = u; }
+    }
+    __syncthreads();
+    a = red[32]; b = red[65];
+}
+
+// argmax with "first maximiser" tie-breaking (smallest id wins), ids >= 0; id = -1 when empty.
+struct ArgMax { double v; int id; };
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+    if (b.id < 0) return a;
+    if (a.id < 0) return b;
+    if (b.v > a.v || (b.v == a.v && b.id < a.id)) return b;
+    return a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax m, double* redv, int* redi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax t; t.v = __shfl_xor_sync(0xffffffffu, m.v, o); t.id = __shfl_xor_sync(0xffffffffu, m.id, o);
+        m = better(m, t);
+    }
+    __syncthreads();
+    if (lane == 0) { redv[warp] = m.v; redi[warp] = m.id; }
+    __syncthreads();
+    if (warp == 0) {
+        ArgMax t; t.v = (lane < nw) ? redv[lane] : 0.0; t.id = (lane < nw) ? redi[lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgMax s; s.v = __shfl_xor_sync(0xffffffffu, t.v, o); s.id = __shfl_xor_sync(0xffffffffu, t.id, o);
+            t = better(t, s);
+        }
+        if (lane == 0) { redv[32] = t.v; redi[32] = t.id; }
+    }
+    __syncthreads();
+    ArgMax r; r.v = redv[32]; r.id = redi[32];
+    return r;
+}
+
+// LinearAlgebra.givensAlgorithm convention (utilities.jl:443 -> LAPACK dlartg, pre-3.10 signs).
+__device__ __forceinline__ void givens(double f, double g, double& c, double& s) {
+    if (g == 0.0) { c = 1.0; s = 0.0; return; }
+    if (f == 0.0) { c = 0.0; s = 1.0; return; }
+    double r = hypot(f, g);
+    c = f / r; s = g / r;
+    if (fabs(f) > fabs(g) && c < 0.0) { c = -c; s = -s; }
+}
+
+}  // namespace mrbf

@@ -1,0 +1,359 @@
+// Batched surrogate evaluation and Jacobians: eval_models / get_gradient / get_jacobian
+// (src/models/RbfModel.jl:783-800 -> RBF model call, grad, jac; callers descent.jl:150-185, 196, algorithm.jl:766-767).
+//
+//   m_l(x)      = sum_i w_il phi(||x - c_i||) + lambda_0l + sum_r lambda_(r+1)l x_r
+//   grad m_l(x) = sum_i w_il psi(||x - c_i||) (x - c_i) + lambda_(1..n)l ,   psi = phi'(rho)/rho
+//
+// Tiled kernel (n <= 64): a CTA owns 64 trial points and streams the centres through shared memory 64 at a
+// time.  Both contractions are register-tiled FP64 GEMMs (4 x 4 micro-tiles, 16 independent DFMA chains):
+//   phase 1   D = X' C'^T          -> rho^2 = |x'|^2 + |c'|^2 - 2 D   (coordinates centred at the first
+//             centre, i.e. the trust-region centre, so the cancellation error is O(eps Delta^2))
+//   phase 2   J_l -= (psi .* w_l) C'  through a shared 64 x 64 tile,   J_l += x' rowsum(psi .* w_l)
+// Values are accumulated in registers and reduced over the 16 threads of a point row with shuffles.
+// The generic kernel (any n) is the simple one-thread-per-point form used for n > 64.
+#include "mrbf_common.cuh"
+#include "mrbf_kernels.h"
+
+namespace mrbf {
+
+constexpr int TM = 64;    // trial points per CTA
+constexpr int TN = 64;    // centres per tile
+constexpr int GLD = TN + 1;
+
+template <int CQ, bool WANT_J>
+__global__ void __launch_bounds__(256, 1) eval_tile_kernel(EvalParams P, int l0, int kk) {
+    constexpr int ND = 16 * CQ;           // padded coordinate count
+    constexpr int KG = WANT_J ? 2 : 4;    // outputs handled per pass
+    extern __shared__ __align__(16) double smem[];
+    double* Xs = smem;                    // ND x TM   coordinate-major
+    double* Cs = Xs + ND * TM;            // ND x TN   coordinate-major (phase 1)
+    double* Cc = Cs + ND * TN;            // TN x ND   centre-major    (phase 2)
+    double* Gs = Cc + TN * ND;            // TM x GLD
+    double* xx = Gs + TM * GLD;           // TM
+    double* cc = xx + TM;                 // TN
+    double* Wt = cc + TN;                 // KG x TN
+    double* xref = Wt + KG * TN;          // ND
+    const int b = blockIdx.y, n = P.n, k = P.k, tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const long long m0 = (long long)blockIdx.x * TM;
+    const int N = P.N[b];
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* w = P.w + (size_t)b * P.train_stride * k;
+    const int pl = P.p > 0 ? P.p : 1;
+    const double* lam = P.lam + (size_t)b * pl * k;
+    const double* X = P.X + (size_t)b * P.M * n;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn; rf.alpha2 = P.alpha2[b];
+
+    for (int c = tid; c < ND; c += 256) xref[c] = (c < n) ? centers[c] : 0.0;
+    __syncthreads();
+    for (int e = tid; e < TM * n; e += 256) {              // coalesced read of the point tile (AoS rows)
+        const int pt = e / n, c = e % n;
+        const long long mi = m0 + pt;
+        Xs[c * TM + pt] = (mi < P.M) ? X[(size_t)mi * n + c] - xref[c] : 0.0;
+    }
+    for (int e = tid; e < TM * (ND - n); e += 256) { const int pt = e % TM, c = n + e / TM; Xs[c * TM + pt] = 0.0; }
+    __syncthreads();
+    if (tid < TM) { double s = 0.0; for (int c = 0; c < n; ++c) { double a = Xs[c * TM + tid]; s = fma(a, a, s); } xx[tid] = s; }
+
+    double accY[4][KG];
+    double accJ[WANT_J ? KG : 1][4][CQ];
+    double gsum[WANT_J ? KG : 1][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int l = 0; l < KG; ++l) accY[a][l] = 0.0;
+    if constexpr (WANT_J) {
+#pragma unroll
+        for (int l = 0; l < KG; ++l)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { gsum[l][a] = 0.0;
+#pragma unroll
+                for (int c = 0; c < CQ; ++c) accJ[l][a][c] = 0.0; }
+    }
+
+    for (int c0 = 0; c0 < N; c0 += TN) {
+        __syncthreads();
+        for (int e = tid; e < TN * n; e += 256) {           // centre tile, both layouts
+            const int j = e / n, c = e % n;
+            const double val = (c0 + j < N) ? centers[(size_t)(c0 + j) * n + c] - xref[c] : 0.0;
+            Cs[c * TN + j] = val; Cc[j * ND + c] = val;
+        }
+        for (int e = tid; e < TN * (ND - n); e += 256) { const int j = e / (ND - n), c = n + e % (ND - n); Cc[j * ND + c] = 0.0; }
+        for (int e = tid; e < KG * TN; e += 256) {
+            const int l = e / TN, j = e % TN;
+            Wt[e] = (l < kk && c0 + j < N) ? w[(size_t)(c0 + j) * k + l0 + l] : 0.0;
+        }
+        __syncthreads();
+        if (tid < TN) { double s = 0.0; for (int c = 0; c < n; ++c) { double a = Cs[c * TN + tid]; s = fma(a, a, s); } cc[tid] = s; }
+        // ---- phase 1: 4 x 4 dot products
+        double d[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[a][j] = 0.0;
+#pragma unroll 2
+        for (int c = 0; c < n; ++c) {
+            const double2 x01 = *reinterpret_cast<const double2*>(Xs + c * TM + 4 * ty);
+            const double2 x23 = *reinterpret_cast<const double2*>(Xs + c * TM + 4 * ty + 2);
+            const double2 c01 = *reinterpret_cast<const double2*>(Cs + c * TN + 4 * tx);
+            const double2 c23 = *reinterpret_cast<const double2*>(Cs + c * TN + 4 * tx + 2);
+            const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+            const double cv[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[a][j] = fma(xv[a], cv[j], d[a][j]);
+        }
+        __syncthreads();                                     // cc ready
+        double psi[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double r2 = fma(-2.0, d[a][j], xx[4 * ty + a] + cc[4 * tx + j]);
+                r2 = fmax(r2, 0.0);
+                double ph, ps;
+                if constexpr (WANT_J) rad_phi_psi(rf, r2, ph, ps); else { ph = rad_phi(rf, r2); ps = 0.0; }
+                d[a][j] = ph; psi[a][j] = ps;
+            }
+#pragma unroll
+        for (int l = 0; l < KG; ++l)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double wj = Wt[l * TN + 4 * tx + j];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) accY[a][l] = fma(d[a][j], wj, accY[a][l]);
+            }
+        if constexpr (WANT_J) {
+            for (int l = 0; l < kk; ++l) {
+                __syncthreads();                             // previous pass finished reading Gs
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) Gs[(4 * ty + a) * GLD + 4 * tx + j] = psi[a][j] * Wt[l * TN + 4 * tx + j];
+                __syncthreads();
+                // ---- phase 2: accJ[l] += G (64 x 64) * C' (64 x ND), micro-tile 4 points x CQ coordinates
+#pragma unroll 4
+                for (int j = 0; j < TN; ++j) {
+                    double g[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) g[a] = Gs[(4 * ty + a) * GLD + j];
+                    double cv[CQ];
+#pragma unroll
+                    for (int c = 0; c < CQ; ++c) cv[c] = Cc[j * ND + tx * CQ + c];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        if (l == 0) gsum[0][a] += g[a]; else gsum[KG - 1][a] += g[a];
+#pragma unroll
+                        for (int c = 0; c < CQ; ++c) {
+                            if (l == 0) accJ[0][a][c] = fma(g[a], cv[c], accJ[0][a][c]);
+                            else accJ[KG - 1][a][c] = fma(g[a], cv[c], accJ[KG - 1][a][c]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- epilogue
+    // values: reduce the 16 partial sums of a point row (lanes tx = 0..15 of a half warp)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int l = 0; l < KG; ++l) {
+            double s = accY[a][l];
+            s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
+            accY[a][l] = s;
+        }
+    if (P.Y && tx == 0) {
+        for (int a = 0; a < 4; ++a) {
+            const long long mi = m0 + 4 * ty + a;
+            if (mi >= P.M) continue;
+            for (int l = 0; l < kk; ++l) {
+                double s = accY[a][l];
+                if (P.deg >= 0) s += lam[l0 + l];
+                if (P.deg >= 1) {
+                    double t = 0.0;
+                    for (int c = 0; c < n; ++c) t = fma(lam[(size_t)(c + 1) * k + l0 + l], Xs[c * TM + 4 * ty + a] + xref[c], t);
+                    s += t;
+                }
+                P.Y[((size_t)b * P.M + mi) * k + l0 + l] = s;
+            }
+        }
+    }
+    if constexpr (WANT_J) if (P.J) {
+        for (int l = 0; l < kk; ++l)
+            for (int a = 0; a < 4; ++a) {
+                const long long mi = m0 + 4 * ty + a;
+                if (mi >= P.M) continue;
+                double* Jrow = P.J + (((size_t)b * P.M + mi) * k + l0 + l) * n;
+#pragma unroll
+                for (int c = 0; c < CQ; ++c) {
+                    const int r = tx * CQ + c;
+                    if (r < n) {
+                        const double gs = (l == 0) ? gsum[0][a] : gsum[KG - 1][a];
+                        const double aj = (l == 0) ? accJ[0][a][c] : accJ[KG - 1][a][c];
+                        double val = fma(Xs[r * TM + 4 * ty + a], gs, -aj);
+                        if (P.deg >= 1) val += lam[(size_t)(r + 1) * k + l0 + l];
+                        Jrow[r] = val;
+                    }
+                }
+            }
+    }
+}
+
+// Generic kernel: one thread per trial point, any n; outputs processed four at a time.
+__global__ void __launch_bounds__(128) eval_generic_kernel(EvalParams P) {
+    const int b = blockIdx.y, n = P.n, k = P.k;
+    const long long mi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mi >= P.M) return;
+    const int N = P.N[b];
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* w = P.w + (size_t)b * P.train_stride * k;
+    const int pl = P.p > 0 ? P.p : 1;
+    const double* lam = P.lam + (size_t)b * pl * k;
+    const double* x = P.X + ((size_t)b * P.M + mi) * n;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn; rf.alpha2 = P.alpha2[b];
+    double* Y = P.Y ? P.Y + ((size_t)b * P.M + mi) * k : nullptr;
+    double* J = P.J ? P.J + ((size_t)b * P.M + mi) * k * n : nullptr;
+    if (J) for (int e = 0; e < k * n; ++e) J[e] = 0.0;
+    for (int l0 = 0; l0 < k; l0 += 4) {
+        const int kk = min(4, k - l0);
+        double y[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < N; ++i) {
+            const double* c = centers + (size_t)i * n;
+            double r2 = 0.0;
+            for (int r = 0; r < n; ++r) { double dd = x[r] - c[r]; r2 = fma(dd, dd, r2); }
+            double ph, ps;
+            rad_phi_psi(rf, r2, ph, ps);
+            for (int l = 0; l < kk; ++l) {
+                const double wl = w[(size_t)i * k + l0 + l];
+                y[l] = fma(wl, ph, y[l]);
+                if (J) {
+                    const double g = wl * ps;
+                    double* Jl = J + (size_t)(l0 + l) * n;
+                    for (int r = 0; r < n; ++r) Jl[r] = fma(g, x[r] - c[r], Jl[r]);
+                }
+            }
+        }
+        for (int l = 0; l < kk; ++l) {
+            double s = y[l];
+            if (P.deg >= 0) s += lam[l0 + l];
+            if (P.deg >= 1) {
+                double t = 0.0;
+                for (int r = 0; r < n; ++r) t = fma(lam[(size_t)(r + 1) * k + l0 + l], x[r], t);
+                s += t;
+                if (J) { double* Jl = J + (size_t)(l0 + l) * n; for (int r = 0; r < n; ++r) Jl[r] += lam[(size_t)(r + 1) * k + l0 + l]; }
+            }
+            if (Y) Y[l0 + l] = s;
+        }
+    }
+}
+
+template <int CQ, bool WANT_J>
+static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launches) {
+    constexpr int ND = 16 * CQ, KG = WANT_J ? 2 : 4;
+    const size_t smem = sizeof(double) * ((size_t)ND * TM + (size_t)ND * TN + (size_t)TN * ND + (size_t)TM * GLD + TM + TN + KG * TN + ND);
+    cudaError_t e = cudaFuncSetAttribute(eval_tile_kernel<CQ, WANT_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long tiles = (P.M + TM - 1) / TM;
+    for (int l0 = 0; l0 < P.k; l0 += KG) {
+        const int kk = (P.k - l0) < KG ? (P.k - l0) : KG;
+        // gridDim.x limit is 2^31-1 tiles: fine for M <= 1.3e11
+        dim3 grid((unsigned)tiles, (unsigned)P.B);
+        eval_tile_kernel<CQ, WANT_J><<<grid, 256, smem, s>>>(P, l0, kk);
+        if (n_launches) ++*n_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
+    if (P.M <= 0 || P.B <= 0) return cudaSuccess;
+    const bool want_j = P.J != nullptr;
+    if (P.n <= 64 && P.B <= 65535) {
+        const int cq = (P.n + 15) / 16;
+        if (want_j) {
+            switch (cq) {
+            case 1: return launch_tile<1, true>(P, s, n_launches);
+            case 2: return launch_tile<2, true>(P, s, n_launches);
+            case 3: return launch_tile<3, true>(P, s, n_launches);
+            default: return launch_tile<4, true>(P, s, n_launches);
+            }
+        } else {
+            switch (cq) {
+            case 1: return launch_tile<1, false>(P, s, n_launches);
+            case 2: return launch_tile<2, false>(P, s, n_launches);
+            case 3: return launch_tile<3, false>(P, s, n_launches);
+            default: return launch_tile<4, false>(P, s, n_launches);
+            }
+        }
+    }
+    if (P.B > 65535) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((P.M + 127) / 128), (unsigned)P.B);
+    eval_generic_kernel<<<grid, 128, 0, s>>>(P);
+    if (n_launches) ++*n_launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Armijo backtracking (src/descent.jl:150-185): all step sizes as one batch of trial points.
+// ------------------------------------------------------------------------------------------------
+__global__ void backtrack_points_kernel(BacktrackParams P) {
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const double* x = P.x + (size_t)b * n; const double* dir = P.dir + (size_t)b * n;
+    double* Xb = P.Xall + (size_t)b * (P.nsteps + 1) * n;
+    double* sg = P.sig_all + (size_t)b * P.nsteps;
+    for (int i = tid; i < n; i += nt) Xb[i] = x[i];
+    for (int sidx = tid; sidx < P.nsteps; sidx += nt) {
+        double s = P.step0[b];
+        for (int i = 0; i < sidx; ++i) s *= P.shrink;        // repeated `*=` like the reference loop
+        sg[sidx] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < P.nsteps * n; e += nt) {
+        const int sidx = e / n, i = e % n;
+        Xb[(size_t)(sidx + 1) * n + i] = __dadd_rn(x[i], __dmul_rn(sg[sidx], dir[i]));   // x .+ step_size .* dir (no fma)
+    }
+}
+
+__global__ void backtrack_pick_kernel(BacktrackParams P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int n = P.n, k = P.k;
+    const double* Yb = P.Yall + (size_t)b * (P.nsteps + 1) * k;
+    const double* sg = P.sig_all + (size_t)b * P.nsteps;
+    const double om = P.omega[b];
+    int i = 0;
+    // reference loop: while i < MAX_LOOPS: if armijo -> break; if step <= MIN -> break; shrink; i += 1
+    for (;;) {
+        bool ok;
+        if (P.strict) {
+            ok = true;
+            for (int l = 0; l < k; ++l) ok = ok && ((Yb[l] - Yb[(size_t)(i + 1) * k + l]) >= sg[i] * P.armijo_c * om);
+        } else {
+            double m0 = Yb[0], m1 = Yb[(size_t)(i + 1) * k];
+            for (int l = 1; l < k; ++l) { m0 = fmax(m0, Yb[l]); m1 = fmax(m1, Yb[(size_t)(i + 1) * k + l]); }
+            ok = (m0 - m1) >= sg[i] * P.armijo_c * om;
+        }
+        if (i >= P.max_loops || ok || sg[i] <= P.min_stepsize) break;
+        ++i;
+    }
+    P.step_index[b] = i;
+    P.sigma[b] = sg[i];
+    const double* Xb = P.Xall + ((size_t)b * (P.nsteps + 1) + i + 1) * n;
+    for (int r = 0; r < n; ++r) P.x_plus[(size_t)b * n + r] = Xb[r];
+    for (int l = 0; l < k; ++l) { P.mx[(size_t)b * k + l] = Yb[l]; P.mx_plus[(size_t)b * k + l] = Yb[(size_t)(i + 1) * k + l]; }
+}
+
+cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s) {
+    backtrack_points_kernel<<<P.B, 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s) {
+    backtrack_pick_kernel<<<(P.B + 127) / 128, 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace mrbf

@@ -1,0 +1,90 @@
+// Parameter blocks and launcher prototypes shared by the kernel translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mrbf_common.cuh"
+
+namespace mrbf {
+
+struct CfgDev {
+    int polynomial_degree;
+    int optimized_sampling;
+    double theta_enlarge_1, theta_enlarge_2, theta_pivot;
+};
+
+struct SelectParams {
+    int B, n, db_stride, found_stride;
+    CfgDev cfg;
+    double delta_max;
+    const double* sites; const int* n_db; const int* x_index; const double* x; const double* delta;
+    const double* glb; const double* gub; const int* flags_in; const int* max_new;
+    int* r1; int* n_r1; int* r2; int* n_r2; double* r3_sites; int* n_r3; double* dirs; int* n_dirs; int* flags_out;
+    // workspace / hand-over to round 4
+    double* S; double* T; unsigned char* cflags; double* WZ; int wz_in_smem;
+    double* lb2; double* ub2; int* found; int* n_found;
+};
+
+struct Round4Params {
+    int B, n, db_stride, found_stride, extra_stride, r4_stride, NM, max_points;
+    CfgDev cfg;
+    RadFn rf;
+    double chol_thr;
+    const double* sites; const int* n_db; const double* lb2; const double* ub2;
+    const int* found; const int* n_found; const double* extra_sites; const int* n_extra;
+    int* r4; int* n_r4; int* status;
+    unsigned char* cand;          // B x db_stride candidate flags (workspace)
+    double* ws; size_t ws_stride; int ws_in_smem;
+};
+
+struct GatherParams {
+    int B, n, k, db_stride, r4_stride, train_stride;
+    const double* sites; const double* values; const int* x_index;
+    const int* r1; const int* n_r1; const int* r2; const int* n_r2;
+    const double* r3_sites; const double* r3_values; const int* n_r3; const int* r4; const int* n_r4;
+    double* train_sites; double* train_values; int* N;
+};
+
+struct BuildParams {
+    int B, n, k, train_stride, p, deg;
+    int kernel, ibeta; double sgn;        // RadFn pieces; alpha2 is per instance
+    double alpha_default;
+    const int* N; const double* sites; const double* values; const double* shape;
+    double* w; double* lam; double* alpha2_out; int* status;
+    double* ws; size_t ws_stride; int ws_in_smem; int ld;
+};
+
+struct EvalParams {
+    int B, n, k, train_stride, p, deg;
+    int kernel, ibeta; double sgn;
+    long long M;
+    const int* N; const double* centers; const double* w; const double* lam; const double* alpha2;
+    const double* X; double* Y; double* J;
+};
+
+struct BacktrackParams {
+    int B, n, k, nsteps, strict;
+    double armijo_c, shrink, min_stepsize; int max_loops;
+    const double* x; const double* dir; const double* step0; const double* omega;
+    const double* Yall;                    // B x (nsteps + 1) x k : m(x) then m(x + sigma_i dir)
+    double* Xall;                          // B x (nsteps + 1) x n
+    double* sig_all;                       // B x nsteps
+    int* step_index; double* sigma; double* x_plus; double* mx; double* mx_plus;
+};
+
+size_t select_smem_bytes(int n, bool wz_in_smem);
+size_t round4_vec_doubles(int n, int NM, int p);
+size_t round4_ws_doubles(int n, int NM, int p);
+size_t build_vec_doubles(int n, int k, int ld, int p);
+size_t build_ws_doubles(int n, int k, int ld, int p);
+
+cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s);
+cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s);
+cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s);
+cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
+cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);
+cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s);
+cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s);
+
+}  // namespace mrbf

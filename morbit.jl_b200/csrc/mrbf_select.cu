@@ -1,0 +1,629 @@
+// Training-set search kernels (rounds 1-4 of prepare_update_model), one CTA per instance.
+//
+// Reference behaviour restated (never copied): src/models/RbfModel.jl:205-307, 352-499, 518-655;
+// src/models/AffinelyIndependentPoints.jl:4-106; src/Databases.jl:324-327; src/utilities.jl:126-221, 437-448.
+//
+// B200 design notes
+//   * One CTA per instance; instances are independent, so the grid is the batch (C3: 4096 CTAs).
+//   * The greedy filter keeps the trailing block W of the Householder Q *explicitly* and updates it by
+//     one reflector per accepted point (O(n (n-j)) instead of the reference's full re-factorisation,
+//     O(n j^2)); same reflectors as LAPACK geqrf (beta = -sign(alpha) ||x||), so Z matches to rounding.
+//   * Round 4 never forms the dense Givens matrix G or the dense (N+1)^3 product of RbfModel.jl:462: only the
+//     last row of G is needed (closed form from the c_j, s_j), Q is kept as its first p columns, and the
+//     rotations are applied to column pairs.  Per candidate: O(N^2) coalesced mat-vecs instead of O(N^3).
+//   * State lives in shared memory when it fits (small n / few points), else in a per-instance global
+//     workspace that stays L2-resident; all mat-vecs are laid out so that consecutive threads read
+//     consecutive addresses.
+#include "mrbf_common.cuh"
+#include "mrbf_kernels.h"
+
+namespace mrbf {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool in_box(const double* s, const double* lb, const double* ub, int n) {
+    bool ok = true;
+    for (int i = 0; i < n; ++i) ok = ok && (lb[i] <= s[i]) && (s[i] <= ub[i]);
+    return ok;
+}
+
+// intersect_box(x, d, lb, ub; return_vals = :absmax), src/utilities.jl:126-221.
+__device__ double intersect_box_absmax(int n, const double* x, const double* d, const double* lb, const double* ub) {
+    bool any = false;
+    for (int i = 0; i < n; ++i) any = any || (d[i] != 0.0);
+    if (!any) return INFINITY;
+    double s_pos = 0.0, s_neg = 0.0;
+    bool have_pos = false, have_neg = false;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < n; ++i) {
+            if (d[i] == 0.0) continue;
+            double tmp = (pass == 0 ? lb[i] : ub[i]) - x[i];
+            double sig;
+            if (tmp != 0.0) sig = tmp / d[i];
+            else if (pass == 0) sig = d[i] > 0.0 ? INFINITY : 0.0;
+            else sig = d[i] < 0.0 ? INFINITY : 0.0;
+            if (sig >= 0.0) { if (!have_pos || sig < s_pos) s_pos = sig; have_pos = true; }
+            else { if (!have_neg || sig > s_neg) s_neg = sig; have_neg = true; }
+        }
+    if (!have_pos) s_pos = 0.0;
+    if (!have_neg) s_neg = 0.0;
+    return fabs(s_pos) >= fabs(s_neg) ? s_pos : s_neg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rounds 1-3
+// ------------------------------------------------------------------------------------------------
+struct FilterState {
+    int n, ldz;
+    double* W;        // n x (n - jY) trailing block of Q (unnormalised), column-major, ld = ldz
+    double* Z;        // same, columns scaled by their inf-norm
+    double* xp;       // n   scratch: W' y
+    double* u;        // n   scratch: W v
+    double* vv;       // n   scratch: reflector
+    double* red;      // 80 doubles reduction scratch
+    int* redi;        // 40 ints
+    int jY;           // columns of Y so far
+};
+
+// cflag bits
+#define CF_BOX1 1
+#define CF_BOX2 2
+#define CF_USED 4
+
+// One run of the affinely-independent filter over the candidates with (cflags & want) == want and
+// !(cflags & (CF_USED | avoid)).  Picks are appended to out[]; returns their number.
+__device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_db x n */, double* T, unsigned char* cflags,
+                          int n_db, unsigned want, unsigned avoid, double piv, int n_wanted, int* out) {
+    const int n = st.n, ldz = st.ldz, tid = threadIdx.x, nt = blockDim.x;
+    int found = 0;
+    // first pick: argmax ||s||_inf, first maximiser, unconditional (AffinelyIndependentPoints.jl:51-69)
+    ArgMax mine; mine.v = 0.0; mine.id = -1;
+    for (int id = tid; id < n_db; id += nt) {
+        unsigned f = cflags[id];
+        if ((f & want) != want || (f & (CF_USED | avoid))) continue;
+        const double* s = S + (size_t)id * n;
+        double v = 0.0;
+        for (int i = 0; i < n; ++i) v = fmax(v, fabs(s[i]));
+        ArgMax c; c.v = v; c.id = id;
+        mine = better(mine, c);
+    }
+    ArgMax best = block_argmax(mine, st.red, st.redi);
+    if (best.id < 0) return 0;
+    for (;;) {
+        // ---- accept best.id: Y <- [Y s], update W (one Householder reflector) and Z
+        const double* y = S + (size_t)best.id * n;
+        const int nw = n - st.jY;                 // columns of W before the update
+        for (int c = tid; c < nw; c += nt) {      // xp = W' y
+            double a = 0.0;
+            const double* wc = st.W + (size_t)c * ldz;
+            for (int i = 0; i < n; ++i) a = fma(wc[i], y[i], a);
+            st.xp[c] = a;
+        }
+        __syncthreads();
+        if (tid == 0) {                           // dlarfg on xp[0..nw)
+            double alpha = st.xp[0], xnorm = 0.0;
+            for (int c = 1; c < nw; ++c) xnorm = hypot(xnorm, st.xp[c]);
+            double tau = 0.0;
+            st.vv[0] = 1.0;
+            if (xnorm != 0.0) {
+                double beta = -copysign(hypot(alpha, xnorm), alpha);
+                tau = (beta - alpha) / beta;
+                double sc = 1.0 / (alpha - beta);
+                for (int c = 1; c < nw; ++c) st.vv[c] = st.xp[c] * sc;
+            } else {
+                for (int c = 1; c < nw; ++c) st.vv[c] = 0.0;
+            }
+            st.red[70] = tau;
+            cflags[best.id] |= CF_USED;
+            out[found] = best.id + 1;
+        }
+        __syncthreads();
+        const double tau = st.red[70];
+        for (int i = tid; i < n; i += nt) {       // u = W v ; then W'[:, c-1] = W[:, c] - tau v_c u  (row-private)
+            double a = 0.0;
+            for (int c = 0; c < nw; ++c) a = fma(st.W[i + (size_t)c * ldz], st.vv[c], a);
+            a *= tau;
+            for (int c = 1; c < nw; ++c) st.W[i + (size_t)(c - 1) * ldz] = fma(-a, st.vv[c], st.W[i + (size_t)c * ldz]);
+        }
+        st.jY += 1;
+        found += 1;
+        __syncthreads();
+        const int zc = n - st.jY;
+        for (int c = tid; c < zc; c += nt) {      // Z = W ./ colmax|W|  (AffinelyIndependentPoints.jl:8)
+            const double* wc = st.W + (size_t)c * ldz;
+            double mx = 0.0;
+            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(wc[i]));
+            double* zcol = st.Z + (size_t)c * ldz;
+            for (int i = 0; i < n; ++i) zcol[i] = wc[i] / mx;
+        }
+        __syncthreads();
+        if (found == n_wanted) break;
+        // ---- score the remaining candidates: || Z (Z' s) ||_inf, strict '>' => first maximiser
+        mine.v = 0.0; mine.id = -1;
+        for (int id = tid; id < n_db; id += nt) {
+            unsigned f = cflags[id];
+            if ((f & want) != want || (f & (CF_USED | avoid))) continue;
+            const double* s = S + (size_t)id * n;
+            double* t = T + (size_t)id * n;
+            double v = 0.0;
+            int c = 0;
+            for (; c + 4 <= zc; c += 4) {         // t = Z' s, four independent chains
+                const double* z0 = st.Z + (size_t)c * ldz; const double* z1 = z0 + ldz;
+                const double* z2 = z1 + ldz; const double* z3 = z2 + ldz;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int i = 0; i < n; ++i) {
+                    double si = s[i];
+                    a0 = fma(z0[i], si, a0); a1 = fma(z1[i], si, a1); a2 = fma(z2[i], si, a2); a3 = fma(z3[i], si, a3);
+                }
+                t[c] = a0; t[c + 1] = a1; t[c + 2] = a2; t[c + 3] = a3;
+            }
+            for (; c < zc; ++c) {
+                const double* z0 = st.Z + (size_t)c * ldz;
+                double a0 = 0;
+                for (int i = 0; i < n; ++i) a0 = fma(z0[i], s[i], a0);
+                t[c] = a0;
+            }
+            int i = 0;
+            for (; i + 4 <= n; i += 4) {          // r = Z t, inf-norm
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int q = 0; q < zc; ++q) {
+                    const double* zq = st.Z + (size_t)q * ldz + i; double tq = t[q];
+                    a0 = fma(zq[0], tq, a0); a1 = fma(zq[1], tq, a1); a2 = fma(zq[2], tq, a2); a3 = fma(zq[3], tq, a3);
+                }
+                v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
+            }
+            for (; i < n; ++i) {
+                double a0 = 0;
+                for (int q = 0; q < zc; ++q) a0 = fma(st.Z[i + (size_t)q * ldz], t[q], a0);
+                v = fmax(v, fabs(a0));
+            }
+            ArgMax cnd; cnd.v = v; cnd.id = id;
+            mine = better(mine, cnd);
+        }
+        best = block_argmax(mine, st.red, st.redi);
+        if (best.id < 0) break;                   // no more candidates
+        if (!(best.v > piv)) break;               // AffinelyIndependentPoints.jl:92
+    }
+    return found;
+}
+
+__global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int ldz = n | 1;
+    double* x = smem;
+    double* lb1 = x + n; double* ub1 = lb1 + n; double* lb2 = ub1 + n; double* ub2 = lb2 + n;
+    double* xp = ub2 + n; double* u = xp + n; double* vv = u + n;
+    double* red = vv + n;                        // 80
+    int* redi = (int*)(red + 80);                // 40 ints = 20 doubles
+    int* ctl = redi + 40;                        // 8 ints control
+    double* wz = red + 80 + 24;
+    double* W = P.wz_in_smem ? wz : P.WZ + (size_t)b * 2 * n * ldz;
+    double* Z = W + (size_t)n * ldz;
+    const int n_db = P.n_db[b];
+    const double* sites = P.sites + (size_t)b * P.db_stride * n;
+    double* S = P.S + (size_t)b * P.db_stride * n;
+    double* T = P.T + (size_t)b * P.db_stride * n;
+    unsigned char* cflags = P.cflags + (size_t)b * P.db_stride;
+    const int x_index = P.x_index[b] - 1;
+    const double delta = P.delta[b];
+    const double delta_1 = P.cfg.theta_enlarge_1 * delta;
+    const double piv = P.cfg.theta_pivot * delta_1;
+    const double delta_2 = P.cfg.theta_enlarge_2 * P.delta_max;
+    int* r1 = P.r1 + (size_t)b * n; int* r2 = P.r2 + (size_t)b * n;
+    double* r3s = P.r3_sites + (size_t)b * n * n;
+    double* dirs = P.dirs + (size_t)b * n * n;
+
+    for (int i = tid; i < n; i += nt) {
+        double xi = P.x[(size_t)b * n + i];
+        x[i] = xi;
+        lb1[i] = fmax(P.glb[i], xi - delta_1); ub1[i] = fmin(P.gub[i], xi + delta_1);   // utilities.jl:290-294
+        lb2[i] = fmax(P.glb[i], xi - delta_2); ub2[i] = fmin(P.gub[i], xi + delta_2);
+    }
+    __syncthreads();
+    // box scan (Databases.jl:324-327) + shifted seeds; also writes the box-2 bounds for round 4
+    for (int id = tid; id < n_db; id += nt) {
+        const double* s = sites + (size_t)id * n;
+        unsigned f = 0;
+        if (id != x_index) {
+            if (in_box(s, lb1, ub1, n)) f |= CF_BOX1;
+            if (in_box(s, lb2, ub2, n)) f |= CF_BOX2;
+        }
+        cflags[id] = (unsigned char)f;
+        double* sh = S + (size_t)id * n;
+        for (int i = 0; i < n; ++i) sh[i] = s[i] - x[i];
+    }
+    for (int i = tid; i < n; i += nt) { P.lb2[(size_t)b * n + i] = lb2[i]; P.ub2[(size_t)b * n + i] = ub2[i]; }
+
+    bool ensure_fl = P.flags_in[2 * b] != 0;
+    bool force_rebuild = P.flags_in[2 * b + 1] != 0;
+    bool rebuilt = false;
+    FilterState st; st.n = n; st.ldz = ldz; st.W = W; st.Z = Z; st.xp = xp; st.u = u; st.vv = vv; st.red = red; st.redi = redi;
+    int n_r1, n_r2, n_r3, n_dirs;
+    bool fully_linear;
+    for (;;) {   // at most two passes: the second is the coordinate rebuild (RbfModel.jl:634-637)
+        __syncthreads();
+        for (int e = tid; e < n * n; e += nt) { int i = e % n, c = e / n; W[i + (size_t)c * ldz] = (i == c) ? 1.0 : 0.0; Z[i + (size_t)c * ldz] = (i == c) ? 1.0 : 0.0; }
+        for (int id = tid; id < n_db; id += nt) cflags[id] &= (unsigned char)~CF_USED;
+        __syncthreads();
+        st.jY = 0; n_r1 = n_r2 = n_r3 = 0; fully_linear = false;
+        const bool skip_search = force_rebuild || !P.cfg.optimized_sampling;
+        if (skip_search) {                       // RbfModel.jl:564-569: directions e_1..e_n in natural order
+            for (int e = tid; e < n * n; e += nt) dirs[e] = ((e % n) == (e / n)) ? 1.0 : 0.0;
+            n_dirs = n;
+        } else {
+            n_r1 = filter_run(st, S, T, cflags, n_db, CF_BOX1, 0, piv, n, r1);
+            const int zc = n - st.jY;            // improving directions = reverse(eachcol(Z)), RbfModel.jl:232
+            for (int e = tid; e < n * zc; e += nt) { int i = e % n, c = e / n; dirs[i + (size_t)c * n] = Z[i + (size_t)(zc - 1 - c) * ldz]; }
+            n_dirs = zc;
+        }
+        int n_missing = n - n_r1;
+        const bool approx = fabs(delta - P.delta_max) <= 1.4901161193847656e-08 * fmax(fabs(delta), fabs(P.delta_max));
+        if (n_missing == 0 || skip_search || ensure_fl || (approx && P.cfg.theta_enlarge_1 == P.cfg.theta_enlarge_2)) {
+            fully_linear = true;                 // RbfModel.jl:588-591
+        } else {                                 // round 2: box 2, excluding every round-1 candidate
+            n_r2 = filter_run(st, S, T, cflags, n_db, CF_BOX2, CF_BOX1, piv, n_missing, r2);
+        }
+        n_missing -= n_r2;
+        bool failed = false;
+        if (n_missing > 0) {                     // round 3, RbfModel.jl:269-307
+            int n_new = min(n_missing, P.max_new[b]); if (n_new < 0) n_new = 0;
+            bool fl = n_new >= n_missing;
+            __syncthreads();
+            if (tid == 0) ctl[0] = 0;
+            __syncthreads();
+            for (int i = tid; i < n_new; i += nt) {
+                const double* d = dirs + (size_t)i * n;
+                double len = intersect_box_absmax(n, x, d, lb1, ub1);
+                double on = 0.0;
+                for (int r = 0; r < n; ++r) { double o = len * d[r]; r3s[(size_t)i * n + r] = x[r] + o; on = fmax(on, fabs(o)); }
+                if (on <= piv) atomicOr(&ctl[0], 1);
+            }
+            __syncthreads();
+            const bool any_small = ctl[0] != 0;
+            if (any_small) {
+                if (ensure_fl && !force_rebuild) failed = true;
+                else fl = false;
+            }
+            if (!failed) { n_r3 = n_new; fully_linear = fl && (n_r2 == 0); }
+        }
+        if (!failed) break;
+        force_rebuild = true; ensure_fl = true; rebuilt = true;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        P.n_r1[b] = n_r1; P.n_r2[b] = n_r2; P.n_r3[b] = n_r3; P.n_dirs[b] = n_dirs;
+        P.flags_out[2 * b] = fully_linear ? 1 : 0; P.flags_out[2 * b + 1] = rebuilt ? 1 : 0;
+        // found set for round 4: [centre; r1; r2] as ids, round-3 sites as extra sites
+        int* found = P.found + (size_t)b * P.found_stride;
+        int nf = 0;
+        found[nf++] = x_index + 1;
+        for (int i = 0; i < n_r1; ++i) found[nf++] = r1[i];
+        for (int i = 0; i < n_r2; ++i) found[nf++] = r2[i];
+        P.n_found[b] = nf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Round 4 (Wild's bounded-Cholesky augmentation), RbfModel.jl:352-499
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int NM = P.NM, MM = P.NM;
+    const int deg = P.cfg.polynomial_degree;
+    const int p = poly_dim(n, deg);
+    const int pl = p > 0 ? p : 1;
+    // shared vectors
+    double* xi = smem;                 // n
+    double* phix = xi + n;             // NM
+    double* q = phix + NM;             // NM
+    double* u = q + NM;                // NM
+    double* v = u + NM;                // NM
+    double* t = v + NM;                // NM
+    double* cs = t + NM;               // pl
+    double* sn = cs + pl;              // pl
+    double* gt = sn + pl;              // pl
+    double* rl = gt + pl;              // pl
+    double* red = rl + pl;             // 80
+    double* mats = red + 80;
+    double* ws = P.ws_in_smem ? mats : P.ws + (size_t)b * P.ws_stride;
+    double* Ct = ws;                               // NM x n   (Ct[k*NM + i] = centre i, coordinate k)
+    double* Phi = Ct + (size_t)NM * n;             // NM x NM
+    double* Q1 = Phi + (size_t)NM * NM;            // NM x pl
+    double* R = Q1 + (size_t)NM * pl;              // pl x pl
+    double* Zt = R + (size_t)pl * pl;              // MM x NM  (Zt[c + i*MM] = Z[i, c])
+    double* Li = Zt + (size_t)MM * NM;             // MM x MM  lower triangular inverse Cholesky factor
+
+    const int n_db = P.n_db[b];
+    const double* sites = P.sites + (size_t)b * P.db_stride * n;
+    const double* lb2 = P.lb2 + (size_t)b * n;
+    const double* ub2 = P.ub2 + (size_t)b * n;
+    const int* found = P.found + (size_t)b * P.found_stride;
+    const int nf_ids = P.n_found[b];
+    const int n_extra = P.n_extra ? P.n_extra[b] : 0;
+    const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
+    int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    int N = nf_ids + n_extra;
+    const int max_points = P.max_points;
+    int nr4 = 0, m = 0;
+    if (!(N < max_points) || N > NM) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = (N > NM) ? -1 : 0; } return; }
+    // candidates (results_in_box_indices(db, lb_2, ub_2, indices_found_so_far), RbfModel.jl:360), ascending ids
+    unsigned char* cand = P.cand + (size_t)b * P.db_stride;
+    for (int id = tid; id < n_db; id += nt) {
+        bool ok = in_box(sites + (size_t)id * n, lb2, ub2, n);
+        for (int f = 0; f < nf_ids && ok; ++f) ok = (found[f] != id + 1);
+        cand[id] = ok ? 1 : 0;
+    }
+
+    // ---- centres, Phi, Pi -> Householder QR -> Q1 (first p columns of the full Q), R
+    for (int e = tid; e < N * n; e += nt) {
+        int i = e / n, k = e % n;
+        double val = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
+        Ct[(size_t)k * NM + i] = val;
+    }
+    __syncthreads();
+    for (int e = tid; e < N * N; e += nt) {
+        int i = e % N, j = e / N;
+        double r2 = 0.0;
+        for (int k = 0; k < n; ++k) { double d = Ct[(size_t)k * NM + i] - Ct[(size_t)k * NM + j]; r2 = fma(d, d, r2); }
+        Phi[i + (size_t)j * NM] = rad_phi(P.rf, r2);
+    }
+    // Pi into Q1's storage (N x p), factor in place, keep reflectors in Q1 below the diagonal temporarily
+    for (int e = tid; e < N * p; e += nt) {
+        int i = e % N, c = e / N;
+        Q1[i + (size_t)c * NM] = (c == 0) ? 1.0 : Ct[(size_t)(c - 1) * NM + i];
+    }
+    for (int e = tid; e < pl * pl; e += nt) R[e] = 0.0;
+    __syncthreads();
+    const int kq = N < p ? N : p;                  // number of reflectors
+    // dgeqr2 on Q1 (N x p); taus kept in `t` (shared)
+    for (int j = 0; j < kq; ++j) {
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < N; i += nt) { double a = Q1[i + (size_t)j * NM]; part = fma(a, a, part); }
+        double xn2 = block_sum(part, red);
+        if (tid == 0) {
+            double alpha = Q1[j + (size_t)j * NM], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
+            if (xnorm != 0.0 && j + 1 < N) {
+                beta = -copysign(hypot(alpha, xnorm), alpha);
+                tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta);
+            }
+            t[j] = tau; red[70] = sc; red[71] = beta;
+        }
+        __syncthreads();
+        const double tau = t[j], sc = red[70];
+        for (int i = j + 1 + tid; i < N; i += nt) Q1[i + (size_t)j * NM] *= sc;
+        if (tid == 0) Q1[j + (size_t)j * NM] = red[71];
+        __syncthreads();
+        if (tau != 0.0)
+            for (int c = j + 1 + warp; c < p; c += nwarps) {      // warp per trailing column
+                double* col = Q1 + (size_t)c * NM; const double* vj = Q1 + (size_t)j * NM;
+                double a = 0.0;
+                for (int i = j + 1 + lane; i < N; i += 32) a = fma(vj[i], col[i], a);
+                a = warp_sum(a) + col[j];
+                a *= tau;
+                for (int i = j + 1 + lane; i < N; i += 32) col[i] = fma(-a, vj[i], col[i]);
+                __syncwarp();
+                if (lane == 0) col[j] -= a;
+            }
+        __syncthreads();
+    }
+    // R (upper trapezoidal, kq x p) out of Q1's upper part
+    for (int e = tid; e < kq * p; e += nt) { int r = e % kq, c = e / kq; if (r <= c) R[r + (size_t)c * pl] = Q1[r + (size_t)c * NM]; }
+    __syncthreads();
+    // explicit first min(N,p) columns of Q: apply H_0..H_{kq-1} (in reverse) to e_c; reflector j lives in column j.
+    // Done column by column into `Zt` scratch (N x kq), then copied over Q1.
+    {
+        double* Qx = Zt;                           // scratch, ld = NM (Zt is MM*NM >= NM*pl doubles)
+        for (int c = warp; c < kq; c += nwarps) {
+            double* col = Qx + (size_t)c * NM;
+            for (int i = lane; i < N; i += 32) col[i] = (i == c) ? 1.0 : 0.0;
+            __syncwarp();
+            for (int j = kq - 1; j >= 0; --j) {
+                const double tau = t[j];
+                if (tau == 0.0) continue;
+                const double* vj = Q1 + (size_t)j * NM;
+                double a = 0.0;
+                for (int i = j + 1 + lane; i < N; i += 32) a = fma(vj[i], col[i], a);
+                a = warp_sum(a) + col[j];
+                a *= tau;
+                for (int i = j + 1 + lane; i < N; i += 32) col[i] = fma(-a, vj[i], col[i]);
+                __syncwarp();
+                if (lane == 0) col[j] -= a;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < N * kq; e += nt) { int i = e % N, c = e / N; Q1[i + (size_t)c * NM] = Qx[i + (size_t)c * NM]; }
+        // when N < p the remaining columns of Q (kq..N-1) do not exist (Q is N x N = N x kq)
+        __syncthreads();
+    }
+    const double phi0 = Phi[0];
+    const int full_rank_dim = deg < 0 ? 0 : p;
+    const double thr = P.chol_thr;                 // (theta_pivot_cholesky^2)^2, RbfModel.jl:370, 452
+
+    for (int id = 0; id < n_db && N < max_points && nr4 < P.r4_stride; ++id) {
+        if (!cand[id]) continue;                   // block-uniform: in box 2 and not in the found set
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) xi[k] = sites[(size_t)id * n + k];
+        __syncthreads();
+        const int J = N < p ? N : p;
+        if (warp == 0) {
+            // Givens sequence on [R; pi_xi'] (utilities.jl:437-448), R untouched until acceptance
+            for (int c = lane; c < p; c += 32) rl[c] = (c == 0) ? 1.0 : xi[c - 1];
+            __syncwarp();
+            for (int j = 0; j < J; ++j) {
+                double c_, s_;
+                givens(R[j + (size_t)j * pl], rl[j], c_, s_);
+                __syncwarp();
+                for (int c = j + lane; c < p; c += 32) rl[c] = -s_ * R[j + (size_t)c * pl] + c_ * rl[c];
+                if (lane == 0) { cs[j] = c_; sn[j] = s_; }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                double gh = 1.0;                   // last row of G: g_j = -s_j prod_{i>j} c_i, g_hat = prod c_i
+                for (int j = J - 1; j >= 0; --j) { gt[j] = -sn[j] * gh; gh *= cs[j]; }
+                red[72] = gh;
+                double nr = 0.0;
+                for (int c = 0; c < p; ++c) nr = hypot(nr, rl[c]);
+                red[73] = nr;
+            }
+        } else {
+            for (int i = tid - 32; i < N; i += nt - 32) {          // kernels(xi), RbfModel.jl:421
+                double r2 = 0.0;
+                for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[(size_t)k * NM + i]; r2 = fma(d, d, r2); }
+                phix[i] = rad_phi(P.rf, r2);
+            }
+        }
+        __syncthreads();
+        if (N < full_rank_dim && red[73] <= 2.220446049250313e-16 * 10) continue;   // RbfModel.jl:433-438
+        const double gh = red[72];
+        for (int i = tid; i < N; i += nt) {        // q = Q g~
+            double a = 0.0;
+            for (int j = 0; j < J; ++j) a = fma(Q1[i + (size_t)j * NM], gt[j], a);
+            q[i] = a;
+        }
+        __syncthreads();
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = tid; i < N; i += nt) {        // u = Phi q  (Phi symmetric, column-major => coalesced over i)
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int j = 0;
+            for (; j + 4 <= N; j += 4) {
+                a0 = fma(Phi[i + (size_t)j * NM], q[j], a0); a1 = fma(Phi[i + (size_t)(j + 1) * NM], q[j + 1], a1);
+                a2 = fma(Phi[i + (size_t)(j + 2) * NM], q[j + 2], a2); a3 = fma(Phi[i + (size_t)(j + 3) * NM], q[j + 3], a3);
+            }
+            for (; j < N; ++j) a0 = fma(Phi[i + (size_t)j * NM], q[j], a0);
+            double a = (a0 + a1) + (a2 + a3);
+            s1 = fma(q[i], a, s1); s2 = fma(phix[i], q[i], s2);
+            u[i] = fma(gh, phix[i], a);
+        }
+        block_sum2(s1, s2, red);                   // includes the barriers that publish u
+        const double sigma = s1 + (2.0 * gh) * s2 + gh * gh * phi0;      // RbfModel.jl:447
+        for (int c = tid; c < m; c += nt) {        // v = Z' u
+            double a0 = 0.0, a1 = 0.0;
+            int i = 0;
+            for (; i + 2 <= N; i += 2) { a0 = fma(Zt[c + (size_t)i * MM], u[i], a0); a1 = fma(Zt[c + (size_t)(i + 1) * MM], u[i + 1], a1); }
+            for (; i < N; ++i) a0 = fma(Zt[c + (size_t)i * MM], u[i], a0);
+            v[c] = a0 + a1;
+        }
+        __syncthreads();
+        double tn = 0.0;
+        for (int r = tid; r < m; r += nt) {        // t = L^{-1} v
+            double a0 = 0.0, a1 = 0.0;
+            int c = 0;
+            for (; c + 2 <= r + 1; c += 2) { a0 = fma(Li[r + (size_t)c * MM], v[c], a0); a1 = fma(Li[r + (size_t)(c + 1) * MM], v[c + 1], a1); }
+            for (; c <= r; ++c) a0 = fma(Li[r + (size_t)c * MM], v[c], a0);
+            double a = a0 + a1;
+            t[r] = a; tn = fma(a, a, tn);
+        }
+        tn = block_sum(tn, red);
+        const double nrm = sqrt(tn);
+        const double tau2 = sigma - nrm * nrm;     // RbfModel.jl:449
+        if (!(tau2 > thr)) continue;               // RbfModel.jl:452
+        // ---- accept
+        const double tv = sqrt(tau2);
+        for (int i = tid; i <= N; i += nt) {       // Q <- blkdiag(Q,1) G': rotate column pairs (j, N)
+            double bcol = (i == N) ? 1.0 : 0.0;
+            for (int j = 0; j < J; ++j) {
+                double a = (i == N) ? 0.0 : Q1[i + (size_t)j * NM];
+                Q1[i + (size_t)j * NM] = cs[j] * a + sn[j] * bcol;
+                bcol = -sn[j] * a + cs[j] * bcol;
+            }
+            if (N < p) Q1[i + (size_t)N * NM] = bcol;             // the new column becomes a pivot column next time
+            else if (i == N) for (int j = J; j < p; ++j) Q1[i + (size_t)j * NM] = 0.0;
+            // Z <- [Z q; 0 g_hat]
+            Zt[m + (size_t)i * MM] = (i == N) ? gh : q[i];
+        }
+        for (int c = tid; c < m; c += nt) Zt[c + (size_t)N * MM] = 0.0;
+        if (N < p) for (int j = J + tid; j < p; j += nt) if (j != N) Q1[N + (size_t)j * NM] = 0.0;
+        // L^{-1} <- [L^{-1} 0; -(t' L^{-1})/tau 1/tau]   (warp per column, coalesced down the column)
+        for (int c = warp; c < m; c += nwarps) {
+            double a = 0.0;
+            for (int r = c + lane; r < m; r += 32) a = fma(t[r], Li[r + (size_t)c * MM], a);
+            a = warp_sum(a);
+            if (lane == 0) v[c] = -a / tv;         // v is free now: holds the new row
+        }
+        if (warp == 0) {                           // R <- rotated [R; pi'] (only rows < p are non-zero)
+            for (int c = lane; c < p; c += 32) rl[c] = (c == 0) ? 1.0 : xi[c - 1];
+            __syncwarp();
+            for (int j = 0; j < J; ++j) {
+                for (int c = lane; c < p; c += 32) {
+                    double a = R[j + (size_t)c * pl], bb = rl[c];
+                    R[j + (size_t)c * pl] = cs[j] * a + sn[j] * bb;
+                    rl[c] = -sn[j] * a + cs[j] * bb;
+                }
+                __syncwarp();
+            }
+            if (N < p) for (int c = lane; c < p; c += 32) R[N + (size_t)c * pl] = rl[c];
+        }
+        for (int i = tid; i < N; i += nt) { Phi[i + (size_t)N * NM] = phix[i]; Phi[N + (size_t)i * NM] = phix[i]; }
+        for (int k = tid; k < n; k += nt) Ct[(size_t)k * NM + N] = xi[k];
+        if (tid == 0) { Phi[N + (size_t)N * NM] = phi0; r4[nr4] = id + 1; }
+        __syncthreads();
+        for (int c = tid; c < m; c += nt) { Li[m + (size_t)c * MM] = v[c]; Li[c + (size_t)m * MM] = 0.0; }
+        if (tid == 0) Li[m + (size_t)m * MM] = 1.0 / tv;
+        N += 1; m += 1; nr4 += 1;
+        __syncthreads();
+    }
+    if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training-set gather (_collect_indices order: centre, r1, r2, r3, r4), RbfModel.jl:178-186, 754-757
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_training_kernel(GatherParams P) {
+    const int b = blockIdx.x, n = P.n, k = P.k, tid = threadIdx.x, nt = blockDim.x;
+    const int n1 = P.n_r1[b], n2 = P.n_r2[b], n3 = P.n_r3[b], n4 = P.n_r4[b];
+    const int N = 1 + n1 + n2 + n3 + n4;
+    const double* sites = P.sites + (size_t)b * P.db_stride * n;
+    const double* values = P.values + (size_t)b * P.db_stride * k;
+    double* ts = P.train_sites + (size_t)b * P.train_stride * n;
+    double* tv = P.train_values + (size_t)b * P.train_stride * k;
+    if (tid == 0) P.N[b] = N <= P.train_stride ? N : -N;
+    if (N > P.train_stride) return;
+    for (int e = tid; e < N * (n + k); e += nt) {
+        int i = e / (n + k), c = e % (n + k);
+        int id = -1, j3 = -1;
+        if (i == 0) id = P.x_index[b];
+        else if (i < 1 + n1) id = P.r1[(size_t)b * n + i - 1];
+        else if (i < 1 + n1 + n2) id = P.r2[(size_t)b * n + i - 1 - n1];
+        else if (i < 1 + n1 + n2 + n3) j3 = i - 1 - n1 - n2;
+        else id = P.r4[(size_t)b * P.r4_stride + i - 1 - n1 - n2 - n3];
+        if (c < n) ts[(size_t)i * n + c] = (j3 >= 0) ? P.r3_sites[((size_t)b * n + j3) * n + c] : sites[(size_t)(id - 1) * n + c];
+        else tv[(size_t)i * k + c - n] = (j3 >= 0) ? P.r3_values[((size_t)b * n + j3) * k + c - n] : values[(size_t)(id - 1) * k + c - n];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+size_t select_smem_bytes(int n, bool wz_in_smem) {
+    size_t d = 8 * (size_t)n + 80 + 24;
+    if (wz_in_smem) d += 2 * (size_t)n * (n | 1);
+    return d * sizeof(double);
+}
+size_t round4_vec_doubles(int n, int NM, int p) { int pl = p > 0 ? p : 1; return (size_t)n + 5 * (size_t)NM + 4 * (size_t)pl + 80; }
+size_t round4_ws_doubles(int n, int NM, int p) {
+    int pl = p > 0 ? p : 1;
+    return (size_t)NM * n + (size_t)NM * NM + (size_t)NM * pl + (size_t)pl * pl + 2 * (size_t)NM * NM;
+}
+
+cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(select_rounds123_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    select_rounds123_kernel<<<P.B, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(round4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    round4_kernel<<<P.B, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s) {
+    gather_training_kernel<<<P.B, 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace mrbf

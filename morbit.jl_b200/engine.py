@@ -1,0 +1,255 @@
+"""Thin object layer over the C ABI: one `Engine` per (thread, device), batched calls.
+
+Host entry points take NumPy arrays (what Julia's `ccall` would pass); `*_dev` entry points take
+torch CUDA tensors (device-resident data, no copies) and enqueue on the engine's stream.
+torch is plumbing only (device memory + streams); all arithmetic happens in libmorbit_rbf.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import MrbfCfg, MrbfError, KERNEL_IDS
+
+
+def max_model_points(cfg, n: int) -> int:
+    """RbfModel.jl:356."""
+    return ((n + 1) * (n + 2)) // 2 if cfg.max_model_points <= 0 else cfg.max_model_points
+
+
+def to_c_cfg(cfg, shape: Optional[float] = None) -> MrbfCfg:
+    sp = cfg.shape_parameter if shape is None else shape
+    if isinstance(sp, str):
+        raise TypeError("string shape parameters must be evaluated by the caller (RbfModel.jl:135-143)")
+    return MrbfCfg(KERNEL_IDS[cfg.kernel], int(cfg.polynomial_degree), float(sp), float(cfg.theta_enlarge_1),
+                   float(cfg.theta_enlarge_2), float(cfg.theta_pivot), float(cfg.theta_pivot_cholesky),
+                   int(cfg.max_model_points), int(bool(cfg.use_max_points)), int(bool(cfg.optimized_sampling)), 0)
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()          # torch tensor
+
+
+@dataclass
+class SelectResult:
+    """Outputs of prepare_update_model's rounds 1-4 for a batch (ids are 1-based)."""
+    r1: object; n_r1: object
+    r2: object; n_r2: object
+    r3_sites: object; n_r3: object
+    r4: object; n_r4: object
+    dirs: object; n_dirs: object
+    flags_out: object
+    status: object
+
+
+class ModelBatch:
+    """Device-resident batch of fitted RBF models (opaque mrbf_model handle)."""
+
+    def __init__(self, engine: "Engine", handle: int):
+        self.engine = engine
+        self.handle = handle
+        dims = (C.c_int32 * 6)()
+        engine._check(engine.lib.mrbf_model_dims(handle, dims))
+        self.B, self.n, self.k, self.train_stride, self.p, self.degree = (int(v) for v in dims)
+
+    def coeffs(self):
+        w = np.zeros((self.B, self.train_stride, self.k))
+        lam = np.zeros((self.B, self.p, self.k))
+        self.engine._check(self.engine.lib.mrbf_model_coeffs(self.engine.ctx, self.handle, _ptr(w), _ptr(lam) if self.p else None))
+        return w, lam
+
+    def free(self):
+        if self.handle:
+            self.engine.lib.mrbf_free_model(self.engine.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.handle and self.engine.ctx:
+                self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = _lib.load()
+        ctx = C.c_void_p()
+        rc = self.lib.mrbf_init(int(device), C.byref(ctx))
+        if rc != 0:
+            raise MrbfError(rc, f"mrbf_init(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
+        self.ctx = ctx
+        self.device = device
+        if stream is not None:
+            self._check(self.lib.mrbf_set_stream(self.ctx, C.c_void_p(stream)))
+
+    def close(self):
+        if self.ctx:
+            self.lib.mrbf_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MrbfError(rc, self.lib.mrbf_last_error(self.ctx).decode(errors="replace"))
+
+    def sync(self):
+        self._check(self.lib.mrbf_sync(self.ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mrbf_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ rounds 1-4 (host buffers)
+    def select_points(self, cfg, sites, n_db, x_index, x, delta, delta_max, glb, gub, ensure_fully_linear=False,
+                      force_rebuild=False, max_new=2**31 - 1) -> SelectResult:
+        sites = _np(sites, np.float64)
+        B, db_stride, n = sites.shape
+        n_db = _np(np.broadcast_to(n_db, (B,)), np.int32); x_index = _np(np.broadcast_to(x_index, (B,)), np.int32)
+        x = _np(x, np.float64).reshape(B, n); delta = _np(np.broadcast_to(delta, (B,)), np.float64)
+        glb = _np(np.broadcast_to(glb, (n,)), np.float64); gub = _np(np.broadcast_to(gub, (n,)), np.float64)
+        flags_in = _np(np.stack([np.broadcast_to(ensure_fully_linear, (B,)), np.broadcast_to(force_rebuild, (B,))], 1), np.int32)
+        max_new = _np(np.clip(np.broadcast_to(max_new, (B,)), 0, 2**31 - 1), np.int32)
+        mp = max_model_points(cfg, n)
+        r1 = np.zeros((B, n), np.int32); r2 = np.zeros((B, n), np.int32); r4 = np.zeros((B, mp), np.int32)
+        cnt = [np.zeros(B, np.int32) for _ in range(5)]
+        r3 = np.zeros((B, n, n)); dirs = np.zeros((B, n, n))
+        flags_out = np.zeros((B, 2), np.int32); status = np.zeros(B, np.int32)
+        ccfg = to_c_cfg(cfg)
+        self._check(self.lib.mrbf_select_points(
+            self.ctx, C.byref(ccfg), B, n, db_stride, _ptr(sites), _ptr(n_db), _ptr(x_index), _ptr(x), _ptr(delta),
+            float(delta_max), _ptr(glb), _ptr(gub), _ptr(flags_in), _ptr(max_new), _ptr(r1), _ptr(cnt[0]), _ptr(r2),
+            _ptr(cnt[1]), _ptr(r3), _ptr(cnt[2]), mp, _ptr(r4), _ptr(cnt[3]), _ptr(dirs), _ptr(cnt[4]), _ptr(flags_out),
+            _ptr(status)))
+        return SelectResult(r1, cnt[0], r2, cnt[1], r3, cnt[2], r4, cnt[3], dirs, cnt[4], flags_out, status)
+
+    def round4(self, cfg, sites, n_db, lb2, ub2, found, n_found, extra_sites=None, n_extra=None):
+        sites = _np(sites, np.float64)
+        B, db_stride, n = sites.shape
+        n_db = _np(np.broadcast_to(n_db, (B,)), np.int32)
+        lb2 = _np(np.broadcast_to(lb2, (B, n)), np.float64); ub2 = _np(np.broadcast_to(ub2, (B, n)), np.float64)
+        found = _np(found, np.int32).reshape(B, -1); n_found = _np(np.broadcast_to(n_found, (B,)), np.int32)
+        es = 0
+        if extra_sites is not None:
+            extra_sites = _np(extra_sites, np.float64).reshape(B, -1, n); es = extra_sites.shape[1]
+            n_extra = _np(np.broadcast_to(n_extra, (B,)), np.int32)
+        mp = max_model_points(cfg, n)
+        r4 = np.zeros((B, max(mp, 1)), np.int32); n_r4 = np.zeros(B, np.int32); status = np.zeros(B, np.int32)
+        ccfg = to_c_cfg(cfg)
+        self._check(self.lib.mrbf_round4(self.ctx, C.byref(ccfg), B, n, db_stride, _ptr(sites), _ptr(n_db), _ptr(lb2), _ptr(ub2),
+                                         found.shape[1], _ptr(found), _ptr(n_found), es,
+                                         _ptr(extra_sites) if es else None, _ptr(n_extra) if es else None,
+                                         r4.shape[1], _ptr(r4), _ptr(n_r4), _ptr(status)))
+        return r4, n_r4, status
+
+    # ------------------------------------------------------------------ rounds 1-4 (device tensors)
+    def select_points_dev(self, cfg, sites, n_db, x_index, x, delta, delta_max, glb, gub, flags_in, max_new, out=None):
+        """All arguments are torch CUDA tensors (float64 / int32); returns a SelectResult of CUDA tensors."""
+        import torch
+        B, db_stride, n = sites.shape
+        mp = max_model_points(cfg, n)
+        dev = sites.device
+        if out is None:
+            i32 = dict(dtype=torch.int32, device=dev); f64 = dict(dtype=torch.float64, device=dev)
+            out = SelectResult(torch.zeros((B, n), **i32), torch.zeros(B, **i32), torch.zeros((B, n), **i32), torch.zeros(B, **i32),
+                               torch.zeros((B, n, n), **f64), torch.zeros(B, **i32), torch.zeros((B, mp), **i32),
+                               torch.zeros(B, **i32), torch.zeros((B, n, n), **f64), torch.zeros(B, **i32),
+                               torch.zeros((B, 2), **i32), torch.zeros(B, **i32))
+        ccfg = to_c_cfg(cfg)
+        self._check(self.lib.mrbf_select_points_dev(
+            self.ctx, C.byref(ccfg), B, n, db_stride, _ptr(sites), _ptr(n_db), _ptr(x_index), _ptr(x), _ptr(delta),
+            float(delta_max), _ptr(glb), _ptr(gub), _ptr(flags_in), _ptr(max_new), _ptr(out.r1), _ptr(out.n_r1), _ptr(out.r2),
+            _ptr(out.n_r2), _ptr(out.r3_sites), _ptr(out.n_r3), out.r4.shape[1], _ptr(out.r4), _ptr(out.n_r4), _ptr(out.dirs),
+            _ptr(out.n_dirs), _ptr(out.flags_out), _ptr(out.status)))
+        return out
+
+    def gather_training_dev(self, sites, values, x_index, sel: SelectResult, r3_values, train_stride, out=None):
+        import torch
+        B, db_stride, n = sites.shape
+        k = values.shape[2]
+        dev = sites.device
+        if out is None:
+            out = (torch.zeros((B, train_stride, n), dtype=torch.float64, device=dev),
+                   torch.zeros((B, train_stride, k), dtype=torch.float64, device=dev),
+                   torch.zeros(B, dtype=torch.int32, device=dev))
+        self._check(self.lib.mrbf_gather_training_dev(
+            self.ctx, B, n, k, db_stride, _ptr(sites), _ptr(values), _ptr(x_index), _ptr(sel.r1), _ptr(sel.n_r1), _ptr(sel.r2),
+            _ptr(sel.n_r2), _ptr(sel.r3_sites), _ptr(r3_values), _ptr(sel.n_r3), sel.r4.shape[1], _ptr(sel.r4), _ptr(sel.n_r4),
+            train_stride, _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
+
+    # ------------------------------------------------------------------ build
+    def build(self, cfg, sites, values, N, shape=None, raise_on_failure: bool = True):
+        sites = _np(sites, np.float64); values = _np(values, np.float64)
+        B, ts, n = sites.shape
+        k = values.shape[2]
+        N = _np(np.broadcast_to(N, (B,)), np.int32)
+        shape_a = None if shape is None else _np(np.broadcast_to(shape, (B,)), np.float64)
+        status = np.zeros(B, np.int32)
+        handle = C.c_void_p()
+        ccfg = to_c_cfg(cfg)
+        rc = self.lib.mrbf_build(self.ctx, C.byref(ccfg), B, n, k, ts, _ptr(N), _ptr(sites), _ptr(values), _ptr(shape_a),
+                                 C.byref(handle), _ptr(status))
+        if rc != 0 and not (rc == _lib.MRBF_ENUMERIC and not raise_on_failure):
+            if handle.value:
+                self.lib.mrbf_free_model(self.ctx, handle)
+            self._check(rc)
+        return ModelBatch(self, handle.value), status
+
+    def build_dev(self, cfg, sites, values, N, shape=None, status=None):
+        import torch
+        B, ts, n = sites.shape
+        k = values.shape[2]
+        if status is None:
+            status = torch.zeros(B, dtype=torch.int32, device=sites.device)
+        handle = C.c_void_p()
+        ccfg = to_c_cfg(cfg)
+        self._check(self.lib.mrbf_build_dev(self.ctx, C.byref(ccfg), B, n, k, ts, _ptr(N), _ptr(sites), _ptr(values), _ptr(shape),
+                                            C.byref(handle), _ptr(status)))
+        return ModelBatch(self, handle.value), status
+
+    # ------------------------------------------------------------------ evaluation
+    def eval(self, model: ModelBatch, X, want_values=True, want_jacobian=False):
+        X = _np(X, np.float64).reshape(model.B, -1, model.n)
+        M = X.shape[1]
+        Y = np.zeros((model.B, M, model.k)) if want_values else None
+        J = np.zeros((model.B, M, model.k, model.n)) if want_jacobian else None
+        self._check(self.lib.mrbf_eval(self.ctx, model.handle, M, _ptr(X), _ptr(Y), _ptr(J)))
+        return Y, J
+
+    def eval_dev(self, model: ModelBatch, X, Y=None, J=None):
+        M = X.shape[1]
+        self._check(self.lib.mrbf_eval_dev(self.ctx, model.handle, M, _ptr(X), _ptr(Y), _ptr(J)))
+        return Y, J
+
+    def backtrack(self, model: ModelBatch, x, direction, step0, omega, armijo_c=1e-6, shrink=0.75,
+                  min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict=True):
+        """descent.jl:150-185 with every step size evaluated in one launch."""
+        if max_loops is None:
+            max_loops = int(math.floor(math.log(min_stepsize) / math.log(shrink)))      # descent.jl:62-66
+        B, n, k = model.B, model.n, model.k
+        x = _np(x, np.float64).reshape(B, n); direction = _np(direction, np.float64).reshape(B, n)
+        step0 = _np(np.broadcast_to(step0, (B,)), np.float64); omega = _np(np.broadcast_to(omega, (B,)), np.float64)
+        idx = np.zeros(B, np.int32); sigma = np.zeros(B); xp = np.zeros((B, n)); mx = np.zeros((B, k)); mxp = np.zeros((B, k))
+        self._check(self.lib.mrbf_backtrack(self.ctx, model.handle, _ptr(x), _ptr(direction), _ptr(step0), _ptr(omega),
+                                            float(armijo_c), float(shrink), float(min_stepsize), int(max_loops), int(bool(strict)),
+                                            _ptr(idx), _ptr(sigma), _ptr(xp), _ptr(mx), _ptr(mxp)))
+        return xp, mxp, sigma[:, None] * direction, idx, mx

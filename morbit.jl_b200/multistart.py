@@ -1,0 +1,118 @@
+"""Lock-step batch of independent multistart instances (BASELINE config C3) and its sharding over GPUs.
+
+The reference runs many `optimize` calls concurrently under Threads.@threads
+(examples/large_scale_benchmarks.jl:253); instances share nothing, so they shard over ranks with no
+collective on the data path.  Only the per-instance results are gathered at the end (torch.distributed:
+NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .engine import Engine, ModelBatch, SelectResult, max_model_points
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block partition [lo, hi) of `total` independent instances; sizes differ by at most 1."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def train_stride_for(cfg, n: int, db_stride: int) -> int:
+    """Upper bound of the training-set size: min(max_points, n + 1 + #database sites)."""
+    return max(n + 1, min(max_model_points(cfg, n), n + db_stride))
+
+
+@dataclass
+class DeviceBatch:
+    """Device-resident state of B instances (torch CUDA tensors)."""
+    sites: object       # B x db_stride x n   float64
+    values: object      # B x db_stride x k   float64
+    n_db: object        # B  int32
+    x_index: object     # B  int32
+    x: object           # B x n
+    delta: object       # B
+    glb: object         # n
+    gub: object         # n
+    flags_in: object    # B x 2 int32
+    max_new: object     # B int32
+
+
+def upload_batch(host: dict, device: str = "cuda:0", pin: bool = False) -> DeviceBatch:
+    """host: dict of NumPy arrays with DeviceBatch's field names."""
+    import torch
+    def up(a, dt):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+        if pin:
+            t = t.pin_memory()
+        return t.to(device, non_blocking=pin)
+    f64, i32 = torch.float64, torch.int32
+    return DeviceBatch(up(host["sites"], f64), up(host["values"], f64), up(host["n_db"], i32), up(host["x_index"], i32),
+                       up(host["x"], f64), up(host["delta"], f64), up(host["glb"], f64), up(host["gub"], f64),
+                       up(host["flags_in"], i32), up(host["max_new"], i32))
+
+
+class MultistartBuilder:
+    """select (rounds 1-4) -> gather -> build for a device-resident batch; buffers are reused across steps."""
+
+    def __init__(self, engine: Engine, cfg, delta_max: float):
+        self.engine, self.cfg, self.delta_max = engine, cfg, float(delta_max)
+        self._sel: Optional[SelectResult] = None
+        self._train = None
+        self._r3_values = None
+        self._status = None
+
+    def select(self, d: DeviceBatch) -> SelectResult:
+        self._sel = self.engine.select_points_dev(self.cfg, d.sites, d.n_db, d.x_index, d.x, d.delta, self.delta_max,
+                                                  d.glb, d.gub, d.flags_in, d.max_new, out=self._sel)
+        return self._sel
+
+    def build(self, d: DeviceBatch, sel: SelectResult, r3_values=None) -> Tuple[ModelBatch, object]:
+        import torch
+        B, db_stride, n = d.sites.shape
+        k = d.values.shape[2]
+        ts = train_stride_for(self.cfg, n, db_stride)
+        if r3_values is None:
+            if self._r3_values is None or self._r3_values.shape != (B, n, k):
+                self._r3_values = torch.zeros((B, n, k), dtype=torch.float64, device=d.sites.device)
+            r3_values = self._r3_values
+        if self._train is not None and self._train[0].shape != (B, ts, n):
+            self._train = None
+        self._train = self.engine.gather_training_dev(d.sites, d.values, d.x_index, sel, r3_values, ts, out=self._train)
+        if self._status is None or self._status.shape[0] != B:
+            self._status = torch.zeros(B, dtype=torch.int32, device=d.sites.device)
+        model, status = self.engine.build_dev(self.cfg, self._train[0], self._train[1], self._train[2], None, self._status)
+        return model, status
+
+    def step(self, d: DeviceBatch) -> Tuple[ModelBatch, SelectResult, object]:
+        sel = self.select(d)
+        model, status = self.build(d, sel)
+        return model, sel, status
+
+
+def gather_results(local: np.ndarray, total: int, rank: int, world: int) -> Optional[np.ndarray]:
+    """Final gather of per-instance result rows to every rank (no collective on the hot path; this is the only one).
+
+    `local` holds this rank's shard (rows shard_range(total, rank, world)).  Uses the initialised
+    torch.distributed process group (NCCL for CUDA tensors, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1 or not dist.is_initialized():
+        return local
+    backend = dist.get_backend()
+    counts = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+    width = int(np.prod(local.shape[1:])) if local.ndim > 1 else 1
+    mx = max(counts)
+    pad = np.zeros((mx, width), dtype=np.float64)
+    pad[: counts[rank]] = local.reshape(counts[rank], width)
+    t = torch.from_numpy(pad)
+    if backend == "nccl":
+        t = t.cuda()
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    rows = [o.cpu().numpy()[: counts[r]] for r, o in enumerate(outs)]
+    return np.concatenate(rows, axis=0).reshape((total,) + tuple(local.shape[1:]))

@@ -1,0 +1,12 @@
+"""Import alias: `import morbit_jl_b200` loads the package that lives in `morbit.jl_b200/`
+(the directory name contains a dot, so it cannot be imported by its own name)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "morbit.jl_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Bar (BASELINE north star):
+bit-exact selected indices / bookkeeping, FP64 coefficients, values and Jacobians <= 1e-10 relative."""
+import zlib
+
+import numpy as np
+import pytest
+
+import morbit_jl_b200 as mb
+from oracle import c_oracle as CO
+from oracle import rbf_oracle as O
+from helpers import random_instances, assert_select_equal
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10          # north-star tolerance for values / Jacobians (relative to the largest magnitude)
+
+
+SELECT_CASES = [
+    # n, kernel, deg, n_db, boxed, efl, max_new, delta, max_model_points, B
+    (2, "cubic", 1, 40, True, True, 2**31 - 1, 0.1, -1, 16),
+    (2, "gaussian", 1, 40, False, False, 2**31 - 1, 0.1, -1, 16),
+    (3, "multiquadric", 1, 10, True, False, 2**31 - 1, 0.05, -1, 16),
+    (5, "multiquadric", 1, 120, True, False, 2**31 - 1, 0.1, -1, 16),
+    (5, "cubic", 1, 40, True, False, 2, 0.1, -1, 16),
+    (5, "gaussian", 1, 40, True, False, 0, 0.1, -1, 8),
+    (6, "multiquadric", 0, 50, True, True, 1, 0.1, -1, 8),
+    (4, "gaussian", -1, 30, True, True, 10, 0.1, -1, 8),
+    (5, "cubic", 1, 12, True, True, 2**31 - 1, 0.1, -1, 16),
+    (8, "cubic", 1, 3, True, False, 3, 0.05, -1, 8),
+    (10, "inv_multiquadric", 1, 300, False, True, 2**31 - 1, 0.1, -1, 8),
+    (10, "cubic", 1, 1, True, True, 2**31 - 1, 0.1, -1, 4),           # empty database: centre only
+    (30, "multiquadric", 1, 128, True, False, 2**31 - 1, 0.1, -1, 8),
+    (30, "cubic", 1, 200, True, False, 2**31 - 1, 0.1, 61, 8),
+    (30, "gaussian", 1, 31, True, True, 2**31 - 1, 0.1, -1, 4),
+    (70, "cubic", 1, 160, True, False, 2**31 - 1, 0.1, 141, 2),       # n > 64: W/Z spill to the global workspace? (no: smem) 
+    (120, "cubic", 1, 130, True, True, 2**31 - 1, 0.1, 241, 1),       # global-workspace variants
+]
+
+
+@pytest.mark.parametrize("n,kernel,deg,n_db,boxed,efl,max_new,delta,mmp,B", SELECT_CASES)
+def test_select_points_matches_oracle(engine, n, kernel, deg, n_db, boxed, efl, max_new, delta, mmp, B):
+    rng = np.random.default_rng(zlib.crc32(repr((n, kernel, deg, n_db, mmp)).encode()))
+    cfg = mb.RbfConfig(kernel=kernel, polynomial_degree=deg, max_model_points=mmp)
+    sites, x, glb, gub = random_instances(rng, B, n, n_db, boxed, on_bound=(n == 5 and n_db == 12))
+    xi = np.ones(B, np.int32)
+    dl = np.full(B, delta)
+    ref = CO.select_points_batched(cfg, sites, xi, x, dl, 0.5, glb, gub, efl, False, min(max_new, 2**31 - 1), nthreads=4)
+    res = engine.select_points(cfg, sites, np.full(B, n_db), xi, x, dl, 0.5, glb, gub, efl, False, max_new)
+    assert np.all(res.status == 0)
+    assert np.all(ref.margins[:, 0] > 1e-9), "knife-edge filter decision in the corpus; change the seed"
+    assert_select_equal(res, ref, B)
+
+
+def test_select_points_ragged_db_and_delta_max(engine):
+    """Per-instance n_db (ragged), Δ ≈ Δmax (round 2 skipped, RbfModel.jl:588), force_rebuild flags."""
+    rng = np.random.default_rng(11)
+    B, n, stride = 12, 6, 90
+    cfg = mb.RbfConfig(kernel="cubic")
+    sites, x, glb, gub = random_instances(rng, B, n, stride)
+    n_db = rng.integers(1, stride + 1, B).astype(np.int32)
+    delta = np.where(np.arange(B) % 3 == 0, 0.5, 0.07)
+    force = (np.arange(B) % 4 == 1)
+    ref_parts = [CO.select_points_batched(cfg, sites[b:b + 1, :n_db[b]], [1], x[b:b + 1], delta[b:b + 1], 0.5, glb, gub,
+                                          False, bool(force[b]), 2**31 - 1) for b in range(B)]
+    res = engine.select_points(cfg, sites, n_db, np.ones(B, np.int32), x, delta, 0.5, glb, gub, False, force, 2**31 - 1)
+    for b, ref in enumerate(ref_parts):
+        for name, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+            assert list(getattr(res, name)[b, :getattr(res, cnt)[b]]) == list(getattr(ref, name)[0, :getattr(ref, cnt)[0]])
+        assert res.n_r3[b] == ref.n_r3[0] and bool(res.flags_out[b, 0]) == bool(ref.fully_linear[0])
+        np.testing.assert_allclose(res.r3_sites[b, :res.n_r3[b]], ref.r3_sites[0, :ref.n_r3[0]], rtol=0, atol=1e-13)
+
+
+def test_round3_pivot_failure_triggers_coordinate_rebuild(engine):
+    """RbfModel.jl:284-289, 634-637: iterate in a corner whose improving direction hits the wall too early."""
+    n = 3
+    cfg = mb.RbfConfig(kernel="cubic")
+    glb, gub = np.zeros(n), np.ones(n)
+    x = np.array([[0.5, 0.5, 0.5]])
+    # one database point such that the remaining improving directions are fine, then shrink the box so
+    # that a direction's wall step is <= pivot: put x next to the upper AND lower bound in one coordinate
+    glb2, gub2 = np.array([0.0, 0.0, 0.499]), np.array([1.0, 1.0, 0.501])
+    sites = np.array([[[0.5, 0.5, 0.5], [0.6, 0.45, 0.5]]])
+    ref = CO.select_points_batched(cfg, sites, [1], x, [0.1], 0.5, glb2, gub2, True, False, 2**31 - 1)
+    res = engine.select_points(cfg, sites, [2], [1], x, [0.1], 0.5, glb2, gub2, True, False, 2**31 - 1)
+    assert_select_equal(res, ref, 1)
+    assert bool(ref.rebuilt[0]), "corpus does not exercise the rebuild path"
+
+
+def test_round4_standalone_few_found(engine):
+    """test/rbf_models.jl:74-86: _rbf_round4 with only the centre as found index."""
+    for n, kernel, deg in [(2, "cubic", 1), (5, "gaussian", 1), (5, "multiquadric", 0), (10, "cubic", 1), (5, "gaussian", -1)]:
+        rng = np.random.default_rng(n * 7 + deg)
+        cfg = mb.RbfConfig(kernel=kernel, polynomial_degree=deg)
+        x = rng.random(n)
+        lb2, ub2 = np.maximum(0.0, x - 1.0), np.minimum(1.0, x + 1.0)
+        sites = np.vstack((x[None], lb2 + (ub2 - lb2) * rng.random((10 * n, n))))
+        ref, margin = CO.round4(cfg, sites, lb2, ub2, [1])
+        r4, n_r4, status = engine.round4(cfg, sites[None], [len(sites)], lb2[None], ub2[None], np.array([[1]]), [1])
+        assert margin > 1e-9
+        assert list(r4[0, :n_r4[0]]) == list(ref)
+
+
+BUILD_CASES = [
+    # n, kernel, deg, N, k, shape
+    (2, "cubic", 1, 6, 2, float("nan")),
+    (5, "cubic", 1, 21, 2, float("nan")),
+    (5, "cubic", 1, 21, 1, 1.0),              # phi = -rho  (examples/large_scale_benchmarks.jl:154-156)
+    (5, "multiquadric", 1, 21, 1, float("nan")),
+    (5, "multiquadric", 0, 15, 3, 2.0),
+    (5, "gaussian", -1, 15, 3, 2.0),
+    (5, "inv_multiquadric", 0, 15, 2, float("nan")),
+    (6, "cubic", 1, 3, 2, float("nan")),      # fewer sites than polynomial terms
+    (3, "cubic", 1, 1, 1, float("nan")),      # single point (max_evals = 1)
+    (30, "multiquadric", 1, 61, 2, float("nan")),
+    (30, "multiquadric", 1, 128, 2, float("nan")),
+    (30, "cubic", 1, 200, 2, float("nan")),   # global-workspace variant
+    (50, "gaussian", 1, 160, 1, 1.0),
+]
+
+
+@pytest.mark.parametrize("n,kernel,deg,N,k,shape", BUILD_CASES)
+def test_build_and_eval_match_oracle(engine, n, kernel, deg, N, k, shape):
+    rng = np.random.default_rng(N * 131 + n)
+    cfg = mb.RbfConfig(kernel=kernel, polynomial_degree=deg, shape_parameter=shape)
+    B = 3
+    S = rng.random((B, N, n))
+    V = np.stack([np.sum(S**2, -1), np.sum(np.sin(3 * S), -1), S[..., 0] * S[..., -1]], -1)[..., :k]
+    wr, lr, st = CO.build_batched(cfg, S, V, [N] * B, nthreads=3)
+    assert np.all(st == 0)
+    model, status = engine.build(cfg, S, V, [N] * B)
+    assert np.all(status == 0)
+    X = np.concatenate((rng.random((B, 37, n)), S[:, : min(N, 3)]), axis=1)       # includes training sites (rho = 0)
+    Y, J = engine.eval(model, X, True, True)
+    Y2, _ = engine.eval(model, X, True, False)
+    for b in range(B):
+        Yr = CO.eval_points(cfg, S[b], wr[b], lr[b], X[b]); Jr = CO.jac_points(cfg, S[b], wr[b], lr[b], X[b])
+        sy, sj = np.abs(Yr).max(), np.abs(Jr).max()
+        assert np.abs(Y[b] - Yr).max() <= RTOL * sy, (np.abs(Y[b] - Yr).max() / sy)
+        assert np.abs(Y2[b] - Yr).max() <= RTOL * sy
+        assert np.abs(J[b] - Jr).max() <= RTOL * sj, (np.abs(J[b] - Jr).max() / sj)
+    # interpolation at the training sites (test/archive/rbf_derivatives.jl style)
+    Ys, _ = engine.eval(model, S, True, False)
+    assert np.abs(Ys - V).max() <= 1e-9 * max(1.0, np.abs(V).max())
+    # coefficients: compared only when the saddle system is well conditioned (cond * eps << 1e-10)
+    w, lam = model.coeffs()
+    mref = O.build_model(S[0], V[0], O.RbfConfig(kernel=kernel, polynomial_degree=deg, shape_parameter=shape))
+    if N > n + 1 and mref.cond < 1e4:
+        assert np.abs(w[0, :N] - wr[0]).max() <= RTOL * mref.cond * np.abs(wr[0]).max()
+        assert np.abs(lam[0] - lr[0]).max() <= RTOL * mref.cond * max(1e-300, np.abs(lr[0]).max())
+    model.free()
+
+
+def test_eval_many_points_and_ragged_N(engine):
+    """M not a multiple of the tile, per-instance N (ragged training sets), k = 5 (> one output pass)."""
+    rng = np.random.default_rng(99)
+    B, n, Ns, k, M = 4, 30, 70, 5, 1000
+    cfg = mb.RbfConfig(kernel="cubic")
+    N = np.array([70, 33, 64, 65], np.int32)
+    S = rng.random((B, Ns, n)); V = rng.standard_normal((B, Ns, k))
+    wr, lr, st = CO.build_batched(cfg, S, V, N, nthreads=4)
+    model, status = engine.build(cfg, S, V, N)
+    X = rng.random((B, M, n))
+    Y, J = engine.eval(model, X, True, True)
+    for b in range(B):
+        Yr = CO.eval_points(cfg, S[b, :N[b]], wr[b, :N[b]], lr[b], X[b], nthreads=4)
+        Jr = CO.jac_points(cfg, S[b, :N[b]], wr[b, :N[b]], lr[b], X[b], nthreads=4)
+        assert np.abs(Y[b] - Yr).max() <= RTOL * np.abs(Yr).max()
+        assert np.abs(J[b] - Jr).max() <= RTOL * np.abs(Jr).max()
+    model.free()
+
+
+def test_eval_generic_kernel_large_n(engine):
+    rng = np.random.default_rng(5)
+    B, n, N, k, M = 1, 100, 150, 2, 200
+    cfg = mb.RbfConfig(kernel="multiquadric")
+    S = rng.random((B, N, n)); V = np.stack([np.sum(S**2, -1), np.sum(np.sin(S), -1)], -1)
+    wr, lr, st = CO.build_batched(cfg, S, V, [N])
+    model, status = engine.build(cfg, S, V, [N])
+    X = rng.random((B, M, n))
+    Y, J = engine.eval(model, X, True, True)
+    Yr = CO.eval_points(cfg, S[0], wr[0], lr[0], X[0]); Jr = CO.jac_points(cfg, S[0], wr[0], lr[0], X[0])
+    assert np.abs(Y[0] - Yr).max() <= RTOL * np.abs(Yr).max()
+    assert np.abs(J[0] - Jr).max() <= RTOL * np.abs(Jr).max()
+    model.free()
+
+
+def test_local_trust_region_cancellation(engine):
+    """Sites within Δ = 1e-3 of each other far from the origin: the centred GEMM form must keep 1e-10."""
+    rng = np.random.default_rng(17)
+    n, N, k = 10, 40, 2
+    cfg = mb.RbfConfig(kernel="cubic")
+    c = 5.0 + rng.random(n)
+    S = (c + 1e-3 * (rng.random((N, n)) * 2 - 1))[None]
+    V = np.stack([np.sum(S**2, -1), np.sum(np.sin(S), -1)], -1)
+    wr, lr, st = CO.build_batched(cfg, S, V, [N])
+    model, status = engine.build(cfg, S, V, [N])
+    X = (c + 1e-3 * (rng.random((64, n)) * 2 - 1))[None]
+    Y, J = engine.eval(model, X, True, True)
+    Yr = CO.eval_points(cfg, S[0], wr[0], lr[0], X[0]); Jr = CO.jac_points(cfg, S[0], wr[0], lr[0], X[0])
+    assert np.abs(Y[0] - Yr).max() <= 1e-9 * np.abs(Yr).max()      # both sides carry cond * eps of the solve
+    assert np.abs(J[0] - Jr).max() <= 1e-7 * np.abs(Jr).max()
+    model.free()
+
+
+def test_backtrack_matches_sequential_reference_loop(engine):
+    rng = np.random.default_rng(21)
+    B, n, N, k = 6, 8, 30, 2
+    cfg = mb.RbfConfig(kernel="cubic")
+    S = rng.random((B, N, n)); V = np.stack([np.sum((S - 0.3)**2, -1), np.sum((S + 0.2)**2, -1)], -1)
+    wr, lr, st = CO.build_batched(cfg, S, V, [N] * B)
+    model, status = engine.build(cfg, S, V, [N] * B)
+    x = rng.random((B, n))
+    ocfg = O.RbfConfig(kernel="cubic")
+    dirs = np.zeros((B, n)); omega = rng.random(B) + 0.1
+    for b in range(B):
+        Jr = CO.jac_points(cfg, S[b], wr[b], lr[b], x[b:b + 1])[0]
+        d = -Jr.sum(0); dirs[b] = d / np.abs(d).max()
+    dirs[-1] *= -1.0            # an ascent direction: backtracks to the minimum step size
+    xp, mxp, step, idx, mx = engine.backtrack(model, x, dirs, 1.0, omega)
+    for b in range(B):
+        ev = lambda z, b=b: CO.eval_points(cfg, S[b], wr[b], lr[b], z[None])[0]
+        xr, mr, sr, ir = O.backtrack(ev, x[b], dirs[b], 1.0, omega[b])
+        assert idx[b] == ir
+        np.testing.assert_array_equal(xp[b], xr)
+        assert np.abs(mxp[b] - mr).max() <= RTOL * np.abs(mr).max()
+    model.free()
+
+
+def test_unsupported_and_error_paths(engine):
+    cfg = mb.RbfConfig(kernel="cubic", use_max_points=True)
+    with pytest.raises(mb.MrbfError):
+        engine.select_points(cfg, np.zeros((1, 2, 2)), [2], [1], np.zeros((1, 2)), [0.1], 0.5, np.zeros(2), np.ones(2))
+    # duplicated sites: reduced kernel matrix not positive definite -> per-instance status, batch survives
+    rng = np.random.default_rng(1)
+    S = rng.random((2, 12, 3)); S[1, 5] = S[1, 4]
+    V = rng.random((2, 12, 1))
+    model, status = engine.build(mb.RbfConfig(kernel="cubic"), S, V, [12, 12], raise_on_failure=False)
+    assert status[0] == 0 and status[1] != 0
+    model.free()
