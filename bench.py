@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native RBF-surrogate hot path (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one pass of the hot path over one batch: for every instance of BASELINE config C3
+(4096 independent multistart ZDT3 n=30 instances per GPU, database snapshot of 128 sites, multiquadric
+RbfConfig) run prepare_update_model (rounds 1-4) + training-set gather + update_model (batched build).
+metric = RBF model builds/s, whole job.  Secondary: surrogate evals/s and Jacobians/s on config C5
+(10^6 trial points x 512 centres, d = 50).  Weak scaling: every rank owns its own 4096 instances, no
+collective on the data path; one final gather of per-instance result rows.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 4096
+N_VARS, N_DB, K_OUT = 30, 128, 2
+DELTA, DELTA_MAX = 0.1, 0.5
+KERNEL = "multiquadric"
+METRIC = "rbf_model_builds_per_s"
+UNIT = "builds/s"
+WORKLOAD = (f"C3: {B_PER_GPU} independent multistart ZDT3 n={N_VARS} k={K_OUT} instances per GPU, database snapshot "
+            f"{N_DB} sites/instance, RbfConfig(kernel=:{KERNEL}) defaults; build = rounds 1-4 + gather + solve")
+
+
+def fp64_peak_tflops():
+    """Measured FP64 FMA-pipe peak of this pool's B200 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no FP64 figure."""
+    path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+    try:
+        d = json.load(open(path))
+        return float(d["peak_used_tflops"]), "measured: tools/fp64_peak.cu (max of DFMA 33.8 / DMMA 37.2 TFLOP/s), profiles/fp64_peaks_r01.json"
+    except Exception:
+        return 37.0, "fallback: nominal B200 FP64 (no measured file)"
+
+
+def build_flops(N, n, k):
+    """SURVEY §8(d) primary figure: assembly + dense LU of the saddle system + solves."""
+    N = np.asarray(N, dtype=np.float64)
+    return 0.5 * N * N * (3 * n + 1) + (2.0 / 3.0) * (N + n + 1) ** 3 + 2 * k * (N + n + 1) ** 2
+
+
+def round4_flops(N0, n_acc, n):
+    """4 N^2 + 6 N (n+1) per candidate (four N-GEMV + sparse Givens), N growing with each acceptance."""
+    tot = 0.0
+    for a, c in zip(np.asarray(N0), np.asarray(n_acc)):
+        Ns = a + np.arange(c, dtype=np.float64)
+        tot += float(np.sum(4 * Ns * Ns + 6 * Ns * (n + 1)))
+    return tot
+
+
+def rounds123_flops(n_cand, n_picked, n):
+    """4 n (n-j) per remaining candidate per filter step (two GEMV with Z in R^{n x (n-j)})."""
+    tot = 0.0
+    for c, p in zip(np.asarray(n_cand), np.asarray(n_picked)):
+        for j in range(1, int(p) + 1):
+            tot += 4.0 * n * (n - j) * max(c - j, 0)
+    return tot
+
+
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def start(self):
+        def run():
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(cfg, host, n_threads, budget_s=12.0):
+    """The oracle's C port (structure-exploiting restatement, oracle/rbf_oracle.c) on the host cores, one instance per
+    thread, on a bounded sample of the same instances."""
+    from oracle import c_oracle as CO
+    from morbit_jl_b200 import synthetic
+    def run(lo, hi):
+        sl = slice(lo, hi)
+        t0 = time.perf_counter()
+        res = CO.select_points_batched(cfg, host["sites"][sl], host["x_index"][sl], host["x"][sl], host["delta"][sl],
+                                       host["delta_max"], host["glb"], host["gub"], False, False, 2**31 - 1, nthreads=n_threads)
+        nb = hi - lo
+        n = host["sites"].shape[2]
+        Ns = 1 + res.n_r1 + res.n_r2 + res.n_r3 + res.n_r4
+        ts = int(Ns.max())
+        S = np.zeros((nb, ts, n)); V = np.zeros((nb, ts, K_OUT))
+        for b in range(nb):
+            ids = [1] + list(res.r1[b, :res.n_r1[b]]) + list(res.r2[b, :res.n_r2[b]])
+            pts = [host["sites"][lo + b, np.array(ids) - 1], res.r3_sites[b, :res.n_r3[b]],
+                   host["sites"][lo + b, res.r4[b, :res.n_r4[b]].astype(int) - 1]]
+            P = np.vstack(pts); S[b, :len(P)] = P; V[b, :len(P)] = synthetic.zdt3(P)
+        CO.build_batched(cfg, S, V, Ns, nthreads=n_threads)
+        return time.perf_counter() - t0
+    probe = max(n_threads, 8)
+    t_probe = run(0, probe)
+    per = t_probe / probe
+    sample = int(min(host["sites"].shape[0], max(probe, budget_s / max(per, 1e-9))))
+    sample = max(probe, (sample // n_threads) * n_threads)
+    t = run(0, sample)
+    return sample / t, sample
+
+
+def eval_sweep(eng, torch, stream, M, kernel, want_j, steps, warmup):
+    """C5: M trial points x 512 centres, d = 50, k = 1; inputs resident in HBM (M*d*8 = 400 MB at 1e6 > L2)."""
+    import morbit_jl_b200 as mb
+    from morbit_jl_b200 import synthetic
+    centers, vals, _ = synthetic.eval_sweep(512, 50, 1, 8, seed=0)
+    cfg = mb.RbfConfig(kernel=kernel, shape_parameter=1.0 if kernel == "gaussian" else float("nan"))
+    model, _ = eng.build(cfg, centers[None], vals[None], [512])
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    cbar = torch.from_numpy(centers.mean(0)).cuda()
+    lo, hi = torch.clamp(cbar - 0.2, min=0.0), torch.clamp(cbar + 0.2, max=1.0)
+    X = (lo + (hi - lo) * torch.rand((1, M, 50), dtype=torch.float64, device="cuda", generator=g)).contiguous()
+    Y = torch.empty((1, M, 1), dtype=torch.float64, device="cuda")
+    J = torch.empty((1, M, 1, 50), dtype=torch.float64, device="cuda") if want_j else None
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            eng.eval_dev(model, X, Y, J)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            eng.eval_dev(model, X, Y, J)
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    model.free()
+    return M / (ms * 1e-3), ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import morbit_jl_b200 as mb
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import MultistartBuilder, upload_batch, train_stride_for, gather_results
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    eng = mb.Engine(local, stream=stream.cuda_stream)
+    cfg = mb.RbfConfig(kernel=KERNEL)
+    B = args.instances
+    host = synthetic.multistart_batch(B, n=N_VARS, n_db=N_DB, delta=DELTA, delta_max=DELTA_MAX, func=synthetic.zdt3,
+                                      first_instance=rank * B)
+    dev = upload_batch(host, f"cuda:{local}")
+    builder = MultistartBuilder(eng, cfg, DELTA_MAX)
+    models = []
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            m, sel, status = builder.step(dev); stream.synchronize(); m.free()
+        l0 = eng.launch_count
+        sampler = ClockSampler(local); sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            m, sel, status = builder.step(dev)
+            models.append(m)
+        e1.record(stream)
+        stream.synchronize()
+        barrier()
+        clocks = sampler.stop()
+        launches = eng.launch_count - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    for m in models[:-1]:
+        m.free()
+    model = models[-1]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers: pinned H2D of the step's inputs, D2H of the result
+    names = ["sites", "values", "n_db", "x_index", "x", "delta", "glb", "gub", "flags_in", "max_new"]
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(host[k])).pin_memory() for k in names}
+    h2d = sum(t.numel() * t.element_size() for t in pinned.values())
+    out_pin = None
+    e2e_models = []
+    with torch.cuda.stream(stream):
+        def e2e_step():
+            nonlocal out_pin
+            for k in names:
+                getattr(dev, k).copy_(pinned[k], non_blocking=True)
+            m, sel, status = builder.step(dev)
+            outs = [sel.r1, sel.n_r1, sel.r2, sel.n_r2, sel.n_r3, sel.r4, sel.n_r4, sel.flags_out, status]
+            if out_pin is None:
+                out_pin = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            for p, o in zip(out_pin, outs):
+                p.copy_(o, non_blocking=True)
+            return m
+        for _ in range(max(1, args.warmup // 2)):
+            m = e2e_step(); stream.synchronize(); m.free()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(args.steps):
+            e2e_models.append(e2e_step())
+        t1.record(stream)
+        stream.synchronize()
+        barrier()
+    e2e_ms = t0.elapsed_time(t1) / args.steps
+    d2h = sum(p.numel() * p.element_size() for p in out_pin)
+    for m in e2e_models:
+        m.free()
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    # ---- per-kernel device times (one extra, untimed-for-the-metric step with event brackets) and roofline
+    eng.profile_enable(True)
+    with torch.cuda.stream(stream):
+        m2, sel, status = builder.step(dev)
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    m2.free()
+    n_r1, n_r2, n_r3, n_r4 = (getattr(sel, a).cpu().numpy() for a in ("n_r1", "n_r2", "n_r3", "n_r4"))
+    N0 = 1 + n_r1 + n_r2 + n_r3
+    Ntrain = N0 + n_r4
+    ok = int((status.cpu().numpy() == 0).sum())
+    peak, peak_src = fp64_peak_tflops()
+    kflops = {"rounds123": rounds123_flops(np.full(B, N_DB - 1), n_r1 + n_r2, N_VARS), "round4": round4_flops(N0, n_r4, N_VARS),
+              "build": float(np.sum(build_flops(Ntrain, N_VARS, K_OUT)))}
+    dom = max(("rounds123", "round4", "build"), key=lambda k: prof[k])
+    ach = kflops[dom] / (prof[dom] * 1e-3) / 1e12
+    step_total = prof["rounds123"] + prof["round4"] + prof["gather"] + prof["build"]
+    roofline = {"bound": "tensor", "pipe": "fp64 (DFMA; B200 FP64 tensor peak equals the FMA-pipe peak)", "kernel": dom,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": {k: round(v, 4) for k, v in prof.items() if k != "eval"},
+                "kernel_share_of_step": round(prof[dom] / step_total, 4) if step_total > 0 else None,
+                "algorithmic_flops_per_launch": kflops[dom]}
+
+    # ---- final gather of per-instance results (the only collective)
+    rows = np.stack([Ntrain, n_r4, status.cpu().numpy()], axis=1).astype(np.float64)
+    allrows = gather_results(rows, world * B, rank, world)
+
+    # ---- secondary metric: surrogate evals/s and Jacobians/s (config C5)
+    secondary = []
+    if args.eval_points > 0:
+        fe = 512 * (3 * 50 + 1 + 2 * 1) + 2 * 51 * 1
+        fj = 512 * (3 * 50 + 1 + 1 * (1 + 2 * 50)) + 50
+        for kern in ("gaussian", "cubic"):
+            ev, ev_ms = eval_sweep(eng, torch, stream, args.eval_points, kern, False, args.steps, args.warmup)
+            jv, jv_ms = eval_sweep(eng, torch, stream, args.eval_points, kern, True, args.steps, args.warmup)
+            if world > 1:
+                t = torch.tensor([ev, jv], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ev, jv = (float(v) * world for v in t.tolist())
+            secondary.append({"metric": "surrogate_evals_per_s", "kernel": kern, "value": ev, "unit": "evals/s", "ms_per_step": ev_ms,
+                              "config": {"workload": f"C5: {args.eval_points} trial points x 512 centres, d=50, k=1, per GPU"},
+                              "roofline": {"bound": "tensor", "pipe": "fp64", "achieved": ev / world * fe / 1e12, "peak": peak,
+                                           "unit": "TFLOP/s", "frac": ev / world * fe / 1e12 / peak, "flop_per_point": fe}})
+            secondary.append({"metric": "surrogate_jacobians_per_s", "kernel": kern, "value": jv, "unit": "jacobians/s", "ms_per_step": jv_ms,
+                              "config": {"workload": f"C5: {args.eval_points} trial points x 512 centres, d=50, k=1, values + Jacobian, per GPU"},
+                              "roofline": {"bound": "tensor", "pipe": "fp64", "achieved": jv / world * fj / 1e12, "peak": peak,
+                                           "unit": "TFLOP/s", "frac": jv / world * fj / 1e12 / peak, "flop_per_point": fj}})
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle as CO
+        nthr = min(os.cpu_count() or 1, CO.max_threads())
+        v, sample = cpu_baseline(cfg, host, nthr)
+        cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
+               "sample": f"first {sample} instances of the same batch, one instance per thread; C port of the reference path "
+                         "(oracle/rbf_oracle.c, cheaper than the reference's dense O(N^3) round-4 update); not Julia"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "instances_per_gpu": B, "n_vars": N_VARS, "n_outputs": K_OUT, "db_sites": N_DB,
+                           "kernel": KERNEL, "mean_training_points": float(Ntrain.mean()), "builds_ok": ok,
+                           "l2": "per-step working set (sites + seeds + round-4 workspace) ~0.9 GB > 126 MB L2; no flush needed",
+                           "parallelism": f"instances sharded over {world} rank(s), no data-path collective"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms,
+                        "path": "pinned host database snapshot -> H2D -> mrbf_select_points_dev + gather + mrbf_build_dev -> D2H of "
+                                "indices/flags/status (models stay device-resident handles, as in the ABI)"},
+                "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
+                "gathered_rows": None if allrows is None else int(allrows.shape[0])}
+        print(json.dumps(line))
+    model.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU formulation of the path.  The reference is Julia and cannot run in this
+    image, so this times the oracle's C port with all host threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import morbit_jl_b200  # noqa: F401  (config class + synthetic inputs only; no GPU work on this arm)
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.surrogate import RbfConfig
+    from oracle import c_oracle as CO
+    nthr = min(os.cpu_count() or 1, CO.max_threads())
+    cfg = RbfConfig(kernel=KERNEL)
+    sample = max(nthr, min(args.instances, args.ref_sample))
+    host = synthetic.multistart_batch(sample, n=N_VARS, n_db=N_DB, delta=DELTA, delta_max=DELTA_MAX, func=synthetic.zdt3)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cpu_baseline_once(cfg, host, nthr, CO, synthetic)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    v = sample / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_instances_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
+                             "sample": f"{sample} instances per step; C port of the reference path (no Julia in this image)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_once(cfg, host, nthr, CO, synthetic):
+    B, _, n = host["sites"].shape
+    res = CO.select_points_batched(cfg, host["sites"], host["x_index"], host["x"], host["delta"], host["delta_max"],
+                                   host["glb"], host["gub"], False, False, 2**31 - 1, nthreads=nthr)
+    Ns = 1 + res.n_r1 + res.n_r2 + res.n_r3 + res.n_r4
+    ts = int(Ns.max())
+    S = np.zeros((B, ts, n)); V = np.zeros((B, ts, K_OUT))
+    for b in range(B):
+        ids = [1] + list(res.r1[b, :res.n_r1[b]]) + list(res.r2[b, :res.n_r2[b]])
+        P = np.vstack([host["sites"][b, np.array(ids) - 1], res.r3_sites[b, :res.n_r3[b]],
+                       host["sites"][b, res.r4[b, :res.n_r4[b]].astype(int) - 1]])
+        S[b, :len(P)] = P; V[b, :len(P)] = synthetic.zdt3(P)
+    CO.build_batched(cfg, S, V, Ns, nthreads=nthr)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=B_PER_GPU, help="instances per GPU (default: the C3 workload)")
+    ap.add_argument("--eval-points", type=int, default=10**6, help="C5 trial points for the secondary metric (0 = skip)")
+    ap.add_argument("--ref-sample", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

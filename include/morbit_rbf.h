@@ -77,6 +77,12 @@ void mrbf_destroy(mrbf_ctx* ctx);
 const char* mrbf_last_error(const mrbf_ctx* ctx);
 /* kernels launched through this context since creation (the bench's gpu_launches counter) */
 int64_t mrbf_launch_count(const mrbf_ctx* ctx);
+/* Instrumentation (not part of the reference interface): when enabled, every kernel launch is bracketed by CUDA
+ * events on the context's stream.  mrbf_profile_read synchronises and returns the device time in ms of the LAST
+ * launch of each kernel class: ms[0] rounds 1-3, ms[1] round 4, ms[2] training-set gather, ms[3] build,
+ * ms[4] eval/Jacobian (all passes of the last call), ms[5..7] reserved (0). */
+int mrbf_profile_enable(mrbf_ctx* ctx, int32_t on);
+int mrbf_profile_read(mrbf_ctx* ctx, double* ms8);
 
 /* ---- training-set search: replaces prepare_update_model rounds 1-4 --------------------------
  * src/models/RbfModel.jl:518-655 (_rbf_round1 :242, _rbf_round2 :251, _rbf_round3 :269, _rbf_round4 :352),

@@ -39,6 +39,8 @@ SIGNATURES = {
     "mrbf_destroy": (None, [_vp]),
     "mrbf_last_error": (C.c_char_p, [_vp]),
     "mrbf_launch_count": (_i64, [_vp]),
+    "mrbf_profile_enable": (C.c_int, [_vp, _i32]),
+    "mrbf_profile_read": (C.c_int, [_vp, _vp]),
     "mrbf_select_points": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32] + [_vp] * 4 + [_vp, _f64] + [_vp] * 4
                            + [_vp] * 6 + [_i32] + [_vp] * 6),
     "mrbf_select_points_dev": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32] + [_vp] * 4 + [_vp, _f64] + [_vp] * 4

@@ -27,6 +27,9 @@ struct mrbf_ctx {
     bool own_stream = false;
     int64_t launches = 0;
     char err[512] = {0};
+    bool prof = false;
+    cudaEvent_t ev0[8] = {nullptr}, ev1[8] = {nullptr};
+    bool ev_used[8] = {false};
     DevBuf ws[16];      // kernel workspaces (grow-only)
     DevBuf hb[32];      // staging for the host-pointer entry points
 };
@@ -54,6 +57,13 @@ int fail(mrbf_ctx* c, int code, const char* fmt, const char* detail = "") {
         cudaError_t e_ = (call);                                                         \
         if (e_ != cudaSuccess) return fail(ctx, MRBF_ECUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
     } while (0)
+
+// event bracket around a kernel class (instrumentation only)
+struct Timed {
+    mrbf_ctx* c; int id;
+    Timed(mrbf_ctx* ctx, int i) : c(ctx), id(i) { if (c->prof) cudaEventRecord(c->ev0[id], c->stream); }
+    ~Timed() { if (c->prof) { cudaEventRecord(c->ev1[id], c->stream); c->ev_used[id] = true; } }
+};
 
 int ensure(mrbf_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -141,7 +151,7 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
         ENSURE(ctx->ws[7], (size_t)B * wsd * sizeof(double));
         R.ws = (double*)ctx->ws[7].p;
     }
-    CK(launch_round4(R, smem, ctx->stream));
+    { Timed t_(ctx, 1); CK(launch_round4(R, smem, ctx->stream)); }
     ctx->launches += 1;
     return MRBF_OK;
 }
@@ -190,8 +200,30 @@ void mrbf_destroy(mrbf_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->ws) if (b.p) cudaFree(b.p);
     for (auto& b : ctx->hb) if (b.p) cudaFree(b.p);
+    for (int i = 0; i < 8; ++i) { if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]); if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int mrbf_profile_enable(mrbf_ctx* ctx, int32_t on) {
+    if (!ctx) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev0[0])
+        for (int i = 0; i < 8; ++i) { CK(cudaEventCreate(&ctx->ev0[i])); CK(cudaEventCreate(&ctx->ev1[i])); }
+    ctx->prof = on != 0;
+    for (int i = 0; i < 8; ++i) ctx->ev_used[i] = false;
+    return MRBF_OK;
+}
+
+int mrbf_profile_read(mrbf_ctx* ctx, double* ms8) {
+    if (!ctx || !ms8) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; ++i) {
+        ms8[i] = 0.0;
+        if (ctx->ev_used[i]) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0[i], ctx->ev1[i])); ms8[i] = ms; }
+    }
+    return MRBF_OK;
 }
 
 const char* mrbf_last_error(const mrbf_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -229,7 +261,7 @@ int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_
     S.lb2 = (double*)ctx->ws[4].p; S.ub2 = S.lb2 + (size_t)B * n;
     ENSURE(ctx->ws[5], ((size_t)B * S.found_stride + B) * sizeof(int));
     S.found = (int*)ctx->ws[5].p; S.n_found = S.found + (size_t)B * S.found_stride;
-    CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem), ctx->stream));
+    { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem), ctx->stream)); }
     ctx->launches += 1;
     if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
         rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,
@@ -332,7 +364,7 @@ int mrbf_gather_training_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int
     G.sites = sites; G.values = values; G.x_index = x_index; G.r1 = r1; G.n_r1 = n_r1; G.r2 = r2; G.n_r2 = n_r2;
     G.r3_sites = r3_sites; G.r3_values = r3_values; G.n_r3 = n_r3; G.r4 = r4; G.n_r4 = n_r4;
     G.train_sites = train_sites; G.train_values = train_values; G.N = N;
-    CK(launch_gather_training(G, ctx->stream));
+    { Timed t_(ctx, 2); CK(launch_gather_training(G, ctx->stream)); }
     ctx->launches += 1;
     return MRBF_OK;
 }
@@ -391,7 +423,7 @@ int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int
     if (e == cudaSuccess) e = cudaMemcpyAsync(m->centers, sites, sizeof(double) * (size_t)B * train_stride * n, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->w, 0, sizeof(double) * (size_t)B * train_stride * k, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->lam, 0, sizeof(double) * (size_t)B * pl * k, ctx->stream);
-    if (e == cudaSuccess) e = launch_build(Pb, smem, ctx->stream);
+    if (e == cudaSuccess) { Timed t_(ctx, 3); e = launch_build(Pb, smem, ctx->stream); }
     if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ECUDA, "CUDA error: %s", cudaGetErrorString(e)); }
     ctx->launches += 1;
     *out = m;
@@ -447,7 +479,7 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
     int nl = 0;
     EvalParams E{};
     fill_eval(E, m, M, X, Y, J);       // with J the same pass also produces the values
-    CK(launch_eval(E, ctx->stream, &nl));
+    { Timed t_(ctx, 4); CK(launch_eval(E, ctx->stream, &nl)); }
     ctx->launches += nl;
     return MRBF_OK;
 }

@@ -114,6 +114,14 @@ class Engine:
     def sync(self):
         self._check(self.lib.mrbf_sync(self.ctx))
 
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.mrbf_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self) -> dict:
+        ms = (C.c_double * 8)()
+        self._check(self.lib.mrbf_profile_read(self.ctx, ms))
+        return dict(rounds123=ms[0], round4=ms[1], gather=ms[2], build=ms[3], eval=ms[4])
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mrbf_launch_count(self.ctx))
