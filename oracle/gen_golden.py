@@ -1,0 +1,70 @@
+"""Generates tests/golden/*.npz from the literal NumPy/LAPACK oracle (oracle/rbf_oracle.py).
+
+The reference holds no golden vectors for this path and cannot be executed here (no Julia), so these
+fixtures pin the ORACLE's outputs, not the reference's; they exist so that the C oracle, the CUDA path and
+future rounds are all compared against the same frozen numbers.    python oracle/gen_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import rbf_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SELECT = [  # name, n, kernel, deg, n_db, boxed, ensure_fully_linear, max_new, delta, max_model_points
+    ("sel_n2_cubic", 2, "cubic", 1, 30, False, True, None, 0.1, -1),
+    ("sel_n5_mq", 5, "multiquadric", 1, 80, True, False, None, 0.1, -1),
+    ("sel_n5_budget2", 5, "cubic", 1, 30, True, False, 2, 0.1, -1),
+    ("sel_n6_deg0", 6, "multiquadric", 0, 40, True, True, 1, 0.1, -1),
+    ("sel_n10_gauss", 10, "gaussian", 1, 150, True, False, None, 0.07, -1),
+    ("sel_n30_mq_cap61", 30, "multiquadric", 1, 100, True, False, None, 0.1, 61),
+]
+BUILD = [  # name, n, kernel, deg, N, k, shape
+    ("mod_n2_cubic", 2, "cubic", 1, 6, 2, float("nan")),
+    ("mod_n5_mq", 5, "multiquadric", 1, 21, 2, float("nan")),
+    ("mod_n5_gauss_nopoly", 5, "gaussian", -1, 15, 1, 2.0),
+    ("mod_n5_imq_deg0", 5, "inv_multiquadric", 0, 15, 2, float("nan")),
+    ("mod_n30_cubic", 30, "cubic", 1, 61, 2, float("nan")),
+    ("mod_n6_underdetermined", 6, "cubic", 1, 3, 1, float("nan")),
+]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for i, (name, n, kernel, deg, n_db, boxed, efl, max_new, delta, mmp) in enumerate(SELECT):
+        rng = np.random.default_rng(1000 + i)
+        cfg = O.RbfConfig(kernel=kernel, polynomial_degree=deg, max_model_points=mmp)
+        glb = np.full(n, 0.0 if boxed else -np.inf); gub = np.full(n, 1.0 if boxed else np.inf)
+        x = rng.random(n)
+        db = O.ArrayDB(); xi = db.new_result(x, [0.0])
+        for _ in range(n_db - 1):
+            db.new_result(np.clip(x + (rng.random(n) * 2 - 1) * 0.6 * rng.random(), glb, gub), [0.0])
+        sites = np.array(db.sites)
+        meta = O.RbfMeta(signature=cfg.signature())
+        O.prepare_update_model(meta, cfg, db, x, xi, delta, 0.5, glb, gub, ensure_fully_linear=efl,
+                               algo_max_evals=O.INT_MAX if max_new is None else max_new + 1)
+        r3 = np.array([db.get_site(j) for j in meta.round3_indices]).reshape(-1, n)
+        np.savez(os.path.join(OUT, name + ".npz"), kind="select", kernel=kernel, deg=deg, mmp=mmp, sites=sites, x=x, x_index=xi,
+                 delta=delta, delta_max=0.5, glb=glb, gub=gub, ensure_fully_linear=efl,
+                 max_new=2**31 - 1 if max_new is None else max_new, r1=np.array(meta.round1_indices, np.int32),
+                 r2=np.array(meta.round2_indices, np.int32), r3_sites=r3, r4=np.array(meta.round4_indices, np.int32),
+                 dirs=np.array(meta.improving_directions).reshape(-1, n), fully_linear=meta.fully_linear)
+    for i, (name, n, kernel, deg, N, k, shape) in enumerate(BUILD):
+        rng = np.random.default_rng(2000 + i)
+        cfg = O.RbfConfig(kernel=kernel, polynomial_degree=deg, shape_parameter=shape)
+        S = rng.random((N, n))
+        V = np.stack([np.sum(S**2, 1), np.sum(np.sin(3 * S), 1)], 1)[:, :k]
+        m = O.build_model(S, V, cfg)
+        X = np.vstack((rng.random((9, n)), S[:2]))
+        Y = np.array([m.eval(xx) for xx in X]); J = np.array([m.jac(xx) for xx in X])
+        np.savez(os.path.join(OUT, name + ".npz"), kind="model", kernel=kernel, deg=deg, shape=shape, sites=S, values=V, X=X, Y=Y, J=J,
+                 w=m.w, lam=m.lam, cond=m.cond)
+    print("wrote", len(SELECT) + len(BUILD), "fixtures to", OUT)
+
+
+if __name__ == "__main__":
+    main()

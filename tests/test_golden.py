@@ -1,0 +1,76 @@
+"""Frozen oracle outputs (tests/golden/*.npz, made by oracle/gen_golden.py): the C oracle on CPU and the CUDA
+path on the GPU must both reproduce them."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import rbf_oracle as O
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+SEL = [g for g in GOLD if os.path.basename(g).startswith("sel_")]
+MOD = [g for g in GOLD if os.path.basename(g).startswith("mod_")]
+
+
+def _cfg(cls, g, **kw):
+    return cls(kernel=str(g["kernel"]), polynomial_degree=int(g["deg"]), **kw)
+
+
+def _check_select(g, r1, r2, r3_sites, r4, dirs, fully_linear):
+    assert list(r1) == list(g["r1"]) and list(r2) == list(g["r2"]) and list(r4) == list(g["r4"])
+    assert bool(fully_linear) == bool(g["fully_linear"])
+    assert r3_sites.shape == g["r3_sites"].shape
+    if r3_sites.size:
+        np.testing.assert_allclose(r3_sites, g["r3_sites"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(dirs, g["dirs"], rtol=0, atol=1e-11)
+
+
+def test_fixtures_exist():
+    assert len(SEL) >= 6 and len(MOD) >= 6
+
+
+@pytest.mark.parametrize("path", SEL, ids=os.path.basename)
+def test_c_oracle_select_matches_golden(path):
+    g = np.load(path)
+    cfg = _cfg(O.RbfConfig, g, max_model_points=int(g["mmp"]))
+    r = CO.select_points_batched(cfg, g["sites"][None], [int(g["x_index"])], g["x"][None], [float(g["delta"])],
+                                 float(g["delta_max"]), g["glb"], g["gub"], bool(g["ensure_fully_linear"]), False, int(g["max_new"]))
+    _check_select(g, r.r1[0, :r.n_r1[0]], r.r2[0, :r.n_r2[0]], r.r3_sites[0, :r.n_r3[0]], r.r4[0, :r.n_r4[0]],
+                  r.dirs[0, :r.n_dirs[0]], r.fully_linear[0])
+
+
+@pytest.mark.parametrize("path", MOD, ids=os.path.basename)
+def test_c_oracle_model_matches_golden(path):
+    g = np.load(path)
+    cfg = _cfg(O.RbfConfig, g, shape_parameter=float(g["shape"]))
+    w, lam, st = CO.build_batched(cfg, g["sites"][None], g["values"][None], [len(g["sites"])])
+    Y = CO.eval_points(cfg, g["sites"], w[0], lam[0], g["X"]); J = CO.jac_points(cfg, g["sites"], w[0], lam[0], g["X"])
+    assert np.abs(Y - g["Y"]).max() <= 1e-10 * np.abs(g["Y"]).max()
+    assert np.abs(J - g["J"]).max() <= 1e-10 * np.abs(g["J"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SEL, ids=os.path.basename)
+def test_cuda_select_matches_golden(engine, path):
+    import morbit_jl_b200 as mb
+    g = np.load(path)
+    cfg = _cfg(mb.RbfConfig, g, max_model_points=int(g["mmp"]))
+    r = engine.select_points(cfg, g["sites"][None], [len(g["sites"])], [int(g["x_index"])], g["x"][None], [float(g["delta"])],
+                             float(g["delta_max"]), g["glb"], g["gub"], bool(g["ensure_fully_linear"]), False, int(g["max_new"]))
+    _check_select(g, r.r1[0, :r.n_r1[0]], r.r2[0, :r.n_r2[0]], r.r3_sites[0, :r.n_r3[0]], r.r4[0, :r.n_r4[0]],
+                  r.dirs[0, :r.n_dirs[0]], r.flags_out[0, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", MOD, ids=os.path.basename)
+def test_cuda_model_matches_golden(engine, path):
+    import morbit_jl_b200 as mb
+    g = np.load(path)
+    cfg = _cfg(mb.RbfConfig, g, shape_parameter=float(g["shape"]))
+    model, status = engine.build(cfg, g["sites"][None], g["values"][None], [len(g["sites"])])
+    Y, J = engine.eval(model, g["X"][None], True, True)
+    assert np.abs(Y[0] - g["Y"]).max() <= 1e-10 * np.abs(g["Y"]).max()
+    assert np.abs(J[0] - g["J"]).max() <= 1e-10 * np.abs(g["J"]).max()
+    model.free()
