@@ -142,17 +142,46 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
     R.extra_sites = extra; R.n_extra = n_extra; R.r4 = r4; R.n_r4 = n_r4; R.status = status;
     ENSURE(ctx->ws[6], (size_t)B * db_stride);
     R.cand = (unsigned char*)ctx->ws[6].p;
+    // 1. shared-memory fast path (regular case N0 == p); marks the instances it cannot take with n_r4 = -1
+    {
+        const size_t fv = round4_fast_vec_doubles(n, NM, p), fsd = round4_fast_state_doubles(n, NM, p);
+        size_t fsmem = fv * sizeof(double);
+        if (fsmem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
+        if ((fv + fsd) * sizeof(double) <= SMEM_LIMIT) { R.fs_in_smem = 1; fsmem = (fv + fsd) * sizeof(double); R.fs = nullptr; R.fs_stride = 0; }
+        else {
+            R.fs_in_smem = 0; R.fs_stride = fsd;
+            ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double));
+            R.fs = (double*)ctx->ws[9].p;
+        }
+        Timed t_(ctx, 1);
+        CK(launch_round4_fast(R, fsmem, ctx->stream));
+        ctx->launches += 1;
+    }
+    // 2. literal kernel for the marked rest (N0 != p: budget-limited round 3, explicit found sets, rank-deficient Pi_0)
     const size_t vecd = round4_vec_doubles(n, NM, p), wsd = round4_ws_doubles(n, NM, p);
     size_t smem = vecd * sizeof(double);
-    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) { R.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); R.ws = nullptr; R.ws_stride = 0; }
-    else {
+    R.only_marked = 1;
+    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) {
+        R.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); R.ws = nullptr; R.ws_stride = 0; R.b0 = 0;
+        Timed t_(ctx, 5);
+        CK(launch_round4(R, smem, ctx->stream, B));
+        ctx->launches += 1;
+    } else {
         if (smem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
         R.ws_in_smem = 0; R.ws_stride = wsd;
-        ENSURE(ctx->ws[7], (size_t)B * wsd * sizeof(double));
+        size_t chunk = ((size_t)4 << 30) / (wsd * sizeof(double));       // <= 4 GiB of workspace per launch
+        if (chunk < 1) chunk = 1;
+        if (chunk > (size_t)B) chunk = B;
+        ENSURE(ctx->ws[7], chunk * wsd * sizeof(double));
         R.ws = (double*)ctx->ws[7].p;
+        Timed t_(ctx, 5);
+        for (int b0 = 0; b0 < B; b0 += (int)chunk) {
+            R.b0 = b0;
+            const int g = (B - b0) < (int)chunk ? (B - b0) : (int)chunk;
+            CK(launch_round4(R, smem, ctx->stream, g));
+            ctx->launches += 1;
+        }
     }
-    { Timed t_(ctx, 1); CK(launch_round4(R, smem, ctx->stream)); }
-    ctx->launches += 1;
     return MRBF_OK;
 }
 

@@ -36,6 +36,9 @@ struct Round4Params {
     int* r4; int* n_r4; int* status;
     unsigned char* cand;          // B x db_stride candidate flags (workspace)
     double* ws; size_t ws_stride; int ws_in_smem;
+    int b0;                       // first instance of this launch (chunked literal launches)
+    int only_marked;              // literal kernel: process only instances the fast kernel marked (n_r4 == -1)
+    double* fs; size_t fs_stride; int fs_in_smem;   // fast-path state
 };
 
 struct GatherParams {
@@ -76,11 +79,14 @@ struct BacktrackParams {
 size_t select_smem_bytes(int n, bool wz_in_smem);
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
+size_t round4_fast_vec_doubles(int n, int NM, int p);
+size_t round4_fast_state_doubles(int n, int NM, int p);
 size_t build_vec_doubles(int n, int k, int ld, int p);
 size_t build_ws_doubles(int n, int k, int ld, int p);
 
 cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s);
-cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s);
+cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid);
+cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s);
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s);
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);

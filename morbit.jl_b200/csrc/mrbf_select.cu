@@ -310,7 +310,8 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
     extern __shared__ double smem[];
-    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int b = P.b0 + blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (P.only_marked && P.n_r4[b] != -1) return;      // handled by the shared-memory fast path
     const int NM = P.NM, MM = P.NM;
     const int deg = P.cfg.polynomial_degree;
     const int p = poly_dim(n, deg);
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
     double* rl = gt + pl;              // pl
     double* red = rl + pl;             // 80
     double* mats = red + 80;
-    double* ws = P.ws_in_smem ? mats : P.ws + (size_t)b * P.ws_stride;
+    double* ws = P.ws_in_smem ? mats : P.ws + (size_t)blockIdx.x * P.ws_stride;
     double* Ct = ws;                               // NM x n   (Ct[k*NM + i] = centre i, coordinate k)
     double* Phi = Ct + (size_t)NM * n;             // NM x NM
     double* Q1 = Phi + (size_t)NM * NM;            // NM x pl
@@ -569,6 +570,291 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
     if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Round 4, shared-memory formulation for the regular case N0 == p (found set = centre + n poised points).
+//
+// Same decisions as RbfModel.jl:420-452, different basis.  Let S0 be the found set (Pi_0 = Pi(S0) is p x p and
+// non-singular).  Every later point xi has the null vector  n_xi = e_xi - sum_{s in S0} c_xi[s] e_s,
+// c_xi = Pi_0^{-T} pi_xi, and these vectors span null(Pi') just like the reference's orthonormal Z.  With
+// A = N' Phi N (the kernel matrix reduced to that basis) and its Cholesky pivot d^2 for xi,
+//       tau^2 (reference, orthonormal basis)  =  g_hat^2 * d^2,     g_hat = prod_j c_j of the Givens sequence,
+// because n_xi = Z t12 + z_new / g_hat (last coordinate) and Schur complements scale by the square of the
+// diagonal entry of a triangular change of basis.  So the O(N^2) state (Phi, Q, Z) collapses to the inverse
+// Cholesky factor of A (m x m, packed), two p x m coefficient blocks and R -- all resident in shared memory
+// for the benchmark shapes -- and the per-candidate work drops from four N-GEMVs over L2/HBM to one
+// triangular mat-vec in shared memory.  Instances that do not qualify (N0 != p, rank-deficient Pi_0) are
+// marked n_r4 = -1 and handled by the literal kernel above.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t tri(int r) { return (size_t)r * (r + 1) / 2; }
+
+__global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int NM = P.NM;
+    const int deg = P.cfg.polynomial_degree;
+    const int p = poly_dim(n, deg);
+    const int pl = p > 0 ? p : 1, pb = pl | 1;
+    const int MM = (NM - p) > 1 ? (NM - p) : 1;
+    // shared vectors
+    double* xi = smem;                 // n
+    double* phix = xi + n;             // NM
+    double* av = phix + NM;            // MM
+    double* tv = av + MM;              // MM
+    double* cvec = tv + MM;            // pl
+    double* ub = cvec + pl;            // pl
+    double* cs = ub + pl;              // pl
+    double* sn = cs + pl;              // pl
+    double* rl = sn + pl;              // pl
+    double* tauq = rl + pl;            // pl
+    double* red = tauq + pl;           // 80
+    double* st = red + 80;
+    double* fs = P.fs_in_smem ? st : P.fs + (size_t)b * P.fs_stride;
+    double* Ct = fs;                               // NM x n  coordinate-major
+    double* M0 = Ct + (size_t)NM * n;              // p x p   Pi_0^{-T}
+    double* P00 = M0 + (size_t)pl * pl;            // p x p   Phi(S0, S0)
+    double* R = P00 + (size_t)pl * pl;             // p x p
+    double* Aq = R + (size_t)pl * pl;              // p x p   scratch (QR of Pi_0)
+    double* Qx = Aq + (size_t)pl * pl;             // p x p   scratch (explicit Q_0)
+    double* Tm = Qx + (size_t)pl * pl;             // p x p   scratch (R_0^{-1})
+    double* Bm = Tm + (size_t)pl * pl;             // pb x MM  b_eta = Phi(S0, eta)
+    double* Cm = Bm + (size_t)pb * MM;             // pb x MM  c_eta
+    double* Li = Cm + (size_t)pb * MM;             // packed lower triangle, row r at tri(r)
+
+    const int n_db = P.n_db[b];
+    const double* sites = P.sites + (size_t)b * P.db_stride * n;
+    const double* lb2 = P.lb2 + (size_t)b * n;
+    const double* ub2 = P.ub2 + (size_t)b * n;
+    const int* found = P.found + (size_t)b * P.found_stride;
+    const int nf_ids = P.n_found[b];
+    const int n_extra = P.n_extra ? P.n_extra[b] : 0;
+    const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
+    int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    const int N0 = nf_ids + n_extra;
+    const int max_points = P.max_points;
+    if (!(N0 < max_points) || N0 > NM) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = (N0 > NM) ? -1 : 0; } return; }
+    if (p > 0 && N0 != p) { if (tid == 0) P.n_r4[b] = -1; return; }         // literal kernel takes over
+
+    unsigned char* cand = P.cand + (size_t)b * P.db_stride;
+    for (int id = tid; id < n_db; id += nt) {
+        bool ok = in_box(sites + (size_t)id * n, lb2, ub2, n);
+        for (int f = 0; f < nf_ids && ok; ++f) ok = (found[f] != id + 1);
+        cand[id] = ok ? 1 : 0;
+    }
+    for (int e = tid; e < N0 * n; e += nt) {
+        int i = e / n, k = e % n;
+        Ct[(size_t)k * NM + i] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
+    }
+    if (tid == 0) red[76] = 0.0;
+    __syncthreads();
+    // The polynomial basis is centred at the first found point and scaled by the spread of S0: c_xi and the
+    // leverage behind g_hat are invariant under that change of basis, and Pi_0 stays well conditioned for tiny Delta.
+    double inv_s = 1.0;
+    if (p > 1) {
+        double mx = 0.0;
+        for (int e = tid; e < N0 * n; e += nt) { int i = e / n, k = e % n; mx = fmax(mx, fabs(Ct[(size_t)k * NM + i] - Ct[(size_t)k * NM])); }
+        mx = warp_max(mx);
+        if (lane == 0) red[40 + warp] = mx;
+        __syncthreads();
+        mx = 0.0;
+        for (int w = 0; w < nwarps; ++w) mx = fmax(mx, red[40 + w]);
+        inv_s = mx > 0.0 ? 1.0 / mx : 1.0;
+        __syncthreads();
+    }
+    if (p > 0) {
+        for (int e = tid; e < p * p; e += nt) {
+            int i = e % p, j = e / p;
+            double r2 = 0.0;
+            for (int k = 0; k < n; ++k) { double d = Ct[(size_t)k * NM + i] - Ct[(size_t)k * NM + j]; r2 = fma(d, d, r2); }
+            P00[i + (size_t)j * pl] = rad_phi(P.rf, r2);
+            Aq[i + (size_t)j * pl] = (j == 0) ? 1.0 : (Ct[(size_t)(j - 1) * NM + i] - Ct[(size_t)(j - 1) * NM]) * inv_s;
+            R[i + (size_t)j * pl] = 0.0;
+        }
+        __syncthreads();
+        // Householder QR of Pi_0 (same reflector conventions as the literal kernel / LAPACK geqr2)
+        for (int j = 0; j < p; ++j) {
+            double part = 0.0;
+            for (int i = j + 1 + tid; i < p; i += nt) { double a = Aq[i + (size_t)j * pl]; part = fma(a, a, part); }
+            double xn2 = block_sum(part, red);
+            if (tid == 0) {
+                double alpha = Aq[j + (size_t)j * pl], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
+                if (xnorm != 0.0 && j + 1 < p) { beta = -copysign(hypot(alpha, xnorm), alpha); tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta); }
+                tauq[j] = tau; red[70] = sc; red[71] = beta;
+            }
+            __syncthreads();
+            const double tau = tauq[j], sc = red[70];
+            for (int i = j + 1 + tid; i < p; i += nt) Aq[i + (size_t)j * pl] *= sc;
+            if (tid == 0) Aq[j + (size_t)j * pl] = red[71];
+            __syncthreads();
+            if (tau != 0.0)
+                for (int c = j + 1 + warp; c < p; c += nwarps) {
+                    double* col = Aq + (size_t)c * pl; const double* vj = Aq + (size_t)j * pl;
+                    double a = 0.0;
+                    for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
+                    a = (warp_sum(a) + col[j]) * tau;
+                    for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
+                    __syncwarp();
+                    if (lane == 0) col[j] -= a;
+                }
+            __syncthreads();
+        }
+        for (int e = tid; e < p * p; e += nt) { int r = e % p, c = e / p; if (r <= c) R[r + (size_t)c * pl] = Aq[r + (size_t)c * pl]; }
+        // explicit Q_0 (warp per column) and T = R_0^{-1} (thread per column)
+        for (int c = warp; c < p; c += nwarps) {
+            double* col = Qx + (size_t)c * pl;
+            for (int i = lane; i < p; i += 32) col[i] = (i == c) ? 1.0 : 0.0;
+            __syncwarp();
+            for (int j = p - 1; j >= 0; --j) {
+                const double tau = tauq[j];
+                if (tau == 0.0) continue;
+                const double* vj = Aq + (size_t)j * pl;
+                double a = 0.0;
+                for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
+                a = (warp_sum(a) + col[j]) * tau;
+                for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
+                __syncwarp();
+                if (lane == 0) col[j] -= a;
+                __syncwarp();
+            }
+        }
+        if (tid == 0) {                            // rank check of Pi_0
+            double mn = INFINITY, mx = 0.0;
+            for (int j = 0; j < p; ++j) { double a = fabs(Aq[j + (size_t)j * pl]); mn = fmin(mn, a); mx = fmax(mx, a); }
+            if (!(mn > 1e-10 * mx)) red[76] = 1.0;
+        }
+        __syncthreads();
+        if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
+        for (int j = tid; j < p; j += nt) {        // column j of R_0^{-1} by back substitution
+            double* x = Tm + (size_t)j * pl;
+            for (int i = j + 1; i < p; ++i) x[i] = 0.0;
+            x[j] = 1.0 / R[j + (size_t)j * pl];
+            for (int i = j - 1; i >= 0; --i) {
+                double a = 0.0;
+                for (int k = i + 1; k <= j; ++k) a = fma(R[i + (size_t)k * pl], x[k], a);
+                x[i] = -a / R[i + (size_t)i * pl];
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < p * p; e += nt) {    // M0 = Q_0 R_0^{-T}:  M0[r, c] = sum_k Q0[r, k] T[c, k]
+            int r = e % p, c = e / p;
+            double a = 0.0;
+            for (int k = c; k < p; ++k) a = fma(Qx[r + (size_t)k * pl], Tm[c + (size_t)k * pl], a);
+            M0[r + (size_t)c * pl] = a;
+        }
+        __syncthreads();
+        for (int e = tid; e < p * p; e += nt) {    // H = (Pi_0' Pi_0)^{-1} = M0' M0  (kept in R's slot)
+            int a_ = e % p, b_ = e / p;
+            double a = 0.0;
+            for (int r = 0; r < p; ++r) a = fma(M0[r + (size_t)a_ * pl], M0[r + (size_t)b_ * pl], a);
+            R[a_ + (size_t)b_ * pl] = a;
+        }
+        __syncthreads();
+    }
+    const double phi0 = rad_phi(P.rf, 0.0);
+    const double thr = P.chol_thr;
+    int N = N0, m = 0, nr4 = 0;
+
+    for (int id = 0; id < n_db && N < max_points && nr4 < P.r4_stride; ++id) {
+        if (!cand[id]) continue;
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) xi[k] = sites[(size_t)id * n + k];
+        __syncthreads();
+        if (warp == 0) {
+            // g_hat^2 = 1 / (1 + pi' (Pi' Pi)^{-1} pi): the product of the Givens cosines of utilities.jl:437-448 in
+            // closed form (leverage of the new row), so no sequential rotation sweep is needed per candidate
+            double part = 0.0;
+            for (int a_ = lane; a_ < p; a_ += 32) {
+                double h = R[a_];
+                for (int c = 1; c < p; ++c) h = fma(R[a_ + (size_t)c * pl], (xi[c - 1] - Ct[(size_t)(c - 1) * NM]) * inv_s, h);
+                rl[a_] = h;
+                part = fma(h, (a_ == 0) ? 1.0 : (xi[a_ - 1] - Ct[(size_t)(a_ - 1) * NM]) * inv_s, part);
+            }
+            part = warp_sum(part);
+            if (lane == 0) { red[72] = 1.0 / (1.0 + part); red[74] = 1.0 + part; }
+        } else if (warp == 1) {
+            // c_xi = Pi_0^{-T} pi_xi
+            for (int r = lane; r < p; r += 32) {
+                double a = M0[r];
+                for (int c = 1; c < p; ++c) a = fma(M0[r + (size_t)c * pl], (xi[c - 1] - Ct[(size_t)(c - 1) * NM]) * inv_s, a);
+                cvec[r] = a;
+            }
+        } else {
+            for (int i = tid - 64; i < N; i += nt - 64) {      // kernels(xi) against every current point
+                double r2 = 0.0;
+                for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[(size_t)k * NM + i]; r2 = fma(d, d, r2); }
+                phix[i] = rad_phi(P.rf, r2);
+            }
+        }
+        __syncthreads();
+        for (int r = tid; r < p; r += nt) {        // ub = b_xi - Phi00 c_xi
+            double a = 0.0;
+            for (int c = 0; c < p; ++c) a = fma(P00[r + (size_t)c * pl], cvec[c], a);
+            ub[r] = phix[r] - a;
+        }
+        __syncthreads();
+        const int base = (p > 0) ? p : N0;         // index of the first round-4 point among the centres
+        for (int e = tid; e < m; e += nt) {        // a[eta] = n_eta' Phi n_xi
+            const double* be = Bm + (size_t)e * pb; const double* ce = Cm + (size_t)e * pb;
+            double a0 = 0.0, a1 = 0.0;
+            for (int r = 0; r < p; ++r) { a0 = fma(be[r], cvec[r], a0); a1 = fma(ce[r], ub[r], a1); }
+            av[e] = phix[base + e] - a0 - a1;
+        }
+        if (warp == nwarps - 1) {                  // A_xixi = phi0 - c.b - c.ub
+            double a = 0.0;
+            for (int r = lane; r < p; r += 32) a = fma(cvec[r], phix[r] + ub[r], a);
+            a = warp_sum(a);
+            if (lane == 0) red[73] = phi0 - a;
+        }
+        __syncthreads();
+        double tn = 0.0;
+        for (int r = tid; r < m; r += nt) {        // t = L^{-1} a   (packed rows)
+            const double* lr = Li + tri(r);
+            double a0 = 0.0, a1 = 0.0;
+            int c = 0;
+            for (; c + 2 <= r + 1; c += 2) { a0 = fma(lr[c], av[c], a0); a1 = fma(lr[c + 1], av[c + 1], a1); }
+            for (; c <= r; ++c) a0 = fma(lr[c], av[c], a0);
+            const double a = a0 + a1;
+            tv[r] = a; tn = fma(a, a, tn);
+        }
+        tn = block_sum(tn, red);
+        const double gh2 = red[72];
+        const double d2 = red[73] - tn;
+        const double tau2 = gh2 * d2;              // == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
+        if (!(tau2 > thr)) continue;               // RbfModel.jl:452
+        // ---- accept
+        const double dd = sqrt(d2);
+        for (int c = tid; c < m; c += nt) {        // new row of L^{-1}: -(t' L^{-1}) / d
+            double a0 = 0.0, a1 = 0.0;
+            int r = c;
+            for (; r + 2 <= m; r += 2) { a0 = fma(tv[r], Li[tri(r) + c], a0); a1 = fma(tv[r + 1], Li[tri(r + 1) + c], a1); }
+            for (; r < m; ++r) a0 = fma(tv[r], Li[tri(r) + c], a0);
+            av[c] = -(a0 + a1) / dd;               // av is free now
+        }
+        {                                          // Sherman-Morrison: H <- H - (H pi)(H pi)' / (1 + pi' H pi)
+            const double inv1 = 1.0 / red[74];
+            for (int e = tid; e < p * p; e += nt) { int a_ = e % p, b_ = e / p; R[a_ + (size_t)b_ * pl] = fma(-rl[a_] * inv1, rl[b_], R[a_ + (size_t)b_ * pl]); }
+        }
+        for (int r = tid; r < p; r += nt) { Bm[(size_t)m * pb + r] = phix[r]; Cm[(size_t)m * pb + r] = cvec[r]; }
+        for (int k = tid; k < n; k += nt) Ct[(size_t)k * NM + N] = xi[k];
+        if (tid == 0) r4[nr4] = id + 1;
+        __syncthreads();
+        for (int c = tid; c < m; c += nt) Li[tri(m) + c] = av[c];
+        if (tid == 0) Li[tri(m) + m] = 1.0 / dd;
+        N += 1; m += 1; nr4 += 1;
+    }
+    __syncthreads();
+    if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
+}
+
+size_t round4_fast_vec_doubles(int n, int NM, int p) {
+    int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
+    return (size_t)n + NM + 2 * (size_t)MM + 6 * (size_t)pl + 80;
+}
+size_t round4_fast_state_doubles(int n, int NM, int p) {
+    int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
+    return (size_t)NM * n + 6 * (size_t)pl * pl + 2 * (size_t)pb * MM + (size_t)MM * (MM + 1) / 2 + 8;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Training-set gather (_collect_indices order: centre, r1, r2, r3, r4), RbfModel.jl:178-186, 754-757
 // ------------------------------------------------------------------------------------------------
@@ -615,10 +901,16 @@ cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStre
     select_rounds123_kernel<<<P.B, 256, smem, s>>>(P);
     return cudaGetLastError();
 }
-cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s) {
+cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid) {
     cudaError_t e = cudaFuncSetAttribute(round4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    round4_kernel<<<P.B, 256, smem, s>>>(P);
+    round4_kernel<<<grid, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(round4_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    round4_fast_kernel<<<P.B, 256, smem, s>>>(P);
     return cudaGetLastError();
 }
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s) {

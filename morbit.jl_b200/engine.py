@@ -120,7 +120,7 @@ class Engine:
     def profile_read(self) -> dict:
         ms = (C.c_double * 8)()
         self._check(self.lib.mrbf_profile_read(self.ctx, ms))
-        return dict(rounds123=ms[0], round4=ms[1], gather=ms[2], build=ms[3], eval=ms[4])
+        return dict(rounds123=ms[0], round4=ms[1], gather=ms[2], build=ms[3], eval=ms[4], round4_fallback=ms[5])
 
     @property
     def launch_count(self) -> int:
