@@ -280,17 +280,20 @@ int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_
     S.flags_in = flags_in; S.max_new = max_new;
     S.r1 = r1; S.n_r1 = n_r1; S.r2 = r2; S.n_r2 = n_r2; S.r3_sites = r3_sites; S.n_r3 = n_r3; S.dirs = dirs; S.n_dirs = n_dirs;
     S.flags_out = flags_out;
-    const size_t seeds = (size_t)B * db_stride * n * sizeof(double);
+    const int ldz = n | 1;
+    S.wz_in_smem = select_smem_bytes(n, true, 0) <= SMEM_LIMIT;
+    // shifted seeds + projections (2 x n x db_stride doubles) stay in shared memory when two CTAs still fit per SM
+    const int st_doubles = 2 * n * db_stride;
+    S.st_in_smem = S.wz_in_smem && select_smem_bytes(n, true, st_doubles) <= 110 * 1024;
+    const size_t seeds = S.st_in_smem ? 16 : (size_t)B * db_stride * n * sizeof(double);
     ENSURE(ctx->ws[0], seeds); ENSURE(ctx->ws[1], seeds); ENSURE(ctx->ws[2], (size_t)B * db_stride);
     S.S = (double*)ctx->ws[0].p; S.T = (double*)ctx->ws[1].p; S.cflags = (unsigned char*)ctx->ws[2].p;
-    const int ldz = n | 1;
-    S.wz_in_smem = select_smem_bytes(n, true) <= SMEM_LIMIT;
     if (!S.wz_in_smem) { ENSURE(ctx->ws[3], (size_t)B * 2 * n * ldz * sizeof(double)); S.WZ = (double*)ctx->ws[3].p; }
     ENSURE(ctx->ws[4], (size_t)B * n * 2 * sizeof(double));
     S.lb2 = (double*)ctx->ws[4].p; S.ub2 = S.lb2 + (size_t)B * n;
     ENSURE(ctx->ws[5], ((size_t)B * S.found_stride + B) * sizeof(int));
     S.found = (int*)ctx->ws[5].p; S.n_found = S.found + (size_t)B * S.found_stride;
-    { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem), ctx->stream)); }
+    { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem, S.st_in_smem ? st_doubles : 0), ctx->stream)); }
     ctx->launches += 1;
     if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
         rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,
@@ -437,13 +440,17 @@ int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int
     Pb.B = B; Pb.n = n; Pb.k = k; Pb.train_stride = train_stride; Pb.p = p; Pb.deg = deg;
     Pb.kernel = rf.kernel; Pb.ibeta = rf.ibeta; Pb.sgn = rf.sgn; Pb.alpha_default = alpha;
     Pb.N = N; Pb.sites = sites; Pb.values = values; Pb.shape = shape;
-    Pb.w = m->w; Pb.lam = m->lam; Pb.alpha2_out = m->alpha2; Pb.status = status; Pb.ld = train_stride;
+    Pb.w = m->w; Pb.lam = m->lam; Pb.alpha2_out = m->alpha2; Pb.status = status; Pb.ld = train_stride | 1;
     const size_t vecd = build_vec_doubles(n, k, Pb.ld, p), wsd = build_ws_doubles(n, k, Pb.ld, p);
     size_t smem = vecd * sizeof(double);
-    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) { Pb.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); }
+    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) { Pb.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); Pb.smem_ws_doubles = (int)wsd; }
     else {
+        // worst case does not fit: give every CTA the whole shared memory; instances whose own N fits use it,
+        // the rest fall back to the global workspace
         if (smem > SMEM_LIMIT) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_EUNSUPPORTED, "training set too large%s"); }
         Pb.ws_in_smem = 0; Pb.ws_stride = wsd;
+        smem = SMEM_LIMIT;
+        Pb.smem_ws_doubles = (int)(SMEM_LIMIT / sizeof(double) - vecd);
         int r_ = ensure(ctx, ctx->ws[8], (size_t)B * wsd * sizeof(double));
         if (r_ != MRBF_OK) { mrbf_free_model(ctx, m); return r_; }
         Pb.ws = (double*)ctx->ws[8].p;

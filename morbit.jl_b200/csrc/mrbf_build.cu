@@ -76,19 +76,22 @@ __device__ void chol_solve(const double* A, int ld, int off, int m, double* Yv, 
 
 __global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
     extern __shared__ double smem[];
-    const int b = blockIdx.x, n = P.n, k = P.k, p = P.p, ld = P.ld;
+    const int b = blockIdx.x, n = P.n, k = P.k, p = P.p;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int pl = p > 0 ? p : 1;
-    double* v = smem;                // ld
-    double* pv = v + ld;             // ld
-    double* tauv = pv + ld;          // pl
+    const int N = P.N[b];
+    // per-instance leading dimension: the system lives in shared memory whenever THIS instance fits
+    const int ld = (N > 0 && N <= P.train_stride) ? (N | 1) : 1;
+    double* v = smem;                // P.ld
+    double* pv = v + P.ld;           // P.ld
+    double* tauv = pv + P.ld;        // pl
     double* red = tauv + pl;         // 80
     double* mats = red + 80;
-    double* ws = P.ws_in_smem ? mats : P.ws + (size_t)b * P.ws_stride;
+    const bool in_smem = P.ws_in_smem || ((size_t)ld * ld + (size_t)ld * (pl + k) <= (size_t)P.smem_ws_doubles);
+    double* ws = in_smem ? mats : P.ws + (size_t)b * P.ws_stride;
     double* A = ws;                              // ld x ld
     double* Pm = A + (size_t)ld * ld;            // ld x pl
     double* Yv = Pm + (size_t)ld * pl;           // ld x k
-    const int N = P.N[b];
     double* w_out = P.w + (size_t)b * P.train_stride * k;
     double* lam_out = P.lam + (size_t)b * pl * k;
     if (N <= 0 || N > P.train_stride) { if (tid == 0) P.status[b] = -1; return; }

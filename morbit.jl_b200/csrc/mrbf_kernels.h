@@ -22,7 +22,7 @@ struct SelectParams {
     const double* glb; const double* gub; const int* flags_in; const int* max_new;
     int* r1; int* n_r1; int* r2; int* n_r2; double* r3_sites; int* n_r3; double* dirs; int* n_dirs; int* flags_out;
     // workspace / hand-over to round 4
-    double* S; double* T; unsigned char* cflags; double* WZ; int wz_in_smem;
+    double* S; double* T; unsigned char* cflags; double* WZ; int wz_in_smem; int st_in_smem;
     double* lb2; double* ub2; int* found; int* n_found;
 };
 
@@ -55,7 +55,7 @@ struct BuildParams {
     double alpha_default;
     const int* N; const double* sites; const double* values; const double* shape;
     double* w; double* lam; double* alpha2_out; int* status;
-    double* ws; size_t ws_stride; int ws_in_smem; int ld;
+    double* ws; size_t ws_stride; int ws_in_smem; int ld; int smem_ws_doubles;
 };
 
 struct EvalParams {
@@ -76,7 +76,7 @@ struct BacktrackParams {
     int* step_index; double* sigma; double* x_plus; double* mx; double* mx_plus;
 };
 
-size_t select_smem_bytes(int n, bool wz_in_smem);
+size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles);
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
 size_t round4_fast_vec_doubles(int n, int NM, int p);

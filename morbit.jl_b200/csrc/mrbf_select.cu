@@ -73,8 +73,8 @@ struct FilterState {
 
 // One run of the affinely-independent filter over the candidates with (cflags & want) == want and
 // !(cflags & (CF_USED | avoid)).  Picks are appended to out[]; returns their number.
-__device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_db x n */, double* T, unsigned char* cflags,
-                          int n_db, unsigned want, unsigned avoid, double piv, int n_wanted, int* out) {
+__device__ __forceinline__ int filter_run(FilterState& st, const double* S /* shifted seeds, coordinate-major: S[i*ldS + id] */, double* T,
+                          int ldS, unsigned char* cflags, int n_db, unsigned want, unsigned avoid, double piv, int n_wanted, int* out) {
     const int n = st.n, ldz = st.ldz, tid = threadIdx.x, nt = blockDim.x;
     int found = 0;
     // first pick: argmax ||s||_inf, first maximiser, unconditional (AffinelyIndependentPoints.jl:51-69)
@@ -82,9 +82,9 @@ __device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_d
     for (int id = tid; id < n_db; id += nt) {
         unsigned f = cflags[id];
         if ((f & want) != want || (f & (CF_USED | avoid))) continue;
-        const double* s = S + (size_t)id * n;
+        const double* s = S + id;
         double v = 0.0;
-        for (int i = 0; i < n; ++i) v = fmax(v, fabs(s[i]));
+        for (int i = 0; i < n; ++i) v = fmax(v, fabs(s[i * ldS]));
         ArgMax c; c.v = v; c.id = id;
         mine = better(mine, c);
     }
@@ -92,12 +92,12 @@ __device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_d
     if (best.id < 0) return 0;
     for (;;) {
         // ---- accept best.id: Y <- [Y s], update W (one Householder reflector) and Z
-        const double* y = S + (size_t)best.id * n;
+        const double* y = S + best.id;
         const int nw = n - st.jY;                 // columns of W before the update
         for (int c = tid; c < nw; c += nt) {      // xp = W' y
             double a = 0.0;
-            const double* wc = st.W + (size_t)c * ldz;
-            for (int i = 0; i < n; ++i) a = fma(wc[i], y[i], a);
+            const double* wc = st.W + c * ldz;
+            for (int i = 0; i < n; ++i) a = fma(wc[i], y[i * ldS], a);
             st.xp[c] = a;
         }
         __syncthreads();
@@ -122,19 +122,19 @@ __device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_d
         const double tau = st.red[70];
         for (int i = tid; i < n; i += nt) {       // u = W v ; then W'[:, c-1] = W[:, c] - tau v_c u  (row-private)
             double a = 0.0;
-            for (int c = 0; c < nw; ++c) a = fma(st.W[i + (size_t)c * ldz], st.vv[c], a);
+            for (int c = 0; c < nw; ++c) a = fma(st.W[i + c * ldz], st.vv[c], a);
             a *= tau;
-            for (int c = 1; c < nw; ++c) st.W[i + (size_t)(c - 1) * ldz] = fma(-a, st.vv[c], st.W[i + (size_t)c * ldz]);
+            for (int c = 1; c < nw; ++c) st.W[i + (c - 1) * ldz] = fma(-a, st.vv[c], st.W[i + c * ldz]);
         }
         st.jY += 1;
         found += 1;
         __syncthreads();
         const int zc = n - st.jY;
         for (int c = tid; c < zc; c += nt) {      // Z = W ./ colmax|W|  (AffinelyIndependentPoints.jl:8)
-            const double* wc = st.W + (size_t)c * ldz;
+            const double* wc = st.W + c * ldz;
             double mx = 0.0;
             for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(wc[i]));
-            double* zcol = st.Z + (size_t)c * ldz;
+            double* zcol = st.Z + c * ldz;
             for (int i = 0; i < n; ++i) zcol[i] = wc[i] / mx;
         }
         __syncthreads();
@@ -144,38 +144,38 @@ __device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_d
         for (int id = tid; id < n_db; id += nt) {
             unsigned f = cflags[id];
             if ((f & want) != want || (f & (CF_USED | avoid))) continue;
-            const double* s = S + (size_t)id * n;
-            double* t = T + (size_t)id * n;
+            const double* s = S + id;
+            double* t = T + id;
             double v = 0.0;
             int c = 0;
             for (; c + 4 <= zc; c += 4) {         // t = Z' s, four independent chains
-                const double* z0 = st.Z + (size_t)c * ldz; const double* z1 = z0 + ldz;
+                const double* z0 = st.Z + c * ldz; const double* z1 = z0 + ldz;
                 const double* z2 = z1 + ldz; const double* z3 = z2 + ldz;
                 double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
                 for (int i = 0; i < n; ++i) {
-                    double si = s[i];
+                    double si = s[i * ldS];
                     a0 = fma(z0[i], si, a0); a1 = fma(z1[i], si, a1); a2 = fma(z2[i], si, a2); a3 = fma(z3[i], si, a3);
                 }
-                t[c] = a0; t[c + 1] = a1; t[c + 2] = a2; t[c + 3] = a3;
+                t[c * ldS] = a0; t[(c + 1) * ldS] = a1; t[(c + 2) * ldS] = a2; t[(c + 3) * ldS] = a3;
             }
             for (; c < zc; ++c) {
-                const double* z0 = st.Z + (size_t)c * ldz;
+                const double* z0 = st.Z + c * ldz;
                 double a0 = 0;
-                for (int i = 0; i < n; ++i) a0 = fma(z0[i], s[i], a0);
-                t[c] = a0;
+                for (int i = 0; i < n; ++i) a0 = fma(z0[i], s[i * ldS], a0);
+                t[c * ldS] = a0;
             }
             int i = 0;
             for (; i + 4 <= n; i += 4) {          // r = Z t, inf-norm
                 double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
                 for (int q = 0; q < zc; ++q) {
-                    const double* zq = st.Z + (size_t)q * ldz + i; double tq = t[q];
+                    const double* zq = st.Z + q * ldz + i; double tq = t[q * ldS];
                     a0 = fma(zq[0], tq, a0); a1 = fma(zq[1], tq, a1); a2 = fma(zq[2], tq, a2); a3 = fma(zq[3], tq, a3);
                 }
                 v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
             }
             for (; i < n; ++i) {
                 double a0 = 0;
-                for (int q = 0; q < zc; ++q) a0 = fma(st.Z[i + (size_t)q * ldz], t[q], a0);
+                for (int q = 0; q < zc; ++q) a0 = fma(st.Z[i + q * ldz], t[q * ldS], a0);
                 v = fmax(v, fabs(a0));
             }
             ArgMax cnd; cnd.v = v; cnd.id = id;
@@ -188,6 +188,7 @@ __device__ int filter_run(FilterState& st, const double* S /* shifted seeds, n_d
     return found;
 }
 
+template <bool WZS, bool STS>   // W/Z in shared memory; seeds/projections in shared memory (fixes the address space at compile time)
 __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x;
@@ -199,12 +200,14 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
     int* redi = (int*)(red + 80);                // 40 ints = 20 doubles
     int* ctl = redi + 40;                        // 8 ints control
     double* wz = red + 80 + 24;
-    double* W = P.wz_in_smem ? wz : P.WZ + (size_t)b * 2 * n * ldz;
-    double* Z = W + (size_t)n * ldz;
+    double* W; double* S; double* T;
+    const int ldS = P.db_stride;
+    if constexpr (WZS) W = wz; else W = P.WZ + (size_t)b * 2 * n * ldz;
+    double* Z = W + n * ldz;
+    if constexpr (STS) { S = wz + 2 * n * ldz; T = S + n * ldS; }                              // coordinate-major seeds
+    else { S = P.S + (size_t)b * P.db_stride * n; T = P.T + (size_t)b * P.db_stride * n; }
     const int n_db = P.n_db[b];
     const double* sites = P.sites + (size_t)b * P.db_stride * n;
-    double* S = P.S + (size_t)b * P.db_stride * n;
-    double* T = P.T + (size_t)b * P.db_stride * n;
     unsigned char* cflags = P.cflags + (size_t)b * P.db_stride;
     const int x_index = P.x_index[b] - 1;
     const double delta = P.delta[b];
@@ -231,8 +234,7 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
             if (in_box(s, lb2, ub2, n)) f |= CF_BOX2;
         }
         cflags[id] = (unsigned char)f;
-        double* sh = S + (size_t)id * n;
-        for (int i = 0; i < n; ++i) sh[i] = s[i] - x[i];
+        for (int i = 0; i < n; ++i) S[i * ldS + id] = s[i] - x[i];
     }
     for (int i = tid; i < n; i += nt) { P.lb2[(size_t)b * n + i] = lb2[i]; P.ub2[(size_t)b * n + i] = ub2[i]; }
 
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
     bool fully_linear;
     for (;;) {   // at most two passes: the second is the coordinate rebuild (RbfModel.jl:634-637)
         __syncthreads();
-        for (int e = tid; e < n * n; e += nt) { int i = e % n, c = e / n; W[i + (size_t)c * ldz] = (i == c) ? 1.0 : 0.0; Z[i + (size_t)c * ldz] = (i == c) ? 1.0 : 0.0; }
+        for (int e = tid; e < n * n; e += nt) { int i = e % n, c = e / n; W[i + c * ldz] = (i == c) ? 1.0 : 0.0; Z[i + c * ldz] = (i == c) ? 1.0 : 0.0; }
         for (int id = tid; id < n_db; id += nt) cflags[id] &= (unsigned char)~CF_USED;
         __syncthreads();
         st.jY = 0; n_r1 = n_r2 = n_r3 = 0; fully_linear = false;
@@ -253,9 +255,9 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
             for (int e = tid; e < n * n; e += nt) dirs[e] = ((e % n) == (e / n)) ? 1.0 : 0.0;
             n_dirs = n;
         } else {
-            n_r1 = filter_run(st, S, T, cflags, n_db, CF_BOX1, 0, piv, n, r1);
+            n_r1 = filter_run(st, S, T, ldS, cflags, n_db, CF_BOX1, 0, piv, n, r1);
             const int zc = n - st.jY;            // improving directions = reverse(eachcol(Z)), RbfModel.jl:232
-            for (int e = tid; e < n * zc; e += nt) { int i = e % n, c = e / n; dirs[i + (size_t)c * n] = Z[i + (size_t)(zc - 1 - c) * ldz]; }
+            for (int e = tid; e < n * zc; e += nt) { int i = e % n, c = e / n; dirs[i + (size_t)c * n] = Z[i + (zc - 1 - c) * ldz]; }
             n_dirs = zc;
         }
         int n_missing = n - n_r1;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
         if (n_missing == 0 || skip_search || ensure_fl || (approx && P.cfg.theta_enlarge_1 == P.cfg.theta_enlarge_2)) {
             fully_linear = true;                 // RbfModel.jl:588-591
         } else {                                 // round 2: box 2, excluding every round-1 candidate
-            n_r2 = filter_run(st, S, T, cflags, n_db, CF_BOX2, CF_BOX1, piv, n_missing, r2);
+            n_r2 = filter_run(st, S, T, ldS, cflags, n_db, CF_BOX2, CF_BOX1, piv, n_missing, r2);
         }
         n_missing -= n_r2;
         bool failed = false;
@@ -586,40 +588,41 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
 // triangular mat-vec in shared memory.  Instances that do not qualify (N0 != p, rank-deficient Pi_0) are
 // marked n_r4 = -1 and handled by the literal kernel above.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ size_t tri(int r) { return (size_t)r * (r + 1) / 2; }
+__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
+template <bool SMEM>
 __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
     extern __shared__ double smem[];
-    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = 256, lane = tid & 31, warp = tid >> 5, nwarps = 8;
     const int NM = P.NM;
     const int deg = P.cfg.polynomial_degree;
     const int p = poly_dim(n, deg);
     const int pl = p > 0 ? p : 1, pb = pl | 1;
     const int MM = (NM - p) > 1 ? (NM - p) : 1;
     // shared vectors
-    double* xi = smem;                 // n
-    double* phix = xi + n;             // NM
+    double* xi0 = smem;                // n   candidate site, double buffered
+    double* xi1 = xi0 + n;             // n
+    double* phix = xi1 + n;            // NM
     double* av = phix + NM;            // MM
     double* tv = av + MM;              // MM
     double* cvec = tv + MM;            // pl
     double* ub = cvec + pl;            // pl
-    double* cs = ub + pl;              // pl
-    double* sn = cs + pl;              // pl
-    double* rl = sn + pl;              // pl
-    double* tauq = rl + pl;            // pl
+    double* hv = ub + pl;              // pl
+    double* tauq = hv + pl;            // pl
     double* red = tauq + pl;           // 80
     double* st = red + 80;
-    double* fs = P.fs_in_smem ? st : P.fs + (size_t)b * P.fs_stride;
-    double* Ct = fs;                               // NM x n  coordinate-major
-    double* M0 = Ct + (size_t)NM * n;              // p x p   Pi_0^{-T}
-    double* P00 = M0 + (size_t)pl * pl;            // p x p   Phi(S0, S0)
-    double* R = P00 + (size_t)pl * pl;             // p x p
-    double* Aq = R + (size_t)pl * pl;              // p x p   scratch (QR of Pi_0)
-    double* Qx = Aq + (size_t)pl * pl;             // p x p   scratch (explicit Q_0)
-    double* Tm = Qx + (size_t)pl * pl;             // p x p   scratch (R_0^{-1})
-    double* Bm = Tm + (size_t)pl * pl;             // pb x MM  b_eta = Phi(S0, eta)
-    double* Cm = Bm + (size_t)pb * MM;             // pb x MM  c_eta
-    double* Li = Cm + (size_t)pb * MM;             // packed lower triangle, row r at tri(r)
+    double* fs;
+    if constexpr (SMEM) fs = st; else fs = P.fs + (size_t)b * P.fs_stride;
+    double* Ct = fs;                   // NM x n  coordinate-major centres
+    double* M0 = Ct + NM * n;          // p x p   Pi_0^{-T}
+    double* P00 = M0 + pl * pl;        // p x p   Phi(S0, S0)
+    double* H = P00 + pl * pl;         // p x p   (Pi' Pi)^{-1} of the current point set
+    double* Aq = H + pl * pl;          // p x p   scratch (QR of Pi_0)
+    double* Qx = Aq + pl * pl;         // p x p   scratch (explicit Q_0)
+    double* Tm = Qx + pl * pl;         // p x p   scratch (R_0^{-1})
+    double* Gm = Tm + pl * pl;         // pb x MM  g_eta = Phi(S0, eta) - Phi00 c_eta
+    double* Cm = Gm + pb * MM;         // pb x MM  c_eta
+    double* Li = Cm + pb * MM;         // packed lower triangle of L^{-1}, row r at tri(r)
 
     const int n_db = P.n_db[b];
     const double* sites = P.sites + (size_t)b * P.db_stride * n;
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
     }
     for (int e = tid; e < N0 * n; e += nt) {
         int i = e / n, k = e % n;
-        Ct[(size_t)k * NM + i] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
+        Ct[k * NM + i] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
     }
     if (tid == 0) red[76] = 0.0;
     __syncthreads();
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
     double inv_s = 1.0;
     if (p > 1) {
         double mx = 0.0;
-        for (int e = tid; e < N0 * n; e += nt) { int i = e / n, k = e % n; mx = fmax(mx, fabs(Ct[(size_t)k * NM + i] - Ct[(size_t)k * NM])); }
+        for (int e = tid; e < N0 * n; e += nt) { int i = e / n, k = e % n; mx = fmax(mx, fabs(Ct[k * NM + i] - Ct[k * NM])); }
         mx = warp_max(mx);
         if (lane == 0) red[40 + warp] = mx;
         __syncthreads();
@@ -665,30 +668,29 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
         for (int e = tid; e < p * p; e += nt) {
             int i = e % p, j = e / p;
             double r2 = 0.0;
-            for (int k = 0; k < n; ++k) { double d = Ct[(size_t)k * NM + i] - Ct[(size_t)k * NM + j]; r2 = fma(d, d, r2); }
-            P00[i + (size_t)j * pl] = rad_phi(P.rf, r2);
-            Aq[i + (size_t)j * pl] = (j == 0) ? 1.0 : (Ct[(size_t)(j - 1) * NM + i] - Ct[(size_t)(j - 1) * NM]) * inv_s;
-            R[i + (size_t)j * pl] = 0.0;
+            for (int k = 0; k < n; ++k) { double d = Ct[k * NM + i] - Ct[k * NM + j]; r2 = fma(d, d, r2); }
+            P00[i + j * pl] = rad_phi(P.rf, r2);
+            Aq[i + j * pl] = (j == 0) ? 1.0 : (Ct[(j - 1) * NM + i] - Ct[(j - 1) * NM]) * inv_s;
         }
         __syncthreads();
         // Householder QR of Pi_0 (same reflector conventions as the literal kernel / LAPACK geqr2)
         for (int j = 0; j < p; ++j) {
             double part = 0.0;
-            for (int i = j + 1 + tid; i < p; i += nt) { double a = Aq[i + (size_t)j * pl]; part = fma(a, a, part); }
+            for (int i = j + 1 + tid; i < p; i += nt) { double a = Aq[i + j * pl]; part = fma(a, a, part); }
             double xn2 = block_sum(part, red);
             if (tid == 0) {
-                double alpha = Aq[j + (size_t)j * pl], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
+                double alpha = Aq[j + j * pl], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
                 if (xnorm != 0.0 && j + 1 < p) { beta = -copysign(hypot(alpha, xnorm), alpha); tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta); }
                 tauq[j] = tau; red[70] = sc; red[71] = beta;
             }
             __syncthreads();
             const double tau = tauq[j], sc = red[70];
-            for (int i = j + 1 + tid; i < p; i += nt) Aq[i + (size_t)j * pl] *= sc;
-            if (tid == 0) Aq[j + (size_t)j * pl] = red[71];
+            for (int i = j + 1 + tid; i < p; i += nt) Aq[i + j * pl] *= sc;
+            if (tid == 0) Aq[j + j * pl] = red[71];
             __syncthreads();
             if (tau != 0.0)
                 for (int c = j + 1 + warp; c < p; c += nwarps) {
-                    double* col = Aq + (size_t)c * pl; const double* vj = Aq + (size_t)j * pl;
+                    double* col = Aq + c * pl; const double* vj = Aq + j * pl;
                     double a = 0.0;
                     for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
                     a = (warp_sum(a) + col[j]) * tau;
@@ -698,16 +700,15 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
                 }
             __syncthreads();
         }
-        for (int e = tid; e < p * p; e += nt) { int r = e % p, c = e / p; if (r <= c) R[r + (size_t)c * pl] = Aq[r + (size_t)c * pl]; }
-        // explicit Q_0 (warp per column) and T = R_0^{-1} (thread per column)
+        // explicit Q_0 (warp per column); T = R_0^{-1} (thread per column) after the rank check
         for (int c = warp; c < p; c += nwarps) {
-            double* col = Qx + (size_t)c * pl;
+            double* col = Qx + c * pl;
             for (int i = lane; i < p; i += 32) col[i] = (i == c) ? 1.0 : 0.0;
             __syncwarp();
             for (int j = p - 1; j >= 0; --j) {
                 const double tau = tauq[j];
                 if (tau == 0.0) continue;
-                const double* vj = Aq + (size_t)j * pl;
+                const double* vj = Aq + j * pl;
                 double a = 0.0;
                 for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
                 a = (warp_sum(a) + col[j]) * tau;
@@ -719,136 +720,150 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
         }
         if (tid == 0) {                            // rank check of Pi_0
             double mn = INFINITY, mx = 0.0;
-            for (int j = 0; j < p; ++j) { double a = fabs(Aq[j + (size_t)j * pl]); mn = fmin(mn, a); mx = fmax(mx, a); }
+            for (int j = 0; j < p; ++j) { double a = fabs(Aq[j + j * pl]); mn = fmin(mn, a); mx = fmax(mx, a); }
             if (!(mn > 1e-10 * mx)) red[76] = 1.0;
         }
         __syncthreads();
         if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
-        for (int j = tid; j < p; j += nt) {        // column j of R_0^{-1} by back substitution
-            double* x = Tm + (size_t)j * pl;
+        for (int j = tid; j < p; j += nt) {        // column j of R_0^{-1} by back substitution (R_0 = upper part of Aq)
+            double* x = Tm + j * pl;
             for (int i = j + 1; i < p; ++i) x[i] = 0.0;
-            x[j] = 1.0 / R[j + (size_t)j * pl];
+            x[j] = 1.0 / Aq[j + j * pl];
             for (int i = j - 1; i >= 0; --i) {
                 double a = 0.0;
-                for (int k = i + 1; k <= j; ++k) a = fma(R[i + (size_t)k * pl], x[k], a);
-                x[i] = -a / R[i + (size_t)i * pl];
+                for (int k = i + 1; k <= j; ++k) a = fma(Aq[i + k * pl], x[k], a);
+                x[i] = -a / Aq[i + i * pl];
             }
         }
         __syncthreads();
         for (int e = tid; e < p * p; e += nt) {    // M0 = Q_0 R_0^{-T}:  M0[r, c] = sum_k Q0[r, k] T[c, k]
             int r = e % p, c = e / p;
             double a = 0.0;
-            for (int k = c; k < p; ++k) a = fma(Qx[r + (size_t)k * pl], Tm[c + (size_t)k * pl], a);
-            M0[r + (size_t)c * pl] = a;
+            for (int k = c; k < p; ++k) a = fma(Qx[r + k * pl], Tm[c + k * pl], a);
+            M0[r + c * pl] = a;
         }
         __syncthreads();
-        for (int e = tid; e < p * p; e += nt) {    // H = (Pi_0' Pi_0)^{-1} = M0' M0  (kept in R's slot)
+        for (int e = tid; e < p * p; e += nt) {    // H = (Pi_0' Pi_0)^{-1} = M0' M0
             int a_ = e % p, b_ = e / p;
             double a = 0.0;
-            for (int r = 0; r < p; ++r) a = fma(M0[r + (size_t)a_ * pl], M0[r + (size_t)b_ * pl], a);
-            R[a_ + (size_t)b_ * pl] = a;
+            for (int r = 0; r < p; ++r) a = fma(M0[r + a_ * pl], M0[r + b_ * pl], a);
+            H[a_ + b_ * pl] = a;
         }
-        __syncthreads();
     }
     const double phi0 = rad_phi(P.rf, 0.0);
     const double thr = P.chol_thr;
+    const int base = (p > 0) ? p : N0;             // index of the first round-4 point among the centres
     int N = N0, m = 0, nr4 = 0;
 
-    for (int id = 0; id < n_db && N < max_points && nr4 < P.r4_stride; ++id) {
-        if (!cand[id]) continue;
-        __syncthreads();
-        for (int k = tid; k < n; k += nt) xi[k] = sites[(size_t)id * n + k];
-        __syncthreads();
+    // candidate stream with one-ahead prefetch of the site (hides the global-memory latency of the next candidate)
+    int id = 0;
+    while (id < n_db && !cand[id]) ++id;
+    for (int k = tid; k < n; k += nt) if (id < n_db) xi0[k] = sites[(size_t)id * n + k];
+    int buf = 0;
+    __syncthreads();
+    while (id < n_db && N < max_points && nr4 < P.r4_stride) {
+        const double* xi = buf ? xi1 : xi0;
+        double* xin = buf ? xi0 : xi1;
+        int nxt = id + 1;
+        while (nxt < n_db && !cand[nxt]) ++nxt;
+        // ---- phase 1: leverage (warp 0) | Lagrange coefficients (warp 1) | kernel column (warps 2..7, + prefetch)
         if (warp == 0) {
             // g_hat^2 = 1 / (1 + pi' (Pi' Pi)^{-1} pi): the product of the Givens cosines of utilities.jl:437-448 in
             // closed form (leverage of the new row), so no sequential rotation sweep is needed per candidate
             double part = 0.0;
             for (int a_ = lane; a_ < p; a_ += 32) {
-                double h = R[a_];
-                for (int c = 1; c < p; ++c) h = fma(R[a_ + (size_t)c * pl], (xi[c - 1] - Ct[(size_t)(c - 1) * NM]) * inv_s, h);
-                rl[a_] = h;
-                part = fma(h, (a_ == 0) ? 1.0 : (xi[a_ - 1] - Ct[(size_t)(a_ - 1) * NM]) * inv_s, part);
+                double h = H[a_];
+                for (int c = 1; c < p; ++c) h = fma(H[a_ + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, h);
+                hv[a_] = h;
+                part = fma(h, (a_ == 0) ? 1.0 : (xi[a_ - 1] - Ct[(a_ - 1) * NM]) * inv_s, part);
             }
             part = warp_sum(part);
             if (lane == 0) { red[72] = 1.0 / (1.0 + part); red[74] = 1.0 + part; }
         } else if (warp == 1) {
-            // c_xi = Pi_0^{-T} pi_xi
-            for (int r = lane; r < p; r += 32) {
+            for (int r = lane; r < p; r += 32) {   // c_xi = Pi_0^{-T} pi_xi
                 double a = M0[r];
-                for (int c = 1; c < p; ++c) a = fma(M0[r + (size_t)c * pl], (xi[c - 1] - Ct[(size_t)(c - 1) * NM]) * inv_s, a);
+                for (int c = 1; c < p; ++c) a = fma(M0[r + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, a);
                 cvec[r] = a;
             }
         } else {
+            if (warp == 2 && nxt < n_db) for (int k = lane; k < n; k += 32) xin[k] = sites[(size_t)nxt * n + k];
             for (int i = tid - 64; i < N; i += nt - 64) {      // kernels(xi) against every current point
                 double r2 = 0.0;
-                for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[(size_t)k * NM + i]; r2 = fma(d, d, r2); }
+                for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[k * NM + i]; r2 = fma(d, d, r2); }
                 phix[i] = rad_phi(P.rf, r2);
             }
         }
         __syncthreads();
-        for (int r = tid; r < p; r += nt) {        // ub = b_xi - Phi00 c_xi
-            double a = 0.0;
-            for (int c = 0; c < p; ++c) a = fma(P00[r + (size_t)c * pl], cvec[c], a);
-            ub[r] = phix[r] - a;
+        // ---- phase 2: a[eta] = n_eta' Phi n_xi (warps 0..6) | u = b_xi - Phi00 c_xi and A_xixi (warp 7)
+        if (warp < 7) {
+            for (int e = tid; e < m; e += 224) {
+                const double* ge = Gm + e * pb; const double* ce = Cm + e * pb;
+                double a0 = 0.0, a1 = 0.0;
+                for (int r = 0; r < p; ++r) { a0 = fma(ge[r], cvec[r], a0); a1 = fma(ce[r], phix[r], a1); }
+                av[e] = phix[base + e] - a0 - a1;
+            }
+        } else {
+            double part = 0.0;
+            for (int r = lane; r < p; r += 32) {
+                double a = 0.0;
+                for (int c = 0; c < p; ++c) a = fma(P00[r + c * pl], cvec[c], a);
+                const double u = phix[r] - a;
+                ub[r] = u;
+                part = fma(cvec[r], phix[r] + u, part);
+            }
+            part = warp_sum(part);
+            if (lane == 0) red[73] = phi0 - part;  // A_xixi = phi0 - c.b - c.u
         }
         __syncthreads();
-        const int base = (p > 0) ? p : N0;         // index of the first round-4 point among the centres
-        for (int e = tid; e < m; e += nt) {        // a[eta] = n_eta' Phi n_xi
-            const double* be = Bm + (size_t)e * pb; const double* ce = Cm + (size_t)e * pb;
-            double a0 = 0.0, a1 = 0.0;
-            for (int r = 0; r < p; ++r) { a0 = fma(be[r], cvec[r], a0); a1 = fma(ce[r], ub[r], a1); }
-            av[e] = phix[base + e] - a0 - a1;
-        }
-        if (warp == nwarps - 1) {                  // A_xixi = phi0 - c.b - c.ub
-            double a = 0.0;
-            for (int r = lane; r < p; r += 32) a = fma(cvec[r], phix[r] + ub[r], a);
-            a = warp_sum(a);
-            if (lane == 0) red[73] = phi0 - a;
-        }
-        __syncthreads();
+        // ---- phase 3: t = L^{-1} a with G threads per row, ||t||^2
+        const int G = (m > 64) ? 2 : ((m > 32) ? 4 : 8);
+        const int rows_per_pass = nt / G;
         double tn = 0.0;
-        for (int r = tid; r < m; r += nt) {        // t = L^{-1} a   (packed rows)
-            const double* lr = Li + tri(r);
-            double a0 = 0.0, a1 = 0.0;
-            int c = 0;
-            for (; c + 2 <= r + 1; c += 2) { a0 = fma(lr[c], av[c], a0); a1 = fma(lr[c + 1], av[c + 1], a1); }
-            for (; c <= r; ++c) a0 = fma(lr[c], av[c], a0);
-            const double a = a0 + a1;
-            tv[r] = a; tn = fma(a, a, tn);
+        for (int r0 = 0; r0 < m; r0 += rows_per_pass) {
+            const int r = r0 + tid / G, l = tid % G;
+            double a = 0.0;
+            if (r < m) {
+                const double* lr = Li + tri(r);
+                for (int c = l; c <= r; c += G) a = fma(lr[c], av[c], a);
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (r < m && l == 0) { tv[r] = a; tn = fma(a, a, tn); }
         }
-        tn = block_sum(tn, red);
+        tn = warp_sum(tn);
+        if (lane == 0) red[48 + warp] = tn;
+        __syncthreads();
+        tn = ((red[48] + red[49]) + (red[50] + red[51])) + ((red[52] + red[53]) + (red[54] + red[55]));
         const double gh2 = red[72];
         const double d2 = red[73] - tn;
         const double tau2 = gh2 * d2;              // == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
-        if (!(tau2 > thr)) continue;               // RbfModel.jl:452
-        // ---- accept
-        const double dd = sqrt(d2);
-        for (int c = tid; c < m; c += nt) {        // new row of L^{-1}: -(t' L^{-1}) / d
-            double a0 = 0.0, a1 = 0.0;
-            int r = c;
-            for (; r + 2 <= m; r += 2) { a0 = fma(tv[r], Li[tri(r) + c], a0); a1 = fma(tv[r + 1], Li[tri(r + 1) + c], a1); }
-            for (; r < m; ++r) a0 = fma(tv[r], Li[tri(r) + c], a0);
-            av[c] = -(a0 + a1) / dd;               // av is free now
+        if (tau2 > thr) {                          // RbfModel.jl:452
+            // ---- accept: new row of L^{-1} = [-(t' L^{-1}) / d, 1/d]
+            const double dd = sqrt(d2);
+            for (int c0 = 0; c0 < m; c0 += rows_per_pass) {
+                const int c = c0 + tid / G, l = tid % G;
+                double a = 0.0;
+                if (c < m) for (int r = c + l; r < m; r += G) a = fma(tv[r], Li[tri(r) + c], a);
+                for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (c < m && l == 0) Li[tri(m) + c] = -a / dd;
+            }
+            if (tid == 0) { Li[tri(m) + m] = 1.0 / dd; r4[nr4] = id + 1; }
+            {                                      // Sherman-Morrison: H <- H - (H pi)(H pi)' / (1 + pi' H pi)
+                const double inv1 = 1.0 / red[74];
+                for (int e = tid; e < p * p; e += nt) { int a_ = e % p, b_ = e / p; H[a_ + b_ * pl] = fma(-hv[a_] * inv1, hv[b_], H[a_ + b_ * pl]); }
+            }
+            for (int r = tid; r < p; r += nt) { Gm[m * pb + r] = ub[r]; Cm[m * pb + r] = cvec[r]; }
+            for (int k = tid; k < n; k += nt) Ct[k * NM + N] = xi[k];
+            N += 1; m += 1; nr4 += 1;
         }
-        {                                          // Sherman-Morrison: H <- H - (H pi)(H pi)' / (1 + pi' H pi)
-            const double inv1 = 1.0 / red[74];
-            for (int e = tid; e < p * p; e += nt) { int a_ = e % p, b_ = e / p; R[a_ + (size_t)b_ * pl] = fma(-rl[a_] * inv1, rl[b_], R[a_ + (size_t)b_ * pl]); }
-        }
-        for (int r = tid; r < p; r += nt) { Bm[(size_t)m * pb + r] = phix[r]; Cm[(size_t)m * pb + r] = cvec[r]; }
-        for (int k = tid; k < n; k += nt) Ct[(size_t)k * NM + N] = xi[k];
-        if (tid == 0) r4[nr4] = id + 1;
+        id = nxt; buf ^= 1;
         __syncthreads();
-        for (int c = tid; c < m; c += nt) Li[tri(m) + c] = av[c];
-        if (tid == 0) Li[tri(m) + m] = 1.0 / dd;
-        N += 1; m += 1; nr4 += 1;
     }
-    __syncthreads();
     if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
 }
 
 size_t round4_fast_vec_doubles(int n, int NM, int p) {
     int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
-    return (size_t)n + NM + 2 * (size_t)MM + 6 * (size_t)pl + 80;
+    return 2 * (size_t)n + NM + 2 * (size_t)MM + 4 * (size_t)pl + 80;
 }
 size_t round4_fast_state_doubles(int n, int NM, int p) {
     int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
@@ -884,9 +899,9 @@ __global__ void gather_training_kernel(GatherParams P) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-size_t select_smem_bytes(int n, bool wz_in_smem) {
+size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles) {
     size_t d = 8 * (size_t)n + 80 + 24;
-    if (wz_in_smem) d += 2 * (size_t)n * (n | 1);
+    if (wz_in_smem) d += 2 * (size_t)n * (n | 1) + (size_t)st_doubles;
     return d * sizeof(double);
 }
 size_t round4_vec_doubles(int n, int NM, int p) { int pl = p > 0 ? p : 1; return (size_t)n + 5 * (size_t)NM + 4 * (size_t)pl + 80; }
@@ -895,11 +910,17 @@ size_t round4_ws_doubles(int n, int NM, int p) {
     return (size_t)NM * n + (size_t)NM * NM + (size_t)NM * pl + (size_t)pl * pl + 2 * (size_t)NM * NM;
 }
 
-cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(select_rounds123_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool WZS, bool STS>
+static cudaError_t launch_select_t(const SelectParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(select_rounds123_kernel<WZS, STS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    select_rounds123_kernel<<<P.B, 256, smem, s>>>(P);
+    select_rounds123_kernel<WZS, STS><<<P.B, 256, smem, s>>>(P);
     return cudaGetLastError();
+}
+cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s) {
+    if (P.wz_in_smem && P.st_in_smem) return launch_select_t<true, true>(P, smem, s);
+    if (P.wz_in_smem) return launch_select_t<true, false>(P, smem, s);
+    return launch_select_t<false, false>(P, smem, s);
 }
 cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid) {
     cudaError_t e = cudaFuncSetAttribute(round4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -908,9 +929,16 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
     return cudaGetLastError();
 }
 cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(round4_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    round4_fast_kernel<<<P.B, 256, smem, s>>>(P);
+    cudaError_t e;
+    if (P.fs_in_smem) {
+        e = cudaFuncSetAttribute(round4_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        round4_fast_kernel<true><<<P.B, 256, smem, s>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(round4_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        round4_fast_kernel<false><<<P.B, 256, smem, s>>>(P);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s) {
