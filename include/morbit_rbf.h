@@ -80,7 +80,8 @@ int64_t mrbf_launch_count(const mrbf_ctx* ctx);
 /* Instrumentation (not part of the reference interface): when enabled, every kernel launch is bracketed by CUDA
  * events on the context's stream.  mrbf_profile_read synchronises and returns the device time in ms of the LAST
  * launch of each kernel class: ms[0] rounds 1-3, ms[1] round 4, ms[2] training-set gather, ms[3] build,
- * ms[4] eval/Jacobian (all passes of the last call), ms[5] round-4 fallback kernel, ms[6..7] reserved (0). */
+ * ms[4] eval/Jacobian (all passes of the last call), ms[5] round-4 fallback kernel, ms[6] build from a kept
+ * factorisation, ms[7] reserved (0). */
 int mrbf_profile_enable(mrbf_ctx* ctx, int32_t on);
 int mrbf_profile_read(mrbf_ctx* ctx, double* ms8);
 
@@ -118,6 +119,29 @@ int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_
                            int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
                            int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
                            int32_t* flags_out, int32_t* status);
+
+/* Same as mrbf_select_points_dev, and additionally keeps the round-4 factorisation of every instance on the device
+ * (inverse Cholesky factor of the reduced kernel matrix, RbfModel.jl:394-396, 469-477) in an opaque handle.  The
+ * reference discards these matrices and notes that keeping them would save work (RbfModel.jl:657-660);
+ * mrbf_build_prepared_dev turns them into the model with two triangular mat-vecs per output.
+ * *prepared must be NULL or a handle from an earlier call (reused when the shapes match, else freed and replaced). */
+typedef struct mrbf_prepared mrbf_prepared;
+int mrbf_select_points_keep_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                                const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                                const double* delta, double delta_max, const double* glb, const double* gub,
+                                const int32_t* flags_in, const int32_t* max_new,
+                                int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                                int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                                int32_t* flags_out, int32_t* status, mrbf_prepared** prepared);
+void mrbf_free_prepared(mrbf_ctx* ctx, mrbf_prepared* prepared);
+/* update_model from a kept factorisation.  values: B x db_stride x k (database values, same ids as `sites`),
+ * r3_values: B x n x k values of the new round-3 sites (may be NULL when there are none).  Instances whose round 4
+ * did not go through the shared-memory path (N0 != p, no round 4 at all) are built by the general route inside the
+ * same call, so the result is always a complete model batch with training order [centre; r1; r2; r3; r4]. */
+int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* prepared, int32_t k,
+                            const double* sites, const double* values, const double* r3_sites, const double* r3_values,
+                            const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                            const int32_t* n_r3, mrbf_model** model, int32_t* status);
 
 /* _rbf_round4 alone with an explicit found set (used after _exploit_other_rbf_metas!, RbfModel.jl:311-342, 562,
  * and called directly by test/rbf_models.jl:74-86).  found: B x found_stride ids (centre first), n_found: B;

@@ -45,6 +45,10 @@ SIGNATURES = {
                            + [_vp] * 6 + [_i32] + [_vp] * 6),
     "mrbf_select_points_dev": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32] + [_vp] * 4 + [_vp, _f64] + [_vp] * 4
                                + [_vp] * 6 + [_i32] + [_vp] * 6),
+    "mrbf_select_points_keep_dev": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32] + [_vp] * 4 + [_vp, _f64] + [_vp] * 4
+                                    + [_vp] * 6 + [_i32] + [_vp] * 6 + [C.POINTER(_vp)]),
+    "mrbf_free_prepared": (None, [_vp, _vp]),
+    "mrbf_build_prepared_dev": (C.c_int, [_vp, C.POINTER(MrbfCfg), _vp, _i32] + [_vp] * 10 + [C.POINTER(_vp), _vp]),
     "mrbf_round4": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp,
                               _i32, _vp, _vp, _vp]),
     "mrbf_gather_training_dev": (C.c_int, [_vp, _i32, _i32, _i32, _i32] + [_vp] * 10 + [_i32, _vp, _vp, _i32, _vp, _vp, _vp]),

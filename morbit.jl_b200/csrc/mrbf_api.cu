@@ -34,6 +34,15 @@ struct mrbf_ctx {
     DevBuf hb[32];      // staging for the host-pointer entry points
 };
 
+struct mrbf_prepared {
+    int B, n, NM, p, db_stride, found_stride, r4_stride, cfg_degree, kernel;
+    double shape;
+    size_t fs_stride;
+    double* fs = nullptr;
+    int* ints = nullptr;        // elig[B], n_found[B], n_extra[B], n_r4[B], found[B*found_stride], r4[B*r4_stride]
+    int *elig, *n_found, *n_extra, *n_r4, *found, *r4;
+};
+
 struct mrbf_model {
     int B, n, k, train_stride, p, deg;
     int kernel, ibeta;
@@ -44,6 +53,8 @@ struct mrbf_model {
     double* lam = nullptr;
     double* alpha2 = nullptr;
 };
+
+extern "C" void mrbf_free_prepared(mrbf_ctx* ctx, mrbf_prepared* kp);
 
 namespace {
 
@@ -123,7 +134,8 @@ int max_points_of(const mrbf_cfg* cfg, int n) {
 
 int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, const double* sites, const int* n_db,
                const double* lb2, const double* ub2, int found_stride, const int* found, const int* n_found,
-               int extra_stride, const double* extra, const int* n_extra, int n0max, int r4_stride, int* r4, int* n_r4, int* status) {
+               int extra_stride, const double* extra, const int* n_extra, int n0max, int r4_stride, int* r4, int* n_r4, int* status,
+               mrbf_prepared** keep_out = nullptr) {
     RadFn rf; double alpha; int cpd;
     int rc = resolve_radfn(ctx, cfg, cfg->shape_parameter, &rf, &alpha, &cpd);
     if (rc != MRBF_OK) return rc;
@@ -147,11 +159,32 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
         const size_t fv = round4_fast_vec_doubles(n, NM, p), fsd = round4_fast_state_doubles(n, NM, p);
         size_t fsmem = fv * sizeof(double);
         if (fsmem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
-        if ((fv + fsd) * sizeof(double) <= SMEM_LIMIT) { R.fs_in_smem = 1; fsmem = (fv + fsd) * sizeof(double); R.fs = nullptr; R.fs_stride = 0; }
+        R.fs_stride = fsd;
+        if (keep_out && *keep_out && (*keep_out)->B == B && (*keep_out)->n == n && (*keep_out)->NM == NM && (*keep_out)->p == p &&
+            (*keep_out)->found_stride == found_stride && (*keep_out)->r4_stride == r4_stride && (*keep_out)->fs_stride == fsd) {
+            mrbf_prepared* kp = *keep_out;       // reuse the caller's handle (same shapes): no allocation on the hot path
+            kp->db_stride = db_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
+            R.keep_fs = kp->fs; R.elig = kp->elig;
+        } else if (keep_out) {
+            if (*keep_out) { mrbf_free_prepared(ctx, *keep_out); *keep_out = nullptr; }
+            mrbf_prepared* kp = new (std::nothrow) mrbf_prepared();
+            if (!kp) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
+            kp->B = B; kp->n = n; kp->NM = NM; kp->p = p; kp->db_stride = db_stride; kp->found_stride = found_stride;
+            kp->r4_stride = r4_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
+            kp->fs_stride = fsd;
+            const size_t ni = (size_t)B * 4 + (size_t)B * found_stride + (size_t)B * r4_stride;
+            cudaError_t e1 = cudaMalloc(&kp->fs, (size_t)B * fsd * sizeof(double));
+            cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc(&kp->ints, ni * sizeof(int)) : e1;
+            if (e2 != cudaSuccess) { cudaFree(kp->fs); delete kp; return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e2)); }
+            kp->elig = kp->ints; kp->n_found = kp->elig + B; kp->n_extra = kp->n_found + B; kp->n_r4 = kp->n_extra + B;
+            kp->found = kp->n_r4 + B; kp->r4 = kp->found + (size_t)B * found_stride;
+            R.keep_fs = kp->fs; R.elig = kp->elig;
+            *keep_out = kp;
+        }
+        if ((fv + fsd) * sizeof(double) <= SMEM_LIMIT) { R.fs_in_smem = 1; fsmem = (fv + fsd) * sizeof(double); R.fs = nullptr; }
         else {
-            R.fs_in_smem = 0; R.fs_stride = fsd;
-            ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double));
-            R.fs = (double*)ctx->ws[9].p;
+            R.fs_in_smem = 0;
+            if (!keep_out) { ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double)); R.fs = (double*)ctx->ws[9].p; }
         }
         Timed t_(ctx, 1);
         CK(launch_round4_fast(R, fsmem, ctx->stream));
@@ -181,6 +214,16 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             CK(launch_round4(R, smem, ctx->stream, g));
             ctx->launches += 1;
         }
+    }
+    if (keep_out) {                           // ids needed later to gather the training values in training order
+        mrbf_prepared* kp = *keep_out;
+        const size_t sB = sizeof(int) * (size_t)B;
+        CK(cudaMemcpyAsync(kp->n_found, n_found, sB, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (n_extra) CK(cudaMemcpyAsync(kp->n_extra, n_extra, sB, cudaMemcpyDeviceToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(kp->n_extra, 0, sB, ctx->stream));
+        CK(cudaMemcpyAsync(kp->n_r4, n_r4, sB, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(kp->found, found, sB * found_stride, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(kp->r4, r4, sB * r4_stride, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return MRBF_OK;
 }
@@ -259,13 +302,13 @@ const char* mrbf_last_error(const mrbf_ctx* ctx) { return ctx ? ctx->err : "null
 int64_t mrbf_launch_count(const mrbf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------ select
-int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
                            const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
                            const double* delta, double delta_max, const double* glb, const double* gub,
                            const int32_t* flags_in, const int32_t* max_new,
                            int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
                            int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
-                           int32_t* flags_out, int32_t* status) {
+                           int32_t* flags_out, int32_t* status, mrbf_prepared** keep) {
     if (!ctx) return MRBF_EINVAL;
     int rc = check_cfg(ctx, cfg);
     if (rc != MRBF_OK) return rc;
@@ -297,13 +340,43 @@ int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_
     ctx->launches += 1;
     if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
         rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,
-                        n, r3_sites, n_r3, n + 1, r4_stride, r4, n_r4, status);
+                        n, r3_sites, n_r3, n + 1, r4_stride, r4, n_r4, status, keep);
         if (rc != MRBF_OK) return rc;
     } else {
         CK(cudaMemsetAsync(n_r4, 0, sizeof(int) * (size_t)B, ctx->stream));
         if (status) CK(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, ctx->stream));
     }
     return MRBF_OK;
+}
+
+int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                           const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                           const double* delta, double delta_max, const double* glb, const double* gub,
+                           const int32_t* flags_in, const int32_t* max_new,
+                           int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                           int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                           int32_t* flags_out, int32_t* status) {
+    return select_points_impl(ctx, cfg, B, n, db_stride, sites, n_db, x_index, x, delta, delta_max, glb, gub, flags_in, max_new,
+                              r1, n_r1, r2, n_r2, r3_sites, n_r3, r4_stride, r4, n_r4, dirs, n_dirs, flags_out, status, nullptr);
+}
+
+int mrbf_select_points_keep_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                                const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                                const double* delta, double delta_max, const double* glb, const double* gub,
+                                const int32_t* flags_in, const int32_t* max_new,
+                                int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                                int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                                int32_t* flags_out, int32_t* status, mrbf_prepared** prepared) {
+    if (!prepared) return MRBF_EINVAL;
+    return select_points_impl(ctx, cfg, B, n, db_stride, sites, n_db, x_index, x, delta, delta_max, glb, gub, flags_in, max_new,
+                              r1, n_r1, r2, n_r2, r3_sites, n_r3, r4_stride, r4, n_r4, dirs, n_dirs, flags_out, status, prepared);
+}
+
+void mrbf_free_prepared(mrbf_ctx* ctx, mrbf_prepared* kp) {
+    if (!kp) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(kp->fs); cudaFree(kp->ints);
+    delete kp;
 }
 
 #define H2D(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
@@ -409,9 +482,10 @@ void mrbf_free_model(mrbf_ctx* ctx, mrbf_model* m) {
     delete m;
 }
 
-int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
-                   const int32_t* N, const double* sites, const double* values, const double* shape,
-                   mrbf_model** out, int32_t* status) {
+static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+                      const int32_t* N, const double* sites, const double* values, const double* shape,
+                      mrbf_model** out, int32_t* status, const mrbf_prepared* kp, const double* db_values, const double* r3_values,
+                      const int* skip_from_prepared) {
     if (!ctx || !out) return MRBF_EINVAL;
     *out = nullptr;
     int rc = check_cfg(ctx, cfg);
@@ -440,6 +514,7 @@ int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int
     Pb.B = B; Pb.n = n; Pb.k = k; Pb.train_stride = train_stride; Pb.p = p; Pb.deg = deg;
     Pb.kernel = rf.kernel; Pb.ibeta = rf.ibeta; Pb.sgn = rf.sgn; Pb.alpha_default = alpha;
     Pb.N = N; Pb.sites = sites; Pb.values = values; Pb.shape = shape;
+    if (kp) { Pb.skip = skip_from_prepared; Pb.centers_out = m->centers; Pb.N_out = m->N; }
     Pb.w = m->w; Pb.lam = m->lam; Pb.alpha2_out = m->alpha2; Pb.status = status; Pb.ld = train_stride | 1;
     const size_t vecd = build_vec_doubles(n, k, Pb.ld, p), wsd = build_ws_doubles(n, k, Pb.ld, p);
     size_t smem = vecd * sizeof(double);
@@ -455,15 +530,67 @@ int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int
         if (r_ != MRBF_OK) { mrbf_free_model(ctx, m); return r_; }
         Pb.ws = (double*)ctx->ws[8].p;
     }
-    e = cudaMemcpyAsync(m->N, N, sizeof(int) * (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(m->centers, sites, sizeof(double) * (size_t)B * train_stride * n, cudaMemcpyDeviceToDevice, ctx->stream);
+    e = cudaSuccess;
+    if (!kp) {
+        e = cudaMemcpyAsync(m->N, N, sizeof(int) * (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m->centers, sites, sizeof(double) * (size_t)B * train_stride * n, cudaMemcpyDeviceToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaMemsetAsync(m->w, 0, sizeof(double) * (size_t)B * train_stride * k, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->lam, 0, sizeof(double) * (size_t)B * pl * k, ctx->stream);
+    if (e == cudaSuccess && kp && kp->cfg_degree == deg && kp->p > 0) {
+        // 1. instances whose round 4 kept its factorisation: two triangular mat-vecs per output
+        PreparedBuildParams Q{};
+        Q.B = B; Q.n = n; Q.k = k; Q.NM = kp->NM; Q.p = kp->p; Q.deg = deg; Q.db_stride = kp->db_stride;
+        Q.found_stride = kp->found_stride; Q.r4_stride = kp->r4_stride; Q.train_stride = train_stride; Q.fs_stride = kp->fs_stride;
+        round4_fast_state_layout(n, kp->NM, kp->p, &Q.off_M0, &Q.off_G, &Q.off_C, &Q.off_L);
+        Q.fs = kp->fs; Q.elig = kp->elig; Q.found = kp->found; Q.n_found = kp->n_found; Q.n_extra = kp->n_extra; Q.r4 = kp->r4; Q.n_r4 = kp->n_r4;
+        Q.values = db_values; Q.r3_values = r3_values; Q.alpha2 = alpha * alpha;
+        Q.centers = m->centers; Q.w = m->w; Q.lam = m->lam; Q.alpha2_out = m->alpha2; Q.N = m->N; Q.status = status; Q.done = (int*)skip_from_prepared;
+        const size_t psm = build_prepared_smem_doubles(n, k, kp->NM, kp->p) * sizeof(double);
+        if (psm <= SMEM_LIMIT) { Timed t_(ctx, 6); e = launch_build_prepared(Q, psm, ctx->stream); ctx->launches += 1; }
+        else e = cudaMemsetAsync((void*)skip_from_prepared, 0, sizeof(int) * (size_t)B, ctx->stream);
+    } else if (e == cudaSuccess && kp) {
+        e = cudaMemsetAsync((void*)skip_from_prepared, 0, sizeof(int) * (size_t)B, ctx->stream);
+    }
+    // 2. general route (for every instance, or for the ones step 1 left)
     if (e == cudaSuccess) { Timed t_(ctx, 3); e = launch_build(Pb, smem, ctx->stream); }
     if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ECUDA, "CUDA error: %s", cudaGetErrorString(e)); }
     ctx->launches += 1;
     *out = m;
     return MRBF_OK;
+}
+
+int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+                   const int32_t* N, const double* sites, const double* values, const double* shape,
+                   mrbf_model** out, int32_t* status) {
+    return build_impl(ctx, cfg, B, n, k, train_stride, N, sites, values, shape, out, status, nullptr, nullptr, nullptr, nullptr);
+}
+
+int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
+                            const double* sites, const double* values, const double* r3_sites, const double* r3_values,
+                            const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                            const int32_t* n_r3, mrbf_model** out, int32_t* status) {
+    if (!ctx || !kp || !out || !cfg) return MRBF_EINVAL;
+    if (cfg->kernel != kp->kernel || !((cfg->shape_parameter == kp->shape) || (cfg->shape_parameter != cfg->shape_parameter && kp->shape != kp->shape)))
+        return fail(ctx, MRBF_EINVAL, "mrbf_build_prepared: kernel/shape differ from the ones the factorisation was made with%s");
+    CK(cudaSetDevice(ctx->device));
+    const int B = kp->B, n = kp->n, ts = kp->NM;
+    // scratch for the general route: gathered training sets + done mask
+    ENSURE(ctx->ws[10], sizeof(double) * (size_t)B * ts * (n + k));
+    ENSURE(ctx->ws[11], sizeof(int) * (size_t)B * 2);
+    double* tsit = (double*)ctx->ws[10].p; double* tval = tsit + (size_t)B * ts * n;
+    int* done = (int*)ctx->ws[11].p; int* Ntmp = done + B;
+    CK(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)B, ctx->stream));
+    // the general route needs the gathered training set of the instances the kept factorisation does not cover;
+    // the gather is cheap, so it runs for all and the build kernel skips the done ones
+    GatherParams G{};
+    G.B = B; G.n = n; G.k = k; G.db_stride = kp->db_stride; G.r4_stride = kp->r4_stride; G.train_stride = ts;
+    G.sites = sites; G.values = values; G.x_index = x_index; G.r1 = r1; G.n_r1 = n_r1; G.r2 = r2; G.n_r2 = n_r2;
+    G.r3_sites = r3_sites; G.r3_values = r3_values; G.n_r3 = n_r3; G.r4 = kp->r4; G.n_r4 = kp->n_r4;
+    G.train_sites = tsit; G.train_values = tval; G.N = Ntmp; G.skip = nullptr;
+    { Timed t_(ctx, 2); CK(launch_gather_training(G, ctx->stream)); }
+    ctx->launches += 1;
+    return build_impl(ctx, cfg, B, n, k, ts, Ntmp, tsit, tval, nullptr, out, status, kp, values, r3_values, done);
 }
 
 int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,

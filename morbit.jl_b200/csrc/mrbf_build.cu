@@ -94,8 +94,14 @@ __global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
     double* Yv = Pm + (size_t)ld * pl;           // ld x k
     double* w_out = P.w + (size_t)b * P.train_stride * k;
     double* lam_out = P.lam + (size_t)b * pl * k;
+    if (P.skip && P.skip[b]) return;                         // already built from the kept round-4 factorisation
     if (N <= 0 || N > P.train_stride) { if (tid == 0) P.status[b] = -1; return; }
     const double* sites = P.sites + (size_t)b * P.train_stride * n;
+    if (P.centers_out) {
+        double* co = P.centers_out + (size_t)b * P.train_stride * n;
+        for (int e = tid; e < N * n; e += nt) co[e] = sites[e];
+        if (tid == 0) P.N_out[b] = N;
+    }
     const double* values = P.values + (size_t)b * P.train_stride * k;
     RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn;
     {
@@ -235,6 +241,118 @@ __global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
     __syncthreads();
     for (int e = tid; e < N * k; e += nt) { const int i = e / k, q = e % k; w_out[e] = Yv[i + (size_t)q * ld]; }
     if (tid == 0) P.status[b] = 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Build from the factorisation kept by round 4 (mrbf_build_prepared).
+//
+// Round 4 already holds, for the training set [S0; accepted points] in _collect_indices order, the inverse
+// Cholesky factor L^{-1} of the kernel matrix reduced to the null space of Pi' (basis n_eta = e_eta - sum_s c_eta[s] e_s).
+// The reference notes that reusing this would save work (RbfModel.jl:657-660, "we do not store the matrices calculated in
+// round 4"); here it turns the O(N^3) build into two triangular mat-vecs:
+//     r = Y_acc - C' Y_0,   u = L^{-T} L^{-1} r,   w = [-C u; u],   lambda~ = Pi_0^{-1} (Y_0 - G u)
+// (G = Phi(S0, acc) - Phi00 C).  lambda~ lives in the centred/scaled basis of round 4 and is mapped back to (1, x).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_prepared_kernel(PreparedBuildParams P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, k = P.k, p = P.p, NM = P.NM, tid = threadIdx.x, nt = blockDim.x;
+    const int pl = p > 0 ? p : 1, pb = pl | 1;
+    const int MM = (NM - p) > 1 ? (NM - p) : 1;
+    if (!P.elig[b]) { if (tid == 0) P.done[b] = 0; return; }
+    const double* fs = P.fs + (size_t)b * P.fs_stride;
+    const double inv_s = fs[P.fs_stride - 1];
+    const int N0 = (int)fs[P.fs_stride - 2], m = (int)fs[P.fs_stride - 3];
+    const int N = N0 + m;
+    const int base = (p > 0) ? p : N0;
+    const double* Ct = fs; const double* M0g = fs + P.off_M0; const double* Gg = fs + P.off_G; const double* Cg = fs + P.off_C;
+    const double* Lg = fs + P.off_L;
+    // shared: y (N x k), r/u (m x k), s (m x k), L^{-1} packed, G, C
+    double* y = smem;                       // N x k   (row i at y + i*k)
+    double* rv = y + (size_t)NM * k;        // MM x k
+    double* sv = rv + (size_t)MM * k;       // MM x k
+    double* t0 = sv + (size_t)MM * k;       // pl x k
+    double* Ls = t0 + (size_t)pl * k;       // tri(MM)
+    double* Gs = Ls + (size_t)MM * (MM + 1) / 2;
+    double* Cs = Gs + (size_t)pb * MM;
+    const int* found = P.found + (size_t)b * P.found_stride;
+    const int nf = P.n_found[b];
+    const int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    const double* values = P.values + (size_t)b * P.db_stride * k;
+    const double* r3v = P.r3_values ? P.r3_values + (size_t)b * n * k : nullptr;
+    for (int e = tid; e < N * k; e += nt) {
+        const int i = e / k, q = e % k;
+        double val;
+        if (i < nf) val = values[(size_t)(found[i] - 1) * k + q];
+        else if (i < N0) val = r3v ? r3v[(size_t)(i - nf) * k + q] : 0.0;
+        else val = values[(size_t)(r4[i - N0] - 1) * k + q];
+        y[e] = val;
+    }
+    const int tl = (m * (m + 1)) >> 1;
+    for (int e = tid; e < tl; e += nt) Ls[e] = Lg[e];
+    for (int e = tid; e < pb * m; e += nt) { Gs[e] = Gg[e]; Cs[e] = Cg[e]; }
+    double* centers = P.centers + (size_t)b * P.train_stride * n;
+    for (int e = tid; e < N * n; e += nt) { const int i = e / n, c = e % n; centers[e] = Ct[(size_t)c * NM + i]; }
+    __syncthreads();
+    for (int e = tid; e < m * k; e += nt) {                  // r = Y_acc - C' Y_0
+        const int eta = e / k, q = e % k;
+        double a = y[(size_t)(base + eta) * k + q];
+        for (int r = 0; r < p; ++r) a = fma(-Cs[eta * pb + r], y[(size_t)r * k + q], a);
+        rv[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * k; e += nt) {                  // s = L^{-1} r
+        const int r = e / k, q = e % k;
+        const double* lr = Ls + ((r * (r + 1)) >> 1);
+        double a = 0.0;
+        for (int c = 0; c <= r; ++c) a = fma(lr[c], rv[(size_t)c * k + q], a);
+        sv[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * k; e += nt) {                  // u = L^{-T} s   (into rv)
+        const int c = e / k, q = e % k;
+        double a = 0.0;
+        for (int r = c; r < m; ++r) a = fma(Ls[((r * (r + 1)) >> 1) + c], sv[(size_t)r * k + q], a);
+        rv[e] = a;
+    }
+    __syncthreads();
+    double* w_out = P.w + (size_t)b * P.train_stride * k;
+    double* lam_out = P.lam + (size_t)b * pl * k;
+    for (int e = tid; e < m * k; e += nt) w_out[(size_t)base * k + e] = rv[e];
+    for (int e = tid; e < p * k; e += nt) {                  // w_0 = -C u ; t0 = Y_0 - G u
+        const int r = e / k, q = e % k;
+        double a = 0.0, g = y[(size_t)r * k + q];
+        for (int eta = 0; eta < m; ++eta) { const double u = rv[(size_t)eta * k + q]; a = fma(Cs[eta * pb + r], u, a); g = fma(-Gs[eta * pb + r], u, g); }
+        w_out[(size_t)r * k + q] = -a;
+        t0[e] = g;
+    }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) {                  // lambda~ = M0' t0 -> into sv (p x k)
+        const int c = e / k, q = e % k;
+        double a = 0.0;
+        for (int r = 0; r < p; ++r) a = fma(M0g[r + (size_t)c * pl], t0[(size_t)r * k + q], a);
+        sv[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) {                  // back to the monomial basis (1, x_1..x_n)
+        const int c = e / k, q = e % k;
+        double val;
+        if (c == 0) { val = sv[q]; for (int j = 1; j < p; ++j) val = fma(-sv[(size_t)j * k + q] * inv_s, Ct[(size_t)(j - 1) * NM], val); }
+        else val = sv[e] * inv_s;
+        lam_out[e] = val;
+    }
+    if (tid == 0) { P.N[b] = N; P.alpha2_out[b] = P.alpha2; P.status[b] = 0; P.done[b] = 1; }
+}
+
+size_t build_prepared_smem_doubles(int n, int k, int NM, int p) {
+    int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
+    return (size_t)NM * k + 2 * (size_t)MM * k + (size_t)pl * k + (size_t)MM * (MM + 1) / 2 + 2 * (size_t)pb * MM;
+}
+cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(build_prepared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    build_prepared_kernel<<<P.B, 256, smem, s>>>(P);
+    return cudaGetLastError();
 }
 
 size_t build_vec_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return 2 * (size_t)ld + pl + 80; }

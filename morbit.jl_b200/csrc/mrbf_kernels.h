@@ -39,6 +39,7 @@ struct Round4Params {
     int b0;                       // first instance of this launch (chunked literal launches)
     int only_marked;              // literal kernel: process only instances the fast kernel marked (n_r4 == -1)
     double* fs; size_t fs_stride; int fs_in_smem;   // fast-path state
+    double* keep_fs; int* elig;                     // kept factorisation (mrbf_prepared) or NULL
 };
 
 struct GatherParams {
@@ -47,6 +48,7 @@ struct GatherParams {
     const int* r1; const int* n_r1; const int* r2; const int* n_r2;
     const double* r3_sites; const double* r3_values; const int* n_r3; const int* r4; const int* n_r4;
     double* train_sites; double* train_values; int* N;
+    const int* skip;      // instances to leave untouched (or NULL)
 };
 
 struct BuildParams {
@@ -56,6 +58,18 @@ struct BuildParams {
     const int* N; const double* sites; const double* values; const double* shape;
     double* w; double* lam; double* alpha2_out; int* status;
     double* ws; size_t ws_stride; int ws_in_smem; int ld; int smem_ws_doubles;
+    const int* skip;      // instances already built by the prepared path (or NULL)
+    double* centers_out;  // when non-NULL the kernel also copies the training sites into the model
+    int* N_out;
+};
+
+struct PreparedBuildParams {
+    int B, n, k, NM, p, deg, db_stride, found_stride, r4_stride, train_stride;
+    size_t fs_stride, off_M0, off_G, off_C, off_L;
+    const double* fs; const int* elig; const int* found; const int* n_found; const int* n_extra; const int* r4; const int* n_r4;
+    const double* values; const double* r3_values;
+    double alpha2;
+    double* centers; double* w; double* lam; double* alpha2_out; int* N; int* status; int* done;
 };
 
 struct EvalParams {
@@ -81,6 +95,7 @@ size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
 size_t round4_fast_vec_doubles(int n, int NM, int p);
 size_t round4_fast_state_doubles(int n, int NM, int p);
+void round4_fast_state_layout(int n, int NM, int p, size_t* off_M0, size_t* off_G, size_t* off_C, size_t* off_L);
 size_t build_vec_doubles(int n, int k, int ld, int p);
 size_t build_ws_doubles(int n, int k, int ld, int p);
 
@@ -89,6 +104,8 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
 cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s);
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s);
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
+cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s);
+size_t build_prepared_smem_doubles(int n, int k, int NM, int p);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);
 cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s);
 cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s);

@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
     double* red = tauq + pl;           // 80
     double* st = red + 80;
     double* fs;
-    if constexpr (SMEM) fs = st; else fs = P.fs + (size_t)b * P.fs_stride;
+    if constexpr (SMEM) fs = st; else fs = (P.keep_fs ? P.keep_fs : P.fs) + (size_t)b * P.fs_stride;
     double* Ct = fs;                   // NM x n  coordinate-major centres
     double* M0 = Ct + NM * n;          // p x p   Pi_0^{-T}
     double* P00 = M0 + pl * pl;        // p x p   Phi(S0, S0)
@@ -635,6 +635,7 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
     int* r4 = P.r4 + (size_t)b * P.r4_stride;
     const int N0 = nf_ids + n_extra;
     const int max_points = P.max_points;
+    if (tid == 0 && P.elig) P.elig[b] = 0;
     if (!(N0 < max_points) || N0 > NM) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = (N0 > NM) ? -1 : 0; } return; }
     if (p > 0 && N0 != p) { if (tid == 0) P.n_r4[b] = -1; return; }         // literal kernel takes over
 
@@ -859,6 +860,21 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
         __syncthreads();
     }
     if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
+    if (P.keep_fs) {
+        // keep the factorisation for mrbf_build_prepared: centres, Pi_0^{-T}, g/c blocks, packed L^{-1}
+        double* out = P.keep_fs + (size_t)b * P.fs_stride;
+        if constexpr (SMEM) {
+            const int used_c = pb * m, used_l = tri(m);
+            for (int e = tid; e < NM * n; e += nt) { int i = e % NM; if (i < N) out[e] = Ct[e]; }
+            double* o = out + NM * n;
+            for (int e = tid; e < pl * pl; e += nt) o[e] = M0[e];
+            o = out + (Gm - fs);
+            for (int e = tid; e < used_c; e += nt) { o[e] = Gm[e]; o[pb * MM + e] = Cm[e]; }
+            o = out + (Li - fs);
+            for (int e = tid; e < used_l; e += nt) o[e] = Li[e];
+        }
+        if (tid == 0) { out[P.fs_stride - 1] = inv_s; out[P.fs_stride - 2] = (double)N0; out[P.fs_stride - 3] = (double)m; P.elig[b] = 1; }
+    }
 }
 
 size_t round4_fast_vec_doubles(int n, int NM, int p) {
@@ -869,12 +885,21 @@ size_t round4_fast_state_doubles(int n, int NM, int p) {
     int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
     return (size_t)NM * n + 6 * (size_t)pl * pl + 2 * (size_t)pb * MM + (size_t)MM * (MM + 1) / 2 + 8;
 }
+// offsets (in doubles) of the blocks mrbf_build_prepared reads from a kept state
+void round4_fast_state_layout(int n, int NM, int p, size_t* off_M0, size_t* off_G, size_t* off_C, size_t* off_L) {
+    int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
+    *off_M0 = (size_t)NM * n;
+    *off_G = *off_M0 + 6 * (size_t)pl * pl;
+    *off_C = *off_G + (size_t)pb * MM;
+    *off_L = *off_C + (size_t)pb * MM;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Training-set gather (_collect_indices order: centre, r1, r2, r3, r4), RbfModel.jl:178-186, 754-757
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_training_kernel(GatherParams P) {
     const int b = blockIdx.x, n = P.n, k = P.k, tid = threadIdx.x, nt = blockDim.x;
+    if (P.skip && P.skip[b]) return;
     const int n1 = P.n_r1[b], n2 = P.n_r2[b], n3 = P.n_r3[b], n4 = P.n_r4[b];
     const int N = 1 + n1 + n2 + n3 + n4;
     const double* sites = P.sites + (size_t)b * P.db_stride * n;

@@ -84,6 +84,25 @@ class ModelBatch:
             pass
 
 
+class Prepared:
+    """Round-4 factorisations kept on the device (opaque mrbf_prepared handle)."""
+
+    def __init__(self, engine: "Engine", handle: int):
+        self.engine, self.handle = engine, handle
+
+    def free(self):
+        if self.handle:
+            self.engine.lib.mrbf_free_prepared(self.engine.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.handle and self.engine.ctx:
+                self.free()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, device: int = 0, stream: Optional[int] = None):
         self.lib = _lib.load()
@@ -120,7 +139,8 @@ class Engine:
     def profile_read(self) -> dict:
         ms = (C.c_double * 8)()
         self._check(self.lib.mrbf_profile_read(self.ctx, ms))
-        return dict(rounds123=ms[0], round4=ms[1], gather=ms[2], build=ms[3], eval=ms[4], round4_fallback=ms[5])
+        return dict(rounds123=ms[0], round4=ms[1], gather=ms[2], build=ms[3], eval=ms[4], round4_fallback=ms[5],
+                    build_prepared=ms[6])
 
     @property
     def launch_count(self) -> int:
@@ -188,6 +208,47 @@ class Engine:
             _ptr(out.n_r2), _ptr(out.r3_sites), _ptr(out.n_r3), out.r4.shape[1], _ptr(out.r4), _ptr(out.n_r4), _ptr(out.dirs),
             _ptr(out.n_dirs), _ptr(out.flags_out), _ptr(out.status)))
         return out
+
+    def select_points_keep_dev(self, cfg, sites, n_db, x_index, x, delta, delta_max, glb, gub, flags_in, max_new, out=None,
+                               prepared=None):
+        """select_points_dev that also keeps the round-4 factorisation on the device; returns (SelectResult, Prepared)."""
+        import torch
+        B, db_stride, n = sites.shape
+        mp = max_model_points(cfg, n)
+        dev = sites.device
+        if out is None:
+            i32 = dict(dtype=torch.int32, device=dev); f64 = dict(dtype=torch.float64, device=dev)
+            out = SelectResult(torch.zeros((B, n), **i32), torch.zeros(B, **i32), torch.zeros((B, n), **i32), torch.zeros(B, **i32),
+                               torch.zeros((B, n, n), **f64), torch.zeros(B, **i32), torch.zeros((B, mp), **i32),
+                               torch.zeros(B, **i32), torch.zeros((B, n, n), **f64), torch.zeros(B, **i32),
+                               torch.zeros((B, 2), **i32), torch.zeros(B, **i32))
+        ccfg = to_c_cfg(cfg)
+        handle = C.c_void_p(prepared.handle if prepared is not None else None)
+        if prepared is not None:
+            prepared.handle = None          # ownership moves through the call (the library may replace the handle)
+        self._check(self.lib.mrbf_select_points_keep_dev(
+            self.ctx, C.byref(ccfg), B, n, db_stride, _ptr(sites), _ptr(n_db), _ptr(x_index), _ptr(x), _ptr(delta),
+            float(delta_max), _ptr(glb), _ptr(gub), _ptr(flags_in), _ptr(max_new), _ptr(out.r1), _ptr(out.n_r1), _ptr(out.r2),
+            _ptr(out.n_r2), _ptr(out.r3_sites), _ptr(out.n_r3), out.r4.shape[1], _ptr(out.r4), _ptr(out.n_r4), _ptr(out.dirs),
+            _ptr(out.n_dirs), _ptr(out.flags_out), _ptr(out.status), C.byref(handle)))
+        if prepared is not None:
+            prepared.handle = handle.value
+            return out, prepared
+        return out, Prepared(self, handle.value)
+
+    def build_prepared_dev(self, cfg, prepared, sites, values, x_index, sel: SelectResult, r3_values=None, status=None):
+        """update_model from the factorisation kept by select_points_keep_dev (general route for the rest)."""
+        import torch
+        B = sites.shape[0]
+        k = values.shape[2]
+        if status is None:
+            status = torch.zeros(B, dtype=torch.int32, device=sites.device)
+        handle = C.c_void_p()
+        ccfg = to_c_cfg(cfg)
+        self._check(self.lib.mrbf_build_prepared_dev(
+            self.ctx, C.byref(ccfg), prepared.handle, k, _ptr(sites), _ptr(values), _ptr(sel.r3_sites), _ptr(r3_values),
+            _ptr(x_index), _ptr(sel.r1), _ptr(sel.n_r1), _ptr(sel.r2), _ptr(sel.n_r2), _ptr(sel.n_r3), C.byref(handle), _ptr(status)))
+        return ModelBatch(self, handle.value), status
 
     def gather_training_dev(self, sites, values, x_index, sel: SelectResult, r3_values, train_stride, out=None):
         import torch

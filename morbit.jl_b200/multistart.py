@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .engine import Engine, ModelBatch, SelectResult, max_model_points
+from .engine import Engine, ModelBatch, Prepared, SelectResult, max_model_points
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -65,6 +65,7 @@ class MultistartBuilder:
         self._train = None
         self._r3_values = None
         self._status = None
+        self._prepared: Optional[Prepared] = None      # reused across steps (no allocation on the hot path)
 
     def select(self, d: DeviceBatch) -> SelectResult:
         self._sel = self.engine.select_points_dev(self.cfg, d.sites, d.n_db, d.x_index, d.x, d.delta, self.delta_max,
@@ -88,10 +89,28 @@ class MultistartBuilder:
         model, status = self.engine.build_dev(self.cfg, self._train[0], self._train[1], self._train[2], None, self._status)
         return model, status
 
-    def step(self, d: DeviceBatch) -> Tuple[ModelBatch, SelectResult, object]:
-        sel = self.select(d)
-        model, status = self.build(d, sel)
-        return model, sel, status
+    def step(self, d: DeviceBatch, fused: bool = True) -> Tuple[ModelBatch, SelectResult, object]:
+        """One build per instance.  fused=True keeps the round-4 factorisation and builds from it
+        (mrbf_select_points_keep_dev + mrbf_build_prepared_dev); fused=False is the reference's two independent
+        phases (rounds 1-4, then a from-scratch solve of the gathered training set)."""
+        if not fused:
+            sel = self.select(d)
+            model, status = self.build(d, sel)
+            return model, sel, status
+        import torch
+        self._sel, self._prepared = self.engine.select_points_keep_dev(self.cfg, d.sites, d.n_db, d.x_index, d.x, d.delta,
+                                                                       self.delta_max, d.glb, d.gub, d.flags_in, d.max_new,
+                                                                       out=self._sel, prepared=self._prepared)
+        prepared = self._prepared
+        B, _, n = d.sites.shape
+        k = d.values.shape[2]
+        if self._r3_values is None or self._r3_values.shape != (B, n, k):
+            self._r3_values = torch.zeros((B, n, k), dtype=torch.float64, device=d.sites.device)
+        if self._status is None or self._status.shape[0] != B:
+            self._status = torch.zeros(B, dtype=torch.int32, device=d.sites.device)
+        model, status = self.engine.build_prepared_dev(self.cfg, prepared, d.sites, d.values, d.x_index, self._sel,
+                                                       self._r3_values, self._status)
+        return model, self._sel, status
 
 
 def gather_results(local: np.ndarray, total: int, rank: int, world: int) -> Optional[np.ndarray]:

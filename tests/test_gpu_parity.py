@@ -235,3 +235,62 @@ def test_unsupported_and_error_paths(engine):
     model, status = engine.build(mb.RbfConfig(kernel="cubic"), S, V, [12, 12], raise_on_failure=False)
     assert status[0] == 0 and status[1] != 0
     model.free()
+
+
+def _oracle_models(cfg, host, res_np):
+    """Training sets [centre; r1; r2; r3; r4] and oracle coefficients for every instance of a batch."""
+    from morbit_jl_b200 import synthetic
+    B, _, n = host["sites"].shape
+    out = []
+    for b in range(B):
+        ids = [1] + list(res_np["r1"][b, :res_np["n_r1"][b]]) + list(res_np["r2"][b, :res_np["n_r2"][b]])
+        P = np.vstack([host["sites"][b, np.array(ids) - 1], res_np["r3_sites"][b, :res_np["n_r3"][b]].reshape(-1, n),
+                       host["sites"][b, res_np["r4"][b, :res_np["n_r4"][b]].astype(int) - 1].reshape(-1, n)])
+        V = synthetic.zdt3(P)
+        w, lam, st = CO.build_batched(cfg, P[None], V[None], [len(P)])
+        out.append((P, w[0], lam[0]))
+    return out
+
+
+@pytest.mark.parametrize("kernel,n,n_db,max_new", [("multiquadric", 30, 128, 2**31 - 1), ("cubic", 10, 60, 2**31 - 1),
+                                                   ("gaussian", 6, 40, 2), ("cubic", 8, 5, 2**31 - 1)])
+def test_build_from_kept_factorisation_matches_oracle(engine, kernel, n, n_db, max_new):
+    """Device-resident multistart step: select (keeping the round-4 factorisation) -> build from it.  Mixed batches
+    (budget-limited instances whose round 4 takes the literal kernel) are completed by the general route."""
+    import torch
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import MultistartBuilder, upload_batch
+    B = 12
+    cfg = mb.RbfConfig(kernel=kernel)
+    host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=0.1, func=synthetic.zdt3, local_fraction=0.4)
+    host["max_new"][:] = max_new
+    host["max_new"][::3] = min(max_new, 1)          # every third instance is budget-limited
+    dev = upload_batch(host, "cuda:0")
+    builder = MultistartBuilder(engine, cfg, host["delta_max"])
+    # round-3 sites need values from the "expensive function": first pass to learn the sites, then supply the values
+    sel = builder.select(dev)
+    engine.sync()
+    r3_sites = sel.r3_sites.cpu().numpy(); n_r3 = sel.n_r3.cpu().numpy()
+    r3_vals = np.zeros((B, n, 2))
+    for b in range(B):
+        r3_vals[b, :n_r3[b]] = synthetic.zdt3(r3_sites[b, :n_r3[b]])
+    r3_dev = torch.from_numpy(r3_vals).cuda()
+    ref = CO.select_points_batched(cfg, host["sites"], host["x_index"], host["x"], host["delta"], host["delta_max"], host["glb"],
+                                   host["gub"], False, False, host["max_new"], nthreads=4)
+    sel2, prepared = engine.select_points_keep_dev(cfg, dev.sites, dev.n_db, dev.x_index, dev.x, dev.delta, host["delta_max"],
+                                                   dev.glb, dev.gub, dev.flags_in, dev.max_new)
+    model, status = engine.build_prepared_dev(cfg, prepared, dev.sites, dev.values, dev.x_index, sel2, r3_dev)
+    engine.sync()
+    res_np = {k: getattr(sel2, k).cpu().numpy() for k in ("r1", "n_r1", "r2", "n_r2", "r3_sites", "n_r3", "r4", "n_r4")}
+    for b in range(B):
+        for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+            assert list(res_np[nm][b, :res_np[cnt][b]]) == list(getattr(ref, nm)[b, :getattr(ref, cnt)[b]]), (b, nm)
+    assert np.all(status.cpu().numpy() == 0)
+    oracle = _oracle_models(cfg, host, res_np)
+    X = host["x"][:, None, :] + 0.1 * (np.random.default_rng(0).random((B, 9, n)) - 0.5)
+    Y, J = engine.eval(model, X, True, True)
+    for b, (P, w, lam) in enumerate(oracle):
+        Yr = CO.eval_points(cfg, P, w, lam, X[b]); Jr = CO.jac_points(cfg, P, w, lam, X[b])
+        assert np.abs(Y[b] - Yr).max() <= RTOL * np.abs(Yr).max(), (b, np.abs(Y[b] - Yr).max() / np.abs(Yr).max())
+        assert np.abs(J[b] - Jr).max() <= RTOL * np.abs(Jr).max(), (b, np.abs(J[b] - Jr).max() / np.abs(Jr).max())
+    prepared.free(); model.free()
