@@ -52,6 +52,10 @@ struct mrbf_model {
     double* w = nullptr;
     double* lam = nullptr;
     double* alpha2 = nullptr;
+    double* pack = nullptr;     // tiled centred copy for the DMMA sweep (n <= 64)
+    int pack_s = 0, pack_nt = 0;
+    size_t pack_tile_doubles = 0;
+    bool pack_valid = false;    // built lazily by the first values-only evaluation
 };
 
 extern "C" void mrbf_free_prepared(mrbf_ctx* ctx, mrbf_prepared* kp);
@@ -478,7 +482,7 @@ int mrbf_gather_training_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int
 void mrbf_free_model(mrbf_ctx* ctx, mrbf_model* m) {
     if (!m) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(m->N); cudaFree(m->centers); cudaFree(m->w); cudaFree(m->lam); cudaFree(m->alpha2);
+    cudaFree(m->N); cudaFree(m->centers); cudaFree(m->w); cudaFree(m->lam); cudaFree(m->alpha2); cudaFree(m->pack);
     delete m;
 }
 
@@ -509,6 +513,10 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     if (e == cudaSuccess) e = cudaMalloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
     if (e == cudaSuccess) e = cudaMalloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
     if (e == cudaSuccess) e = cudaMalloc(&m->alpha2, sizeof(double) * (size_t)B);
+    if (e == cudaSuccess && n <= 64 && k <= 16) {   // geometry of the tiled copy; the buffer itself is allocated on first use
+        m->pack_s = eval_pack_stride(n); m->pack_nt = (train_stride + 63) / 64;
+        m->pack_tile_doubles = (size_t)64 * m->pack_s + 64 + (size_t)k * 64;
+    }
     if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
     BuildParams Pb{};
     Pb.B = B; Pb.n = n; Pb.k = k; Pb.train_stride = train_stride; Pb.p = p; Pb.deg = deg;
@@ -633,6 +641,7 @@ static void fill_eval(EvalParams& E, const mrbf_model* m, int64_t M, const doubl
     E.B = m->B; E.n = m->n; E.k = m->k; E.train_stride = m->train_stride; E.p = m->p; E.deg = m->deg;
     E.kernel = m->kernel; E.ibeta = m->ibeta; E.sgn = m->sgn; E.M = M;
     E.N = m->N; E.centers = m->centers; E.w = m->w; E.lam = m->lam; E.alpha2 = m->alpha2; E.X = X; E.Y = Y; E.J = J;
+    E.pack = m->pack_valid ? m->pack : nullptr; E.pack_s = m->pack_s; E.pack_nt = m->pack_nt; E.pack_tile_doubles = m->pack_tile_doubles;
 }
 
 int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X, double* Y, double* J) {
@@ -640,6 +649,22 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
     if (M == 0 || (!Y && !J)) return MRBF_OK;
     CK(cudaSetDevice(ctx->device));
     int nl = 0;
+    if (!J && m->pack_tile_doubles && !m->pack_valid) {
+        // first values-only evaluation of this model: re-tile it once for the tensor-path sweep (the handle is logically const)
+        mrbf_model* mm = const_cast<mrbf_model*>(m);
+        if (!mm->pack) {
+            cudaError_t e = cudaMalloc(&mm->pack, sizeof(double) * (size_t)m->B * m->pack_nt * m->pack_tile_doubles);
+            if (e != cudaSuccess) { mm->pack = nullptr; mm->pack_tile_doubles = 0; }
+        }
+        if (mm->pack) {
+            PackParams K{};
+            K.B = m->B; K.n = m->n; K.k = m->k; K.train_stride = m->train_stride; K.s = m->pack_s; K.nt = m->pack_nt;
+            K.tile_doubles = m->pack_tile_doubles; K.N = m->N; K.centers = m->centers; K.w = m->w; K.pack = mm->pack;
+            CK(launch_eval_pack(K, ctx->stream));
+            ctx->launches += 1;
+            mm->pack_valid = true;
+        }
+    }
     EvalParams E{};
     fill_eval(E, m, M, X, Y, J);       // with J the same pass also produces the values
     { Timed t_(ctx, 4); CK(launch_eval(E, ctx->stream, &nl)); }

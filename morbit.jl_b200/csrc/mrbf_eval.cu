@@ -250,6 +250,224 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(EvalParams P) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Values-only sweep on the FP64 tensor path (DMMA, mma.sync m8n8k4 f64) with TMA-staged centre tiles.
+//
+// The model is re-tiled once (eval_pack_kernel): per 64 centres one contiguous block
+//     [64 x s centred centre rows | 64 squared norms | k x 64 coefficients],   s = padded row stride (= 4 mod 16 doubles,
+// so the 8 rows x 4 doubles of an operand fragment fall into two conflict-free shared-memory wavefronts).
+// A CTA owns 128 trial points (X' tile staged once) and streams the centre tiles with cp.async.bulk (TMA 1-D bulk
+// copy) into a two-deep ring guarded by mbarriers, so the copy of tile t+1 overlaps the tensor work of tile t.
+// 8 warps = 4 (point direction) x 2 (centre direction); a warp computes a 32 x 32 block of X'C'^T as 4 x 4 DMMA
+// fragments (16 independent accumulator chains), then rho^2 = |x'|^2 + |c'|^2 - 2 D, phi, and the weighted row sums.
+// ------------------------------------------------------------------------------------------------
+constexpr int DM_TM = 128;   // trial points per CTA
+constexpr int DM_TN = 64;    // centres per tile
+
+__host__ __device__ inline int pack_stride(int n) {
+    int s = (n + 3) & ~3;
+    while ((s & 15) != 4 && (s & 15) != 12) s += 4;
+    return s;
+}
+int eval_pack_stride(int n) { return pack_stride(n); }
+
+__global__ void eval_pack_kernel(PackParams P) {
+    const int b = blockIdx.y, t = blockIdx.x, n = P.n, k = P.k, s = P.s, tid = threadIdx.x, nt = blockDim.x;
+    const int N = P.N[b];
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* w = P.w + (size_t)b * P.train_stride * k;
+    double* out = P.pack + ((size_t)b * P.nt + t) * P.tile_doubles;
+    double* cc = out + (size_t)DM_TN * s;
+    double* Wt = cc + DM_TN;
+    for (int e = tid; e < DM_TN * s; e += nt) {
+        const int j = e / s, c = e % s, gi = t * DM_TN + j;
+        out[e] = (gi < N && c < n) ? centers[(size_t)gi * n + c] - centers[c] : 0.0;
+    }
+    for (int j = tid; j < DM_TN; j += nt) {
+        const int gi = t * DM_TN + j;
+        double a = 0.0;
+        if (gi < N) for (int c = 0; c < n; ++c) { double d = centers[(size_t)gi * n + c] - centers[c]; a = fma(d, d, a); }
+        cc[j] = a;
+    }
+    for (int e = tid; e < k * DM_TN; e += nt) {
+        const int l = e / DM_TN, j = e % DM_TN, gi = t * DM_TN + j;
+        Wt[e] = (gi < N) ? w[(size_t)gi * k + l] : 0.0;
+    }
+}
+
+cudaError_t launch_eval_pack(const PackParams& P, cudaStream_t s) {
+    dim3 grid((unsigned)P.nt, (unsigned)P.B);
+    eval_pack_kernel<<<grid, 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0, int kk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.y, n = P.n, k = P.k, s = P.pack_s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int tile_d = (int)P.pack_tile_doubles;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);          // 2 mbarriers
+    double* buf0 = reinterpret_cast<double*>(smem_raw + 128);
+    double* buf1 = buf0 + tile_d;
+    double* Xs = buf1 + tile_d;                  // DM_TM x s
+    double* xx = Xs + DM_TM * s;                 // DM_TM
+    double* Yp = xx + DM_TM;                     // 2 x DM_TM x 4  partial sums of the two centre-direction warps
+    const long long m0 = (long long)blockIdx.x * DM_TM;
+    const int N = P.N[b];
+    const int ntiles = (N + DM_TN - 1) / DM_TN;
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* X = P.X + (size_t)b * P.M * n;
+    const double* pack = P.pack + (size_t)b * P.pack_nt * P.pack_tile_doubles;
+    const int pl = P.p > 0 ? P.p : 1;
+    const double* lam = P.lam + (size_t)b * pl * k;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn; rf.alpha2 = P.alpha2[b];
+    const unsigned tile_bytes = (unsigned)(tile_d * sizeof(double));
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (ntiles > 0) {                        // tile 0 -> buffer 0
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(buf0)), "l"(pack), "r"(tile_bytes), "r"(smem_u32(&bar[0])) : "memory");
+        }
+    }
+    // X' tile: rows centred at the first centre, zero padded to the row stride
+    for (int e = tid; e < DM_TM * s; e += 256) {
+        const int pt = e / s, c = e % s;
+        const long long mi = m0 + pt;
+        Xs[e] = (mi < P.M && c < n) ? X[(size_t)mi * n + c] - centers[c] : 0.0;
+    }
+    __syncthreads();
+    if (tid < DM_TM) { double a = 0.0; for (int c = 0; c < n; ++c) { double v = Xs[tid * s + c]; a = fma(v, v, a); } xx[tid] = a; }
+    __syncthreads();
+
+    const int qr = lane >> 2, qc = lane & 3;     // fragment coordinates: row T/4, k-offset / column pair T%4
+    double xr[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xr[a] = xx[32 * wm + 8 * a + qr];
+    double ysum[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) ysum[a][l] = 0.0;
+    const int ksteps = ((n + 3) & ~3) >> 2;
+    const double* xa = Xs + (32 * wm + qr) * s + qc;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int cur = t & 1;
+        if (tid == 0 && t + 1 < ntiles) {        // prefetch tile t+1 into the other buffer (its readers passed the barrier below)
+            const int nb = cur ^ 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(nb ? buf1 : buf0)), "l"(pack + (size_t)(t + 1) * tile_d), "r"(tile_bytes), "r"(smem_u32(&bar[nb])) : "memory");
+        }
+        {                                        // wait for tile t
+            const unsigned parity = (unsigned)((t >> 1) & 1);
+            unsigned ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bar[cur])), "r"(parity) : "memory");
+            }
+        }
+        const double* Cs = cur ? buf1 : buf0;
+        const double* ccs = Cs + DM_TN * s;
+        const double* Wt = ccs + DM_TN;
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+        const double* cb = Cs + (32 * wn + qr) * s + qc;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) fa[a] = xa[8 * a * s + 4 * ks];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fb[c] = cb[8 * c * s + 4 * ks];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dmma884(acc[a][c], fa[a], fb[c]);
+        }
+        // epilogue of the tile: D[row qr + 8a][col 2 qc + e + 8c]
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 32 * wn + 8 * c + 2 * qc + e;
+                const double ccv = ccs[col];
+                double wv[4];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) wv[l] = (l < kk) ? Wt[l * DM_TN + col] : 0.0;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    double r2 = fma(-2.0, acc[a][c][e], xr[a] + ccv);
+                    r2 = fmax(r2, 0.0);
+                    const double ph = rad_phi(rf, r2);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) if (l < kk) ysum[a][l] = fma(ph, wv[l], ysum[a][l]);
+                }
+            }
+        __syncthreads();                         // everyone is done with buffer `cur`
+    }
+    // reduce over the 4 lanes of a quad (column pairs), then over the two centre-direction warps through shared memory
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            double v = ysum[a][l];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (qc == 0) Yp[(wn * DM_TM + 32 * wm + 8 * a + qr) * 4 + l] = v;
+        }
+    __syncthreads();
+    if (tid < DM_TM) {
+        const long long mi = m0 + tid;
+        if (mi < P.M) {
+            for (int l = 0; l < kk; ++l) {
+                double v = Yp[tid * 4 + l] + Yp[(DM_TM + tid) * 4 + l];
+                if (P.deg >= 0) v += lam[l0 + l];
+                if (P.deg >= 1) {
+                    double tsum = 0.0;
+                    for (int c = 0; c < n; ++c) tsum = fma(lam[(size_t)(c + 1) * k + l0 + l], Xs[tid * s + c] + centers[c], tsum);
+                    v += tsum;
+                }
+                P.Y[((size_t)b * P.M + mi) * k + l0 + l] = v;
+            }
+        }
+    }
+}
+
+static cudaError_t launch_dmma(const EvalParams& P, cudaStream_t s, int* n_launches) {
+    const int st = P.pack_s;
+    const size_t smem = 128 + sizeof(double) * (2 * P.pack_tile_doubles + (size_t)DM_TM * st + DM_TM + 2 * DM_TM * 4);
+    cudaError_t e = cudaFuncSetAttribute(eval_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long tiles = (P.M + DM_TM - 1) / DM_TM;
+    for (int l0 = 0; l0 < P.k; l0 += 4) {
+        const int kk = (P.k - l0) < 4 ? (P.k - l0) : 4;
+        dim3 grid((unsigned)tiles, (unsigned)P.B);
+        eval_dmma_kernel<<<grid, 256, smem, s>>>(P, l0, kk);
+        if (n_launches) ++*n_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 template <int CQ, bool WANT_J>
 static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launches) {
     constexpr int ND = 16 * CQ, KG = WANT_J ? 2 : 4;
@@ -272,6 +490,7 @@ static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launc
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
     if (P.M <= 0 || P.B <= 0) return cudaSuccess;
     const bool want_j = P.J != nullptr;
+    if (!want_j && P.pack && P.n <= 64 && P.B <= 65535 && P.k <= 16) return launch_dmma(P, s, n_launches);
     if (P.n <= 64 && P.B <= 65535) {
         const int cq = (P.n + 15) / 16;
         if (want_j) {

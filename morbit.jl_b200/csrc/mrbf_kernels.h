@@ -78,6 +78,14 @@ struct EvalParams {
     long long M;
     const int* N; const double* centers; const double* w; const double* lam; const double* alpha2;
     const double* X; double* Y; double* J;
+    // tiled, centred copy of the model for the DMMA kernel (built once per model): per instance nt tiles of
+    // [64 x s centre rows | 64 squared norms | k x 64 coefficients]
+    const double* pack; int pack_s, pack_nt; size_t pack_tile_doubles;
+};
+
+struct PackParams {
+    int B, n, k, train_stride, s, nt; size_t tile_doubles;
+    const int* N; const double* centers; const double* w; double* pack;
 };
 
 struct BacktrackParams {
@@ -107,6 +115,8 @@ cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s);
 size_t build_prepared_smem_doubles(int n, int k, int NM, int p);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);
+cudaError_t launch_eval_pack(const PackParams& P, cudaStream_t s);
+int eval_pack_stride(int n);
 cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s);
 cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s);
 
