@@ -649,8 +649,8 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
     if (M == 0 || (!Y && !J)) return MRBF_OK;
     CK(cudaSetDevice(ctx->device));
     int nl = 0;
-    if (!J && m->pack_tile_doubles && !m->pack_valid) {
-        // first values-only evaluation of this model: re-tile it once for the tensor-path sweep (the handle is logically const)
+    if (m->pack_tile_doubles && !m->pack_valid) {
+        // first evaluation of this model: re-tile it once for the tensor-path sweep (the handle is logically const)
         mrbf_model* mm = const_cast<mrbf_model*>(m);
         if (!mm->pack) {
             cudaError_t e = cudaMalloc(&mm->pack, sizeof(double) * (size_t)m->B * m->pack_nt * m->pack_tile_doubles);

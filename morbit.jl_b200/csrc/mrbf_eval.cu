@@ -468,6 +468,196 @@ static cudaError_t launch_dmma(const EvalParams& P, cudaStream_t s, int* n_launc
     return cudaSuccess;
 }
 
+
+// Values + Jacobian on the FP64 tensor path, one output per pass.  8 warps x 16 trial points; a warp sweeps all 64
+// centres of a tile:  phase 1  D = X'C'^T (2 x 8 DMMA fragments)  ->  phi, psi;  G = psi .* w stays in the accumulator
+// registers and is re-shaped from the C-fragment to the A-fragment layout with two quad shuffles per fragment;
+// phase 2  Jacc += G C' (2 x ceil(n/8) fragments).  J = x' rowsum(G) - Jacc + lambda.  No shared-memory round trip
+// and no CTA barrier between the two contractions.
+__global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int l0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.y, n = P.n, k = P.k, s = P.pack_s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_d = (int)P.pack_tile_doubles;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
+    double* buf0 = reinterpret_cast<double*>(smem_raw + 128);
+    double* buf1 = buf0 + tile_d;
+    double* Xs = buf1 + tile_d;                  // DM_TM x s
+    double* xx = Xs + DM_TM * s;                 // DM_TM
+    const long long m0 = (long long)blockIdx.x * DM_TM;
+    const int N = P.N[b];
+    const int ntiles = (N + DM_TN - 1) / DM_TN;
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* X = P.X + (size_t)b * P.M * n;
+    const double* pack = P.pack + (size_t)b * P.pack_nt * P.pack_tile_doubles;
+    const int pl = P.p > 0 ? P.p : 1;
+    const double* lam = P.lam + (size_t)b * pl * k;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn; rf.alpha2 = P.alpha2[b];
+    const unsigned tile_bytes = (unsigned)(tile_d * sizeof(double));
+    const int ncb = (n + 7) >> 3;                // coordinate blocks of 8
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (ntiles > 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(buf0)), "l"(pack), "r"(tile_bytes), "r"(smem_u32(&bar[0])) : "memory");
+        }
+    }
+    for (int e = tid; e < DM_TM * s; e += 256) {
+        const int pt = e / s, c = e % s;
+        const long long mi = m0 + pt;
+        Xs[e] = (mi < P.M && c < n) ? X[(size_t)mi * n + c] - centers[c] : 0.0;
+    }
+    __syncthreads();
+    if (tid < DM_TM) { double a = 0.0; for (int c = 0; c < n; ++c) { double v = Xs[tid * s + c]; a = fma(v, v, a); } xx[tid] = a; }
+    __syncthreads();
+
+    const int qr = lane >> 2, qc = lane & 3;
+    const int row0 = 16 * warp;
+    double xr[2] = {xx[row0 + qr], xx[row0 + 8 + qr]};
+    double ysum[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
+    double jacc[2][8][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { jacc[a][c][0] = 0.0; jacc[a][c][1] = 0.0; }
+    const int ksteps = ((n + 3) & ~3) >> 2;
+    const double* xa = Xs + (row0 + qr) * s + qc;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int cur = t & 1;
+        if (tid == 0 && t + 1 < ntiles) {
+            const int nb = cur ^ 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(nb ? buf1 : buf0)), "l"(pack + (size_t)(t + 1) * tile_d), "r"(tile_bytes), "r"(smem_u32(&bar[nb])) : "memory");
+        }
+        {
+            const unsigned parity = (unsigned)((t >> 1) & 1);
+            unsigned ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bar[cur])), "r"(parity) : "memory");
+            }
+        }
+        const double* Cs = cur ? buf1 : buf0;
+        const double* ccs = Cs + DM_TN * s;
+        const double* Wt = ccs + DM_TN + (size_t)l0 * DM_TN;
+        double acc[2][8][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+        const double* cb = Cs + qr * s + qc;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {     // phase 1
+            const double fa0 = xa[4 * ks], fa1 = xa[8 * s + 4 * ks];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double fb = cb[8 * c * s + 4 * ks];
+                dmma884(acc[0][c], fa0, fb);
+                dmma884(acc[1][c], fa1, fb);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * c + 2 * qc + e;
+                const double ccv = ccs[col], wv = Wt[col];
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    double r2 = fma(-2.0, acc[a][c][e], xr[a] + ccv);
+                    r2 = fmax(r2, 0.0);
+                    double ph, ps;
+                    rad_phi_psi(rf, r2, ph, ps);
+                    ysum[a] = fma(ph, wv, ysum[a]);
+                    const double g = ps * wv;
+                    gsum[a] += g;
+                    acc[a][c][e] = g;              // G in C-fragment layout
+                }
+            }
+        // phase 2: Jacc += G (16 x 64) * C' (64 x 8 ncb)
+#pragma unroll
+        for (int kc = 0; kc < 16; ++kc) {
+            const int c = kc >> 1, h = kc & 1;
+            const int src = (lane & ~3) | (2 * h + (qc >> 1));
+            double fa[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const double v0 = __shfl_sync(0xffffffffu, acc[a][c][0], src);
+                const double v1 = __shfl_sync(0xffffffffu, acc[a][c][1], src);
+                fa[a] = (qc & 1) ? v1 : v0;
+            }
+            const double* brow = Cs + (4 * kc + qc) * s + qr;
+#pragma unroll
+            for (int cbk = 0; cbk < 8; ++cbk) {
+                if (cbk < ncb) {
+                    const double fb = brow[8 * cbk];
+                    dmma884(jacc[0][cbk], fa[0], fb);
+                    dmma884(jacc[1][cbk], fa[1], fb);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        double v = ysum[a], g = gsum[a];
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+        g += __shfl_xor_sync(0xffffffffu, g, 1); g += __shfl_xor_sync(0xffffffffu, g, 2);
+        ysum[a] = v; gsum[a] = g;
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int row = row0 + 8 * a + qr;
+        const long long mi = m0 + row;
+        if (mi >= P.M) continue;
+        if (P.Y && qc == 0) {
+            double v = ysum[a];
+            if (P.deg >= 0) v += lam[l0];
+            if (P.deg >= 1) {
+                double tsum = 0.0;
+                for (int c = 0; c < n; ++c) tsum = fma(lam[(size_t)(c + 1) * k + l0], Xs[row * s + c] + centers[c], tsum);
+                v += tsum;
+            }
+            P.Y[((size_t)b * P.M + mi) * k + l0] = v;
+        }
+        double* Jrow = P.J + (((size_t)b * P.M + mi) * k + l0) * n;
+#pragma unroll
+        for (int cbk = 0; cbk < 8; ++cbk)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * cbk + 2 * qc + e;
+                if (cbk < ncb && col < n) {
+                    double val = fma(Xs[row * s + col], gsum[a], -jacc[a][cbk][e]);
+                    if (P.deg >= 1) val += lam[(size_t)(col + 1) * k + l0];
+                    Jrow[col] = val;
+                }
+            }
+    }
+}
+
+static cudaError_t launch_dmma_jac(const EvalParams& P, cudaStream_t s, int* n_launches) {
+    const int st = P.pack_s;
+    const size_t smem = 128 + sizeof(double) * (2 * P.pack_tile_doubles + (size_t)DM_TM * st + DM_TM);
+    cudaError_t e = cudaFuncSetAttribute(eval_dmma_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long tiles = (P.M + DM_TM - 1) / DM_TM;
+    for (int l0 = 0; l0 < P.k; ++l0) {
+        dim3 grid((unsigned)tiles, (unsigned)P.B);
+        eval_dmma_jac_kernel<<<grid, 256, smem, s>>>(P, l0);
+        if (n_launches) ++*n_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 template <int CQ, bool WANT_J>
 static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launches) {
     constexpr int ND = 16 * CQ, KG = WANT_J ? 2 : 4;
@@ -490,7 +680,7 @@ static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launc
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
     if (P.M <= 0 || P.B <= 0) return cudaSuccess;
     const bool want_j = P.J != nullptr;
-    if (!want_j && P.pack && P.n <= 64 && P.B <= 65535 && P.k <= 16) return launch_dmma(P, s, n_launches);
+    if (P.pack && P.n <= 64 && P.B <= 65535 && P.k <= 16) return want_j ? launch_dmma_jac(P, s, n_launches) : launch_dmma(P, s, n_launches);
     if (P.n <= 64 && P.B <= 65535) {
         const int cq = (P.n + 15) / 16;
         if (want_j) {
