@@ -101,22 +101,24 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
             st.xp[c] = a;
         }
         __syncthreads();
-        if (tid == 0) {                           // dlarfg on xp[0..nw)
-            double alpha = st.xp[0], xnorm = 0.0;
-            for (int c = 1; c < nw; ++c) xnorm = hypot(xnorm, st.xp[c]);
-            double tau = 0.0;
-            st.vv[0] = 1.0;
+        if (tid < 32) {                           // dlarfg on xp[0..nw), one warp
+            const double alpha = st.xp[0];
+            double ss = 0.0;
+            for (int c = 1 + tid; c < nw; c += 32) ss = fma(st.xp[c], st.xp[c], ss);
+            const double xnorm = sqrt(warp_sum(ss));
+            double tau = 0.0, sc = 0.0;
             if (xnorm != 0.0) {
-                double beta = -copysign(hypot(alpha, xnorm), alpha);
+                const double beta = -copysign(hypot(alpha, xnorm), alpha);
                 tau = (beta - alpha) / beta;
-                double sc = 1.0 / (alpha - beta);
-                for (int c = 1; c < nw; ++c) st.vv[c] = st.xp[c] * sc;
-            } else {
-                for (int c = 1; c < nw; ++c) st.vv[c] = 0.0;
+                sc = 1.0 / (alpha - beta);
             }
-            st.red[70] = tau;
-            cflags[best.id] |= CF_USED;
-            out[found] = best.id + 1;
+            for (int c = 1 + tid; c < nw; c += 32) st.vv[c] = st.xp[c] * sc;
+            if (tid == 0) {
+                st.vv[0] = 1.0;
+                st.red[70] = tau;
+                cflags[best.id] |= CF_USED;
+                out[found] = best.id + 1;
+            }
         }
         __syncthreads();
         const double tau = st.red[70];
@@ -139,47 +141,60 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
         }
         __syncthreads();
         if (found == n_wanted) break;
-        // ---- score the remaining candidates: || Z (Z' s) ||_inf, strict '>' => first maximiser
+        // ---- score the remaining candidates: || Z (Z' s) ||_inf, strict '>' => first maximiser.
+        // G threads share a candidate (t = Z's split by columns, r = Z t split by rows); every dot product keeps
+        // its sequential accumulation order, so the scores do not depend on G.
         mine.v = 0.0; mine.id = -1;
-        for (int id = tid; id < n_db; id += nt) {
-            unsigned f = cflags[id];
-            if ((f & want) != want || (f & (CF_USED | avoid))) continue;
-            const double* s = S + id;
-            double* t = T + id;
-            double v = 0.0;
-            int c = 0;
-            for (; c + 4 <= zc; c += 4) {         // t = Z' s, four independent chains
-                const double* z0 = st.Z + c * ldz; const double* z1 = z0 + ldz;
-                const double* z2 = z1 + ldz; const double* z3 = z2 + ldz;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                for (int i = 0; i < n; ++i) {
-                    double si = s[i * ldS];
-                    a0 = fma(z0[i], si, a0); a1 = fma(z1[i], si, a1); a2 = fma(z2[i], si, a2); a3 = fma(z3[i], si, a3);
+        {
+            const int G = (n_db > 128) ? 1 : ((n_db > 64) ? 2 : ((n_db > 32) ? 4 : 8));
+            const int cpp = nt / G;
+            for (int c0 = 0; c0 < n_db; c0 += cpp) {
+                const int id = c0 + tid / G, h = tid % G;
+                bool act = false;
+                if (id < n_db) { unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
+                const double* s = S + id;
+                double* t = T + id;
+                double v = 0.0;
+                if (act) {
+                    int c = h;
+                    for (; c + 3 * G < zc; c += 4 * G) {      // t = Z' s, four independent chains
+                        const double* z0 = st.Z + c * ldz; const double* z1 = z0 + G * ldz;
+                        const double* z2 = z1 + G * ldz; const double* z3 = z2 + G * ldz;
+                        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                        for (int i = 0; i < n; ++i) {
+                            const double si = s[i * ldS];
+                            a0 = fma(z0[i], si, a0); a1 = fma(z1[i], si, a1); a2 = fma(z2[i], si, a2); a3 = fma(z3[i], si, a3);
+                        }
+                        t[c * ldS] = a0; t[(c + G) * ldS] = a1; t[(c + 2 * G) * ldS] = a2; t[(c + 3 * G) * ldS] = a3;
+                    }
+                    for (; c < zc; c += G) {
+                        const double* z0 = st.Z + c * ldz;
+                        double a0 = 0;
+                        for (int i = 0; i < n; ++i) a0 = fma(z0[i], s[i * ldS], a0);
+                        t[c * ldS] = a0;
+                    }
                 }
-                t[c * ldS] = a0; t[(c + 1) * ldS] = a1; t[(c + 2) * ldS] = a2; t[(c + 3) * ldS] = a3;
-            }
-            for (; c < zc; ++c) {
-                const double* z0 = st.Z + c * ldz;
-                double a0 = 0;
-                for (int i = 0; i < n; ++i) a0 = fma(z0[i], s[i * ldS], a0);
-                t[c * ldS] = a0;
-            }
-            int i = 0;
-            for (; i + 4 <= n; i += 4) {          // r = Z t, inf-norm
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                for (int q = 0; q < zc; ++q) {
-                    const double* zq = st.Z + q * ldz + i; double tq = t[q * ldS];
-                    a0 = fma(zq[0], tq, a0); a1 = fma(zq[1], tq, a1); a2 = fma(zq[2], tq, a2); a3 = fma(zq[3], tq, a3);
+                __syncwarp();
+                if (act) {
+                    int i = h;
+                    for (; i + 3 * G < n; i += 4 * G) {       // r = Z t, inf-norm
+                        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                        for (int q = 0; q < zc; ++q) {
+                            const double* zq = st.Z + q * ldz + i; const double tq = t[q * ldS];
+                            a0 = fma(zq[0], tq, a0); a1 = fma(zq[G], tq, a1); a2 = fma(zq[2 * G], tq, a2); a3 = fma(zq[3 * G], tq, a3);
+                        }
+                        v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
+                    }
+                    for (; i < n; i += G) {
+                        double a0 = 0;
+                        for (int q = 0; q < zc; ++q) a0 = fma(st.Z[i + q * ldz], t[q * ldS], a0);
+                        v = fmax(v, fabs(a0));
+                    }
                 }
-                v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
+                for (int o = G >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+                __syncwarp();
+                if (act && h == 0) { ArgMax cnd; cnd.v = v; cnd.id = id; mine = better(mine, cnd); }
             }
-            for (; i < n; ++i) {
-                double a0 = 0;
-                for (int q = 0; q < zc; ++q) a0 = fma(st.Z[i + q * ldz], t[q * ldS], a0);
-                v = fmax(v, fabs(a0));
-            }
-            ArgMax cnd; cnd.v = v; cnd.id = id;
-            mine = better(mine, cnd);
         }
         best = block_argmax(mine, st.red, st.redi);
         if (best.id < 0) break;                   // no more candidates

@@ -1,0 +1,249 @@
+"""The reference's own test file (test/rbf_models.jl) and the BASELINE single-instance configs C1/C2/C4, driven through
+the Python mirror of the plugin interface (same method names as the Julia shim) with the oracle as the checker."""
+import numpy as np
+import pytest
+
+import morbit_jl_b200 as mb
+from morbit_jl_b200 import synthetic
+from oracle import c_oracle as CO
+from oracle import rbf_oracle as O
+
+pytestmark = pytest.mark.gpu
+f1 = lambda x: np.array([np.sum(np.asarray(x)**2)])       # test/rbf_models.jl:4
+
+
+def _initialize(cfg, n, constrained, rng, algo_max_evals=mb.surrogate.INT_MAX):
+    """test/rbf_models.jl:6-25 (initialize_data with one RBF objective)."""
+    scal = mb.VarScaler(np.zeros(n) if constrained else np.full(n, -np.inf), np.ones(n) if constrained else np.full(n, np.inf))
+    x0 = rng.random(n)
+    db = mb.ArrayDB(n)
+    xi = db.new_result(x0, f1(x0))
+    fi = ("f1",)
+    sdb = mb.SuperDB({fi: db})
+    it = mb.IterData(x0, float(np.float32(0.1)), {fi: xi})
+    ac = mb.AlgoConfig(max_evals=algo_max_evals)
+    mop = mb.MopStub({"f1": 1})
+    meta = mb.prepare_init_model(cfg, fi, mop, scal, it, sdb, ac)
+    n_evals = 1 + db.eval_missing(f1)
+    mod, meta = mb.init_model(meta, cfg, fi, mop, scal, it, sdb, ac)
+    return fi, mop, scal, it, sdb, ac, db, meta, mod, n_evals
+
+
+@pytest.mark.parametrize("n", [2, 5, 10])
+@pytest.mark.parametrize("kernel", ["cubic", "inv_multiquadric", "multiquadric", "gaussian"])
+@pytest.mark.parametrize("deg", [-1, 0, 1])
+@pytest.mark.parametrize("constrained", [True, False])
+def test_rbf_models_jl(n, kernel, deg, constrained):
+    rng = np.random.default_rng(1234 + 7 * n + deg)
+    # :35-44  max_evals = 1, max_model_points = 1 -> one evaluation, model from a single point
+    cfg = mb.RbfConfig(kernel=kernel, polynomial_degree=deg, max_evals=1, max_model_points=1)
+    fi, mop, scal, it, sdb, ac, db, meta, mod, n_evals = _initialize(cfg, n, constrained, rng)
+    assert n_evals == 1
+    assert np.allclose(mb.eval_models(mod, scal, it.x_scaled), f1(it.x_scaled))
+    # :47-59  50 n unevaluated sites in the local box -> fully linear after update_surrogates!
+    if deg == 1:
+        lb, ub = np.maximum(scal.lb, it.x_scaled - it.delta), np.minimum(scal.ub, it.x_scaled + it.delta)
+        for _ in range(50 * n):
+            db.new_result(lb + (ub - lb) * rng.random(n), None)
+        meta = mb.prepare_update_model(mod, meta, cfg, fi, mop, scal, it, sdb, ac, ensure_fully_linear=True)
+        db.eval_missing(f1)
+        mod, meta = mb.update_model(mod, meta, cfg, fi, mop, scal, it, sdb, ac)
+        assert mb.fully_linear(mod)
+    # :67-71  budget via the algorithm config
+    cfg = mb.RbfConfig(kernel=kernel, polynomial_degree=deg)
+    fi, mop, scal, it, sdb, ac, db, meta, mod, n_evals = _initialize(cfg, n, constrained, rng, algo_max_evals=1)
+    assert n_evals == 1
+    # :74-86  _rbf_round4 with only the centre as found index and 10 n candidates
+    x = it.x_scaled
+    lb2, ub2 = np.maximum(scal.lb, x - cfg.theta_enlarge_2 * ac.delta_max), np.minimum(scal.ub, x + cfg.theta_enlarge_2 * ac.delta_max)
+    for _ in range(10 * n):
+        db.new_result(lb2 + (ub2 - lb2) * rng.random(n), None)
+    r4 = mb._rbf_round4(db, lb2, ub2, x, it.delta, [it.x_indices[fi]], cfg)
+    ocfg = O.RbfConfig(kernel=kernel, polynomial_degree=deg)
+    ref, _ = CO.round4(ocfg, db.sites_array(), lb2, ub2, [it.x_indices[fi]])
+    assert r4 == [int(v) for v in ref]
+    # :89-96  default config: fully linear at init
+    if deg == 1:
+        fi, mop, scal, it, sdb, ac, db, meta, mod, n_evals = _initialize(cfg, n, constrained, rng)
+        assert mb.fully_linear(mod) and n_evals == n + 1
+    # :104-111  interpolation at the centre, gradient == Jacobian row, gradient ~ finite differences
+    x = it.x_scaled
+    assert np.allclose(mb.eval_models(mod, scal, x)[-1], f1(x)[0])
+    dm = mb.get_gradient(mod, scal, x, 1)
+    assert np.array_equal(dm, mb.get_jacobian(mod, scal, x)[0])
+    h = 1e-6
+    fd = np.array([(mb.eval_models(mod, scal, x + h * e)[-1] - mb.eval_models(mod, scal, x - h * e)[-1]) / (2 * h) for e in np.eye(n)])
+    assert np.allclose(dm, fd, rtol=1e-4, atol=1e-5)
+    assert np.allclose(mb.eval_models(mod, scal, x, [1]), mb.eval_models(mod, scal, x)[:1])
+
+
+def test_rounds_1_to_3_shared_between_kernels():
+    """test/rbf_models.jl:123-168: two groups differing only in the kernel share rounds 1-3 by site."""
+    rng = np.random.default_rng(5)
+    n = 2
+    cfg1, cfg2 = mb.RbfConfig(kernel="gaussian"), mb.RbfConfig(kernel="multiquadric")
+    f2 = lambda x: np.array([np.sum(np.abs(x))])
+    x0 = rng.random(n)
+    db1, db2 = mb.ArrayDB(n), mb.ArrayDB(n)
+    i1 = db1.new_result(x0, f1(x0)); i2 = db2.new_result(x0, f2(x0))
+    for _ in range(20):
+        xi = rng.random(n)
+        db1.new_result(xi, None); db2.new_result(xi, None)
+    sdb = mb.SuperDB({("a",): db1, ("b",): db2})
+    scal = mb.VarScaler(np.full(n, -np.inf), np.full(n, np.inf))
+    it = mb.IterData(x0, 0.1, {("a",): i1, ("b",): i2})
+    ac = mb.AlgoConfig(max_evals=1)
+    mop = mb.MopStub({"a": 1, "b": 1})
+    m1 = mb.RbfMeta(signature=cfg1.signature(), func_indices=("a",))
+    m2 = mb.RbfMeta(signature=cfg2.signature(), func_indices=("b",))
+    meta_array = []
+    m1 = mb.prepare_update_model(None, m1, cfg1, ("a",), mop, scal, it, sdb, ac, ensure_fully_linear=True, meta_array=meta_array)
+    meta_array.append(m1)
+    m2 = mb.prepare_update_model(None, m2, cfg2, ("b",), mop, scal, it, sdb, ac, ensure_fully_linear=True, meta_array=meta_array)
+    for fn in ("round1_indices", "round2_indices", "round3_indices"):
+        a, b = getattr(m1, fn), getattr(m2, fn)
+        assert len(a) == len(b) and all(np.array_equal(db1.get_site(i), db2.get_site(j)) for i, j in zip(a, b))
+    db1.eval_missing(f1); db2.eval_missing(f2)
+    mod1, _ = mb.update_model(None, m1, cfg1, ("a",), mop, scal, it, sdb, ac)
+    mod2, _ = mb.update_model(None, m2, cfg2, ("b",), mop, scal, it, sdb, ac)
+    # container Jacobian ~ finite differences of container values (:164-168)
+    J = np.vstack([mb.get_jacobian(mod1, scal, x0), mb.get_jacobian(mod2, scal, x0)])
+    h = 1e-6
+    fd = np.array([[(mb.eval_models(m, scal, x0 + h * e)[0] - mb.eval_models(m, scal, x0 - h * e)[0]) / (2 * h) for e in np.eye(n)]
+                   for m in (mod1, mod2)])
+    assert np.allclose(J, fd, rtol=1e-4, atol=1e-5)
+
+
+def _common_descent(J):
+    """Minimum-norm element of the convex hull of the normalised gradients (k <= 2): a descent direction for every output,
+    so the Armijo loop stops at a moderate step instead of a rounding-noise decision at the minimum step size."""
+    G = J / np.maximum(np.linalg.norm(J, axis=1, keepdims=True), 1e-300)
+    if len(G) == 1:
+        return -G[0]
+    g1, g2 = G[0], G[1]
+    den = float(np.dot(g1 - g2, g1 - g2))
+    lam = 0.5 if den == 0 else float(np.clip(np.dot(g2 - g1, g2) / den, 0.0, 1.0))
+    return -(lam * g1 + (1 - lam) * g2)
+
+
+def _run_iterations(cfg, ocfg, func, x0, glb, gub, n_iter, delta0=0.1, delta_max=0.5):
+    """A small trust-region-like loop (iterate moves along the oracle model's descent direction, radius shrinks/grows)
+    that replays identical (database, iterate, radius) states through the plugin and the oracle."""
+    n = len(x0); k = len(func(x0))
+    fi = ("f",)
+    db = mb.ArrayDB(n); odb = O.ArrayDB()
+    xi = db.new_result(x0, func(x0)); odb.new_result(x0, func(x0))
+    sdb = mb.SuperDB({fi: db}); scal = mb.VarScaler(glb, gub); ac = mb.AlgoConfig(delta_max=delta_max); mop = mb.MopStub({"f": 1})
+    it = mb.IterData(x0.copy(), delta0, {fi: xi})
+    meta = mb.RbfMeta(signature=cfg.signature(), func_indices=fi); ometa = O.RbfMeta(signature=ocfg.signature())
+    mod = None
+    for t in range(n_iter):
+        efl = (t == 0) or (t % 3 == 2)
+        meta = mb.prepare_update_model(mod, meta, cfg, fi, mop, scal, it, sdb, ac, ensure_fully_linear=efl)
+        t4 = O.Round4Trace()
+        O.prepare_update_model(ometa, ocfg, odb, it.x_scaled, it.x_indices[fi], it.delta, delta_max, glb, gub, ensure_fully_linear=efl,
+                               num_objf_evals=mop.num_evals["f"], trace4=t4)
+        reordered = False
+        for fn in ("round1_indices", "round2_indices", "round3_indices", "round4_indices"):
+            a, e = getattr(meta, fn), getattr(ometa, fn)
+            if a != e and sorted(a) == sorted(e) and fn in ("round1_indices", "round2_indices"):
+                # exact-arithmetic tie between candidates (symmetric problem): the greedy order is decided by rounding in
+                # the reference as well; the selected SET must still agree.  The states diverge legitimately from here.
+                reordered = True
+                continue
+            if a != e and fn == "round4_indices" and any(abs(v) < 1e-12 for v in t4.tau2):
+                # a candidate that duplicates a training site: tau^2 is pure cancellation noise (-5e-17 here) and the
+                # reference's own `tau^2 > 1e-28` test is a coin flip on it; everything before that candidate must agree
+                kn = next(i for i, v in enumerate(t4.tau2) if abs(v) < 1e-12)
+                n_before = sum(t4.accepted[:kn])
+                assert a[:n_before] == e[:n_before], (t, fn, a, e)
+                reordered = True
+                continue
+            assert a == e or reordered, (t, fn, a, e)
+        if reordered:
+            return db.num_entries
+        assert meta.fully_linear == ometa.fully_linear and db.unevaluated_ids == odb.unevaluated_ids
+        assert db.num_entries == odb.num_entries
+        mop.num_evals["f"] += db.eval_missing(func); odb.eval_missing(func)
+        mod, meta = mb.update_model(mod, meta, cfg, fi, mop, scal, it, sdb, ac)
+        omod = O.update_model(ometa, ocfg, odb)
+        x = it.x_scaled
+        Yr, Jr = omod.eval(x), omod.jac(x)
+        Y, J = mb.eval_models(mod, scal, x), mb.get_jacobian(mod, scal, x)
+        assert np.abs(Y - Yr).max() <= 1e-10 * max(1.0, np.abs(Yr).max())
+        assert np.abs(J - Jr).max() <= 1e-9 * max(1.0, np.abs(Jr).max()), (t, np.abs(J - Jr).max())
+        d = _common_descent(Jr)
+        if np.abs(d).max() < 1e-6:
+            break                                                        # Pareto-critical for the model: nothing to compare
+        d = d / np.abs(d).max()
+        d = np.clip(x + it.delta * d, glb, gub) - x                      # stay inside the box and the trust region
+        if np.abs(d).max() < 1e-9:
+            break
+        xp, mxp, step = mb._backtrack(x, d / max(np.abs(d).max(), 1e-300), np.abs(d).max(), 0.1, mod)
+        xr, mr, sr, ir = O.backtrack(omod.eval, x, d / max(np.abs(d).max(), 1e-300), np.abs(d).max(), 0.1)
+        np.testing.assert_array_equal(xp, xr)
+        xr = np.clip(xr, glb, gub)              # Morbit's iterates are always feasible (rounding can leave the box by 1e-34)
+        fx = func(xr)
+        new_id = db.new_result(xr, fx); odb.new_result(xr, fx); mop.num_evals["f"] += 1
+        better = np.all(fx <= np.array(db.get_value(it.x_indices[fi])) + 1e-12)
+        if better:
+            it = mb.IterData(xr.copy(), min(delta_max, it.delta * 2.0), {fi: new_id})
+        else:
+            it = mb.IterData(x.copy(), it.delta * 0.75, it.x_indices)
+    return db.num_entries
+
+
+def test_c1_two_parabolas_iterations():
+    """BASELINE config C1: examples/example_two_parabolas.jl, n = 2, k = 2, cubic, unbounded."""
+    x0 = np.array([-np.pi, 2.71828])
+    n_entries = _run_iterations(mb.RbfConfig(kernel="cubic"), O.RbfConfig(kernel="cubic"), synthetic.two_parabolas, x0,
+                                np.full(2, -np.inf), np.full(2, np.inf), n_iter=10)
+    assert n_entries >= 13
+
+
+def test_c2_zdt1_n30_iterations():
+    """BASELINE config C2: ZDT1 n = 30, k = 2, multiquadric, boxed [0,1]^30, max_model_points 2n+1 as in large_scale_benchmarks.jl."""
+    x0 = synthetic.halton(1, 30)[0]
+    wts = 1.0 + np.arange(29) / 29.0          # weighted g: plain ZDT1 is symmetric in x_2..x_n, which makes the greedy
+    def zdt1w(X):                             # filter's candidate scores tie exactly (order then decided by rounding)
+        X = np.asarray(X); f1_ = X[..., 0]
+        g = 1.0 + 9.0 * np.sum(wts * X[..., 1:], axis=-1) / wts.sum()
+        return np.stack([f1_, g * (1.0 - np.sqrt(np.maximum(f1_, 0.0) / g))], axis=-1)
+    n_entries = _run_iterations(mb.RbfConfig(kernel="multiquadric", max_model_points=61),
+                                O.RbfConfig(kernel="multiquadric", max_model_points=61), zdt1w, x0, np.zeros(30), np.ones(30), n_iter=5)
+    assert n_entries >= 33
+    # plain (symmetric) ZDT1: ties are tolerated as set-equality
+    _run_iterations(mb.RbfConfig(kernel="multiquadric", max_model_points=61), O.RbfConfig(kernel="multiquadric", max_model_points=61),
+                    synthetic.zdt1, x0, np.zeros(30), np.ones(30), n_iter=5)
+
+
+def test_c4_n200_quadratic_select_and_build(engine):
+    """BASELINE config C4 (shape): n = 200, 5 outputs in one group, cubic with shape_parameter = 1.0 (phi = -rho) and default,
+    max_model_points = 2n+1 = 401; database of 300 sites (global-workspace variants of every kernel)."""
+    rng = np.random.default_rng(4)
+    n, k, n_db = 200, 5, 300
+    a = rng.random((k, n)); D = 0.5 + rng.random((k, n))
+    func = lambda X: np.stack([np.sum(D[j] * (X - a[j])**2, axis=-1) for j in range(k)], axis=-1)
+    x = 0.3 + 0.4 * rng.random(n)
+    sites = np.vstack((x[None], np.clip(x + (rng.random((n_db - 1, n)) * 2 - 1) * 0.25 * rng.random((n_db - 1, 1)), 0, 1)))
+    for shape in (1.0, float("nan")):
+        cfg = mb.RbfConfig(kernel="cubic", shape_parameter=shape, max_model_points=2 * n + 1, theta_enlarge_1=2.0, theta_pivot=0.25)
+        ref = CO.select_points_batched(cfg, sites[None], [1], x[None], [0.1], 0.5, np.zeros(n), np.ones(n), True, False, 2**31 - 1)
+        res = engine.select_points(cfg, sites[None], [n_db], [1], x[None], [0.1], 0.5, np.zeros(n), np.ones(n), True, False)
+        for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+            assert list(getattr(res, nm)[0, :getattr(res, cnt)[0]]) == list(getattr(ref, nm)[0, :getattr(ref, cnt)[0]]), nm
+        assert res.n_r3[0] == ref.n_r3[0]
+        np.testing.assert_allclose(res.r3_sites[0, :res.n_r3[0]], ref.r3_sites[0, :ref.n_r3[0]], rtol=0, atol=1e-13)
+        ids = [1] + list(res.r1[0, :res.n_r1[0]]) + list(res.r2[0, :res.n_r2[0]])
+        P = np.vstack([sites[np.array(ids) - 1], res.r3_sites[0, :res.n_r3[0]], sites[res.r4[0, :res.n_r4[0]].astype(int) - 1]])
+        V = func(P)
+        wr, lr, st = CO.build_batched(cfg, P[None], V[None], [len(P)])
+        model, status = engine.build(cfg, P[None], V[None], [len(P)])
+        X = x + 0.05 * (rng.random((8, n)) - 0.5)
+        Y, J = engine.eval(model, X[None], True, True)
+        Yr = CO.eval_points(cfg, P, wr[0], lr[0], X); Jr = CO.jac_points(cfg, P, wr[0], lr[0], X)
+        cond = O.build_model(P, V, O.RbfConfig(kernel="cubic", shape_parameter=shape)).cond
+        tol = max(1e-10, 20 * cond * np.finfo(float).eps)     # LU vs null-space solves differ at O(cond * eps): cond ~ 1e8 for rho^3 here
+        assert np.abs(Y[0] - Yr).max() <= 1e-10 * np.abs(Yr).max()
+        assert np.abs(J[0] - Jr).max() <= tol * np.abs(Jr).max(), (cond, np.abs(J[0] - Jr).max() / np.abs(Jr).max())
+        model.free()
