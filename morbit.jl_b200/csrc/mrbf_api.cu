@@ -156,11 +156,17 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
     R.chol_thr = t2 * t2;
     R.sites = sites; R.n_db = n_db; R.lb2 = lb2; R.ub2 = ub2; R.found = found; R.n_found = n_found;
     R.extra_sites = extra; R.n_extra = n_extra; R.r4 = r4; R.n_r4 = n_r4; R.status = status;
-    ENSURE(ctx->ws[6], (size_t)B * db_stride);
+    ENSURE(ctx->ws[6], (size_t)B * db_stride * 5);      // int candidate list + byte flags per database entry
     R.cand = (unsigned char*)ctx->ws[6].p;
     // 1. shared-memory fast path (regular case N0 == p); marks the instances it cannot take with n_r4 = -1
     {
-        const size_t fv = round4_fast_vec_doubles(n, NM, p), fsd = round4_fast_state_doubles(n, NM, p);
+        const size_t fsd = round4_fast_state_doubles(n, NM, p);
+        // block size: 8 candidates per block when the block buffers still fit beside the state in shared memory, else 4
+        int Tb = 8;
+        size_t fv = round4_block_vec_doubles(8, n, NM, p);
+        if ((fv + fsd) * sizeof(double) > SMEM_LIMIT && (round4_block_vec_doubles(4, n, NM, p) + fsd) * sizeof(double) <= SMEM_LIMIT) {
+            Tb = 4; fv = round4_block_vec_doubles(4, n, NM, p);
+        }
         size_t fsmem = fv * sizeof(double);
         if (fsmem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
         R.fs_stride = fsd;
@@ -191,7 +197,7 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             if (!keep_out) { ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double)); R.fs = (double*)ctx->ws[9].p; }
         }
         Timed t_(ctx, 1);
-        CK(launch_round4_fast(R, fsmem, ctx->stream));
+        CK(launch_round4_block(R, Tb, fsmem, ctx->stream));
         ctx->launches += 1;
     }
     // 2. literal kernel for the marked rest (N0 != p: budget-limited round 3, explicit found sets, rank-deficient Pi_0)

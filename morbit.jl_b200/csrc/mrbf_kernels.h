@@ -110,6 +110,8 @@ size_t build_ws_doubles(int n, int k, int ld, int p);
 cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid);
 cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s);
+cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s);
+size_t round4_block_vec_doubles(int T, int n, int NM, int p);
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s);
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s);

@@ -892,6 +892,439 @@ __global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
     }
 }
 
+template <int T, bool SMEM>
+__global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
+    // Blocked variant of the shared-memory round 4: T candidates are evaluated together against the factorisation as it was
+    // before the block (a rejected candidate never changes the state, so this speculation cannot fail); the few quantities
+    // that depend on which block members were accepted -- the extra Cholesky entries e_ij, the pivots d_j^2 and the
+    // leverages -- are resolved by an O(T^3) scalar "panel" step, exactly the recurrences of a blocked left-looking
+    // Cholesky.  Barriers per candidate drop from ~4 to ~9/T and every phase has T times more parallel work.
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = 256, lane = tid & 31, warp = tid >> 5, nwarps = 8;
+    const int NM = P.NM;
+    const int deg = P.cfg.polynomial_degree;
+    const int p = poly_dim(n, deg);
+    const int pl = p > 0 ? p : 1, pb = pl | 1;
+    const int MM = (NM - p) > 1 ? (NM - p) : 1;
+    // block buffers
+    double* XI = smem;                 // T x n    candidate sites
+    double* PH = XI + T * n;           // T x NM   kernel columns against the current centres
+    double* CV = PH + T * NM;          // T x pl   c_xi
+    double* UB = CV + T * pl;          // T x pl   u_xi = b_xi - Phi00 c_xi
+    double* HV = UB + T * pl;          // T x pl   H pi_xi
+    double* AV = HV + T * pl;          // T x MM   a_xi
+    double* TV = AV + T * MM;          // T x MM   t_xi = L^{-1} a_xi
+    double* Kx = TV + T * MM;          // T x T    phi(xi_i, xi_j)
+    double* Ax = Kx + T * T;           // T x T    A_ij (i < j), A_jj on the diagonal
+    double* Dx = Ax + T * T;           // T x T    t_i . t_j
+    double* Sx = Dx + T * T;           // T x T    pi_i' H pi_j (i < j), leverage on the diagonal
+    double* Ex = Sx + T * T;           // T x T    panel: e_ij (extra Cholesky entries), d_j on the diagonal
+    double* Px = Ex + T * T;           // T x T    panel: inverse of the accepted part of [e, d]
+    double* Sc = Px + T * T;           // T x T    panel: corrected s'_ij, 1 + lev'_j on the diagonal
+    double* tnp = Sc + T * T;          // 8 x T    per-warp partial ||t_j||^2
+    double* tauq = tnp + 8 * T;        // pl
+    double* red = tauq + pl;           // 80
+    int* ib = reinterpret_cast<int*>(red + 80);   // ids[T], acc[T], pos[T], misc[8]
+    double* st = red + 80 + 2 * T + 4;
+    double* fs;
+    if constexpr (SMEM) fs = st; else fs = (P.keep_fs ? P.keep_fs : P.fs) + (size_t)b * P.fs_stride;
+    double* Ct = fs;                   // NM x n  coordinate-major centres
+    double* M0 = Ct + NM * n;          // p x p   Pi_0^{-T}
+    double* P00 = M0 + pl * pl;        // p x p   Phi(S0, S0)
+    double* H = P00 + pl * pl;         // p x p   (Pi' Pi)^{-1} of the current point set
+    double* Aq = H + pl * pl;          // p x p   scratch (QR of Pi_0)
+    double* Qx = Aq + pl * pl;         // p x p   scratch (explicit Q_0)
+    double* Tm = Qx + pl * pl;         // p x p   scratch (R_0^{-1})
+    double* Gm = Tm + pl * pl;         // pb x MM  g_eta = Phi(S0, eta) - Phi00 c_eta
+    double* Cm = Gm + pb * MM;         // pb x MM  c_eta
+    double* Li = Cm + pb * MM;         // packed lower triangle of L^{-1}, row r at tri(r)
+
+    const int n_db = P.n_db[b];
+    const double* sites = P.sites + (size_t)b * P.db_stride * n;
+    const double* lb2 = P.lb2 + (size_t)b * n;
+    const double* ub2 = P.ub2 + (size_t)b * n;
+    const int* found = P.found + (size_t)b * P.found_stride;
+    const int nf_ids = P.n_found[b];
+    const int n_extra = P.n_extra ? P.n_extra[b] : 0;
+    const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
+    int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    const int N0 = nf_ids + n_extra;
+    const int max_points = P.max_points;
+    if (tid == 0 && P.elig) P.elig[b] = 0;
+    if (!(N0 < max_points) || N0 > NM) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = (N0 > NM) ? -1 : 0; } return; }
+    if (p > 0 && N0 != p) { if (tid == 0) P.n_r4[b] = -1; return; }         // literal kernel takes over
+
+    // compact, ascending candidate list (results_in_box_indices minus the found set)
+    unsigned char* cand = P.cand + (size_t)P.B * P.db_stride * sizeof(int) + (size_t)b * P.db_stride;
+    int* clist = reinterpret_cast<int*>(P.cand) + (size_t)b * P.db_stride;
+    for (int id = tid; id < n_db; id += nt) {
+        bool ok = in_box(sites + (size_t)id * n, lb2, ub2, n);
+        for (int f = 0; f < nf_ids && ok; ++f) ok = (found[f] != id + 1);
+        cand[id] = ok ? 1 : 0;
+    }
+    for (int e = tid; e < N0 * n; e += nt) {
+        int i = e / n, k = e % n;
+        Ct[k * NM + i] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
+    }
+    if (tid == 0) red[76] = 0.0;
+    __syncthreads();
+    // The polynomial basis is centred at the first found point and scaled by the spread of S0: c_xi and the
+    // leverage behind g_hat are invariant under that change of basis, and Pi_0 stays well conditioned for tiny Delta.
+    double inv_s = 1.0;
+    if (p > 1) {
+        double mx = 0.0;
+        for (int e = tid; e < N0 * n; e += nt) { int i = e / n, k = e % n; mx = fmax(mx, fabs(Ct[k * NM + i] - Ct[k * NM])); }
+        mx = warp_max(mx);
+        if (lane == 0) red[40 + warp] = mx;
+        __syncthreads();
+        mx = 0.0;
+        for (int w = 0; w < nwarps; ++w) mx = fmax(mx, red[40 + w]);
+        inv_s = mx > 0.0 ? 1.0 / mx : 1.0;
+        __syncthreads();
+    }
+    if (p > 0) {
+        for (int e = tid; e < p * p; e += nt) {
+            int i = e % p, j = e / p;
+            double r2 = 0.0;
+            for (int k = 0; k < n; ++k) { double d = Ct[k * NM + i] - Ct[k * NM + j]; r2 = fma(d, d, r2); }
+            P00[i + j * pl] = rad_phi(P.rf, r2);
+            Aq[i + j * pl] = (j == 0) ? 1.0 : (Ct[(j - 1) * NM + i] - Ct[(j - 1) * NM]) * inv_s;
+        }
+        __syncthreads();
+        // Householder QR of Pi_0 (same reflector conventions as the literal kernel / LAPACK geqr2)
+        for (int j = 0; j < p; ++j) {
+            double part = 0.0;
+            for (int i = j + 1 + tid; i < p; i += nt) { double a = Aq[i + j * pl]; part = fma(a, a, part); }
+            double xn2 = block_sum(part, red);
+            if (tid == 0) {
+                double alpha = Aq[j + j * pl], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
+                if (xnorm != 0.0 && j + 1 < p) { beta = -copysign(hypot(alpha, xnorm), alpha); tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta); }
+                tauq[j] = tau; red[70] = sc; red[71] = beta;
+            }
+            __syncthreads();
+            const double tau = tauq[j], sc = red[70];
+            for (int i = j + 1 + tid; i < p; i += nt) Aq[i + j * pl] *= sc;
+            if (tid == 0) Aq[j + j * pl] = red[71];
+            __syncthreads();
+            if (tau != 0.0)
+                for (int c = j + 1 + warp; c < p; c += nwarps) {
+                    double* col = Aq + c * pl; const double* vj = Aq + j * pl;
+                    double a = 0.0;
+                    for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
+                    a = (warp_sum(a) + col[j]) * tau;
+                    for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
+                    __syncwarp();
+                    if (lane == 0) col[j] -= a;
+                }
+            __syncthreads();
+        }
+        // explicit Q_0 (warp per column); T = R_0^{-1} (thread per column) after the rank check
+        for (int c = warp; c < p; c += nwarps) {
+            double* col = Qx + c * pl;
+            for (int i = lane; i < p; i += 32) col[i] = (i == c) ? 1.0 : 0.0;
+            __syncwarp();
+            for (int j = p - 1; j >= 0; --j) {
+                const double tau = tauq[j];
+                if (tau == 0.0) continue;
+                const double* vj = Aq + j * pl;
+                double a = 0.0;
+                for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
+                a = (warp_sum(a) + col[j]) * tau;
+                for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
+                __syncwarp();
+                if (lane == 0) col[j] -= a;
+                __syncwarp();
+            }
+        }
+        if (tid == 0) {                            // rank check of Pi_0
+            double mn = INFINITY, mx = 0.0;
+            for (int j = 0; j < p; ++j) { double a = fabs(Aq[j + j * pl]); mn = fmin(mn, a); mx = fmax(mx, a); }
+            if (!(mn > 1e-10 * mx)) red[76] = 1.0;
+        }
+        __syncthreads();
+        if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
+        for (int j = tid; j < p; j += nt) {        // column j of R_0^{-1} by back substitution (R_0 = upper part of Aq)
+            double* x = Tm + j * pl;
+            for (int i = j + 1; i < p; ++i) x[i] = 0.0;
+            x[j] = 1.0 / Aq[j + j * pl];
+            for (int i = j - 1; i >= 0; --i) {
+                double a = 0.0;
+                for (int k = i + 1; k <= j; ++k) a = fma(Aq[i + k * pl], x[k], a);
+                x[i] = -a / Aq[i + i * pl];
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < p * p; e += nt) {    // M0 = Q_0 R_0^{-T}:  M0[r, c] = sum_k Q0[r, k] T[c, k]
+            int r = e % p, c = e / p;
+            double a = 0.0;
+            for (int k = c; k < p; ++k) a = fma(Qx[r + k * pl], Tm[c + k * pl], a);
+            M0[r + c * pl] = a;
+        }
+        __syncthreads();
+        for (int e = tid; e < p * p; e += nt) {    // H = (Pi_0' Pi_0)^{-1} = M0' M0
+            int a_ = e % p, b_ = e / p;
+            double a = 0.0;
+            for (int r = 0; r < p; ++r) a = fma(M0[r + a_ * pl], M0[r + b_ * pl], a);
+            H[a_ + b_ * pl] = a;
+        }
+    }
+    const double phi0 = rad_phi(P.rf, 0.0);
+    const double thr = P.chol_thr;
+    const int base = (p > 0) ? p : N0;             // index of the first round-4 point among the centres
+    int N = N0, m = 0, nr4 = 0;
+
+    // ---- candidate list: warp w compacts the contiguous id segment [w L, (w+1) L)
+    int nc;
+    {
+        const int L = (((n_db + nwarps - 1) / nwarps) + 31) & ~31;
+        const int lo = warp * L, hi = min(n_db, lo + L);
+        int cnt = 0;
+        for (int i0 = lo; i0 < hi; i0 += 32) {
+            const int id = i0 + lane;
+            const unsigned msk = __ballot_sync(0xffffffffu, id < hi && cand[id]);
+            cnt += __popc(msk);
+        }
+        if (lane == 0) ib[3 * T + warp] = cnt;
+        __syncthreads();
+        int basew = 0;
+        for (int w = 0; w < warp; ++w) basew += ib[3 * T + w];
+        nc = 0;
+        for (int w = 0; w < nwarps; ++w) nc += ib[3 * T + w];
+        for (int i0 = lo; i0 < hi; i0 += 32) {
+            const int id = i0 + lane;
+            const bool f = id < hi && cand[id];
+            const unsigned msk = __ballot_sync(0xffffffffu, f);
+            if (f) clist[basew + __popc(msk & ((1u << lane) - 1u))] = id;
+            basew += __popc(msk);
+        }
+        __syncthreads();
+    }
+
+    for (int pos = 0; pos < nc && N < max_points && nr4 < P.r4_stride; pos += T) {
+        const int tb = min(T, nc - pos);
+        // ---- P0: candidate sites
+        for (int e = tid; e < tb * n; e += nt) { const int j = e / n, k = e % n; XI[j * n + k] = sites[(size_t)clist[pos + j] * n + k]; }
+        if (tid < tb) ib[tid] = clist[pos + tid];
+        __syncthreads();
+        // ---- P1: leverage vectors, Lagrange coefficients, kernel columns, cross kernel values (independent row tasks)
+        {
+            const int per = 2 * p + N;
+            const int ntask = tb * per + tb * tb;
+            for (int e = tid; e < ntask; e += nt) {
+                if (e < tb * per) {
+                    const int j = e / per, r = e % per;
+                    const double* xi = XI + j * n;
+                    if (r < p) {                   // HV[j][r] = sum_c H[r,c] pi~[c]
+                        double h = H[r];
+                        for (int c = 1; c < p; ++c) h = fma(H[r + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, h);
+                        HV[j * pl + r] = h;
+                    } else if (r < 2 * p) {        // CV[j][r'] = sum_c M0[r',c] pi~[c]
+                        const int rr = r - p;
+                        double a = M0[rr];
+                        for (int c = 1; c < p; ++c) a = fma(M0[rr + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, a);
+                        CV[j * pl + rr] = a;
+                    } else {                       // kernel column
+                        const int i = r - 2 * p;
+                        double r2 = 0.0;
+                        for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[k * NM + i]; r2 = fma(d, d, r2); }
+                        PH[j * NM + i] = rad_phi(P.rf, r2);
+                    }
+                } else {
+                    const int q = e - tb * per, i = q / tb, j = q % tb;
+                    if (i < j) {
+                        double r2 = 0.0;
+                        for (int k = 0; k < n; ++k) { double d = XI[i * n + k] - XI[j * n + k]; r2 = fma(d, d, r2); }
+                        Kx[i * T + j] = rad_phi(P.rf, r2);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P2: u_j = b_j - Phi00 c_j ; a_j[eta] = phi(eta, xi_j) - g_eta.c_j - c_eta.b_j ; leverage l_j = pi_j.h_j
+        {
+            const int per = p + m + 1;
+            for (int e = tid; e < tb * per; e += nt) {
+                const int j = e / per, r = e % per;
+                const double* cv = CV + j * pl; const double* ph = PH + j * NM;
+                if (r < p) {
+                    double a = 0.0;
+                    for (int c = 0; c < p; ++c) a = fma(P00[r + c * pl], cv[c], a);
+                    UB[j * pl + r] = ph[r] - a;
+                } else if (r < p + m) {
+                    const int eta = r - p;
+                    const double* ge = Gm + eta * pb; const double* ce = Cm + eta * pb;
+                    double a0 = 0.0, a1 = 0.0;
+                    for (int c = 0; c < p; ++c) { a0 = fma(ge[c], cv[c], a0); a1 = fma(ce[c], ph[c], a1); }
+                    AV[j * MM + eta] = ph[base + eta] - a0 - a1;
+                } else {
+                    const double* xi = XI + j * n; const double* hv = HV + j * pl;
+                    double a = (p > 0) ? hv[0] : 0.0;
+                    for (int c = 1; c < p; ++c) a = fma(hv[c], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, a);
+                    Sx[j * T + j] = a;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P3: t_j = L^{-1} a_j for all block members at once (G threads per row share the row of L^{-1})
+        const int G = (m > 64) ? 2 : ((m > 32) ? 4 : 8);
+        const int rows_per_pass = nt / G;
+        {
+            double tn[T];
+#pragma unroll
+            for (int j = 0; j < T; ++j) tn[j] = 0.0;
+            for (int r0 = 0; r0 < m; r0 += rows_per_pass) {
+                const int r = r0 + tid / G, l = tid % G;
+                double acc[T];
+#pragma unroll
+                for (int j = 0; j < T; ++j) acc[j] = 0.0;
+                if (r < m) {
+                    const double* lr = Li + tri(r);
+                    for (int c = l; c <= r; c += G) {
+                        const double lv = lr[c];
+#pragma unroll
+                        for (int j = 0; j < T; ++j) acc[j] = fma(lv, AV[j * MM + c], acc[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    double a = acc[j];
+                    for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if (r < m && l == 0) { TV[j * MM + r] = a; tn[j] = fma(a, a, tn[j]); }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < T; ++j) { const double s_ = warp_sum(tn[j]); if (lane == 0) tnp[warp * T + j] = s_; }
+        }
+        __syncthreads();
+        // ---- P4: pair quantities (warp per pair): A_ij, t_i.t_j, pi_i' H pi_j ; diagonal A_jj
+        for (int q = warp; q < tb * tb; q += nwarps) {
+            const int i = q / tb, j = q % tb;
+            if (i < j) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                for (int c = lane; c < p; c += 32) {
+                    a0 = fma(UB[i * pl + c], CV[j * pl + c], a0);
+                    a0 = fma(CV[i * pl + c], PH[j * NM + c], a0);
+                    const double pj = (c == 0) ? 1.0 : (XI[j * n + c - 1] - Ct[(c - 1) * NM]) * inv_s;
+                    a2 = fma(HV[i * pl + c], pj, a2);
+                }
+                for (int r = lane; r < m; r += 32) a1 = fma(TV[i * MM + r], TV[j * MM + r], a1);
+                a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+                if (lane == 0) { Ax[i * T + j] = Kx[i * T + j] - a0; Dx[i * T + j] = a1; Sx[i * T + j] = a2; }
+            } else if (i == j) {
+                double a0 = 0.0;
+                for (int c = lane; c < p; c += 32) a0 = fma(CV[j * pl + c], PH[j * NM + c] + UB[j * pl + c], a0);
+                a0 = warp_sum(a0);
+                if (lane == 0) Ax[j * T + j] = phi0 - a0;
+            }
+        }
+        __syncthreads();
+        // ---- P5: panel (one thread, O(T^3) scalars): resolve the dependence on accepted block members
+        if (tid == 0) {
+            int na = 0;
+            for (int j = 0; j < tb; ++j) {
+                double tnj = 0.0;
+                for (int w = 0; w < nwarps; ++w) tnj += tnp[w * T + j];
+                double dj2 = Ax[j * T + j] - tnj;
+                double lev = Sx[j * T + j];
+                for (int qi = 0; qi < na; ++qi) {
+                    const int i = ib[2 * T + qi];                  // qi-th accepted member of this block
+                    double e = Ax[i * T + j] - Dx[i * T + j];
+                    double sp = Sx[i * T + j];
+                    for (int ql = 0; ql < qi; ++ql) {
+                        const int l = ib[2 * T + ql];
+                        e -= Ex[l * T + i] * Ex[l * T + j];
+                        sp -= Sc[l * T + i] * Sc[l * T + j] / Sc[l * T + l];
+                    }
+                    e /= Ex[i * T + i];
+                    Ex[i * T + j] = e; Sc[i * T + j] = sp;
+                    dj2 -= e * e;
+                    lev -= sp * sp / Sc[i * T + i];
+                }
+                const double tau2 = dj2 / (1.0 + lev);             // == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
+                const bool ok = (tau2 > thr) && (N + na < max_points) && (nr4 + na < P.r4_stride);   // RbfModel.jl:452, 402
+                ib[T + j] = ok ? 1 : 0;
+                if (ok) { Ex[j * T + j] = sqrt(dj2); Sc[j * T + j] = 1.0 + lev; ib[2 * T + na] = j; ++na; }
+            }
+            // inverse of the accepted panel P_ = [e_ij below the diagonal, d_j on it]  (na x na, lower)
+            for (int q = 0; q < na; ++q) {
+                const int jq = ib[2 * T + q];
+                for (int c = 0; c <= q; ++c) {
+                    double v = (c == q) ? 1.0 : 0.0;
+                    for (int q2 = c; q2 < q; ++q2) v -= Ex[ib[2 * T + q2] * T + jq] * Px[q2 * T + c];
+                    Px[q * T + c] = v / Ex[jq * T + jq];
+                }
+            }
+            ib[3 * T + 8] = na;
+        }
+        __syncthreads();
+        const int na = ib[3 * T + 8];
+        // ---- P6: append the accepted members
+        if (na > 0) {
+            // new rows of L^{-1}: columns < m from  -P_^{-1} (T_ L^{-1}),  columns >= m from P_^{-1}
+            for (int c0 = 0; c0 < m; c0 += rows_per_pass) {
+                const int c = c0 + tid / G, l = tid % G;
+                double acc[T];
+#pragma unroll
+                for (int q = 0; q < T; ++q) acc[q] = 0.0;
+                if (c < m)
+                    for (int r = c + l; r < m; r += G) {
+                        const double lv = Li[tri(r) + c];
+#pragma unroll
+                        for (int q = 0; q < T; ++q) if (q < na) acc[q] = fma(TV[ib[2 * T + q] * MM + r], lv, acc[q]);
+                    }
+#pragma unroll
+                for (int q = 0; q < T; ++q) for (int o = G >> 1; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+                if (c < m && l == 0) {
+#pragma unroll
+                    for (int q = 0; q < T; ++q) if (q < na) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int q2 = 0; q2 < T; ++q2) if (q2 <= q) v = fma(Px[q * T + q2], acc[q2], v);
+                        Li[tri(m + q) + c] = -v;
+                    }
+                }
+            }
+            for (int e = tid; e < na * na; e += nt) { const int q = e / na, c = e % na; if (c <= q) Li[tri(m + q) + m + c] = Px[q * T + c]; }
+            for (int e = tid; e < na * p; e += nt) { const int q = e / p, r = e % p, j = ib[2 * T + q]; Gm[(m + q) * pb + r] = UB[j * pl + r]; Cm[(m + q) * pb + r] = CV[j * pl + r]; }
+            for (int e = tid; e < na * n; e += nt) { const int q = e / n, k = e % n; Ct[k * NM + N + q] = XI[ib[2 * T + q] * n + k]; }
+            if (tid < na) r4[nr4 + tid] = ib[ib[2 * T + tid]] + 1;
+            // corrected leverage vectors h'_q = h_q - sum_{q' < q} h'_q' s'_q'q / (1 + lev'_q'), then H -= sum h' h'^T / (1 + lev')
+            for (int r = tid; r < p; r += nt)
+                for (int q = 1; q < na; ++q) {
+                    const int jq = ib[2 * T + q];
+                    double h = HV[jq * pl + r];
+                    for (int q2 = 0; q2 < q; ++q2) { const int j2 = ib[2 * T + q2]; h -= HV[j2 * pl + r] * Sc[j2 * T + jq] / Sc[j2 * T + j2]; }
+                    HV[jq * pl + r] = h;
+                }
+            __syncthreads();
+            for (int e = tid; e < p * p; e += nt) {
+                const int a_ = e % p, b_ = e / p;
+                double h = H[a_ + b_ * pl];
+                for (int q = 0; q < na; ++q) { const int jq = ib[2 * T + q]; h = fma(-HV[jq * pl + a_] / Sc[jq * T + jq], HV[jq * pl + b_], h); }
+                H[a_ + b_ * pl] = h;
+            }
+            N += na; m += na; nr4 += na;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
+    if (P.keep_fs) {
+        // keep the factorisation for mrbf_build_prepared: centres, Pi_0^{-T}, g/c blocks, packed L^{-1}
+        double* out = P.keep_fs + (size_t)b * P.fs_stride;
+        if constexpr (SMEM) {
+            const int used_c = pb * m, used_l = tri(m);
+            for (int e = tid; e < NM * n; e += nt) { int i = e % NM; if (i < N) out[e] = Ct[e]; }
+            double* o = out + NM * n;
+            for (int e = tid; e < pl * pl; e += nt) o[e] = M0[e];
+            o = out + (Gm - fs);
+            for (int e = tid; e < used_c; e += nt) { o[e] = Gm[e]; o[pb * MM + e] = Cm[e]; }
+            o = out + (Li - fs);
+            for (int e = tid; e < used_l; e += nt) o[e] = Li[e];
+        }
+        if (tid == 0) { out[P.fs_stride - 1] = inv_s; out[P.fs_stride - 2] = (double)N0; out[P.fs_stride - 3] = (double)m; P.elig[b] = 1; }
+    }
+}
+
 size_t round4_fast_vec_doubles(int n, int NM, int p) {
     int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
     return 2 * (size_t)n + NM + 2 * (size_t)MM + 4 * (size_t)pl + 80;
@@ -967,6 +1400,27 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
     if (e != cudaSuccess) return e;
     round4_kernel<<<grid, 256, smem, s>>>(P);
     return cudaGetLastError();
+}
+size_t round4_block_vec_doubles(int T, int n, int NM, int p) {
+    int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
+    return (size_t)T * n + (size_t)T * NM + 3 * (size_t)T * pl + 2 * (size_t)T * MM + 7 * (size_t)T * T + 8 * (size_t)T + pl + 80 + 2 * T + 4;
+}
+template <int T>
+static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream_t s) {
+    cudaError_t e;
+    if (P.fs_in_smem) {
+        e = cudaFuncSetAttribute(round4_block_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        round4_block_kernel<T, true><<<P.B, 256, smem, s>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(round4_block_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        round4_block_kernel<T, false><<<P.B, 256, smem, s>>>(P);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s) {
+    return T == 8 ? launch_block_t<8>(P, smem, s) : launch_block_t<4>(P, smem, s);
 }
 cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s) {
     cudaError_t e;
