@@ -921,7 +921,9 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
     double* Ex = Sx + T * T;           // T x T    panel: e_ij (extra Cholesky entries), d_j on the diagonal
     double* Px = Ex + T * T;           // T x T    panel: inverse of the accepted part of [e, d]
     double* Sc = Px + T * T;           // T x T    panel: corrected s'_ij, 1 + lev'_j on the diagonal
-    double* tnp = Sc + T * T;          // 8 x T    per-warp partial ||t_j||^2
+    double* PT = Sc + T * T;           // T x pl   pi~ of the block members
+    double* RI = PT + T * pl;          // T        1 / (1 + lev'_j) of accepted members
+    double* tnp = RI + T;              // 8 x T    per-warp partial ||t_j||^2
     double* tauq = tnp + 8 * T;        // pl
     double* red = tauq + pl;           // 80
     int* ib = reinterpret_cast<int*>(red + 80);   // ids[T], acc[T], pos[T], misc[8]
@@ -991,81 +993,36 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
             Aq[i + j * pl] = (j == 0) ? 1.0 : (Ct[(j - 1) * NM + i] - Ct[(j - 1) * NM]) * inv_s;
         }
         __syncthreads();
-        // Householder QR of Pi_0 (same reflector conventions as the literal kernel / LAPACK geqr2)
-        for (int j = 0; j < p; ++j) {
-            double part = 0.0;
-            for (int i = j + 1 + tid; i < p; i += nt) { double a = Aq[i + j * pl]; part = fma(a, a, part); }
-            double xn2 = block_sum(part, red);
-            if (tid == 0) {
-                double alpha = Aq[j + j * pl], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
-                if (xnorm != 0.0 && j + 1 < p) { beta = -copysign(hypot(alpha, xnorm), alpha); tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta); }
-                tauq[j] = tau; red[70] = sc; red[71] = beta;
-            }
-            __syncthreads();
-            const double tau = tauq[j], sc = red[70];
-            for (int i = j + 1 + tid; i < p; i += nt) Aq[i + j * pl] *= sc;
-            if (tid == 0) Aq[j + j * pl] = red[71];
-            __syncthreads();
-            if (tau != 0.0)
-                for (int c = j + 1 + warp; c < p; c += nwarps) {
-                    double* col = Aq + c * pl; const double* vj = Aq + j * pl;
-                    double a = 0.0;
-                    for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
-                    a = (warp_sum(a) + col[j]) * tau;
-                    for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
-                    __syncwarp();
-                    if (lane == 0) col[j] -= a;
-                }
-            __syncthreads();
-        }
-        // explicit Q_0 (warp per column); T = R_0^{-1} (thread per column) after the rank check
-        for (int c = warp; c < p; c += nwarps) {
-            double* col = Qx + c * pl;
-            for (int i = lane; i < p; i += 32) col[i] = (i == c) ? 1.0 : 0.0;
-            __syncwarp();
-            for (int j = p - 1; j >= 0; --j) {
-                const double tau = tauq[j];
-                if (tau == 0.0) continue;
-                const double* vj = Aq + j * pl;
-                double a = 0.0;
-                for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
-                a = (warp_sum(a) + col[j]) * tau;
-                for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
-                __syncwarp();
-                if (lane == 0) col[j] -= a;
-                __syncwarp();
-            }
-        }
-        if (tid == 0) {                            // rank check of Pi_0
-            double mn = INFINITY, mx = 0.0;
-            for (int j = 0; j < p; ++j) { double a = fabs(Aq[j + j * pl]); mn = fmin(mn, a); mx = fmax(mx, a); }
-            if (!(mn > 1e-10 * mx)) red[76] = 1.0;
-        }
+        // Pi_0^{-1} by Gauss-Jordan with partial pivoting on [Pi_0 | I] (p x 2p, Aq and Qx are adjacent), block parallel
+        for (int e = tid; e < p * p; e += nt) { int i = e % p, j = e / p; Qx[i + j * pl] = (i == j) ? 1.0 : 0.0; }
         __syncthreads();
-        if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
-        for (int j = tid; j < p; j += nt) {        // column j of R_0^{-1} by back substitution (R_0 = upper part of Aq)
-            double* x = Tm + j * pl;
-            for (int i = j + 1; i < p; ++i) x[i] = 0.0;
-            x[j] = 1.0 / Aq[j + j * pl];
-            for (int i = j - 1; i >= 0; --i) {
-                double a = 0.0;
-                for (int k = i + 1; k <= j; ++k) a = fma(Aq[i + k * pl], x[k], a);
-                x[i] = -a / Aq[i + i * pl];
+        int* redi = reinterpret_cast<int*>(red + 40);
+        for (int kk = 0; kk < p; ++kk) {
+            ArgMax mine; mine.v = 0.0; mine.id = -1;
+            for (int i = kk + tid; i < p; i += nt) { ArgMax c_; c_.v = fabs(Aq[i + kk * pl]); c_.id = i; mine = better(mine, c_); }
+            const ArgMax pv = block_argmax(mine, red, redi);
+            if (!(pv.v > 1e-12)) { if (tid == 0) P.n_r4[b] = -1; return; }      // Pi_0 (scaled to O(1)) is rank deficient
+            const double rp = 1.0 / Aq[pv.id + kk * pl];
+            __syncthreads();
+            for (int c = tid; c < 2 * p; c += nt) {                              // swap rows kk <-> pivot, scale the pivot row
+                const double a = Aq[pv.id + c * pl], bq = Aq[kk + c * pl];
+                Aq[pv.id + c * pl] = bq; Aq[kk + c * pl] = a * rp;
             }
+            __syncthreads();
+            for (int e = tid; e < p * 2 * p; e += nt) {                          // eliminate column kk from every other row
+                const int i = e % p, c = e / p;
+                if (i != kk && c != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], Aq[kk + c * pl], Aq[i + c * pl]);
+            }
+            __syncthreads();
+            for (int i = tid; i < p; i += nt) if (i != kk) Aq[i + kk * pl] = 0.0;
+            __syncthreads();
         }
-        __syncthreads();
-        for (int e = tid; e < p * p; e += nt) {    // M0 = Q_0 R_0^{-T}:  M0[r, c] = sum_k Q0[r, k] T[c, k]
-            int r = e % p, c = e / p;
+        for (int e = tid; e < p * p; e += nt) {    // M0 = Pi_0^{-T};  H = (Pi_0' Pi_0)^{-1} = Pi_0^{-1} Pi_0^{-T}
+            const int r = e % p, c = e / p;
+            M0[r + c * pl] = Qx[c + r * pl];
             double a = 0.0;
-            for (int k = c; k < p; ++k) a = fma(Qx[r + k * pl], Tm[c + k * pl], a);
-            M0[r + c * pl] = a;
-        }
-        __syncthreads();
-        for (int e = tid; e < p * p; e += nt) {    // H = (Pi_0' Pi_0)^{-1} = M0' M0
-            int a_ = e % p, b_ = e / p;
-            double a = 0.0;
-            for (int r = 0; r < p; ++r) a = fma(M0[r + a_ * pl], M0[r + b_ * pl], a);
-            H[a_ + b_ * pl] = a;
+            for (int k2 = 0; k2 < p; ++k2) a = fma(Qx[r + k2 * pl], Qx[c + k2 * pl], a);
+            H[r + c * pl] = a;
         }
     }
     const double phi0 = rad_phi(P.rf, 0.0);
@@ -1106,36 +1063,47 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
         for (int e = tid; e < tb * n; e += nt) { const int j = e / n, k = e % n; XI[j * n + k] = sites[(size_t)clist[pos + j] * n + k]; }
         if (tid < tb) ib[tid] = clist[pos + tid];
         __syncthreads();
+        for (int e = tid; e < tb * p; e += nt) { const int j = e / p, c = e % p; PT[j * pl + c] = (c == 0) ? 1.0 : (XI[j * n + c - 1] - Ct[(c - 1) * NM]) * inv_s; }
+        __syncthreads();
         // ---- P1: leverage vectors, Lagrange coefficients, kernel columns, cross kernel values (independent row tasks)
         {
             const int per = 2 * p + N;
-            const int ntask = tb * per + tb * tb;
-            for (int e = tid; e < ntask; e += nt) {
-                if (e < tb * per) {
-                    const int j = e / per, r = e % per;
-                    const double* xi = XI + j * n;
-                    if (r < p) {                   // HV[j][r] = sum_c H[r,c] pi~[c]
-                        double h = H[r];
-                        for (int c = 1; c < p; ++c) h = fma(H[r + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, h);
-                        HV[j * pl + r] = h;
-                    } else if (r < 2 * p) {        // CV[j][r'] = sum_c M0[r',c] pi~[c]
-                        const int rr = r - p;
-                        double a = M0[rr];
-                        for (int c = 1; c < p; ++c) a = fma(M0[rr + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, a);
-                        CV[j * pl + rr] = a;
-                    } else {                       // kernel column
-                        const int i = r - 2 * p;
-                        double r2 = 0.0;
-                        for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[k * NM + i]; r2 = fma(d, d, r2); }
-                        PH[j * NM + i] = rad_phi(P.rf, r2);
+            int j = tid / per, r = tid - j * per;
+            for (; j < tb; ) {
+                const double* xi = XI + j * n; const double* pt = PT + j * pl;
+                if (r < p) {                       // HV[j][r] = sum_c H[r,c] pi~[c]
+                    double h0 = 0.0, h1 = 0.0;
+                    int c = 0;
+                    for (; c + 2 <= p; c += 2) { h0 = fma(H[r + c * pl], pt[c], h0); h1 = fma(H[r + (c + 1) * pl], pt[c + 1], h1); }
+                    for (; c < p; ++c) h0 = fma(H[r + c * pl], pt[c], h0);
+                    HV[j * pl + r] = h0 + h1;
+                } else if (r < 2 * p) {            // CV[j][r'] = sum_c M0[r',c] pi~[c]
+                    const int rr = r - p;
+                    double h0 = 0.0, h1 = 0.0;
+                    int c = 0;
+                    for (; c + 2 <= p; c += 2) { h0 = fma(M0[rr + c * pl], pt[c], h0); h1 = fma(M0[rr + (c + 1) * pl], pt[c + 1], h1); }
+                    for (; c < p; ++c) h0 = fma(M0[rr + c * pl], pt[c], h0);
+                    CV[j * pl + rr] = h0 + h1;
+                } else {                           // kernel column
+                    const int i = r - 2 * p;
+                    double r2a = 0.0, r2b = 0.0;
+                    int k = 0;
+                    for (; k + 2 <= n; k += 2) {
+                        const double d0 = xi[k] - Ct[k * NM + i], d1 = xi[k + 1] - Ct[(k + 1) * NM + i];
+                        r2a = fma(d0, d0, r2a); r2b = fma(d1, d1, r2b);
                     }
-                } else {
-                    const int q = e - tb * per, i = q / tb, j = q % tb;
-                    if (i < j) {
-                        double r2 = 0.0;
-                        for (int k = 0; k < n; ++k) { double d = XI[i * n + k] - XI[j * n + k]; r2 = fma(d, d, r2); }
-                        Kx[i * T + j] = rad_phi(P.rf, r2);
-                    }
+                    for (; k < n; ++k) { const double d0 = xi[k] - Ct[k * NM + i]; r2a = fma(d0, d0, r2a); }
+                    PH[j * NM + i] = rad_phi(P.rf, r2a + r2b);
+                }
+                r += nt;
+                while (r >= per) { r -= per; ++j; }
+            }
+            for (int q = tid; q < tb * tb; q += nt) {
+                const int i = q / tb, j2 = q % tb;
+                if (i < j2) {
+                    double r2 = 0.0;
+                    for (int k = 0; k < n; ++k) { double d = XI[i * n + k] - XI[j2 * n + k]; r2 = fma(d, d, r2); }
+                    Kx[i * T + j2] = rad_phi(P.rf, r2);
                 }
             }
         }
@@ -1143,13 +1111,15 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
         // ---- P2: u_j = b_j - Phi00 c_j ; a_j[eta] = phi(eta, xi_j) - g_eta.c_j - c_eta.b_j ; leverage l_j = pi_j.h_j
         {
             const int per = p + m + 1;
-            for (int e = tid; e < tb * per; e += nt) {
-                const int j = e / per, r = e % per;
+            int j = tid / per, r = tid - j * per;
+            for (; j < tb; ) {
                 const double* cv = CV + j * pl; const double* ph = PH + j * NM;
                 if (r < p) {
-                    double a = 0.0;
-                    for (int c = 0; c < p; ++c) a = fma(P00[r + c * pl], cv[c], a);
-                    UB[j * pl + r] = ph[r] - a;
+                    double a0 = 0.0, a1 = 0.0;
+                    int c = 0;
+                    for (; c + 2 <= p; c += 2) { a0 = fma(P00[r + c * pl], cv[c], a0); a1 = fma(P00[r + (c + 1) * pl], cv[c + 1], a1); }
+                    for (; c < p; ++c) a0 = fma(P00[r + c * pl], cv[c], a0);
+                    UB[j * pl + r] = ph[r] - (a0 + a1);
                 } else if (r < p + m) {
                     const int eta = r - p;
                     const double* ge = Gm + eta * pb; const double* ce = Cm + eta * pb;
@@ -1157,11 +1127,13 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
                     for (int c = 0; c < p; ++c) { a0 = fma(ge[c], cv[c], a0); a1 = fma(ce[c], ph[c], a1); }
                     AV[j * MM + eta] = ph[base + eta] - a0 - a1;
                 } else {
-                    const double* xi = XI + j * n; const double* hv = HV + j * pl;
-                    double a = (p > 0) ? hv[0] : 0.0;
-                    for (int c = 1; c < p; ++c) a = fma(hv[c], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, a);
+                    const double* hv = HV + j * pl; const double* pt = PT + j * pl;
+                    double a = 0.0;
+                    for (int c = 0; c < p; ++c) a = fma(hv[c], pt[c], a);
                     Sx[j * T + j] = a;
                 }
+                r += nt;
+                while (r >= per) { r -= per; ++j; }
             }
         }
         __syncthreads();
@@ -1197,15 +1169,16 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
         }
         __syncthreads();
         // ---- P4: pair quantities (warp per pair): A_ij, t_i.t_j, pi_i' H pi_j ; diagonal A_jj
-        for (int q = warp; q < tb * tb; q += nwarps) {
-            const int i = q / tb, j = q % tb;
+        for (int q = warp; q < (tb * (tb + 1)) / 2; q += nwarps) {
+            int j = 0;
+            while (((j + 1) * (j + 2)) / 2 <= q) ++j;          // q = j (j + 1) / 2 + i,  i <= j
+            const int i = q - (j * (j + 1)) / 2;
             if (i < j) {
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
                 for (int c = lane; c < p; c += 32) {
                     a0 = fma(UB[i * pl + c], CV[j * pl + c], a0);
                     a0 = fma(CV[i * pl + c], PH[j * NM + c], a0);
-                    const double pj = (c == 0) ? 1.0 : (XI[j * n + c - 1] - Ct[(c - 1) * NM]) * inv_s;
-                    a2 = fma(HV[i * pl + c], pj, a2);
+                    a2 = fma(HV[i * pl + c], PT[j * pl + c], a2);
                 }
                 for (int r = lane; r < m; r += 32) a1 = fma(TV[i * MM + r], TV[j * MM + r], a1);
                 a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
@@ -1218,43 +1191,58 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
             }
         }
         __syncthreads();
-        // ---- P5: panel (one thread, O(T^3) scalars): resolve the dependence on accepted block members
-        if (tid == 0) {
-            int na = 0;
-            for (int j = 0; j < tb; ++j) {
+        // ---- P5: panel (one warp, lane = block member): resolve the dependence on accepted block members.
+        // Lane i decides once every accepted l < i has been folded into its pivot and leverage; the lanes j > i then
+        // fold member i into theirs (the recurrences of a left-looking Cholesky / of successive Sherman-Morrison updates).
+        if (warp == 0) {
+            const int j = lane;
+            double dj2 = 0.0, lev = 0.0;
+            if (j < tb) {
                 double tnj = 0.0;
                 for (int w = 0; w < nwarps; ++w) tnj += tnp[w * T + j];
-                double dj2 = Ax[j * T + j] - tnj;
-                double lev = Sx[j * T + j];
-                for (int qi = 0; qi < na; ++qi) {
-                    const int i = ib[2 * T + qi];                  // qi-th accepted member of this block
-                    double e = Ax[i * T + j] - Dx[i * T + j];
-                    double sp = Sx[i * T + j];
-                    for (int ql = 0; ql < qi; ++ql) {
-                        const int l = ib[2 * T + ql];
-                        e -= Ex[l * T + i] * Ex[l * T + j];
-                        sp -= Sc[l * T + i] * Sc[l * T + j] / Sc[l * T + l];
-                    }
-                    e /= Ex[i * T + i];
-                    Ex[i * T + j] = e; Sc[i * T + j] = sp;
-                    dj2 -= e * e;
-                    lev -= sp * sp / Sc[i * T + i];
-                }
-                const double tau2 = dj2 / (1.0 + lev);             // == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
-                const bool ok = (tau2 > thr) && (N + na < max_points) && (nr4 + na < P.r4_stride);   // RbfModel.jl:452, 402
-                ib[T + j] = ok ? 1 : 0;
-                if (ok) { Ex[j * T + j] = sqrt(dj2); Sc[j * T + j] = 1.0 + lev; ib[2 * T + na] = j; ++na; }
+                dj2 = Ax[j * T + j] - tnj; lev = Sx[j * T + j];
             }
-            // inverse of the accepted panel P_ = [e_ij below the diagonal, d_j on it]  (na x na, lower)
-            for (int q = 0; q < na; ++q) {
-                const int jq = ib[2 * T + q];
-                for (int c = 0; c <= q; ++c) {
+            int na_ = 0;
+            int al[T];
+            for (int i = 0; i < tb; ++i) {
+                const double d2i = __shfl_sync(0xffffffffu, dj2, i), levi = __shfl_sync(0xffffffffu, lev, i);
+                const double tau2 = d2i / (1.0 + levi);          // == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
+                const bool ok = (tau2 > thr) && (N + na_ < max_points) && (nr4 + na_ < P.r4_stride);    // RbfModel.jl:452, 402
+                if (lane == 0) ib[T + i] = ok ? 1 : 0;
+                if (ok) {
+                    const double di = sqrt(d2i), ri = 1.0 / (1.0 + levi), rdi = 1.0 / di;
+                    if (lane == 0) { ib[2 * T + na_] = i; Ex[i * T + i] = di; Sc[i * T + i] = 1.0 + levi; RI[i] = ri; }
+                    if (j > i && j < tb) {
+                        double e = Ax[i * T + j] - Dx[i * T + j];
+                        double sp = Sx[i * T + j];
+#pragma unroll
+                        for (int ql = 0; ql < T; ++ql) if (ql < na_) {
+                            const int l = al[ql];
+                            e = fma(-Ex[l * T + i], Ex[l * T + j], e);
+                            sp = fma(-Sc[l * T + i] * RI[l], Sc[l * T + j], sp);
+                        }
+                        e *= rdi;
+                        Ex[i * T + j] = e; Sc[i * T + j] = sp;
+                        dj2 = fma(-e, e, dj2);
+                        lev = fma(-sp * ri, sp, lev);
+                    }
+#pragma unroll
+                    for (int ql = 0; ql < T; ++ql) if (ql == na_) al[ql] = i;
+                    ++na_;
+                }
+                __syncwarp();
+            }
+            // inverse of the accepted panel P_ = [e_ij below the diagonal, d_j on it]: lane c owns column c
+            if (lane < na_) {
+                const int c = lane;
+                for (int q = c; q < na_; ++q) {
+                    const int jq = ib[2 * T + q];
                     double v = (c == q) ? 1.0 : 0.0;
-                    for (int q2 = c; q2 < q; ++q2) v -= Ex[ib[2 * T + q2] * T + jq] * Px[q2 * T + c];
+                    for (int q2 = c; q2 < q; ++q2) v = fma(-Ex[ib[2 * T + q2] * T + jq], Px[q2 * T + c], v);
                     Px[q * T + c] = v / Ex[jq * T + jq];
                 }
             }
-            ib[3 * T + 8] = na;
+            if (lane == 0) ib[3 * T + 8] = na_;
         }
         __syncthreads();
         const int na = ib[3 * T + 8];
@@ -1293,14 +1281,14 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
                 for (int q = 1; q < na; ++q) {
                     const int jq = ib[2 * T + q];
                     double h = HV[jq * pl + r];
-                    for (int q2 = 0; q2 < q; ++q2) { const int j2 = ib[2 * T + q2]; h -= HV[j2 * pl + r] * Sc[j2 * T + jq] / Sc[j2 * T + j2]; }
+                    for (int q2 = 0; q2 < q; ++q2) { const int j2 = ib[2 * T + q2]; h = fma(-HV[j2 * pl + r], Sc[j2 * T + jq] * RI[j2], h); }
                     HV[jq * pl + r] = h;
                 }
             __syncthreads();
             for (int e = tid; e < p * p; e += nt) {
                 const int a_ = e % p, b_ = e / p;
                 double h = H[a_ + b_ * pl];
-                for (int q = 0; q < na; ++q) { const int jq = ib[2 * T + q]; h = fma(-HV[jq * pl + a_] / Sc[jq * T + jq], HV[jq * pl + b_], h); }
+                for (int q = 0; q < na; ++q) { const int jq = ib[2 * T + q]; h = fma(-HV[jq * pl + a_] * RI[jq], HV[jq * pl + b_], h); }
                 H[a_ + b_ * pl] = h;
             }
             N += na; m += na; nr4 += na;
@@ -1403,7 +1391,7 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
 }
 size_t round4_block_vec_doubles(int T, int n, int NM, int p) {
     int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
-    return (size_t)T * n + (size_t)T * NM + 3 * (size_t)T * pl + 2 * (size_t)T * MM + 7 * (size_t)T * T + 8 * (size_t)T + pl + 80 + 2 * T + 4;
+    return (size_t)T * n + (size_t)T * NM + 4 * (size_t)T * pl + 2 * (size_t)T * MM + 7 * (size_t)T * T + 9 * (size_t)T + pl + 80 + 2 * T + 4;
 }
 template <int T>
 static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream_t s) {

@@ -170,8 +170,9 @@ def _run_iterations(cfg, ocfg, func, x0, glb, gub, n_iter, delta0=0.1, delta_max
         x = it.x_scaled
         Yr, Jr = omod.eval(x), omod.jac(x)
         Y, J = mb.eval_models(mod, scal, x), mb.get_jacobian(mod, scal, x)
-        assert np.abs(Y - Yr).max() <= 1e-10 * max(1.0, np.abs(Yr).max())
-        assert np.abs(J - Jr).max() <= 1e-9 * max(1.0, np.abs(Jr).max()), (t, np.abs(J - Jr).max())
+        ctol = 20 * omod.cond * np.finfo(float).eps           # LU (oracle) vs null-space solves differ at O(cond * eps)
+        assert np.abs(Y - Yr).max() <= max(1e-10, ctol) * max(1.0, np.abs(Yr).max())
+        assert np.abs(J - Jr).max() <= max(1e-9, ctol) * max(1.0, np.abs(Jr).max()), (t, omod.cond, np.abs(J - Jr).max())
         d = _common_descent(Jr)
         if np.abs(d).max() < 1e-6:
             break                                                        # Pareto-critical for the model: nothing to compare
