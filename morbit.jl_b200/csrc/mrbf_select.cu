@@ -996,25 +996,32 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
         // Pi_0^{-1} by Gauss-Jordan with partial pivoting on [Pi_0 | I] (p x 2p, Aq and Qx are adjacent), block parallel
         for (int e = tid; e < p * p; e += nt) { int i = e % p, j = e / p; Qx[i + j * pl] = (i == j) ? 1.0 : 0.0; }
         __syncthreads();
-        int* redi = reinterpret_cast<int*>(red + 40);
         for (int kk = 0; kk < p; ++kk) {
-            ArgMax mine; mine.v = 0.0; mine.id = -1;
-            for (int i = kk + tid; i < p; i += nt) { ArgMax c_; c_.v = fabs(Aq[i + kk * pl]); c_.id = i; mine = better(mine, c_); }
-            const ArgMax pv = block_argmax(mine, red, redi);
-            if (!(pv.v > 1e-12)) { if (tid == 0) P.n_r4[b] = -1; return; }      // Pi_0 (scaled to O(1)) is rank deficient
-            const double rp = 1.0 / Aq[pv.id + kk * pl];
-            __syncthreads();
-            for (int c = tid; c < 2 * p; c += nt) {                              // swap rows kk <-> pivot, scale the pivot row
-                const double a = Aq[pv.id + c * pl], bq = Aq[kk + c * pl];
-                Aq[pv.id + c * pl] = bq; Aq[kk + c * pl] = a * rp;
+            if (warp == 0) {                       // pivot search, row swap and scaling by one warp
+                ArgMax mine; mine.v = 0.0; mine.id = -1;
+                for (int i = kk + lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(Aq[i + kk * pl]); c_.id = i; mine = better(mine, c_); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
+                    mine = better(mine, t_);
+                }
+                if (!(mine.v > 1e-12)) { if (lane == 0) red[76] = 1.0; }       // Pi_0 (scaled to O(1)) is rank deficient
+                else {
+                    const double rp = 1.0 / Aq[mine.id + kk * pl];
+                    __syncwarp();
+                    for (int c = kk + lane; c < 2 * p; c += 32) {
+                        const double a = Aq[mine.id + c * pl], bq = Aq[kk + c * pl];
+                        Aq[mine.id + c * pl] = bq; Aq[kk + c * pl] = a * rp;
+                    }
+                }
             }
             __syncthreads();
-            for (int e = tid; e < p * 2 * p; e += nt) {                          // eliminate column kk from every other row
-                const int i = e % p, c = e / p;
-                if (i != kk && c != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], Aq[kk + c * pl], Aq[i + c * pl]);
+            if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
+            // eliminate column kk from every other row; columns <= kk of the left block are never read again
+            for (int c = kk + 1 + warp; c < 2 * p; c += nwarps) {
+                const double pk = Aq[kk + c * pl];
+                for (int i = lane; i < p; i += 32) if (i != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], pk, Aq[i + c * pl]);
             }
-            __syncthreads();
-            for (int i = tid; i < p; i += nt) if (i != kk) Aq[i + kk * pl] = 0.0;
             __syncthreads();
         }
         for (int e = tid; e < p * p; e += nt) {    // M0 = Pi_0^{-T};  H = (Pi_0' Pi_0)^{-1} = Pi_0^{-1} Pi_0^{-T}
@@ -1065,76 +1072,72 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
         __syncthreads();
         for (int e = tid; e < tb * p; e += nt) { const int j = e / p, c = e % p; PT[j * pl + c] = (c == 0) ? 1.0 : (XI[j * n + c - 1] - Ct[(c - 1) * NM]) * inv_s; }
         __syncthreads();
-        // ---- P1: leverage vectors, Lagrange coefficients, kernel columns, cross kernel values (independent row tasks)
-        {
-            const int per = 2 * p + N;
-            int j = tid / per, r = tid - j * per;
-            for (; j < tb; ) {
-                const double* xi = XI + j * n; const double* pt = PT + j * pl;
-                if (r < p) {                       // HV[j][r] = sum_c H[r,c] pi~[c]
-                    double h0 = 0.0, h1 = 0.0;
-                    int c = 0;
-                    for (; c + 2 <= p; c += 2) { h0 = fma(H[r + c * pl], pt[c], h0); h1 = fma(H[r + (c + 1) * pl], pt[c + 1], h1); }
-                    for (; c < p; ++c) h0 = fma(H[r + c * pl], pt[c], h0);
-                    HV[j * pl + r] = h0 + h1;
-                } else if (r < 2 * p) {            // CV[j][r'] = sum_c M0[r',c] pi~[c]
-                    const int rr = r - p;
-                    double h0 = 0.0, h1 = 0.0;
-                    int c = 0;
-                    for (; c + 2 <= p; c += 2) { h0 = fma(M0[rr + c * pl], pt[c], h0); h1 = fma(M0[rr + (c + 1) * pl], pt[c + 1], h1); }
-                    for (; c < p; ++c) h0 = fma(M0[rr + c * pl], pt[c], h0);
-                    CV[j * pl + rr] = h0 + h1;
-                } else {                           // kernel column
-                    const int i = r - 2 * p;
-                    double r2a = 0.0, r2b = 0.0;
-                    int k = 0;
-                    for (; k + 2 <= n; k += 2) {
-                        const double d0 = xi[k] - Ct[k * NM + i], d1 = xi[k + 1] - Ct[(k + 1) * NM + i];
-                        r2a = fma(d0, d0, r2a); r2b = fma(d1, d1, r2b);
-                    }
-                    for (; k < n; ++k) { const double d0 = xi[k] - Ct[k * NM + i]; r2a = fma(d0, d0, r2a); }
-                    PH[j * NM + i] = rad_phi(P.rf, r2a + r2b);
+        // ---- P1: leverage vectors, Lagrange coefficients, kernel columns: one thread per row, all block members at once
+        // (the matrix row / centre is loaded once and feeds T independent accumulator chains)
+        for (int r = tid; r < 2 * p + N; r += nt) {
+            double acc[T];
+#pragma unroll
+            for (int j = 0; j < T; ++j) acc[j] = 0.0;
+            if (r < 2 * p) {
+                const double* Mx = (r < p) ? (H + r) : (M0 + (r - p));
+                for (int c = 0; c < p; ++c) {
+                    const double mv = Mx[c * pl];
+#pragma unroll
+                    for (int j = 0; j < T; ++j) acc[j] = fma(mv, PT[j * pl + c], acc[j]);
                 }
-                r += nt;
-                while (r >= per) { r -= per; ++j; }
+                double* dst = (r < p) ? (HV + r) : (CV + (r - p));
+#pragma unroll
+                for (int j = 0; j < T; ++j) if (j < tb) dst[j * pl] = acc[j];
+            } else {
+                const int i = r - 2 * p;
+                for (int k = 0; k < n; ++k) {
+                    const double cv_ = Ct[k * NM + i];
+#pragma unroll
+                    for (int j = 0; j < T; ++j) { const double d = XI[j * n + k] - cv_; acc[j] = fma(d, d, acc[j]); }
+                }
+#pragma unroll
+                for (int j = 0; j < T; ++j) if (j < tb) PH[j * NM + i] = rad_phi(P.rf, acc[j]);
             }
-            for (int q = tid; q < tb * tb; q += nt) {
-                const int i = q / tb, j2 = q % tb;
-                if (i < j2) {
-                    double r2 = 0.0;
-                    for (int k = 0; k < n; ++k) { double d = XI[i * n + k] - XI[j2 * n + k]; r2 = fma(d, d, r2); }
-                    Kx[i * T + j2] = rad_phi(P.rf, r2);
-                }
+        }
+        for (int q = tid; q < tb * tb; q += nt) {
+            const int i = q / tb, j2 = q % tb;
+            if (i < j2) {
+                double r2 = 0.0;
+                for (int k = 0; k < n; ++k) { double d = XI[i * n + k] - XI[j2 * n + k]; r2 = fma(d, d, r2); }
+                Kx[i * T + j2] = rad_phi(P.rf, r2);
             }
         }
         __syncthreads();
         // ---- P2: u_j = b_j - Phi00 c_j ; a_j[eta] = phi(eta, xi_j) - g_eta.c_j - c_eta.b_j ; leverage l_j = pi_j.h_j
-        {
-            const int per = p + m + 1;
-            int j = tid / per, r = tid - j * per;
-            for (; j < tb; ) {
-                const double* cv = CV + j * pl; const double* ph = PH + j * NM;
-                if (r < p) {
-                    double a0 = 0.0, a1 = 0.0;
-                    int c = 0;
-                    for (; c + 2 <= p; c += 2) { a0 = fma(P00[r + c * pl], cv[c], a0); a1 = fma(P00[r + (c + 1) * pl], cv[c + 1], a1); }
-                    for (; c < p; ++c) a0 = fma(P00[r + c * pl], cv[c], a0);
-                    UB[j * pl + r] = ph[r] - (a0 + a1);
-                } else if (r < p + m) {
-                    const int eta = r - p;
-                    const double* ge = Gm + eta * pb; const double* ce = Cm + eta * pb;
-                    double a0 = 0.0, a1 = 0.0;
-                    for (int c = 0; c < p; ++c) { a0 = fma(ge[c], cv[c], a0); a1 = fma(ce[c], ph[c], a1); }
-                    AV[j * MM + eta] = ph[base + eta] - a0 - a1;
-                } else {
-                    const double* hv = HV + j * pl; const double* pt = PT + j * pl;
-                    double a = 0.0;
-                    for (int c = 0; c < p; ++c) a = fma(hv[c], pt[c], a);
-                    Sx[j * T + j] = a;
+        for (int r = tid; r < p + m; r += nt) {
+            double acc[T];
+#pragma unroll
+            for (int j = 0; j < T; ++j) acc[j] = 0.0;
+            if (r < p) {
+                for (int c = 0; c < p; ++c) {
+                    const double mv = P00[r + c * pl];
+#pragma unroll
+                    for (int j = 0; j < T; ++j) acc[j] = fma(mv, CV[j * pl + c], acc[j]);
                 }
-                r += nt;
-                while (r >= per) { r -= per; ++j; }
+#pragma unroll
+                for (int j = 0; j < T; ++j) if (j < tb) UB[j * pl + r] = PH[j * NM + r] - acc[j];
+            } else {
+                const int eta = r - p;
+                const double* ge = Gm + eta * pb; const double* ce = Cm + eta * pb;
+                for (int c = 0; c < p; ++c) {
+                    const double gv = ge[c], cv_ = ce[c];
+#pragma unroll
+                    for (int j = 0; j < T; ++j) acc[j] = fma(gv, CV[j * pl + c], fma(cv_, PH[j * NM + c], acc[j]));
+                }
+#pragma unroll
+                for (int j = 0; j < T; ++j) if (j < tb) AV[j * MM + eta] = PH[j * NM + base + eta] - acc[j];
             }
+        }
+        if (tid >= nt - 32 && lane < tb) {         // leverages by the last warp
+            const double* hv = HV + lane * pl; const double* pt = PT + lane * pl;
+            double a = 0.0;
+            for (int c = 0; c < p; ++c) a = fma(hv[c], pt[c], a);
+            Sx[lane * T + lane] = a;
         }
         __syncthreads();
         // ---- P3: t_j = L^{-1} a_j for all block members at once (G threads per row share the row of L^{-1})
@@ -1168,26 +1171,35 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
             for (int j = 0; j < T; ++j) { const double s_ = warp_sum(tn[j]); if (lane == 0) tnp[warp * T + j] = s_; }
         }
         __syncthreads();
-        // ---- P4: pair quantities (warp per pair): A_ij, t_i.t_j, pi_i' H pi_j ; diagonal A_jj
-        for (int q = warp; q < (tb * (tb + 1)) / 2; q += nwarps) {
-            int j = 0;
-            while (((j + 1) * (j + 2)) / 2 <= q) ++j;          // q = j (j + 1) / 2 + i,  i <= j
-            const int i = q - (j * (j + 1)) / 2;
-            if (i < j) {
+        // ---- P4: pair quantities, 8 lanes per pair (i <= j): A_ij, t_i.t_j, pi_i' H pi_j ; diagonal A_jj
+        {
+            const int npair = (tb * (tb + 1)) / 2;
+            for (int q0 = 0; q0 < npair; q0 += nt / 8) {
+                const int q = q0 + (tid >> 3), l8 = tid & 7;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-                for (int c = lane; c < p; c += 32) {
-                    a0 = fma(UB[i * pl + c], CV[j * pl + c], a0);
-                    a0 = fma(CV[i * pl + c], PH[j * NM + c], a0);
-                    a2 = fma(HV[i * pl + c], PT[j * pl + c], a2);
+                int i = 0, j = 0;
+                if (q < npair) {
+                    while (((j + 1) * (j + 2)) / 2 <= q) ++j;          // q = j (j + 1) / 2 + i,  i <= j
+                    i = q - (j * (j + 1)) / 2;
+                    if (i < j) {
+                        for (int c = l8; c < p; c += 8) {
+                            a0 = fma(UB[i * pl + c], CV[j * pl + c], a0);
+                            a0 = fma(CV[i * pl + c], PH[j * NM + c], a0);
+                            a2 = fma(HV[i * pl + c], PT[j * pl + c], a2);
+                        }
+                        for (int r = l8; r < m; r += 8) a1 = fma(TV[i * MM + r], TV[j * MM + r], a1);
+                    } else {
+                        for (int c = l8; c < p; c += 8) a0 = fma(CV[j * pl + c], PH[j * NM + c] + UB[j * pl + c], a0);
+                    }
                 }
-                for (int r = lane; r < m; r += 32) a1 = fma(TV[i * MM + r], TV[j * MM + r], a1);
-                a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-                if (lane == 0) { Ax[i * T + j] = Kx[i * T + j] - a0; Dx[i * T + j] = a1; Sx[i * T + j] = a2; }
-            } else if (i == j) {
-                double a0 = 0.0;
-                for (int c = lane; c < p; c += 32) a0 = fma(CV[j * pl + c], PH[j * NM + c] + UB[j * pl + c], a0);
-                a0 = warp_sum(a0);
-                if (lane == 0) Ax[j * T + j] = phi0 - a0;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                }
+                if (q < npair && l8 == 0) {
+                    if (i < j) { Ax[i * T + j] = Kx[i * T + j] - a0; Dx[i * T + j] = a1; Sx[i * T + j] = a2; }
+                    else Ax[j * T + j] = phi0 - a0;
+                }
             }
         }
         __syncthreads();

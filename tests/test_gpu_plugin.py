@@ -168,6 +168,8 @@ def _run_iterations(cfg, ocfg, func, x0, glb, gub, n_iter, delta0=0.1, delta_max
         mod, meta = mb.update_model(mod, meta, cfg, fi, mop, scal, it, sdb, ac)
         omod = O.update_model(ometa, ocfg, odb)
         x = it.x_scaled
+        if omod.cond > 1e8:
+            break          # ill-conditioned training set: values agree only to cond * eps, Armijo decisions become knife-edge
         Yr, Jr = omod.eval(x), omod.jac(x)
         Y, J = mb.eval_models(mod, scal, x), mb.get_jacobian(mod, scal, x)
         ctol = 20 * omod.cond * np.finfo(float).eps           # LU (oracle) vs null-space solves differ at O(cond * eps)
