@@ -75,31 +75,44 @@ struct FilterState {
 // !(cflags & (CF_USED | avoid)).  Picks are appended to out[]; returns their number.
 __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* shifted seeds, coordinate-major: S[i*ldS + id] */, double* T,
                           int ldS, unsigned char* cflags, int n_db, unsigned want, unsigned avoid, double piv, int n_wanted, int* out) {
+    // T holds, per candidate, the projection coefficients y = W' s on the current trailing block W (coordinate-major like S).
+    // They are updated with the same reflector that updates W (O(n-j) per candidate and step) instead of being recomputed
+    // (O(n (n-j))), and the score || Z (Z' s) ||_inf is evaluated as || W (y ./ d^2) ||_inf with d the column inf-norms of W.
     const int n = st.n, ldz = st.ldz, tid = threadIdx.x, nt = blockDim.x;
+    const int G = (n_db > 128) ? 1 : ((n_db > 64) ? 2 : ((n_db > 32) ? 4 : 8));
+    const int cpp = nt / G;
+    double* invd2 = st.u;
     int found = 0;
-    // first pick: argmax ||s||_inf, first maximiser, unconditional (AffinelyIndependentPoints.jl:51-69)
+    // ---- y = W' s for every candidate of this run, and the first pick: argmax ||s||_inf, first maximiser, unconditional
     ArgMax mine; mine.v = 0.0; mine.id = -1;
-    for (int id = tid; id < n_db; id += nt) {
-        unsigned f = cflags[id];
-        if ((f & want) != want || (f & (CF_USED | avoid))) continue;
-        const double* s = S + id;
-        double v = 0.0;
-        for (int i = 0; i < n; ++i) v = fmax(v, fabs(s[i * ldS]));
-        ArgMax c; c.v = v; c.id = id;
-        mine = better(mine, c);
+    {
+        const int nw0 = n - st.jY;
+        for (int c0 = 0; c0 < n_db; c0 += cpp) {
+            const int id = c0 + tid / G, h = tid % G;
+            bool act = false;
+            if (id < n_db) { unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
+            if (!act) continue;
+            const double* s = S + id;
+            for (int c = h; c < nw0; c += G) {
+                const double* wc = st.W + c * ldz;
+                double a = 0.0;
+                for (int i = 0; i < n; ++i) a = fma(wc[i], s[i * ldS], a);
+                T[c * ldS + id] = a;
+            }
+            if (h == 0) {
+                double v = 0.0;
+                for (int i = 0; i < n; ++i) v = fmax(v, fabs(s[i * ldS]));
+                ArgMax c_; c_.v = v; c_.id = id;
+                mine = better(mine, c_);
+            }
+        }
     }
     ArgMax best = block_argmax(mine, st.red, st.redi);
     if (best.id < 0) return 0;
     for (;;) {
-        // ---- accept best.id: Y <- [Y s], update W (one Householder reflector) and Z
-        const double* y = S + best.id;
+        // ---- accept best.id: Y <- [Y s]; its projection on W is already in T
         const int nw = n - st.jY;                 // columns of W before the update
-        for (int c = tid; c < nw; c += nt) {      // xp = W' y
-            double a = 0.0;
-            const double* wc = st.W + c * ldz;
-            for (int i = 0; i < n; ++i) a = fma(wc[i], y[i * ldS], a);
-            st.xp[c] = a;
-        }
+        for (int c = tid; c < nw; c += nt) st.xp[c] = T[c * ldS + best.id];
         __syncthreads();
         if (tid < 32) {                           // dlarfg on xp[0..nw), one warp
             const double alpha = st.xp[0];
@@ -128,11 +141,61 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
             a *= tau;
             for (int c = 1; c < nw; ++c) st.W[i + (c - 1) * ldz] = fma(-a, st.vv[c], st.W[i + c * ldz]);
         }
+        for (int id = tid; id < n_db; id += nt) { // same reflector on the candidates' coefficients: y' = (y - tau v (v.y))[1:]
+            unsigned f = cflags[id];
+            if ((f & want) != want || (f & (CF_USED | avoid))) continue;
+            double* y = T + id;
+            double a = 0.0;
+            for (int c = 0; c < nw; ++c) a = fma(st.vv[c], y[c * ldS], a);
+            a *= tau;
+            for (int c = 1; c < nw; ++c) y[(c - 1) * ldS] = fma(-a, st.vv[c], y[c * ldS]);
+        }
         st.jY += 1;
         found += 1;
         __syncthreads();
         const int zc = n - st.jY;
-        for (int c = tid; c < zc; c += nt) {      // Z = W ./ colmax|W|  (AffinelyIndependentPoints.jl:8)
+        if (found == n_wanted) break;
+        for (int c = tid; c < zc; c += nt) {      // d_c = ||W[:, c]||_inf  (AffinelyIndependentPoints.jl:8)
+            const double* wc = st.W + c * ldz;
+            double mx = 0.0;
+            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(wc[i]));
+            invd2[c] = 1.0 / (mx * mx);
+        }
+        __syncthreads();
+        // ---- score the remaining candidates: || Z (Z' s) ||_inf = || W (y ./ d^2) ||_inf, strict '>' => first maximiser
+        mine.v = 0.0; mine.id = -1;
+        for (int c0 = 0; c0 < n_db; c0 += cpp) {
+            const int id = c0 + tid / G, h = tid % G;
+            bool act = false;
+            if (id < n_db) { unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
+            const double* y = T + id;
+            double v = 0.0;
+            if (act) {
+                int i = h;
+                for (; i + 3 * G < n; i += 4 * G) {
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    for (int q = 0; q < zc; ++q) {
+                        const double* wq = st.W + q * ldz + i; const double tq = y[q * ldS] * invd2[q];
+                        a0 = fma(wq[0], tq, a0); a1 = fma(wq[G], tq, a1); a2 = fma(wq[2 * G], tq, a2); a3 = fma(wq[3 * G], tq, a3);
+                    }
+                    v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
+                }
+                for (; i < n; i += G) {
+                    double a0 = 0;
+                    for (int q = 0; q < zc; ++q) a0 = fma(st.W[i + q * ldz], y[q * ldS] * invd2[q], a0);
+                    v = fmax(v, fabs(a0));
+                }
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (act && h == 0) { ArgMax cnd; cnd.v = v; cnd.id = id; mine = better(mine, cnd); }
+        }
+        best = block_argmax(mine, st.red, st.redi);
+        if (best.id < 0) break;                   // no more candidates
+        if (!(best.v > piv)) break;               // AffinelyIndependentPoints.jl:92
+    }
+    {                                             // Z = W ./ colmax|W| for the caller (improving directions)
+        const int zc = n - st.jY;
+        for (int c = tid; c < zc; c += nt) {
             const double* wc = st.W + c * ldz;
             double mx = 0.0;
             for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(wc[i]));
@@ -140,65 +203,6 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
             for (int i = 0; i < n; ++i) zcol[i] = wc[i] / mx;
         }
         __syncthreads();
-        if (found == n_wanted) break;
-        // ---- score the remaining candidates: || Z (Z' s) ||_inf, strict '>' => first maximiser.
-        // G threads share a candidate (t = Z's split by columns, r = Z t split by rows); every dot product keeps
-        // its sequential accumulation order, so the scores do not depend on G.
-        mine.v = 0.0; mine.id = -1;
-        {
-            const int G = (n_db > 128) ? 1 : ((n_db > 64) ? 2 : ((n_db > 32) ? 4 : 8));
-            const int cpp = nt / G;
-            for (int c0 = 0; c0 < n_db; c0 += cpp) {
-                const int id = c0 + tid / G, h = tid % G;
-                bool act = false;
-                if (id < n_db) { unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
-                const double* s = S + id;
-                double* t = T + id;
-                double v = 0.0;
-                if (act) {
-                    int c = h;
-                    for (; c + 3 * G < zc; c += 4 * G) {      // t = Z' s, four independent chains
-                        const double* z0 = st.Z + c * ldz; const double* z1 = z0 + G * ldz;
-                        const double* z2 = z1 + G * ldz; const double* z3 = z2 + G * ldz;
-                        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                        for (int i = 0; i < n; ++i) {
-                            const double si = s[i * ldS];
-                            a0 = fma(z0[i], si, a0); a1 = fma(z1[i], si, a1); a2 = fma(z2[i], si, a2); a3 = fma(z3[i], si, a3);
-                        }
-                        t[c * ldS] = a0; t[(c + G) * ldS] = a1; t[(c + 2 * G) * ldS] = a2; t[(c + 3 * G) * ldS] = a3;
-                    }
-                    for (; c < zc; c += G) {
-                        const double* z0 = st.Z + c * ldz;
-                        double a0 = 0;
-                        for (int i = 0; i < n; ++i) a0 = fma(z0[i], s[i * ldS], a0);
-                        t[c * ldS] = a0;
-                    }
-                }
-                __syncwarp();
-                if (act) {
-                    int i = h;
-                    for (; i + 3 * G < n; i += 4 * G) {       // r = Z t, inf-norm
-                        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                        for (int q = 0; q < zc; ++q) {
-                            const double* zq = st.Z + q * ldz + i; const double tq = t[q * ldS];
-                            a0 = fma(zq[0], tq, a0); a1 = fma(zq[G], tq, a1); a2 = fma(zq[2 * G], tq, a2); a3 = fma(zq[3 * G], tq, a3);
-                        }
-                        v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
-                    }
-                    for (; i < n; i += G) {
-                        double a0 = 0;
-                        for (int q = 0; q < zc; ++q) a0 = fma(st.Z[i + q * ldz], t[q * ldS], a0);
-                        v = fmax(v, fabs(a0));
-                    }
-                }
-                for (int o = G >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-                __syncwarp();
-                if (act && h == 0) { ArgMax cnd; cnd.v = v; cnd.id = id; mine = better(mine, cnd); }
-            }
-        }
-        best = block_argmax(mine, st.red, st.redi);
-        if (best.id < 0) break;                   // no more candidates
-        if (!(best.v > piv)) break;               // AffinelyIndependentPoints.jl:92
     }
     return found;
 }
