@@ -183,7 +183,6 @@ def run_ours(args):
                                       first_instance=rank * B)
     dev = upload_batch(host, f"cuda:{local}")
     builder = MultistartBuilder(eng, cfg, DELTA_MAX)
-    models = []
 
     def barrier():
         torch.cuda.synchronize()
@@ -192,25 +191,22 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
+        model = None            # every step replaces the previous iteration's models in place (no allocation per step)
         for _ in range(args.warmup):
-            m, sel, status = builder.step(dev); stream.synchronize(); m.free()
+            model, sel, status = builder.step(dev, recycle=model); stream.synchronize()
         l0 = eng.launch_count
         sampler = ClockSampler(local); sampler.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            m, sel, status = builder.step(dev)
-            models.append(m)
+            model, sel, status = builder.step(dev, recycle=model)
         e1.record(stream)
         stream.synchronize()
         barrier()
         clocks = sampler.stop()
         launches = eng.launch_count - l0
     ms = e0.elapsed_time(e1) / args.steps
-    for m in models[:-1]:
-        m.free()
-    model = models[-1]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -222,33 +218,38 @@ def run_ours(args):
     pinned = {k: torch.from_numpy(np.ascontiguousarray(host[k])).pin_memory() for k in names}
     h2d = sum(t.numel() * t.element_size() for t in pinned.values())
     out_pin = None
-    e2e_models = []
     with torch.cuda.stream(stream):
-        def e2e_step():
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+        def e2e_step(prev):
             nonlocal out_pin
+            marks[0].record(stream)
             for k in names:
                 getattr(dev, k).copy_(pinned[k], non_blocking=True)
-            m, sel, status = builder.step(dev)
+            marks[1].record(stream)
+            m, sel, status = builder.step(dev, recycle=prev)
+            marks[2].record(stream)
             outs = [sel.r1, sel.n_r1, sel.r2, sel.n_r2, sel.n_r3, sel.r4, sel.n_r4, sel.flags_out, status]
             if out_pin is None:
                 out_pin = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
             for p, o in zip(out_pin, outs):
                 p.copy_(o, non_blocking=True)
+            marks[3].record(stream)
             return m
         for _ in range(max(1, args.warmup // 2)):
-            m = e2e_step(); stream.synchronize(); m.free()
+            model = e2e_step(model); stream.synchronize()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(stream)
         for _ in range(args.steps):
-            e2e_models.append(e2e_step())
+            model = e2e_step(model)
         t1.record(stream)
         stream.synchronize()
         barrier()
     e2e_ms = t0.elapsed_time(t1) / args.steps
+    e2e_parts = {"h2d_ms": marks[0].elapsed_time(marks[1]), "compute_ms": marks[1].elapsed_time(marks[2]),
+                 "d2h_ms": marks[2].elapsed_time(marks[3])}       # last step
     d2h = sum(p.numel() * p.element_size() for p in out_pin)
-    for m in e2e_models:
-        m.free()
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -257,10 +258,9 @@ def run_ours(args):
     # ---- per-kernel device times (one extra, untimed-for-the-metric step with event brackets) and roofline
     eng.profile_enable(True)
     with torch.cuda.stream(stream):
-        m2, sel, status = builder.step(dev)
+        model, sel, status = builder.step(dev, recycle=model)
     prof = eng.profile_read()
     eng.profile_enable(False)
-    m2.free()
     n_r1, n_r2, n_r3, n_r4 = (getattr(sel, a).cpu().numpy() for a in ("n_r1", "n_r2", "n_r3", "n_r4"))
     N0 = 1 + n_r1 + n_r2 + n_r3
     Ntrain = N0 + n_r4
@@ -320,12 +320,12 @@ def run_ours(args):
                            "parallelism": f"instances sharded over {world} rank(s), no data-path collective"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_ms,
+                        "ms_per_step": e2e_ms, "last_step_parts": {k: round(v, 3) for k, v in e2e_parts.items()},
                         "path": "pinned host database snapshot -> H2D -> mrbf_select_points_dev + gather + mrbf_build_dev -> D2H of "
                                 "indices/flags/status (models stay device-resident handles, as in the ABI)"},
                 "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
                 "gathered_rows": None if allrows is None else int(allrows.shape[0])}
-        print(json.dumps(line))
+        emit(line)
     model.free()
     if world > 1:
         dist.destroy_process_group()
@@ -360,7 +360,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
                              "sample": f"{sample} instances per step; C port of the reference path (no Julia in this image)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_once(cfg, host, nthr, CO, synthetic):
@@ -378,7 +378,21 @@ def cpu_baseline_once(cfg, host, nthr, CO, synthetic):
     CO.build_batched(cfg, S, V, Ns, nthreads=nthr)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to fd 1 (NCCL's version
+    banner, library chatter) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -166,7 +166,9 @@ int mrbf_gather_training_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int
 /* ---- model build: replaces update_model -> RBF.RBFInterpolationModel ---------------------------
  * src/models/RbfModel.jl:743-767.  sites B x train_stride x n, values B x train_stride x k, N: B (sites used).
  * shape: B per-instance shape parameters or NULL (then cfg->shape_parameter).  Creates one device-resident
- * handle for the whole batch.  status[b]: 0 ok, > 0 reduced kernel matrix not positive definite at that column. */
+ * handle for the whole batch.  *model must be NULL or a handle from an earlier build call: its device buffers are
+ * recycled when the shapes match (no allocation on the hot path; the reference likewise replaces the model in
+ * place, SurrogateContainer.jl:376-382), else it is freed and replaced.  On error *model is NULL.  status[b]: 0 ok, > 0 reduced kernel matrix not positive definite at that column. */
 int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
                const int32_t* N, const double* sites, const double* values, const double* shape,
                mrbf_model** model, int32_t* status);

@@ -41,6 +41,8 @@ struct mrbf_prepared {
     double* fs = nullptr;
     int* ints = nullptr;        // elig[B], n_found[B], n_extra[B], n_r4[B], found[B*found_stride], r4[B*r4_stride]
     int *elig, *n_found, *n_extra, *n_r4, *found, *r4;
+    int kind = 0;               // 0: round4_block_kernel layout (round4_fast_state_layout), 1: round4_schur_kernel layout
+    SchurGeom geom{};
 };
 
 struct mrbf_model {
@@ -158,22 +160,31 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
     R.extra_sites = extra; R.n_extra = n_extra; R.r4 = r4; R.n_r4 = n_r4; R.status = status;
     ENSURE(ctx->ws[6], (size_t)B * db_stride * 5);      // int candidate list + byte flags per database entry
     R.cand = (unsigned char*)ctx->ws[6].p;
-    // 1. shared-memory fast path (regular case N0 == p); marks the instances it cannot take with n_r4 = -1
+    // 1. fast paths for the regular case N0 == p; both mark the instances they cannot take with n_r4 = -1.
+    //    (a) register-tiled right-looking elimination when the database has <= 128 sites and its panels fit in shared memory,
+    //    (b) else the blocked left-looking kernel (state in shared memory or in a global workspace).
     {
-        const size_t fsd = round4_fast_state_doubles(n, NM, p);
-        // block size: 8 candidates per block when the block buffers still fit beside the state in shared memory, else 4
+        const SchurGeom geom = round4_schur_geom(n, p, db_stride);
+        const bool schur = geom.eligible != 0;
+        const size_t fsd = schur ? geom.state_doubles : round4_fast_state_doubles(n, NM, p);
         int Tb = 8;
-        size_t fv = round4_block_vec_doubles(8, n, NM, p);
-        if ((fv + fsd) * sizeof(double) > SMEM_LIMIT && (round4_block_vec_doubles(4, n, NM, p) + fsd) * sizeof(double) <= SMEM_LIMIT) {
-            Tb = 4; fv = round4_block_vec_doubles(4, n, NM, p);
+        size_t fv = 0, fsmem = 0;
+        if (!schur) {
+            // block size: 8 candidates per block when the block buffers still fit beside the state in shared memory, else 4
+            fv = round4_block_vec_doubles(8, n, NM, p);
+            if ((fv + fsd) * sizeof(double) > SMEM_LIMIT && (round4_block_vec_doubles(4, n, NM, p) + fsd) * sizeof(double) <= SMEM_LIMIT) {
+                Tb = 4; fv = round4_block_vec_doubles(4, n, NM, p);
+            }
+            fsmem = fv * sizeof(double);
+            if (fsmem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
         }
-        size_t fsmem = fv * sizeof(double);
-        if (fsmem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
         R.fs_stride = fsd;
         if (keep_out && *keep_out && (*keep_out)->B == B && (*keep_out)->n == n && (*keep_out)->NM == NM && (*keep_out)->p == p &&
-            (*keep_out)->found_stride == found_stride && (*keep_out)->r4_stride == r4_stride && (*keep_out)->fs_stride == fsd) {
+            (*keep_out)->found_stride == found_stride && (*keep_out)->r4_stride == r4_stride && (*keep_out)->fs_stride == fsd &&
+            (*keep_out)->kind == (schur ? 1 : 0)) {
             mrbf_prepared* kp = *keep_out;       // reuse the caller's handle (same shapes): no allocation on the hot path
             kp->db_stride = db_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
+            kp->geom = geom;
             R.keep_fs = kp->fs; R.elig = kp->elig;
         } else if (keep_out) {
             if (*keep_out) { mrbf_free_prepared(ctx, *keep_out); *keep_out = nullptr; }
@@ -181,7 +192,7 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             if (!kp) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
             kp->B = B; kp->n = n; kp->NM = NM; kp->p = p; kp->db_stride = db_stride; kp->found_stride = found_stride;
             kp->r4_stride = r4_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
-            kp->fs_stride = fsd;
+            kp->fs_stride = fsd; kp->kind = schur ? 1 : 0; kp->geom = geom;
             const size_t ni = (size_t)B * 4 + (size_t)B * found_stride + (size_t)B * r4_stride;
             cudaError_t e1 = cudaMalloc(&kp->fs, (size_t)B * fsd * sizeof(double));
             cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc(&kp->ints, ni * sizeof(int)) : e1;
@@ -191,13 +202,18 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             R.keep_fs = kp->fs; R.elig = kp->elig;
             *keep_out = kp;
         }
-        if ((fv + fsd) * sizeof(double) <= SMEM_LIMIT) { R.fs_in_smem = 1; fsmem = (fv + fsd) * sizeof(double); R.fs = nullptr; }
-        else {
-            R.fs_in_smem = 0;
-            if (!keep_out) { ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double)); R.fs = (double*)ctx->ws[9].p; }
+        if (schur) {
+            Timed t_(ctx, 1);
+            CK(launch_round4_schur(R, geom, ctx->stream));
+        } else {
+            if ((fv + fsd) * sizeof(double) <= SMEM_LIMIT) { R.fs_in_smem = 1; fsmem = (fv + fsd) * sizeof(double); R.fs = nullptr; }
+            else {
+                R.fs_in_smem = 0;
+                if (!keep_out) { ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double)); R.fs = (double*)ctx->ws[9].p; }
+            }
+            Timed t_(ctx, 1);
+            CK(launch_round4_block(R, Tb, fsmem, ctx->stream));
         }
-        Timed t_(ctx, 1);
-        CK(launch_round4_block(R, Tb, fsmem, ctx->stream));
         ctx->launches += 1;
     }
     // 2. literal kernel for the marked rest (N0 != p: budget-limited round 3, explicit found sets, rank-deficient Pi_0)
@@ -495,8 +511,9 @@ void mrbf_free_model(mrbf_ctx* ctx, mrbf_model* m) {
 static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
                       const int32_t* N, const double* sites, const double* values, const double* shape,
                       mrbf_model** out, int32_t* status, const mrbf_prepared* kp, const double* db_values, const double* r3_values,
-                      const int* skip_from_prepared) {
+                      const int* skip_from_prepared, const double* db_sites = nullptr, const double* r3_sites = nullptr) {
     if (!ctx || !out) return MRBF_EINVAL;
+    mrbf_model* recycle = *out;                 // NULL, or an earlier handle whose device buffers are reused when the shapes match
     *out = nullptr;
     int rc = check_cfg(ctx, cfg);
     if (rc != MRBF_OK) return rc;
@@ -509,21 +526,28 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     if (deg < cpd - 1) deg = cpd - 1;           // degree raised to cpd_order - 1 (assumption U4)
     if (deg > 1) return fail(ctx, MRBF_EUNSUPPORTED, "kernel needs a polynomial tail of degree > 1%s");
     const int p = poly_dim(n, deg), pl = p > 0 ? p : 1;
-    mrbf_model* m = new (std::nothrow) mrbf_model();
-    if (!m) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
-    m->B = B; m->n = n; m->k = k; m->train_stride = train_stride; m->p = p; m->deg = deg;
-    m->kernel = rf.kernel; m->ibeta = rf.ibeta; m->sgn = rf.sgn;
+    mrbf_model* m = nullptr;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaMalloc(&m->N, sizeof(int) * (size_t)B);
-    if (e == cudaSuccess) e = cudaMalloc(&m->centers, sizeof(double) * (size_t)B * train_stride * n);
-    if (e == cudaSuccess) e = cudaMalloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
-    if (e == cudaSuccess) e = cudaMalloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
-    if (e == cudaSuccess) e = cudaMalloc(&m->alpha2, sizeof(double) * (size_t)B);
-    if (e == cudaSuccess && n <= 64 && k <= 16) {   // geometry of the tiled copy; the buffer itself is allocated on first use
-        m->pack_s = eval_pack_stride(n); m->pack_nt = (train_stride + 63) / 64;
-        m->pack_tile_doubles = (size_t)64 * m->pack_s + 64 + (size_t)k * 64;
+    if (recycle && recycle->B == B && recycle->n == n && recycle->k == k && recycle->train_stride == train_stride && recycle->p == p) {
+        m = recycle;                            // same stream => ordered after every earlier use of the handle
+        m->deg = deg; m->pack_valid = false;
+    } else {
+        if (recycle) mrbf_free_model(ctx, recycle);
+        m = new (std::nothrow) mrbf_model();
+        if (!m) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
+        m->B = B; m->n = n; m->k = k; m->train_stride = train_stride; m->p = p; m->deg = deg;
+        if (e == cudaSuccess) e = cudaMalloc(&m->N, sizeof(int) * (size_t)B);
+        if (e == cudaSuccess) e = cudaMalloc(&m->centers, sizeof(double) * (size_t)B * train_stride * n);
+        if (e == cudaSuccess) e = cudaMalloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
+        if (e == cudaSuccess) e = cudaMalloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
+        if (e == cudaSuccess) e = cudaMalloc(&m->alpha2, sizeof(double) * (size_t)B);
+        if (e == cudaSuccess && n <= 64 && k <= 16) {   // geometry of the tiled copy; the buffer itself is allocated on first use
+            m->pack_s = eval_pack_stride(n); m->pack_nt = (train_stride + 63) / 64;
+            m->pack_tile_doubles = (size_t)64 * m->pack_s + 64 + (size_t)k * 64;
+        }
+        if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
     }
-    if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    m->kernel = rf.kernel; m->ibeta = rf.ibeta; m->sgn = rf.sgn;
     BuildParams Pb{};
     Pb.B = B; Pb.n = n; Pb.k = k; Pb.train_stride = train_stride; Pb.p = p; Pb.deg = deg;
     Pb.kernel = rf.kernel; Pb.ibeta = rf.ibeta; Pb.sgn = rf.sgn; Pb.alpha_default = alpha;
@@ -551,7 +575,20 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     }
     if (e == cudaSuccess) e = cudaMemsetAsync(m->w, 0, sizeof(double) * (size_t)B * train_stride * k, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->lam, 0, sizeof(double) * (size_t)B * pl * k, ctx->stream);
-    if (e == cudaSuccess && kp && kp->cfg_degree == deg && kp->p > 0) {
+    if (e == cudaSuccess && kp && kp->kind == 1 && kp->cfg_degree == deg && kp->p > 0) {
+        // 1'. factorisation kept by round4_schur_kernel: two triangular solves per output
+        SchurBuildParams Q{};
+        const SchurGeom& g = kp->geom;
+        Q.B = B; Q.n = n; Q.k = k; Q.p = kp->p; Q.deg = deg; Q.db_stride = kp->db_stride; Q.found_stride = kp->found_stride;
+        Q.r4_stride = kp->r4_stride; Q.train_stride = train_stride; Q.MC = g.MC; Q.fs_stride = kp->fs_stride;
+        Q.off_M0 = g.off_M0; Q.off_U = g.off_U; Q.off_C = g.off_C; Q.off_L = g.off_L; Q.off_acc = g.off_acc;
+        Q.fs = kp->fs; Q.elig = kp->elig; Q.found = kp->found; Q.n_found = kp->n_found; Q.r4 = kp->r4;
+        Q.sites = db_sites; Q.values = db_values; Q.r3_sites = r3_sites; Q.r3_values = r3_values; Q.alpha2 = alpha * alpha;
+        Q.centers = m->centers; Q.w = m->w; Q.lam = m->lam; Q.alpha2_out = m->alpha2; Q.N = m->N; Q.status = status; Q.done = (int*)skip_from_prepared;
+        const size_t psm = build_schur_smem_doubles(k, g.MC, kp->p) * sizeof(double);
+        if (psm <= SMEM_LIMIT) { Timed t_(ctx, 6); e = launch_build_schur(Q, psm, ctx->stream); ctx->launches += 1; }
+        else e = cudaMemsetAsync((void*)skip_from_prepared, 0, sizeof(int) * (size_t)B, ctx->stream);
+    } else if (e == cudaSuccess && kp && kp->cfg_degree == deg && kp->p > 0) {
         // 1. instances whose round 4 kept its factorisation: two triangular mat-vecs per output
         PreparedBuildParams Q{};
         Q.B = B; Q.n = n; Q.k = k; Q.NM = kp->NM; Q.p = kp->p; Q.deg = deg; Q.db_stride = kp->db_stride;
@@ -604,7 +641,7 @@ int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepa
     G.train_sites = tsit; G.train_values = tval; G.N = Ntmp; G.skip = nullptr;
     { Timed t_(ctx, 2); CK(launch_gather_training(G, ctx->stream)); }
     ctx->launches += 1;
-    return build_impl(ctx, cfg, B, n, k, ts, Ntmp, tsit, tval, nullptr, out, status, kp, values, r3_values, done);
+    return build_impl(ctx, cfg, B, n, k, ts, Ntmp, tsit, tval, nullptr, out, status, kp, values, r3_values, done, sites, r3_sites);
 }
 
 int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,

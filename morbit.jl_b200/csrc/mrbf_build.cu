@@ -355,6 +355,128 @@ cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cud
     return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Build from the factorisation kept by round4_schur_kernel (mrbf_round4_schur.cu).
+//
+// That kernel leaves, per instance: M0 = Pi_0^{-T}, the panels C (Lagrange coefficients) and U = Phi(S0, .) - Phi00 C over
+// the candidate positions, and the Cholesky factor L of A = N' Phi N over the accepted candidates (column q = q-th accepted
+// pivot, rows indexed by candidate position).  With the training order [S0; accepted] (_collect_indices, RbfModel.jl:178-186):
+//     r = Y_acc - C_acc' Y_0,   L L' u = r,   w = [-C_acc u; u],   lambda~ = Pi_0^{-1} (Y_0 - U_acc u)
+// i.e. two triangular solves per output instead of the O(N^3) saddle-point solve of RBFInterpolationModel (RbfModel.jl:759).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, k = P.k, p = P.p, MC = P.MC, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (!P.elig[b]) { if (tid == 0) P.done[b] = 0; return; }
+    const double* fs = P.fs + (size_t)b * P.fs_stride;
+    const double* meta = fs + P.off_acc + MC;
+    const double inv_s = meta[0];
+    const int N0 = (int)meta[1], m = (int)meta[2];
+    const int N = N0 + m;
+    const double* M0g = fs + P.off_M0; const double* Ug = fs + P.off_U; const double* Cg = fs + P.off_C; const double* Lg = fs + P.off_L;
+    double* y0 = smem;                          // p x k
+    double* rv = y0 + (size_t)p * k;            // MC x k  (stored output-major: rv[o * MC + q])
+    double* t0 = rv + (size_t)MC * k;           // p x k
+    double* sv = t0 + (size_t)p * k;            // p x k
+    double* invd = sv + (size_t)p * k;          // MC
+    double* Ls = invd + MC;                     // packed columns: column q at cs(q) = q m - q (q - 1) / 2, rows q..m-1
+    int* accpos = reinterpret_cast<int*>(Ls + ((size_t)MC * (MC + 1)) / 2);
+    const int* found = P.found + (size_t)b * P.found_stride;
+    const int nf = P.n_found[b];
+    const int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    const double* sites = P.sites + (size_t)b * P.db_stride * n;
+    const double* values = P.values + (size_t)b * P.db_stride * k;
+    const double* r3s = P.r3_sites ? P.r3_sites + (size_t)b * n * n : nullptr;
+    const double* r3v = P.r3_values ? P.r3_values + (size_t)b * n * k : nullptr;
+    for (int q = tid; q < m; q += nt) accpos[q] = (int)fs[P.off_acc + q];
+    for (int e = tid; e < p * k; e += nt) {
+        const int i = e / k, o = e % k;
+        y0[e] = (i < nf) ? values[(size_t)(found[i] - 1) * k + o] : (r3v ? r3v[(size_t)(i - nf) * k + o] : 0.0);
+    }
+    double* centers = P.centers + (size_t)b * P.train_stride * n;
+    for (int e = tid; e < N * n; e += nt) {
+        const int i = e / n, c = e % n;
+        double v;
+        if (i < nf) v = sites[(size_t)(found[i] - 1) * n + c];
+        else if (i < N0) v = r3s[(size_t)(i - nf) * n + c];
+        else v = sites[(size_t)(r4[i - N0] - 1) * n + c];
+        centers[e] = v;
+    }
+    __syncthreads();
+    for (int q = warp; q < m; q += nwarps) {     // packed copy of L restricted to the accepted rows
+        const double* Lc = Lg + (size_t)q * MC;
+        double* dst = Ls + ((size_t)q * m - ((size_t)q * (q - 1)) / 2) - q;
+        for (int q2 = q + lane; q2 < m; q2 += 32) { const double v = Lc[accpos[q2]]; dst[q2] = v; if (q2 == q) invd[q] = 1.0 / v; }
+    }
+    for (int e = tid; e < m * k; e += nt) {      // r = Y_acc - C_acc' Y_0
+        const int q = e % m, o = e / m;
+        double a = values[(size_t)(r4[q] - 1) * k + o];
+        const double* cq = Cg + accpos[q];
+        for (int r = 0; r < p; ++r) a = fma(-cq[(size_t)r * MC], y0[r * k + o], a);
+        rv[o * MC + q] = a;
+    }
+    __syncthreads();
+    for (int o = warp; o < k; o += nwarps) {     // L t = r, then L' u = t: one warp per output, column-oriented updates
+        double* r = rv + o * MC;
+        for (int q = 0; q < m; ++q) {
+            const double t = r[q] * invd[q];
+            const double* col = Ls + ((size_t)q * m - ((size_t)q * (q - 1)) / 2) - q;
+            __syncwarp();
+            if (lane == 0) r[q] = t;
+            for (int q2 = q + 1 + lane; q2 < m; q2 += 32) r[q2] = fma(-col[q2], t, r[q2]);
+            __syncwarp();
+        }
+        for (int q = m - 1; q >= 0; --q) {
+            const double* col = Ls + ((size_t)q * m - ((size_t)q * (q - 1)) / 2) - q;
+            double a = 0.0;
+            for (int q2 = q + 1 + lane; q2 < m; q2 += 32) a = fma(col[q2], r[q2], a);
+            a = warp_sum(a);
+            __syncwarp();
+            if (lane == 0) r[q] = (r[q] - a) * invd[q];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* w_out = P.w + (size_t)b * P.train_stride * k;
+    double* lam_out = P.lam + (size_t)b * p * k;
+    for (int e = tid; e < m * k; e += nt) { const int q = e / k, o = e % k; w_out[(size_t)(p + q) * k + o] = rv[o * MC + q]; }
+    for (int e = warp; e < p * k; e += nwarps) { // w_0 = -C_acc u ; t0 = Y_0 - U_acc u   (warp per entry, lanes over the accepted points)
+        const int r = e / k, o = e % k;
+        const double* u = rv + o * MC;
+        double a = 0.0, g = 0.0;
+        for (int q = lane; q < m; q += 32) { const int pos = accpos[q]; a = fma(Cg[(size_t)r * MC + pos], u[q], a); g = fma(Ug[(size_t)r * MC + pos], u[q], g); }
+        a = warp_sum(a); g = warp_sum(g);
+        if (lane == 0) { w_out[(size_t)r * k + o] = -a; t0[e] = y0[e] - g; }
+    }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) {      // lambda~ = Pi_0^{-1} t0 = M0' t0
+        const int c = e / k, o = e % k;
+        double a = 0.0;
+        for (int r = 0; r < p; ++r) a = fma(M0g[r + (size_t)c * p], t0[r * k + o], a);
+        sv[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) {      // back from the centred / scaled basis to the monomials (1, x_1..x_n)
+        const int c = e / k, o = e % k;
+        double val;
+        if (c == 0) { val = sv[o]; for (int j = 1; j < p; ++j) val = fma(-sv[(size_t)j * k + o] * inv_s, centers[j - 1], val); }
+        else val = sv[e] * inv_s;
+        lam_out[e] = val;
+    }
+    if (tid == 0) { P.N[b] = N; P.alpha2_out[b] = P.alpha2; P.status[b] = 0; P.done[b] = 1; }
+}
+
+size_t build_schur_smem_doubles(int k, int MC, int p) {
+    return 3 * (size_t)p * k + (size_t)MC * k + MC + ((size_t)MC * (MC + 1)) / 2 + (MC + 1) / 2 + 2;
+}
+cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(build_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    build_schur_kernel<<<P.B, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
 size_t build_vec_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return 2 * (size_t)ld + pl + 80; }
 size_t build_ws_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return (size_t)ld * ld + (size_t)ld * pl + (size_t)ld * k; }
 

@@ -87,6 +87,13 @@ __device__ __forceinline__ void rad_phi_psi(const RadFn& f, double r2, double& p
     }
 }
 
+// results_in_box_indices' test (Databases.jl:324-327): inclusive bounds on every coordinate.
+__device__ __forceinline__ bool in_box_pt(const double* s, const double* lb, const double* ub, int n) {
+    bool ok = true;
+    for (int i = 0; i < n; ++i) ok = ok && (lb[i] <= s[i]) && (s[i] <= ub[i]);
+    return ok;
+}
+
 __host__ __device__ inline int poly_dim(int n, int deg) { return deg < 0 ? 0 : (deg == 0 ? 1 : n + 1); }
 
 // ---- block-wide reductions (deterministic order) ----------------------------------------------

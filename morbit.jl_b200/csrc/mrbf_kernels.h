@@ -42,6 +42,14 @@ struct Round4Params {
     double* keep_fs; int* elig;                     // kept factorisation (mrbf_prepared) or NULL
 };
 
+// Geometry of the register-tiled round-4 kernel (mrbf_round4_schur.cu): shared-memory offsets and the layout of the
+// kept factorisation, all in doubles.
+struct SchurGeom {
+    int MC, TR, ntiles, nthreads, eligible;
+    size_t sm_C, sm_V, sm_Xc, sm_X0, sm_M0, sm_P00, sm_col, sm_red, sm_int, smem_doubles;
+    size_t off_M0, off_U, off_C, off_L, off_acc, state_doubles;
+};
+
 struct GatherParams {
     int B, n, k, db_stride, r4_stride, train_stride;
     const double* sites; const double* values; const int* x_index;
@@ -68,6 +76,16 @@ struct PreparedBuildParams {
     size_t fs_stride, off_M0, off_G, off_C, off_L;
     const double* fs; const int* elig; const int* found; const int* n_found; const int* n_extra; const int* r4; const int* n_r4;
     const double* values; const double* r3_values;
+    double alpha2;
+    double* centers; double* w; double* lam; double* alpha2_out; int* N; int* status; int* done;
+};
+
+// Build from the factorisation kept by round4_schur_kernel (layout: SchurGeom::off_*).
+struct SchurBuildParams {
+    int B, n, k, p, deg, db_stride, found_stride, r4_stride, train_stride, MC;
+    size_t fs_stride, off_M0, off_U, off_C, off_L, off_acc;
+    const double* fs; const int* elig; const int* found; const int* n_found; const int* r4;
+    const double* sites; const double* values; const double* r3_sites; const double* r3_values;
     double alpha2;
     double* centers; double* w; double* lam; double* alpha2_out; int* N; int* status; int* done;
 };
@@ -112,10 +130,14 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
 cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s);
 cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s);
 size_t round4_block_vec_doubles(int T, int n, int NM, int p);
+SchurGeom round4_schur_geom(int n, int p, int db_stride);
+cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaStream_t s);
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s);
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s);
 size_t build_prepared_smem_doubles(int n, int k, int NM, int p);
+cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStream_t s);
+size_t build_schur_smem_doubles(int k, int MC, int p);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);
 cudaError_t launch_eval_pack(const PackParams& P, cudaStream_t s);
 int eval_pack_stride(int n);

@@ -236,14 +236,19 @@ class Engine:
             return out, prepared
         return out, Prepared(self, handle.value)
 
-    def build_prepared_dev(self, cfg, prepared, sites, values, x_index, sel: SelectResult, r3_values=None, status=None):
-        """update_model from the factorisation kept by select_points_keep_dev (general route for the rest)."""
+    def build_prepared_dev(self, cfg, prepared, sites, values, x_index, sel: SelectResult, r3_values=None, status=None,
+                           recycle: Optional[ModelBatch] = None):
+        """update_model from the factorisation kept by select_points_keep_dev (general route for the rest).
+        `recycle`: an earlier ModelBatch whose device buffers are reused when the shapes match (it must not be used
+        afterwards; the returned ModelBatch replaces it)."""
         import torch
         B = sites.shape[0]
         k = values.shape[2]
         if status is None:
             status = torch.zeros(B, dtype=torch.int32, device=sites.device)
-        handle = C.c_void_p()
+        handle = C.c_void_p(recycle.handle if recycle is not None else None)
+        if recycle is not None:
+            recycle.handle = None               # ownership moves through the call
         ccfg = to_c_cfg(cfg)
         self._check(self.lib.mrbf_build_prepared_dev(
             self.ctx, C.byref(ccfg), prepared.handle, k, _ptr(sites), _ptr(values), _ptr(sel.r3_sites), _ptr(r3_values),
@@ -283,13 +288,15 @@ class Engine:
             self._check(rc)
         return ModelBatch(self, handle.value), status
 
-    def build_dev(self, cfg, sites, values, N, shape=None, status=None):
+    def build_dev(self, cfg, sites, values, N, shape=None, status=None, recycle: Optional[ModelBatch] = None):
         import torch
         B, ts, n = sites.shape
         k = values.shape[2]
         if status is None:
             status = torch.zeros(B, dtype=torch.int32, device=sites.device)
-        handle = C.c_void_p()
+        handle = C.c_void_p(recycle.handle if recycle is not None else None)
+        if recycle is not None:
+            recycle.handle = None
         ccfg = to_c_cfg(cfg)
         self._check(self.lib.mrbf_build_dev(self.ctx, C.byref(ccfg), B, n, k, ts, _ptr(N), _ptr(sites), _ptr(values), _ptr(shape),
                                             C.byref(handle), _ptr(status)))

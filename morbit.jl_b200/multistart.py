@@ -72,7 +72,7 @@ class MultistartBuilder:
                                                   d.glb, d.gub, d.flags_in, d.max_new, out=self._sel)
         return self._sel
 
-    def build(self, d: DeviceBatch, sel: SelectResult, r3_values=None) -> Tuple[ModelBatch, object]:
+    def build(self, d: DeviceBatch, sel: SelectResult, r3_values=None, recycle=None) -> Tuple[ModelBatch, object]:
         import torch
         B, db_stride, n = d.sites.shape
         k = d.values.shape[2]
@@ -86,16 +86,18 @@ class MultistartBuilder:
         self._train = self.engine.gather_training_dev(d.sites, d.values, d.x_index, sel, r3_values, ts, out=self._train)
         if self._status is None or self._status.shape[0] != B:
             self._status = torch.zeros(B, dtype=torch.int32, device=d.sites.device)
-        model, status = self.engine.build_dev(self.cfg, self._train[0], self._train[1], self._train[2], None, self._status)
+        model, status = self.engine.build_dev(self.cfg, self._train[0], self._train[1], self._train[2], None, self._status,
+                                              recycle=recycle)
         return model, status
 
-    def step(self, d: DeviceBatch, fused: bool = True) -> Tuple[ModelBatch, SelectResult, object]:
+    def step(self, d: DeviceBatch, fused: bool = True, recycle=None) -> Tuple[ModelBatch, SelectResult, object]:
         """One build per instance.  fused=True keeps the round-4 factorisation and builds from it
         (mrbf_select_points_keep_dev + mrbf_build_prepared_dev); fused=False is the reference's two independent
-        phases (rounds 1-4, then a from-scratch solve of the gathered training set)."""
+        phases (rounds 1-4, then a from-scratch solve of the gathered training set).  `recycle`: the previous
+        iteration's ModelBatch, replaced in place like SurrogateContainer.jl:376-382 (no allocation per step)."""
         if not fused:
             sel = self.select(d)
-            model, status = self.build(d, sel)
+            model, status = self.build(d, sel, recycle=recycle)
             return model, sel, status
         import torch
         self._sel, self._prepared = self.engine.select_points_keep_dev(self.cfg, d.sites, d.n_db, d.x_index, d.x, d.delta,
@@ -109,7 +111,7 @@ class MultistartBuilder:
         if self._status is None or self._status.shape[0] != B:
             self._status = torch.zeros(B, dtype=torch.int32, device=d.sites.device)
         model, status = self.engine.build_prepared_dev(self.cfg, prepared, d.sites, d.values, d.x_index, self._sel,
-                                                       self._r3_values, self._status)
+                                                       self._r3_values, self._status, recycle=recycle)
         return model, self._sel, status
 
 
