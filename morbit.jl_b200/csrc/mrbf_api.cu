@@ -141,7 +141,7 @@ int max_points_of(const mrbf_cfg* cfg, int n) {
 int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, const double* sites, const int* n_db,
                const double* lb2, const double* ub2, int found_stride, const int* found, const int* n_found,
                int extra_stride, const double* extra, const int* n_extra, int n0max, int r4_stride, int* r4, int* n_r4, int* status,
-               mrbf_prepared** keep_out = nullptr) {
+               mrbf_prepared** keep_out = nullptr, const unsigned char* cflags = nullptr) {
     RadFn rf; double alpha; int cpd;
     int rc = resolve_radfn(ctx, cfg, cfg->shape_parameter, &rf, &alpha, &cpd);
     if (rc != MRBF_OK) return rc;
@@ -160,6 +160,7 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
     R.extra_sites = extra; R.n_extra = n_extra; R.r4 = r4; R.n_r4 = n_r4; R.status = status;
     ENSURE(ctx->ws[6], (size_t)B * db_stride * 5);      // int candidate list + byte flags per database entry
     R.cand = (unsigned char*)ctx->ws[6].p;
+    R.cflags = cflags;
     // 1. fast paths for the regular case N0 == p; both mark the instances they cannot take with n_r4 = -1.
     //    (a) register-tiled right-looking elimination when the database has <= 128 sites and its panels fit in shared memory,
     //    (b) else the blocked left-looking kernel (state in shared memory or in a global workspace).
@@ -366,7 +367,7 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     ctx->launches += 1;
     if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
         rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,
-                        n, r3_sites, n_r3, n + 1, r4_stride, r4, n_r4, status, keep);
+                        n, r3_sites, n_r3, n + 1, r4_stride, r4, n_r4, status, keep, S.cflags);
         if (rc != MRBF_OK) return rc;
     } else {
         CK(cudaMemsetAsync(n_r4, 0, sizeof(int) * (size_t)B, ctx->stream));

@@ -35,6 +35,7 @@ struct Round4Params {
     const int* found; const int* n_found; const double* extra_sites; const int* n_extra;
     int* r4; int* n_r4; int* status;
     unsigned char* cand;          // B x db_stride candidate flags (workspace)
+    const unsigned char* cflags;  // flag bytes of select_rounds123_kernel (bit 2: in box 2, bit 4: picked) or NULL
     double* ws; size_t ws_stride; int ws_in_smem;
     int b0;                       // first instance of this launch (chunked literal launches)
     int only_marked;              // literal kernel: process only instances the fast kernel marked (n_r4 == -1)

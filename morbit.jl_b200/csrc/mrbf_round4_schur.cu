@@ -30,6 +30,25 @@ namespace mrbf {
 
 __host__ __device__ inline int schur_tiles(int TR) { return (TR * (TR + 1)) / 2; }
 
+// split-phase barrier (mbarrier in shared memory): arrive does not block, wait spins on the phase parity
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_drop(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
 SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     SchurGeom g{};
     const int pl = p > 0 ? p : 1;
@@ -45,8 +64,8 @@ SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     g.sm_C = 0; g.sm_V = (size_t)pl * g.MC;
     g.sm_Xc = cv; g.sm_X0 = g.sm_Xc + (size_t)n * g.MC;
     g.sm_M0 = up4(g.sm_X0 + (size_t)pl * n); g.sm_P00 = up4(g.sm_M0 + (size_t)pl * pl);
-    g.sm_col = up4(g.sm_P00 + (size_t)pl * pl);                         // colA[2][MC], colW[2][MC], pivot values[2][4]
-    g.sm_red = g.sm_col + (size_t)4 * g.MC + 8;
+    g.sm_col = up4(g.sm_P00 + (size_t)pl * pl);                         // ring[3] of { colA, colAs, colW, colWs : [4][MC] }, then info[3][24]
+    g.sm_red = g.sm_col + (size_t)48 * g.MC + 3 * 24;
     g.sm_int = g.sm_red + 80;                                           // clist[MC] ints, wcnt[32] ints, flags[db_stride] bytes
     const size_t ints = (size_t)g.MC + 32 + ((size_t)db_stride + 3) / 4 + 4;
     g.smem_doubles = g.sm_int + (ints + 1) / 2;
@@ -61,10 +80,10 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = poly_dim(n, P.cfg.polynomial_degree), pl = p;
-    const int MC = g.MC, TR = g.TR, MQ = MC >> 2;
+    const int MC = g.MC;
     double* Cs = smem + g.sm_C; double* Vs = smem + g.sm_V; double* Xc = smem + g.sm_Xc; double* X0 = smem + g.sm_X0;
     double* M0 = smem + g.sm_M0; double* P00 = smem + g.sm_P00;
-    double* colA = smem + g.sm_col; double* colW = colA + 2 * MC; double* diag = colW + 2 * MC;
+    double* ring = smem + g.sm_col; double* info = ring + 48 * MC;
     double* red = smem + g.sm_red;
     int* clist = reinterpret_cast<int*>(smem + g.sm_int); int* wcnt = clist + MC;
     unsigned char* cflag = reinterpret_cast<unsigned char*>(wcnt + 32);
@@ -86,11 +105,20 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     if (!(N0 < max_points)) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
     if (N0 != p || n_db > MC) { if (tid == 0) P.n_r4[b] = -1; return; }      // literal kernel takes over
 
-    // ---- candidates: results_in_box_indices(db, lb_2, ub_2, found) in ascending id order (RbfModel.jl:360)
-    for (int id = tid; id < n_db; id += nt) {
-        bool ok = in_box_pt(sites + (size_t)id * n, lb2, ub2, n);
-        for (int f = 0; f < nf_ids && ok; ++f) ok = (found[f] != id + 1);
-        cflag[id] = ok ? 1 : 0;
+    // ---- candidates: results_in_box_indices(db, lb_2, ub_2, found) in ascending id order (RbfModel.jl:360).  After rounds
+    // 1-3 the box-2 flags and the picked ids are already in the flag bytes of select_rounds123_kernel.
+    if (P.cflags) {
+        const unsigned char* cf = P.cflags + (size_t)b * P.db_stride;
+        for (int id = tid; id < n_db; id += nt) { const unsigned f = cf[id]; cflag[id] = ((f & 2u) && !(f & 4u)) ? 1 : 0; }
+    } else {
+        for (int id = tid; id < n_db; id += nt) cflag[id] = 1;
+        __syncthreads();
+        for (int e = tid; e < n_db * n; e += nt) {
+            const int id = e / n, k = e % n;
+            const double v = sites[e];
+            if (!(lb2[k] <= v && v <= ub2[k])) cflag[id] = 0;
+        }
+        for (int e = tid; e < nf_ids; e += nt) { const int id = found[e] - 1; if (id >= 0 && id < n_db) cflag[id] = 0; }
     }
     for (int e = tid; e < p * n; e += nt) {
         const int i = e / n, k = e % n;
@@ -132,9 +160,10 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     }
     __syncthreads();
     if (mc == 0) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
+    const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
     // candidate sites, coordinate-major (Xc[k][i]); the padding columns repeat the centre (finite, never a pivot)
-    for (int e = tid; e < MC * n; e += nt) {
-        const int i = e / n, k = e % n;
+    for (int e = tid; e < MCa * n; e += nt) {
+        const int i = e % MCa, k = e / MCa;
         Xc[k * MC + i] = (i < mc) ? sites[(size_t)clist[i] * n + k] : X0[k];
     }
     for (int e = tid; e < p * p; e += nt) {
@@ -146,42 +175,66 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
         Qx[i + j * pl] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
-    // ---- Pi_0^{-1} by Gauss-Jordan with partial pivoting on [Pi_0 | I]
-    for (int kk = 0; kk < p; ++kk) {
-        if (warp == 0) {
-            ArgMax mine; mine.v = 0.0; mine.id = -1;
-            for (int i = kk + lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(Aq[i + kk * pl]); c_.id = i; mine = better(mine, c_); }
+    // ---- Pi_0^{-1} by Gauss-Jordan with partial pivoting on [Pi_0 | I], ONE barrier per step: the row swap and the scaling
+    // of the pivot row are folded into the column updates, and warp 0 -- which always owns column kk + 1 -- finds the next
+    // pivot as soon as that column is final, while the other warps are still eliminating.
+    int* pivi = reinterpret_cast<int*>(red + 60);   // [2] pivot rows
+    double* pivr = red + 62;                        // [2] reciprocal pivots
+    if (warp == 0) {
+        ArgMax mine; mine.v = 0.0; mine.id = -1;
+        for (int i = lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(Aq[i]); c_.id = i; mine = better(mine, c_); }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
-                mine = better(mine, t_);
-            }
-            if (!(mine.v > 1e-12)) { if (lane == 0) red[76] = 1.0; }       // Pi_0 (scaled to O(1)) is rank deficient
-            else {
-                const double rp = 1.0 / Aq[mine.id + kk * pl];
-                __syncwarp();
-                for (int c = kk + lane; c < 2 * p; c += 32) {
-                    const double a = Aq[mine.id + c * pl], bq = Aq[kk + c * pl];
-                    Aq[mine.id + c * pl] = bq; Aq[kk + c * pl] = a * rp;
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
+            mine = better(mine, t_);
+        }
+        if (lane == 0) { if (!(mine.v > 1e-12)) red[76] = 1.0; else { pivi[0] = mine.id; pivr[0] = 1.0 / Aq[mine.id]; } }
+    }
+    __syncthreads();
+    for (int kk = 0; kk < p; ++kk) {
+        if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }       // Pi_0 (scaled to O(1)) is rank deficient
+        const int piv = pivi[kk & 1];
+        const double rp = pivr[kk & 1];
+        const double* colk = Aq + kk * pl;          // multipliers: column kk as it was before the swap (nobody writes it)
+        const double dkk = colk[kk];
+        for (int c0 = kk + 1 + 4 * warp; c0 < 2 * p; c0 += 4 * nwarps) {      // a quad of columns per warp, lanes over the rows
+            double* col = Aq + c0 * pl;
+            const int nc = min(4, 2 * p - c0);
+            double a_k[4], pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < nc) { a_k[q] = col[q * pl + kk]; pk[q] = col[q * pl + piv] * rp; }   // scaled pivot-row entries
+            __syncwarp();
+            for (int i = lane; i < p; i += 32) {
+                const double mult = (i == piv) ? dkk : colk[i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q < nc) {
+                    const double old = (i == piv) ? a_k[q] : col[q * pl + i];           // row piv receives row kk (swap)
+                    col[q * pl + i] = (i == kk) ? pk[q] : fma(-mult, pk[q], old);
                 }
             }
-        }
-        __syncthreads();
-        if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
-        for (int c = kk + 1 + warp; c < 2 * p; c += nwarps) {
-            const double pk = Aq[kk + c * pl];
-            for (int i = lane; i < p; i += 32) if (i != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], pk, Aq[i + c * pl]);
+            if (c0 == kk + 1 && kk + 1 < p) {       // warp 0: next pivot from the now final column kk + 1
+                __syncwarp();
+                ArgMax mine; mine.v = 0.0; mine.id = -1;
+                for (int i = kk + 1 + lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(col[i]); c_.id = i; mine = better(mine, c_); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
+                    mine = better(mine, t_);
+                }
+                if (lane == 0) { if (!(mine.v > 1e-12)) red[76] = 1.0; else { pivi[(kk + 1) & 1] = mine.id; pivr[(kk + 1) & 1] = 1.0 / col[mine.id]; } }
+            }
         }
         __syncthreads();
     }
+    if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
     for (int e = tid; e < p * p; e += nt) { const int r = e % p, c = e / p; M0[r + c * pl] = Qx[c + r * pl]; }   // M0 = Pi_0^{-T}
     __syncthreads();                                // Gauss-Jordan scratch is dead from here on
     double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
     if (keep) for (int e = tid; e < p * p; e += nt) keep[g.off_M0 + e] = M0[e];
 
     // ---- panels: C = Pi_0^{-T} pi~ (Lagrange coefficients) and B = Phi(S0, candidates), one (row, 4 candidates) task per thread
-    for (int t = tid; t < p * MQ; t += nt) {
-        const int r = t / MQ, i4 = (t % MQ) * 4;
+    for (int t = tid; t < p * TRa; t += nt) {
+        const int r = t / TRa, i4 = (t % TRa) * 4;
         double c0 = M0[r], c1 = c0, c2 = c0, c3 = c0;            // pi~[0] = 1
         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
         for (int k = 0; k < n; ++k) {
@@ -201,8 +254,8 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     }
     __syncthreads();
     // ---- U = B - Phi00 C (kept for the build), V = B - Phi00 C / 2 (in place of B)
-    for (int t = tid; t < p * MQ; t += nt) {
-        const int r = t / MQ, i4 = (t % MQ) * 4;
+    for (int t = tid; t < p * TRa; t += nt) {
+        const int r = t / TRa, i4 = (t % TRa) * 4;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         for (int c = 0; c < p; ++c) {
             const double pv = P00[r + c * pl];
@@ -213,16 +266,23 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
         if (keep) *reinterpret_cast<double4*>(keep + g.off_U + r * MC + i4) = make_double4(bb.x - s0, bb.y - s1, bb.z - s2, bb.w - s3);
         *reinterpret_cast<double4*>(Vs + r * MC + i4) = make_double4(fma(-0.5, s0, bb.x), fma(-0.5, s1, bb.y), fma(-0.5, s2, bb.z), fma(-0.5, s3, bb.w));
     }
+    // split-phase barriers of the elimination, one pair per slot of the three-deep ring of pivot blocks:
+    //   barD: the diagonal tile of the block has been factorised (one arrival), barP: the whole pivot panel is published
+    //   (one arrival per warp that is still alive).
+    unsigned long long* barD = reinterpret_cast<unsigned long long*>(red + 64);      // [3]
+    unsigned long long* barP = barD + 3;                                             // [3]
+    if (tid == 0) for (int q = 0; q < 3; ++q) { mbar_init(&barD[q], 1); mbar_init(&barP[q], nwarps); }
     __syncthreads();
 
     // ---- tiles: thread t owns tile (I, K), I >= K, of A and of W.  Tiles are numbered column by column from the LAST tile
     // column, so the tiles that are still live at pivot j (K >= j / 4) are always a prefix of the thread block.
     int tI = 0, tK = 0;
-    const bool has_tile = tid < g.ntiles;
+    const int ntl = schur_tiles(TRa);
+    const bool has_tile = tid < ntl;
     if (has_tile) {
-        int s = 0;
-        while (((s + 1) * (s + 2)) / 2 <= tid) ++s;
-        tK = TR - 1 - s; tI = tK + (tid - (s * (s + 1)) / 2);
+        int s_ = 0;
+        while (((s_ + 1) * (s_ + 2)) / 2 <= tid) ++s_;
+        tK = TRa - 1 - s_; tI = tK + (tid - (s_ * (s_ + 1)) / 2);
     }
     double A[4][4], W[4][4];
     if (has_tile) {
@@ -260,81 +320,128 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
                 }
         }
     }
-    // Publishing pivot column jn: the owners of tile column jn / 4 write their entries below the diagonal (zeros above, so
-    // the rank-1 update needs no masks); the owner of the diagonal entry also publishes d^2, 1 + lev and their reciprocal
-    // roots -- the only divisions of the step, done by ONE thread instead of by the whole block.
-    //   pv[0] = d^2, pv[1] = 1 + lev, pv[2] = 1 / d, pv[3] = 1 / (1 + lev)
-    double* pvs = diag;                             // 2 x 4 doubles
-#define SCHUR_PUBLISH(SLOT, JN, CN)                                                                              \
-    {                                                                                                            \
-        double* na_ = colA + (SLOT) * MC; double* nw_ = colW + (SLOT) * MC;                                      \
-        _Pragma("unroll") for (int a = 0; a < 4; ++a) {                                                          \
-            const int i = 4 * tI + a;                                                                            \
-            na_[i] = (i > (JN)) ? A[a][CN] : 0.0; nw_[i] = (i > (JN)) ? W[a][CN] : 0.0;                           \
-            if (i == (JN)) {                                                                                     \
-                const double da_ = A[a][CN], dw_ = W[a][CN];                                                     \
-                pvs[4 * (SLOT) + 0] = da_; pvs[4 * (SLOT) + 1] = dw_;                                            \
-                pvs[4 * (SLOT) + 2] = rsqrt(da_); pvs[4 * (SLOT) + 3] = 1.0 / dw_;                                \
-            }                                                                                                    \
-        }                                                                                                        \
-    }
-    if (has_tile && tK == 0) SCHUR_PUBLISH(0, 0, 0)
-    __syncthreads();
-
-    // ---- elimination over the candidates in ascending id order
+    // ---- blocked right-looking elimination over the candidates in ascending id order, four pivots (one tile column) per block.
+    //   1. the thread that owns the diagonal tile (K, K) runs the four pivot tests and eliminations inside its registers
+    //      (RbfModel.jl:447-452; a rejected pivot gets a zero multiplier, so nothing downstream branches on it) -> barD
+    //   2. the other tiles of tile column K finish their four pivot columns against the diagonal tile's multipliers, publish
+    //      them (raw and scaled by 1/d^2) and stream the Cholesky factor rows out for mrbf_build_prepared_dev        -> barP
+    //   3. every tile to the right applies the rank-4 update.  Tile column K + 1 sits in the lowest live thread ids and its
+    //      diagonal tile starts step 1 of the next block as soon as its own update is done; warps without live tiles leave.
     const double thr = P.chol_thr;
-    int nacc = 0;
-    bool full = false;
-    for (int j0 = 0; j0 < mc && !full; j0 += 4) {
-        const int Kj = j0 >> 2;
-        const int live = schur_tiles(TR - Kj);       // tiles with K >= Kj
+    const int cap = min(max_points - N0, P.r4_stride);       // RbfModel.jl:402
+    int nacc = 0, nacc_diag = -1;
+    const int my_last = __shfl_sync(0xffffffffu, has_tile ? tK : -1, 0);             // lane 0 holds this warp's largest tile column
+    for (int K = 0; K < TRa; ++K) {
+        const int slot = K % 3;
+        const unsigned par = (unsigned)((K / 3) & 1);
+        const int j0 = 4 * K;
+        double* cA = ring + (size_t)slot * 16 * MC; double* cAs = cA + 4 * MC; double* cW = cAs + 4 * MC; double* cWs = cW + 4 * MC;
+        double* inf = info + slot * 24;              // [0..3] 1/d, [4..7] 1/d^2 (0 if rejected), [8..11] 1/(1+lev) (0 if rejected), [12] mask, [13] stop
+        if (has_tile && tK == K && tI == K) {        // ---- 1. diagonal tile
+            int mask = 0, na = nacc;
+            double rdv[4], rav[4], rwv[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = j0 + jj;
-            if (j >= mc || full) break;
-            const int cur = jj & 1, nxt = cur ^ 1;
-            const double dA = pvs[4 * cur], rw = pvs[4 * cur + 3];
-            const double tau2 = dA * rw;            // d^2 / (1 + lev) == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
-            if (tau2 > thr) {                        // RbfModel.jl:452
-                const double* ca = colA + cur * MC; const double* cw = colW + cur * MC;
-                const double rd = pvs[4 * cur + 2];
-                if (tid < live) {
-                    const double ra = rd * rd;
-                    {
-                        const double4 i4 = *reinterpret_cast<const double4*>(ca + 4 * tI), k4 = *reinterpret_cast<const double4*>(ca + 4 * tK);
-                        const double ai[4] = {i4.x * ra, i4.y * ra, i4.z * ra, i4.w * ra}, ak[4] = {k4.x, k4.y, k4.z, k4.w};
+            for (int q = 0; q < 4; ++q) {
+                const double dA = A[q][q], dW = W[q][q];
+                const double rw = 1.0 / dW;
+                const bool ok = (j0 + q < mc) && (na < cap) && (dA * rw > thr);      // d^2 / (1 + lev) == sigma - ||L^-1 v||^2
+                const double rd = ok ? rsqrt(dA) : 0.0;
+                rdv[q] = rd; rav[q] = rd * rd; rwv[q] = ok ? rw : 0.0;
+                if (ok) { mask |= 1 << q; na += 1; }
 #pragma unroll
-                        for (int a = 0; a < 4; ++a)
+                for (int r = q + 1; r < 4; ++r)
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) A[a][c] = fma(-ai[a], ak[c], A[a][c]);
+                    for (int c = q + 1; c <= r; ++c) {
+                        A[r][c] = fma(-A[r][q] * rav[q], A[c][q], A[r][c]);
+                        W[r][c] = fma(-W[r][q] * rwv[q], W[c][q], W[r][c]);
                     }
-                    {
-                        const double4 i4 = *reinterpret_cast<const double4*>(cw + 4 * tI), k4 = *reinterpret_cast<const double4*>(cw + 4 * tK);
-                        const double wi[4] = {i4.x * rw, i4.y * rw, i4.z * rw, i4.w * rw}, wk[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) W[a][c] = fma(-wi[a], wk[c], W[a][c]);
-                    }
-                }
-                if (keep) {                          // column nacc of the Cholesky factor of A: pivot column / d, d on the diagonal
-                    double* Lc = keep + g.off_L + (size_t)nacc * MC;
-                    for (int i = j + tid; i < mc; i += nt) Lc[i] = (i == j) ? dA * rd : ca[i] * rd;
-                    if (tid == 0) keep[g.off_acc + nacc] = (double)j;
-                }
-                if (tid == 0) r4[nacc] = clist[j] + 1;
-                nacc += 1;
-                full = !(N0 + nacc < max_points) || !(nacc < P.r4_stride);       // RbfModel.jl:402
             }
-            // publish pivot column j + 1 (final after this update): owners are the tiles of tile column (j + 1) / 4
-            if (j + 1 < mc && !full) {
-                const int cn = (jj + 1) & 3, Kn = (jj == 3) ? Kj + 1 : Kj;
-                if (has_tile && tK == Kn) SCHUR_PUBLISH(nxt, j + 1, cn)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                inf[q] = rdv[q]; inf[4 + q] = rav[q]; inf[8 + q] = rwv[q];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double va = (r > q) ? A[r][q] : 0.0, vw = (r > q) ? W[r][q] : 0.0;
+                    cA[q * MC + j0 + r] = va; cAs[q * MC + j0 + r] = va * rav[q];
+                    cW[q * MC + j0 + r] = vw; cWs[q * MC + j0 + r] = vw * rwv[q];
+                }
             }
-            __syncthreads();
+            inf[12] = (double)mask; inf[13] = (na >= cap || j0 + 4 >= mc) ? 1.0 : 0.0;
+            nacc_diag = na;
+            mbar_arrive(&barD[slot]);
+            int q_out = nacc;                       // ids, positions and the diagonal block of the Cholesky factor
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (mask & (1 << q)) {
+                r4[q_out] = clist[j0 + q] + 1;
+                if (keep) {
+                    keep[g.off_acc + q_out] = (double)(j0 + q);
+                    double* Lc = keep + g.off_L + (size_t)q_out * MC + j0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) if (r >= q && j0 + r < mc) Lc[r] = (r == q) ? A[q][q] * rdv[q] : A[r][q] * rdv[q];
+                }
+                q_out += 1;
+            }
+        }
+        if (has_tile && tK == K && tI > K) {         // ---- 2. the rest of the pivot panel
+            mbar_wait(&barD[slot], par);
+            const int mask = (int)inf[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int jj = q + 1; jj < 4; ++jj) {
+                    const double la = cAs[q * MC + j0 + jj], lw = cWs[q * MC + j0 + jj];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { A[a][jj] = fma(-A[a][q], la, A[a][jj]); W[a][jj] = fma(-W[a][q], lw, W[a][jj]); }
+                }
+            int q_out = nacc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double rd = inf[q], ra = inf[4 + q], rw = inf[8 + q];
+                *reinterpret_cast<double4*>(cA + q * MC + 4 * tI) = make_double4(A[0][q], A[1][q], A[2][q], A[3][q]);
+                *reinterpret_cast<double4*>(cAs + q * MC + 4 * tI) = make_double4(A[0][q] * ra, A[1][q] * ra, A[2][q] * ra, A[3][q] * ra);
+                *reinterpret_cast<double4*>(cW + q * MC + 4 * tI) = make_double4(W[0][q], W[1][q], W[2][q], W[3][q]);
+                *reinterpret_cast<double4*>(cWs + q * MC + 4 * tI) = make_double4(W[0][q] * rw, W[1][q] * rw, W[2][q] * rw, W[3][q] * rw);
+                if (mask & (1 << q)) {
+                    if (keep) *reinterpret_cast<double4*>(keep + g.off_L + (size_t)q_out * MC + 4 * tI) =
+                                  make_double4(A[0][q] * rd, A[1][q] * rd, A[2][q] * rd, A[3][q] * rd);
+                    q_out += 1;
+                }
+            }
+        }
+        __syncwarp();
+        const bool leaving = my_last <= K;           // no tile of this warp lies to the right of tile column K
+        if (lane == 0) {
+            if (!leaving) mbar_arrive(&barP[slot]);
+            else { mbar_arrive_drop(&barP[slot]); mbar_arrive_drop(&barP[(slot + 1) % 3]); mbar_arrive_drop(&barP[(slot + 2) % 3]); }
+        }
+        if (leaving) break;
+        mbar_wait(&barP[slot], par);
+        nacc += __popc((unsigned)(int)inf[12]);
+        if (inf[13] != 0.0) break;                   // capacity reached (RbfModel.jl:402) or no candidates left
+        if (has_tile && tK > K) {                    // ---- 3. rank-4 update
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                {
+                    const double4 i4 = *reinterpret_cast<const double4*>(cAs + q * MC + 4 * tI), k4 = *reinterpret_cast<const double4*>(cA + q * MC + 4 * tK);
+                    const double ai[4] = {i4.x, i4.y, i4.z, i4.w}, ak[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) A[a][c] = fma(-ai[a], ak[c], A[a][c]);
+                }
+                {
+                    const double4 i4 = *reinterpret_cast<const double4*>(cWs + q * MC + 4 * tI), k4 = *reinterpret_cast<const double4*>(cW + q * MC + 4 * tK);
+                    const double wi[4] = {i4.x, i4.y, i4.z, i4.w}, wk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) W[a][c] = fma(-wi[a], wk[c], W[a][c]);
+                }
+            }
         }
     }
-#undef SCHUR_PUBLISH
+    // thread 0 owns the last diagonal tile: it is alive until the end and has seen every accepted pivot
+    if (nacc_diag >= 0) nacc = nacc_diag;
     if (tid == 0) {
         P.n_r4[b] = nacc; if (P.status) P.status[b] = 0;
         if (keep) {
