@@ -38,6 +38,28 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
+// Row index (lo <= i < hi) of the entry of largest magnitude in col[], -1 if none exceeds 1e-12.  One warp; the magnitudes
+// are compared as integers (IEEE doubles order like their bit patterns) with redux.sync when the range fits a warp.
+__device__ __forceinline__ int warp_argmax_abs(const double* col, int lo, int hi, int lane) {
+    if (hi - lo <= 32) {
+        const int i = lo + lane;
+        const double v = (i < hi) ? fabs(col[i]) : 0.0;
+        const unsigned vh = (unsigned)__double2hiint(v), vl = (unsigned)__double2loint(v);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, vh);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
+        const unsigned win = __ballot_sync(0xffffffffu, vh == mh && vl == ml);
+        const double mv = __hiloint2double((int)mh, (int)ml);
+        return (mv > 1e-12) ? lo + (__ffs(win) - 1) : -1;
+    }
+    ArgMax mine; mine.v = 0.0; mine.id = -1;
+    for (int i = lo + lane; i < hi; i += 32) { ArgMax c_; c_.v = fabs(col[i]); c_.id = i; mine = better(mine, c_); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
+        mine = better(mine, t_);
+    }
+    return (mine.v > 1e-12) ? mine.id : -1;
+}
 __device__ __forceinline__ void mbar_arrive_drop(unsigned long long* bar) {
     asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
@@ -181,14 +203,8 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     int* pivi = reinterpret_cast<int*>(red + 60);   // [2] pivot rows
     double* pivr = red + 62;                        // [2] reciprocal pivots
     if (warp == 0) {
-        ArgMax mine; mine.v = 0.0; mine.id = -1;
-        for (int i = lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(Aq[i]); c_.id = i; mine = better(mine, c_); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
-            mine = better(mine, t_);
-        }
-        if (lane == 0) { if (!(mine.v > 1e-12)) red[76] = 1.0; else { pivi[0] = mine.id; pivr[0] = 1.0 / Aq[mine.id]; } }
+        const int pv_ = warp_argmax_abs(Aq, 0, p, lane);
+        if (lane == 0) { if (pv_ < 0) red[76] = 1.0; else { pivi[0] = pv_; pivr[0] = 1.0 / Aq[pv_]; } }
     }
     __syncthreads();
     for (int kk = 0; kk < p; ++kk) {
@@ -197,9 +213,11 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
         const double rp = pivr[kk & 1];
         const double* colk = Aq + kk * pl;          // multipliers: column kk as it was before the swap (nobody writes it)
         const double dkk = colk[kk];
-        for (int c0 = kk + 1 + 4 * warp; c0 < 2 * p; c0 += 4 * nwarps) {      // a quad of columns per warp, lanes over the rows
-            double* col = Aq + c0 * pl;
-            const int nc = min(4, 2 * p - c0);
+        // warp 0 takes column kk + 1 alone, then finds the next pivot and its reciprocal; warps 1.. take quads of the other columns
+        const int ncols = 2 * p - (kk + 1);
+        for (int q0 = (warp == 0) ? 0 : 1 + 4 * (warp - 1); q0 < ncols; q0 += 4 * (nwarps - 1)) {
+            double* col = Aq + (kk + 1 + q0) * pl;
+            const int nc = (warp == 0) ? 1 : min(4, ncols - q0);
             double a_k[4], pk[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (q < nc) { a_k[q] = col[q * pl + kk]; pk[q] = col[q * pl + piv] * rp; }   // scaled pivot-row entries
@@ -212,17 +230,12 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
                     col[q * pl + i] = (i == kk) ? pk[q] : fma(-mult, pk[q], old);
                 }
             }
-            if (c0 == kk + 1 && kk + 1 < p) {       // warp 0: next pivot from the now final column kk + 1
+            if (warp == 0 && q0 == 0 && kk + 1 < p) {
                 __syncwarp();
-                ArgMax mine; mine.v = 0.0; mine.id = -1;
-                for (int i = kk + 1 + lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(col[i]); c_.id = i; mine = better(mine, c_); }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
-                    mine = better(mine, t_);
-                }
-                if (lane == 0) { if (!(mine.v > 1e-12)) red[76] = 1.0; else { pivi[(kk + 1) & 1] = mine.id; pivr[(kk + 1) & 1] = 1.0 / col[mine.id]; } }
+                const int pv_ = warp_argmax_abs(col, kk + 1, p, lane);
+                if (lane == 0) { if (pv_ < 0) red[76] = 1.0; else { pivi[(kk + 1) & 1] = pv_; pivr[(kk + 1) & 1] = 1.0 / col[pv_]; } }
             }
+            if (warp == 0) break;                   // the remaining columns belong to the other warps
         }
         __syncthreads();
     }
@@ -343,9 +356,9 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double dA = A[q][q], dW = W[q][q];
-                const double rw = 1.0 / dW;
+                const double rw = 1.0 / dW, rs = rsqrt(dA);                           // independent: their latencies overlap
                 const bool ok = (j0 + q < mc) && (na < cap) && (dA * rw > thr);      // d^2 / (1 + lev) == sigma - ||L^-1 v||^2
-                const double rd = ok ? rsqrt(dA) : 0.0;
+                const double rd = ok ? rs : 0.0;
                 rdv[q] = rd; rav[q] = rd * rd; rwv[q] = ok ? rw : 0.0;
                 if (ok) { mask |= 1 << q; na += 1; }
 #pragma unroll
