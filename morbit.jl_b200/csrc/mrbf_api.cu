@@ -351,19 +351,21 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     S.r1 = r1; S.n_r1 = n_r1; S.r2 = r2; S.n_r2 = n_r2; S.r3_sites = r3_sites; S.n_r3 = n_r3; S.dirs = dirs; S.n_dirs = n_dirs;
     S.flags_out = flags_out;
     const int ldz = n | 1;
-    S.wz_in_smem = select_smem_bytes(n, true, 0) <= SMEM_LIMIT;
-    // shifted seeds + projections (2 x n x db_stride doubles) stay in shared memory when two CTAs still fit per SM
-    const int st_doubles = 2 * n * db_stride;
-    S.st_in_smem = S.wz_in_smem && select_smem_bytes(n, true, st_doubles) <= 110 * 1024;
-    const size_t seeds = S.st_in_smem ? 16 : (size_t)B * db_stride * n * sizeof(double);
-    ENSURE(ctx->ws[0], seeds); ENSURE(ctx->ws[1], seeds); ENSURE(ctx->ws[2], (size_t)B * db_stride);
+    S.wz_in_smem = select_smem_bytes(n, true, 0, db_stride) <= SMEM_LIMIT;
+    // projection coefficients (n x ldS doubles, ldS = db_stride rounded up to even) stay in shared memory when three CTAs
+    // still fit per SM; the shifted seeds always live in the global workspace
+    const int ldS = (db_stride + 1) & ~1;
+    const int st_doubles = n * ldS;
+    S.st_in_smem = S.wz_in_smem && select_smem_bytes(n, true, st_doubles, db_stride) <= 74 * 1024;
+    const size_t seeds = (size_t)B * ldS * n * sizeof(double);
+    ENSURE(ctx->ws[0], seeds); ENSURE(ctx->ws[1], S.st_in_smem ? 16 : seeds); ENSURE(ctx->ws[2], (size_t)B * db_stride);
     S.S = (double*)ctx->ws[0].p; S.T = (double*)ctx->ws[1].p; S.cflags = (unsigned char*)ctx->ws[2].p;
     if (!S.wz_in_smem) { ENSURE(ctx->ws[3], (size_t)B * 2 * n * ldz * sizeof(double)); S.WZ = (double*)ctx->ws[3].p; }
     ENSURE(ctx->ws[4], (size_t)B * n * 2 * sizeof(double));
     S.lb2 = (double*)ctx->ws[4].p; S.ub2 = S.lb2 + (size_t)B * n;
     ENSURE(ctx->ws[5], ((size_t)B * S.found_stride + B) * sizeof(int));
     S.found = (int*)ctx->ws[5].p; S.n_found = S.found + (size_t)B * S.found_stride;
-    { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem, S.st_in_smem ? st_doubles : 0), ctx->stream)); }
+    { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem, S.st_in_smem ? st_doubles : 0, db_stride), ctx->stream)); }
     ctx->launches += 1;
     if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
         rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,

@@ -117,7 +117,7 @@ struct BacktrackParams {
     int* step_index; double* sigma; double* x_plus; double* mx; double* mx_plus;
 };
 
-size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles);
+size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride);
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
 size_t round4_fast_vec_doubles(int n, int NM, int p);

@@ -63,6 +63,7 @@ struct FilterState {
     double* vv;       // n   scratch: reflector
     double* red;      // 80 doubles reduction scratch
     int* redi;        // 40 ints
+    int* cl;          // db_stride ints: compacted candidate list of the current run
     int jY;           // columns of Y so far
 };
 
@@ -73,51 +74,71 @@ struct FilterState {
 
 // One run of the affinely-independent filter over the candidates with (cflags & want) == want and
 // !(cflags & (CF_USED | avoid)).  Picks are appended to out[]; returns their number.
+//
+// The candidates of the run are compacted into a dense list cl[] (ascending ids, so "first maximiser" = smallest position).
+// T holds, per list position, the projection coefficients y = W' s on the current trailing block W (coordinate-major).
+// They are updated with the same reflector that updates W (O(n-j) per candidate and step) instead of being recomputed
+// (O(n (n-j))), and the scores || Z (Z' s) ||_inf = || (W D^-2) y ||_inf  (D = column inf-norms of W, AffinelyIndependentPoints.jl:8)
+// of all candidates are one small GEMM per step, register-tiled 4 rows x 4 candidates per thread.
 __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* shifted seeds, coordinate-major: S[i*ldS + id] */, double* T,
                           int ldS, unsigned char* cflags, int n_db, unsigned want, unsigned avoid, double piv, int n_wanted, int* out) {
-    // T holds, per candidate, the projection coefficients y = W' s on the current trailing block W (coordinate-major like S).
-    // They are updated with the same reflector that updates W (O(n-j) per candidate and step) instead of being recomputed
-    // (O(n (n-j))), and the score || Z (Z' s) ||_inf is evaluated as || W (y ./ d^2) ||_inf with d the column inf-norms of W.
-    const int n = st.n, ldz = st.ldz, tid = threadIdx.x, nt = blockDim.x;
-    const int G = (n_db > 128) ? 1 : ((n_db > 64) ? 2 : ((n_db > 32) ? 4 : 8));
-    const int cpp = nt / G;
-    double* invd2 = st.u;
+    const int n = st.n, ldz = st.ldz, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int* cl = st.cl;
+    double* Wt = st.Z;                            // W D^-2 while the run lasts; the real Z is written at the end
     int found = 0;
+    // ---- compact candidate list (one warp; n_db is small)
+    if (warp == 0) {
+        int base = 0;
+        for (int i0 = 0; i0 < n_db; i0 += 32) {
+            const int id = i0 + lane;
+            bool act = false;
+            if (id < n_db) { const unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
+            const unsigned msk = __ballot_sync(0xffffffffu, act);
+            if (act) cl[base + __popc(msk & ((1u << lane) - 1u))] = id;
+            base += __popc(msk);
+        }
+        if (lane == 0) st.redi[36] = base;
+    }
+    __syncthreads();
+    const int nc = st.redi[36];
+    if (nc == 0) return 0;
     // ---- y = W' s for every candidate of this run, and the first pick: argmax ||s||_inf, first maximiser, unconditional
     ArgMax mine; mine.v = 0.0; mine.id = -1;
     {
         const int nw0 = n - st.jY;
-        for (int c0 = 0; c0 < n_db; c0 += cpp) {
-            const int id = c0 + tid / G, h = tid % G;
-            bool act = false;
-            if (id < n_db) { unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
-            if (!act) continue;
-            const double* s = S + id;
+        const int G = (nc > 128) ? 1 : ((nc > 64) ? 2 : ((nc > 32) ? 4 : 8));
+        const int cpp = nt / G;
+        for (int c0 = 0; c0 < nc; c0 += cpp) {
+            const int pos = c0 + tid / G, h = tid % G;
+            if (pos >= nc) continue;
+            const double* s = S + cl[pos];
             for (int c = h; c < nw0; c += G) {
                 const double* wc = st.W + c * ldz;
-                double a = 0.0;
-                for (int i = 0; i < n; ++i) a = fma(wc[i], s[i * ldS], a);
-                T[c * ldS + id] = a;
+                double a0 = 0.0, a1 = 0.0;
+                int i = 0;
+                for (; i + 1 < n; i += 2) { a0 = fma(wc[i], s[i * ldS], a0); a1 = fma(wc[i + 1], s[(i + 1) * ldS], a1); }
+                if (i < n) a0 = fma(wc[i], s[i * ldS], a0);
+                T[c * ldS + pos] = a0 + a1;
             }
             if (h == 0) {
                 double v = 0.0;
                 for (int i = 0; i < n; ++i) v = fmax(v, fabs(s[i * ldS]));
-                ArgMax c_; c_.v = v; c_.id = id;
+                ArgMax c_; c_.v = v; c_.id = pos;
                 mine = better(mine, c_);
             }
         }
     }
     ArgMax best = block_argmax(mine, st.red, st.redi);
-    if (best.id < 0) return 0;
+    const int RQ = (n + 3) >> 2;                  // row quads of the scoring GEMM
+    int RQ2 = 1; while (RQ2 < RQ && RQ2 < 32) RQ2 <<= 1;
     for (;;) {
-        // ---- accept best.id: Y <- [Y s]; its projection on W is already in T
+        // ---- accept position best.id: Y <- [Y s]; its projection on W is already in T.  dlarfg on that column, one warp.
         const int nw = n - st.jY;                 // columns of W before the update
-        for (int c = tid; c < nw; c += nt) st.xp[c] = T[c * ldS + best.id];
-        __syncthreads();
-        if (tid < 32) {                           // dlarfg on xp[0..nw), one warp
-            const double alpha = st.xp[0];
+        const int bpos = best.id;
+        if (warp == 0) {
             double ss = 0.0;
-            for (int c = 1 + tid; c < nw; c += 32) ss = fma(st.xp[c], st.xp[c], ss);
+            for (int c = 1 + lane; c < nw; c += 32) { const double x_ = T[c * ldS + bpos]; ss = fma(x_, x_, ss); }
+            const double alpha = T[bpos];
             const double xnorm = sqrt(warp_sum(ss));
             double tau = 0.0, sc = 0.0;
             if (xnorm != 0.0) {
@@ -125,69 +146,103 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
                 tau = (beta - alpha) / beta;
                 sc = 1.0 / (alpha - beta);
             }
-            for (int c = 1 + tid; c < nw; c += 32) st.vv[c] = st.xp[c] * sc;
-            if (tid == 0) {
+            for (int c = 1 + lane; c < nw; c += 32) st.vv[c] = T[c * ldS + bpos] * sc;
+            if (lane == 0) {
                 st.vv[0] = 1.0;
                 st.red[70] = tau;
-                cflags[best.id] |= CF_USED;
-                out[found] = best.id + 1;
+                const int id = cl[bpos];
+                cflags[id] |= CF_USED;
+                out[found] = id + 1;
+                cl[bpos] = ~id;                   // stays in the list (its column of T is dead) but never wins again
             }
         }
         __syncthreads();
         const double tau = st.red[70];
-        for (int i = tid; i < n; i += nt) {       // u = W v ; then W'[:, c-1] = W[:, c] - tau v_c u  (row-private)
-            double a = 0.0;
-            for (int c = 0; c < nw; ++c) a = fma(st.W[i + c * ldz], st.vv[c], a);
-            a *= tau;
-            for (int c = 1; c < nw; ++c) st.W[i + (c - 1) * ldz] = fma(-a, st.vv[c], st.W[i + c * ldz]);
-        }
-        for (int id = tid; id < n_db; id += nt) { // same reflector on the candidates' coefficients: y' = (y - tau v (v.y))[1:]
-            unsigned f = cflags[id];
-            if ((f & want) != want || (f & (CF_USED | avoid))) continue;
-            double* y = T + id;
-            double a = 0.0;
-            for (int c = 0; c < nw; ++c) a = fma(st.vv[c], y[c * ldS], a);
-            a *= tau;
-            for (int c = 1; c < nw; ++c) y[(c - 1) * ldS] = fma(-a, st.vv[c], y[c * ldS]);
+        // ---- the reflector on W (row-private) and on the candidates' coefficients (position-private); 4 partial sums each
+        for (int w = tid; w < n + nc; w += nt) {
+            if (w < n) {                          // u = W v ; W'[:, c-1] = W[:, c] - tau u v_c
+                const double* wr = st.W + w;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int c = 0;
+                for (; c + 3 < nw; c += 4) {
+                    a0 = fma(wr[c * ldz], st.vv[c], a0); a1 = fma(wr[(c + 1) * ldz], st.vv[c + 1], a1);
+                    a2 = fma(wr[(c + 2) * ldz], st.vv[c + 2], a2); a3 = fma(wr[(c + 3) * ldz], st.vv[c + 3], a3);
+                }
+                for (; c < nw; ++c) a0 = fma(wr[c * ldz], st.vv[c], a0);
+                const double a = ((a0 + a1) + (a2 + a3)) * tau;
+                double* ww = st.W + w;
+                for (c = 1; c < nw; ++c) ww[(c - 1) * ldz] = fma(-a, st.vv[c], ww[c * ldz]);
+            } else {                              // y' = (y - tau v (v.y))[1:]
+                double* y = T + (w - n);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int c = 0;
+                for (; c + 3 < nw; c += 4) {
+                    a0 = fma(st.vv[c], y[c * ldS], a0); a1 = fma(st.vv[c + 1], y[(c + 1) * ldS], a1);
+                    a2 = fma(st.vv[c + 2], y[(c + 2) * ldS], a2); a3 = fma(st.vv[c + 3], y[(c + 3) * ldS], a3);
+                }
+                for (; c < nw; ++c) a0 = fma(st.vv[c], y[c * ldS], a0);
+                const double a = ((a0 + a1) + (a2 + a3)) * tau;
+                for (c = 1; c < nw; ++c) y[(c - 1) * ldS] = fma(-a, st.vv[c], y[c * ldS]);
+            }
         }
         st.jY += 1;
         found += 1;
         __syncthreads();
         const int zc = n - st.jY;
         if (found == n_wanted) break;
-        for (int c = tid; c < zc; c += nt) {      // d_c = ||W[:, c]||_inf  (AffinelyIndependentPoints.jl:8)
+        // ---- Wt = W D^-2, D = column inf-norms of W (AffinelyIndependentPoints.jl:8): one warp per column
+        for (int c = warp; c < zc; c += nwarps) {
             const double* wc = st.W + c * ldz;
             double mx = 0.0;
-            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(wc[i]));
-            invd2[c] = 1.0 / (mx * mx);
+            for (int i = lane; i < n; i += 32) mx = fmax(mx, fabs(wc[i]));
+            mx = warp_max(mx);
+            const double r = 1.0 / (mx * mx);
+            for (int i = lane; i < n; i += 32) Wt[c * ldz + i] = wc[i] * r;
         }
         __syncthreads();
-        // ---- score the remaining candidates: || Z (Z' s) ||_inf = || W (y ./ d^2) ||_inf, strict '>' => first maximiser
+        // ---- scores: thread = (row quad rq, candidate quad cq); acc[4 rows][4 candidates] += Wt[rows, q] * y[q, candidates]
         mine.v = 0.0; mine.id = -1;
-        for (int c0 = 0; c0 < n_db; c0 += cpp) {
-            const int id = c0 + tid / G, h = tid % G;
-            bool act = false;
-            if (id < n_db) { unsigned f = cflags[id]; act = ((f & want) == want) && !(f & (CF_USED | avoid)); }
-            const double* y = T + id;
-            double v = 0.0;
-            if (act) {
-                int i = h;
-                for (; i + 3 * G < n; i += 4 * G) {
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                    for (int q = 0; q < zc; ++q) {
-                        const double* wq = st.W + q * ldz + i; const double tq = y[q * ldS] * invd2[q];
-                        a0 = fma(wq[0], tq, a0); a1 = fma(wq[G], tq, a1); a2 = fma(wq[2 * G], tq, a2); a3 = fma(wq[3 * G], tq, a3);
+        {
+            const int CQ = (nc + 3) >> 2;
+            const int rq0 = tid % RQ2, cqs = nt / RQ2;
+            for (int cq = tid / RQ2; cq < ((CQ + cqs - 1) / cqs) * cqs; cq += cqs) {
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;       // max |.| over this thread's rows, per candidate of the quad
+                if (cq < CQ)
+                    for (int rq = rq0; rq < RQ; rq += RQ2) {
+                        const int i0 = 4 * rq;
+                        const bool r1 = i0 + 1 < n, r2 = i0 + 2 < n, r3 = i0 + 3 < n;
+                        double acc[4][4];
+#pragma unroll
+                        for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                            for (int c_ = 0; c_ < 4; ++c_) acc[a_][c_] = 0.0;
+                        const double* wp = Wt + i0; const double* yp = T + 4 * cq;
+                        for (int q = 0; q < zc; ++q) {
+                            const double w0 = wp[q * ldz], w1 = r1 ? wp[q * ldz + 1] : 0.0, w2 = r2 ? wp[q * ldz + 2] : 0.0, w3 = r3 ? wp[q * ldz + 3] : 0.0;
+                            const double2 ya = *reinterpret_cast<const double2*>(yp + q * ldS), yb = *reinterpret_cast<const double2*>(yp + q * ldS + 2);
+                            acc[0][0] = fma(w0, ya.x, acc[0][0]); acc[0][1] = fma(w0, ya.y, acc[0][1]); acc[0][2] = fma(w0, yb.x, acc[0][2]); acc[0][3] = fma(w0, yb.y, acc[0][3]);
+                            acc[1][0] = fma(w1, ya.x, acc[1][0]); acc[1][1] = fma(w1, ya.y, acc[1][1]); acc[1][2] = fma(w1, yb.x, acc[1][2]); acc[1][3] = fma(w1, yb.y, acc[1][3]);
+                            acc[2][0] = fma(w2, ya.x, acc[2][0]); acc[2][1] = fma(w2, ya.y, acc[2][1]); acc[2][2] = fma(w2, yb.x, acc[2][2]); acc[2][3] = fma(w2, yb.y, acc[2][3]);
+                            acc[3][0] = fma(w3, ya.x, acc[3][0]); acc[3][1] = fma(w3, ya.y, acc[3][1]); acc[3][2] = fma(w3, yb.x, acc[3][2]); acc[3][3] = fma(w3, yb.y, acc[3][3]);
+                        }
+#pragma unroll
+                        for (int a_ = 0; a_ < 4; ++a_) {
+                            v0 = fmax(v0, fabs(acc[a_][0])); v1 = fmax(v1, fabs(acc[a_][1])); v2 = fmax(v2, fabs(acc[a_][2])); v3 = fmax(v3, fabs(acc[a_][3]));
+                        }
                     }
-                    v = fmax(fmax(v, fabs(a0)), fmax(fabs(a1), fmax(fabs(a2), fabs(a3))));
+                for (int o = RQ2 >> 1; o > 0; o >>= 1) {
+                    v0 = fmax(v0, __shfl_xor_sync(0xffffffffu, v0, o)); v1 = fmax(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                    v2 = fmax(v2, __shfl_xor_sync(0xffffffffu, v2, o)); v3 = fmax(v3, __shfl_xor_sync(0xffffffffu, v3, o));
                 }
-                for (; i < n; i += G) {
-                    double a0 = 0;
-                    for (int q = 0; q < zc; ++q) a0 = fma(st.W[i + q * ldz], y[q * ldS] * invd2[q], a0);
-                    v = fmax(v, fabs(a0));
+                if (rq0 == 0 && cq < CQ) {
+                    const double vs[4] = {v0, v1, v2, v3};
+#pragma unroll
+                    for (int c_ = 0; c_ < 4; ++c_) {
+                        const int pos = 4 * cq + c_;
+                        if (pos < nc && cl[pos] >= 0) { ArgMax cnd; cnd.v = vs[c_]; cnd.id = pos; mine = better(mine, cnd); }
+                    }
                 }
             }
-            for (int o = G >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (act && h == 0) { ArgMax cnd; cnd.v = v; cnd.id = id; mine = better(mine, cnd); }
         }
         best = block_argmax(mine, st.red, st.redi);
         if (best.id < 0) break;                   // no more candidates
@@ -195,20 +250,21 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
     }
     {                                             // Z = W ./ colmax|W| for the caller (improving directions)
         const int zc = n - st.jY;
-        for (int c = tid; c < zc; c += nt) {
+        __syncthreads();
+        for (int c = warp; c < zc; c += nwarps) {
             const double* wc = st.W + c * ldz;
             double mx = 0.0;
-            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(wc[i]));
-            double* zcol = st.Z + c * ldz;
-            for (int i = 0; i < n; ++i) zcol[i] = wc[i] / mx;
+            for (int i = lane; i < n; i += 32) mx = fmax(mx, fabs(wc[i]));
+            mx = warp_max(mx);
+            for (int i = lane; i < n; i += 32) st.Z[c * ldz + i] = wc[i] / mx;
         }
         __syncthreads();
     }
     return found;
 }
 
-template <bool WZS, bool STS>   // W/Z in shared memory; seeds/projections in shared memory (fixes the address space at compile time)
-__global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
+template <bool WZS, bool STS>   // W/Z in shared memory; projections in shared memory (fixes the address space at compile time)
+__global__ void __launch_bounds__(256, 3) select_rounds123_kernel(SelectParams P) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x;
     const int ldz = n | 1;
@@ -218,13 +274,16 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
     double* red = vv + n;                        // 80
     int* redi = (int*)(red + 80);                // 40 ints = 20 doubles
     int* ctl = redi + 40;                        // 8 ints control
-    double* wz = red + 80 + 24;
+    int* cl = ctl + 8;                           // db_stride ints (compacted candidate list)
+    double* wz = red + 80 + 24 + 2 * ((P.db_stride + 3) / 4);
     double* W; double* S; double* T;
-    const int ldS = P.db_stride;
+    const int ldS = (P.db_stride + 1) & ~1;      // even: the scoring tiles read coefficient pairs
     if constexpr (WZS) W = wz; else W = P.WZ + (size_t)b * 2 * n * ldz;
     double* Z = W + n * ldz;
-    if constexpr (STS) { S = wz + 2 * n * ldz; T = S + n * ldS; }                              // coordinate-major seeds
-    else { S = P.S + (size_t)b * P.db_stride * n; T = P.T + (size_t)b * P.db_stride * n; }
+    // shifted seeds (read once per run) stay in the L2-resident global workspace; the projection coefficients T, which every
+    // step reads and updates, live in shared memory when they fit
+    S = P.S + (size_t)b * ldS * n;
+    if constexpr (STS) T = wz + 2 * n * ldz; else T = P.T + (size_t)b * ldS * n;
     const int n_db = P.n_db[b];
     const double* sites = P.sites + (size_t)b * P.db_stride * n;
     unsigned char* cflags = P.cflags + (size_t)b * P.db_stride;
@@ -260,7 +319,7 @@ __global__ void __launch_bounds__(256) select_rounds123_kernel(SelectParams P) {
     bool ensure_fl = P.flags_in[2 * b] != 0;
     bool force_rebuild = P.flags_in[2 * b + 1] != 0;
     bool rebuilt = false;
-    FilterState st; st.n = n; st.ldz = ldz; st.W = W; st.Z = Z; st.xp = xp; st.u = u; st.vv = vv; st.red = red; st.redi = redi;
+    FilterState st; st.n = n; st.ldz = ldz; st.W = W; st.Z = Z; st.xp = xp; st.u = u; st.vv = vv; st.red = red; st.redi = redi; st.cl = cl;
     int n_r1, n_r2, n_r3, n_dirs;
     bool fully_linear;
     for (;;) {   // at most two passes: the second is the coordinate rebuild (RbfModel.jl:634-637)
@@ -1376,8 +1435,8 @@ __global__ void gather_training_kernel(GatherParams P) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles) {
-    size_t d = 8 * (size_t)n + 80 + 24;
+size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride) {
+    size_t d = 8 * (size_t)n + 80 + 24 + 2 * (((size_t)db_stride + 3) / 4);
     if (wz_in_smem) d += 2 * (size_t)n * (n | 1) + (size_t)st_doubles;
     return d * sizeof(double);
 }
