@@ -41,6 +41,7 @@ struct Round4Params {
     int only_marked;              // literal kernel: process only instances the fast kernel marked (n_r4 == -1)
     double* fs; size_t fs_stride; int fs_in_smem;   // fast-path state
     double* keep_fs; int* elig;                     // kept factorisation (mrbf_prepared) or NULL
+    long long* dbg_clock;                           // instrumentation (MRBF_DEBUG_CLOCK): phase time stamps of CTA 0, or NULL
 };
 
 // Geometry of the register-tiled round-4 kernel (mrbf_round4_schur.cu): shared-memory offsets and the layout of the

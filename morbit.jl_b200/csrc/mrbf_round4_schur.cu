@@ -38,6 +38,26 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
+// Reciprocal and reciprocal square root for the sequential pivot chains: hardware seed (about 20 bits) + two Newton steps,
+// accurate to a few ulp -- the full IEEE division / rsqrt sequences cost ~300 cycles of latency per pivot on one thread.
+// Arguments are normal positive numbers here (pivots > 1e-12, d^2 > 1e-28 checked by the caller, 1 + lev >= 1).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5); y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5); y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5); y = fma(y, e, y);
+    return y;
+}
+
 // Row index (lo <= i < hi) of the entry of largest magnitude in col[], -1 if none exceeds 1e-12.  One warp; the magnitudes
 // are compared as integers (IEEE doubles order like their bit patterns) with redux.sync when the range fits a warp.
 __device__ __forceinline__ int warp_argmax_abs(const double* col, int lo, int hi, int lane) {
@@ -112,6 +132,9 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     double* Aq = smem;                 // Gauss-Jordan scratch [Pi_0 | I] (p x 2p), dead before C is written
     double* Qx = Aq + pl * pl;
 
+#define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+#define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+    SCHUR_STAMP(0);
     const int n_db = P.n_db[b];
     const double* sites = P.sites + (size_t)b * P.db_stride * n;
     const double* lb2 = P.lb2 + (size_t)b * n;
@@ -197,6 +220,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
         Qx[i + j * pl] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
+    SCHUR_STAMP(1);
     // ---- Pi_0^{-1} by Gauss-Jordan with partial pivoting on [Pi_0 | I], ONE barrier per step: the row swap and the scaling
     // of the pivot row are folded into the column updates, and warp 0 -- which always owns column kk + 1 -- finds the next
     // pivot as soon as that column is final, while the other warps are still eliminating.
@@ -204,7 +228,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     double* pivr = red + 62;                        // [2] reciprocal pivots
     if (warp == 0) {
         const int pv_ = warp_argmax_abs(Aq, 0, p, lane);
-        if (lane == 0) { if (pv_ < 0) red[76] = 1.0; else { pivi[0] = pv_; pivr[0] = 1.0 / Aq[pv_]; } }
+        if (lane == 0) { if (pv_ < 0) red[76] = 1.0; else { pivi[0] = pv_; pivr[0] = fast_rcp(Aq[pv_]); } }
     }
     __syncthreads();
     for (int kk = 0; kk < p; ++kk) {
@@ -233,7 +257,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
             if (warp == 0 && q0 == 0 && kk + 1 < p) {
                 __syncwarp();
                 const int pv_ = warp_argmax_abs(col, kk + 1, p, lane);
-                if (lane == 0) { if (pv_ < 0) red[76] = 1.0; else { pivi[(kk + 1) & 1] = pv_; pivr[(kk + 1) & 1] = 1.0 / col[pv_]; } }
+                if (lane == 0) { if (pv_ < 0) red[76] = 1.0; else { pivi[(kk + 1) & 1] = pv_; pivr[(kk + 1) & 1] = fast_rcp(col[pv_]); } }
             }
             if (warp == 0) break;                   // the remaining columns belong to the other warps
         }
@@ -245,6 +269,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
     if (keep) for (int e = tid; e < p * p; e += nt) keep[g.off_M0 + e] = M0[e];
 
+    SCHUR_STAMP(2);
     // ---- panels: C = Pi_0^{-T} pi~ (Lagrange coefficients) and B = Phi(S0, candidates), one (row, 4 candidates) task per thread
     for (int t = tid; t < p * TRa; t += nt) {
         const int r = t / TRa, i4 = (t % TRa) * 4;
@@ -287,6 +312,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     if (tid == 0) for (int q = 0; q < 3; ++q) { mbar_init(&barD[q], 1); mbar_init(&barP[q], nwarps); }
     __syncthreads();
 
+    SCHUR_STAMP(3);
     // ---- tiles: thread t owns tile (I, K), I >= K, of A and of W.  Tiles are numbered column by column from the LAST tile
     // column, so the tiles that are still live at pivot j (K >= j / 4) are always a prefix of the thread block.
     int tI = 0, tK = 0;
@@ -333,6 +359,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
                 }
         }
     }
+    SCHUR_STAMP(4);
     // ---- blocked right-looking elimination over the candidates in ascending id order, four pivots (one tile column) per block.
     //   1. the thread that owns the diagonal tile (K, K) runs the four pivot tests and eliminations inside its registers
     //      (RbfModel.jl:447-452; a rejected pivot gets a zero multiplier, so nothing downstream branches on it) -> barD
@@ -350,13 +377,15 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
         const int j0 = 4 * K;
         double* cA = ring + (size_t)slot * 16 * MC; double* cAs = cA + 4 * MC; double* cW = cAs + 4 * MC; double* cWs = cW + 4 * MC;
         double* inf = info + slot * 24;              // [0..3] 1/d, [4..7] 1/d^2 (0 if rejected), [8..11] 1/(1+lev) (0 if rejected), [12] mask, [13] stop
+        if (K < 40) SCHUR_STAMP(8 + 2 * K);
         if (has_tile && tK == K && tI == K) {        // ---- 1. diagonal tile
+            if (K < 25) SCHUR_STAMPX(128 + 8 * K);
             int mask = 0, na = nacc;
             double rdv[4], rav[4], rwv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double dA = A[q][q], dW = W[q][q];
-                const double rw = 1.0 / dW, rs = rsqrt(dA);                           // independent: their latencies overlap
+                const double rw = fast_rcp(dW), rs = fast_rsqrt(fmax(dA, 1e-300));      // independent: their latencies overlap
                 const bool ok = (j0 + q < mc) && (na < cap) && (dA * rw > thr);      // d^2 / (1 + lev) == sigma - ||L^-1 v||^2
                 const double rd = ok ? rs : 0.0;
                 rdv[q] = rd; rav[q] = rd * rd; rwv[q] = ok ? rw : 0.0;
@@ -369,34 +398,28 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
                         W[r][c] = fma(-W[r][q] * rwv[q], W[c][q], W[r][c]);
                     }
             }
+            if (K < 25) SCHUR_STAMPX(128 + 8 * K + 1);
+            *reinterpret_cast<double4*>(inf) = make_double4(rdv[0], rdv[1], rdv[2], rdv[3]);
+            *reinterpret_cast<double4*>(inf + 4) = make_double4(rav[0], rav[1], rav[2], rav[3]);
+            *reinterpret_cast<double4*>(inf + 8) = make_double4(rwv[0], rwv[1], rwv[2], rwv[3]);
+            *reinterpret_cast<double2*>(inf + 12) = make_double2((double)mask, (na >= cap || j0 + 4 >= mc) ? 1.0 : 0.0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                inf[q] = rdv[q]; inf[4 + q] = rav[q]; inf[8 + q] = rwv[q];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const double va = (r > q) ? A[r][q] : 0.0, vw = (r > q) ? W[r][q] : 0.0;
-                    cA[q * MC + j0 + r] = va; cAs[q * MC + j0 + r] = va * rav[q];
-                    cW[q * MC + j0 + r] = vw; cWs[q * MC + j0 + r] = vw * rwv[q];
-                }
+            for (int q = 0; q < 4; ++q) {           // rows j0..j0+3 of the four pivot columns: zeros on and above the diagonal
+                const double a1 = (q < 1) ? A[1][q] : 0.0, a2 = (q < 2) ? A[2][q] : 0.0, a3 = (q < 3) ? A[3][q] : 0.0;
+                const double w1 = (q < 1) ? W[1][q] : 0.0, w2 = (q < 2) ? W[2][q] : 0.0, w3 = (q < 3) ? W[3][q] : 0.0;
+                *reinterpret_cast<double4*>(cA + q * MC + j0) = make_double4(0.0, a1, a2, a3);
+                *reinterpret_cast<double4*>(cAs + q * MC + j0) = make_double4(0.0, a1 * rav[q], a2 * rav[q], a3 * rav[q]);
+                *reinterpret_cast<double4*>(cW + q * MC + j0) = make_double4(0.0, w1, w2, w3);
+                *reinterpret_cast<double4*>(cWs + q * MC + j0) = make_double4(0.0, w1 * rwv[q], w2 * rwv[q], w3 * rwv[q]);
             }
-            inf[12] = (double)mask; inf[13] = (na >= cap || j0 + 4 >= mc) ? 1.0 : 0.0;
             nacc_diag = na;
             mbar_arrive(&barD[slot]);
-            int q_out = nacc;                       // ids, positions and the diagonal block of the Cholesky factor
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (mask & (1 << q)) {
-                r4[q_out] = clist[j0 + q] + 1;
-                if (keep) {
-                    keep[g.off_acc + q_out] = (double)(j0 + q);
-                    double* Lc = keep + g.off_L + (size_t)q_out * MC + j0;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) if (r >= q && j0 + r < mc) Lc[r] = (r == q) ? A[q][q] * rdv[q] : A[r][q] * rdv[q];
-                }
-                q_out += 1;
-            }
+            if (K < 25) SCHUR_STAMPX(128 + 8 * K + 2);
         }
+        __syncwarp();                                // panel tiles that share the diagonal tile's warp start after it, not beside it
         if (has_tile && tK == K && tI > K) {         // ---- 2. the rest of the pivot panel
             mbar_wait(&barD[slot], par);
+            if (K < 25 && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 3);
             const int mask = (int)inf[12];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
@@ -421,14 +444,32 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
                 }
             }
         }
+        if (K < 25 && has_tile && tK == K && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 4);
         __syncwarp();
         const bool leaving = my_last <= K;           // no tile of this warp lies to the right of tile column K
         if (lane == 0) {
             if (!leaving) mbar_arrive(&barP[slot]);
             else { mbar_arrive_drop(&barP[slot]); mbar_arrive_drop(&barP[(slot + 1) % 3]); mbar_arrive_drop(&barP[(slot + 2) % 3]); }
         }
+        if (has_tile && tK == K && tI == K) {        // ids, positions and the diagonal block of the Cholesky factor (off the critical path)
+            int q_out = nacc;
+            const int dmask = (int)inf[12];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (dmask & (1 << q)) {
+                r4[q_out] = clist[j0 + q] + 1;
+                if (keep) {
+                    keep[g.off_acc + q_out] = (double)(j0 + q);
+                    double* Lc = keep + g.off_L + (size_t)q_out * MC + j0;
+                    const double rd = inf[q];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) if (r >= q && j0 + r < mc) Lc[r] = A[r][q] * rd;
+                }
+                q_out += 1;
+            }
+        }
         if (leaving) break;
         mbar_wait(&barP[slot], par);
+        if (K < 40) SCHUR_STAMP(9 + 2 * K);
         nacc += __popc((unsigned)(int)inf[12]);
         if (inf[13] != 0.0) break;                   // capacity reached (RbfModel.jl:402) or no candidates left
         if (has_tile && tK > K) {                    // ---- 3. rank-4 update
@@ -453,6 +494,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
             }
         }
     }
+    SCHUR_STAMP(5);
     // thread 0 owns the last diagonal tile: it is alive until the end and has seen every accepted pivot
     if (nacc_diag >= 0) nacc = nacc_diag;
     if (tid == 0) {
