@@ -271,8 +271,12 @@ def run_ours(args):
     dom = max(("rounds123", "round4", "build", "build_prepared"), key=lambda k: prof[k])
     ach = kflops[dom] / (prof[dom] * 1e-3) / 1e12
     step_total = prof["rounds123"] + prof["round4"] + prof["round4_fallback"] + prof["gather"] + prof["build"] + prof["build_prepared"]
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json"))).get(dom) if B == B_PER_GPU else None
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "pipe": "fp64 (DFMA; B200 FP64 tensor peak equals the FMA-pipe peak)", "kernel": dom,
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": {k: round(v, 4) for k, v in prof.items() if k != "eval"},
                 "kernel_share_of_step": round(prof[dom] / step_total, 4) if step_total > 0 else None,
                 "algorithmic_flops_per_launch": kflops[dom]}

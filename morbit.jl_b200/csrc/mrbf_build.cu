@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
     double* invd = sv + (size_t)p * k;          // MC
     double* Ls = invd + MC;                     // packed columns: column q at cs(q) = q m - q (q - 1) / 2, rows q..m-1
     int* accpos = reinterpret_cast<int*>(Ls + ((size_t)MC * (MC + 1)) / 2);
+    int* isacc = accpos + MC;
     const int* found = P.found + (size_t)b * P.found_stride;
     const int nf = P.n_found[b];
     const int* r4 = P.r4 + (size_t)b * P.r4_stride;
@@ -404,48 +405,78 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
         centers[e] = v;
     }
     __syncthreads();
-    for (int q = warp; q < m; q += nwarps) {     // packed copy of L restricted to the accepted rows
+    // L as round 4 left it: column q holds the rows (candidate positions) >= accpos[q].  It is packed by POSITION -- the column of
+    // the pivot at position j starts at cs(j) = j mc - j (j - 1) / 2 -- so the copy is coalesced and needs no gather; rows of rejected
+    // candidates ride along (they are updated but never used as pivots).
+    const int mc = (int)meta[3];
+    for (int q = warp; q < m; q += nwarps) {
+        const int j = accpos[q];
         const double* Lc = Lg + (size_t)q * MC;
-        double* dst = Ls + ((size_t)q * m - ((size_t)q * (q - 1)) / 2) - q;
-        for (int q2 = q + lane; q2 < m; q2 += 32) { const double v = Lc[accpos[q2]]; dst[q2] = v; if (q2 == q) invd[q] = 1.0 / v; }
+        double* dst = Ls + ((size_t)j * mc - ((size_t)j * (j - 1)) / 2) - j;
+        for (int i = j + lane; i < mc; i += 32) { const double v = Lc[i]; dst[i] = v; if (i == j) invd[q] = 1.0 / v; }
     }
-    for (int e = tid; e < m * k; e += nt) {      // r = Y_acc - C_acc' Y_0
+    for (int e = tid; e < mc * k; e += nt) rv[(e / mc) * MC + (e % mc)] = 0.0;
+    for (int i = tid; i < mc; i += nt) isacc[i] = 0;
+    __syncthreads();
+    for (int q = tid; q < m; q += nt) isacc[accpos[q]] = 1;
+    for (int e = tid; e < m * k; e += nt) {      // r = Y_acc - C_acc' Y_0, stored by candidate position
         const int q = e % m, o = e / m;
         double a = values[(size_t)(r4[q] - 1) * k + o];
         const double* cq = Cg + accpos[q];
         for (int r = 0; r < p; ++r) a = fma(-cq[(size_t)r * MC], y0[r * k + o], a);
-        rv[o * MC + q] = a;
+        rv[o * MC + accpos[q]] = a;
     }
     __syncthreads();
-    for (int o = warp; o < k; o += nwarps) {     // L t = r, then L' u = t: one warp per output, column-oriented updates
+    // L t = r, then L' u = t.  One warp per output; the right-hand side stays in registers (lane l owns positions l, l + 32,
+    // l + 64, l + 96 -- mc <= 128), the pivot entry travels by one shuffle per step and both sweeps are axpy updates (no
+    // reductions): forward with column j of L (contiguous), backward with row j of L (one entry per earlier column).
+    for (int o = warp; o < k; o += nwarps) {
         double* r = rv + o * MC;
+        double r0 = (lane < mc) ? r[lane] : 0.0, r1 = (lane + 32 < mc) ? r[lane + 32] : 0.0;
+        double r2 = (lane + 64 < mc) ? r[lane + 64] : 0.0, r3 = (lane + 96 < mc) ? r[lane + 96] : 0.0;
         for (int q = 0; q < m; ++q) {
-            const double t = r[q] * invd[q];
-            const double* col = Ls + ((size_t)q * m - ((size_t)q * (q - 1)) / 2) - q;
-            __syncwarp();
-            if (lane == 0) r[q] = t;
-            for (int q2 = q + 1 + lane; q2 < m; q2 += 32) r[q2] = fma(-col[q2], t, r[q2]);
-            __syncwarp();
+            const int j = accpos[q], sl = j >> 5;
+            const double mine = (sl == 0) ? r0 : ((sl == 1) ? r1 : ((sl == 2) ? r2 : r3));
+            const double t = __shfl_sync(0xffffffffu, mine, j & 31) * invd[q];
+            const double* col = Ls + ((size_t)j * mc - ((size_t)j * (j - 1)) / 2) - j;
+            const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
+            if (i0 == j) r0 = t; else if (i0 > j && i0 < mc) r0 = fma(-col[i0], t, r0);
+            if (i1 == j) r1 = t; else if (i1 > j && i1 < mc) r1 = fma(-col[i1], t, r1);
+            if (i2 == j) r2 = t; else if (i2 > j && i2 < mc) r2 = fma(-col[i2], t, r2);
+            if (i3 == j) r3 = t; else if (i3 > j && i3 < mc) r3 = fma(-col[i3], t, r3);
         }
+        // rejected positions carry no unknown: zero them, then sweep back
+        if (!(lane < mc && isacc[lane])) r0 = 0.0;
+        if (!(lane + 32 < mc && isacc[lane + 32])) r1 = 0.0;
+        if (!(lane + 64 < mc && isacc[lane + 64])) r2 = 0.0;
+        if (!(lane + 96 < mc && isacc[lane + 96])) r3 = 0.0;
+        // offsets of this lane's columns in the packed storage: element (row j, column i) sits at cs(i) - i + j
+        const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
+        const int c0 = i0 * mc - (i0 * (i0 - 1)) / 2 - i0, c1 = i1 * mc - (i1 * (i1 - 1)) / 2 - i1;
+        const int c2 = i2 * mc - (i2 * (i2 - 1)) / 2 - i2, c3 = i3 * mc - (i3 * (i3 - 1)) / 2 - i3;
         for (int q = m - 1; q >= 0; --q) {
-            const double* col = Ls + ((size_t)q * m - ((size_t)q * (q - 1)) / 2) - q;
-            double a = 0.0;
-            for (int q2 = q + 1 + lane; q2 < m; q2 += 32) a = fma(col[q2], r[q2], a);
-            a = warp_sum(a);
-            __syncwarp();
-            if (lane == 0) r[q] = (r[q] - a) * invd[q];
-            __syncwarp();
+            const int j = accpos[q], sl = j >> 5;
+            const double mine = (sl == 0) ? r0 : ((sl == 1) ? r1 : ((sl == 2) ? r2 : r3));
+            const double u = __shfl_sync(0xffffffffu, mine, j & 31) * invd[q];
+            if (i0 == j) r0 = u; else if (i0 < j && isacc[i0]) r0 = fma(-Ls[c0 + j], u, r0);
+            if (i1 == j) r1 = u; else if (i1 < j && isacc[i1]) r1 = fma(-Ls[c1 + j], u, r1);
+            if (i2 == j) r2 = u; else if (i2 < j && isacc[i2]) r2 = fma(-Ls[c2 + j], u, r2);
+            if (i3 == j) r3 = u; else if (i3 < j && isacc[i3]) r3 = fma(-Ls[c3 + j], u, r3);
         }
+        if (lane < mc) r[lane] = r0;
+        if (lane + 32 < mc) r[lane + 32] = r1;
+        if (lane + 64 < mc) r[lane + 64] = r2;
+        if (lane + 96 < mc) r[lane + 96] = r3;
     }
     __syncthreads();
     double* w_out = P.w + (size_t)b * P.train_stride * k;
     double* lam_out = P.lam + (size_t)b * p * k;
-    for (int e = tid; e < m * k; e += nt) { const int q = e / k, o = e % k; w_out[(size_t)(p + q) * k + o] = rv[o * MC + q]; }
+    for (int e = tid; e < m * k; e += nt) { const int q = e / k, o = e % k; w_out[(size_t)(p + q) * k + o] = rv[o * MC + accpos[q]]; }
     for (int e = warp; e < p * k; e += nwarps) { // w_0 = -C_acc u ; t0 = Y_0 - U_acc u   (warp per entry, lanes over the accepted points)
         const int r = e / k, o = e % k;
         const double* u = rv + o * MC;
         double a = 0.0, g = 0.0;
-        for (int q = lane; q < m; q += 32) { const int pos = accpos[q]; a = fma(Cg[(size_t)r * MC + pos], u[q], a); g = fma(Ug[(size_t)r * MC + pos], u[q], g); }
+        for (int q = lane; q < m; q += 32) { const int pos = accpos[q]; a = fma(Cg[(size_t)r * MC + pos], u[pos], a); g = fma(Ug[(size_t)r * MC + pos], u[pos], g); }
         a = warp_sum(a); g = warp_sum(g);
         if (lane == 0) { w_out[(size_t)r * k + o] = -a; t0[e] = y0[e] - g; }
     }
@@ -468,7 +499,7 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
 }
 
 size_t build_schur_smem_doubles(int k, int MC, int p) {
-    return 3 * (size_t)p * k + (size_t)MC * k + MC + ((size_t)MC * (MC + 1)) / 2 + (MC + 1) / 2 + 2;
+    return 3 * (size_t)p * k + (size_t)MC * k + MC + ((size_t)MC * (MC + 1)) / 2 + MC + 2;
 }
 cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(build_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
