@@ -115,6 +115,67 @@ class MultistartBuilder:
         return model, self._sel, status
 
 
+class HostPipeline:
+    """One build per instance from HOST database snapshots (what a host-language caller such as the Julia shim hands over),
+    with the copies hidden behind the kernels: the batch is cut into `chunks` slices; the pinned host -> device copy of slice
+    c + 1 runs on a copy stream while slice c is processed on the engine's stream, and the device -> host copy of slice c's
+    indices / flags / status runs while slice c + 1 computes.  Nothing about the results changes -- instances are independent."""
+
+    NAMES = ("sites", "values", "n_db", "x_index", "x", "delta", "flags_in", "max_new")
+    OUTS = ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "flags_out")
+
+    def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2):
+        import torch
+        self.torch = torch
+        self.engine, self.cfg, self.chunks, self.compute = engine, cfg, chunks, compute_stream
+        B = host["sites"].shape[0]
+        self.bounds = [shard_range(B, c, chunks) for c in range(chunks)]
+        f64, i32 = torch.float64, torch.int32
+        dt = dict(sites=f64, values=f64, n_db=i32, x_index=i32, x=f64, delta=f64, flags_in=i32, max_new=i32)
+        self.pinned = [{k: torch.from_numpy(np.ascontiguousarray(host[k][lo:hi])).to(dt[k]).pin_memory() for k in self.NAMES}
+                       for lo, hi in self.bounds]
+        glb = torch.from_numpy(np.ascontiguousarray(host["glb"])).to(f64).to(device)
+        gub = torch.from_numpy(np.ascontiguousarray(host["gub"])).to(f64).to(device)
+        self.dev = [DeviceBatch(*(torch.empty_like(pc[k], device=device) for k in ("sites", "values", "n_db", "x_index", "x", "delta")),
+                                glb, gub, torch.empty_like(pc["flags_in"], device=device), torch.empty_like(pc["max_new"], device=device))
+                    for pc in self.pinned]
+        self.builders = [MultistartBuilder(engine, cfg, delta_max) for _ in range(chunks)]
+        self.models = [None] * chunks
+        self.out_pinned = [None] * chunks
+        self.copy_in, self.copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(chunks)]
+        self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for pc in self.pinned for t in pc.values())
+        self.d2h_bytes = 0
+
+    def step(self):
+        """Enqueue one pass over the whole batch; returns immediately (synchronise the compute stream to wait for it)."""
+        torch = self.torch
+        for c in range(self.chunks):
+            with torch.cuda.stream(self.copy_in):
+                self.copy_in.wait_event(self.ev_comp[c])          # the slice's device buffers are free again
+                for k in self.NAMES:
+                    getattr(self.dev[c], k).copy_(self.pinned[c][k], non_blocking=True)
+                self.ev_in[c].record(self.copy_in)
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(self.ev_in[c])
+                self.compute.wait_event(self.ev_out[c])           # the previous step's result copy of this slice has left
+                self.models[c], sel, status = self.builders[c].step(self.dev[c], recycle=self.models[c])
+                self.ev_comp[c].record(self.compute)
+            outs = [getattr(sel, k) for k in self.OUTS] + [status]
+            if self.out_pinned[c] is None:
+                self.out_pinned[c] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                self.d2h_bytes += sum(o.numel() * o.element_size() for o in outs)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(self.ev_comp[c])
+                for p, o in zip(self.out_pinned[c], outs):
+                    p.copy_(o, non_blocking=True)
+                self.ev_out[c].record(self.copy_out)
+        self.compute.wait_event(self.ev_out[self.chunks - 1])     # the step ends when its last result copy has landed
+        return self.models, self.out_pinned
+
+
 def gather_results(local: np.ndarray, total: int, rank: int, world: int) -> Optional[np.ndarray]:
     """Final gather of per-instance result rows to every rank (no collective on the hot path; this is the only one).
 

@@ -294,3 +294,37 @@ def test_build_from_kept_factorisation_matches_oracle(engine, kernel, n, n_db, m
         assert np.abs(Y[b] - Yr).max() <= RTOL * np.abs(Yr).max(), (b, np.abs(Y[b] - Yr).max() / np.abs(Yr).max())
         assert np.abs(J[b] - Jr).max() <= RTOL * np.abs(Jr).max(), (b, np.abs(J[b] - Jr).max() / np.abs(Jr).max())
     prepared.free(); model.free()
+
+
+@pytest.mark.gpu
+def test_host_pipeline_overlapped_copies_match_oracle(engine):
+    """multistart.HostPipeline: host database snapshots in, indices / flags / status out, copies of one slice overlapping the kernels
+    of the other; two passes (the second recycles the model handles and the kept factorisations).  Indices must be the oracle's."""
+    import torch
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import HostPipeline
+    B, n, n_db = 21, 12, 64
+    cfg = mb.RbfConfig(kernel="multiquadric")
+    host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=0.1, func=synthetic.zdt3, local_fraction=0.5)
+    ref = CO.select_points_batched(cfg, host["sites"], host["x_index"], host["x"], host["delta"], host["delta_max"], host["glb"],
+                                   host["gub"], False, False, host["max_new"], nthreads=4)
+    stream = torch.cuda.Stream()
+    eng = mb.Engine(0, stream=stream.cuda_stream)
+    pipe = HostPipeline(eng, cfg, host["delta_max"], host, "cuda:0", stream, chunks=3)
+    for _ in range(2):
+        models, outs = pipe.step()
+        stream.synchronize()
+        b0 = 0
+        for c, (lo, hi) in enumerate(pipe.bounds):
+            o = dict(zip(HostPipeline.OUTS + ("status",), (t.numpy() for t in outs[c])))
+            assert np.all(o["status"] == 0)
+            for b in range(lo, hi):
+                for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+                    assert list(o[nm][b - lo, :o[cnt][b - lo]]) == list(getattr(ref, nm)[b, :getattr(ref, cnt)[b]]), (b, nm)
+                assert o["n_r3"][b - lo] == ref.n_r3[b]
+            assert models[c].B == hi - lo
+            b0 = hi
+        assert b0 == B
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
+    for m in models:
+        m.free()
