@@ -41,6 +41,7 @@ struct Round4Params {
     int only_marked;              // literal kernel: process only instances the fast kernel marked (n_r4 == -1)
     double* fs; size_t fs_stride; int fs_in_smem;   // fast-path state
     double* keep_fs; int* elig;                     // kept factorisation (mrbf_prepared) or NULL
+    double* panel_ws;                               // round4_panels_kernel -> round4_schur_kernel hand-over (B x SchurGeom::pw_doubles)
     long long* dbg_clock;                           // instrumentation (MRBF_DEBUG_CLOCK): phase time stamps of CTA 0, or NULL
 };
 
@@ -48,7 +49,9 @@ struct Round4Params {
 // kept factorisation, all in doubles.
 struct SchurGeom {
     int MC, TR, ntiles, nthreads, eligible;
-    size_t sm_C, sm_V, sm_Xc, sm_X0, sm_M0, sm_P00, sm_col, sm_red, sm_int, smem_doubles;
+    size_t sm_C, sm_V, sm_Xc, sm_col, sm_red, sm_int, smem_doubles;          // kernel 2 (tiles + elimination)
+    size_t ps_Aq, ps_X0, ps_M0, ps_P00, ps_red, ps_int, ps_doubles;           // kernel 1 (panels)
+    size_t pw_C, pw_V, pw_Xc, pw_clist, pw_meta, pw_doubles;                  // global panel workspace per instance
     size_t off_M0, off_U, off_C, off_L, off_acc, state_doubles;
 };
 

@@ -102,35 +102,44 @@ SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     if (nt < 256) nt = 256;
     g.nthreads = nt;
     auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };          // every block starts 32-byte aligned (double4 accesses)
-    const size_t cv = up4((size_t)2 * pl * (g.MC > pl ? g.MC : pl));   // [C | V] panels; Gauss-Jordan scratch aliases them
-    g.sm_C = 0; g.sm_V = (size_t)pl * g.MC;
-    g.sm_Xc = cv; g.sm_X0 = g.sm_Xc + (size_t)n * g.MC;
-    g.sm_M0 = up4(g.sm_X0 + (size_t)pl * n); g.sm_P00 = up4(g.sm_M0 + (size_t)pl * pl);
-    g.sm_col = up4(g.sm_P00 + (size_t)pl * pl);                         // ring[3] of { colA, colAs, colW, colWs : [4][MC] }, then info[3][24]
+    const size_t ints = (size_t)g.MC + 32 + ((size_t)db_stride + 3) / 4 + 4;   // clist[MC], wcnt[32], flags[db_stride] bytes
+    // kernel 1 (panels): shared memory
+    g.ps_Aq = 0; g.ps_X0 = up4((size_t)2 * pl * pl); g.ps_M0 = up4(g.ps_X0 + (size_t)pl * n); g.ps_P00 = up4(g.ps_M0 + (size_t)pl * pl);
+    g.ps_red = up4(g.ps_P00 + (size_t)pl * pl); g.ps_int = g.ps_red + 80; g.ps_doubles = g.ps_int + (ints + 1) / 2;
+    // panel workspace (global, per instance): C (p x MC), V (p x MC), Xc (n x MC), clist (MC ints), meta (8)
+    g.pw_C = 0; g.pw_V = (size_t)pl * g.MC; g.pw_Xc = g.pw_V + (size_t)pl * g.MC; g.pw_clist = g.pw_Xc + (size_t)n * g.MC;
+    g.pw_meta = up4(g.pw_clist + (g.MC + 1) / 2); g.pw_doubles = g.pw_meta + 8;
+    // kernel 2 (tiles + elimination): shared memory
+    g.sm_C = 0; g.sm_V = (size_t)pl * g.MC; g.sm_Xc = g.sm_V + (size_t)pl * g.MC;
+    g.sm_col = g.sm_Xc + (size_t)n * g.MC;                              // ring[3] of { colA, colAs, colW, colWs : [4][MC] }, then info[3][24]
     g.sm_red = g.sm_col + (size_t)48 * g.MC + 3 * 24;
-    g.sm_int = g.sm_red + 80;                                           // clist[MC] ints, wcnt[32] ints, flags[db_stride] bytes
-    const size_t ints = (size_t)g.MC + 32 + ((size_t)db_stride + 3) / 4 + 4;
-    g.smem_doubles = g.sm_int + (ints + 1) / 2;
+    g.sm_int = g.sm_red + 80;
+    g.smem_doubles = g.sm_int + ((size_t)g.MC + 1) / 2 + 2;
     // kept state per instance: M0 (p x p), U (p x MC), C (p x MC), L (MC x MC, column q = q-th accepted pivot), accpos (MC), meta (8)
     g.off_M0 = 0; g.off_U = up4((size_t)pl * pl); g.off_C = g.off_U + (size_t)pl * g.MC; g.off_L = g.off_C + (size_t)pl * g.MC;
     g.off_acc = g.off_L + (size_t)g.MC * g.MC; g.state_doubles = up4(g.off_acc + g.MC + 8);
-    g.eligible = (p > 0 && g.MC <= 128 && g.nthreads <= 544 && g.smem_doubles * sizeof(double) <= (size_t)225 * 1024) ? 1 : 0;
+    g.eligible = (p > 0 && g.MC <= 128 && g.nthreads <= 544 && g.smem_doubles * sizeof(double) <= (size_t)225 * 1024 &&
+                  g.ps_doubles * sizeof(double) <= (size_t)225 * 1024) ? 1 : 0;
     return g;
 }
 
-__global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, SchurGeom g) {
+// Kernel 1 of 2: candidate list, Pi_0^{-1} and the panels C, V, Xc of one instance, written to the global panel workspace
+// (and C, U, M0 to the kept factorisation).  Small footprint (the Gauss-Jordan scratch and three p x p matrices in shared
+// memory, 64 registers), so four to five instances share an SM and hide each other's pivot chains.
+__global__ void __launch_bounds__(256, 4) round4_panels_kernel(Round4Params P, SchurGeom g) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = poly_dim(n, P.cfg.polynomial_degree), pl = p;
     const int MC = g.MC;
-    double* Cs = smem + g.sm_C; double* Vs = smem + g.sm_V; double* Xc = smem + g.sm_Xc; double* X0 = smem + g.sm_X0;
-    double* M0 = smem + g.sm_M0; double* P00 = smem + g.sm_P00;
-    double* ring = smem + g.sm_col; double* info = ring + 48 * MC;
-    double* red = smem + g.sm_red;
-    int* clist = reinterpret_cast<int*>(smem + g.sm_int); int* wcnt = clist + MC;
-    unsigned char* cflag = reinterpret_cast<unsigned char*>(wcnt + 32);
-    double* Aq = smem;                 // Gauss-Jordan scratch [Pi_0 | I] (p x 2p), dead before C is written
+    double* pw = P.panel_ws + (size_t)blockIdx.x * g.pw_doubles;
+    double* Cs = pw + g.pw_C; double* Vs = pw + g.pw_V; double* Xc = pw + g.pw_Xc;      // panels: global (L2-resident) workspace
+    double* pmeta = pw + g.pw_meta;
+    double* Aq = smem + g.ps_Aq;       // Gauss-Jordan scratch [Pi_0 | I] (p x 2p)
     double* Qx = Aq + pl * pl;
+    double* X0 = smem + g.ps_X0; double* M0 = smem + g.ps_M0; double* P00 = smem + g.ps_P00;
+    double* red = smem + g.ps_red;
+    int* clist = reinterpret_cast<int*>(smem + g.ps_int); int* wcnt = clist + MC;
+    unsigned char* cflag = reinterpret_cast<unsigned char*>(wcnt + 32);
 
 #define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
 #define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
@@ -143,10 +152,10 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     const int nf_ids = P.n_found[b];
     const int n_extra = P.n_extra ? P.n_extra[b] : 0;
     const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
-    int* r4 = P.r4 + (size_t)b * P.r4_stride;
     const int N0 = nf_ids + n_extra;
     const int max_points = P.max_points;
     if (tid == 0 && P.elig) P.elig[b] = 0;
+    if (tid == 0) pmeta[0] = 0.0;                  // [0] number of candidates handed to kernel 2 (0: nothing to do)
     if (!(N0 < max_points)) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
     if (N0 != p || n_db > MC) { if (tid == 0) P.n_r4[b] = -1; return; }      // literal kernel takes over
 
@@ -304,6 +313,46 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
         if (keep) *reinterpret_cast<double4*>(keep + g.off_U + r * MC + i4) = make_double4(bb.x - s0, bb.y - s1, bb.z - s2, bb.w - s3);
         *reinterpret_cast<double4*>(Vs + r * MC + i4) = make_double4(fma(-0.5, s0, bb.x), fma(-0.5, s1, bb.y), fma(-0.5, s2, bb.z), fma(-0.5, s3, bb.w));
     }
+    for (int i = tid; i < mc; i += nt) reinterpret_cast<int*>(pw + g.pw_clist)[i] = clist[i];
+    if (tid == 0) { pmeta[1] = inv_s; pmeta[2] = (double)N0; pmeta[0] = (double)mc; }
+    SCHUR_STAMP(3);
+}
+
+// Kernel 2 of 2: the panels come back from the workspace into shared memory, every thread computes its 4 x 4 tiles of A and W and
+// the blocked elimination runs in registers.  One CTA per SM (the tiles fill the register file).
+__global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, SchurGeom g) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int p = poly_dim(n, P.cfg.polynomial_degree);
+    const int MC = g.MC;
+    double* Cs = smem + g.sm_C; double* Vs = smem + g.sm_V; double* Xc = smem + g.sm_Xc;
+    double* ring = smem + g.sm_col; double* info = ring + 48 * MC;
+    double* red = smem + g.sm_red;
+    int* clist = reinterpret_cast<int*>(smem + g.sm_int);
+#define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+#define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+    SCHUR_STAMP(6);
+    const double* pw = P.panel_ws + (size_t)b * g.pw_doubles;
+    const double* pmeta = pw + g.pw_meta;
+    const int mc = (int)pmeta[0];
+    if (mc == 0) return;                            // kernel 1 has already written n_r4 (0, or -1 for the literal kernel)
+    const double inv_s = pmeta[1];
+    const int N0 = (int)pmeta[2];
+    const int max_points = P.max_points;
+    int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
+    const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
+    {
+        const int q4 = MCa >> 2;
+        const double* Cg = pw + g.pw_C; const double* Vg = pw + g.pw_V; const double* Xg = pw + g.pw_Xc;
+        for (int e = tid; e < (2 * p + n) * q4; e += nt) {
+            const int r = e / q4, i4 = (e % q4) * 4;
+            const double* src = (r < p) ? Cg + (size_t)r * MC : ((r < 2 * p) ? Vg + (size_t)(r - p) * MC : Xg + (size_t)(r - 2 * p) * MC);
+            double* dst = (r < p) ? Cs + r * MC : ((r < 2 * p) ? Vs + (r - p) * MC : Xc + (r - 2 * p) * MC);
+            *reinterpret_cast<double4*>(dst + i4) = *reinterpret_cast<const double4*>(src + i4);
+        }
+        for (int i = tid; i < mc; i += nt) clist[i] = reinterpret_cast<const int*>(pw + g.pw_clist)[i];
+    }
     // split-phase barriers of the elimination, one pair per slot of the three-deep ring of pivot blocks:
     //   barD: the diagonal tile of the block has been factorised (one arrival), barP: the whole pivot panel is published
     //   (one arrival per warp that is still alive).
@@ -312,7 +361,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     if (tid == 0) for (int q = 0; q < 3; ++q) { mbar_init(&barD[q], 1); mbar_init(&barP[q], nwarps); }
     __syncthreads();
 
-    SCHUR_STAMP(3);
+    SCHUR_STAMP(7);
     // ---- tiles: thread t owns tile (I, K), I >= K, of A and of W.  Tiles are numbered column by column from the LAST tile
     // column, so the tiles that are still live at pivot j (K >= j / 4) are always a prefix of the thread block.
     int tI = 0, tK = 0;
@@ -508,9 +557,11 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
 }
 
 cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaStream_t s) {
-    const size_t smem = g.smem_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(round4_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t psmem = g.ps_doubles * sizeof(double), smem = g.smem_doubles * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(round4_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(round4_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    round4_panels_kernel<<<P.B, 256, psmem, s>>>(P, g);
     round4_schur_kernel<<<P.B, g.nthreads, smem, s>>>(P, g);
     return cudaGetLastError();
 }
