@@ -287,6 +287,32 @@ def run_ours(args):
                               "roofline": {"bound": "tensor", "pipe": "fp64", "achieved": jv / world * fj / 1e12, "peak": peak,
                                            "unit": "TFLOP/s", "frac": jv / world * fj / 1e12 / peak, "flop_per_point": fj}})
 
+    # ---- secondary metric: one steepest-descent step per instance on the fitted surrogates (descent.jl:187-260):
+    # Jacobian at the iterate -> LP for the direction (mrbf_descent_direction_dev) ; SURVEY 8(f) rank 1
+    if args.descent:
+        Xc = dev.x.reshape(B, 1, N_VARS).contiguous()
+        Jc = torch.empty((B, 1, K_OUT, N_VARS), dtype=torch.float64, device="cuda")
+        out = None
+        with torch.cuda.stream(stream):
+            for _ in range(args.warmup):
+                eng.eval_dev(model, Xc, None, Jc); out = eng.descent_direction_dev(Jc.view(B, K_OUT, N_VARS), dev.x, dev.glb, dev.gub, True, out)
+            d0, d1, d2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            stream.synchronize()
+            d0.record(stream)
+            for _ in range(args.steps):
+                eng.eval_dev(model, Xc, None, Jc)
+            d1.record(stream)
+            for _ in range(args.steps):
+                out = eng.descent_direction_dev(Jc.view(B, K_OUT, N_VARS), dev.x, dev.glb, dev.gub, True, out)
+            d2.record(stream)
+            stream.synchronize()
+        jac_ms, lp_ms = d0.elapsed_time(d1) / args.steps, d1.elapsed_time(d2) / args.steps
+        secondary.append({"metric": "descent_directions_per_s", "value": world * B / ((jac_ms + lp_ms) * 1e-3), "unit": "directions/s",
+                          "ms_per_step": jac_ms + lp_ms, "jacobian_ms": jac_ms, "lp_ms": lp_ms,
+                          "lp_iterations_mean": float(out[2].double().mean().item()), "lp_ok": int((out[3] == 0).sum().item()),
+                          "config": {"workload": f"{B} instances per GPU: surrogate Jacobian at the iterate (k={K_OUT}, n={N_VARS}) + exact LP "
+                                                 "for the constrained steepest-descent direction"}})
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as CO
@@ -388,6 +414,7 @@ def main():
     ap.add_argument("--eval-points", type=int, default=10**6, help="C5 trial points for the secondary metric (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-descent", dest="descent", action="store_false", help="skip the steepest-descent secondary metric")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the batch in the end-to-end pipeline (1 = no overlap)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -196,6 +196,19 @@ int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* model, const double* x, cons
                    const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
                    int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus);
 
+/* ---- steepest-descent direction: replaces _steepest_descent_direction (src/descent.jl:75-135, JuMP + OSQP) -----------
+ *      min alpha  s.t.  Df_i . d <= alpha * ||Df_i||_2 (rows normalised iff `normalize`),  -1 <= d <= 1,  lb <= x + d <= ub
+ * solved exactly (bounded-variable simplex, k x k basis) for B instances at once.
+ *   jac B x k x n (row l = gradient of output l, as mrbf_eval returns it), x B x n, lb / ub: n global scaled bounds
+ *   (+-INFINITY when unbounded).  Outputs: d B x n, omega B (= -alpha, the criticality measure), iters B (may be NULL),
+ *   status B (0 optimal, 1 iteration limit).  k <= 8.  Linear constraints of the MOP (A_eq, A_ineq) are not supported. */
+int mrbf_descent_direction(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, const double* jac, const double* x,
+                           const double* lb, const double* ub, int32_t normalize,
+                           double* d, double* omega, int32_t* iters, int32_t* status);
+int mrbf_descent_direction_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, const double* jac, const double* x,
+                               const double* lb, const double* ub, int32_t normalize,
+                               double* d, double* omega, int32_t* iters, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

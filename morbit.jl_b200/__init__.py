@@ -16,7 +16,7 @@ from .surrogate import (  # noqa: E402
     RBF_KERNELS, RbfConfig, RbfMeta, RbfModel, ArrayDB, SuperDB, IterData, VarScaler, AlgoConfig, MopStub,
     max_evals, combinable, get_saveable, fully_linear, set_fully_linear, num_outputs, get_sub_db,
     prepare_init_model, prepare_update_model, prepare_improve_model, init_model, update_model, improve_model,
-    eval_models, get_gradient, get_jacobian, _rbf_round4, _collect_indices, _backtrack, default_engine,
+    eval_models, get_gradient, get_jacobian, _rbf_round4, _collect_indices, _backtrack, _steepest_descent_direction, default_engine,
 )
 from . import multistart  # noqa: E402
 

@@ -791,4 +791,43 @@ int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const do
     return MRBF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ steepest-descent LP
+int mrbf_descent_direction_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, const double* jac, const double* x,
+                               const double* lb, const double* ub, int32_t normalize,
+                               double* d, double* omega, int32_t* iters, int32_t* status) {
+    if (!ctx || !jac || !x || !lb || !ub || !d || !omega) return MRBF_EINVAL;
+    if (B <= 0 || n <= 0 || k <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    if (k > descent_max_outputs()) return fail(ctx, MRBF_EUNSUPPORTED, "mrbf_descent_direction supports at most 8 outputs%s");
+    CK(cudaSetDevice(ctx->device));
+    DescentParams P{};
+    P.B = B; P.n = n; P.k = k; P.normalize = normalize ? 1 : 0; P.warp_doubles = descent_warp_doubles(n, k);
+    if (4 * P.warp_doubles * sizeof(double) > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "too many variables for mrbf_descent_direction%s");
+    P.jac = jac; P.x = x; P.lb = lb; P.ub = ub; P.d = d; P.omega = omega; P.iters = iters; P.status = status;
+    CK(launch_descent_direction(P, ctx->stream));
+    ctx->launches += 1;
+    return MRBF_OK;
+}
+
+int mrbf_descent_direction(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, const double* jac, const double* x,
+                           const double* lb, const double* ub, int32_t normalize,
+                           double* d, double* omega, int32_t* iters, int32_t* status) {
+    if (!ctx || !jac || !x || !lb || !ub || !d || !omega) return MRBF_EINVAL;
+    if (B <= 0 || n <= 0 || k <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bj = sizeof(double) * (size_t)B * k * n, bx = sizeof(double) * (size_t)B * n, bn = sizeof(double) * (size_t)n;
+    ENSURE(ctx->hb[20], bj + 2 * bx + 2 * bn + sizeof(double) * (size_t)B + 2 * sizeof(int) * (size_t)B);
+    double* d_j = (double*)ctx->hb[20].p; double* d_x = d_j + (size_t)B * k * n; double* d_d = d_x + (size_t)B * n;
+    double* d_lb = d_d + (size_t)B * n; double* d_ub = d_lb + n; double* d_om = d_ub + n;
+    int* d_it = (int*)(d_om + B); int* d_st = d_it + B;
+    H2D(d_j, jac, bj); H2D(d_x, x, bx); H2D(d_lb, lb, bn); H2D(d_ub, ub, bn);
+    int rc = mrbf_descent_direction_dev(ctx, B, n, k, d_j, d_x, d_lb, d_ub, normalize, d_d, d_om, d_it, d_st);
+    if (rc != MRBF_OK) return rc;
+    D2H(d, d_d, bx); D2H(omega, d_om, sizeof(double) * (size_t)B);
+    if (iters) D2H(iters, d_it, sizeof(int) * (size_t)B);
+    if (status) D2H(status, d_st, sizeof(int) * (size_t)B);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
 }  // extern "C"

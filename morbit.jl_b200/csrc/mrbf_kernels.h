@@ -121,6 +121,12 @@ struct BacktrackParams {
     int* step_index; double* sigma; double* x_plus; double* mx; double* mx_plus;
 };
 
+struct DescentParams {
+    int B, n, k, normalize; size_t warp_doubles;
+    const double* jac; const double* x; const double* lb; const double* ub;
+    double* d; double* omega; int* iters; int* status;
+};
+
 size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride);
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
@@ -146,6 +152,9 @@ size_t build_schur_smem_doubles(int k, int MC, int p);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);
 cudaError_t launch_eval_pack(const PackParams& P, cudaStream_t s);
 int eval_pack_stride(int n);
+cudaError_t launch_descent_direction(const DescentParams& P, cudaStream_t s);
+size_t descent_warp_doubles(int n, int k);
+int descent_max_outputs();
 cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s);
 cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s);
 

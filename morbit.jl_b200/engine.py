@@ -316,6 +316,29 @@ class Engine:
         self._check(self.lib.mrbf_eval_dev(self.ctx, model.handle, M, _ptr(X), _ptr(Y), _ptr(J)))
         return Y, J
 
+    # ------------------------------------------------------------------ steepest-descent direction (descent.jl:75-135)
+    def descent_direction(self, jac, x, lb, ub, normalize: bool = True):
+        """Batched _steepest_descent_direction: jac B x k x n, x B x n, lb / ub n -> (d B x n, omega B, iters B, status B)."""
+        jac = _np(jac, np.float64)
+        B, k, n = jac.shape
+        x = _np(x, np.float64).reshape(B, n)
+        lb = _np(np.broadcast_to(lb, (n,)), np.float64); ub = _np(np.broadcast_to(ub, (n,)), np.float64)
+        d = np.zeros((B, n)); omega = np.zeros(B); iters = np.zeros(B, np.int32); status = np.zeros(B, np.int32)
+        self._check(self.lib.mrbf_descent_direction(self.ctx, B, n, k, _ptr(jac), _ptr(x), _ptr(lb), _ptr(ub), int(bool(normalize)),
+                                                    _ptr(d), _ptr(omega), _ptr(iters), _ptr(status)))
+        return d, omega, iters, status
+
+    def descent_direction_dev(self, jac, x, lb, ub, normalize: bool = True, out=None):
+        """Device tensors in and out (enqueued on the engine's stream)."""
+        import torch
+        B, k, n = jac.shape
+        if out is None:
+            f64 = dict(dtype=torch.float64, device=jac.device); i32 = dict(dtype=torch.int32, device=jac.device)
+            out = (torch.empty((B, n), **f64), torch.empty(B, **f64), torch.empty(B, **i32), torch.empty(B, **i32))
+        self._check(self.lib.mrbf_descent_direction_dev(self.ctx, B, n, k, _ptr(jac), _ptr(x), _ptr(lb), _ptr(ub), int(bool(normalize)),
+                                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3])))
+        return out
+
     def backtrack(self, model: ModelBatch, x, direction, step0, omega, armijo_c=1e-6, shrink=0.75,
                   min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict=True):
         """descent.jl:150-185 with every step size evaluated in one launch."""

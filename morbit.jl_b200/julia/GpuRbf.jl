@@ -218,4 +218,20 @@ function _backtrack_gpu(mod::GpuRbfModel, x::Vector{Float64}, dir::Vector{Float6
     return x₊, mx₊, σ[1] .* dir
 end
 
+# Constrained steepest-descent direction (descent.jl:91-135): the LP that the reference hands to JuMP + OSQP, solved exactly on
+# the device.  Drop-in for `_steepest_descent_direction(x, ∇F, lb, ub, [], [], [], [], normalize)` when the MOP has no linear
+# constraints (descent.jl:239 passes them through; with constraints the reference method stays in charge).
+function _steepest_descent_direction_gpu(ctx::Ptr{Cvoid}, x::Vector{Float64}, ∇F::Matrix{Float64}, lb::Vector{Float64}, ub::Vector{Float64},
+                                         normalize::Bool = true)
+    k, n = size(∇F)
+    jac = permutedims(∇F)                       # k x n row-major == n x k column-major
+    d = zeros(n); ω = Float64[0]; iters = Int32[0]; status = Int32[0]
+    _check(ctx, ccall((:mrbf_descent_direction, LIBMRBF), Cint,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        ctx, 1, n, k, jac, x, lb, ub, normalize, d, ω, iters, status))
+    status[1] == 0 || return zeros(n), -Inf     # descent.jl:129-133
+    return d, ω[1]
+end
+
 # user-facing: add_objective!(mop, f; model_cfg = GpuRbfConfig(rbf = RbfConfig(kernel = :multiquadric)), n_out = 2)

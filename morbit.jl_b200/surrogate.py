@@ -391,6 +391,21 @@ def get_gradient(mod: RbfModel, scal, x_scaled, ell: int):
     return get_jacobian(mod, scal, x_scaled, [ell])[0]
 
 
+def _steepest_descent_direction(x, jac, lb, ub, A_eq=None, b_eq=None, A_ineq=None, b_ineq=None, normalize=True,
+                                engine: Optional[Engine] = None):
+    """_steepest_descent_direction, descent.jl:91-135: returns (d, omega).  The reference hands the LP to JuMP + OSQP
+    (eps_rel = 1e-5); here it is solved exactly on the device.  Linear constraints of the MOP are outside the hot path."""
+    for a in (A_eq, b_eq, A_ineq, b_ineq):
+        if a is not None and len(a) > 0:
+            raise NotImplementedError("linear constraints are not part of the GPU hot path")
+    eng = engine or default_engine()
+    d, omega, _it, status = eng.descent_direction(np.asarray(jac, dtype=np.float64)[None], np.asarray(x, dtype=np.float64)[None],
+                                                  lb, ub, normalize)
+    if status[0] != 0:           # the reference warns and returns (zeros, -Inf) when the LP solver fails (descent.jl:129-133)
+        return np.zeros(len(x)), -math.inf
+    return d[0], float(omega[0])
+
+
 def _backtrack(x, direction, step_size, omega, mod: RbfModel, *, armijo_const_rhs=1e-6, armijo_const_shrink=0.75,
                min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict_backtracking=True):
     """_backtrack, descent.jl:150-185: returns (x₊, m(x₊), step)."""
