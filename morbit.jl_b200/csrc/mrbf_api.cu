@@ -715,7 +715,7 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
     if (M == 0 || (!Y && !J)) return MRBF_OK;
     CK(cudaSetDevice(ctx->device));
     int nl = 0;
-    if (m->pack_tile_doubles && !m->pack_valid) {
+    if (m->pack_tile_doubles && !m->pack_valid && M > 8) {   // (a handful of points goes through eval_small_kernel, which needs no tiles)
         // first evaluation of this model: re-tile it once for the tensor-path sweep (the handle is logically const)
         mrbf_model* mm = const_cast<mrbf_model*>(m);
         if (!mm->pack) {

@@ -202,6 +202,75 @@ __global__ void __launch_bounds__(256, 1) eval_tile_kernel(EvalParams P, int l0,
     }
 }
 
+// Few trial points per instance (the Jacobian at the iterate, the rho test: M = 1; descent.jl:196, algorithm.jl:766): the tiled
+// kernels would run 64-point tiles with one live row.  Here ONE WARP takes one (instance, point): lanes over the centres for
+// phi / psi (each lane walks its centre's contiguous coordinates), the weighted psi go through shared memory, then lanes over
+// the coordinates accumulate the Jacobian rows with coalesced reads of the centre matrix.
+__global__ void __launch_bounds__(128) eval_small_kernel(EvalParams P, int warp_doubles) {
+    extern __shared__ double sm_small[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long q = (long long)blockIdx.x * 4 + wib;
+    if (q >= (long long)P.B * P.M) return;
+    const int b = (int)(q / P.M);
+    const long long mi = q % P.M;
+    const int n = P.n, k = P.k;
+    double* xs = sm_small + (size_t)wib * warp_doubles;      // n
+    double* sw = xs + n;                                      // N x k   w_il * psi_i
+    const int N = P.N[b];
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* w = P.w + (size_t)b * P.train_stride * k;
+    const int pl = P.p > 0 ? P.p : 1;
+    const double* lam = P.lam + (size_t)b * pl * k;
+    const double* x = P.X + ((size_t)b * P.M + mi) * n;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn; rf.alpha2 = P.alpha2[b];
+    for (int c = lane; c < n; c += 32) xs[c] = x[c];
+    __syncwarp();
+    const bool want_j = P.J != nullptr;
+    for (int l0 = 0; l0 < k; l0 += 4) {
+        const int kk = min(4, k - l0);
+        double y[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = lane; i < N; i += 32) {
+            const double* c = centers + (size_t)i * n;
+            double r0 = 0.0, r1 = 0.0;
+            int r = 0;
+            for (; r + 1 < n; r += 2) { const double d0 = xs[r] - c[r], d1 = xs[r + 1] - c[r + 1]; r0 = fma(d0, d0, r0); r1 = fma(d1, d1, r1); }
+            if (r < n) { const double d0 = xs[r] - c[r]; r0 = fma(d0, d0, r0); }
+            double ph, ps;
+            rad_phi_psi(rf, r0 + r1, ph, ps);
+            for (int l = 0; l < kk; ++l) {
+                const double wl = w[(size_t)i * k + l0 + l];
+                y[l] = fma(wl, ph, y[l]);
+                if (want_j) sw[i * k + l0 + l] = wl * ps;
+            }
+        }
+        for (int l = 0; l < kk; ++l) {
+            double sacc = warp_sum(y[l]);
+            if (P.deg >= 0) sacc += lam[l0 + l];
+            if (P.deg >= 1) {
+                double t = 0.0;
+                for (int r = lane; r < n; r += 32) t = fma(lam[(size_t)(r + 1) * k + l0 + l], xs[r], t);
+                sacc += warp_sum(t);
+            }
+            if (P.Y && lane == 0) P.Y[((size_t)b * P.M + mi) * k + l0 + l] = sacc;
+        }
+    }
+    if (!want_j) return;
+    __syncwarp();
+    double* J = P.J + ((size_t)b * P.M + mi) * k * n;
+    for (int c = lane; c < n; c += 32) {
+        const double xc = xs[c];
+        for (int l0 = 0; l0 < k; l0 += 4) {
+            const int kk = min(4, k - l0);
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = 0; i < N; ++i) {
+                const double dc = xc - centers[(size_t)i * n + c];
+                for (int l = 0; l < kk; ++l) a[l] = fma(sw[i * k + l0 + l], dc, a[l]);
+            }
+            for (int l = 0; l < kk; ++l) J[(size_t)(l0 + l) * n + c] = a[l] + ((P.deg >= 1) ? lam[(size_t)(c + 1) * k + l0 + l] : 0.0);
+        }
+    }
+}
+
 // Generic kernel: one thread per trial point, any n; outputs processed four at a time.
 __global__ void __launch_bounds__(128) eval_generic_kernel(EvalParams P) {
     const int b = blockIdx.y, n = P.n, k = P.k;
@@ -680,6 +749,18 @@ static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launc
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
     if (P.M <= 0 || P.B <= 0) return cudaSuccess;
     const bool want_j = P.J != nullptr;
+    {   // a handful of points per instance: one warp per point
+        const int wd = P.n + P.train_stride * P.k;
+        const long long q = (long long)P.B * P.M;
+        if (P.M <= 8 && (size_t)4 * wd * sizeof(double) <= 96 * 1024 && (q + 3) / 4 < 2147483647LL) {
+            const size_t smem = (size_t)4 * wd * sizeof(double);
+            cudaError_t e = cudaFuncSetAttribute(eval_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            eval_small_kernel<<<(unsigned)((q + 3) / 4), 128, smem, s>>>(P, wd);
+            if (n_launches) ++*n_launches;
+            return cudaGetLastError();
+        }
+    }
     if (P.pack && P.n <= 64 && P.B <= 65535 && P.k <= 16) return want_j ? launch_dmma_jac(P, s, n_launches) : launch_dmma(P, s, n_launches);
     if (P.n <= 64 && P.B <= 65535) {
         const int cq = (P.n + 15) / 16;
