@@ -102,6 +102,15 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def host_threads() -> int:
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1; the oracle's OpenMP loops take an explicit thread
+    count, so the CPU arm still uses every core of the box (only rank 0 runs it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(cfg, host, n_threads, budget_s=12.0):
     """The oracle's C port (structure-exploiting restatement, oracle/rbf_oracle.c) on the host cores, one instance per
     thread, on a bounded sample of the same instances."""
@@ -316,7 +325,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as CO
-        nthr = min(os.cpu_count() or 1, CO.max_threads())
+        nthr = host_threads()
         v, sample = cpu_baseline(cfg, host, nthr)
         cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
                "sample": f"first {sample} instances of the same batch, one instance per thread; C port of the reference path "
@@ -353,7 +362,7 @@ def run_reference(args):
     from morbit_jl_b200 import synthetic
     from morbit_jl_b200.surrogate import RbfConfig
     from oracle import c_oracle as CO
-    nthr = min(os.cpu_count() or 1, CO.max_threads())
+    nthr = host_threads()
     cfg = RbfConfig(kernel=KERNEL)
     sample = max(nthr, min(args.instances, args.ref_sample))
     host = synthetic.multistart_batch(sample, n=N_VARS, n_db=N_DB, delta=DELTA, delta_max=DELTA_MAX, func=synthetic.zdt3)
