@@ -328,3 +328,49 @@ def test_host_pipeline_overlapped_copies_match_oracle(engine):
     assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
     for m in models:
         m.free()
+
+
+def test_c3_full_size_properties(engine):
+    """BASELINE config C3 at full size (4096 instances, n = 30, k = 2, 128 database sites): size-independent properties of the
+    whole batch plus exact parity with the oracle on a sample of instances."""
+    import torch
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import MultistartBuilder, upload_batch
+    B, n, n_db, k = 4096, 30, 128, 2
+    cfg = mb.RbfConfig(kernel="multiquadric")
+    host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=0.1, delta_max=0.5, func=synthetic.zdt3)
+    dev = upload_batch(host, "cuda:0")
+    builder = MultistartBuilder(engine, cfg, host["delta_max"])
+    model, sel, status = builder.step(dev)
+    model, sel, status = builder.step(dev, recycle=model)            # second pass: recycled handles give the same answer
+    engine.sync()
+    assert int((status != 0).sum().item()) == 0
+    r = {a: getattr(sel, a).cpu().numpy() for a in ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "r3_sites")}
+    mp = mb.max_model_points(cfg, n)
+    Ntrain = 1 + r["n_r1"] + r["n_r2"] + r["n_r3"] + r["n_r4"]
+    assert np.all(r["n_r4"] >= 0) and np.all(Ntrain <= mp) and np.all(r["n_r1"] + r["n_r2"] + r["n_r3"] <= n)
+    for b in range(0, B, 7):
+        ids = np.concatenate([[host["x_index"][b]], r["r1"][b, :r["n_r1"][b]], r["r2"][b, :r["n_r2"][b]], r["r4"][b, :r["n_r4"][b]]])
+        assert len(set(ids.tolist())) == len(ids) and ids.min() >= 1 and ids.max() <= n_db       # a training set has no duplicates
+        r4 = r["r4"][b, :r["n_r4"][b]]
+        assert np.all(np.diff(r4) > 0)                    # round 4 walks the candidates in ascending id order (RbfModel.jl:404-406)
+    # interpolation at every training site of every instance (the defining property of the model, test/rbf_models.jl:104)
+    w, lam = model.coeffs()
+    assert np.all(np.isfinite(w)) and np.all(np.isfinite(lam))
+    X = np.zeros((B, 8, n)); Yref = np.zeros((B, 8, k))
+    rng = np.random.default_rng(0)
+    for b in range(B):
+        ids = np.concatenate([[host["x_index"][b]], r["r1"][b, :r["n_r1"][b]], r["r2"][b, :r["n_r2"][b]], r["r4"][b, :r["n_r4"][b]]]) - 1
+        pick = rng.choice(ids, size=8, replace=len(ids) < 8)
+        X[b] = host["sites"][b, pick]; Yref[b] = host["values"][b, pick]
+    Y, _ = engine.eval(model, X, True, False)
+    assert np.abs(Y - Yref).max() <= 1e-8 * max(1.0, np.abs(Yref).max()), np.abs(Y - Yref).max()
+    # exact parity with the oracle on a sample
+    sample = np.arange(0, B, 64)
+    ref = CO.select_points_batched(cfg, host["sites"][sample], host["x_index"][sample], host["x"][sample], host["delta"][sample],
+                                   host["delta_max"], host["glb"], host["gub"], False, False, host["max_new"][sample], nthreads=8)
+    for j, b in enumerate(sample):
+        for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+            assert list(r[nm][b, :r[cnt][b]]) == list(getattr(ref, nm)[j, :getattr(ref, cnt)[j]]), (b, nm)
+        assert r["n_r3"][b] == ref.n_r3[j]
+    model.free()
