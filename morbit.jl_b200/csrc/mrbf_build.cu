@@ -37,11 +37,19 @@ __device__ void chol_lower(double* A, int ld, int off, int m, double* red) {
         const int rem = m - c - 1;
         for (int i = tid; i < rem; i += nt) A[pc + 1 + i + (size_t)pc * ld] /= dd;
         __syncthreads();
-        for (int e = tid; e < rem * rem; e += nt) {
-            const int i = e % rem, l = e / rem;
-            if (i >= l) {
-                const int gi = pc + 1 + i, gl = pc + 1 + l;
-                A[gi + (size_t)gl * ld] = fma(-A[gi + (size_t)pc * ld], A[gl + (size_t)pc * ld], A[gi + (size_t)gl * ld]);
+        {   // trailing update, lower triangle only: a warp per column, lanes down the rows (coalesced, no index divisions)
+            const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+            const double* colp = A + (size_t)pc * ld + pc + 1;
+            for (int l = warp; l < rem; l += nwarps) {
+                const double al = colp[l];
+                double* dst = A + (size_t)(pc + 1 + l) * ld + pc + 1;
+                int i = l + lane;
+                for (; i + 96 < rem; i += 128) {             // four independent load pairs in flight per lane
+                    const double c0 = colp[i], c1 = colp[i + 32], c2 = colp[i + 64], c3 = colp[i + 96];
+                    const double d0 = dst[i], d1 = dst[i + 32], d2 = dst[i + 64], d3 = dst[i + 96];
+                    dst[i] = fma(-c0, al, d0); dst[i + 32] = fma(-c1, al, d1); dst[i + 64] = fma(-c2, al, d2); dst[i + 96] = fma(-c3, al, d3);
+                }
+                for (; i < rem; i += 32) dst[i] = fma(-colp[i], al, dst[i]);
             }
         }
         __syncthreads();
@@ -74,7 +82,10 @@ __device__ void chol_solve(const double* A, int ld, int off, int m, double* Yv, 
     }
 }
 
-__global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
+// NT = 256 for batches (one CTA per system, many systems per SM-wave); NT = 1024 when only a few large systems are built and
+// the L2 latency of the global workspace, not the number of CTAs, limits the time.
+template <int NT>
+__global__ void __launch_bounds__(NT) build_kernel(BuildParams P) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, k = P.k, p = P.p;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -112,12 +123,27 @@ __global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
     }
     if (tid == 0) red[74] = 0.0;
     // ---- assembly (Gram matrix, polynomial block, right-hand sides)
-    for (int e = tid; e < N * N; e += nt) {
-        const int i = e % N, j = e / N;
-        const double* si = sites + (size_t)i * n; const double* sj = sites + (size_t)j * n;
-        double r2 = 0.0;
-        for (int c = 0; c < n; ++c) { double d = si[c] - sj[c]; r2 = fma(d, d, r2); }
-        A[i + (size_t)j * ld] = rad_phi(rf, r2);
+    {
+        // when the system itself lives in the global workspace, the (otherwise idle) shared memory stages the sites: the
+        // row-per-thread reads of the distance loop are uncoalesced in global memory
+        const double* sp = sites;
+        if (!in_smem && (size_t)N * n <= (size_t)P.smem_ws_doubles) {
+            for (int e = tid; e < N * n; e += nt) mats[e] = sites[e];
+            __syncthreads();
+            sp = mats;
+        }
+        for (int j = warp; j < N; j += nwarps) {             // a warp per column, lanes down the rows: lower triangle, then mirror
+            const double* sj = sp + (size_t)j * n;
+            for (int i = j + lane; i < N; i += 32) {
+                const double* si = sp + (size_t)i * n;
+                double r2 = 0.0;
+                for (int c = 0; c < n; ++c) { const double d = si[c] - sj[c]; r2 = fma(d, d, r2); }
+                const double ph = rad_phi(rf, r2);
+                A[i + (size_t)j * ld] = ph;
+                A[j + (size_t)i * ld] = ph;
+            }
+        }
+        __syncthreads();                                      // the staging area may be reused below
     }
     for (int e = tid; e < N * p; e += nt) { const int i = e % N, c = e / N; Pm[i + (size_t)c * ld] = (c == 0) ? 1.0 : sites[(size_t)i * n + c - 1]; }
     for (int e = tid; e < N * k; e += nt) { const int i = e % N, q = e / N; Yv[i + (size_t)q * ld] = values[(size_t)i * k + q]; }
@@ -183,6 +209,13 @@ __global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
         for (int i = tid; i < N; i += nt) {
             double a0 = 0.0, a1 = 0.0;
             int l = j;
+            for (; l + 8 <= N; l += 8) {                     // eight loads in flight per thread
+                const double* ap = A + i + (size_t)l * ld;
+                const double x0 = ap[0], x1 = ap[ld], x2 = ap[2 * (size_t)ld], x3 = ap[3 * (size_t)ld];
+                const double x4 = ap[4 * (size_t)ld], x5 = ap[5 * (size_t)ld], x6 = ap[6 * (size_t)ld], x7 = ap[7 * (size_t)ld];
+                a0 = fma(x0, v[l], a0); a1 = fma(x1, v[l + 1], a1); a0 = fma(x2, v[l + 2], a0); a1 = fma(x3, v[l + 3], a1);
+                a0 = fma(x4, v[l + 4], a0); a1 = fma(x5, v[l + 5], a1); a0 = fma(x6, v[l + 6], a0); a1 = fma(x7, v[l + 7], a1);
+            }
             for (; l + 2 <= N; l += 2) { a0 = fma(A[i + (size_t)l * ld], v[l], a0); a1 = fma(A[i + (size_t)(l + 1) * ld], v[l + 1], a1); }
             for (; l < N; ++l) a0 = fma(A[i + (size_t)l * ld], v[l], a0);
             const double a = tau * (a0 + a1);
@@ -192,9 +225,16 @@ __global__ void __launch_bounds__(256) build_kernel(BuildParams P) {
         const double K = 0.5 * tau * block_sum(part2, red);
         for (int i = tid; i < N; i += nt) pv[i] = fma(-K, v[i], pv[i]);
         __syncthreads();
-        for (int e = tid; e < N * N; e += nt) {
-            const int i = e % N, l = e / N;
-            if (i >= j || l >= j) A[i + (size_t)l * ld] -= v[i] * pv[l] + pv[i] * v[l];
+        for (int l = warp; l < N; l += nwarps) {            // rank-2 update, a warp per column (v is zero above row j)
+            const double vl = v[l], pl_ = pv[l];
+            double* dst = A + (size_t)l * ld;
+            int i = ((l >= j) ? 0 : j) + lane;
+            for (; i + 96 < N; i += 128) {
+                const double d0 = dst[i], d1 = dst[i + 32], d2 = dst[i + 64], d3 = dst[i + 96];
+                dst[i] = d0 - (v[i] * pl_ + pv[i] * vl); dst[i + 32] = d1 - (v[i + 32] * pl_ + pv[i + 32] * vl);
+                dst[i + 64] = d2 - (v[i + 64] * pl_ + pv[i + 64] * vl); dst[i + 96] = d3 - (v[i + 96] * pl_ + pv[i + 96] * vl);
+            }
+            for (; i < N; i += 32) dst[i] -= v[i] * pl_ + pv[i] * vl;
         }
         __syncthreads();
     }
@@ -512,9 +552,12 @@ size_t build_vec_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; 
 size_t build_ws_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return (size_t)ld * ld + (size_t)ld * pl + (size_t)ld * k; }
 
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool few_large = P.B <= 148 && !P.ws_in_smem;
+    cudaError_t e = few_large ? cudaFuncSetAttribute(build_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(build_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    build_kernel<<<P.B, 256, smem, s>>>(P);
+    if (few_large) build_kernel<1024><<<P.B, 1024, smem, s>>>(P);
+    else build_kernel<256><<<P.B, 256, smem, s>>>(P);
     return cudaGetLastError();
 }
 
