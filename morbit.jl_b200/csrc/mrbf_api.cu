@@ -621,7 +621,9 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
         Q.values = db_values; Q.r3_values = r3_values; Q.alpha2 = alpha * alpha;
         Q.centers = m->centers; Q.w = m->w; Q.lam = m->lam; Q.alpha2_out = m->alpha2; Q.N = m->N; Q.status = status; Q.done = (int*)skip_from_prepared;
         const size_t psm = build_prepared_smem_doubles(n, k, kp->NM, kp->p) * sizeof(double);
+        const size_t ssm = build_prepared_stream_smem_doubles(n, k, kp->NM, kp->p) * sizeof(double);
         if (psm <= SMEM_LIMIT) { Timed t_(ctx, 6); e = launch_build_prepared(Q, psm, ctx->stream); ctx->launches += 1; }
+        else if (ssm <= SMEM_LIMIT) { Timed t_(ctx, 6); e = launch_build_prepared_stream(Q, ssm, ctx->stream); ctx->launches += 1; }   // L^-1 streamed
         else e = cudaMemsetAsync((void*)skip_from_prepared, 0, sizeof(int) * (size_t)B, ctx->stream);
     } else if (e == cudaSuccess && kp) {
         e = cudaMemsetAsync((void*)skip_from_prepared, 0, sizeof(int) * (size_t)B, ctx->stream);

@@ -384,6 +384,126 @@ __global__ void __launch_bounds__(256) build_prepared_kernel(PreparedBuildParams
     if (tid == 0) { P.N[b] = N; P.alpha2_out[b] = P.alpha2; P.status[b] = 0; P.done[b] = 1; }
 }
 
+// The same build when the kept factorisation is too large for shared memory (large databases: m up to several hundred accepted
+// points, packed L^{-1} of ~1 MB per instance): L^{-1} is STREAMED from global memory, twice, row by row with coalesced reads --
+// pass 1: s = L^{-1} r (a warp per row, lanes along the row), pass 2: u = L^{-T} s as row axpys into per-warp partial sums.
+// Everything else is small and lives in shared memory.  Replaces an O(N^3) from-scratch solve per instance.
+__global__ void __launch_bounds__(256) build_prepared_stream_kernel(PreparedBuildParams P) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, n = P.n, k = P.k, p = P.p, NM = P.NM, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int pl = p > 0 ? p : 1, pb = pl | 1;
+    const int MM = (NM - p) > 1 ? (NM - p) : 1;
+    if (!P.elig[b]) { if (tid == 0) P.done[b] = 0; return; }
+    const double* fs = P.fs + (size_t)b * P.fs_stride;
+    const double inv_s = fs[P.fs_stride - 1];
+    const int N0 = (int)fs[P.fs_stride - 2], m = (int)fs[P.fs_stride - 3];
+    const int N = N0 + m;
+    const int base = (p > 0) ? p : N0;
+    const double* Ct = fs; const double* M0g = fs + P.off_M0; const double* Gg = fs + P.off_G; const double* Cg = fs + P.off_C;
+    const double* Lg = fs + P.off_L;
+    double* y = smem;                       // NM x k
+    double* rv = y + (size_t)NM * k;        // MM x k   r, later u
+    double* sv = rv + (size_t)MM * k;       // MM x k   s
+    double* t0 = sv + (size_t)MM * k;       // pl x k
+    double* up = t0 + (size_t)pl * k;       // nwarps x MM x k partial sums of pass 2
+    const int* found = P.found + (size_t)b * P.found_stride;
+    const int nf = P.n_found[b];
+    const int* r4 = P.r4 + (size_t)b * P.r4_stride;
+    const double* values = P.values + (size_t)b * P.db_stride * k;
+    const double* r3v = P.r3_values ? P.r3_values + (size_t)b * n * k : nullptr;
+    for (int e = tid; e < N * k; e += nt) {
+        const int i = e / k, q = e % k;
+        double val;
+        if (i < nf) val = values[(size_t)(found[i] - 1) * k + q];
+        else if (i < N0) val = r3v ? r3v[(size_t)(i - nf) * k + q] : 0.0;
+        else val = values[(size_t)(r4[i - N0] - 1) * k + q];
+        y[e] = val;
+    }
+    double* centers = P.centers + (size_t)b * P.train_stride * n;
+    for (int e = tid; e < N * n; e += nt) { const int i = e / n, c = e % n; centers[e] = Ct[(size_t)c * NM + i]; }
+    for (int e = tid; e < nwarps * m * k; e += nt) up[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < m * k; e += nt) {                  // r = Y_acc - C' Y_0
+        const int eta = e / k, q = e % k;
+        double a = y[(size_t)(base + eta) * k + q];
+        const double* ce = Cg + (size_t)eta * pb;
+        for (int r = 0; r < p; ++r) a = fma(-ce[r], y[(size_t)r * k + q], a);
+        rv[e] = a;
+    }
+    __syncthreads();
+    for (int r = warp; r < m; r += nwarps) {                 // pass 1: s_r = sum_{c <= r} Linv[r][c] r_c  (k <= 4 outputs at a time)
+        const double* lr = Lg + (((size_t)r * (r + 1)) >> 1);
+        for (int q0 = 0; q0 < k; q0 += 4) {
+            const int kk = min(4, k - q0);
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int c = lane; c <= r; c += 32) {
+                const double lv = lr[c];
+                for (int q = 0; q < kk; ++q) a[q] = fma(lv, rv[(size_t)c * k + q0 + q], a[q]);
+            }
+            for (int q = 0; q < kk; ++q) { const double t = warp_sum(a[q]); if (lane == 0) sv[(size_t)r * k + q0 + q] = t; }
+        }
+    }
+    __syncthreads();
+    {                                                        // pass 2: u_c = sum_{r >= c} Linv[r][c] s_r, accumulated per warp
+        double* mine = up + (size_t)warp * m * k;
+        for (int r = warp; r < m; r += nwarps) {
+            const double* lr = Lg + (((size_t)r * (r + 1)) >> 1);
+            for (int c = lane; c <= r; c += 32) {
+                const double lv = lr[c];
+                for (int q = 0; q < k; ++q) mine[(size_t)c * k + q] = fma(lv, sv[(size_t)r * k + q], mine[(size_t)c * k + q]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < m * k; e += nt) {
+        double a = 0.0;
+        for (int w = 0; w < nwarps; ++w) a += up[(size_t)w * m * k + e];
+        rv[e] = a;
+    }
+    __syncthreads();
+    double* w_out = P.w + (size_t)b * P.train_stride * k;
+    double* lam_out = P.lam + (size_t)b * pl * k;
+    for (int e = tid; e < m * k; e += nt) w_out[(size_t)base * k + e] = rv[e];
+    for (int e = warp; e < p * k; e += nwarps) {             // w_0 = -C u ; t0 = Y_0 - G u   (warp per entry, lanes over the accepted points)
+        const int r = e / k, q = e % k;
+        double a = 0.0, g = 0.0;
+        for (int eta = lane; eta < m; eta += 32) {
+            const double u = rv[(size_t)eta * k + q];
+            a = fma(Cg[(size_t)eta * pb + r], u, a); g = fma(Gg[(size_t)eta * pb + r], u, g);
+        }
+        a = warp_sum(a); g = warp_sum(g);
+        if (lane == 0) { w_out[(size_t)r * k + q] = -a; t0[e] = y[(size_t)r * k + q] - g; }
+    }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) {                  // lambda~ = M0' t0
+        const int c = e / k, q = e % k;
+        double a = 0.0;
+        for (int r = 0; r < p; ++r) a = fma(M0g[r + (size_t)c * pl], t0[(size_t)r * k + q], a);
+        sv[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < p * k; e += nt) {                  // back to the monomial basis (1, x_1..x_n)
+        const int c = e / k, q = e % k;
+        double val;
+        if (c == 0) { val = sv[q]; for (int j = 1; j < p; ++j) val = fma(-sv[(size_t)j * k + q] * inv_s, Ct[(size_t)(j - 1) * NM], val); }
+        else val = sv[e] * inv_s;
+        lam_out[e] = val;
+    }
+    if (tid == 0) { P.N[b] = N; P.alpha2_out[b] = P.alpha2; P.status[b] = 0; P.done[b] = 1; }
+}
+
+size_t build_prepared_stream_smem_doubles(int n, int k, int NM, int p) {
+    (void)n;
+    int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
+    return (size_t)NM * k + 2 * (size_t)MM * k + (size_t)pl * k + 8 * (size_t)MM * k + 8;
+}
+cudaError_t launch_build_prepared_stream(const PreparedBuildParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(build_prepared_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    build_prepared_stream_kernel<<<P.B, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
 size_t build_prepared_smem_doubles(int n, int k, int NM, int p) {
     int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
     return (size_t)NM * k + 2 * (size_t)MM * k + (size_t)pl * k + (size_t)MM * (MM + 1) / 2 + 2 * (size_t)pb * MM;

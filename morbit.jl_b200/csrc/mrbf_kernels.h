@@ -147,6 +147,8 @@ cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s);
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s);
 size_t build_prepared_smem_doubles(int n, int k, int NM, int p);
+cudaError_t launch_build_prepared_stream(const PreparedBuildParams& P, size_t smem, cudaStream_t s);
+size_t build_prepared_stream_smem_doubles(int n, int k, int NM, int p);
 cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStream_t s);
 size_t build_schur_smem_doubles(int k, int MC, int p);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);

@@ -374,3 +374,39 @@ def test_c3_full_size_properties(engine):
             assert list(r[nm][b, :r[cnt][b]]) == list(getattr(ref, nm)[j, :getattr(ref, cnt)[j]]), (b, nm)
         assert r["n_r3"][b] == ref.n_r3[j]
     model.free()
+
+
+def test_large_database_block_kernel_and_streamed_build(engine):
+    """Rich database (600 sites, n = 30): max_model_points = 496 training points.  Round 4 goes through round4_block_kernel (state in the
+    L2-resident workspace) and the model is built from its kept L^{-1}, streamed from global memory (build_prepared_stream_kernel)."""
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import MultistartBuilder, upload_batch
+    B, n, n_db = 3, 30, 600
+    cfg = mb.RbfConfig(kernel="multiquadric")
+    host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=0.1, func=synthetic.zdt3)
+    dev = upload_batch(host, "cuda:0")
+    builder = MultistartBuilder(engine, cfg, host["delta_max"])
+    model, sel, status = builder.step(dev)
+    engine.sync()
+    prof_before = engine.launch_count
+    assert np.all(status.cpu().numpy() == 0)
+    ref = CO.select_points_batched(cfg, host["sites"], host["x_index"], host["x"], host["delta"], host["delta_max"], host["glb"],
+                                   host["gub"], False, False, host["max_new"], nthreads=4)
+    res_np = {k: getattr(sel, k).cpu().numpy() for k in ("r1", "n_r1", "r2", "n_r2", "r3_sites", "n_r3", "r4", "n_r4")}
+    for b in range(B):
+        for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+            assert list(res_np[nm][b, :res_np[cnt][b]]) == list(getattr(ref, nm)[b, :getattr(ref, cnt)[b]]), (b, nm)
+    assert np.all(1 + res_np["n_r1"] + res_np["n_r2"] + res_np["n_r3"] + res_np["n_r4"] == mb.max_model_points(cfg, n))
+    oracle = _oracle_models(cfg, host, res_np)
+    X = host["x"][:, None, :] + 0.1 * (np.random.default_rng(0).random((B, 9, n)) - 0.5)
+    Y, J = engine.eval(model, X, True, True)
+    for b, (P, w, lam) in enumerate(oracle):
+        Yr = CO.eval_points(cfg, P, w, lam, X[b]); Jr = CO.jac_points(cfg, P, w, lam, X[b])
+        # 496 multiquadric centres in a small box: cond ~ 1e12, the two solution routes differ at cond * eps
+        assert np.abs(Y[b] - Yr).max() <= 1e-6 * np.abs(Yr).max(), (b, np.abs(Y[b] - Yr).max() / np.abs(Yr).max())
+        assert np.abs(J[b] - Jr).max() <= 1e-4 * np.abs(Jr).max(), (b, np.abs(J[b] - Jr).max() / np.abs(Jr).max())
+    # interpolation at the training sites is the sharper check of the streamed solve
+    for b, (P, w, lam) in enumerate(oracle):
+        Yt, _ = engine.eval(model, np.repeat(P[None, :8], B, axis=0), True, False)
+        assert np.abs(Yt[b] - synthetic.zdt3(P[:8])).max() <= 1e-7, np.abs(Yt[b] - synthetic.zdt3(P[:8])).max()
+    model.free()
