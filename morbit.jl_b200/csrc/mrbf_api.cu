@@ -370,7 +370,7 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     S.flags_in = flags_in; S.max_new = max_new;
     S.r1 = r1; S.n_r1 = n_r1; S.r2 = r2; S.n_r2 = n_r2; S.r3_sites = r3_sites; S.n_r3 = n_r3; S.dirs = dirs; S.n_dirs = n_dirs;
     S.flags_out = flags_out;
-    const int ldz = n | 1;
+    const int ldz = (n + 3) & ~3;
     S.wz_in_smem = select_smem_bytes(n, true, 0, db_stride) <= SMEM_LIMIT;
     // projection coefficients (n x ldS doubles, ldS = db_stride rounded up to even) stay in shared memory when three CTAs
     // still fit per SM; the shifted seeds always live in the global workspace

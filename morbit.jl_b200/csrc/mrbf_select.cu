@@ -72,6 +72,23 @@ struct FilterState {
 #define CF_BOX2 2
 #define CF_USED 4
 
+// Block arg-max over non-negative scores with "first maximiser" tie-breaking (smallest position wins), one barrier: the warp stage
+// compares the scores as integers with redux.sync (IEEE doubles >= 0 order like their bit patterns), the eight warp winners are
+// combined by every thread.  `par` alternates the scratch slots so that consecutive calls need no protective barrier.
+__device__ __forceinline__ ArgMax block_argmax_pos(ArgMax m, double* redv, int* redi, int par) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const double v = (m.id >= 0) ? m.v : 0.0;
+    const unsigned vh = (unsigned)__double2hiint(v), vl = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, vh);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
+    const unsigned mid = __reduce_min_sync(0xffffffffu, (vh == mh && vl == ml && m.id >= 0) ? (unsigned)m.id : 0x7fffffffu);
+    if (lane == 0) { redv[par * 16 + warp] = __hiloint2double((int)mh, (int)ml); redi[par * 16 + warp] = (mid == 0x7fffffffu) ? -1 : (int)mid; }
+    __syncthreads();
+    ArgMax r; r.v = 0.0; r.id = -1;
+    for (int w = 0; w < nw; ++w) { ArgMax c_; c_.v = redv[par * 16 + w]; c_.id = redi[par * 16 + w]; r = better(r, c_); }
+    return r;
+}
+
 // One run of the affinely-independent filter over the candidates with (cflags & want) == want and
 // !(cflags & (CF_USED | avoid)).  Picks are appended to out[]; returns their number.
 //
@@ -128,7 +145,8 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
             }
         }
     }
-    ArgMax best = block_argmax(mine, st.red, st.redi);
+    int apar = 0;
+    ArgMax best = block_argmax_pos(mine, st.red, st.redi, apar); apar ^= 1;
     const int RQ = (n + 3) >> 2;                  // row quads of the scoring GEMM
     int RQ2 = 1; while (RQ2 < RQ && RQ2 < 32) RQ2 <<= 1;
     for (;;) {
@@ -210,7 +228,6 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
                 if (cq < CQ)
                     for (int rq = rq0; rq < RQ; rq += RQ2) {
                         const int i0 = 4 * rq;
-                        const bool r1 = i0 + 1 < n, r2 = i0 + 2 < n, r3 = i0 + 3 < n;
                         double acc[4][4];
 #pragma unroll
                         for (int a_ = 0; a_ < 4; ++a_)
@@ -218,7 +235,8 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
                             for (int c_ = 0; c_ < 4; ++c_) acc[a_][c_] = 0.0;
                         const double* wp = Wt + i0; const double* yp = T + 4 * cq;
                         for (int q = 0; q < zc; ++q) {
-                            const double w0 = wp[q * ldz], w1 = r1 ? wp[q * ldz + 1] : 0.0, w2 = r2 ? wp[q * ldz + 2] : 0.0, w3 = r3 ? wp[q * ldz + 3] : 0.0;
+                            const double2 wa = *reinterpret_cast<const double2*>(wp + q * ldz), wb = *reinterpret_cast<const double2*>(wp + q * ldz + 2);
+                            const double w0 = wa.x, w1 = wa.y, w2 = wb.x, w3 = wb.y;      // rows >= n of Wt are zero
                             const double2 ya = *reinterpret_cast<const double2*>(yp + q * ldS), yb = *reinterpret_cast<const double2*>(yp + q * ldS + 2);
                             acc[0][0] = fma(w0, ya.x, acc[0][0]); acc[0][1] = fma(w0, ya.y, acc[0][1]); acc[0][2] = fma(w0, yb.x, acc[0][2]); acc[0][3] = fma(w0, yb.y, acc[0][3]);
                             acc[1][0] = fma(w1, ya.x, acc[1][0]); acc[1][1] = fma(w1, ya.y, acc[1][1]); acc[1][2] = fma(w1, yb.x, acc[1][2]); acc[1][3] = fma(w1, yb.y, acc[1][3]);
@@ -244,7 +262,7 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
                 }
             }
         }
-        best = block_argmax(mine, st.red, st.redi);
+        best = block_argmax_pos(mine, st.red, st.redi, apar); apar ^= 1;
         if (best.id < 0) break;                   // no more candidates
         if (!(best.v > piv)) break;               // AffinelyIndependentPoints.jl:92
     }
@@ -267,7 +285,7 @@ template <bool WZS, bool STS>   // W/Z in shared memory; projections in shared m
 __global__ void __launch_bounds__(256, 3) select_rounds123_kernel(SelectParams P) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x;
-    const int ldz = n | 1;
+    const int ldz = (n + 3) & ~3;              // rows padded to a multiple of 4 (zero rows): the scoring tiles load row quads
     double* x = smem;
     double* lb1 = x + n; double* ub1 = lb1 + n; double* lb2 = ub1 + n; double* ub2 = lb2 + n;
     double* xp = ub2 + n; double* u = xp + n; double* vv = u + n;
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(256, 3) select_rounds123_kernel(SelectParams P
     bool fully_linear;
     for (;;) {   // at most two passes: the second is the coordinate rebuild (RbfModel.jl:634-637)
         __syncthreads();
-        for (int e = tid; e < n * n; e += nt) { int i = e % n, c = e / n; W[i + c * ldz] = (i == c) ? 1.0 : 0.0; Z[i + c * ldz] = (i == c) ? 1.0 : 0.0; }
+        for (int e = tid; e < ldz * n; e += nt) { int i = e % ldz, c = e / ldz; W[i + c * ldz] = (i == c) ? 1.0 : 0.0; Z[i + c * ldz] = (i == c) ? 1.0 : 0.0; }
         for (int id = tid; id < n_db; id += nt) cflags[id] &= (unsigned char)~CF_USED;
         __syncthreads();
         st.jY = 0; n_r1 = n_r2 = n_r3 = 0; fully_linear = false;
@@ -1437,7 +1455,7 @@ __global__ void gather_training_kernel(GatherParams P) {
 // ------------------------------------------------------------------------------------------------
 size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride) {
     size_t d = 8 * (size_t)n + 80 + 24 + 2 * (((size_t)db_stride + 3) / 4);
-    if (wz_in_smem) d += 2 * (size_t)n * (n | 1) + (size_t)st_doubles;
+    if (wz_in_smem) d += 2 * (size_t)n * ((n + 3) & ~3) + (size_t)st_doubles;
     return d * sizeof(double);
 }
 size_t round4_vec_doubles(int n, int NM, int p) { int pl = p > 0 ? p : 1; return (size_t)n + 5 * (size_t)NM + 4 * (size_t)pl + 80; }
