@@ -255,3 +255,46 @@ def test_c4_n200_quadratic_select_and_build(engine):
         assert np.abs(Y[0] - Yr).max() <= 1e-10 * np.abs(Yr).max()
         assert np.abs(J[0] - Jr).max() <= tol * np.abs(Jr).max(), (cond, np.abs(J[0] - Jr).max() / np.abs(Jr).max())
         model.free()
+
+
+def test_reentrant_contexts_from_concurrent_threads():
+    """The reference's benchmark driver runs many optimize() calls under Threads.@threads (examples/large_scale_benchmarks.jl:253):
+    the plugin is entered from several host threads at once, each with its own context.  Two threads, two contexts, interleaved
+    select -> build -> eval calls must give exactly what the same calls give serially (no global mutable state in the library)."""
+    import threading
+    from morbit_jl_b200 import synthetic
+
+    def work(seed, out):
+        eng = mb.Engine(0)
+        cfg = mb.RbfConfig(kernel="cubic" if seed % 2 else "multiquadric")
+        res_all = []
+        for rep in range(6):
+            h = synthetic.multistart_batch(5, n=8 + seed, n_db=40 + 7 * rep, delta=0.1, func=synthetic.zdt3, local_fraction=0.5,
+                                           first_instance=100 * seed + rep)
+            res = eng.select_points(cfg, h["sites"], h["n_db"], h["x_index"], h["x"], h["delta"], h["delta_max"], h["glb"], h["gub"])
+            n = h["sites"].shape[2]
+            N = 1 + res.n_r1 + res.n_r2 + res.n_r3 + res.n_r4
+            ts = int(N.max())
+            S = np.zeros((5, ts, n)); V = np.zeros((5, ts, 2))
+            for b in range(5):
+                ids = [int(h["x_index"][b])] + list(res.r1[b, :res.n_r1[b]]) + list(res.r2[b, :res.n_r2[b]])
+                P = np.vstack([h["sites"][b, np.array(ids) - 1], res.r3_sites[b, :res.n_r3[b]].reshape(-1, n),
+                               h["sites"][b, res.r4[b, :res.n_r4[b]].astype(int) - 1].reshape(-1, n)])
+                S[b, :len(P)] = P; V[b, :len(P)] = synthetic.zdt3(P)
+            model, status = eng.build(cfg, S, V, N)
+            Y, J = eng.eval(model, h["x"][:, None, :], True, True)
+            res_all.append((res.r1.copy(), res.r4.copy(), res.n_r4.copy(), Y.copy(), J.copy()))
+            model.free()
+        out[seed] = res_all
+        eng.close()
+
+    serial, threaded = {}, {}
+    for s_ in (1, 2):
+        work(s_, serial)
+    ths = [threading.Thread(target=work, args=(s_, threaded)) for s_ in (1, 2)]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    for s_ in (1, 2):
+        for a, b in zip(serial[s_], threaded[s_]):
+            for x_, y_ in zip(a, b):
+                assert np.array_equal(x_, y_)
