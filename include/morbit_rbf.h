@@ -133,6 +133,14 @@ int mrbf_select_points_keep_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, i
                                 int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
                                 int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
                                 int32_t* flags_out, int32_t* status, mrbf_prepared** prepared);
+/* Host-pointer twins (what the Julia shim of a single optimize() run calls): same arguments, host memory. */
+int mrbf_select_points_keep(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                            const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                            const double* delta, double delta_max, const double* glb, const double* gub,
+                            const int32_t* flags_in, const int32_t* max_new,
+                            int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                            int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                            int32_t* flags_out, int32_t* status, mrbf_prepared** prepared);
 void mrbf_free_prepared(mrbf_ctx* ctx, mrbf_prepared* prepared);
 /* update_model from a kept factorisation.  values: B x db_stride x k (database values, same ids as `sites`),
  * r3_values: B x n x k values of the new round-3 sites (may be NULL when there are none).  Instances whose round 4
@@ -142,6 +150,11 @@ int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepa
                             const double* sites, const double* values, const double* r3_sites, const double* r3_values,
                             const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
                             const int32_t* n_r3, mrbf_model** model, int32_t* status);
+
+int mrbf_build_prepared(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* prepared, int32_t k,
+                        const double* sites, const double* values, const double* r3_sites, const double* r3_values,
+                        const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                        const int32_t* n_r3, mrbf_model** model, int32_t* status);
 
 /* _rbf_round4 alone with an explicit found set (used after _exploit_other_rbf_metas!, RbfModel.jl:311-342, 562,
  * and called directly by test/rbf_models.jl:74-86).  found: B x found_stride ids (centre first), n_found: B;

@@ -47,6 +47,9 @@ SIGNATURES = {
                                + [_vp] * 6 + [_i32] + [_vp] * 6),
     "mrbf_select_points_keep_dev": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32] + [_vp] * 4 + [_vp, _f64] + [_vp] * 4
                                     + [_vp] * 6 + [_i32] + [_vp] * 6 + [C.POINTER(_vp)]),
+    "mrbf_select_points_keep": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32] + [_vp] * 4 + [_vp, _f64] + [_vp] * 4
+                                + [_vp] * 6 + [_i32] + [_vp] * 6 + [C.POINTER(_vp)]),
+    "mrbf_build_prepared": (C.c_int, [_vp, C.POINTER(MrbfCfg), _vp, _i32] + [_vp] * 10 + [C.POINTER(_vp), _vp]),
     "mrbf_free_prepared": (None, [_vp, _vp]),
     "mrbf_build_prepared_dev": (C.c_int, [_vp, C.POINTER(MrbfCfg), _vp, _i32] + [_vp] * 10 + [C.POINTER(_vp), _vp]),
     "mrbf_round4": (C.c_int, [_vp, C.POINTER(MrbfCfg), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp,

@@ -431,13 +431,13 @@ void mrbf_free_prepared(mrbf_ctx* ctx, mrbf_prepared* kp) {
 #define H2D(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
 #define D2H(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
 
-int mrbf_select_points(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+static int select_points_host(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
                        const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
                        const double* delta, double delta_max, const double* glb, const double* gub,
                        const int32_t* flags_in, const int32_t* max_new,
                        int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
                        int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
-                       int32_t* flags_out, int32_t* status) {
+                       int32_t* flags_out, int32_t* status, mrbf_prepared** keep) {
     if (!ctx) return MRBF_EINVAL;
     if (B <= 0 || n <= 0 || db_stride <= 0 || r4_stride < 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
     CK(cudaSetDevice(ctx->device));
@@ -454,9 +454,9 @@ int mrbf_select_points(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n,
     double* d_r3 = (double*)ctx->hb[4].p; double* d_dirs = d_r3 + (size_t)B * n * n;
     H2D(d_sites, sites, sites_b); H2D(d_ndb, n_db, sB); H2D(d_xi, x_index, sB); H2D(d_maxnew, max_new, sB); H2D(d_flags, flags_in, 2 * sB);
     H2D(d_x, x, dBn); H2D(d_delta, delta, sizeof(double) * (size_t)B); H2D(d_glb, glb, sizeof(double) * n); H2D(d_gub, gub, sizeof(double) * n);
-    int rc = mrbf_select_points_dev(ctx, cfg, B, n, db_stride, d_sites, d_ndb, d_xi, d_x, d_delta, delta_max, d_glb, d_gub, d_flags,
-                                    d_maxnew, d_r1, d_cnt, d_r2, d_cnt + B, d_r3, d_cnt + 2 * B, r4_stride, d_r4, d_cnt + 3 * B,
-                                    d_dirs, d_cnt + 4 * B, d_cnt + 5 * B, d_cnt + 7 * B);
+    int rc = select_points_impl(ctx, cfg, B, n, db_stride, d_sites, d_ndb, d_xi, d_x, d_delta, delta_max, d_glb, d_gub, d_flags,
+                                d_maxnew, d_r1, d_cnt, d_r2, d_cnt + B, d_r3, d_cnt + 2 * B, r4_stride, d_r4, d_cnt + 3 * B,
+                                d_dirs, d_cnt + 4 * B, d_cnt + 5 * B, d_cnt + 7 * B, keep);
     if (rc != MRBF_OK) return rc;
     D2H(r1, d_r1, sizeof(int) * (size_t)B * n); D2H(r2, d_r2, sizeof(int) * (size_t)B * n);
     if (r4_stride > 0) D2H(r4, d_r4, sizeof(int) * (size_t)B * r4_stride);
@@ -466,6 +466,29 @@ int mrbf_select_points(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n,
     D2H(r3_sites, d_r3, sizeof(double) * (size_t)B * n * n); D2H(dirs, d_dirs, sizeof(double) * (size_t)B * n * n);
     CK(cudaStreamSynchronize(ctx->stream));
     return MRBF_OK;
+}
+
+int mrbf_select_points(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                       const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                       const double* delta, double delta_max, const double* glb, const double* gub,
+                       const int32_t* flags_in, const int32_t* max_new,
+                       int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                       int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                       int32_t* flags_out, int32_t* status) {
+    return select_points_host(ctx, cfg, B, n, db_stride, sites, n_db, x_index, x, delta, delta_max, glb, gub, flags_in, max_new,
+                              r1, n_r1, r2, n_r2, r3_sites, n_r3, r4_stride, r4, n_r4, dirs, n_dirs, flags_out, status, nullptr);
+}
+
+int mrbf_select_points_keep(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
+                            const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
+                            const double* delta, double delta_max, const double* glb, const double* gub,
+                            const int32_t* flags_in, const int32_t* max_new,
+                            int32_t* r1, int32_t* n_r1, int32_t* r2, int32_t* n_r2, double* r3_sites, int32_t* n_r3,
+                            int32_t r4_stride, int32_t* r4, int32_t* n_r4, double* dirs, int32_t* n_dirs,
+                            int32_t* flags_out, int32_t* status, mrbf_prepared** prepared) {
+    if (!prepared) return MRBF_EINVAL;
+    return select_points_host(ctx, cfg, B, n, db_stride, sites, n_db, x_index, x, delta, delta_max, glb, gub, flags_in, max_new,
+                              r1, n_r1, r2, n_r2, r3_sites, n_r3, r4_stride, r4, n_r4, dirs, n_dirs, flags_out, status, prepared);
 }
 
 int mrbf_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
@@ -667,6 +690,34 @@ int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepa
     { Timed t_(ctx, 2); CK(launch_gather_training(G, ctx->stream)); }
     ctx->launches += 1;
     return build_impl(ctx, cfg, B, n, k, ts, Ntmp, tsit, tval, nullptr, out, status, kp, values, r3_values, done, sites, r3_sites);
+}
+
+int mrbf_build_prepared(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
+                        const double* sites, const double* values, const double* r3_sites, const double* r3_values,
+                        const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                        const int32_t* n_r3, mrbf_model** out, int32_t* status) {
+    if (!ctx || !kp || !out || !cfg || !sites || !values || !x_index || !r1 || !n_r1 || !r2 || !n_r2 || !n_r3) return MRBF_EINVAL;
+    if (k <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    const int B = kp->B, n = kp->n, dbs = kp->db_stride;
+    const size_t sb = sizeof(double) * (size_t)B * dbs * n, vb = sizeof(double) * (size_t)B * dbs * k;
+    const size_t r3s = sizeof(double) * (size_t)B * n * n, r3v = sizeof(double) * (size_t)B * n * k, sB = sizeof(int) * (size_t)B;
+    ENSURE(ctx->hb[21], sb + vb + r3s + r3v); ENSURE(ctx->hb[22], sB * 5 + 2 * sizeof(int) * (size_t)B * n);
+    double* d_s = (double*)ctx->hb[21].p; double* d_v = d_s + (size_t)B * dbs * n; double* d_r3s = d_v + (size_t)B * dbs * k;
+    double* d_r3v = d_r3s + (size_t)B * n * n;
+    int* d_xi = (int*)ctx->hb[22].p; int* d_n1 = d_xi + B; int* d_n2 = d_n1 + B; int* d_n3 = d_n2 + B; int* d_st = d_n3 + B;
+    int* d_r1 = d_st + B; int* d_r2 = d_r1 + (size_t)B * n;
+    H2D(d_s, sites, sb); H2D(d_v, values, vb);
+    if (r3_sites) H2D(d_r3s, r3_sites, r3s); else CK(cudaMemsetAsync(d_r3s, 0, r3s, ctx->stream));
+    if (r3_values) H2D(d_r3v, r3_values, r3v); else CK(cudaMemsetAsync(d_r3v, 0, r3v, ctx->stream));
+    H2D(d_xi, x_index, sB); H2D(d_n1, n_r1, sB); H2D(d_n2, n_r2, sB); H2D(d_n3, n_r3, sB);
+    H2D(d_r1, r1, sizeof(int) * (size_t)B * n); H2D(d_r2, r2, sizeof(int) * (size_t)B * n);
+    int rc = mrbf_build_prepared_dev(ctx, cfg, kp, k, d_s, d_v, d_r3s, d_r3v, d_xi, d_r1, d_n1, d_r2, d_n2, d_n3, out, d_st);
+    if (rc != MRBF_OK) return rc;
+    if (status) D2H(status, d_st, sB);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (status) for (int b = 0; b < B; ++b) if (status[b] != 0) return fail(ctx, MRBF_ENUMERIC, "at least one system failed; see status[]%s");
+    return MRBF_OK;
 }
 
 int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,

@@ -169,6 +169,57 @@ class Engine:
             _ptr(status)))
         return SelectResult(r1, cnt[0], r2, cnt[1], r3, cnt[2], r4, cnt[3], dirs, cnt[4], flags_out, status)
 
+    def select_points_keep(self, cfg, sites, n_db, x_index, x, delta, delta_max, glb, gub, ensure_fully_linear=False,
+                           force_rebuild=False, max_new=2**31 - 1, prepared: Optional["Prepared"] = None):
+        """select_points that also keeps the round-4 factorisation on the device (host buffers in and out); returns
+        (SelectResult, Prepared).  build_prepared turns the pair into the model without a from-scratch solve."""
+        sites = _np(sites, np.float64)
+        B, db_stride, n = sites.shape
+        n_db = _np(np.broadcast_to(n_db, (B,)), np.int32); x_index = _np(np.broadcast_to(x_index, (B,)), np.int32)
+        x = _np(x, np.float64).reshape(B, n); delta = _np(np.broadcast_to(delta, (B,)), np.float64)
+        glb = _np(np.broadcast_to(glb, (n,)), np.float64); gub = _np(np.broadcast_to(gub, (n,)), np.float64)
+        flags_in = _np(np.stack([np.broadcast_to(ensure_fully_linear, (B,)), np.broadcast_to(force_rebuild, (B,))], 1), np.int32)
+        max_new = _np(np.clip(np.broadcast_to(max_new, (B,)), 0, 2**31 - 1), np.int32)
+        mp = max_model_points(cfg, n)
+        r1 = np.zeros((B, n), np.int32); r2 = np.zeros((B, n), np.int32); r4 = np.zeros((B, mp), np.int32)
+        cnt = [np.zeros(B, np.int32) for _ in range(5)]
+        r3 = np.zeros((B, n, n)); dirs = np.zeros((B, n, n))
+        flags_out = np.zeros((B, 2), np.int32); status = np.zeros(B, np.int32)
+        ccfg = to_c_cfg(cfg)
+        handle = C.c_void_p(prepared.handle if prepared is not None else None)
+        if prepared is not None:
+            prepared.handle = None
+        self._check(self.lib.mrbf_select_points_keep(
+            self.ctx, C.byref(ccfg), B, n, db_stride, _ptr(sites), _ptr(n_db), _ptr(x_index), _ptr(x), _ptr(delta),
+            float(delta_max), _ptr(glb), _ptr(gub), _ptr(flags_in), _ptr(max_new), _ptr(r1), _ptr(cnt[0]), _ptr(r2),
+            _ptr(cnt[1]), _ptr(r3), _ptr(cnt[2]), mp, _ptr(r4), _ptr(cnt[3]), _ptr(dirs), _ptr(cnt[4]), _ptr(flags_out),
+            _ptr(status), C.byref(handle)))
+        res = SelectResult(r1, cnt[0], r2, cnt[1], r3, cnt[2], r4, cnt[3], dirs, cnt[4], flags_out, status)
+        if prepared is not None:
+            prepared.handle = handle.value
+            return res, prepared
+        return res, Prepared(self, handle.value)
+
+    def build_prepared(self, cfg, prepared: "Prepared", sites, values, x_index, sel: SelectResult, r3_values=None,
+                       recycle: Optional[ModelBatch] = None):
+        """update_model from the factorisation kept by select_points_keep (host buffers).  sites / values: the same database
+        arrays (B x db_stride x n / k) the selection saw; r3_values: B x n x k values of the new round-3 sites."""
+        sites = _np(sites, np.float64); values = _np(values, np.float64)
+        B, db_stride, n = sites.shape
+        k = values.shape[2]
+        x_index = _np(np.broadcast_to(x_index, (B,)), np.int32)
+        r3v = None if r3_values is None else _np(r3_values, np.float64).reshape(B, n, k)
+        status = np.zeros(B, np.int32)
+        handle = C.c_void_p(recycle.handle if recycle is not None else None)
+        if recycle is not None:
+            recycle.handle = None
+        ccfg = to_c_cfg(cfg)
+        self._check(self.lib.mrbf_build_prepared(
+            self.ctx, C.byref(ccfg), prepared.handle, k, _ptr(sites), _ptr(values), _ptr(_np(sel.r3_sites, np.float64)), _ptr(r3v),
+            _ptr(x_index), _ptr(_np(sel.r1, np.int32)), _ptr(_np(sel.n_r1, np.int32)), _ptr(_np(sel.r2, np.int32)),
+            _ptr(_np(sel.n_r2, np.int32)), _ptr(_np(sel.n_r3, np.int32)), C.byref(handle), _ptr(status)))
+        return ModelBatch(self, handle.value), status
+
     def round4(self, cfg, sites, n_db, lb2, ub2, found, n_found, extra_sites=None, n_extra=None):
         sites = _np(sites, np.float64)
         B, db_stride, n = sites.shape

@@ -96,6 +96,9 @@ class RbfMeta:
     round4_indices: List[int] = field(default_factory=list)
     fully_linear: bool = False
     improving_directions: List[np.ndarray] = field(default_factory=list)
+    # not part of the reference's RbfMeta: the round-4 factorisation kept on the device between prepare_update_model and
+    # update_model (the reference recomputes it, RbfModel.jl:657-660), and the database size the selection saw
+    _kept: object = field(default=None, repr=False, compare=False)
 
 
 def _collect_indices(meta: RbfMeta, include_x: bool = True) -> List[int]:      # :178-186
@@ -279,6 +282,7 @@ def prepare_update_model(mod, meta: RbfMeta, cfg: RbfConfig, func_indices, mop, 
     meta.center_index = x_index
     cfg_num = _with_numeric_shape(cfg, delta)
     if skip_first_rounds:                              # @goto round4, :562
+        meta._kept = None
         meta.round4_indices = []
         if cfg.optimized_sampling:
             delta_2 = cfg.theta_enlarge_2 * delta_max
@@ -288,8 +292,11 @@ def prepare_update_model(mod, meta: RbfMeta, cfg: RbfConfig, func_indices, mop, 
     num_objf_evals = max((mop.num_evals.get(ind, 0) for ind in func_indices), default=0) if mop is not None else 0
     budget = min(algo_config.max_evals, cfg.max_evals) - 1 - num_objf_evals - len(db.unevaluated_ids)      # :613-618
     max_new = int(max(0, min(budget, 2**31 - 1)))
-    res = eng.select_points(cfg_num, db.sites_array()[None], [db.num_entries], [x_index], x[None], [delta], delta_max,
-                            scal.lb, scal.ub, ensure_fully_linear, force_rebuild, max_new)
+    n_db0 = db.num_entries
+    prev = meta._kept[1] if meta._kept is not None else None
+    res, prepared = eng.select_points_keep(cfg_num, db.sites_array()[None], [n_db0], [x_index], x[None], [delta], delta_max,
+                                           scal.lb, scal.ub, ensure_fully_linear, force_rebuild, max_new, prepared=prev)
+    meta._kept = (res, prepared, n_db0, x_index)
     meta.round1_indices = [int(v) for v in res.r1[0, : res.n_r1[0]]]
     meta.round2_indices = [int(v) for v in res.r2[0, : res.n_r2[0]]]
     meta.improving_directions = [res.dirs[0, c].copy() for c in range(res.n_dirs[0])]
@@ -315,6 +322,7 @@ def prepare_improve_model(mod, meta: RbfMeta, cfg: RbfConfig, func_indices, mop,
         success = False
         if float(np.max(np.abs(offset))) > piv:
             meta.round1_indices.append(db.new_result(x + offset, None))
+            meta._kept = None                       # the training set changed: the kept factorisation no longer describes it
             success = True
         if not meta.improving_directions and success:
             meta.fully_linear = True
@@ -360,7 +368,23 @@ def update_model(mod, meta: RbfMeta, cfg: RbfConfig, func_indices, mop, scal, it
         raise ValueError("training results without values: call eval_missing! between prepare_* and update_model")
     values = np.array(vals)
     shape = _shape_value(iter_data.delta, cfg)
-    model, _status = eng.build(_with_numeric_shape(cfg, iter_data.delta), sites[None], values[None], [len(ids)], [shape])
+    cfg_num = _with_numeric_shape(cfg, iter_data.delta)
+    if meta._kept is not None and not isinstance(cfg.shape_parameter, str):
+        # round 4 kept its factorisation for exactly this training set: finish the model from it (two triangular solves)
+        res, prepared, n_db0, x_index = meta._kept
+        k = values.shape[1]
+        dbv = np.zeros((1, n_db0, k))
+        for i in range(n_db0):
+            v = db.get_value(i + 1)
+            if v is not None:
+                dbv[0, i] = v
+        r3v = np.zeros((1, sites.shape[1], k))                      # values of the new round-3 sites, n x k
+        for j, rid in enumerate(meta.round3_indices):
+            r3v[0, j] = db.get_value(rid)
+        model, _status = eng.build_prepared(cfg_num, prepared, db.sites_array()[None, :n_db0], dbv, [x_index], res, r3v,
+                                            recycle=mod.model if isinstance(mod, RbfModel) else None)
+        return RbfModel(model, meta.fully_linear), meta
+    model, _status = eng.build(cfg_num, sites[None], values[None], [len(ids)], [shape])
     return RbfModel(model, meta.fully_linear), meta
 
 

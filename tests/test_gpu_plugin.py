@@ -283,7 +283,8 @@ def test_reentrant_contexts_from_concurrent_threads():
                 S[b, :len(P)] = P; V[b, :len(P)] = synthetic.zdt3(P)
             model, status = eng.build(cfg, S, V, N)
             Y, J = eng.eval(model, h["x"][:, None, :], True, True)
-            res_all.append((res.r1.copy(), res.r4.copy(), res.n_r4.copy(), Y.copy(), J.copy()))
+            valid = lambda a, c: np.concatenate([a[b, :c[b]] for b in range(5)])      # entries beyond the counts are undefined
+            res_all.append((valid(res.r1, res.n_r1), valid(res.r2, res.n_r2), valid(res.r4, res.n_r4), res.n_r4.copy(), Y.copy(), J.copy()))
             model.free()
         out[seed] = res_all
         eng.close()
