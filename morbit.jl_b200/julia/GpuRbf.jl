@@ -218,6 +218,13 @@ function _backtrack_gpu(mod::GpuRbfModel, x::Vector{Float64}, dir::Vector{Float6
     return x₊, mx₊, σ[1] .* dir
 end
 
+# Optional fast path for update_model: `prepare_update_model` may call `mrbf_select_points_keep` (same arguments as
+# `mrbf_select_points` plus a `Ref{Ptr{Cvoid}}` for the kept round-4 factorisation, stored in the GpuRbfMeta) and `update_model`
+# then calls `mrbf_build_prepared(ctx, cfg, prepared, k, sites, values, r3_sites, r3_values, x_index, r1, n_r1, r2, n_r2, n_r3,
+# handle, status)` with the database arrays the selection saw and the freshly evaluated round-3 values: the model is finished with
+# two triangular solves instead of a from-scratch factorisation (the reference notes this saving itself, RbfModel.jl:657-660).
+# `prepare_improve_model` appends a site and therefore drops the kept factorisation (falls back to `mrbf_build`).
+
 # Constrained steepest-descent direction (descent.jl:91-135): the LP that the reference hands to JuMP + OSQP, solved exactly on
 # the device.  Drop-in for `_steepest_descent_direction(x, ∇F, lb, ub, [], [], [], [], normalize)` when the MOP has no linear
 # constraints (descent.jl:239 passes them through; with constraints the reference method stays in charge).

@@ -34,6 +34,17 @@ def main():
             if model[0] is not None: model[0].free()
             model[0], _ = eng.build(cfg, P[None], V[None], [N])
         t_sel, t_build = med(sel), med(build)
+        kept = [None, None]
+        def sel_keep():
+            kept[0], kept[1] = eng.select_points_keep(cfg, h["sites"], h["n_db"], h["x_index"], h["x"], h["delta"], h["delta_max"], h["glb"],
+                                                      h["gub"], prepared=kept[1])
+        sel_keep()
+        r3v = (synthetic.zdt3 if n > 2 else synthetic.two_parabolas)(kept[0].r3_sites[0])[None]
+        m2 = [None]
+        def build_kept():
+            m2[0], _ = eng.build_prepared(cfg, kept[1], h["sites"], h["values"], h["x_index"], kept[0], r3v, recycle=m2[0])
+        t_selk, t_buildk = med(sel_keep), med(build_kept)
+        m2[0].free(); kept[1].free()
         x = h["x"][:, None, :]
         t_eval = med(lambda: eng.eval(model[0], x, True, False), 50)
         t_jac = med(lambda: eng.eval(model[0], x, False, True), 50)
@@ -43,7 +54,7 @@ def main():
                                                       False, False, 2**31 - 1, nthreads=1), 5)
         c_build = med(lambda: CO.build_batched(cfg, P[None], V[None], [N], nthreads=1), 5)
         rows.append({"n": n, "db_sites": n_db, "max_model_points": mmp, "kernel": kern, "training_points": N,
-                     "gpu_ms": {"select_points": t_sel, "build": t_build, "eval_1pt": t_eval, "jacobian_1pt": t_jac, "backtrack_118pts": t_bt},
+                     "gpu_ms": {"select_points": t_sel, "build": t_build, "select_points_keep": t_selk, "build_prepared": t_buildk, "eval_1pt": t_eval, "jacobian_1pt": t_jac, "backtrack_118pts": t_bt},
                      "cpu_port_1core_ms": {"select_points": c_sel, "build": c_build}})
         model[0].free()
     print(json.dumps({"what": "B = 1 latencies through the host-pointer C ABI (wall clock, median)", "rows": rows}, indent=1))
