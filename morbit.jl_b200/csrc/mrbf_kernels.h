@@ -130,7 +130,6 @@ struct DescentParams {
 size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride);
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
-size_t round4_fast_vec_doubles(int n, int NM, int p);
 size_t round4_fast_state_doubles(int n, int NM, int p);
 void round4_fast_state_layout(int n, int NM, int p, size_t* off_M0, size_t* off_G, size_t* off_C, size_t* off_L);
 size_t build_vec_doubles(int n, int k, int ld, int p);
@@ -138,7 +137,6 @@ size_t build_ws_doubles(int n, int k, int ld, int p);
 
 cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s);
 cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid);
-cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s);
 cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s);
 size_t round4_block_vec_doubles(int T, int n, int NM, int p);
 SchurGeom round4_schur_geom(int n, int p, int db_stride);

@@ -670,7 +670,8 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
 
 
 // ------------------------------------------------------------------------------------------------
-// Round 4, shared-memory formulation for the regular case N0 == p (found set = centre + n poised points).
+// Round 4, Lagrange-basis formulation for the regular case N0 == p (found set = centre + n poised points): the blocked
+// left-looking kernel for large databases (round4_schur_kernel in mrbf_round4_schur.cu takes databases of <= 128 sites).
 //
 // Same decisions as RbfModel.jl:420-452, different basis.  Let S0 be the found set (Pi_0 = Pi(S0) is p x p and
 // non-singular).  Every later point xi has the null vector  n_xi = e_xi - sum_{s in S0} c_xi[s] e_s,
@@ -685,293 +686,6 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
 // marked n_r4 = -1 and handled by the literal kernel above.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
-
-template <bool SMEM>
-__global__ void __launch_bounds__(256) round4_fast_kernel(Round4Params P) {
-    extern __shared__ double smem[];
-    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = 256, lane = tid & 31, warp = tid >> 5, nwarps = 8;
-    const int NM = P.NM;
-    const int deg = P.cfg.polynomial_degree;
-    const int p = poly_dim(n, deg);
-    const int pl = p > 0 ? p : 1, pb = pl | 1;
-    const int MM = (NM - p) > 1 ? (NM - p) : 1;
-    // shared vectors
-    double* xi0 = smem;                // n   candidate site, double buffered
-    double* xi1 = xi0 + n;             // n
-    double* phix = xi1 + n;            // NM
-    double* av = phix + NM;            // MM
-    double* tv = av + MM;              // MM
-    double* cvec = tv + MM;            // pl
-    double* ub = cvec + pl;            // pl
-    double* hv = ub + pl;              // pl
-    double* tauq = hv + pl;            // pl
-    double* red = tauq + pl;           // 80
-    double* st = red + 80;
-    double* fs;
-    if constexpr (SMEM) fs = st; else fs = (P.keep_fs ? P.keep_fs : P.fs) + (size_t)b * P.fs_stride;
-    double* Ct = fs;                   // NM x n  coordinate-major centres
-    double* M0 = Ct + NM * n;          // p x p   Pi_0^{-T}
-    double* P00 = M0 + pl * pl;        // p x p   Phi(S0, S0)
-    double* H = P00 + pl * pl;         // p x p   (Pi' Pi)^{-1} of the current point set
-    double* Aq = H + pl * pl;          // p x p   scratch (QR of Pi_0)
-    double* Qx = Aq + pl * pl;         // p x p   scratch (explicit Q_0)
-    double* Tm = Qx + pl * pl;         // p x p   scratch (R_0^{-1})
-    double* Gm = Tm + pl * pl;         // pb x MM  g_eta = Phi(S0, eta) - Phi00 c_eta
-    double* Cm = Gm + pb * MM;         // pb x MM  c_eta
-    double* Li = Cm + pb * MM;         // packed lower triangle of L^{-1}, row r at tri(r)
-
-    const int n_db = P.n_db[b];
-    const double* sites = P.sites + (size_t)b * P.db_stride * n;
-    const double* lb2 = P.lb2 + (size_t)b * n;
-    const double* ub2 = P.ub2 + (size_t)b * n;
-    const int* found = P.found + (size_t)b * P.found_stride;
-    const int nf_ids = P.n_found[b];
-    const int n_extra = P.n_extra ? P.n_extra[b] : 0;
-    const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
-    int* r4 = P.r4 + (size_t)b * P.r4_stride;
-    const int N0 = nf_ids + n_extra;
-    const int max_points = P.max_points;
-    if (tid == 0 && P.elig) P.elig[b] = 0;
-    if (!(N0 < max_points) || N0 > NM) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = (N0 > NM) ? -1 : 0; } return; }
-    if (p > 0 && N0 != p) { if (tid == 0) P.n_r4[b] = -1; return; }         // literal kernel takes over
-
-    unsigned char* cand = P.cand + (size_t)b * P.db_stride;
-    for (int id = tid; id < n_db; id += nt) {
-        bool ok = in_box(sites + (size_t)id * n, lb2, ub2, n);
-        for (int f = 0; f < nf_ids && ok; ++f) ok = (found[f] != id + 1);
-        cand[id] = ok ? 1 : 0;
-    }
-    for (int e = tid; e < N0 * n; e += nt) {
-        int i = e / n, k = e % n;
-        Ct[k * NM + i] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
-    }
-    if (tid == 0) red[76] = 0.0;
-    __syncthreads();
-    // The polynomial basis is centred at the first found point and scaled by the spread of S0: c_xi and the
-    // leverage behind g_hat are invariant under that change of basis, and Pi_0 stays well conditioned for tiny Delta.
-    double inv_s = 1.0;
-    if (p > 1) {
-        double mx = 0.0;
-        for (int e = tid; e < N0 * n; e += nt) { int i = e / n, k = e % n; mx = fmax(mx, fabs(Ct[k * NM + i] - Ct[k * NM])); }
-        mx = warp_max(mx);
-        if (lane == 0) red[40 + warp] = mx;
-        __syncthreads();
-        mx = 0.0;
-        for (int w = 0; w < nwarps; ++w) mx = fmax(mx, red[40 + w]);
-        inv_s = mx > 0.0 ? 1.0 / mx : 1.0;
-        __syncthreads();
-    }
-    if (p > 0) {
-        for (int e = tid; e < p * p; e += nt) {
-            int i = e % p, j = e / p;
-            double r2 = 0.0;
-            for (int k = 0; k < n; ++k) { double d = Ct[k * NM + i] - Ct[k * NM + j]; r2 = fma(d, d, r2); }
-            P00[i + j * pl] = rad_phi(P.rf, r2);
-            Aq[i + j * pl] = (j == 0) ? 1.0 : (Ct[(j - 1) * NM + i] - Ct[(j - 1) * NM]) * inv_s;
-        }
-        __syncthreads();
-        // Householder QR of Pi_0 (same reflector conventions as the literal kernel / LAPACK geqr2)
-        for (int j = 0; j < p; ++j) {
-            double part = 0.0;
-            for (int i = j + 1 + tid; i < p; i += nt) { double a = Aq[i + j * pl]; part = fma(a, a, part); }
-            double xn2 = block_sum(part, red);
-            if (tid == 0) {
-                double alpha = Aq[j + j * pl], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
-                if (xnorm != 0.0 && j + 1 < p) { beta = -copysign(hypot(alpha, xnorm), alpha); tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta); }
-                tauq[j] = tau; red[70] = sc; red[71] = beta;
-            }
-            __syncthreads();
-            const double tau = tauq[j], sc = red[70];
-            for (int i = j + 1 + tid; i < p; i += nt) Aq[i + j * pl] *= sc;
-            if (tid == 0) Aq[j + j * pl] = red[71];
-            __syncthreads();
-            if (tau != 0.0)
-                for (int c = j + 1 + warp; c < p; c += nwarps) {
-                    double* col = Aq + c * pl; const double* vj = Aq + j * pl;
-                    double a = 0.0;
-                    for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
-                    a = (warp_sum(a) + col[j]) * tau;
-                    for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
-                    __syncwarp();
-                    if (lane == 0) col[j] -= a;
-                }
-            __syncthreads();
-        }
-        // explicit Q_0 (warp per column); T = R_0^{-1} (thread per column) after the rank check
-        for (int c = warp; c < p; c += nwarps) {
-            double* col = Qx + c * pl;
-            for (int i = lane; i < p; i += 32) col[i] = (i == c) ? 1.0 : 0.0;
-            __syncwarp();
-            for (int j = p - 1; j >= 0; --j) {
-                const double tau = tauq[j];
-                if (tau == 0.0) continue;
-                const double* vj = Aq + j * pl;
-                double a = 0.0;
-                for (int i = j + 1 + lane; i < p; i += 32) a = fma(vj[i], col[i], a);
-                a = (warp_sum(a) + col[j]) * tau;
-                for (int i = j + 1 + lane; i < p; i += 32) col[i] = fma(-a, vj[i], col[i]);
-                __syncwarp();
-                if (lane == 0) col[j] -= a;
-                __syncwarp();
-            }
-        }
-        if (tid == 0) {                            // rank check of Pi_0
-            double mn = INFINITY, mx = 0.0;
-            for (int j = 0; j < p; ++j) { double a = fabs(Aq[j + j * pl]); mn = fmin(mn, a); mx = fmax(mx, a); }
-            if (!(mn > 1e-10 * mx)) red[76] = 1.0;
-        }
-        __syncthreads();
-        if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
-        for (int j = tid; j < p; j += nt) {        // column j of R_0^{-1} by back substitution (R_0 = upper part of Aq)
-            double* x = Tm + j * pl;
-            for (int i = j + 1; i < p; ++i) x[i] = 0.0;
-            x[j] = 1.0 / Aq[j + j * pl];
-            for (int i = j - 1; i >= 0; --i) {
-                double a = 0.0;
-                for (int k = i + 1; k <= j; ++k) a = fma(Aq[i + k * pl], x[k], a);
-                x[i] = -a / Aq[i + i * pl];
-            }
-        }
-        __syncthreads();
-        for (int e = tid; e < p * p; e += nt) {    // M0 = Q_0 R_0^{-T}:  M0[r, c] = sum_k Q0[r, k] T[c, k]
-            int r = e % p, c = e / p;
-            double a = 0.0;
-            for (int k = c; k < p; ++k) a = fma(Qx[r + k * pl], Tm[c + k * pl], a);
-            M0[r + c * pl] = a;
-        }
-        __syncthreads();
-        for (int e = tid; e < p * p; e += nt) {    // H = (Pi_0' Pi_0)^{-1} = M0' M0
-            int a_ = e % p, b_ = e / p;
-            double a = 0.0;
-            for (int r = 0; r < p; ++r) a = fma(M0[r + a_ * pl], M0[r + b_ * pl], a);
-            H[a_ + b_ * pl] = a;
-        }
-    }
-    const double phi0 = rad_phi(P.rf, 0.0);
-    const double thr = P.chol_thr;
-    const int base = (p > 0) ? p : N0;             // index of the first round-4 point among the centres
-    int N = N0, m = 0, nr4 = 0;
-
-    // candidate stream with one-ahead prefetch of the site (hides the global-memory latency of the next candidate)
-    int id = 0;
-    while (id < n_db && !cand[id]) ++id;
-    for (int k = tid; k < n; k += nt) if (id < n_db) xi0[k] = sites[(size_t)id * n + k];
-    int buf = 0;
-    __syncthreads();
-    while (id < n_db && N < max_points && nr4 < P.r4_stride) {
-        const double* xi = buf ? xi1 : xi0;
-        double* xin = buf ? xi0 : xi1;
-        int nxt = id + 1;
-        while (nxt < n_db && !cand[nxt]) ++nxt;
-        // ---- phase 1: leverage (warp 0) | Lagrange coefficients (warp 1) | kernel column (warps 2..7, + prefetch)
-        if (warp == 0) {
-            // g_hat^2 = 1 / (1 + pi' (Pi' Pi)^{-1} pi): the product of the Givens cosines of utilities.jl:437-448 in
-            // closed form (leverage of the new row), so no sequential rotation sweep is needed per candidate
-            double part = 0.0;
-            for (int a_ = lane; a_ < p; a_ += 32) {
-                double h = H[a_];
-                for (int c = 1; c < p; ++c) h = fma(H[a_ + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, h);
-                hv[a_] = h;
-                part = fma(h, (a_ == 0) ? 1.0 : (xi[a_ - 1] - Ct[(a_ - 1) * NM]) * inv_s, part);
-            }
-            part = warp_sum(part);
-            if (lane == 0) { red[72] = 1.0 / (1.0 + part); red[74] = 1.0 + part; }
-        } else if (warp == 1) {
-            for (int r = lane; r < p; r += 32) {   // c_xi = Pi_0^{-T} pi_xi
-                double a = M0[r];
-                for (int c = 1; c < p; ++c) a = fma(M0[r + c * pl], (xi[c - 1] - Ct[(c - 1) * NM]) * inv_s, a);
-                cvec[r] = a;
-            }
-        } else {
-            if (warp == 2 && nxt < n_db) for (int k = lane; k < n; k += 32) xin[k] = sites[(size_t)nxt * n + k];
-            for (int i = tid - 64; i < N; i += nt - 64) {      // kernels(xi) against every current point
-                double r2 = 0.0;
-                for (int k = 0; k < n; ++k) { double d = xi[k] - Ct[k * NM + i]; r2 = fma(d, d, r2); }
-                phix[i] = rad_phi(P.rf, r2);
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: a[eta] = n_eta' Phi n_xi (warps 0..6) | u = b_xi - Phi00 c_xi and A_xixi (warp 7)
-        if (warp < 7) {
-            for (int e = tid; e < m; e += 224) {
-                const double* ge = Gm + e * pb; const double* ce = Cm + e * pb;
-                double a0 = 0.0, a1 = 0.0;
-                for (int r = 0; r < p; ++r) { a0 = fma(ge[r], cvec[r], a0); a1 = fma(ce[r], phix[r], a1); }
-                av[e] = phix[base + e] - a0 - a1;
-            }
-        } else {
-            double part = 0.0;
-            for (int r = lane; r < p; r += 32) {
-                double a = 0.0;
-                for (int c = 0; c < p; ++c) a = fma(P00[r + c * pl], cvec[c], a);
-                const double u = phix[r] - a;
-                ub[r] = u;
-                part = fma(cvec[r], phix[r] + u, part);
-            }
-            part = warp_sum(part);
-            if (lane == 0) red[73] = phi0 - part;  // A_xixi = phi0 - c.b - c.u
-        }
-        __syncthreads();
-        // ---- phase 3: t = L^{-1} a with G threads per row, ||t||^2
-        const int G = (m > 64) ? 2 : ((m > 32) ? 4 : 8);
-        const int rows_per_pass = nt / G;
-        double tn = 0.0;
-        for (int r0 = 0; r0 < m; r0 += rows_per_pass) {
-            const int r = r0 + tid / G, l = tid % G;
-            double a = 0.0;
-            if (r < m) {
-                const double* lr = Li + tri(r);
-                for (int c = l; c <= r; c += G) a = fma(lr[c], av[c], a);
-            }
-            for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (r < m && l == 0) { tv[r] = a; tn = fma(a, a, tn); }
-        }
-        tn = warp_sum(tn);
-        if (lane == 0) red[48 + warp] = tn;
-        __syncthreads();
-        tn = ((red[48] + red[49]) + (red[50] + red[51])) + ((red[52] + red[53]) + (red[54] + red[55]));
-        const double gh2 = red[72];
-        const double d2 = red[73] - tn;
-        const double tau2 = gh2 * d2;              // == sigma - ||L^-1 v||^2 of RbfModel.jl:447-449
-        if (tau2 > thr) {                          // RbfModel.jl:452
-            // ---- accept: new row of L^{-1} = [-(t' L^{-1}) / d, 1/d]
-            const double dd = sqrt(d2);
-            for (int c0 = 0; c0 < m; c0 += rows_per_pass) {
-                const int c = c0 + tid / G, l = tid % G;
-                double a = 0.0;
-                if (c < m) for (int r = c + l; r < m; r += G) a = fma(tv[r], Li[tri(r) + c], a);
-                for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (c < m && l == 0) Li[tri(m) + c] = -a / dd;
-            }
-            if (tid == 0) { Li[tri(m) + m] = 1.0 / dd; r4[nr4] = id + 1; }
-            {                                      // Sherman-Morrison: H <- H - (H pi)(H pi)' / (1 + pi' H pi)
-                const double inv1 = 1.0 / red[74];
-                for (int e = tid; e < p * p; e += nt) { int a_ = e % p, b_ = e / p; H[a_ + b_ * pl] = fma(-hv[a_] * inv1, hv[b_], H[a_ + b_ * pl]); }
-            }
-            for (int r = tid; r < p; r += nt) { Gm[m * pb + r] = ub[r]; Cm[m * pb + r] = cvec[r]; }
-            for (int k = tid; k < n; k += nt) Ct[k * NM + N] = xi[k];
-            N += 1; m += 1; nr4 += 1;
-        }
-        id = nxt; buf ^= 1;
-        __syncthreads();
-    }
-    if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
-    if (P.keep_fs) {
-        // keep the factorisation for mrbf_build_prepared: centres, Pi_0^{-T}, g/c blocks, packed L^{-1}
-        double* out = P.keep_fs + (size_t)b * P.fs_stride;
-        if constexpr (SMEM) {
-            const int used_c = pb * m, used_l = tri(m);
-            for (int e = tid; e < NM * n; e += nt) { int i = e % NM; if (i < N) out[e] = Ct[e]; }
-            double* o = out + NM * n;
-            for (int e = tid; e < pl * pl; e += nt) o[e] = M0[e];
-            o = out + (Gm - fs);
-            for (int e = tid; e < used_c; e += nt) { o[e] = Gm[e]; o[pb * MM + e] = Cm[e]; }
-            o = out + (Li - fs);
-            for (int e = tid; e < used_l; e += nt) o[e] = Li[e];
-        }
-        if (tid == 0) { out[P.fs_stride - 1] = inv_s; out[P.fs_stride - 2] = (double)N0; out[P.fs_stride - 3] = (double)m; P.elig[b] = 1; }
-    }
-}
 
 template <int T, bool SMEM>
 __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
@@ -1406,10 +1120,6 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
     }
 }
 
-size_t round4_fast_vec_doubles(int n, int NM, int p) {
-    int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
-    return 2 * (size_t)n + NM + 2 * (size_t)MM + 4 * (size_t)pl + 80;
-}
 size_t round4_fast_state_doubles(int n, int NM, int p) {
     int pl = p > 0 ? p : 1, pb = pl | 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
     return (size_t)NM * n + 6 * (size_t)pl * pl + 2 * (size_t)pb * MM + (size_t)MM * (MM + 1) / 2 + 8;
@@ -1502,19 +1212,6 @@ static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream
 }
 cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s) {
     return T == 8 ? launch_block_t<8>(P, smem, s) : launch_block_t<4>(P, smem, s);
-}
-cudaError_t launch_round4_fast(const Round4Params& P, size_t smem, cudaStream_t s) {
-    cudaError_t e;
-    if (P.fs_in_smem) {
-        e = cudaFuncSetAttribute(round4_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        round4_fast_kernel<true><<<P.B, 256, smem, s>>>(P);
-    } else {
-        e = cudaFuncSetAttribute(round4_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        round4_fast_kernel<false><<<P.B, 256, smem, s>>>(P);
-    }
-    return cudaGetLastError();
 }
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s) {
     gather_training_kernel<<<P.B, 128, 0, s>>>(P);
