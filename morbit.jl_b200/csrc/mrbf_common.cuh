@@ -87,6 +87,65 @@ __device__ __forceinline__ void rad_phi_psi(const RadFn& f, double r2, double& p
     }
 }
 
+// Reciprocal and reciprocal square root: hardware seed (about 20 bits) + Newton steps, accurate to a few ulp.  For normal positive
+// arguments; the full IEEE division / sqrt sequences cost several times as many FP64-pipe instructions.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5); y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5); y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5); y = fma(y, e, y);
+    return y;
+}
+
+// Radial functions with the kernel fixed at COMPILE time for the throughput sweeps (no switch, no exponent loop in the epilogue
+// of every point-centre pair).  RK_GENERIC falls back to the run-time versions.
+enum { RK_GENERIC = 0, RK_CUBIC3 = 1, RK_MQ = 2, RK_GAUSS = 3 };
+__host__ __device__ inline int rad_kind(int kernel, int ibeta) {
+    if (kernel == MRBF_CUBIC && ibeta == 3) return RK_CUBIC3;
+    if (kernel == MRBF_MULTIQUADRIC) return RK_MQ;
+    if (kernel == MRBF_GAUSSIAN) return RK_GAUSS;
+    return RK_GENERIC;
+}
+template <int RK>
+__device__ __forceinline__ double rad_phi_t(const RadFn& f, double r2) {
+    if constexpr (RK == RK_CUBIC3) {             // rho^3 = r2 * sqrt(r2)   (sign (-1)^2 = +1)
+        const double r = (r2 > 0.0) ? r2 * fast_rsqrt(r2) : 0.0;
+        return r2 * r;
+    } else if constexpr (RK == RK_MQ) {          // -sqrt(1 + (alpha rho)^2), argument >= 1
+        const double t = fma(f.alpha2, r2, 1.0);
+        return -(t * fast_rsqrt(t));
+    } else if constexpr (RK == RK_GAUSS) {
+        return exp(-f.alpha2 * r2);
+    } else {
+        return rad_phi(f, r2);
+    }
+}
+template <int RK>
+__device__ __forceinline__ void rad_phi_psi_t(const RadFn& f, double r2, double& phi, double& psi) {
+    if constexpr (RK == RK_CUBIC3) {
+        const double r = (r2 > 0.0) ? r2 * fast_rsqrt(r2) : 0.0;
+        phi = r2 * r; psi = 3.0 * r;
+    } else if constexpr (RK == RK_MQ) {
+        const double t = fma(f.alpha2, r2, 1.0);
+        const double rs = fast_rsqrt(t);
+        phi = -(t * rs); psi = -f.alpha2 * rs;
+    } else if constexpr (RK == RK_GAUSS) {
+        const double e = exp(-f.alpha2 * r2);
+        phi = e; psi = -2.0 * f.alpha2 * e;
+    } else {
+        rad_phi_psi(f, r2, phi, psi);
+    }
+}
+
 // results_in_box_indices' test (Databases.jl:324-327): inclusive bounds on every coordinate.
 __device__ __forceinline__ bool in_box_pt(const double* s, const double* lb, const double* ub, int n) {
     bool ok = true;

@@ -378,7 +378,9 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
                  : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0, int kk) {
+template <int RK, int KK>
+__global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0) {
+    constexpr int kk = KK;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.y, n = P.n, k = P.k, s = P.pack_s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0,
                 for (int a = 0; a < 4; ++a) {
                     double r2 = fma(-2.0, acc[a][c][e], xr[a] + ccv);
                     r2 = fmax(r2, 0.0);
-                    const double ph = rad_phi(rf, r2);
+                    const double ph = rad_phi_t<RK>(rf, r2);
 #pragma unroll
                     for (int l = 0; l < 4; ++l) if (l < kk) ysum[a][l] = fma(ph, wv[l], ysum[a][l]);
                 }
@@ -520,29 +522,44 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0,
     }
 }
 
+template <int RK, int KK>
+static cudaError_t launch_dmma_t(const EvalParams& P, cudaStream_t s, int l0, size_t smem, dim3 grid) {
+    cudaError_t e = cudaFuncSetAttribute(eval_dmma_kernel<RK, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    eval_dmma_kernel<RK, KK><<<grid, 256, smem, s>>>(P, l0);
+    return cudaGetLastError();
+}
+template <int RK>
+static cudaError_t launch_dmma_k(const EvalParams& P, cudaStream_t s, int l0, int kk, size_t smem, dim3 grid) {
+    switch (kk) {
+    case 1: return launch_dmma_t<RK, 1>(P, s, l0, smem, grid);
+    case 2: return launch_dmma_t<RK, 2>(P, s, l0, smem, grid);
+    case 3: return launch_dmma_t<RK, 3>(P, s, l0, smem, grid);
+    default: return launch_dmma_t<RK, 4>(P, s, l0, smem, grid);
+    }
+}
 static cudaError_t launch_dmma(const EvalParams& P, cudaStream_t s, int* n_launches) {
     const int st = P.pack_s;
     const size_t smem = 128 + sizeof(double) * (2 * P.pack_tile_doubles + (size_t)DM_TM * st + DM_TM + 2 * DM_TM * 4);
-    cudaError_t e = cudaFuncSetAttribute(eval_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const long long tiles = (P.M + DM_TM - 1) / DM_TM;
+    const int rk = rad_kind(P.kernel, P.ibeta);
     for (int l0 = 0; l0 < P.k; l0 += 4) {
         const int kk = (P.k - l0) < 4 ? (P.k - l0) : 4;
         dim3 grid((unsigned)tiles, (unsigned)P.B);
-        eval_dmma_kernel<<<grid, 256, smem, s>>>(P, l0, kk);
+        cudaError_t e;
+        switch (rk) {
+        case RK_CUBIC3: e = launch_dmma_k<RK_CUBIC3>(P, s, l0, kk, smem, grid); break;
+        case RK_MQ: e = launch_dmma_k<RK_MQ>(P, s, l0, kk, smem, grid); break;
+        case RK_GAUSS: e = launch_dmma_k<RK_GAUSS>(P, s, l0, kk, smem, grid); break;
+        default: e = launch_dmma_k<RK_GENERIC>(P, s, l0, kk, smem, grid); break;
+        }
         if (n_launches) ++*n_launches;
-        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-
-// Values + Jacobian on the FP64 tensor path, one output per pass.  8 warps x 16 trial points; a warp sweeps all 64
-// centres of a tile:  phase 1  D = X'C'^T (2 x 8 DMMA fragments)  ->  phi, psi;  G = psi .* w stays in the accumulator
-// registers and is re-shaped from the C-fragment to the A-fragment layout with two quad shuffles per fragment;
-// phase 2  Jacc += G C' (2 x ceil(n/8) fragments).  J = x' rowsum(G) - Jacc + lambda.  No shared-memory round trip
-// and no CTA barrier between the two contractions.
+template <int RK>
 __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int l0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.y, n = P.n, k = P.k, s = P.pack_s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -643,7 +660,7 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
                     double r2 = fma(-2.0, acc[a][c][e], xr[a] + ccv);
                     r2 = fmax(r2, 0.0);
                     double ph, ps;
-                    rad_phi_psi(rf, r2, ph, ps);
+                    rad_phi_psi_t<RK>(rf, r2, ph, ps);
                     ysum[a] = fma(ph, wv, ysum[a]);
                     const double g = ps * wv;
                     gsum[a] += g;
@@ -711,20 +728,29 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
     }
 }
 
-static cudaError_t launch_dmma_jac(const EvalParams& P, cudaStream_t s, int* n_launches) {
+template <int RK>
+static cudaError_t launch_dmma_jac_t(const EvalParams& P, cudaStream_t s, int* n_launches) {
     const int st = P.pack_s;
     const size_t smem = 128 + sizeof(double) * (2 * P.pack_tile_doubles + (size_t)DM_TM * st + DM_TM);
-    cudaError_t e = cudaFuncSetAttribute(eval_dmma_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(eval_dmma_jac_kernel<RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long tiles = (P.M + DM_TM - 1) / DM_TM;
     for (int l0 = 0; l0 < P.k; ++l0) {
         dim3 grid((unsigned)tiles, (unsigned)P.B);
-        eval_dmma_jac_kernel<<<grid, 256, smem, s>>>(P, l0);
+        eval_dmma_jac_kernel<RK><<<grid, 256, smem, s>>>(P, l0);
         if (n_launches) ++*n_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+static cudaError_t launch_dmma_jac(const EvalParams& P, cudaStream_t s, int* n_launches) {
+    switch (rad_kind(P.kernel, P.ibeta)) {
+    case RK_CUBIC3: return launch_dmma_jac_t<RK_CUBIC3>(P, s, n_launches);
+    case RK_MQ: return launch_dmma_jac_t<RK_MQ>(P, s, n_launches);
+    case RK_GAUSS: return launch_dmma_jac_t<RK_GAUSS>(P, s, n_launches);
+    default: return launch_dmma_jac_t<RK_GENERIC>(P, s, n_launches);
+    }
 }
 
 template <int CQ, bool WANT_J>

@@ -38,26 +38,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
-// Reciprocal and reciprocal square root for the sequential pivot chains: hardware seed (about 20 bits) + two Newton steps,
-// accurate to a few ulp -- the full IEEE division / rsqrt sequences cost ~300 cycles of latency per pivot on one thread.
-// Arguments are normal positive numbers here (pivots > 1e-12, d^2 > 1e-28 checked by the caller, 1 + lev >= 1).
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0); r = fma(r, e, r);
-    e = fma(-x, r, 1.0); r = fma(r, e, r);
-    return r;
-}
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double h = 0.5 * x;
-    double e = fma(-h * y, y, 0.5); y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5); y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5); y = fma(y, e, y);
-    return y;
-}
-
 // Row index (lo <= i < hi) of the entry of largest magnitude in col[], -1 if none exceeds 1e-12.  One warp; the magnitudes
 // are compared as integers (IEEE doubles order like their bit patterns) with redux.sync when the range fits a warp.
 __device__ __forceinline__ int warp_argmax_abs(const double* col, int lo, int hi, int lane) {
