@@ -385,8 +385,20 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     S.lb2 = (double*)ctx->ws[4].p; S.ub2 = S.lb2 + (size_t)B * n;
     ENSURE(ctx->ws[5], ((size_t)B * S.found_stride + B) * sizeof(int));
     S.found = (int*)ctx->ws[5].p; S.n_found = S.found + (size_t)B * S.found_stride;
+    const bool dbg123 = getenv("MRBF_DEBUG_CLOCK") != nullptr;
+    if (dbg123) { ENSURE(ctx->ws[14], 64 * sizeof(long long)); CK(cudaMemsetAsync(ctx->ws[14].p, 0, 64 * sizeof(long long), ctx->stream)); S.dbg_clock = (long long*)ctx->ws[14].p; }
     { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem, S.st_in_smem ? st_doubles : 0, db_stride), ctx->stream)); }
     ctx->launches += 1;
+    if (dbg123) {
+        long long h[64];
+        CK(cudaMemcpyAsync(h, ctx->ws[14].p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[mrbf clock] rounds 1-3 of instance 0: %lld cycles; first filter steps (dlarfg / reflector update / W D^-2 / scores / arg-max):", h[1] - h[0]);
+        for (int q = 0; q < 4 && h[8 + 8 * q]; ++q)
+            fprintf(stderr, " %lld/%lld/%lld/%lld/%lld", h[9 + 8 * q] - h[8 + 8 * q], h[10 + 8 * q] - h[9 + 8 * q], h[11 + 8 * q] - h[10 + 8 * q],
+                    h[12 + 8 * q] - h[11 + 8 * q], h[13 + 8 * q] - h[12 + 8 * q]);
+        fprintf(stderr, "\n");
+    }
     if (cfg->optimized_sampling) {           // RbfModel.jl:647-652
         rc = run_round4(ctx, cfg, B, n, db_stride, sites, n_db, S.lb2, S.ub2, S.found_stride, S.found, S.n_found,
                         n, r3_sites, n_r3, n + 1, r4_stride, r4, n_r4, status, keep, S.cflags);

@@ -24,6 +24,7 @@ struct SelectParams {
     // workspace / hand-over to round 4
     double* S; double* T; unsigned char* cflags; double* WZ; int wz_in_smem; int st_in_smem;
     double* lb2; double* ub2; int* found; int* n_found;
+    long long* dbg_clock;         // instrumentation (MRBF_DEBUG_CLOCK): phase time stamps of CTA 0, or NULL
 };
 
 struct Round4Params {

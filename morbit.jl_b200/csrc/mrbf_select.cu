@@ -64,6 +64,7 @@ struct FilterState {
     double* red;      // 80 doubles reduction scratch
     int* redi;        // 40 ints
     int* cl;          // db_stride ints: compacted candidate list of the current run
+    long long* dbg;   // instrumentation: clock stamps of CTA 0 (or NULL)
     int jY;           // columns of Y so far
 };
 
@@ -149,63 +150,80 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
     ArgMax best = block_argmax_pos(mine, st.red, st.redi, apar); apar ^= 1;
     const int RQ = (n + 3) >> 2;                  // row quads of the scoring GEMM
     int RQ2 = 1; while (RQ2 < RQ && RQ2 < 32) RQ2 <<= 1;
+#define FSTAMP(i) do { if (st.dbg && threadIdx.x == 0 && found < 4) st.dbg[8 + 8 * found + (i)] = clock64(); } while (0)
     for (;;) {
+        FSTAMP(0);
         // ---- accept position best.id: Y <- [Y s]; its projection on W is already in T.  dlarfg on that column, one warp.
         const int nw = n - st.jY;                 // columns of W before the update
         const int bpos = best.id;
-        if (warp == 0) {
-            double ss = 0.0;
-            for (int c = 1 + lane; c < nw; c += 32) { const double x_ = T[c * ldS + bpos]; ss = fma(x_, x_, ss); }
-            const double alpha = T[bpos];
-            const double xnorm = sqrt(warp_sum(ss));
-            double tau = 0.0, sc = 0.0;
-            if (xnorm != 0.0) {
-                const double beta = -copysign(hypot(alpha, xnorm), alpha);
-                tau = (beta - alpha) / beta;
-                sc = 1.0 / (alpha - beta);
+        // Every thread derives the reflector of the picked column for itself (broadcast reads of that column of T, ~100 instructions) --
+        // cheaper than one warp doing it while seven wait at a barrier.  The picked candidate is excluded from the update below, so its
+        // column stays intact until the barrier at the end of the phase.
+        //   beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = [1; x(2:) / (alpha - beta)]   (LAPACK dlarfg; the values are
+        //   O(Delta), so no rescaling loop is needed; reciprocal-root / reciprocal seeds + Newton instead of hypot and two divisions)
+        const double* xcol = T + bpos;
+        double tau = 0.0, sc = 0.0;
+        {
+            double s0 = 0.0, s1 = 0.0;
+            int c = 1;
+            for (; c + 1 < nw; c += 2) { const double x0 = xcol[c * ldS], x1 = xcol[(c + 1) * ldS]; s0 = fma(x0, x0, s0); s1 = fma(x1, x1, s1); }
+            if (c < nw) { const double x0 = xcol[c * ldS]; s0 = fma(x0, x0, s0); }
+            const double sig = s0 + s1, alpha = xcol[0];
+            if (sig != 0.0) {
+                const double nn = fma(alpha, alpha, sig);
+                const double beta = -copysign(nn * fast_rsqrt(nn), alpha);
+                tau = (beta - alpha) * fast_rcp(beta);
+                sc = fast_rcp(alpha - beta);
             }
-            for (int c = 1 + lane; c < nw; c += 32) st.vv[c] = T[c * ldS + bpos] * sc;
-            if (lane == 0) {
-                st.vv[0] = 1.0;
-                st.red[70] = tau;
-                const int id = cl[bpos];
-                cflags[id] |= CF_USED;
-                out[found] = id + 1;
-                cl[bpos] = ~id;                   // stays in the list (its column of T is dead) but never wins again
+        }
+        if (tid == 0) {
+            const int id = cl[bpos];
+            cflags[id] |= CF_USED;
+            out[found] = id + 1;
+        }
+        FSTAMP(1);
+        // ---- the reflector on W (row-private) and on the candidates' coefficients (position-private).  When the block has two
+        // threads per task, the column range of a task is split between a lane pair (half the serial chain).
+        {
+            const int ntask = n + nc;
+            const int SP = (2 * ntask <= nt) ? 2 : 1;
+            const int half = (SP == 2) ? (tid & 1) : 0;
+            const int mid = (SP == 2) ? ((nw + 1) >> 1) : nw;        // half 0: columns [0, mid), half 1: [mid, nw)
+            const int c_lo = half ? mid : 0, c_hi = half ? nw : mid;
+            for (int w0 = 0; w0 < ntask; w0 += nt / SP) {
+                const int w = w0 + tid / SP;
+                const bool act = w < ntask;
+                double* base_ = nullptr; int ldx = 0;
+                if (act) { if (w < n) { base_ = st.W + w; ldx = ldz; } else { base_ = T + (w - n); ldx = ldS; } }
+                const bool upd_ = act && (w - n != bpos);      // the picked column is read by everybody in this phase: leave it alone
+                double a0 = 0.0, a1 = 0.0;
+                if (upd_) {
+                    int c = c_lo;
+                    if (c == 0 && c < c_hi) { a0 = base_[0]; c = 1; }                                   // v_0 = 1
+                    for (; c + 1 < c_hi; c += 2) { a0 = fma(base_[c * ldx], xcol[c * ldS] * sc, a0); a1 = fma(base_[(c + 1) * ldx], xcol[(c + 1) * ldS] * sc, a1); }
+                    if (c < c_hi) a0 = fma(base_[c * ldx], xcol[c * ldS] * sc, a0);
+                }
+                double a = a0 + a1;
+                if (SP == 2) a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a *= tau;
+                // x'[c-1] = x[c] - a v_c for c = 1..nw-1: half 1 overwrites position mid-1, which half 0 still needs as a source
+                double keep_ = 0.0;
+                if (upd_ && SP == 2 && half == 0 && mid - 1 >= 1) keep_ = base_[(mid - 1) * ldx];
+                if (SP == 2) __syncwarp();
+                if (upd_) {
+                    const int lo = (c_lo < 1) ? 1 : c_lo;
+                    for (int c = lo; c < c_hi; ++c) {
+                        const double src = (SP == 2 && half == 0 && c == mid - 1) ? keep_ : base_[c * ldx];
+                        base_[(c - 1) * ldx] = fma(-a * sc, xcol[c * ldS], src);
+                    }
+                }
             }
         }
         __syncthreads();
-        const double tau = st.red[70];
-        // ---- the reflector on W (row-private) and on the candidates' coefficients (position-private); 4 partial sums each
-        for (int w = tid; w < n + nc; w += nt) {
-            if (w < n) {                          // u = W v ; W'[:, c-1] = W[:, c] - tau u v_c
-                const double* wr = st.W + w;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int c = 0;
-                for (; c + 3 < nw; c += 4) {
-                    a0 = fma(wr[c * ldz], st.vv[c], a0); a1 = fma(wr[(c + 1) * ldz], st.vv[c + 1], a1);
-                    a2 = fma(wr[(c + 2) * ldz], st.vv[c + 2], a2); a3 = fma(wr[(c + 3) * ldz], st.vv[c + 3], a3);
-                }
-                for (; c < nw; ++c) a0 = fma(wr[c * ldz], st.vv[c], a0);
-                const double a = ((a0 + a1) + (a2 + a3)) * tau;
-                double* ww = st.W + w;
-                for (c = 1; c < nw; ++c) ww[(c - 1) * ldz] = fma(-a, st.vv[c], ww[c * ldz]);
-            } else {                              // y' = (y - tau v (v.y))[1:]
-                double* y = T + (w - n);
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int c = 0;
-                for (; c + 3 < nw; c += 4) {
-                    a0 = fma(st.vv[c], y[c * ldS], a0); a1 = fma(st.vv[c + 1], y[(c + 1) * ldS], a1);
-                    a2 = fma(st.vv[c + 2], y[(c + 2) * ldS], a2); a3 = fma(st.vv[c + 3], y[(c + 3) * ldS], a3);
-                }
-                for (; c < nw; ++c) a0 = fma(st.vv[c], y[c * ldS], a0);
-                const double a = ((a0 + a1) + (a2 + a3)) * tau;
-                for (c = 1; c < nw; ++c) y[(c - 1) * ldS] = fma(-a, st.vv[c], y[c * ldS]);
-            }
-        }
+        FSTAMP(2);
+        if (tid == 0) cl[bpos] = ~cl[bpos];      // stays in the list (its column of T is dead) but never wins again
         st.jY += 1;
         found += 1;
-        __syncthreads();
         const int zc = n - st.jY;
         if (found == n_wanted) break;
         // ---- Wt = W D^-2, D = column inf-norms of W (AffinelyIndependentPoints.jl:8): one warp per column
@@ -213,11 +231,17 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
             const double* wc = st.W + c * ldz;
             double mx = 0.0;
             for (int i = lane; i < n; i += 32) mx = fmax(mx, fabs(wc[i]));
-            mx = warp_max(mx);
-            const double r = 1.0 / (mx * mx);
+            {                                             // warp max of non-negative doubles as integers (two redux instead of five shuffles)
+                const unsigned vh = (unsigned)__double2hiint(mx), vl = (unsigned)__double2loint(mx);
+                const unsigned mh = __reduce_max_sync(0xffffffffu, vh);
+                const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
+                mx = __hiloint2double((int)mh, (int)ml);
+            }
+            const double r = fast_rcp(mx * mx);
             for (int i = lane; i < n; i += 32) Wt[c * ldz + i] = wc[i] * r;
         }
         __syncthreads();
+        if (st.dbg && threadIdx.x == 0 && found <= 4) st.dbg[8 + 8 * (found - 1) + 3] = clock64();
         // ---- scores: thread = (row quad rq, candidate quad cq); acc[4 rows][4 candidates] += Wt[rows, q] * y[q, candidates]
         mine.v = 0.0; mine.id = -1;
         {
@@ -262,7 +286,9 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
                 }
             }
         }
+        if (st.dbg && threadIdx.x == 0 && found <= 4) st.dbg[8 + 8 * (found - 1) + 4] = clock64();
         best = block_argmax_pos(mine, st.red, st.redi, apar); apar ^= 1;
+        if (st.dbg && threadIdx.x == 0 && found <= 4) st.dbg[8 + 8 * (found - 1) + 5] = clock64();
         if (best.id < 0) break;                   // no more candidates
         if (!(best.v > piv)) break;               // AffinelyIndependentPoints.jl:92
     }
@@ -337,7 +363,8 @@ __global__ void __launch_bounds__(256, 3) select_rounds123_kernel(SelectParams P
     bool ensure_fl = P.flags_in[2 * b] != 0;
     bool force_rebuild = P.flags_in[2 * b + 1] != 0;
     bool rebuilt = false;
-    FilterState st; st.n = n; st.ldz = ldz; st.W = W; st.Z = Z; st.xp = xp; st.u = u; st.vv = vv; st.red = red; st.redi = redi; st.cl = cl;
+    FilterState st; st.n = n; st.ldz = ldz; st.W = W; st.Z = Z; st.xp = xp; st.u = u; st.vv = vv; st.red = red; st.redi = redi; st.cl = cl; st.dbg = (b == 0) ? P.dbg_clock : nullptr;
+    if (st.dbg && tid == 0) st.dbg[0] = clock64();
     int n_r1, n_r2, n_r3, n_dirs;
     bool fully_linear;
     for (;;) {   // at most two passes: the second is the coordinate rebuild (RbfModel.jl:634-637)
@@ -390,6 +417,7 @@ __global__ void __launch_bounds__(256, 3) select_rounds123_kernel(SelectParams P
         force_rebuild = true; ensure_fl = true; rebuilt = true;
     }
     __syncthreads();
+    if (st.dbg && tid == 0) st.dbg[1] = clock64();
     if (tid == 0) {
         P.n_r1[b] = n_r1; P.n_r2[b] = n_r2; P.n_r3[b] = n_r3; P.n_dirs[b] = n_dirs;
         P.flags_out[2 * b] = fully_linear ? 1 : 0; P.flags_out[2 * b + 1] = rebuilt ? 1 : 0;
