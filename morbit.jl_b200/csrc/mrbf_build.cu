@@ -525,24 +525,26 @@ cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cud
 //     r = Y_acc - C_acc' Y_0,   L L' u = r,   w = [-C_acc u; u],   lambda~ = Pi_0^{-1} (Y_0 - U_acc u)
 // i.e. two triangular solves per output instead of the O(N^3) saddle-point solve of RBFInterpolationModel (RbfModel.jl:759).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
+__global__ void __launch_bounds__(64, 16) build_schur_kernel(SchurBuildParams P) {
+    // Two warps per instance and ~6 KB of shared memory: the triangular sweeps are serial chains, so the SM is filled with many
+    // instances instead of wide CTAs.  L stays in global memory (L2): the forward sweep walks its columns (contiguous), the
+    // backward sweep its rows (one entry per earlier column); both prefetch the next step's entries into registers.
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, k = P.k, p = P.p, MC = P.MC, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     if (!P.elig[b]) { if (tid == 0) P.done[b] = 0; return; }
     const double* fs = P.fs + (size_t)b * P.fs_stride;
     const double* meta = fs + P.off_acc + MC;
     const double inv_s = meta[0];
-    const int N0 = (int)meta[1], m = (int)meta[2];
+    const int N0 = (int)meta[1], m = (int)meta[2], mc = (int)meta[3];
     const int N = N0 + m;
     const double* M0g = fs + P.off_M0; const double* Ug = fs + P.off_U; const double* Cg = fs + P.off_C; const double* Lg = fs + P.off_L;
     double* y0 = smem;                          // p x k
-    double* rv = y0 + (size_t)p * k;            // MC x k  (stored output-major: rv[o * MC + q])
+    double* rv = y0 + (size_t)p * k;            // MC x k  (output-major, indexed by candidate position: rv[o * MC + pos])
     double* t0 = rv + (size_t)MC * k;           // p x k
     double* sv = t0 + (size_t)p * k;            // p x k
-    double* invd = sv + (size_t)p * k;          // MC
-    double* Ls = invd + MC;                     // packed columns: column q at cs(q) = q m - q (q - 1) / 2, rows q..m-1
-    int* accpos = reinterpret_cast<int*>(Ls + ((size_t)MC * (MC + 1)) / 2);
-    int* isacc = accpos + MC;
+    double* invd = sv + (size_t)p * k;          // MC  1 / L_qq by accepted ordinal
+    int* accpos = reinterpret_cast<int*>(invd + MC);     // ordinal -> position
+    int* posq = accpos + MC;                              // position -> ordinal, -1 for rejected candidates
     const int* found = P.found + (size_t)b * P.found_stride;
     const int nf = P.n_found[b];
     const int* r4 = P.r4 + (size_t)b * P.r4_stride;
@@ -550,7 +552,14 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
     const double* values = P.values + (size_t)b * P.db_stride * k;
     const double* r3s = P.r3_sites ? P.r3_sites + (size_t)b * n * n : nullptr;
     const double* r3v = P.r3_values ? P.r3_values + (size_t)b * n * k : nullptr;
-    for (int q = tid; q < m; q += nt) accpos[q] = (int)fs[P.off_acc + q];
+    for (int i = tid; i < mc; i += nt) posq[i] = -1;
+    for (int e = tid; e < mc * k; e += nt) rv[(e / mc) * MC + (e % mc)] = 0.0;
+    __syncthreads();
+    for (int q = tid; q < m; q += nt) {
+        const int j = (int)fs[P.off_acc + q];
+        accpos[q] = j; posq[j] = q;
+        invd[q] = 1.0 / Lg[(size_t)q * MC + j];
+    }
     for (int e = tid; e < p * k; e += nt) {
         const int i = e / k, o = e % k;
         y0[e] = (i < nf) ? values[(size_t)(found[i] - 1) * k + o] : (r3v ? r3v[(size_t)(i - nf) * k + o] : 0.0);
@@ -565,20 +574,6 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
         centers[e] = v;
     }
     __syncthreads();
-    // L as round 4 left it: column q holds the rows (candidate positions) >= accpos[q].  It is packed by POSITION -- the column of
-    // the pivot at position j starts at cs(j) = j mc - j (j - 1) / 2 -- so the copy is coalesced and needs no gather; rows of rejected
-    // candidates ride along (they are updated but never used as pivots).
-    const int mc = (int)meta[3];
-    for (int q = warp; q < m; q += nwarps) {
-        const int j = accpos[q];
-        const double* Lc = Lg + (size_t)q * MC;
-        double* dst = Ls + ((size_t)j * mc - ((size_t)j * (j - 1)) / 2) - j;
-        for (int i = j + lane; i < mc; i += 32) { const double v = Lc[i]; dst[i] = v; if (i == j) invd[q] = 1.0 / v; }
-    }
-    for (int e = tid; e < mc * k; e += nt) rv[(e / mc) * MC + (e % mc)] = 0.0;
-    for (int i = tid; i < mc; i += nt) isacc[i] = 0;
-    __syncthreads();
-    for (int q = tid; q < m; q += nt) isacc[accpos[q]] = 1;
     for (int e = tid; e < m * k; e += nt) {      // r = Y_acc - C_acc' Y_0, stored by candidate position
         const int q = e % m, o = e / m;
         double a = values[(size_t)(r4[q] - 1) * k + o];
@@ -588,45 +583,65 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
     }
     __syncthreads();
     // L t = r, then L' u = t.  One warp per output; the right-hand side stays in registers (lane l owns positions l, l + 32,
-    // l + 64, l + 96 -- mc <= 128), the pivot entry travels by one shuffle per step and both sweeps are axpy updates (no
-    // reductions): forward with column j of L (contiguous), backward with row j of L (one entry per earlier column).
+    // l + 64, l + 96 -- mc <= 128), the pivot entry travels by one shuffle per step and both sweeps are axpy updates.
     for (int o = warp; o < k; o += nwarps) {
         double* r = rv + o * MC;
-        double r0 = (lane < mc) ? r[lane] : 0.0, r1 = (lane + 32 < mc) ? r[lane + 32] : 0.0;
-        double r2 = (lane + 64 < mc) ? r[lane + 64] : 0.0, r3 = (lane + 96 < mc) ? r[lane + 96] : 0.0;
+        const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
+        double r0 = (i0 < mc) ? r[i0] : 0.0, r1 = (i1 < mc) ? r[i1] : 0.0, r2 = (i2 < mc) ? r[i2] : 0.0, r3 = (i3 < mc) ? r[i3] : 0.0;
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;                    // column of the current step, prefetched
+        if (m > 0) {
+            const double* col = Lg;
+            c0 = (i0 < mc) ? col[i0] : 0.0; c1 = (i1 < mc) ? col[i1] : 0.0; c2 = (i2 < mc) ? col[i2] : 0.0; c3 = (i3 < mc) ? col[i3] : 0.0;
+        }
         for (int q = 0; q < m; ++q) {
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+            if (q + 1 < m) {                                                   // next column on its way while this one is used
+                const double* col = Lg + (size_t)(q + 1) * MC;
+                n0 = (i0 < mc) ? col[i0] : 0.0; n1 = (i1 < mc) ? col[i1] : 0.0; n2 = (i2 < mc) ? col[i2] : 0.0; n3 = (i3 < mc) ? col[i3] : 0.0;
+            }
             const int j = accpos[q], sl = j >> 5;
             const double mine = (sl == 0) ? r0 : ((sl == 1) ? r1 : ((sl == 2) ? r2 : r3));
             const double t = __shfl_sync(0xffffffffu, mine, j & 31) * invd[q];
-            const double* col = Ls + ((size_t)j * mc - ((size_t)j * (j - 1)) / 2) - j;
-            const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
-            if (i0 == j) r0 = t; else if (i0 > j && i0 < mc) r0 = fma(-col[i0], t, r0);
-            if (i1 == j) r1 = t; else if (i1 > j && i1 < mc) r1 = fma(-col[i1], t, r1);
-            if (i2 == j) r2 = t; else if (i2 > j && i2 < mc) r2 = fma(-col[i2], t, r2);
-            if (i3 == j) r3 = t; else if (i3 > j && i3 < mc) r3 = fma(-col[i3], t, r3);
+            if (i0 == j) r0 = t; else if (i0 > j) r0 = fma(-c0, t, r0);
+            if (i1 == j) r1 = t; else if (i1 > j) r1 = fma(-c1, t, r1);
+            if (i2 == j) r2 = t; else if (i2 > j) r2 = fma(-c2, t, r2);
+            if (i3 == j) r3 = t; else if (i3 > j) r3 = fma(-c3, t, r3);
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         }
-        // rejected positions carry no unknown: zero them, then sweep back
-        if (!(lane < mc && isacc[lane])) r0 = 0.0;
-        if (!(lane + 32 < mc && isacc[lane + 32])) r1 = 0.0;
-        if (!(lane + 64 < mc && isacc[lane + 64])) r2 = 0.0;
-        if (!(lane + 96 < mc && isacc[lane + 96])) r3 = 0.0;
-        // offsets of this lane's columns in the packed storage: element (row j, column i) sits at cs(i) - i + j
-        const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
-        const int c0 = i0 * mc - (i0 * (i0 - 1)) / 2 - i0, c1 = i1 * mc - (i1 * (i1 - 1)) / 2 - i1;
-        const int c2 = i2 * mc - (i2 * (i2 - 1)) / 2 - i2, c3 = i3 * mc - (i3 * (i3 - 1)) / 2 - i3;
+        // rejected positions carry no unknown.  Backward sweep column by column as well (contiguous, coalesced reads of L; a row-wise
+        // axpy would touch one 32-byte sector per entry): u_j = (t_j - sum_{i > j} L[i][j] u_i) / L_jj with a warp reduction per step.
+        if (!(i0 < mc && posq[i0] >= 0)) r0 = 0.0;
+        if (!(i1 < mc && posq[i1] >= 0)) r1 = 0.0;
+        if (!(i2 < mc && posq[i2] >= 0)) r2 = 0.0;
+        if (!(i3 < mc && posq[i3] >= 0)) r3 = 0.0;
+        if (m > 0) {
+            const double* col = Lg + (size_t)(m - 1) * MC;
+            c0 = (i0 < mc) ? col[i0] : 0.0; c1 = (i1 < mc) ? col[i1] : 0.0; c2 = (i2 < mc) ? col[i2] : 0.0; c3 = (i3 < mc) ? col[i3] : 0.0;
+        }
         for (int q = m - 1; q >= 0; --q) {
-            const int j = accpos[q], sl = j >> 5;
-            const double mine = (sl == 0) ? r0 : ((sl == 1) ? r1 : ((sl == 2) ? r2 : r3));
-            const double u = __shfl_sync(0xffffffffu, mine, j & 31) * invd[q];
-            if (i0 == j) r0 = u; else if (i0 < j && isacc[i0]) r0 = fma(-Ls[c0 + j], u, r0);
-            if (i1 == j) r1 = u; else if (i1 < j && isacc[i1]) r1 = fma(-Ls[c1 + j], u, r1);
-            if (i2 == j) r2 = u; else if (i2 < j && isacc[i2]) r2 = fma(-Ls[c2 + j], u, r2);
-            if (i3 == j) r3 = u; else if (i3 < j && isacc[i3]) r3 = fma(-Ls[c3 + j], u, r3);
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+            if (q > 0) {
+                const double* col = Lg + (size_t)(q - 1) * MC;
+                n0 = (i0 < mc) ? col[i0] : 0.0; n1 = (i1 < mc) ? col[i1] : 0.0; n2 = (i2 < mc) ? col[i2] : 0.0; n3 = (i3 < mc) ? col[i3] : 0.0;
+            }
+            const int j = accpos[q];
+            double part = 0.0;
+            if (i0 > j) part = fma(c0, r0, part);
+            if (i1 > j) part = fma(c1, r1, part);
+            if (i2 > j) part = fma(c2, r2, part);
+            if (i3 > j) part = fma(c3, r3, part);
+            part = warp_sum(part);
+            const double id_ = invd[q];
+            if (i0 == j) r0 = (r0 - part) * id_;
+            if (i1 == j) r1 = (r1 - part) * id_;
+            if (i2 == j) r2 = (r2 - part) * id_;
+            if (i3 == j) r3 = (r3 - part) * id_;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         }
-        if (lane < mc) r[lane] = r0;
-        if (lane + 32 < mc) r[lane + 32] = r1;
-        if (lane + 64 < mc) r[lane + 64] = r2;
-        if (lane + 96 < mc) r[lane + 96] = r3;
+        if (i0 < mc) r[i0] = r0;
+        if (i1 < mc) r[i1] = r1;
+        if (i2 < mc) r[i2] = r2;
+        if (i3 < mc) r[i3] = r3;
     }
     __syncthreads();
     double* w_out = P.w + (size_t)b * P.train_stride * k;
@@ -659,12 +674,12 @@ __global__ void __launch_bounds__(256) build_schur_kernel(SchurBuildParams P) {
 }
 
 size_t build_schur_smem_doubles(int k, int MC, int p) {
-    return 3 * (size_t)p * k + (size_t)MC * k + MC + ((size_t)MC * (MC + 1)) / 2 + MC + 2;
+    return 3 * (size_t)p * k + (size_t)MC * k + MC + MC + 2;
 }
 cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(build_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    build_schur_kernel<<<P.B, 256, smem, s>>>(P);
+    build_schur_kernel<<<P.B, 64, smem, s>>>(P);
     return cudaGetLastError();
 }
 
