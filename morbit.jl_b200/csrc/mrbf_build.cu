@@ -589,15 +589,17 @@ __global__ void __launch_bounds__(64, 16) build_schur_kernel(SchurBuildParams P)
         const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
         double r0 = (i0 < mc) ? r[i0] : 0.0, r1 = (i1 < mc) ? r[i1] : 0.0, r2 = (i2 < mc) ? r[i2] : 0.0, r3 = (i3 < mc) ? r[i3] : 0.0;
         double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;                    // column of the current step, prefetched
-        if (m > 0) {
-            const double* col = Lg;
-            c0 = (i0 < mc) ? col[i0] : 0.0; c1 = (i1 < mc) ? col[i1] : 0.0; c2 = (i2 < mc) ? col[i2] : 0.0; c3 = (i3 < mc) ? col[i3] : 0.0;
+        if (m > 0) {                                                           // only the rows below the pivot are ever used
+            const double* col = Lg; const int jn = accpos[0];
+            c0 = (i0 > jn && i0 < mc) ? col[i0] : 0.0; c1 = (i1 > jn && i1 < mc) ? col[i1] : 0.0;
+            c2 = (i2 > jn && i2 < mc) ? col[i2] : 0.0; c3 = (i3 > jn && i3 < mc) ? col[i3] : 0.0;
         }
         for (int q = 0; q < m; ++q) {
             double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
             if (q + 1 < m) {                                                   // next column on its way while this one is used
-                const double* col = Lg + (size_t)(q + 1) * MC;
-                n0 = (i0 < mc) ? col[i0] : 0.0; n1 = (i1 < mc) ? col[i1] : 0.0; n2 = (i2 < mc) ? col[i2] : 0.0; n3 = (i3 < mc) ? col[i3] : 0.0;
+                const double* col = Lg + (size_t)(q + 1) * MC; const int jn = accpos[q + 1];
+                n0 = (i0 > jn && i0 < mc) ? col[i0] : 0.0; n1 = (i1 > jn && i1 < mc) ? col[i1] : 0.0;
+                n2 = (i2 > jn && i2 < mc) ? col[i2] : 0.0; n3 = (i3 > jn && i3 < mc) ? col[i3] : 0.0;
             }
             const int j = accpos[q], sl = j >> 5;
             const double mine = (sl == 0) ? r0 : ((sl == 1) ? r1 : ((sl == 2) ? r2 : r3));
@@ -615,14 +617,16 @@ __global__ void __launch_bounds__(64, 16) build_schur_kernel(SchurBuildParams P)
         if (!(i2 < mc && posq[i2] >= 0)) r2 = 0.0;
         if (!(i3 < mc && posq[i3] >= 0)) r3 = 0.0;
         if (m > 0) {
-            const double* col = Lg + (size_t)(m - 1) * MC;
-            c0 = (i0 < mc) ? col[i0] : 0.0; c1 = (i1 < mc) ? col[i1] : 0.0; c2 = (i2 < mc) ? col[i2] : 0.0; c3 = (i3 < mc) ? col[i3] : 0.0;
+            const double* col = Lg + (size_t)(m - 1) * MC; const int jn = accpos[m - 1];
+            c0 = (i0 > jn && i0 < mc) ? col[i0] : 0.0; c1 = (i1 > jn && i1 < mc) ? col[i1] : 0.0;
+            c2 = (i2 > jn && i2 < mc) ? col[i2] : 0.0; c3 = (i3 > jn && i3 < mc) ? col[i3] : 0.0;
         }
         for (int q = m - 1; q >= 0; --q) {
             double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
             if (q > 0) {
-                const double* col = Lg + (size_t)(q - 1) * MC;
-                n0 = (i0 < mc) ? col[i0] : 0.0; n1 = (i1 < mc) ? col[i1] : 0.0; n2 = (i2 < mc) ? col[i2] : 0.0; n3 = (i3 < mc) ? col[i3] : 0.0;
+                const double* col = Lg + (size_t)(q - 1) * MC; const int jn = accpos[q - 1];
+                n0 = (i0 > jn && i0 < mc) ? col[i0] : 0.0; n1 = (i1 > jn && i1 < mc) ? col[i1] : 0.0;
+                n2 = (i2 > jn && i2 < mc) ? col[i2] : 0.0; n3 = (i3 > jn && i3 < mc) ? col[i3] : 0.0;
             }
             const int j = accpos[q];
             double part = 0.0;
