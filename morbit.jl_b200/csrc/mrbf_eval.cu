@@ -559,7 +559,9 @@ static cudaError_t launch_dmma(const EvalParams& P, cudaStream_t s, int* n_launc
     return cudaSuccess;
 }
 
-template <int RK>
+// KO outputs per pass (1 or 2): the distance contraction and the radial functions are shared, only the weighting of psi and the
+// second contraction are per output.
+template <int RK, int KO>
 __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int l0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.y, n = P.n, k = P.k, s = P.pack_s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -604,12 +606,16 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
     const int qr = lane >> 2, qc = lane & 3;
     const int row0 = 16 * warp;
     double xr[2] = {xx[row0 + qr], xx[row0 + 8 + qr]};
-    double ysum[2] = {0.0, 0.0}, gsum[2] = {0.0, 0.0};
-    double jacc[2][8][2];
+    double ysum[KO][2], gsum[KO][2];
+    double jacc[KO][2][8][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int o = 0; o < KO; ++o)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { jacc[a][c][0] = 0.0; jacc[a][c][1] = 0.0; }
+        for (int a = 0; a < 2; ++a) {
+            ysum[o][a] = 0.0; gsum[o][a] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { jacc[o][a][c][0] = 0.0; jacc[o][a][c][1] = 0.0; }
+        }
     const int ksteps = ((n + 3) & ~3) >> 2;
     const double* xa = Xs + (row0 + qr) * s + qc;
 
@@ -654,20 +660,22 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int col = 8 * c + 2 * qc + e;
-                const double ccv = ccs[col], wv = Wt[col];
+                const double ccv = ccs[col];
+                double wv[KO];
+#pragma unroll
+                for (int o = 0; o < KO; ++o) wv[o] = Wt[o * DM_TN + col];
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
                     double r2 = fma(-2.0, acc[a][c][e], xr[a] + ccv);
                     r2 = fmax(r2, 0.0);
                     double ph, ps;
                     rad_phi_psi_t<RK>(rf, r2, ph, ps);
-                    ysum[a] = fma(ph, wv, ysum[a]);
-                    const double g = ps * wv;
-                    gsum[a] += g;
-                    acc[a][c][e] = g;              // G in C-fragment layout
+#pragma unroll
+                    for (int o = 0; o < KO; ++o) { ysum[o][a] = fma(ph, wv[o], ysum[o][a]); gsum[o][a] = fma(ps, wv[o], gsum[o][a]); }
+                    acc[a][c][e] = ps;             // psi in C-fragment layout; the output weights are applied per k-column below
                 }
             }
-        // phase 2: Jacc += G (16 x 64) * C' (64 x 8 ncb)
+        // phase 2: Jacc_o += (psi . w_o) (16 x 64) * C' (64 x 8 ncb)
 #pragma unroll
         for (int kc = 0; kc < 16; ++kc) {
             const int c = kc >> 1, h = kc & 1;
@@ -680,51 +688,60 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
                 fa[a] = (qc & 1) ? v1 : v0;
             }
             const double* brow = Cs + (4 * kc + qc) * s + qr;
+            double fo[KO][2];
+#pragma unroll
+            for (int o = 0; o < KO; ++o) { const double wk_ = Wt[o * DM_TN + 4 * kc + qc]; fo[o][0] = fa[0] * wk_; fo[o][1] = fa[1] * wk_; }
 #pragma unroll
             for (int cbk = 0; cbk < 8; ++cbk) {
                 if (cbk < ncb) {
                     const double fb = brow[8 * cbk];
-                    dmma884(jacc[0][cbk], fa[0], fb);
-                    dmma884(jacc[1][cbk], fa[1], fb);
+#pragma unroll
+                    for (int o = 0; o < KO; ++o) { dmma884(jacc[o][0][cbk], fo[o][0], fb); dmma884(jacc[o][1][cbk], fo[o][1], fb); }
                 }
             }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        double v = ysum[a], g = gsum[a];
-        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-        g += __shfl_xor_sync(0xffffffffu, g, 1); g += __shfl_xor_sync(0xffffffffu, g, 2);
-        ysum[a] = v; gsum[a] = g;
-    }
+    for (int o = 0; o < KO; ++o)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            double v = ysum[o][a], g = gsum[o][a];
+            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+            g += __shfl_xor_sync(0xffffffffu, g, 1); g += __shfl_xor_sync(0xffffffffu, g, 2);
+            ysum[o][a] = v; gsum[o][a] = g;
+        }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const int row = row0 + 8 * a + qr;
         const long long mi = m0 + row;
         if (mi >= P.M) continue;
-        if (P.Y && qc == 0) {
-            double v = ysum[a];
-            if (P.deg >= 0) v += lam[l0];
-            if (P.deg >= 1) {
-                double tsum = 0.0;
-                for (int c = 0; c < n; ++c) tsum = fma(lam[(size_t)(c + 1) * k + l0], Xs[row * s + c] + centers[c], tsum);
-                v += tsum;
-            }
-            P.Y[((size_t)b * P.M + mi) * k + l0] = v;
-        }
-        double* Jrow = P.J + (((size_t)b * P.M + mi) * k + l0) * n;
 #pragma unroll
-        for (int cbk = 0; cbk < 8; ++cbk)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = 8 * cbk + 2 * qc + e;
-                if (cbk < ncb && col < n) {
-                    double val = fma(Xs[row * s + col], gsum[a], -jacc[a][cbk][e]);
-                    if (P.deg >= 1) val += lam[(size_t)(col + 1) * k + l0];
-                    Jrow[col] = val;
+        for (int o = 0; o < KO; ++o) {
+            const int lo_ = l0 + o;
+            if (P.Y && qc == 0) {
+                double v = ysum[o][a];
+                if (P.deg >= 0) v += lam[lo_];
+                if (P.deg >= 1) {
+                    double tsum = 0.0;
+                    for (int c = 0; c < n; ++c) tsum = fma(lam[(size_t)(c + 1) * k + lo_], Xs[row * s + c] + centers[c], tsum);
+                    v += tsum;
                 }
+                P.Y[((size_t)b * P.M + mi) * k + lo_] = v;
             }
+            double* Jrow = P.J + (((size_t)b * P.M + mi) * k + lo_) * n;
+#pragma unroll
+            for (int cbk = 0; cbk < 8; ++cbk)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * cbk + 2 * qc + e;
+                    if (cbk < ncb && col < n) {
+                        double val = fma(Xs[row * s + col], gsum[o][a], -jacc[o][a][cbk][e]);
+                        if (P.deg >= 1) val += lam[(size_t)(col + 1) * k + lo_];
+                        Jrow[col] = val;
+                    }
+                }
+        }
     }
 }
 
@@ -732,12 +749,14 @@ template <int RK>
 static cudaError_t launch_dmma_jac_t(const EvalParams& P, cudaStream_t s, int* n_launches) {
     const int st = P.pack_s;
     const size_t smem = 128 + sizeof(double) * (2 * P.pack_tile_doubles + (size_t)DM_TM * st + DM_TM);
-    cudaError_t e = cudaFuncSetAttribute(eval_dmma_jac_kernel<RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(eval_dmma_jac_kernel<RK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_dmma_jac_kernel<RK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long tiles = (P.M + DM_TM - 1) / DM_TM;
-    for (int l0 = 0; l0 < P.k; ++l0) {
+    for (int l0 = 0; l0 < P.k;) {                // two outputs per pass while there are two left
         dim3 grid((unsigned)tiles, (unsigned)P.B);
-        eval_dmma_jac_kernel<RK><<<grid, 256, smem, s>>>(P, l0);
+        if (l0 + 1 < P.k) { eval_dmma_jac_kernel<RK, 2><<<grid, 256, smem, s>>>(P, l0); l0 += 2; }
+        else { eval_dmma_jac_kernel<RK, 1><<<grid, 256, smem, s>>>(P, l0); l0 += 1; }
         if (n_launches) ++*n_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
