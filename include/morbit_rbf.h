@@ -208,6 +208,10 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* model, int64_t M, const doubl
 int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* model, const double* x, const double* dir, const double* step0,
                    const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
                    int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus);
+/* same with device pointers (all outputs required), enqueued on the context's stream */
+int mrbf_backtrack_dev(mrbf_ctx* ctx, const mrbf_model* model, const double* x, const double* dir, const double* step0,
+                       const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
+                       int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus);
 
 /* ---- steepest-descent direction: replaces _steepest_descent_direction (src/descent.jl:75-135, JuMP + OSQP) -----------
  *      min alpha  s.t.  Df_i . d <= alpha * ||Df_i||_2 (rows normalised iff `normalize`),  -1 <= d <= 1,  lb <= x + d <= ub

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mrbf_eval": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "mrbf_eval_dev": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "mrbf_backtrack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mrbf_backtrack_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mrbf_descent_direction": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mrbf_descent_direction_dev": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
 }

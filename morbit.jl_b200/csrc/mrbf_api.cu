@@ -822,31 +822,42 @@ int mrbf_eval(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X, do
     return MRBF_OK;
 }
 
-int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const double* dir, const double* step0,
-                   const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
-                   int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus) {
-    if (!ctx || !m || !x || !dir || !step0 || !omega || max_loops < 0) return MRBF_EINVAL;
+int mrbf_backtrack_dev(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const double* dir, const double* step0,
+                       const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
+                       int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus) {
+    if (!ctx || !m || !x || !dir || !step0 || !omega || max_loops < 0 || !step_index || !sigma || !x_plus || !mx || !mx_plus) return MRBF_EINVAL;
     CK(cudaSetDevice(ctx->device));
     const int B = m->B, n = m->n, k = m->k, ns = max_loops + 1;
-    const size_t dBn = sizeof(double) * (size_t)B * n, dB = sizeof(double) * (size_t)B, dBk = sizeof(double) * (size_t)B * k;
-    ENSURE(ctx->hb[14], 3 * dBn + 3 * dB + 2 * dBk + sizeof(int) * (size_t)B);
     ENSURE(ctx->hb[15], sizeof(double) * (size_t)B * (ns + 1) * (n + k) + sizeof(double) * (size_t)B * ns);
-    double* d_x = (double*)ctx->hb[14].p; double* d_dir = d_x + (size_t)B * n; double* d_xp = d_dir + (size_t)B * n;
-    double* d_step = d_xp + (size_t)B * n; double* d_om = d_step + B; double* d_sig = d_om + B;
-    double* d_mx = d_sig + B; double* d_mxp = d_mx + (size_t)B * k; int* d_idx = (int*)(d_mxp + (size_t)B * k);
     double* d_Xall = (double*)ctx->hb[15].p; double* d_Yall = d_Xall + (size_t)B * (ns + 1) * n; double* d_sall = d_Yall + (size_t)B * (ns + 1) * k;
-    H2D(d_x, x, dBn); H2D(d_dir, dir, dBn); H2D(d_step, step0, dB); H2D(d_om, omega, dB);
     BacktrackParams Q{};
     Q.B = B; Q.n = n; Q.k = k; Q.nsteps = ns; Q.strict = strict; Q.armijo_c = armijo_c; Q.shrink = shrink;
     Q.min_stepsize = min_stepsize; Q.max_loops = max_loops;
-    Q.x = d_x; Q.dir = d_dir; Q.step0 = d_step; Q.omega = d_om; Q.Yall = d_Yall; Q.Xall = d_Xall; Q.sig_all = d_sall;
-    Q.step_index = d_idx; Q.sigma = d_sig; Q.x_plus = d_xp; Q.mx = d_mx; Q.mx_plus = d_mxp;
+    Q.x = x; Q.dir = dir; Q.step0 = step0; Q.omega = omega; Q.Yall = d_Yall; Q.Xall = d_Xall; Q.sig_all = d_sall;
+    Q.step_index = step_index; Q.sigma = sigma; Q.x_plus = x_plus; Q.mx = mx; Q.mx_plus = mx_plus;
     CK(launch_backtrack_points(Q, ctx->stream));
     ctx->launches += 1;
     int rc = mrbf_eval_dev(ctx, m, ns + 1, d_Xall, d_Yall, nullptr);
     if (rc != MRBF_OK) return rc;
     CK(launch_backtrack_pick(Q, ctx->stream));
     ctx->launches += 1;
+    return MRBF_OK;
+}
+
+int mrbf_backtrack(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const double* dir, const double* step0,
+                   const double* omega, double armijo_c, double shrink, double min_stepsize, int32_t max_loops,
+                   int32_t strict, int32_t* step_index, double* sigma, double* x_plus, double* mx, double* mx_plus) {
+    if (!ctx || !m || !x || !dir || !step0 || !omega || max_loops < 0) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int B = m->B, n = m->n, k = m->k;
+    const size_t dBn = sizeof(double) * (size_t)B * n, dB = sizeof(double) * (size_t)B, dBk = sizeof(double) * (size_t)B * k;
+    ENSURE(ctx->hb[14], 3 * dBn + 3 * dB + 2 * dBk + sizeof(int) * (size_t)B);
+    double* d_x = (double*)ctx->hb[14].p; double* d_dir = d_x + (size_t)B * n; double* d_xp = d_dir + (size_t)B * n;
+    double* d_step = d_xp + (size_t)B * n; double* d_om = d_step + B; double* d_sig = d_om + B;
+    double* d_mx = d_sig + B; double* d_mxp = d_mx + (size_t)B * k; int* d_idx = (int*)(d_mxp + (size_t)B * k);
+    H2D(d_x, x, dBn); H2D(d_dir, dir, dBn); H2D(d_step, step0, dB); H2D(d_om, omega, dB);
+    int rc = mrbf_backtrack_dev(ctx, m, d_x, d_dir, d_step, d_om, armijo_c, shrink, min_stepsize, max_loops, strict, d_idx, d_sig, d_xp, d_mx, d_mxp);
+    if (rc != MRBF_OK) return rc;
     if (step_index) D2H(step_index, d_idx, sizeof(int) * (size_t)B);
     if (sigma) D2H(sigma, d_sig, dB);
     if (x_plus) D2H(x_plus, d_xp, dBn);

@@ -390,6 +390,23 @@ class Engine:
                                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3])))
         return out
 
+    def backtrack_dev(self, model: ModelBatch, x, direction, step0, omega, armijo_c=1e-6, shrink=0.75,
+                      min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict=True, out=None):
+        """descent.jl:150-185 for device tensors (x, direction: B x n; step0, omega: B); returns
+        (step_index, sigma, x_plus, mx, mx_plus) as device tensors, enqueued on the engine's stream."""
+        import torch
+        if max_loops is None:
+            max_loops = int(math.floor(math.log(min_stepsize) / math.log(shrink)))
+        B, n, k = model.B, model.n, model.k
+        if out is None:
+            f64 = dict(dtype=torch.float64, device=x.device)
+            out = (torch.empty(B, dtype=torch.int32, device=x.device), torch.empty(B, **f64), torch.empty((B, n), **f64),
+                   torch.empty((B, k), **f64), torch.empty((B, k), **f64))
+        self._check(self.lib.mrbf_backtrack_dev(self.ctx, model.handle, _ptr(x), _ptr(direction), _ptr(step0), _ptr(omega),
+                                                float(armijo_c), float(shrink), float(min_stepsize), int(max_loops), int(bool(strict)),
+                                                _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(out[4])))
+        return out
+
     def backtrack(self, model: ModelBatch, x, direction, step0, omega, armijo_c=1e-6, shrink=0.75,
                   min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict=True):
         """descent.jl:150-185 with every step size evaluated in one launch."""

@@ -71,3 +71,24 @@ def test_descent_then_backtrack_on_a_built_model(engine):
             assert np.all(mx[b] - mxp[b] >= -1e-12)        # a descent step for every output of the model
         assert np.all(xp[b] >= -1e-12) and np.all(xp[b] <= 1 + 1e-12)
     model.free()
+
+
+def test_backtrack_dev_equals_host_entry_point(engine):
+    """mrbf_backtrack_dev (device pointers, no synchronisation) returns exactly what mrbf_backtrack returns."""
+    import torch
+    from morbit_jl_b200 import synthetic
+    rng = np.random.default_rng(11)
+    B, n, N = 9, 6, 25
+    cfg = mb.RbfConfig(kernel="multiquadric")
+    sites = rng.random((B, N, n)); vals = synthetic.zdt3(sites)
+    model, _ = engine.build(cfg, sites, vals, [N] * B)
+    x = sites[:, 0, :].copy()
+    d = rng.normal(size=(B, n)); d /= np.abs(d).max(axis=1, keepdims=True)
+    step0 = np.full(B, 0.3); omega = rng.random(B)
+    xp, mxp, step, idx, mx = engine.backtrack(model, x, d, step0, omega)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = engine.backtrack_dev(model, t(x), t(d), t(step0), t(omega))
+    engine.sync()
+    assert np.array_equal(out[0].cpu().numpy(), idx)
+    assert np.array_equal(out[2].cpu().numpy(), xp) and np.array_equal(out[3].cpu().numpy(), mx) and np.array_equal(out[4].cpu().numpy(), mxp)
+    model.free()
