@@ -458,3 +458,46 @@ def test_select_points_randomised_sweep(engine):
                 assert bool(res.flags_out[b, 0]) == bool(ref.fully_linear[0])
             n_cases += 1
     assert n_cases == 48 * 6 and n_noise <= 8
+
+
+def test_kept_factorisation_randomised_sweep(engine):
+    """Seeded random sweep of the device-resident step (select keeping the round-4 factorisation -> build from it): the model built by
+    build_schur_kernel (or the general route for the instances it does not cover) must agree with the oracle's from-scratch solve of
+    the SAME training set to 1e-10 relative in values and Jacobians, scaled by the conditioning of the training set."""
+    import torch
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import upload_batch
+    rng = np.random.default_rng(777)
+    kernels = ["cubic", "multiquadric", "gaussian"]
+    for trial in range(18):
+        n = int(rng.integers(3, 13)); n_db = int(rng.integers(6, 129)); B = 5
+        cfg = mb.RbfConfig(kernel=kernels[trial % 3], max_model_points=int(rng.choice([-1, -1, 2 * n + 1, n + 4])))
+        host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=float(rng.choice([0.05, 0.1])), func=synthetic.zdt3,
+                                          local_fraction=float(rng.choice([0.2, 0.5, 0.9])), first_instance=1000 * trial)
+        dev = upload_batch(host, "cuda:0")
+        sel, prepared = engine.select_points_keep_dev(cfg, dev.sites, dev.n_db, dev.x_index, dev.x, dev.delta, host["delta_max"],
+                                                      dev.glb, dev.gub, dev.flags_in, dev.max_new)
+        engine.sync()
+        res_np = {k_: getattr(sel, k_).cpu().numpy() for k_ in ("r1", "n_r1", "r2", "n_r2", "r3_sites", "n_r3", "r4", "n_r4")}
+        r3_vals = np.zeros((B, n, 2))
+        for b in range(B):
+            r3_vals[b, :res_np["n_r3"][b]] = synthetic.zdt3(res_np["r3_sites"][b, :res_np["n_r3"][b]])
+        model, status = engine.build_prepared_dev(cfg, prepared, dev.sites, dev.values, dev.x_index, sel, torch.from_numpy(r3_vals).cuda())
+        engine.sync()
+        st = status.cpu().numpy()
+        X = host["x"][:, None, :] + 0.05 * (rng.random((B, 6, n)) - 0.5)
+        Y, J = engine.eval(model, X, True, True)
+        for b in range(B):
+            if st[b] != 0:
+                continue                      # duplicated sites etc.: reported per instance, checked elsewhere
+            ids = [1] + list(res_np["r1"][b, :res_np["n_r1"][b]]) + list(res_np["r2"][b, :res_np["n_r2"][b]])
+            P = np.vstack([host["sites"][b, np.array(ids) - 1], res_np["r3_sites"][b, :res_np["n_r3"][b]].reshape(-1, n),
+                           host["sites"][b, res_np["r4"][b, :res_np["n_r4"][b]].astype(int) - 1].reshape(-1, n)])
+            V = synthetic.zdt3(P)
+            omod = O.build_model(P, V, O.RbfConfig(kernel=cfg.kernel))
+            tol = max(RTOL, 20 * omod.cond * np.finfo(float).eps)
+            Yr = np.array([omod.eval(xx) for xx in X[b]]); Jr = np.array([omod.jac(xx) for xx in X[b]])
+            assert np.abs(Y[b] - Yr).max() <= tol * max(1.0, np.abs(Yr).max()), (trial, b, np.abs(Y[b] - Yr).max(), omod.cond)
+            assert np.abs(J[b] - Jr).max() <= 10 * tol * max(1.0, np.abs(Jr).max()), (trial, b, np.abs(J[b] - Jr).max(), omod.cond)
+        assert (st == 0).sum() >= B - 1
+        model.free(); prepared.free()
