@@ -698,7 +698,15 @@ int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepa
     G.B = B; G.n = n; G.k = k; G.db_stride = kp->db_stride; G.r4_stride = kp->r4_stride; G.train_stride = ts;
     G.sites = sites; G.values = values; G.x_index = x_index; G.r1 = r1; G.n_r1 = n_r1; G.r2 = r2; G.n_r2 = n_r2;
     G.r3_sites = r3_sites; G.r3_values = r3_values; G.n_r3 = n_r3; G.r4 = kp->r4; G.n_r4 = kp->n_r4;
-    G.train_sites = tsit; G.train_values = tval; G.N = Ntmp; G.skip = nullptr;
+    G.train_sites = tsit; G.train_values = tval; G.N = Ntmp;
+    {   // instances whose factorisation was kept (and will be used: same conditions as in build_impl) never take the general route
+        RadFn rf_; double a_; int cpd_ = 0;
+        int deg_ = cfg->polynomial_degree;
+        if (resolve_radfn(ctx, cfg, cfg->shape_parameter, &rf_, &a_, &cpd_) == MRBF_OK && deg_ < cpd_ - 1) deg_ = cpd_ - 1;
+        const bool schur_build = kp->kind == 1 && kp->cfg_degree == deg_ && kp->p > 0 &&
+                                 build_schur_smem_doubles(k, kp->geom.MC, kp->p) * sizeof(double) <= SMEM_LIMIT;
+        G.skip = schur_build ? kp->elig : nullptr;
+    }
     { Timed t_(ctx, 2); CK(launch_gather_training(G, ctx->stream)); }
     ctx->launches += 1;
     return build_impl(ctx, cfg, B, n, k, ts, Ntmp, tsit, tval, nullptr, out, status, kp, values, r3_values, done, sites, r3_sites);
