@@ -49,7 +49,7 @@ struct Round4Params {
 // Geometry of the register-tiled round-4 kernel (mrbf_round4_schur.cu): shared-memory offsets and the layout of the
 // kept factorisation, all in doubles.
 struct SchurGeom {
-    int MC, TR, ntiles, nthreads, eligible;
+    int MC, TR, ntiles, nthreads, eligible, two_variants;
     size_t sm_C, sm_V, sm_Xc, sm_col, sm_red, sm_int, smem_doubles;          // kernel 2 (tiles + elimination)
     size_t ps_Aq, ps_X0, ps_M0, ps_P00, ps_red, ps_int, ps_doubles;           // kernel 1 (panels)
     size_t pw_C, pw_V, pw_Xc, pw_clist, pw_meta, pw_doubles;                  // global panel workspace per instance

@@ -98,6 +98,7 @@ SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     // kept state per instance: M0 (p x p), U (p x MC), C (p x MC), L (MC x MC, column q = q-th accepted pivot), accpos (MC), meta (8)
     g.off_M0 = 0; g.off_U = up4((size_t)pl * pl); g.off_C = g.off_U + (size_t)pl * g.MC; g.off_L = g.off_C + (size_t)pl * g.MC;
     g.off_acc = g.off_L + (size_t)g.MC * g.MC; g.state_doubles = up4(g.off_acc + g.MC + 8);
+    g.two_variants = g.ntiles > 352 ? 1 : 0;
     g.eligible = (p > 0 && g.MC <= 128 && g.nthreads <= 544 && g.smem_doubles * sizeof(double) <= (size_t)225 * 1024 &&
                   g.ps_doubles * sizeof(double) <= (size_t)225 * 1024) ? 1 : 0;
     return g;
@@ -300,7 +301,11 @@ __global__ void __launch_bounds__(256, 4) round4_panels_kernel(Round4Params P, S
 
 // Kernel 2 of 2: the panels come back from the workspace into shared memory, every thread computes its 4 x 4 tiles of A and W and
 // the blocked elimination runs in registers.  One CTA per SM (the tiles fill the register file).
-__global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, SchurGeom g) {
+// Two launch shapes of the same code, every instance is taken by exactly one: SMALL (<= 352 tiles, i.e. <= 100 candidates: 352
+// threads, so the CTA leaves ~28 k registers and 80 KB of shared memory of its SM to CTAs of other streams -- rounds 1-3, the
+// panels kernel or the build of another slice of the batch) and the full shape (544 threads, <= 128 candidates).
+template <bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Round4Params P, SchurGeom g) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = poly_dim(n, P.cfg.polynomial_degree);
@@ -322,6 +327,7 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
     int* r4 = P.r4 + (size_t)b * P.r4_stride;
     double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
     const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
+    if (g.two_variants && (SMALL != (schur_tiles(TRa) <= 352))) return;      // the other launch shape's instance
     {
         const int q4 = MCa >> 2;
         const double* Cg = pw + g.pw_C; const double* Vg = pw + g.pw_V; const double* Xg = pw + g.pw_Xc;
@@ -539,10 +545,18 @@ __global__ void __launch_bounds__(544, 1) round4_schur_kernel(Round4Params P, Sc
 cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaStream_t s) {
     const size_t psmem = g.ps_doubles * sizeof(double), smem = g.smem_doubles * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(round4_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(round4_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(round4_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(round4_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     round4_panels_kernel<<<P.B, 256, psmem, s>>>(P, g);
-    round4_schur_kernel<<<P.B, g.nthreads, smem, s>>>(P, g);
+    if (g.two_variants) {
+        round4_schur_kernel<true><<<P.B, 352, smem, s>>>(P, g);
+        round4_schur_kernel<false><<<P.B, g.nthreads, smem, s>>>(P, g);
+    } else if (g.nthreads <= 352) {
+        round4_schur_kernel<true><<<P.B, g.nthreads, smem, s>>>(P, g);
+    } else {
+        round4_schur_kernel<false><<<P.B, g.nthreads, smem, s>>>(P, g);
+    }
     return cudaGetLastError();
 }
 
