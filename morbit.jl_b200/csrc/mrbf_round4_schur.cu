@@ -17,9 +17,13 @@
 //     candidates) never touch memory: every thread owns one 4 x 4 tile of each in registers, computed directly from
 //     the shared-memory panels C (Lagrange coefficients), V = B - Phi00 C / 2 and the candidate sites
 //         A_ij = phi(|xi_i - xi_j|) - c_i.v_j - v_i.c_j ,      W_ij = delta_ij + c_i.c_j .
-//     Per pivot: the tile column owners publish the pivot column (64 B per thread), one barrier, every live tile does
-//     a 4 x 4 rank-1 update of A and of W.  The Cholesky factor column (pivot column / d) is streamed out for
-//     mrbf_build_prepared_dev, which finishes the model with two triangular solves per output.
+//     The elimination is blocked, four pivots (one tile column) at a time: the diagonal-tile thread runs the four pivot
+//     tests in registers, the tiles of that tile column publish the pivot panel, every tile to the right applies the
+//     rank-4 update; the hand-overs are split-phase mbarriers.  The Cholesky factor rows (pivot column / d) are streamed
+//     out for mrbf_build_prepared_dev, which finishes the model with two triangular solves per output.
+//   * two kernels: round4_panels_kernel (candidate list, Pi_0^{-1}, panels; four instances per SM) hands the panels over
+//     through an L2-resident workspace to round4_schur_kernel (tiles + elimination; the tiles fill the register file, one
+//     instance per SM, in two launch shapes: <= 100 candidates on 352 threads / 157 registers, else 544 threads).
 //
 // Instances that do not qualify (N0 != p, singular Pi_0) are marked n_r4 = -1 for the literal kernel; batches whose
 // database is larger than 128 sites or whose panels do not fit in shared memory use round4_block_kernel instead.
