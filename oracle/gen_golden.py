@@ -31,6 +31,11 @@ BUILD = [  # name, n, kernel, deg, N, k, shape
     ("mod_n30_cubic", 30, "cubic", 1, 61, 2, float("nan")),
     ("mod_n6_underdetermined", 6, "cubic", 1, 3, 1, float("nan")),
 ]
+DESCENT = [  # name, n, k, boxed, normalize
+    ("lp_n2_k2", 2, 2, False, True),
+    ("lp_n30_k2_box", 30, 2, True, True),
+    ("lp_n12_k5_box_raw", 12, 5, True, False),
+]
 
 
 def main():
@@ -63,7 +68,20 @@ def main():
         Y = np.array([m.eval(xx) for xx in X]); J = np.array([m.jac(xx) for xx in X])
         np.savez(os.path.join(OUT, name + ".npz"), kind="model", kernel=kernel, deg=deg, shape=shape, sites=S, values=V, X=X, Y=Y, J=J,
                  w=m.w, lam=m.lam, cond=m.cond)
-    print("wrote", len(SELECT) + len(BUILD), "fixtures to", OUT)
+    from oracle import descent_oracle as D
+    for i, (name, n, k, boxed, normalize) in enumerate(DESCENT):          # steepest-descent LP (descent.jl:75-135), HiGHS
+        rng = np.random.default_rng(3000 + i)
+        B = 8
+        jac = rng.normal(size=(B, k, n)) * rng.choice([1.0, 1e-3, 20.0], size=(B, 1, 1))
+        x = rng.random((B, n))
+        lb = np.full(n, 0.0 if boxed else -np.inf); ub = np.full(n, 1.0 if boxed else np.inf)
+        if boxed:
+            x[::3, 0] = 0.0; x[1::3, -1] = 1.0
+        d = np.zeros((B, n)); om = np.zeros(B)
+        for b in range(B):
+            d[b], om[b] = D.lp_highs(x[b], jac[b], lb, ub, normalize)
+        np.savez(os.path.join(OUT, name + ".npz"), kind="descent", jac=jac, x=x, lb=lb, ub=ub, normalize=normalize, d=d, omega=om)
+    print("wrote", len(SELECT) + len(BUILD) + len(DESCENT), "fixtures to", OUT)
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ def _check_select(g, r1, r2, r3_sites, r4, dirs, fully_linear):
 
 
 def test_fixtures_exist():
-    assert len(SEL) >= 6 and len(MOD) >= 6
+    assert len(SEL) >= 6 and len(MOD) >= 6 and len([g for g in GOLD if os.path.basename(g).startswith("lp_")]) >= 3
 
 
 @pytest.mark.parametrize("path", SEL, ids=os.path.basename)
@@ -74,3 +74,31 @@ def test_cuda_model_matches_golden(engine, path):
     assert np.abs(Y[0] - g["Y"]).max() <= 1e-10 * np.abs(g["Y"]).max()
     assert np.abs(J[0] - g["J"]).max() <= 1e-10 * np.abs(g["J"]).max()
     model.free()
+
+
+LP = [g for g in GOLD if os.path.basename(g).startswith("lp_")]
+
+
+@pytest.mark.parametrize("path", LP, ids=os.path.basename)
+def test_lp_oracles_match_golden(path):
+    """Steepest-descent LP (descent.jl:75-135): HiGHS reproduces the frozen criticality values; for k = 2 the independent breakpoint
+    enumeration agrees with them too."""
+    from oracle import descent_oracle as D
+    g = np.load(path)
+    for b in range(len(g["omega"])):
+        d, om = D.lp_highs(g["x"][b], g["jac"][b], g["lb"], g["ub"], bool(g["normalize"]))
+        assert abs(om - g["omega"][b]) <= 1e-10 * max(1.0, abs(g["omega"][b]))
+        if g["jac"].shape[1] == 2:
+            assert abs(D.lp_k2_exact(g["x"][b], g["jac"][b], g["lb"], g["ub"], bool(g["normalize"])) - g["omega"][b]) <= 1e-9 * max(1.0, abs(g["omega"][b]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", LP, ids=os.path.basename)
+def test_cuda_descent_direction_matches_golden(engine, path):
+    from oracle import descent_oracle as D
+    g = np.load(path)
+    d, omega, iters, status = engine.descent_direction(g["jac"], g["x"], g["lb"], g["ub"], bool(g["normalize"]))
+    assert np.all(status == 0)
+    assert np.abs(omega - g["omega"]).max() <= 1e-9 * max(1.0, np.abs(g["omega"]).max())
+    for b in range(len(omega)):
+        D.check_optimal(g["x"][b], g["jac"][b], g["lb"], g["ub"], d[b], omega[b], bool(g["normalize"]))
