@@ -226,6 +226,24 @@ int mrbf_descent_direction_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, c
                                const double* lb, const double* ub, int32_t normalize,
                                double* d, double* omega, int32_t* iters, int32_t* status);
 
+/* ---- device-resident database + model swap (lock-step multistart driver) ----------------------
+ * new_result!(db, x, y) for B databases that live on the device (src/Databases.jl:174-183; value-less results are the
+ * "unevaluated" ones of :202-205 and are stored as NaN rows): instance b appends its first n_add[b] rows of
+ * new_sites (B x add_stride x n) / new_values (B x add_stride x k, or NULL => NaN) behind its n_db[b] sites, ids
+ * n_db[b]+1 .. ; first_id[b] = id of the first appended row; n_db is updated in place.  status[b] = 1 (and nothing is
+ * written, first_id[b] = 0) when the instance's capacity db_stride would be exceeded.  The box scan of
+ * results_in_box_indices (:324-327) runs inside mrbf_select_points*_dev on the same buffers, so an iteration uploads
+ * nothing but the values of the newly evaluated sites. */
+int mrbf_db_append_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int32_t db_stride, double* sites, double* values,
+                       int32_t* n_db, int32_t add_stride, const double* new_sites, const double* new_values,
+                       const int32_t* n_add, int32_t* first_id, int32_t* status);
+/* Replace instances of a model batch by instances of another (the container swaps a rebuilt model in,
+ * src/SurrogateContainer.jl:376-382): instance s < S of `src` becomes instance map[s] of `dst` (map[s] < 0: skipped).
+ * Lets a lock-step driver rebuild a subset of the instances (criticality loop, model-improvement steps) in a compact
+ * batch.  Both batches must have the same n, k, polynomial tail and radial function; `dst` may have a larger train_stride
+ * (room for more training points per instance) than `src`. */
+int mrbf_model_scatter_dev(mrbf_ctx* ctx, mrbf_model* dst, const mrbf_model* src, const int32_t* map, int32_t S);
+
 #ifdef __cplusplus
 }
 #endif

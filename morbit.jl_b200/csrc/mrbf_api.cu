@@ -914,4 +914,37 @@ int mrbf_descent_direction(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, const
     return MRBF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ device-resident database
+int mrbf_db_append_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int32_t db_stride, double* sites, double* values,
+                       int32_t* n_db, int32_t add_stride, const double* new_sites, const double* new_values,
+                       const int32_t* n_add, int32_t* first_id, int32_t* status) {
+    if (!ctx || !sites || !values || !n_db || !new_sites || !n_add || !first_id) return MRBF_EINVAL;
+    if (B <= 0 || n <= 0 || k <= 0 || db_stride <= 0 || add_stride <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
+    CK(cudaSetDevice(ctx->device));
+    DbAppendParams P{};
+    P.B = B; P.n = n; P.k = k; P.db_stride = db_stride; P.add_stride = add_stride;
+    P.sites = sites; P.values = values; P.n_db = n_db; P.new_sites = new_sites; P.new_values = new_values; P.n_add = n_add;
+    P.first_id = first_id; P.status = status;
+    CK(launch_db_append(P, ctx->stream));
+    ctx->launches += 1;
+    return MRBF_OK;
+}
+
+int mrbf_model_scatter_dev(mrbf_ctx* ctx, mrbf_model* dst, const mrbf_model* src, const int32_t* map, int32_t S) {
+    if (!ctx || !dst || !src || !map) return MRBF_EINVAL;
+    if (S <= 0 || S > src->B) return fail(ctx, MRBF_EINVAL, "mrbf_model_scatter: S must be in 1..B(src)%s");
+    if (dst->n != src->n || dst->k != src->k || dst->train_stride < src->train_stride || dst->p != src->p || dst->deg != src->deg ||
+        dst->kernel != src->kernel || dst->ibeta != src->ibeta || dst->sgn != src->sgn)
+        return fail(ctx, MRBF_EINVAL, "mrbf_model_scatter: the two model batches differ in shape or radial function%s");
+    CK(cudaSetDevice(ctx->device));
+    ModelScatterParams P{};
+    P.S = S; P.B_dst = dst->B; P.n = src->n; P.k = src->k; P.train_stride = src->train_stride; P.dst_stride = dst->train_stride; P.pl = src->p > 0 ? src->p : 1;
+    P.map = map; P.src_N = src->N; P.src_centers = src->centers; P.src_w = src->w; P.src_lam = src->lam; P.src_alpha2 = src->alpha2;
+    P.dst_N = dst->N; P.dst_centers = dst->centers; P.dst_w = dst->w; P.dst_lam = dst->lam; P.dst_alpha2 = dst->alpha2;
+    CK(launch_model_scatter(P, ctx->stream));
+    dst->pack_valid = false;
+    ctx->launches += 1;
+    return MRBF_OK;
+}
+
 }  // extern "C"

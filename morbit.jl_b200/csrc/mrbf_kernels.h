@@ -128,6 +128,20 @@ struct DescentParams {
     double* d; double* omega; int* iters; int* status;
 };
 
+struct DbAppendParams {
+    int B, n, k, db_stride, add_stride;
+    double* sites; double* values; int* n_db;
+    const double* new_sites; const double* new_values; const int* n_add;
+    int* first_id; int* status;
+};
+
+struct ModelScatterParams {
+    int S, B_dst, n, k, train_stride, dst_stride, pl;
+    const int* map;
+    const int* src_N; const double* src_centers; const double* src_w; const double* src_lam; const double* src_alpha2;
+    int* dst_N; double* dst_centers; double* dst_w; double* dst_lam; double* dst_alpha2;
+};
+
 size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride);
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
@@ -158,5 +172,7 @@ size_t descent_warp_doubles(int n, int k);
 int descent_max_outputs();
 cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s);
 cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s);
+cudaError_t launch_db_append(const DbAppendParams& P, cudaStream_t s);
+cudaError_t launch_model_scatter(const ModelScatterParams& P, cudaStream_t s);
 
 }  // namespace mrbf

@@ -407,6 +407,27 @@ class Engine:
                                                 _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(out[4])))
         return out
 
+    # ------------------------------------------------------------------ device-resident database / model swap
+    def db_append_dev(self, sites, values, n_db, new_sites, new_values, n_add, first_id=None, status=None):
+        """new_result! for B device-resident databases (Databases.jl:174-183): appends the first n_add[b] rows of new_sites
+        (B x add_stride x n) and new_values (B x add_stride x k, None => NaN = unevaluated); n_db is updated in place.
+        Returns (first_id, status) -- status[b] = 1 when the capacity would be exceeded (nothing written)."""
+        import torch
+        B, db_stride, n = sites.shape
+        k = values.shape[2]
+        if first_id is None:
+            first_id = torch.empty(B, dtype=torch.int32, device=sites.device)
+        if status is None:
+            status = torch.empty(B, dtype=torch.int32, device=sites.device)
+        self._check(self.lib.mrbf_db_append_dev(self.ctx, B, n, k, db_stride, _ptr(sites), _ptr(values), _ptr(n_db), new_sites.shape[1],
+                                                _ptr(new_sites), _ptr(new_values), _ptr(n_add), _ptr(first_id), _ptr(status)))
+        return first_id, status
+
+    def model_scatter_dev(self, dst: ModelBatch, src: ModelBatch, index_map, S: Optional[int] = None):
+        """Instance s < S of `src` replaces instance index_map[s] of `dst` (negative: skipped), SurrogateContainer.jl:376-382."""
+        self._check(self.lib.mrbf_model_scatter_dev(self.ctx, dst.handle, src.handle, _ptr(index_map),
+                                                    int(index_map.shape[0] if S is None else S)))
+
     def backtrack(self, model: ModelBatch, x, direction, step0, omega, armijo_c=1e-6, shrink=0.75,
                   min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict=True):
         """descent.jl:150-185 with every step size evaluated in one launch."""

@@ -312,6 +312,12 @@ class FilterTrace:
     """Decision margins, so tests can detect knife-edge inputs."""
     best: List[float] = field(default_factory=list)
     runner_up: List[float] = field(default_factory=list)
+    first: List[bool] = field(default_factory=list)     # entry belongs to an unconditional first pick (exact arg-max of exact norms)
+
+    def knife_edge(self, rtol: float = 1e-9) -> bool:
+        """True when a pivot test or an arg-max between candidates was decided by less than rtol (relative)."""
+        return any((not f) and abs(b - r) <= rtol * max(abs(b), abs(r)) for b, r, f in zip(self.best, self.runner_up, self.first)
+                   if math.isfinite(b) and math.isfinite(r))
 
 
 def affinely_independent_filter(x0, seeds: Sequence[np.ndarray], pivot_val: float, n_wanted: int,
@@ -330,7 +336,7 @@ def affinely_independent_filter(x0, seeds: Sequence[np.ndarray], pivot_val: floa
     i0 = int(np.argmax(norms))                   # np.argmax returns the first maximiser
     if trace is not None:
         srt = sorted(norms, reverse=True)
-        trace.best.append(srt[0]); trace.runner_up.append(srt[1] if len(srt) > 1 else -math.inf)
+        trace.best.append(srt[0]); trace.runner_up.append(srt[1] if len(srt) > 1 else -math.inf); trace.first.append(True)
     Y = np.hstack((Y, shifted[i0][:, None]))
     Z = orthogonal_complement_matrix(Y)
     cand = [i for i in range(len(shifted)) if i != i0]
@@ -348,7 +354,7 @@ def affinely_independent_filter(x0, seeds: Sequence[np.ndarray], pivot_val: floa
             elif val > second:
                 second = val
         if trace is not None:
-            trace.best.append(best_val); trace.runner_up.append(max(second, pivot_val))
+            trace.best.append(best_val); trace.runner_up.append(max(second, pivot_val)); trace.first.append(False)
         if best_val > pivot_val:
             Y = np.hstack((Y, shifted[best_index][:, None]))
             Z = orthogonal_complement_matrix(Y)
