@@ -36,6 +36,9 @@ WORKLOAD = (f"C3: {B_PER_GPU} independent multistart ZDT3 n={N_VARS} k={K_OUT} i
             f"(from the kept round-4 factorisation)")
 
 
+LS_CODES = {0: "CONTINUE", 1: "MAX_ITER", 2: "BUDGET_EXHAUSTED", 3: "CRITICAL", 4: "TOLERANCE", 5: "INFEASIBLE", 6: "DB_FULL", 7: "NUMERIC"}
+
+
 def fp64_peak_tflops():
     """Measured FP64 FMA-pipe peak of this pool's B200 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no FP64 figure."""
     path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
@@ -335,6 +338,38 @@ def run_ours(args):
                           "config": {"workload": f"{B} instances per GPU: surrogate Jacobian at the iterate (k={K_OUT}, n={N_VARS}) + exact LP "
                                                  "for the constrained steepest-descent direction"}})
 
+
+    # ---- secondary metric: the whole multistart run in lock-step with device-resident databases:
+    # every instance starts from its Halton point with an empty database and runs iterate! (algorithm.jl:615-917) until it stops
+    if args.lockstep_iters > 0:
+        import time as _time
+        from morbit_jl_b200 import lockstep as LS
+        x0 = synthetic.halton(rank * B + B, N_VARS)[rank * B:]
+        with torch.cuda.stream(stream):
+            barrier()
+            t0 = _time.perf_counter()
+            drv = LS.LockstepDriver(cfg, synthetic.zdt3, x0, np.zeros(N_VARS), np.ones(N_VARS), LS.AlgorithmConfig(max_iter=args.lockstep_iters),
+                                    device=f"cuda:{local}", capacity=N_DB, engine=eng)
+            l0 = eng.launch_count
+            drv.run()
+            stream.synchronize()
+            t_run = _time.perf_counter() - t0
+        it_total = float(drv.iters_done.sum().item()); ev_total = float(drv.num_evals.sum().item())
+        t = torch.tensor([t_run], dtype=torch.float64, device="cuda"); c = torch.tensor([it_total, ev_total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        rc, cnt = np.unique(drv.ret.cpu().numpy(), return_counts=True)
+        secondary.append({"metric": "multistart_instance_iterations_per_s", "value": float(c[0].item()) / float(t.item()), "unit": "iterations/s",
+                          "wall_s": float(t.item()), "lockstep_iterations": int(drv.iter_counter - 1), "instance_iterations": float(c[0].item()),
+                          "true_function_evaluations": float(c[1].item()), "host_function_calls": int(drv.n_func_calls),
+                          "gpu_launches": int(eng.launch_count - l0),
+                          "stop_codes_rank0": {LS_CODES.get(int(a), str(int(a))): int(b_) for a, b_ in zip(rc, cnt)},
+                          "build_failures_rank0": int((drv.build_failures > 0).sum().item()),
+                          "config": {"workload": f"C3 end to end: {B} ZDT3 n={N_VARS} instances per GPU from their Halton starting points, empty databases, "
+                                                 f"max_iter={args.lockstep_iters}, database capacity {N_DB}; wall clock incl. the host objective "
+                                                 "function (NumPy) and its copies; databases never leave the device"}})
+        del drv
+
     clocks = sampler.stop()      # sampled from the first timed step to the end of the device work (build loop, e2e loop, sweeps)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -438,6 +473,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-descent", dest="descent", action="store_false", help="skip the steepest-descent secondary metric")
+    ap.add_argument("--lockstep-iters", type=int, default=20, help="max_iter of the lock-step multistart run (secondary metric; 0 = skip)")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the batch in the end-to-end pipeline (1 = no overlap)")
     args = ap.parse_args()
     if args.impl == "reference":

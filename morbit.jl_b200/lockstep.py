@@ -161,6 +161,7 @@ class LockstepDriver:
         self.r4 = torch.zeros((B, mp), **i32); self.n_r4 = torch.zeros(B, **i32)
         self.dirs = torch.zeros((B, n, n), **f64); self.n_dirs = torch.zeros(B, **i32)
         self.fully_linear = torch.zeros(B, dtype=torch.bool, device=dev)
+        self.build_failures = torch.zeros(B, **i32)
         self.model: Optional[ModelBatch] = None
         self._scratch = {}
         self._all = torch.arange(B, device=dev)
@@ -170,6 +171,7 @@ class LockstepDriver:
         self._lp_out = None
         self._bt_out = None
         self._X2 = torch.zeros((B, 2, n), **f64); self._Y2 = torch.zeros((B, 2, k), **f64)
+        self.numeric_log: List[dict] = []
         self.trace: List[dict] = []          # record=True: host copies of the state after every iterate()
         self.lp_calls: List[dict] = []       # record=True: every criticality computation in order (mask, d, omega)
         # initialize_data: x0 is result #1 of every database (build_super_db, utilities.jl:39)
@@ -251,6 +253,9 @@ class LockstepDriver:
         mdl, status = E.build_prepared_dev(self.cfg, sc.prepared, sites, values, x_index, sel, r3_values, status,
                                            recycle=sc.model)
         bad = (sel.status != 0) | (status != 0)
+        if self.record and bool(bad[:S].any()):
+            self.numeric_log.append(dict(iter=self.iter_counter, select=int((sel.status[:S] != 0).sum()), build=int((status[:S] != 0).sum()),
+                                         build_codes=status[:S][status[:S] != 0][:8].cpu().tolist()))
         # new_result! of the round-3 sites (ids n_db+1.., RbfModel.jl:301-305), now with their values
         tgt = idx_p[:S]
         self._n_add.zero_()
@@ -259,14 +264,22 @@ class LockstepDriver:
         self._add_values[tgt] = r3_values[:S]
         first = self._append(self._add_sites, self._add_values, self._n_add)
         self.num_evals[tgt] += sel.n_r3[:S].to(torch.int64)
-        # commit the meta data
+        # commit the meta data -- only where the coefficient solve succeeded.  A failed solve (reduced kernel matrix not positive
+        # definite: the reference's own training sets become numerically singular on exactly structured databases, its LU then
+        # returns coefficients with cond ~ 1e18) keeps the instance's previous model and meta data; the instance goes on and the
+        # event is counted in `build_failures`.  Without a previous model (initialisation) the instance stops with NUMERIC.
+        ok = ~bad[:S]
+        if main_missing:
+            self.ret[tgt] = torch.where(bad[:S] & (self.ret[tgt] == CONTINUE), NUMERIC, self.ret[tgt])
+        self.build_failures[tgt] += bad[:S].to(torch.int32)
+        tk = tgt[ok]
         for name in ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "dirs", "n_dirs", "r3_sites"):
-            getattr(self, name)[tgt] = getattr(sel, name)[:S]
-        self.r3_values[tgt] = r3_values[:S]
-        self.r3_first[tgt] = first[tgt]
-        self.center[tgt] = x_index[:S]
-        self.fully_linear[tgt] = sel.flags_out[:S, 0] != 0
-        self.ret[tgt] = torch.where(bad[:S] & (self.ret[tgt] == CONTINUE), NUMERIC, self.ret[tgt])
+            getattr(self, name)[tk] = getattr(sel, name)[:S][ok]
+        self.r3_values[tk] = r3_values[:S][ok]
+        self.r3_first[tk] = first[tk]
+        self.center[tk] = x_index[:S][ok]
+        self.fully_linear[tk] = sel.flags_out[:S, 0][ok] != 0
+        self.fully_linear[tgt[~ok]] = False
         if main_missing:
             # main model batch: room for the training set of the select kernels plus the sites that model-improvement steps
             # push onto round1_indices afterwards (RbfModel.jl:719); allocated once through a placeholder build
@@ -276,6 +289,8 @@ class LockstepDriver:
         sc.model = mdl
         if imap is None:
             imap = self._all.to(torch.int32)
+        imap = imap.clone()
+        imap[:S] = torch.where(ok, imap[:S], -1)
         E.model_scatter_dev(self.model, mdl, imap.contiguous(), Sp)
 
     def _improve(self, idx):
@@ -327,7 +342,11 @@ class LockstepDriver:
         sc.train = E.gather_training_dev(g(self.sites), g(self.values), g(self.x_index), sel, g(self.r3_values), ts, out=sc.train)
         status = torch.zeros(Sp, dtype=torch.int32, device=self.dev)
         sc.model_scratch, status = E.build_dev(cfg, sc.train[0], sc.train[1], sc.train[2], None, status, recycle=sc.model_scratch)
-        self.ret[idx] = torch.where((status[:S] != 0) & (self.ret[idx] == CONTINUE), NUMERIC, self.ret[idx])
+        ok = status[:S] == 0                               # a failed solve keeps the previous model (see _update)
+        self.build_failures[idx] += (~ok).to(torch.int32)
+        self.fully_linear[idx[~ok]] = False
+        imap = imap.clone()
+        imap[:S] = torch.where(ok, imap[:S], -1)
         E.model_scatter_dev(self.model, sc.model_scratch, imap.contiguous(), Sp)
 
     # ------------------------------------------------------------------ criticality (descent.jl:187-241)
@@ -396,7 +415,7 @@ class LockstepDriver:
 
         def stop(mask, code):
             nonlocal active, stat
-            m = mask & active
+            m = mask & active & (self.ret == CONTINUE)
             self.ret = W(m, code, self.ret)
             stat = W(m, EARLY_EXIT, stat)
             active = active & ~m

@@ -24,12 +24,14 @@ def halton(num: int, dim: int, start: int = 1) -> np.ndarray:
 
 
 def zdt1(X: np.ndarray) -> np.ndarray:
+    X = np.clip(X, 0.0, 1.0)        # identity on the feasible box; the reference's wall steps can leave it by an ulp (sqrt domain)
     f1 = X[..., 0]
     g = 1.0 + 9.0 * np.mean(X[..., 1:], axis=-1)
     return np.stack([f1, g * (1.0 - np.sqrt(f1 / g))], axis=-1)
 
 
 def zdt3(X: np.ndarray) -> np.ndarray:
+    X = np.clip(X, 0.0, 1.0)
     f1 = X[..., 0]
     g = 1.0 + 9.0 * np.mean(X[..., 1:], axis=-1)
     h = 1.0 - np.sqrt(f1 / g) - (f1 / g) * np.sin(10.0 * np.pi * f1)
