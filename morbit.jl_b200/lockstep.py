@@ -97,6 +97,25 @@ def _intersect_box_absmax(torch, x, d, lb, ub):
     return torch.where(nz.any(1), out, inf)
 
 
+class _Phase:
+    """Wall-clock accounting of the driver's phases (only when LockstepDriver(profile=True): it synchronises around every phase)."""
+    def __init__(self, drv, name):
+        self.drv, self.name = drv, name
+
+    def __enter__(self):
+        if self.drv.profile:
+            import time
+            self.drv.torch.cuda.synchronize(self.drv.dev)
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if self.drv.profile:
+            import time
+            self.drv.torch.cuda.synchronize(self.drv.dev)
+            self.drv.phase_s[self.name] = self.drv.phase_s.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
+
+
 class _Scratch:
     """Per-batch-size scratch: select outputs, kept factorisation, model batch (reused: no allocation per iteration)."""
     def __init__(self):
@@ -117,7 +136,8 @@ class LockstepDriver:
     """
 
     def __init__(self, cfg, func: Callable, x0, glb, gub, ac: Optional[AlgorithmConfig] = None, device: str = "cuda:0",
-                 capacity: int = 128, func_on_device: bool = False, record: bool = False, engine: Optional[Engine] = None):
+                 capacity: int = 128, func_on_device: bool = False, record: bool = False, engine: Optional[Engine] = None,
+                 profile: bool = False, scratch: Optional[dict] = None):
         import torch
         self.torch = torch
         if engine is None:
@@ -127,6 +147,7 @@ class LockstepDriver:
         self.engine, self.cfg, self.func, self.ac = engine, cfg, func, ac or AlgorithmConfig()
         self.func_on_device, self.record = func_on_device, record
         self.n_func_calls = 0
+        self.profile, self.phase_s = profile, {}
         self.n_sites_evaluated = 0
         if self.ac.delta_max > 1.0:
             raise ValueError("delta_max > 1: compute_descent_step's second branch (descent.jl:276-311) is not covered")
@@ -163,7 +184,7 @@ class LockstepDriver:
         self.fully_linear = torch.zeros(B, dtype=torch.bool, device=dev)
         self.build_failures = torch.zeros(B, **i32)
         self.model: Optional[ModelBatch] = None
-        self._scratch = {}
+        self._scratch = scratch if scratch is not None else {}      # per-size device scratch; may be handed on from an earlier driver
         self._all = torch.arange(B, device=dev)
         self._first_id = torch.zeros(B, **i32); self._app_status = torch.zeros(B, **i32)
         self._add_sites = torch.zeros((B, n, n), **f64); self._add_values = torch.zeros((B, n, k), **f64); self._n_add = torch.zeros(B, **i32)
@@ -184,10 +205,11 @@ class LockstepDriver:
         torch = self.torch
         self.n_func_calls += 1
         self.n_sites_evaluated += int(X.shape[0])
-        if self.func_on_device:
-            return self.func(X).to(torch.float64).contiguous()
-        Y = np.asarray(self.func(X.cpu().numpy()), np.float64)
-        return torch.from_numpy(np.ascontiguousarray(Y.reshape(X.shape[0], -1))).to(self.dev)
+        with _Phase(self, "objective_function"):
+            if self.func_on_device:
+                return self.func(X).to(torch.float64).contiguous()
+            Y = np.asarray(self.func(X.cpu().numpy()), np.float64)
+            return torch.from_numpy(np.ascontiguousarray(Y.reshape(X.shape[0], -1))).to(self.dev)
 
     # ------------------------------------------------------------------ database
     def _append(self, new_sites, new_values, n_add):
@@ -238,8 +260,9 @@ class LockstepDriver:
         sc = self._scratch.setdefault(Sp, _Scratch())
         flags = torch.zeros((Sp, 2), dtype=torch.int32, device=self.dev)
         flags[:, 0] = 1 if ensure_fully_linear else 0
-        sel, sc.prepared = E.select_points_keep_dev(self.cfg, sites, n_db, x_index, x, delta, float(self.ac.delta_max), self.glb,
-                                                    self.gub, flags, self._max_new(idx_p), out=sc.sel, prepared=sc.prepared)
+        with _Phase(self, "select_rounds_1_4"):
+            sel, sc.prepared = E.select_points_keep_dev(self.cfg, sites, n_db, x_index, x, delta, float(self.ac.delta_max), self.glb,
+                                                        self.gub, flags, self._max_new(idx_p), out=sc.sel, prepared=sc.prepared)
         sc.sel = sel
         n = self.n
         new = torch.arange(n, device=self.dev)[None, :] < sel.n_r3[:, None]            # (Sp, n) rows of r3_sites that are new sites
@@ -250,8 +273,9 @@ class LockstepDriver:
             r3_values[new] = self._f(sel.r3_sites[new])                                 # eval_missing!, Databases.jl:258-277
         status = torch.zeros(Sp, dtype=torch.int32, device=self.dev)
         main_missing = self.model is None
-        mdl, status = E.build_prepared_dev(self.cfg, sc.prepared, sites, values, x_index, sel, r3_values, status,
-                                           recycle=sc.model)
+        with _Phase(self, "build_from_kept_factor"):
+            mdl, status = E.build_prepared_dev(self.cfg, sc.prepared, sites, values, x_index, sel, r3_values, status,
+                                               recycle=sc.model)
         bad = (sel.status != 0) | (status != 0)
         if self.record and bool(bad[:S].any()):
             self.numeric_log.append(dict(iter=self.iter_counter, select=int((sel.status[:S] != 0).sum()), build=int((status[:S] != 0).sum()),
@@ -341,7 +365,8 @@ class LockstepDriver:
             sc.train = None
         sc.train = E.gather_training_dev(g(self.sites), g(self.values), g(self.x_index), sel, g(self.r3_values), ts, out=sc.train)
         status = torch.zeros(Sp, dtype=torch.int32, device=self.dev)
-        sc.model_scratch, status = E.build_dev(cfg, sc.train[0], sc.train[1], sc.train[2], None, status, recycle=sc.model_scratch)
+        with _Phase(self, "improve_build_from_scratch"):
+            sc.model_scratch, status = E.build_dev(cfg, sc.train[0], sc.train[1], sc.train[2], None, status, recycle=sc.model_scratch)
         ok = status[:S] == 0                               # a failed solve keeps the previous model (see _update)
         self.build_failures[idx] += (~ok).to(torch.int32)
         self.fully_linear[idx[~ok]] = False
@@ -350,14 +375,15 @@ class LockstepDriver:
         E.model_scatter_dev(self.model, sc.model_scratch, imap.contiguous(), Sp)
 
     # ------------------------------------------------------------------ criticality (descent.jl:187-241)
-    def _criticality(self, mask=None):
+    def _criticality(self, mask=None, rec=True):
         """Jacobian at the iterate + exact LP for every instance; (omega, d).  `mask` only labels the recorded call."""
         E = self.engine
-        E.eval_dev(self.model, self.x[:, None, :].contiguous(), None, self._J)
-        self._lp_out = E.descent_direction_dev(self._J.view(self.B, self.k, self.n), self.x, self.glb, self.gub, self.ac.normalize,
-                                               out=self._lp_out)
+        with _Phase(self, "jacobian_lp"):
+            E.eval_dev(self.model, self.x[:, None, :].contiguous(), None, self._J)
+            self._lp_out = E.descent_direction_dev(self._J.view(self.B, self.k, self.n), self.x, self.glb, self.gub, self.ac.normalize,
+                                                   out=self._lp_out)
         d, omega = self._lp_out[0].clone(), self._lp_out[1].clone()
-        if self.record:
+        if self.record and rec:
             m = (self.ret == CONTINUE) if mask is None else mask
             self.lp_calls.append(dict(mask=m.cpu().numpy().copy(), d=d.cpu().numpy(), omega=omega.cpu().numpy()))
         return omega, d
@@ -373,6 +399,7 @@ class LockstepDriver:
         exit_c = torch.zeros_like(C)
         do_loops = C.clone()
         nfl = C & ~self.fully_linear
+        self._fail_mark = self.build_failures.clone()
         if bool(nfl.any()):
             self._update(nfl.nonzero().flatten(), True)
             om2, d2 = self._criticality(nfl)
@@ -381,6 +408,11 @@ class LockstepDriver:
         delta = self.delta.clone()
         delta_0 = self.delta.clone()
         in_loop = do_loops & (delta > ac.mu * omega) & (self.ret == CONTINUE)
+        # The reference rebuilds the models in every loop with the iterate's UNCHANGED radius (:572-579), i.e. with the same inputs
+        # as the loop before unless that update appended new round-3 sites.  An update that appended nothing is a fixed point
+        # (same database, iterate, radius, flags => same training set, model, omega), so it is not recomputed -- exact, not a
+        # heuristic; the loop counters, radius and exit tests still advance as in the reference.
+        fixed = nfl & (self.n_r3 == 0) & (self.build_failures == self._fail_mark)
         while bool(in_loop.any()):
             stop = in_loop & ((loops >= ac.max_critical_loops) | ~self._budget_okay())
             exit_c |= stop
@@ -388,9 +420,15 @@ class LockstepDriver:
             if not bool(in_loop.any()):
                 break
             delta = torch.where(in_loop, ac.gamma_crit * delta, delta)
-            self._update(in_loop.nonzero().flatten(), True)          # the iterate keeps its radius (reference quirk, :572-579)
-            om2, d2 = self._criticality(in_loop)
-            omega = torch.where(in_loop, om2, omega); d = torch.where(in_loop[:, None], d2, d)
+            need = in_loop & ~fixed
+            if bool(need.any()):
+                self._fail_mark = self.build_failures.clone()
+                self._update(need.nonzero().flatten(), True)      # the iterate keeps its radius (reference quirk, :572-579)
+                om2, d2 = self._criticality(need, rec=False)
+                omega = torch.where(need, om2, omega); d = torch.where(need[:, None], d2, d)
+                fixed = fixed | (need & (self.n_r3 == 0) & (self.build_failures == self._fail_mark))
+            if self.record:
+                self.lp_calls.append(dict(mask=in_loop.cpu().numpy().copy(), d=d.cpu().numpy(), omega=omega.cpu().numpy()))
             loops += in_loop.to(torch.int32)
             tol = in_loop & ((delta <= ac.delta_tol_abs) | ((omega <= ac.omega_tol_rel) & (delta <= ac.delta_tol_rel))
                              | (omega <= ac.omega_tol_abs) | ~self.fully_linear)
@@ -451,8 +489,9 @@ class LockstepDriver:
             norm_d = d.abs().max(1).values
             sigma = W(norm_d > 0, torch.minimum(self.delta / norm_d, torch.ones_like(norm_d)), torch.ones_like(norm_d))
             small = ~(sigma > ac.min_stepsize)
-            self._bt_out = E.backtrack_dev(self.model, x, d.contiguous(), sigma.contiguous(), omega.contiguous(), ac.armijo_const_rhs,
-                                           ac.armijo_const_shrink, ac.min_stepsize, None, ac.strict_backtracking, out=self._bt_out)
+            with _Phase(self, "backtrack"):
+                self._bt_out = E.backtrack_dev(self.model, x, d.contiguous(), sigma.contiguous(), omega.contiguous(), ac.armijo_const_rhs,
+                                               ac.armijo_const_shrink, ac.min_stepsize, None, ac.strict_backtracking, out=self._bt_out)
             x_trial = W(small[:, None], x, self._bt_out[2])
             omega = W(small, torch.zeros_like(omega), omega)
             act_idx = active.nonzero().flatten()
@@ -464,7 +503,8 @@ class LockstepDriver:
             new_index = self._append(self._add_sites, self._add_values, self._n_add)     # put_eval_result_into_db!, :764
             active = active & (self.ret == CONTINUE)
             self._X2[:, 0] = x; self._X2[:, 1] = x_trial
-            E.eval_dev(self.model, self._X2, self._Y2, None)                             # :766-767
+            with _Phase(self, "rho_evals"):
+                E.eval_dev(self.model, self._X2, self._Y2, None)                             # :766-767
             mx, mx_trial = self._Y2[:, 0], self._Y2[:, 1]
             steplength = W(active, (x - x_trial).abs().max(1).values, steplength)        # :773
             if ac.strict_acceptance_test:
