@@ -202,6 +202,134 @@ __global__ void __launch_bounds__(256, 1) eval_tile_kernel(EvalParams P, int l0,
     }
 }
 
+// Values for many trial points when n > 64 (BASELINE config C4: n = 200 -- the Armijo batches of descent.jl:150-185): the tile of
+// 64 trial points stays in shared memory with ALL its coordinates (coordinate-major, centred at the first centre), the centre
+// tiles are streamed through shared memory in chunks of WC coordinates, and the distance contraction runs on the same 4 x 4
+// register micro-tiles as eval_tile_kernel.  The generic one-thread-per-point kernel it replaces ran at ~1 % of the FP64 peak.
+constexpr int WC = 32;          // coordinates per streamed chunk
+constexpr int CLD = TN + 2;     // padded row of the centre chunk (16-byte aligned rows, 4-way instead of 32-way store conflicts)
+
+__global__ void __launch_bounds__(256, 1) eval_wide_kernel(EvalParams P, int l0, int kk, int npad) {
+    constexpr int KG = 4;
+    extern __shared__ __align__(16) double smem[];
+    double* Xs = smem;                    // npad x TM
+    double* Cs = Xs + (size_t)npad * TM;  // WC x CLD
+    double* xx = Cs + WC * CLD;           // TM
+    double* cc = xx + TM;                 // TN
+    double* Wt = cc + TN;                 // KG x TN
+    double* xref = Wt + KG * TN;          // npad
+    const int b = blockIdx.y, n = P.n, k = P.k, tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const long long m0 = (long long)blockIdx.x * TM;
+    const int N = P.N[b];
+    const double* centers = P.centers + (size_t)b * P.train_stride * n;
+    const double* w = P.w + (size_t)b * P.train_stride * k;
+    const int pl = P.p > 0 ? P.p : 1;
+    const double* lam = P.lam + (size_t)b * pl * k;
+    const double* X = P.X + (size_t)b * P.M * n;
+    RadFn rf; rf.kernel = P.kernel; rf.ibeta = P.ibeta; rf.sgn = P.sgn; rf.alpha2 = P.alpha2[b];
+
+    for (int c = tid; c < npad; c += 256) xref[c] = (c < n) ? centers[c] : 0.0;
+    __syncthreads();
+    for (int e = tid; e < TM * n; e += 256) {              // coalesced read of the point tile (AoS rows)
+        const int pt = e / n, c = e % n;
+        const long long mi = m0 + pt;
+        Xs[c * TM + pt] = (mi < P.M) ? X[(size_t)mi * n + c] - xref[c] : 0.0;
+    }
+    for (int e = tid; e < TM * (npad - n); e += 256) { const int pt = e % TM, c = n + e / TM; Xs[c * TM + pt] = 0.0; }
+    __syncthreads();
+    if (tid < TM) { double s = 0.0; for (int c = 0; c < n; ++c) { double a = Xs[c * TM + tid]; s = fma(a, a, s); } xx[tid] = s; }
+
+    double accY[4][KG];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int l = 0; l < KG; ++l) accY[a][l] = 0.0;
+
+    for (int c0 = 0; c0 < N; c0 += TN) {
+        double d[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[a][j] = 0.0;
+        double ccp = 0.0;
+        for (int k0 = 0; k0 < npad; k0 += WC) {
+            __syncthreads();                                 // the previous chunk (and the previous tile's Wt / cc) has been consumed
+            for (int e = tid; e < TN * WC; e += 256) {       // lanes over the chunk's coordinates: contiguous 256-byte reads per centre
+                const int j = e / WC, c = e % WC;
+                Cs[c * CLD + j] = (c0 + j < N && k0 + c < n) ? centers[(size_t)(c0 + j) * n + k0 + c] - xref[k0 + c] : 0.0;
+            }
+            if (k0 == 0)
+                for (int e = tid; e < KG * TN; e += 256) {
+                    const int l = e / TN, j = e % TN;
+                    Wt[e] = (l < kk && c0 + j < N) ? w[(size_t)(c0 + j) * k + l0 + l] : 0.0;
+                }
+            __syncthreads();
+            if (tid < TN) {
+#pragma unroll 8
+                for (int c = 0; c < WC; ++c) { const double a = Cs[c * CLD + tid]; ccp = fma(a, a, ccp); }
+            }
+            const double* xrow = Xs + (size_t)k0 * TM + 4 * ty;
+#pragma unroll 4
+            for (int c = 0; c < WC; ++c) {
+                const double2 x01 = *reinterpret_cast<const double2*>(xrow + c * TM);
+                const double2 x23 = *reinterpret_cast<const double2*>(xrow + c * TM + 2);
+                const double2 c01 = *reinterpret_cast<const double2*>(Cs + c * CLD + 4 * tx);
+                const double2 c23 = *reinterpret_cast<const double2*>(Cs + c * CLD + 4 * tx + 2);
+                const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+                const double cv[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[a][j] = fma(xv[a], cv[j], d[a][j]);
+            }
+        }
+        if (tid < TN) cc[tid] = ccp;
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double r2 = fma(-2.0, d[a][j], xx[4 * ty + a] + cc[4 * tx + j]);
+                r2 = fmax(r2, 0.0);
+                d[a][j] = rad_phi(rf, r2);
+            }
+#pragma unroll
+        for (int l = 0; l < KG; ++l)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double wj = Wt[l * TN + 4 * tx + j];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) accY[a][l] = fma(d[a][j], wj, accY[a][l]);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int l = 0; l < KG; ++l) {
+            double s = accY[a][l];
+            s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
+            accY[a][l] = s;
+        }
+    if (P.Y && tx == 0) {
+        for (int a = 0; a < 4; ++a) {
+            const long long mi = m0 + 4 * ty + a;
+            if (mi >= P.M) continue;
+            for (int l = 0; l < kk; ++l) {
+                double s = accY[a][l];
+                if (P.deg >= 0) s += lam[l0 + l];
+                if (P.deg >= 1) {
+                    double t = 0.0;
+                    for (int c = 0; c < n; ++c) t = fma(lam[(size_t)(c + 1) * k + l0 + l], Xs[c * TM + 4 * ty + a] + xref[c], t);
+                    s += t;
+                }
+                P.Y[((size_t)b * P.M + mi) * k + l0 + l] = s;
+            }
+        }
+    }
+}
+
 // Few trial points per instance (the Jacobian at the iterate, the rho test: M = 1; descent.jl:196, algorithm.jl:766): the tiled
 // kernels would run 64-point tiles with one live row.  Here ONE WARP takes one (instance, point): lanes over the centres for
 // phi / psi (each lane walks its centre's contiguous coordinates), the weighted psi go through shared memory, then lanes over
@@ -791,6 +919,27 @@ static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launc
     return cudaSuccess;
 }
 
+static size_t eval_wide_smem(int npad) {
+    return sizeof(double) * ((size_t)npad * TM + (size_t)WC * CLD + TM + TN + 4 * TN + npad);
+}
+
+static cudaError_t launch_wide(const EvalParams& P, cudaStream_t s, int* n_launches) {
+    const int npad = ((P.n + WC - 1) / WC) * WC;
+    const size_t smem = eval_wide_smem(npad);
+    cudaError_t e = cudaFuncSetAttribute(eval_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long tiles = (P.M + TM - 1) / TM;
+    for (int l0 = 0; l0 < P.k; l0 += 4) {
+        const int kk = (P.k - l0) < 4 ? (P.k - l0) : 4;
+        dim3 grid((unsigned)tiles, (unsigned)P.B);
+        eval_wide_kernel<<<grid, 256, smem, s>>>(P, l0, kk, npad);
+        if (n_launches) ++*n_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
     if (P.M <= 0 || P.B <= 0) return cudaSuccess;
     const bool want_j = P.J != nullptr;
@@ -826,6 +975,7 @@ cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
         }
     }
     if (P.B > 65535) return cudaErrorInvalidValue;
+    if (!want_j && P.n > 64 && eval_wide_smem(((P.n + WC - 1) / WC) * WC) <= 227 * 1024) return launch_wide(P, s, n_launches);
     dim3 grid((unsigned)((P.M + 127) / 128), (unsigned)P.B);
     eval_generic_kernel<<<grid, 128, 0, s>>>(P);
     if (n_launches) ++*n_launches;

@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
             // eliminate column kk from every other row; columns <= kk of the left block are never read again
             for (int c = kk + 1 + warp; c < 2 * p; c += nwarps) {
                 const double pk = Aq[kk + c * pl];
+#pragma unroll 8
                 for (int i = lane; i < p; i += 32) if (i != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], pk, Aq[i + c * pl]);
             }
             __syncthreads();
@@ -903,6 +904,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
             for (int j = 0; j < T; ++j) acc[j] = 0.0;
             if (r < 2 * p) {
                 const double* Mx = (r < p) ? (H + r) : (M0 + (r - p));
+#pragma unroll 8
                 for (int c = 0; c < p; ++c) {
                     const double mv = Mx[c * pl];
 #pragma unroll
@@ -913,6 +915,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
                 for (int j = 0; j < T; ++j) if (j < tb) dst[j * pl] = acc[j];
             } else {
                 const int i = r - 2 * p;
+#pragma unroll 8
                 for (int k = 0; k < n; ++k) {
                     const double cv_ = Ct[k * NM + i];
 #pragma unroll
@@ -937,6 +940,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
 #pragma unroll
             for (int j = 0; j < T; ++j) acc[j] = 0.0;
             if (r < p) {
+#pragma unroll 8
                 for (int c = 0; c < p; ++c) {
                     const double mv = P00[r + c * pl];
 #pragma unroll
@@ -947,6 +951,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
             } else {
                 const int eta = r - p;
                 const double* ge = Gm + eta * pb; const double* ce = Cm + eta * pb;
+#pragma unroll 8
                 for (int c = 0; c < p; ++c) {
                     const double gv = ge[c], cv_ = ce[c];
 #pragma unroll
@@ -977,6 +982,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
                 for (int j = 0; j < T; ++j) acc[j] = 0.0;
                 if (r < m) {
                     const double* lr = Li + tri(r);
+#pragma unroll 4
                     for (int c = l; c <= r; c += G) {
                         const double lv = lr[c];
 #pragma unroll
@@ -1090,6 +1096,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
 #pragma unroll
                 for (int q = 0; q < T; ++q) acc[q] = 0.0;
                 if (c < m)
+#pragma unroll 4
                     for (int r = c + l; r < m; r += G) {
                         const double lv = Li[tri(r) + c];
 #pragma unroll
@@ -1120,6 +1127,7 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
                     HV[jq * pl + r] = h;
                 }
             __syncthreads();
+#pragma unroll 4
             for (int e = tid; e < p * p; e += nt) {
                 const int a_ = e % p, b_ = e / p;
                 double h = H[a_ + b_ * pl];

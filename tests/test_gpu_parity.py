@@ -182,6 +182,36 @@ def test_eval_generic_kernel_large_n(engine):
     model.free()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,N,k,M,kernel", [(200, 401, 5, 119, "cubic"), (70, 90, 1, 300, "gaussian"), (65, 110, 6, 64, "multiquadric"),
+                                            (130, 200, 2, 9, "cubic")])
+def test_eval_wide_kernel_values_large_n(engine, n, N, k, M, kernel):
+    """n > 64, values only (the Armijo batches of BASELINE config C4: n = 200, 401 centres, 5 outputs, 119 trial points):
+    eval_wide_kernel against the oracle, ragged N per instance, trial points inside the trust region."""
+    rng = np.random.default_rng(n + N)
+    B = 3
+    cfg = mb.RbfConfig(kernel=kernel)
+    Ns = [N, max(n + 2, N - 37), N]
+    S = np.zeros((B, N, n)); V = np.zeros((B, N, k))
+    for b in range(B):
+        x = 0.3 + 0.4 * rng.random(n)
+        S[b] = x + 0.2 * (rng.random((N, n)) - 0.5)
+        V[b] = np.stack([np.sum((S[b] - 0.1 * l) ** 2, -1) for l in range(k)], -1)
+    wr, lr, st = CO.build_batched(cfg, S, V, Ns)
+    model, status = engine.build(cfg, S, V, Ns)
+    X = S[:, :1] + 0.1 * (rng.random((B, M, n)) - 0.5)
+    Y, _ = engine.eval(model, X, True, False)
+    for b in range(B):
+        Yr = CO.eval_points(cfg, S[b, :Ns[b]], wr[b, :Ns[b]], lr[b], X[b])
+        cond = O.build_model(S[b, :Ns[b]], V[b, :Ns[b]], O.RbfConfig(kernel=kernel)).cond
+        tol = max(RTOL, 20 * cond * np.finfo(float).eps)          # LU (oracle) vs null-space solves differ at O(cond * eps)
+        assert np.abs(Y[b] - Yr).max() <= tol * np.abs(Yr).max(), (b, cond, np.abs(Y[b] - Yr).max() / np.abs(Yr).max())
+    # the same points through the Jacobian route (generic kernel) give the same values
+    Y2, _ = engine.eval(model, X, True, True)
+    assert np.abs(Y - Y2).max() <= 1e-12 * np.abs(Y2).max()
+    model.free()
+
+
 def test_local_trust_region_cancellation(engine):
     """Sites within Δ = 1e-3 of each other far from the origin: the centred GEMM form must keep 1e-10."""
     rng = np.random.default_rng(17)

@@ -31,9 +31,9 @@ def main():
     stream = torch.cuda.Stream()
     eng = mb.Engine(0, stream=stream.cuda_stream)
     rows = []
-    for shape in (float("nan"), 1.0):
+    for shape in ((float("nan"), 1.0) if len(sys.argv) < 2 else (float("nan"),)):
         cfg = mb.RbfConfig(kernel="cubic", shape_parameter=shape, max_model_points=2 * n + 1, theta_enlarge_1=2.0, theta_pivot=0.25)
-        for B in (1, 64, 592):
+        for B in ((1, 64, 592) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1].split(','))):
             host, func = batch(B, n, k, n_db)
             dev = upload_batch(host)
             builder = MultistartBuilder(eng, cfg, 0.5)
