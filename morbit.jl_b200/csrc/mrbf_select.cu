@@ -715,15 +715,18 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
-template <int T, bool SMEM>
-__global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
+template <int T, bool SMEM, int NT>
+__global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
     // Blocked variant of the shared-memory round 4: T candidates are evaluated together against the factorisation as it was
     // before the block (a rejected candidate never changes the state, so this speculation cannot fail); the few quantities
     // that depend on which block members were accepted -- the extra Cholesky entries e_ij, the pivots d_j^2 and the
     // leverages -- are resolved by an O(T^3) scalar "panel" step, exactly the recurrences of a blocked left-looking
     // Cholesky.  Barriers per candidate drop from ~4 to ~9/T and every phase has T times more parallel work.
     extern __shared__ double smem[];
-    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = 256, lane = tid & 31, warp = tid >> 5, nwarps = 8;
+    // NT = 256 when the state lives in shared memory; 1024 when it lives in global memory (large n or many model points):
+    // every phase is then a stream of L2 accesses and four times the warps hide four times the latency.
+    constexpr int nt = NT, nwarps = NT / 32;
+    const int b = blockIdx.x, n = P.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NM = P.NM;
     const int deg = P.cfg.polynomial_degree;
     const int p = poly_dim(n, deg);
@@ -746,11 +749,11 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
     double* Sc = Px + T * T;           // T x T    panel: corrected s'_ij, 1 + lev'_j on the diagonal
     double* PT = Sc + T * T;           // T x pl   pi~ of the block members
     double* RI = PT + T * pl;          // T        1 / (1 + lev'_j) of accepted members
-    double* tnp = RI + T;              // 8 x T    per-warp partial ||t_j||^2
-    double* tauq = tnp + 8 * T;        // pl
+    double* tnp = RI + T;              // nwarps x T  per-warp partial ||t_j||^2 (room for 32 warps)
+    double* tauq = tnp + 32 * T;       // pl
     double* red = tauq + pl;           // 80
-    int* ib = reinterpret_cast<int*>(red + 80);   // ids[T], acc[T], pos[T], misc[8]
-    double* st = red + 80 + 2 * T + 4;
+    int* ib = reinterpret_cast<int*>(red + 80);   // ids[T], acc[T], pos[T], per-warp counts[nwarps], na
+    double* st = red + 80 + 2 * T + 4 + 16;
     double* fs;
     if constexpr (SMEM) fs = st; else fs = (P.keep_fs ? P.keep_fs : P.fs) + (size_t)b * P.fs_stride;
     double* Ct = fs;                   // NM x n  coordinate-major centres
@@ -1083,10 +1086,10 @@ __global__ void __launch_bounds__(256) round4_block_kernel(Round4Params P) {
                     Px[q * T + c] = v / Ex[jq * T + jq];
                 }
             }
-            if (lane == 0) ib[3 * T + 8] = na_;
+            if (lane == 0) ib[3 * T + nwarps] = na_;
         }
         __syncthreads();
-        const int na = ib[3 * T + 8];
+        const int na = ib[3 * T + nwarps];
         // ---- P6: append the accepted members
         if (na > 0) {
             // new rows of L^{-1}: columns < m from  -P_^{-1} (T_ L^{-1}),  columns >= m from P_^{-1}
@@ -1230,19 +1233,19 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
 }
 size_t round4_block_vec_doubles(int T, int n, int NM, int p) {
     int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
-    return (size_t)T * n + (size_t)T * NM + 4 * (size_t)T * pl + 2 * (size_t)T * MM + 7 * (size_t)T * T + 9 * (size_t)T + pl + 80 + 2 * T + 4;
+    return (size_t)T * n + (size_t)T * NM + 4 * (size_t)T * pl + 2 * (size_t)T * MM + 7 * (size_t)T * T + 33 * (size_t)T + pl + 80 + 2 * T + 4 + 16;
 }
 template <int T>
 static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream_t s) {
     cudaError_t e;
     if (P.fs_in_smem) {
-        e = cudaFuncSetAttribute(round4_block_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(round4_block_kernel<T, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        round4_block_kernel<T, true><<<P.B, 256, smem, s>>>(P);
+        round4_block_kernel<T, true, 256><<<P.B, 256, smem, s>>>(P);
     } else {
-        e = cudaFuncSetAttribute(round4_block_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(round4_block_kernel<T, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        round4_block_kernel<T, false><<<P.B, 256, smem, s>>>(P);
+        round4_block_kernel<T, false, 1024><<<P.B, 1024, smem, s>>>(P);
     }
     return cudaGetLastError();
 }
