@@ -17,6 +17,7 @@
 // The whole system lives in shared memory when (N^2 + N (p + k)) doubles fit, else in an L2-resident
 // global workspace; the code is identical, only the base pointer differs.
 #include "mrbf_common.cuh"
+#include <cstdlib>
 #include "mrbf_kernels.h"
 
 namespace mrbf {
@@ -690,14 +691,22 @@ cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStrea
 size_t build_vec_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return 2 * (size_t)ld + pl + 80; }
 size_t build_ws_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; return (size_t)ld * ld + (size_t)ld * pl + (size_t)ld * k; }
 
+template <int NT>
+static cudaError_t launch_build_nt(const BuildParams& P, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(build_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    build_kernel<NT><<<P.B, NT, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_build(const BuildParams& P, size_t smem, cudaStream_t s) {
     const bool few_large = P.B <= 148 && !P.ws_in_smem;
-    cudaError_t e = few_large ? cudaFuncSetAttribute(build_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : cudaFuncSetAttribute(build_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (few_large) build_kernel<1024><<<P.B, 1024, smem, s>>>(P);
-    else build_kernel<256><<<P.B, 256, smem, s>>>(P);
-    return cudaGetLastError();
+    int nt = few_large ? 1024 : 256;
+    // a system that needs more than half of the SM's shared memory runs one CTA per SM anyway: more threads per CTA then shorten
+    // every barrier phase at no cost in occupancy
+    if (!few_large && smem > 113 * 1024) nt = 1024;
+    if (const char* ev = getenv("MRBF_BUILD_NT")) { const int v = atoi(ev); if (v == 256 || v == 512 || v == 1024) nt = v; }
+    return nt == 1024 ? launch_build_nt<1024>(P, smem, s) : (nt == 512 ? launch_build_nt<512>(P, smem, s) : launch_build_nt<256>(P, smem, s));
 }
 
 }  // namespace mrbf

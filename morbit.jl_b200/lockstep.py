@@ -257,7 +257,7 @@ class LockstepDriver:
             n_db, x_index = self.n_db.index_select(0, idx_p), self.x_index.index_select(0, idx_p)
             x, delta = self.x.index_select(0, idx_p), self.delta.index_select(0, idx_p)
         Sp = int(idx_p.numel())
-        sc = self._scratch.setdefault(Sp, _Scratch())
+        sc = self._scratch.setdefault((Sp, self.n, self.k, self.cap, self.cfg.kernel, self.cfg.max_model_points, self.cfg.polynomial_degree), _Scratch())
         flags = torch.zeros((Sp, 2), dtype=torch.int32, device=self.dev)
         flags[:, 0] = 1 if ensure_fully_linear else 0
         with _Phase(self, "select_rounds_1_4"):
@@ -356,7 +356,7 @@ class LockstepDriver:
         # improve_model = update_model: from-scratch solve of [centre; r1; r2; r3; r4] for the whole sub-batch
         S, idx_p, imap = self._subset(idx)
         Sp = int(idx_p.numel())
-        sc = self._scratch.setdefault(Sp, _Scratch())
+        sc = self._scratch.setdefault((Sp, self.n, self.k, self.cap, self.cfg.kernel, self.cfg.max_model_points, self.cfg.polynomial_degree), _Scratch())
         g = lambda t: t.index_select(0, idx_p)
         sel = SelectResult(g(self.r1), g(self.n_r1), g(self.r2), g(self.n_r2), g(self.r3_sites), g(self.n_r3), g(self.r4), g(self.n_r4),
                            None, None, None, None)
