@@ -22,43 +22,80 @@
 
 namespace mrbf {
 
-// Right-looking Cholesky (lower) of the m x m block of A starting at (off, off).  red[74] <- failing column + 1.
-__device__ void chol_lower(double* A, int ld, int off, int m, double* red) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+// Right-looking Cholesky (lower) of the m x m block of A starting at (off, off); returns 0, or the failing column + 1 (the same
+// value in every thread).  ONE barrier per column: every thread reads the pivot d^2 itself (no thread-0 section), the trailing update
+// uses the unscaled column (a_il -= u_i u_l / d^2), and the scaling of column c (u / d, diagonal <- d) is deferred into the phase
+// of column c + 1, where nobody reads that column any more.
+__device__ int chol_lower(double* A, int ld, int off, int m) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    double prev_d2 = 1.0;
     for (int c = 0; c < m; ++c) {
         const int pc = off + c;
-        if (tid == 0) {
-            double d = A[pc + (size_t)pc * ld];
-            if (!(d > 0.0)) red[74] = (double)(c + 1);
-            else { d = sqrt(d); A[pc + (size_t)pc * ld] = d; red[75] = d; }
-        }
-        __syncthreads();
-        if (red[74] != 0.0) return;
-        const double dd = red[75];
+        const double d2 = A[pc + (size_t)pc * ld];           // final: the barrier below closed the update of column c - 1
+        if (!(d2 > 0.0)) return c + 1;                        // uniform: every thread read the same value
+        const double rd2 = 1.0 / d2;
         const int rem = m - c - 1;
-        for (int i = tid; i < rem; i += nt) A[pc + 1 + i + (size_t)pc * ld] /= dd;
-        __syncthreads();
+        if (c > 0) {                                          // deferred scaling of column c - 1
+            const double dp = sqrt(prev_d2), rdp = 1.0 / dp;
+            double* pcol = A + (size_t)(pc - 1) * ld + pc;
+            for (int i = tid; i <= rem; i += nt) pcol[i] *= rdp;
+            if (tid == 0) A[pc - 1 + (size_t)(pc - 1) * ld] = dp;
+        }
         {   // trailing update, lower triangle only: a warp per column, lanes down the rows (coalesced, no index divisions)
-            const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
             const double* colp = A + (size_t)pc * ld + pc + 1;
             for (int l = warp; l < rem; l += nwarps) {
-                const double al = colp[l];
+                const double al = colp[l] * rd2;
                 double* dst = A + (size_t)(pc + 1 + l) * ld + pc + 1;
                 int i = l + lane;
                 for (; i + 96 < rem; i += 128) {             // four independent load pairs in flight per lane
                     const double c0 = colp[i], c1 = colp[i + 32], c2 = colp[i + 64], c3 = colp[i + 96];
-                    const double d0 = dst[i], d1 = dst[i + 32], d2 = dst[i + 64], d3 = dst[i + 96];
-                    dst[i] = fma(-c0, al, d0); dst[i + 32] = fma(-c1, al, d1); dst[i + 64] = fma(-c2, al, d2); dst[i + 96] = fma(-c3, al, d3);
+                    const double d0 = dst[i], d1 = dst[i + 32], d2_ = dst[i + 64], d3 = dst[i + 96];
+                    dst[i] = fma(-c0, al, d0); dst[i + 32] = fma(-c1, al, d1); dst[i + 64] = fma(-c2, al, d2_); dst[i + 96] = fma(-c3, al, d3);
                 }
                 for (; i < rem; i += 32) dst[i] = fma(-colp[i], al, dst[i]);
             }
         }
+        prev_d2 = d2;
         __syncthreads();
     }
+    if (m > 0 && tid == 0) { const int pl_ = off + m - 1; A[pl_ + (size_t)pl_ * ld] = sqrt(prev_d2); }
+    __syncthreads();
+    return 0;
 }
 
-// Solve L L' U = Y in place for the k columns of Yv (rows off..off+m), L from chol_lower.
+// Solve L L' U = Y in place for the k columns of Yv (rows off..off+m), L from chol_lower.  A warp per right-hand side, no block
+// barriers inside: forward substitution as column axpys (the column of L is contiguous), backward substitution as column dots.
 __device__ void chol_solve(const double* A, int ld, int off, int m, double* Yv, int ldy, int k) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int q = warp; q < k; q += nwarps) {
+        double* y = Yv + (size_t)q * ldy;
+        for (int c = 0; c < m; ++c) {                 // forward
+            const int pc = off + c;
+            const double* col = A + (size_t)pc * ld;
+            const double yc = y[pc] / col[pc];
+            __syncwarp();
+            if (lane == 0) y[pc] = yc;
+            for (int i = pc + 1 + lane; i < off + m; i += 32) y[i] = fma(-col[i], yc, y[i]);
+            __syncwarp();
+        }
+        for (int c = m - 1; c >= 0; --c) {            // backward with L'
+            const int pc = off + c;
+            const double* col = A + (size_t)pc * ld;
+            double a = 0.0;
+            for (int i = pc + 1 + lane; i < off + m; i += 32) a = fma(col[i], y[i], a);
+            a = warp_sum(a);
+            __syncwarp();
+            if (lane == 0) y[pc] = (y[pc] - a) / col[pc];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+
+// The same solve with the whole CTA per step and block barriers: better when A lives in the global workspace (every step is an
+// L2 round trip, which 32 warps overlap and one warp does not).
+__device__ void chol_solve_block(const double* A, int ld, int off, int m, double* Yv, int ldy, int k) {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int c = 0; c < m; ++c) {                 // forward
         const int pc = off + c;
@@ -159,8 +196,8 @@ __global__ void __launch_bounds__(NT) build_kernel(BuildParams P) {
             A[i + (size_t)j * ld] = a;
         }
         __syncthreads();
-        chol_lower(A, ld, 0, N, red);
-        if (red[74] != 0.0) { if (tid == 0) P.status[b] = (int)red[74]; return; }
+        const int bad0 = chol_lower(A, ld, 0, N);
+        if (bad0) { if (tid == 0) P.status[b] = bad0; return; }
         chol_solve(A, ld, 0, N, Yv, ld, k);
         for (int e = tid; e < p * k; e += nt) {
             const int c = e / k, q = e % k;
@@ -173,29 +210,28 @@ __global__ void __launch_bounds__(NT) build_kernel(BuildParams P) {
         return;
     }
 
-    // ---- Householder QR of Pi, reflectors applied to Pi, Y and two-sidedly to Phi
+    // ---- Householder QR of Pi, reflectors applied to Pi, Y and two-sidedly to Phi.  Three barriers per reflector: the column norm
+    // and v' pv are computed by every warp for itself (identical arithmetic, no block reduction), pv - K v is folded into the
+    // rank-2 update, and the rows of pv = tau Phi v are split over G threads each.
+    const int G = (nt >= 1024) ? 8 : ((nt >= 512) ? 4 : 2);
     for (int j = 0; j < p; ++j) {
         double part = 0.0;
-        for (int i = j + 1 + tid; i < N; i += nt) { double a = Pm[i + (size_t)j * ld]; part = fma(a, a, part); }
-        const double xn2 = block_sum(part, red);
-        if (tid == 0) {
-            double alpha = Pm[j + (size_t)j * ld], xnorm = sqrt(xn2), tau = 0.0, sc = 0.0, beta = alpha;
+        for (int i = j + 1 + lane; i < N; i += 32) { const double a = Pm[i + (size_t)j * ld]; part = fma(a, a, part); }
+        const double xn2 = warp_sum(part);
+        const double alpha = Pm[j + (size_t)j * ld];
+        double tau = 0.0, sc = 0.0, beta = alpha;
+        {
+            const double xnorm = sqrt(xn2);
             if (xnorm != 0.0) {
                 beta = -copysign(hypot(alpha, xnorm), alpha);
                 tau = (beta - alpha) / beta; sc = 1.0 / (alpha - beta);
             }
-            tauv[j] = tau; red[70] = sc; red[71] = beta;
         }
-        __syncthreads();
-        const double tau = tauv[j], sc = red[70];
-        for (int i = tid; i < N; i += nt) {
-            double vi = (i < j) ? 0.0 : ((i == j) ? 1.0 : Pm[i + (size_t)j * ld] * sc);
-            v[i] = vi;
-            if (i > j) Pm[i + (size_t)j * ld] = vi;
-        }
-        if (tid == 0) Pm[j + (size_t)j * ld] = red[71];
-        __syncthreads();
-        if (tau == 0.0) continue;
+        for (int i = tid; i < N; i += nt) v[i] = (i < j) ? 0.0 : ((i == j) ? 1.0 : Pm[i + (size_t)j * ld] * sc);
+        __syncthreads();                                     // v complete; nobody reads column j of Pi any more in this step
+        for (int i = j + 1 + tid; i < N; i += nt) Pm[i + (size_t)j * ld] = v[i];
+        if (tid == 0) { Pm[j + (size_t)j * ld] = beta; tauv[j] = tau; }
+        if (tau == 0.0) { __syncthreads(); continue; }
         // trailing columns of Pi and all columns of Y: warp per column
         const int ncols = (p - j - 1) + k;
         for (int cc = warp; cc < ncols; cc += nwarps) {
@@ -205,61 +241,63 @@ __global__ void __launch_bounds__(NT) build_kernel(BuildParams P) {
             a = warp_sum(a) * tau;
             for (int i = j + lane; i < N; i += 32) col[i] = fma(-a, v[i], col[i]);
         }
-        // Phi <- H Phi H :  pv = tau Phi v ; K = tau/2 v'pv ; wv = pv - K v ; Phi -= v wv' + wv v'
-        double part2 = 0.0;
-        for (int i = tid; i < N; i += nt) {
+        // pv = tau Phi v (v is zero above row j)
+        for (int r0 = 0; r0 < N; r0 += nt / G) {
+            const int i = r0 + tid / G, g = tid % G;
             double a0 = 0.0, a1 = 0.0;
-            int l = j;
-            for (; l + 8 <= N; l += 8) {                     // eight loads in flight per thread
-                const double* ap = A + i + (size_t)l * ld;
-                const double x0 = ap[0], x1 = ap[ld], x2 = ap[2 * (size_t)ld], x3 = ap[3 * (size_t)ld];
-                const double x4 = ap[4 * (size_t)ld], x5 = ap[5 * (size_t)ld], x6 = ap[6 * (size_t)ld], x7 = ap[7 * (size_t)ld];
-                a0 = fma(x0, v[l], a0); a1 = fma(x1, v[l + 1], a1); a0 = fma(x2, v[l + 2], a0); a1 = fma(x3, v[l + 3], a1);
-                a0 = fma(x4, v[l + 4], a0); a1 = fma(x5, v[l + 5], a1); a0 = fma(x6, v[l + 6], a0); a1 = fma(x7, v[l + 7], a1);
+            if (i < N) {
+                int l = j + g;
+                for (; l + G < N; l += 2 * G) { a0 = fma(A[i + (size_t)l * ld], v[l], a0); a1 = fma(A[i + (size_t)(l + G) * ld], v[l + G], a1); }
+                if (l < N) a0 = fma(A[i + (size_t)l * ld], v[l], a0);
             }
-            for (; l + 2 <= N; l += 2) { a0 = fma(A[i + (size_t)l * ld], v[l], a0); a1 = fma(A[i + (size_t)(l + 1) * ld], v[l + 1], a1); }
-            for (; l < N; ++l) a0 = fma(A[i + (size_t)l * ld], v[l], a0);
-            const double a = tau * (a0 + a1);
-            pv[i] = a;
-            part2 = fma(v[i], a, part2);
+            a0 += a1;
+            for (int o = G >> 1; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            if (i < N && g == 0) pv[i] = tau * a0;
         }
-        const double K = 0.5 * tau * block_sum(part2, red);
-        for (int i = tid; i < N; i += nt) pv[i] = fma(-K, v[i], pv[i]);
-        __syncthreads();
-        for (int l = warp; l < N; l += nwarps) {            // rank-2 update, a warp per column (v is zero above row j)
-            const double vl = v[l], pl_ = pv[l];
+        __syncthreads();                                     // pv complete
+        double part2 = 0.0;
+        for (int i = j + lane; i < N; i += 32) part2 = fma(v[i], pv[i], part2);
+        const double K = 0.5 * tau * warp_sum(part2);
+        // Phi <- H Phi H :  wv = pv - K v ;  Phi -= v wv' + wv v'   (a warp per column; v is zero above row j)
+        for (int l = warp; l < N; l += nwarps) {
+            const double vl = v[l], wl = fma(-K, vl, pv[l]);
             double* dst = A + (size_t)l * ld;
             int i = ((l >= j) ? 0 : j) + lane;
             for (; i + 96 < N; i += 128) {
                 const double d0 = dst[i], d1 = dst[i + 32], d2 = dst[i + 64], d3 = dst[i + 96];
-                dst[i] = d0 - (v[i] * pl_ + pv[i] * vl); dst[i + 32] = d1 - (v[i + 32] * pl_ + pv[i + 32] * vl);
-                dst[i + 64] = d2 - (v[i + 64] * pl_ + pv[i + 64] * vl); dst[i + 96] = d3 - (v[i + 96] * pl_ + pv[i + 96] * vl);
+                const double v0 = v[i], v1 = v[i + 32], v2 = v[i + 64], v3 = v[i + 96];
+                dst[i] = d0 - (v0 * wl + fma(-K, v0, pv[i]) * vl); dst[i + 32] = d1 - (v1 * wl + fma(-K, v1, pv[i + 32]) * vl);
+                dst[i + 64] = d2 - (v2 * wl + fma(-K, v2, pv[i + 64]) * vl); dst[i + 96] = d3 - (v3 * wl + fma(-K, v3, pv[i + 96]) * vl);
             }
-            for (; i < N; i += 32) dst[i] -= v[i] * pl_ + pv[i] * vl;
+            for (; i < N; i += 32) { const double vi = v[i]; dst[i] -= vi * wl + fma(-K, vi, pv[i]) * vl; }
         }
         __syncthreads();
     }
     // ---- Cholesky of Z' Phi Z and the solves
     const int m = N - p;
-    chol_lower(A, ld, p, m, red);
-    if (red[74] != 0.0) { if (tid == 0) P.status[b] = (int)red[74]; return; }
-    chol_solve(A, ld, p, m, Yv, ld, k);                      // rows p.. of Yv now hold u
-    for (int e = tid; e < p * k; e += nt) {                  // top block: (Q'y)_top - Phi~[top, bottom] u
-        const int r = e % p, q = e / p;
-        double a = Yv[r + (size_t)q * ld];
-        for (int c = 0; c < m; ++c) a = fma(-A[r + (size_t)(p + c) * ld], Yv[p + c + (size_t)q * ld], a);
-        Yv[r + (size_t)q * ld] = a;
+    const int bad = chol_lower(A, ld, p, m);
+    if (bad) { if (tid == 0) P.status[b] = bad; return; }
+    if (in_smem) chol_solve(A, ld, p, m, Yv, ld, k); else chol_solve_block(A, ld, p, m, Yv, ld, k);    // rows p.. of Yv now hold u
+    for (int o = warp; o < p * k; o += nwarps) {             // top block: (Q'y)_top - Phi~[top, bottom] u, a warp per entry
+        const int r = o % p, q = o / p;
+        double a = 0.0;
+        for (int c = lane; c < m; c += 32) a = fma(A[r + (size_t)(p + c) * ld], Yv[p + c + (size_t)q * ld], a);
+        a = warp_sum(a);
+        if (lane == 0) Yv[r + (size_t)q * ld] -= a;
     }
     __syncthreads();
-    for (int c = p - 1; c >= 0; --c) {                       // R lambda = top
-        if (tid < k) Yv[c + (size_t)tid * ld] /= Pm[c + (size_t)c * ld];
-        __syncthreads();
-        for (int e = tid; e < c * k; e += nt) {
-            const int r = e % c, q = e / c;
-            Yv[r + (size_t)q * ld] = fma(-Pm[r + (size_t)c * ld], Yv[c + (size_t)q * ld], Yv[r + (size_t)q * ld]);
+    for (int q = warp; q < k; q += nwarps) {                 // R lambda = top: a warp per right-hand side, column axpys (no block barriers)
+        double* y = Yv + (size_t)q * ld;
+        for (int c = p - 1; c >= 0; --c) {
+            const double* col = Pm + (size_t)c * ld;
+            const double yc = y[c] / col[c];
+            __syncwarp();
+            if (lane == 0) y[c] = yc;
+            for (int r = lane; r < c; r += 32) y[r] = fma(-col[r], yc, y[r]);
+            __syncwarp();
         }
-        __syncthreads();
     }
+    __syncthreads();
     for (int e = tid; e < p * k; e += nt) { const int c = e / k, q = e % k; lam_out[(size_t)c * k + q] = Yv[c + (size_t)q * ld]; }
     __syncthreads();
     for (int e = tid; e < p * k; e += nt) { const int r = e % p, q = e / p; Yv[r + (size_t)q * ld] = 0.0; }

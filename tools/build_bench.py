@@ -17,7 +17,10 @@ def main():
     stream = torch.cuda.Stream()
     eng = mb.Engine(0, stream=stream.cuda_stream)
     rows = []
-    for (B, n, N, k, kern) in ((4096, 30, 61, 2, "multiquadric"), (4096, 30, 128, 2, "multiquadric"), (4096, 10, 66, 2, "cubic"), (1024, 30, 256, 2, "multiquadric")):
+    configs = ((4096, 30, 61, 2, "multiquadric"), (4096, 30, 128, 2, "multiquadric"), (4096, 10, 66, 2, "cubic"), (1024, 30, 256, 2, "multiquadric"))
+    if len(sys.argv) > 1:
+        configs = (configs[int(sys.argv[1])],)
+    for (B, n, N, k, kern) in configs:
         rng = np.random.default_rng(N)
         cfg = mb.RbfConfig(kernel=kern)
         x = 0.3 + 0.4 * rng.random((B, 1, n))
