@@ -614,7 +614,14 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     Pb.w = m->w; Pb.lam = m->lam; Pb.alpha2_out = m->alpha2; Pb.status = status; Pb.ld = train_stride | 1;
     const size_t vecd = build_vec_doubles(n, k, Pb.ld, p), wsd = build_ws_doubles(n, k, Pb.ld, p);
     size_t smem = vecd * sizeof(double);
-    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) { Pb.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); Pb.smem_ws_doubles = (int)wsd; }
+    if ((vecd + wsd) * sizeof(double) <= SMEM_LIMIT) {
+        Pb.ws_in_smem = 1; smem = (vecd + wsd) * sizeof(double); Pb.smem_ws_doubles = (int)wsd;
+        // room left: stage the sites coordinate-major for the Gram-matrix assembly (row-per-lane reads of the AoS sites in global
+        // memory cost 32 L1 wavefronts per load instruction -- 40 % of the LSU traffic of the whole kernel)
+        const size_t stage = (size_t)n * (size_t)(train_stride | 1);
+        // only when the system alone already limits the SM to one CTA: for small systems the extra shared memory costs residency
+        if (smem > 113 * 1024 && (vecd + wsd + stage) * sizeof(double) <= SMEM_LIMIT) { Pb.stage_off = (int)(vecd + wsd); smem += stage * sizeof(double); }
+    }
     else {
         // worst case does not fit: give every CTA the whole shared memory; instances whose own N fits use it,
         // the rest fall back to the global workspace

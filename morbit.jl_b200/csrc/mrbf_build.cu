@@ -170,6 +170,22 @@ __global__ void __launch_bounds__(NT) build_kernel(BuildParams P) {
             __syncthreads();
             sp = mats;
         }
+        if (in_smem && P.stage_off > 0) {
+            // sites staged coordinate-major (St[c * Np + i]): lanes down the rows read consecutive doubles, the column's site is a broadcast
+            double* St = smem + P.stage_off;
+            const int Np = N | 1;
+            for (int e = tid; e < N * n; e += nt) { const int i = e / n, c = e % n; St[c * Np + i] = sites[e]; }
+            __syncthreads();
+            for (int j = warp; j < N; j += nwarps)
+                for (int i = j + lane; i < N; i += 32) {
+                    double r2 = 0.0;
+#pragma unroll 6
+                    for (int c = 0; c < n; ++c) { const double d = St[c * Np + i] - St[c * Np + j]; r2 = fma(d, d, r2); }
+                    const double ph = rad_phi(rf, r2);
+                    A[i + (size_t)j * ld] = ph;
+                    A[j + (size_t)i * ld] = ph;
+                }
+        } else
         for (int j = warp; j < N; j += nwarps) {             // a warp per column, lanes down the rows: lower triangle, then mirror
             const double* sj = sp + (size_t)j * n;
             for (int i = j + lane; i < N; i += 32) {

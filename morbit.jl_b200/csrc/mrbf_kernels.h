@@ -72,6 +72,7 @@ struct BuildParams {
     const int* N; const double* sites; const double* values; const double* shape;
     double* w; double* lam; double* alpha2_out; int* status;
     double* ws; size_t ws_stride; int ws_in_smem; int ld; int smem_ws_doubles;
+    int stage_off;        // > 0: offset (doubles) of a coordinate-major staging area for the sites behind the in-smem system
     const int* skip;      // instances already built by the prepared path (or NULL)
     double* centers_out;  // when non-NULL the kernel also copies the training sites into the model
     int* N_out;
