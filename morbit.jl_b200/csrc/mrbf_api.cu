@@ -230,6 +230,13 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             if ((fv + fsd) * sizeof(double) <= SMEM_LIMIT) { R.fs_in_smem = 1; fsmem = (fv + fsd) * sizeof(double); R.fs = nullptr; }
             else {
                 R.fs_in_smem = 0;
+                // the state streams from L2 / HBM: when the reduced system can get large (many model points beyond the polynomial
+                // basis) 16 candidates share every pass over the packed L^{-1}
+                const char* t16 = getenv("MRBF_R4_T16");
+                const bool want16 = t16 ? atoi(t16) != 0 : (NM - p >= 192);
+                if (want16 && round4_block_vec_doubles(16, n, NM, p) * sizeof(double) <= SMEM_LIMIT) {
+                    Tb = 16; fsmem = round4_block_vec_doubles(16, n, NM, p) * sizeof(double);
+                }
                 if (!keep_out) { ENSURE(ctx->ws[9], (size_t)B * fsd * sizeof(double)); R.fs = (double*)ctx->ws[9].p; }
             }
             Timed t_(ctx, 1);

@@ -1250,6 +1250,12 @@ static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream
     return cudaGetLastError();
 }
 cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s) {
+    if (T == 16) {      // global-memory state, many accepted points: 16 candidates per pass over the packed L^{-1} (half the L2 / HBM traffic)
+        cudaError_t e = cudaFuncSetAttribute(round4_block_kernel<16, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        round4_block_kernel<16, false, 512><<<P.B, 512, smem, s>>>(P);
+        return cudaGetLastError();
+    }
     return T == 8 ? launch_block_t<8>(P, smem, s) : launch_block_t<4>(P, smem, s);
 }
 cudaError_t launch_gather_training(const GatherParams& P, cudaStream_t s) {
