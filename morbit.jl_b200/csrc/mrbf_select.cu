@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
             // eliminate column kk from every other row; columns <= kk of the left block are never read again
             for (int c = kk + 1 + warp; c < 2 * p; c += nwarps) {
                 const double pk = Aq[kk + c * pl];
+                if (pk == 0.0) continue;           // identity columns of the right block that no pivot row has touched yet: nothing to eliminate
 #pragma unroll 8
                 for (int i = lane; i < p; i += 32) if (i != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], pk, Aq[i + c * pl]);
             }

@@ -16,8 +16,9 @@ def main():
     eng = mb.Engine(0, stream=stream.cuda_stream)
     cfg = mb.RbfConfig(kernel="multiquadric")
     rows = []
-    for n_db in (31, 128, 512):
-        B = 4096
+    sizes = (31, 128, 512) if len(sys.argv) < 2 else (int(sys.argv[1]),)
+    for n_db in sizes:
+        B = 4096 if len(sys.argv) < 3 else int(sys.argv[2])
         host = synthetic.multistart_batch(B, n=30, n_db=n_db, delta=0.1, delta_max=0.5, func=synthetic.zdt3)
         dev = upload_batch(host, "cuda:0")
         builder = MultistartBuilder(eng, cfg, 0.5)
