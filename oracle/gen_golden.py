@@ -31,6 +31,9 @@ BUILD = [  # name, n, kernel, deg, N, k, shape
     ("mod_n30_cubic", 30, "cubic", 1, 61, 2, float("nan")),
     ("mod_n6_underdetermined", 6, "cubic", 1, 3, 1, float("nan")),
 ]
+TRAJ = [  # name, starting points, max_iter: example_two_parabolas.jl (x0 of the example first)
+    ("traj_two_parabolas", [[-np.pi, 2.71828], [2.0, -1.5], [0.4, 2.9], [-2.2, -0.6]], 25),
+]
 DESCENT = [  # name, n, k, boxed, normalize
     ("lp_n2_k2", 2, 2, False, True),
     ("lp_n30_k2_box", 30, 2, True, True),
@@ -81,7 +84,24 @@ def main():
         for b in range(B):
             d[b], om[b] = D.lp_highs(x[b], jac[b], lb, ub, normalize)
         np.savez(os.path.join(OUT, name + ".npz"), kind="descent", jac=jac, x=x, lb=lb, ub=ub, normalize=normalize, d=d, omega=om)
-    print("wrote", len(SELECT) + len(BUILD) + len(DESCENT), "fixtures to", OUT)
+    from oracle import iterate_oracle as IO
+    for name, x0s, max_iter in TRAJ:                                        # whole optimize runs (algorithm.jl:919-958), two parabolas
+        f = lambda z: np.array([np.sum((np.asarray(z) - 1.0) ** 2), np.sum((np.asarray(z) + 1.0) ** 2)])
+        x0s = np.asarray(x0s, np.float64); n = x0s.shape[1]
+        T = max_iter + 1
+        rec = dict(ret=np.full((len(x0s), T), -1), it_stat=np.full((len(x0s), T), -1), x_index=np.zeros((len(x0s), T), int),
+                   n_db=np.zeros((len(x0s), T), int), delta=np.zeros((len(x0s), T)), x=np.zeros((len(x0s), T, n)), fx=np.zeros((len(x0s), T, 2)),
+                   rho=np.full((len(x0s), T), np.nan), omega=np.full((len(x0s), T), np.nan), n_train=np.zeros((len(x0s), T), int),
+                   knife=np.zeros((len(x0s), T), bool), n_iter=np.zeros(len(x0s), int))
+        for b, x0 in enumerate(x0s):
+            run = IO.optimize(f, x0, np.full(n, -np.inf), np.full(n, np.inf), O.RbfConfig(kernel="cubic"), IO.AlgoConfig(max_iter=max_iter))
+            rec["n_iter"][b] = len(run.records)
+            for t, r in enumerate(run.records):
+                rec["ret"][b, t], rec["it_stat"][b, t], rec["x_index"][b, t], rec["n_db"][b, t] = r.ret_code, r.it_stat, r.x_index, r.n_db
+                rec["delta"][b, t], rec["x"][b, t], rec["fx"][b, t], rec["rho"][b, t], rec["omega"][b, t] = r.delta, r.x, r.fx, r.rho, r.omega
+                rec["n_train"][b, t], rec["knife"][b, t] = len(r.training_ids), r.knife
+        np.savez(os.path.join(OUT, name + ".npz"), kind="trajectory", x0=x0s, max_iter=max_iter, **rec)
+    print("wrote", len(SELECT) + len(BUILD) + len(DESCENT) + len(TRAJ), "fixtures to", OUT)
 
 
 if __name__ == "__main__":
