@@ -307,8 +307,8 @@ __device__ __forceinline__ int filter_run(FilterState& st, const double* S /* sh
     return found;
 }
 
-template <bool WZS, bool STS>   // W/Z in shared memory; projections in shared memory (fixes the address space at compile time)
-__global__ void __launch_bounds__(256, 3) select_rounds123_kernel(SelectParams P) {
+template <bool WZS, bool STS, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) select_rounds123_kernel(SelectParams P) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x;
     const int ldz = (n + 3) & ~3;              // rows padded to a multiple of 4 (zero rows): the scoring tiles load row quads
@@ -1214,17 +1214,19 @@ size_t round4_ws_doubles(int n, int NM, int p) {
     return (size_t)NM * n + (size_t)NM * NM + (size_t)NM * pl + (size_t)pl * pl + 2 * (size_t)NM * NM;
 }
 
-template <bool WZS, bool STS>
+template <bool WZS, bool STS, int NT>
 static cudaError_t launch_select_t(const SelectParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(select_rounds123_kernel<WZS, STS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(select_rounds123_kernel<WZS, STS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    select_rounds123_kernel<WZS, STS><<<P.B, 256, smem, s>>>(P);
+    select_rounds123_kernel<WZS, STS, NT><<<P.B, NT, smem, s>>>(P);
     return cudaGetLastError();
 }
 cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s) {
-    if (P.wz_in_smem && P.st_in_smem) return launch_select_t<true, true>(P, smem, s);
-    if (P.wz_in_smem) return launch_select_t<true, false>(P, smem, s);
-    return launch_select_t<false, false>(P, smem, s);
+    if (P.wz_in_smem && P.st_in_smem) return launch_select_t<true, true, 256>(P, smem, s);
+    if (P.wz_in_smem) return launch_select_t<true, false, 256>(P, smem, s);
+    // W / Z in the global workspace (n > ~100): every phase streams L2, twice the warps hide twice the latency (the block arg-max
+    // has scratch for 16 warps)
+    return launch_select_t<false, false, 512>(P, smem, s);
 }
 cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid) {
     cudaError_t e = cudaFuncSetAttribute(round4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
