@@ -823,32 +823,37 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         for (int e = tid; e < p * p; e += nt) { int i = e % p, j = e / p; Qx[i + j * pl] = (i == j) ? 1.0 : 0.0; }
         __syncthreads();
         for (int kk = 0; kk < p; ++kk) {
-            if (warp == 0) {                       // pivot search, row swap and scaling by one warp
-                ArgMax mine; mine.v = 0.0; mine.id = -1;
-                for (int i = kk + lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(Aq[i + kk * pl]); c_.id = i; mine = better(mine, c_); }
+            // One barrier per step and no serial section: EVERY warp finds the pivot of column kk for itself (identical arithmetic,
+            // hence identical result), and the warp that owns a column performs that column's row swap and scaling on the fly.
+            // Column kk itself is dead after this step, so it is neither swapped nor scaled: its multipliers are read through
+            // the swap (row piv <- the old diagonal entry).
+            ArgMax mine; mine.v = 0.0; mine.id = -1;
+            for (int i = kk + lane; i < p; i += 32) { ArgMax c_; c_.v = fabs(Aq[i + kk * pl]); c_.id = i; mine = better(mine, c_); }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
-                    mine = better(mine, t_);
-                }
-                if (!(mine.v > 1e-12)) { if (lane == 0) red[76] = 1.0; }       // Pi_0 (scaled to O(1)) is rank deficient
-                else {
-                    const double rp = 1.0 / Aq[mine.id + kk * pl];
-                    __syncwarp();
-                    for (int c = kk + lane; c < 2 * p; c += 32) {
-                        const double a = Aq[mine.id + c * pl], bq = Aq[kk + c * pl];
-                        Aq[mine.id + c * pl] = bq; Aq[kk + c * pl] = a * rp;
-                    }
-                }
+            for (int o = 16; o > 0; o >>= 1) {
+                ArgMax t_; t_.v = __shfl_xor_sync(0xffffffffu, mine.v, o); t_.id = __shfl_xor_sync(0xffffffffu, mine.id, o);
+                mine = better(mine, t_);
             }
-            __syncthreads();
-            if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
-            // eliminate column kk from every other row; columns <= kk of the left block are never read again
+            if (!(mine.v > 1e-12)) { if (tid == 0) P.n_r4[b] = -1; return; }       // Pi_0 (scaled to O(1)) is rank deficient: uniform exit
+            const int piv = mine.id;
+            const double rp = 1.0 / Aq[piv + kk * pl];
+            const double dkk = Aq[kk + kk * pl];                // multiplier of row piv after the swap
             for (int c = kk + 1 + warp; c < 2 * p; c += nwarps) {
-                const double pk = Aq[kk + c * pl];
-                if (pk == 0.0) continue;           // identity columns of the right block that no pivot row has touched yet: nothing to eliminate
+                const double a = Aq[piv + c * pl], bq = Aq[kk + c * pl];
+                const double pk = a * rp;
+                __syncwarp();
+                if (pk == 0.0) {                                 // identity columns no pivot row has touched yet: only the swap
+                    if (piv != kk && lane == 0) { Aq[piv + c * pl] = bq; Aq[kk + c * pl] = 0.0; }
+                    continue;
+                }
 #pragma unroll 8
-                for (int i = lane; i < p; i += 32) if (i != kk) Aq[i + c * pl] = fma(-Aq[i + kk * pl], pk, Aq[i + c * pl]);
+                for (int i = lane; i < p; i += 32) {
+                    double v_;
+                    if (i == kk) v_ = pk;
+                    else if (i == piv) v_ = fma(-dkk, pk, bq);
+                    else v_ = fma(-Aq[i + kk * pl], pk, Aq[i + c * pl]);
+                    Aq[i + c * pl] = v_;
+                }
             }
             __syncthreads();
         }
