@@ -353,7 +353,20 @@ class LockstepDriver:
             self.n_r1[tgt] += 1
             self.num_evals[tgt] += 1
             self.fully_linear[tgt] = self.fully_linear[tgt] | (self.n_dirs[tgt] == 0)
-        # improve_model = update_model: from-scratch solve of [centre; r1; r2; r3; r4] for the whole sub-batch
+            # `meta.improving_directions` still holds the directions round 3 has used (RbfModel.jl:575-577, 625), so the new site can
+            # be an exact copy of a round-3 site: the interpolation system is then singular by construction.  That solve is not
+            # attempted; it counts as a failed build (previous model kept, see _update)
+            valid = torch.arange(n, device=self.dev)[None, :] < self.n_r3[tgt][:, None]
+            dup = ((self.r3_sites[tgt] == new_site[ok][:, None, :]).all(-1) & valid).any(-1)
+            self.build_failures[tgt[dup]] += 1
+            self.fully_linear[tgt[dup]] = False
+            success = success.clone()
+            success[ok[dup]] = False
+        # improve_model = update_model: from-scratch solve of [centre; r1; r2; r3; r4].  Only the instances whose training set changed
+        # are solved again: for the others update_model would reproduce the model they already hold
+        if not bool(success.any()):
+            return
+        idx = idx[success]
         S, idx_p, imap = self._subset(idx)
         Sp = int(idx_p.numel())
         sc = self._scratch.setdefault((Sp, self.n, self.k, self.cap, self.cfg.kernel, self.cfg.max_model_points, self.cfg.polynomial_degree), _Scratch())
