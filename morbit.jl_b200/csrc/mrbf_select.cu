@@ -813,9 +813,13 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
     if (p > 0) {
         for (int e = tid; e < p * p; e += nt) {
             int i = e % p, j = e / p;
-            double r2 = 0.0;
-            for (int k = 0; k < n; ++k) { double d = Ct[k * NM + i] - Ct[k * NM + j]; r2 = fma(d, d, r2); }
-            P00[i + j * pl] = rad_phi(P.rf, r2);
+            if (i >= j) {                          // symmetric (bit for bit: (a - b)^2 == (b - a)^2): lower half, mirrored
+                double r2 = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) { double d = Ct[k * NM + i] - Ct[k * NM + j]; r2 = fma(d, d, r2); }
+                const double ph = rad_phi(P.rf, r2);
+                P00[i + j * pl] = ph; P00[j + i * pl] = ph;
+            }
             Aq[i + j * pl] = (j == 0) ? 1.0 : (Ct[(j - 1) * NM + i] - Ct[(j - 1) * NM]) * inv_s;
         }
         __syncthreads();
@@ -860,9 +864,12 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         for (int e = tid; e < p * p; e += nt) {    // M0 = Pi_0^{-T};  H = (Pi_0' Pi_0)^{-1} = Pi_0^{-1} Pi_0^{-T}
             const int r = e % p, c = e / p;
             M0[r + c * pl] = Qx[c + r * pl];
-            double a = 0.0;
-            for (int k2 = 0; k2 < p; ++k2) a = fma(Qx[r + k2 * pl], Qx[c + k2 * pl], a);
-            H[r + c * pl] = a;
+            if (r >= c) {                          // symmetric, and bit-identical under the swap of the two factors
+                double a = 0.0;
+#pragma unroll 4
+                for (int k2 = 0; k2 < p; ++k2) a = fma(Qx[r + k2 * pl], Qx[c + k2 * pl], a);
+                H[r + c * pl] = a; H[c + r * pl] = a;
+            }
         }
     }
     const double phi0 = rad_phi(P.rf, 0.0);
