@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         }
         __syncthreads();
         // ---- P3: t_j = L^{-1} a_j for all block members at once (G threads per row share the row of L^{-1})
-        const int G = (m > 64) ? 2 : ((m > 32) ? 4 : 8);
+        const int G = (!SMEM) ? 8 : ((m > 64) ? 2 : ((m > 32) ? 4 : 8));   // state in global memory: eight lanes read a 64-byte piece of a row of L^{-1}
         const int rows_per_pass = nt / G;
         {
             double tn[T];
