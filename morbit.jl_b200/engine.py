@@ -244,7 +244,7 @@ class Engine:
         """All arguments are torch CUDA tensors (float64 / int32); returns a SelectResult of CUDA tensors."""
         import torch
         B, db_stride, n = sites.shape
-        mp = max_model_points(cfg, n)
+        mp = max(1, min(max_model_points(cfg, n), db_stride))    # round 4 accepts database sites only: never more than db_stride ids
         dev = sites.device
         if out is None:
             i32 = dict(dtype=torch.int32, device=dev); f64 = dict(dtype=torch.float64, device=dev)
@@ -265,7 +265,7 @@ class Engine:
         """select_points_dev that also keeps the round-4 factorisation on the device; returns (SelectResult, Prepared)."""
         import torch
         B, db_stride, n = sites.shape
-        mp = max_model_points(cfg, n)
+        mp = max(1, min(max_model_points(cfg, n), db_stride))    # round 4 accepts database sites only: never more than db_stride ids
         dev = sites.device
         if out is None:
             i32 = dict(dtype=torch.int32, device=dev); f64 = dict(dtype=torch.float64, device=dev)

@@ -173,7 +173,7 @@ class LockstepDriver:
         self.it_stat = torch.zeros(B, **i32)
         self.iter_counter = 1
         self.iters_done = torch.zeros(B, **i32)
-        mp = max_model_points(cfg, n)
+        mp = max(1, min(max_model_points(cfg, n), self.cap))     # same width as the select outputs (engine.select_points_keep_dev)
         # RbfMeta of every instance (src/models/RbfModel.jl:148-159)
         self.r1 = torch.zeros((B, n), **i32); self.n_r1 = torch.zeros(B, **i32)
         self.r2 = torch.zeros((B, n), **i32); self.n_r2 = torch.zeros(B, **i32)

@@ -124,7 +124,7 @@ class HostPipeline:
     NAMES = ("sites", "values", "n_db", "x_index", "x", "delta", "flags_in", "max_new")
     OUTS = ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "flags_out")
 
-    def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2):
+    def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2, buffers: int = 1):
         import torch
         self.torch = torch
         self.engine, self.cfg, self.chunks, self.compute = engine, cfg, chunks, compute_stream
@@ -136,15 +136,18 @@ class HostPipeline:
                        for lo, hi in self.bounds]
         glb = torch.from_numpy(np.ascontiguousarray(host["glb"])).to(f64).to(device)
         gub = torch.from_numpy(np.ascontiguousarray(host["gub"])).to(f64).to(device)
-        self.dev = [DeviceBatch(*(torch.empty_like(pc[k], device=device) for k in ("sites", "values", "n_db", "x_index", "x", "delta")),
-                                glb, gub, torch.empty_like(pc["flags_in"], device=device), torch.empty_like(pc["max_new"], device=device))
-                    for pc in self.pinned]
+        # `buffers` device copies of every slice, used in turn: with two, the host -> device copy of the NEXT step's snapshot runs
+        # behind the kernels of the current step even when the batch is not cut into slices (chunks = 1: full-size launches)
+        self.buffers, self._turn = max(1, int(buffers)), 0
+        self.dev = [[DeviceBatch(*(torch.empty_like(pc[k], device=device) for k in ("sites", "values", "n_db", "x_index", "x", "delta")),
+                                 glb, gub, torch.empty_like(pc["flags_in"], device=device), torch.empty_like(pc["max_new"], device=device))
+                     for _ in range(self.buffers)] for pc in self.pinned]
         self.builders = [MultistartBuilder(engine, cfg, delta_max) for _ in range(chunks)]
         self.models = [None] * chunks
         self.out_pinned = [None] * chunks
         self.copy_in, self.copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
         self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
-        self.ev_comp = [torch.cuda.Event() for _ in range(chunks)]
+        self.ev_comp = [[torch.cuda.Event() for _ in range(self.buffers)] for _ in range(chunks)]
         self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
         self.h2d_bytes = sum(t.numel() * t.element_size() for pc in self.pinned for t in pc.values())
         self.d2h_bytes = 0
@@ -152,23 +155,25 @@ class HostPipeline:
     def step(self):
         """Enqueue one pass over the whole batch; returns immediately (synchronise the compute stream to wait for it)."""
         torch = self.torch
+        t = self._turn
+        self._turn = (t + 1) % self.buffers
         for c in range(self.chunks):
             with torch.cuda.stream(self.copy_in):
-                self.copy_in.wait_event(self.ev_comp[c])          # the slice's device buffers are free again
+                self.copy_in.wait_event(self.ev_comp[c][t])       # this device buffer of the slice is free again
                 for k in self.NAMES:
-                    getattr(self.dev[c], k).copy_(self.pinned[c][k], non_blocking=True)
+                    getattr(self.dev[c][t], k).copy_(self.pinned[c][k], non_blocking=True)
                 self.ev_in[c].record(self.copy_in)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self.ev_in[c])
                 self.compute.wait_event(self.ev_out[c])           # the previous step's result copy of this slice has left
-                self.models[c], sel, status = self.builders[c].step(self.dev[c], recycle=self.models[c])
-                self.ev_comp[c].record(self.compute)
+                self.models[c], sel, status = self.builders[c].step(self.dev[c][t], recycle=self.models[c])
+                self.ev_comp[c][t].record(self.compute)
             outs = [getattr(sel, k) for k in self.OUTS] + [status]
             if self.out_pinned[c] is None:
                 self.out_pinned[c] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
                 self.d2h_bytes += sum(o.numel() * o.element_size() for o in outs)
             with torch.cuda.stream(self.copy_out):
-                self.copy_out.wait_event(self.ev_comp[c])
+                self.copy_out.wait_event(self.ev_comp[c][t])
                 for p, o in zip(self.out_pinned[c], outs):
                     p.copy_(o, non_blocking=True)
                 self.ev_out[c].record(self.copy_out)

@@ -327,9 +327,11 @@ def test_build_from_kept_factorisation_matches_oracle(engine, kernel, n, n_db, m
 
 
 @pytest.mark.gpu
-def test_host_pipeline_overlapped_copies_match_oracle(engine):
+@pytest.mark.parametrize("chunks,buffers,passes", [(3, 1, 2), (1, 2, 4), (2, 2, 3)])
+def test_host_pipeline_overlapped_copies_match_oracle(engine, chunks, buffers, passes):
     """multistart.HostPipeline: host database snapshots in, indices / flags / status out, copies of one slice overlapping the kernels
-    of the other; two passes (the second recycles the model handles and the kept factorisations).  Indices must be the oracle's."""
+    of the other (chunks > 1) or the upload of the next step overlapping the kernels of this one (buffers = 2); several passes (the
+    later ones recycle the model handles, the kept factorisations and the device buffers).  Indices must be the oracle's."""
     import torch
     from morbit_jl_b200 import synthetic
     from morbit_jl_b200.multistart import HostPipeline
@@ -340,8 +342,8 @@ def test_host_pipeline_overlapped_copies_match_oracle(engine):
                                    host["gub"], False, False, host["max_new"], nthreads=4)
     stream = torch.cuda.Stream()
     eng = mb.Engine(0, stream=stream.cuda_stream)
-    pipe = HostPipeline(eng, cfg, host["delta_max"], host, "cuda:0", stream, chunks=3)
-    for _ in range(2):
+    pipe = HostPipeline(eng, cfg, host["delta_max"], host, "cuda:0", stream, chunks=chunks, buffers=buffers)
+    for _ in range(passes):
         models, outs = pipe.step()
         stream.synchronize()
         b0 = 0
