@@ -228,20 +228,21 @@ def run_ours(args):
     # as the Julia shim hands it over), D2H of the indices / flags / status; multistart.HostPipeline hides the copies of one
     # half of the batch behind the kernels of the other half
     from morbit_jl_b200.multistart import HostPipeline
-    pipe = HostPipeline(eng, cfg, DELTA_MAX, host, f"cuda:{local}", stream, chunks=args.e2e_chunks, buffers=args.e2e_buffers)
-    for _ in range(max(1, args.warmup // 2)):
-        pipe.step(); stream.synchronize()
+    pipe = HostPipeline(eng, cfg, DELTA_MAX, host, f"cuda:{local}", stream, chunks=args.e2e_chunks, buffers=args.e2e_buffers, outputs=args.e2e_outputs)
+    for _ in range(max(args.e2e_outputs * args.e2e_buffers, args.warmup // 2)):      # every buffer / output set used once (allocations)
+        pipe.step(); pipe.drain(); stream.synchronize()
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record(stream)
     for _ in range(args.steps):
-        pipe.step()
+        _, e2e_outs = pipe.step()
+    pipe.drain()                    # the last steps' result copies are inside the timed region
     t1.record(stream)
     stream.synchronize()
     barrier()
     e2e_ms = t0.elapsed_time(t1) / args.steps
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    e2e_status_ok = int(sum(int((o[-1].numpy() == 0).sum()) for o in pipe.out_pinned))
+    e2e_status_ok = int(sum(int((o[-1].numpy() == 0).sum()) for o in e2e_outs))
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -394,11 +395,12 @@ def run_ours(args):
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "chunks": args.e2e_chunks, "builds_ok": e2e_status_ok,
-                        "buffers": args.e2e_buffers,
+                        "buffers": args.e2e_buffers, "outputs": args.e2e_outputs,
                         "path": "pinned host database snapshot -> H2D -> mrbf_select_points_keep_dev + mrbf_build_prepared_dev -> D2H of "
                                 "indices/flags/status (models stay device-resident handles, as in the ABI); multistart.HostPipeline: "
                                 f"{args.e2e_chunks} slice(s) of the batch, {args.e2e_buffers} device buffer(s) per slice -- the upload of the next "
-                                "snapshot runs behind the kernels of the current one, every step's result copy lands before the next step's kernels start"},
+                                f"snapshot runs behind the kernels of the current one; {args.e2e_outputs} set(s) of result buffers -- a step's result copy "
+                                "runs behind the next step's kernels, the timed region ends when the last copy has landed"},
                 "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
                 "gathered_rows": None if allrows is None else int(allrows.shape[0])}
         emit(line)
@@ -481,6 +483,7 @@ def main():
     ap.add_argument("--no-descent", dest="descent", action="store_false", help="skip the steepest-descent secondary metric")
     ap.add_argument("--lockstep-iters", type=int, default=20, help="max_iter of the lock-step multistart run (secondary metric; 0 = skip)")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="slices of the batch in the end-to-end pipeline")
+    ap.add_argument("--e2e-outputs", type=int, default=2, help="sets of result buffers (2: a step's result copy runs behind the next step's kernels)")
     ap.add_argument("--e2e-buffers", type=int, default=2, help="device buffers per slice (2: the next step's upload overlaps this step's kernels)")
     args = ap.parse_args()
     if args.impl == "reference":

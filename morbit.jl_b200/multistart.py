@@ -124,7 +124,8 @@ class HostPipeline:
     NAMES = ("sites", "values", "n_db", "x_index", "x", "delta", "flags_in", "max_new")
     OUTS = ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "flags_out")
 
-    def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2, buffers: int = 1):
+    def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2, buffers: int = 1,
+                 outputs: int = 1):
         import torch
         self.torch = torch
         self.engine, self.cfg, self.chunks, self.compute = engine, cfg, chunks, compute_stream
@@ -142,13 +143,16 @@ class HostPipeline:
         self.dev = [[DeviceBatch(*(torch.empty_like(pc[k], device=device) for k in ("sites", "values", "n_db", "x_index", "x", "delta")),
                                  glb, gub, torch.empty_like(pc["flags_in"], device=device), torch.empty_like(pc["max_new"], device=device))
                      for _ in range(self.buffers)] for pc in self.pinned]
-        self.builders = [MultistartBuilder(engine, cfg, delta_max) for _ in range(chunks)]
-        self.models = [None] * chunks
-        self.out_pinned = [None] * chunks
+        # `outputs` sets of result buffers (select outputs, kept factorisations, models, pinned host copies), used in turn: with two,
+        # the device -> host copy of a step's results runs behind the kernels of the NEXT step (drain() waits for the last one)
+        self.outputs, self._uturn = max(1, int(outputs)), 0
+        self.builders = [[MultistartBuilder(engine, cfg, delta_max) for _ in range(self.outputs)] for _ in range(chunks)]
+        self.models = [[None] * self.outputs for _ in range(chunks)]
+        self.out_pinned = [[None] * self.outputs for _ in range(chunks)]
         self.copy_in, self.copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
         self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
         self.ev_comp = [[torch.cuda.Event() for _ in range(self.buffers)] for _ in range(chunks)]
-        self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
+        self.ev_out = [[torch.cuda.Event() for _ in range(self.outputs)] for _ in range(chunks)]
         self.h2d_bytes = sum(t.numel() * t.element_size() for pc in self.pinned for t in pc.values())
         self.d2h_bytes = 0
 
@@ -157,6 +161,8 @@ class HostPipeline:
         torch = self.torch
         t = self._turn
         self._turn = (t + 1) % self.buffers
+        u = self._uturn
+        self._uturn = (u + 1) % self.outputs
         for c in range(self.chunks):
             with torch.cuda.stream(self.copy_in):
                 self.copy_in.wait_event(self.ev_comp[c][t])       # this device buffer of the slice is free again
@@ -165,20 +171,28 @@ class HostPipeline:
                 self.ev_in[c].record(self.copy_in)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self.ev_in[c])
-                self.compute.wait_event(self.ev_out[c])           # the previous step's result copy of this slice has left
-                self.models[c], sel, status = self.builders[c].step(self.dev[c][t], recycle=self.models[c])
+                self.compute.wait_event(self.ev_out[c][u])        # the last result copy out of this set of output buffers has left
+                self.models[c][u], sel, status = self.builders[c][u].step(self.dev[c][t], recycle=self.models[c][u])
                 self.ev_comp[c][t].record(self.compute)
             outs = [getattr(sel, k) for k in self.OUTS] + [status]
-            if self.out_pinned[c] is None:
-                self.out_pinned[c] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-                self.d2h_bytes += sum(o.numel() * o.element_size() for o in outs)
+            if self.out_pinned[c][u] is None:
+                self.out_pinned[c][u] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                if u == 0:
+                    self.d2h_bytes += sum(o.numel() * o.element_size() for o in outs)
             with torch.cuda.stream(self.copy_out):
                 self.copy_out.wait_event(self.ev_comp[c][t])
-                for p, o in zip(self.out_pinned[c], outs):
+                for p, o in zip(self.out_pinned[c][u], outs):
                     p.copy_(o, non_blocking=True)
-                self.ev_out[c].record(self.copy_out)
-        self.compute.wait_event(self.ev_out[self.chunks - 1])     # the step ends when its last result copy has landed
-        return self.models, self.out_pinned
+                self.ev_out[c][u].record(self.copy_out)
+        if self.outputs == 1:
+            self.compute.wait_event(self.ev_out[self.chunks - 1][0])     # the step ends when its last result copy has landed
+        return [m[u] for m in self.models], [o[u] for o in self.out_pinned]
+
+    def drain(self):
+        """Make the compute stream wait for every result copy enqueued so far (the end of a pipelined run with outputs > 1)."""
+        for c in range(self.chunks):
+            for u in range(self.outputs):
+                self.compute.wait_event(self.ev_out[c][u])
 
 
 def gather_results(local: np.ndarray, total: int, rank: int, world: int) -> Optional[np.ndarray]:

@@ -327,8 +327,8 @@ def test_build_from_kept_factorisation_matches_oracle(engine, kernel, n, n_db, m
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("chunks,buffers,passes", [(3, 1, 2), (1, 2, 4), (2, 2, 3)])
-def test_host_pipeline_overlapped_copies_match_oracle(engine, chunks, buffers, passes):
+@pytest.mark.parametrize("chunks,buffers,outputs,passes", [(3, 1, 1, 2), (1, 2, 1, 4), (2, 2, 2, 3), (1, 2, 2, 5)])
+def test_host_pipeline_overlapped_copies_match_oracle(engine, chunks, buffers, outputs, passes):
     """multistart.HostPipeline: host database snapshots in, indices / flags / status out, copies of one slice overlapping the kernels
     of the other (chunks > 1) or the upload of the next step overlapping the kernels of this one (buffers = 2); several passes (the
     later ones recycle the model handles, the kept factorisations and the device buffers).  Indices must be the oracle's."""
@@ -342,9 +342,10 @@ def test_host_pipeline_overlapped_copies_match_oracle(engine, chunks, buffers, p
                                    host["gub"], False, False, host["max_new"], nthreads=4)
     stream = torch.cuda.Stream()
     eng = mb.Engine(0, stream=stream.cuda_stream)
-    pipe = HostPipeline(eng, cfg, host["delta_max"], host, "cuda:0", stream, chunks=chunks, buffers=buffers)
+    pipe = HostPipeline(eng, cfg, host["delta_max"], host, "cuda:0", stream, chunks=chunks, buffers=buffers, outputs=outputs)
     for _ in range(passes):
         models, outs = pipe.step()
+        pipe.drain()
         stream.synchronize()
         b0 = 0
         for c, (lo, hi) in enumerate(pipe.bounds):
