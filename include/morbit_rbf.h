@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MRBF_ABI_VERSION 1
+#define MRBF_ABI_VERSION 2
 
 /* src/models/RbfModel.jl:48-54 (RbfKernels), same order */
 enum mrbf_kernel {
@@ -73,6 +73,12 @@ int mrbf_abi_version(void);
 int mrbf_init(int device, mrbf_ctx** ctx);                 /* creates a private non-blocking stream */
 int mrbf_set_stream(mrbf_ctx* ctx, void* cuda_stream);     /* run on the caller's cudaStream_t instead */
 int mrbf_sync(mrbf_ctx* ctx);
+/* rtol of the reference's `Δ ≈ Δ_max` test that skips round 2 (src/models/RbfModel.jl:588).  Julia's isapprox uses
+ * max(sqrt(eps(T))) over the two argument types, and delta_max(algo_config) of the DEFAULT config is a Float32 literal
+ * (src/AbstractConfigInterface.jl:31), so a run with default settings compares with sqrt(eps(Float32)) = 3.4526698e-4, a run with an
+ * AlgorithmConfig{Float64} with sqrt(eps(Float64)) = 1.49e-8 (the library default).  The Julia shim passes
+ * Base.rtoldefault(typeof(Δ), typeof(delta_max(ac)), 0). */
+int mrbf_set_isapprox_rtol(mrbf_ctx* ctx, double rtol);
 void mrbf_destroy(mrbf_ctx* ctx);
 const char* mrbf_last_error(const mrbf_ctx* ctx);
 /* kernels launched through this context since creation (the bench's gpu_launches counter) */
@@ -124,7 +130,9 @@ int mrbf_select_points_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_
  * (inverse Cholesky factor of the reduced kernel matrix, RbfModel.jl:394-396, 469-477) in an opaque handle.  The
  * reference discards these matrices and notes that keeping them would save work (RbfModel.jl:657-660);
  * mrbf_build_prepared_dev turns them into the model with two triangular mat-vecs per output.
- * *prepared must be NULL or a handle from an earlier call (reused when the shapes match, else freed and replaced). */
+ * *prepared must be NULL or a handle from an earlier call (reused when the shapes match, else freed and replaced).
+ * With cfg->optimized_sampling == 0 there is no round 4 and nothing to keep (RbfModel.jl:564-569, 647-652): the handle then
+ * only records the found set, and mrbf_build_prepared* builds [centre; r1; r2; r3] by the general route. */
 typedef struct mrbf_prepared mrbf_prepared;
 int mrbf_select_points_keep_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t db_stride,
                                 const double* sites, const int32_t* n_db, const int32_t* x_index, const double* x,
@@ -181,7 +189,11 @@ int mrbf_gather_training_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int
  * shape: B per-instance shape parameters or NULL (then cfg->shape_parameter).  Creates one device-resident
  * handle for the whole batch.  *model must be NULL or a handle from an earlier build call: its device buffers are
  * recycled when the shapes match (no allocation on the hot path; the reference likewise replaces the model in
- * place, SurrogateContainer.jl:376-382), else it is freed and replaced.  On error *model is NULL.  status[b]: 0 ok, > 0 reduced kernel matrix not positive definite at that column. */
+ * place, SurrogateContainer.jl:376-382), else it is freed and replaced.  status[b]: 0 ok, > 0 reduced kernel matrix not
+ * positive definite at that column.
+ * Ownership rule of every mrbf_build* entry point: the handle passed in through *model belongs to the call.  MRBF_OK and
+ * MRBF_ENUMERIC (host-pointer twins only: at least one instance failed numerically, the others are fine -- read status[])
+ * return a VALID handle in *model; every other error releases the handle and leaves *model NULL. */
 int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
                const int32_t* N, const double* sites, const double* values, const double* shape,
                mrbf_model** model, int32_t* status);

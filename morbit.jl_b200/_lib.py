@@ -36,6 +36,7 @@ SIGNATURES = {
     "mrbf_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "mrbf_set_stream": (C.c_int, [_vp, _vp]),
     "mrbf_sync": (C.c_int, [_vp]),
+    "mrbf_set_isapprox_rtol": (C.c_int, [_vp, _f64]),
     "mrbf_destroy": (None, [_vp]),
     "mrbf_last_error": (C.c_char_p, [_vp]),
     "mrbf_launch_count": (_i64, [_vp]),

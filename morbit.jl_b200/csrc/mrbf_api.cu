@@ -29,6 +29,7 @@ struct mrbf_ctx {
     int64_t launches = 0;
     char err[512] = {0};
     bool prof = false;
+    double isapprox_rtol = 1.4901161193847656e-08;   // sqrt(eps(Float64)); see mrbf_set_isapprox_rtol
     cudaEvent_t ev0[8] = {nullptr}, ev1[8] = {nullptr};
     bool ev_used[8] = {false};
     DevBuf ws[16];      // kernel workspaces (grow-only)
@@ -42,7 +43,8 @@ struct mrbf_prepared {
     double* fs = nullptr;
     int* ints = nullptr;        // elig[B], n_found[B], n_extra[B], n_r4[B], found[B*found_stride], r4[B*r4_stride]
     int *elig, *n_found, *n_extra, *n_r4, *found, *r4;
-    int kind = 0;               // 0: round4_block_kernel layout (round4_fast_state_layout), 1: round4_schur_kernel layout
+    int kind = 0;               // 0: round4_block_kernel layout (round4_fast_state_layout), 1: round4_schur_kernel layout,
+                                // 2: no factorisation at all (optimized_sampling = false): every instance takes the general route
     SchurGeom geom{};
 };
 
@@ -89,7 +91,10 @@ int ensure(mrbf_ctx* ctx, DevBuf& b, size_t bytes) {
     if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8;
     cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();        // the failure is reported here; do not leave it for the next launch check to trip over
+        b.p = nullptr; return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
     b.cap = want;
     return MRBF_OK;
 }
@@ -139,6 +144,37 @@ int max_points_of(const mrbf_cfg* cfg, int n) {
     return cfg->max_model_points <= 0 ? ((n + 1) * (n + 2)) / 2 : cfg->max_model_points;
 }
 
+// Allocate (or reuse, when every shape matches) the caller's kept-factorisation handle.
+int ensure_prepared(mrbf_ctx* ctx, mrbf_prepared** keep_out, const mrbf_cfg* cfg, int B, int n, int NM, int p, int db_stride,
+                    int found_stride, int r4_stride, size_t fsd, int kind, const SchurGeom& geom) {
+    if (*keep_out && (*keep_out)->B == B && (*keep_out)->n == n && (*keep_out)->NM == NM && (*keep_out)->p == p &&
+        (*keep_out)->found_stride == found_stride && (*keep_out)->r4_stride == r4_stride && (*keep_out)->fs_stride == fsd &&
+        (*keep_out)->kind == kind) {
+        mrbf_prepared* kp = *keep_out;       // reuse the caller's handle (same shapes): no allocation on the hot path
+        kp->db_stride = db_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
+        kp->geom = geom;
+        return MRBF_OK;
+    }
+    if (*keep_out) { mrbf_free_prepared(ctx, *keep_out); *keep_out = nullptr; }
+    mrbf_prepared* kp = new (std::nothrow) mrbf_prepared();
+    if (!kp) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
+    kp->B = B; kp->n = n; kp->NM = NM; kp->p = p; kp->db_stride = db_stride; kp->found_stride = found_stride;
+    kp->r4_stride = r4_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
+    kp->fs_stride = fsd; kp->kind = kind; kp->geom = geom;
+    const size_t ni = (size_t)B * 4 + (size_t)B * found_stride + (size_t)B * r4_stride;
+    cudaError_t e1 = cudaMalloc(&kp->fs, (size_t)B * (fsd ? fsd : 1) * sizeof(double));
+    cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc(&kp->ints, ni * sizeof(int)) : e1;
+    if (e2 != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(kp->fs); delete kp;
+        return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e2));
+    }
+    kp->elig = kp->ints; kp->n_found = kp->elig + B; kp->n_extra = kp->n_found + B; kp->n_r4 = kp->n_extra + B;
+    kp->found = kp->n_r4 + B; kp->r4 = kp->found + (size_t)B * found_stride;
+    *keep_out = kp;
+    return MRBF_OK;
+}
+
 int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, const double* sites, const int* n_db,
                const double* lb2, const double* ub2, int found_stride, const int* found, const int* n_found,
                int extra_stride, const double* extra, const int* n_extra, int n0max, int r4_stride, int* r4, int* n_r4, int* status,
@@ -181,28 +217,10 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             if (fsmem > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "max_model_points too large for the round-4 kernel%s");
         }
         R.fs_stride = fsd;
-        if (keep_out && *keep_out && (*keep_out)->B == B && (*keep_out)->n == n && (*keep_out)->NM == NM && (*keep_out)->p == p &&
-            (*keep_out)->found_stride == found_stride && (*keep_out)->r4_stride == r4_stride && (*keep_out)->fs_stride == fsd &&
-            (*keep_out)->kind == (schur ? 1 : 0)) {
-            mrbf_prepared* kp = *keep_out;       // reuse the caller's handle (same shapes): no allocation on the hot path
-            kp->db_stride = db_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
-            kp->geom = geom;
-            R.keep_fs = kp->fs; R.elig = kp->elig;
-        } else if (keep_out) {
-            if (*keep_out) { mrbf_free_prepared(ctx, *keep_out); *keep_out = nullptr; }
-            mrbf_prepared* kp = new (std::nothrow) mrbf_prepared();
-            if (!kp) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
-            kp->B = B; kp->n = n; kp->NM = NM; kp->p = p; kp->db_stride = db_stride; kp->found_stride = found_stride;
-            kp->r4_stride = r4_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
-            kp->fs_stride = fsd; kp->kind = schur ? 1 : 0; kp->geom = geom;
-            const size_t ni = (size_t)B * 4 + (size_t)B * found_stride + (size_t)B * r4_stride;
-            cudaError_t e1 = cudaMalloc(&kp->fs, (size_t)B * fsd * sizeof(double));
-            cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc(&kp->ints, ni * sizeof(int)) : e1;
-            if (e2 != cudaSuccess) { cudaFree(kp->fs); delete kp; return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e2)); }
-            kp->elig = kp->ints; kp->n_found = kp->elig + B; kp->n_extra = kp->n_found + B; kp->n_r4 = kp->n_extra + B;
-            kp->found = kp->n_r4 + B; kp->r4 = kp->found + (size_t)B * found_stride;
-            R.keep_fs = kp->fs; R.elig = kp->elig;
-            *keep_out = kp;
+        if (keep_out) {
+            rc = ensure_prepared(ctx, keep_out, cfg, B, n, NM, p, db_stride, found_stride, r4_stride, fsd, schur ? 1 : 0, geom);
+            if (rc != MRBF_OK) return rc;
+            R.keep_fs = (*keep_out)->fs; R.elig = (*keep_out)->elig;
         }
         if (schur) {
             ENSURE(ctx->ws[13], (size_t)B * geom.pw_doubles * sizeof(double));
@@ -314,6 +332,12 @@ int mrbf_set_stream(mrbf_ctx* ctx, void* s) {
     return MRBF_OK;
 }
 
+int mrbf_set_isapprox_rtol(mrbf_ctx* ctx, double rtol) {
+    if (!ctx || !(rtol >= 0.0)) return MRBF_EINVAL;
+    ctx->isapprox_rtol = rtol;
+    return MRBF_OK;
+}
+
 int mrbf_sync(mrbf_ctx* ctx) {
     if (!ctx) return MRBF_EINVAL;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -372,7 +396,7 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     S.B = B; S.n = n; S.db_stride = db_stride; S.found_stride = 2 * n + 1;
     S.cfg.polynomial_degree = cfg->polynomial_degree; S.cfg.optimized_sampling = cfg->optimized_sampling;
     S.cfg.theta_enlarge_1 = cfg->theta_enlarge_1; S.cfg.theta_enlarge_2 = cfg->theta_enlarge_2; S.cfg.theta_pivot = cfg->theta_pivot;
-    S.delta_max = delta_max;
+    S.delta_max = delta_max; S.approx_rtol = ctx->isapprox_rtol;
     S.sites = sites; S.n_db = n_db; S.x_index = x_index; S.x = x; S.delta = delta; S.glb = glb; S.gub = gub;
     S.flags_in = flags_in; S.max_new = max_new;
     S.r1 = r1; S.n_r1 = n_r1; S.r2 = r2; S.n_r2 = n_r2; S.r3_sites = r3_sites; S.n_r3 = n_r3; S.dirs = dirs; S.n_dirs = n_dirs;
@@ -413,6 +437,22 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     } else {
         CK(cudaMemsetAsync(n_r4, 0, sizeof(int) * (size_t)B, ctx->stream));
         if (status) CK(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, ctx->stream));
+        if (keep) {
+            // No round 4, hence no factorisation (RbfModel.jl:564-569, 647-652): the handle still records the found set so that
+            // mrbf_build_prepared* builds [centre; r1; r2; r3] by the general route (elig = 0, n_r4 = 0 for every instance).
+            const int p = poly_dim(n, cfg->polynomial_degree);
+            int NM = n + 1 + db_stride; const int mpts = max_points_of(cfg, n); if (NM > mpts) NM = mpts; if (NM < n + 1) NM = n + 1;
+            rc = ensure_prepared(ctx, keep, cfg, B, n, NM, p, db_stride, S.found_stride, r4_stride, 0, 2, SchurGeom{});
+            if (rc != MRBF_OK) return rc;
+            mrbf_prepared* kp = *keep;
+            const size_t sB = sizeof(int) * (size_t)B;
+            CK(cudaMemsetAsync(kp->elig, 0, sB, ctx->stream));
+            CK(cudaMemcpyAsync(kp->n_found, S.n_found, sB, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemsetAsync(kp->n_extra, 0, sB, ctx->stream));
+            CK(cudaMemsetAsync(kp->n_r4, 0, sB, ctx->stream));
+            CK(cudaMemcpyAsync(kp->found, S.found, sB * S.found_stride, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (r4_stride > 0) CK(cudaMemsetAsync(kp->r4, 0, sB * r4_stride, ctx->stream));
+        }
     }
     return MRBF_OK;
 }
@@ -580,6 +620,8 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     if (!ctx || !out) return MRBF_EINVAL;
     mrbf_model* recycle = *out;                 // NULL, or an earlier handle whose device buffers are reused when the shapes match
     *out = nullptr;
+    // Ownership of the handle passed in moved into this call: every error return releases it (*model stays NULL).
+    struct Drop { mrbf_ctx* c; mrbf_model** r; ~Drop() { if (*r) { mrbf_free_model(c, *r); *r = nullptr; } } } drop_{ctx, &recycle};
     int rc = check_cfg(ctx, cfg);
     if (rc != MRBF_OK) return rc;
     if (B <= 0 || n <= 0 || k <= 0 || k > 256 || train_stride <= 0) return fail(ctx, MRBF_EINVAL, "bad sizes%s");
@@ -594,10 +636,10 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     mrbf_model* m = nullptr;
     cudaError_t e = cudaSuccess;
     if (recycle && recycle->B == B && recycle->n == n && recycle->k == k && recycle->train_stride == train_stride && recycle->p == p) {
-        m = recycle;                            // same stream => ordered after every earlier use of the handle
+        m = recycle; recycle = nullptr;         // same stream => ordered after every earlier use of the handle
         m->deg = deg; m->pack_valid = false;
     } else {
-        if (recycle) mrbf_free_model(ctx, recycle);
+        if (recycle) { mrbf_free_model(ctx, recycle); recycle = nullptr; }
         m = new (std::nothrow) mrbf_model();
         if (!m) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
         m->B = B; m->n = n; m->k = k; m->train_stride = train_stride; m->p = p; m->deg = deg;
@@ -610,7 +652,7 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
             m->pack_s = eval_pack_stride(n); m->pack_nt = (train_stride + 63) / 64;
             m->pack_tile_doubles = (size_t)64 * m->pack_s + 64 + (size_t)k * 64;
         }
-        if (e != cudaSuccess) { mrbf_free_model(ctx, m); return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { (void)cudaGetLastError(); mrbf_free_model(ctx, m); return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
     }
     m->kernel = rf.kernel; m->ibeta = rf.ibeta; m->sgn = rf.sgn;
     BuildParams Pb{};
@@ -660,7 +702,7 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
         const size_t psm = build_schur_smem_doubles(k, g.MC, kp->p) * sizeof(double);
         if (psm <= SMEM_LIMIT) { Timed t_(ctx, 6); e = launch_build_schur(Q, psm, ctx->stream); ctx->launches += 1; }
         else e = cudaMemsetAsync((void*)skip_from_prepared, 0, sizeof(int) * (size_t)B, ctx->stream);
-    } else if (e == cudaSuccess && kp && kp->cfg_degree == deg && kp->p > 0) {
+    } else if (e == cudaSuccess && kp && kp->kind == 0 && kp->cfg_degree == deg && kp->p > 0) {
         // 1. instances whose round 4 kept its factorisation: two triangular mat-vecs per output
         PreparedBuildParams Q{};
         Q.B = B; Q.n = n; Q.k = k; Q.NM = kp->NM; Q.p = kp->p; Q.deg = deg; Q.db_stride = kp->db_stride;
@@ -685,13 +727,13 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     return MRBF_OK;
 }
 
-int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+static int mrbf_build_dev_inner(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
                    const int32_t* N, const double* sites, const double* values, const double* shape,
                    mrbf_model** out, int32_t* status) {
     return build_impl(ctx, cfg, B, n, k, train_stride, N, sites, values, shape, out, status, nullptr, nullptr, nullptr, nullptr);
 }
 
-int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
+static int mrbf_build_prepared_dev_inner(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
                             const double* sites, const double* values, const double* r3_sites, const double* r3_values,
                             const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
                             const int32_t* n_r3, mrbf_model** out, int32_t* status) {
@@ -726,7 +768,7 @@ int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepa
     return build_impl(ctx, cfg, B, n, k, ts, Ntmp, tsit, tval, nullptr, out, status, kp, values, r3_values, done, sites, r3_sites);
 }
 
-int mrbf_build_prepared(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
+static int mrbf_build_prepared_inner(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
                         const double* sites, const double* values, const double* r3_sites, const double* r3_values,
                         const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
                         const int32_t* n_r3, mrbf_model** out, int32_t* status) {
@@ -746,7 +788,7 @@ int mrbf_build_prepared(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared*
     if (r3_values) H2D(d_r3v, r3_values, r3v); else CK(cudaMemsetAsync(d_r3v, 0, r3v, ctx->stream));
     H2D(d_xi, x_index, sB); H2D(d_n1, n_r1, sB); H2D(d_n2, n_r2, sB); H2D(d_n3, n_r3, sB);
     H2D(d_r1, r1, sizeof(int) * (size_t)B * n); H2D(d_r2, r2, sizeof(int) * (size_t)B * n);
-    int rc = mrbf_build_prepared_dev(ctx, cfg, kp, k, d_s, d_v, d_r3s, d_r3v, d_xi, d_r1, d_n1, d_r2, d_n2, d_n3, out, d_st);
+    int rc = mrbf_build_prepared_dev_inner(ctx, cfg, kp, k, d_s, d_v, d_r3s, d_r3v, d_xi, d_r1, d_n1, d_r2, d_n2, d_n3, out, d_st);
     if (rc != MRBF_OK) return rc;
     if (status) D2H(status, d_st, sB);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -754,7 +796,7 @@ int mrbf_build_prepared(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared*
     return MRBF_OK;
 }
 
-int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+static int mrbf_build_inner(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
                const int32_t* N, const double* sites, const double* values, const double* shape,
                mrbf_model** out, int32_t* status) {
     if (!ctx || !out) return MRBF_EINVAL;
@@ -766,12 +808,43 @@ int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t
     double* d_shape = (double*)ctx->hb[10].p; int* d_N = (int*)(d_shape + B); int* d_status = d_N + B;
     H2D(d_s, sites, sb); H2D(d_v, values, vb); H2D(d_N, N, sizeof(int) * (size_t)B);
     if (shape) H2D(d_shape, shape, sizeof(double) * (size_t)B);
-    int rc = mrbf_build_dev(ctx, cfg, B, n, k, train_stride, d_N, d_s, d_v, shape ? d_shape : nullptr, out, d_status);
+    int rc = mrbf_build_dev_inner(ctx, cfg, B, n, k, train_stride, d_N, d_s, d_v, shape ? d_shape : nullptr, out, d_status);
     if (rc != MRBF_OK) return rc;
     if (status) D2H(status, d_status, sizeof(int) * (size_t)B);
     CK(cudaStreamSynchronize(ctx->stream));
     if (status) for (int b = 0; b < B; ++b) if (status[b] != 0) return fail(ctx, MRBF_ENUMERIC, "at least one system failed; see status[]%s");
     return MRBF_OK;
+}
+
+// Public wrappers: one ownership rule for the in/out model handle.  MRBF_OK and MRBF_ENUMERIC (some instances failed
+// numerically, see status[]) return a valid handle; every other error releases whatever handle is involved and returns NULL.
+static int settle_model(mrbf_ctx* ctx, mrbf_model** out, int rc) {
+    if (rc != MRBF_OK && rc != MRBF_ENUMERIC && out && *out) { mrbf_free_model(ctx, *out); *out = nullptr; }
+    return rc;
+}
+int mrbf_build_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+                   const int32_t* N, const double* sites, const double* values, const double* shape,
+                   mrbf_model** out, int32_t* status) {
+    return settle_model(ctx, out, mrbf_build_dev_inner(ctx, cfg, B, n, k, train_stride, N, sites, values, shape, out, status));
+}
+int mrbf_build(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, int32_t k, int32_t train_stride,
+               const int32_t* N, const double* sites, const double* values, const double* shape,
+               mrbf_model** out, int32_t* status) {
+    return settle_model(ctx, out, mrbf_build_inner(ctx, cfg, B, n, k, train_stride, N, sites, values, shape, out, status));
+}
+int mrbf_build_prepared_dev(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
+                            const double* sites, const double* values, const double* r3_sites, const double* r3_values,
+                            const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                            const int32_t* n_r3, mrbf_model** out, int32_t* status) {
+    return settle_model(ctx, out, mrbf_build_prepared_dev_inner(ctx, cfg, kp, k, sites, values, r3_sites, r3_values, x_index, r1, n_r1, r2, n_r2,
+                                                                n_r3, out, status));
+}
+int mrbf_build_prepared(mrbf_ctx* ctx, const mrbf_cfg* cfg, const mrbf_prepared* kp, int32_t k,
+                        const double* sites, const double* values, const double* r3_sites, const double* r3_values,
+                        const int32_t* x_index, const int32_t* r1, const int32_t* n_r1, const int32_t* r2, const int32_t* n_r2,
+                        const int32_t* n_r3, mrbf_model** out, int32_t* status) {
+    return settle_model(ctx, out, mrbf_build_prepared_inner(ctx, cfg, kp, k, sites, values, r3_sites, r3_values, x_index, r1, n_r1, r2, n_r2,
+                                                            n_r3, out, status));
 }
 
 int mrbf_model_dims(const mrbf_model* m, int32_t* out6) {
@@ -807,7 +880,7 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
         mrbf_model* mm = const_cast<mrbf_model*>(m);
         if (!mm->pack) {
             cudaError_t e = cudaMalloc(&mm->pack, sizeof(double) * (size_t)m->B * m->pack_nt * m->pack_tile_doubles);
-            if (e != cudaSuccess) { mm->pack = nullptr; mm->pack_tile_doubles = 0; }
+            if (e != cudaSuccess) { (void)cudaGetLastError(); mm->pack = nullptr; mm->pack_tile_doubles = 0; }   // handled: fall back to the tile kernels
         }
         if (mm->pack) {
             PackParams K{};

@@ -18,6 +18,7 @@ struct SelectParams {
     int B, n, db_stride, found_stride;
     CfgDev cfg;
     double delta_max;
+    double approx_rtol;           // rtol of isapprox(delta, delta_max), RbfModel.jl:588 (mrbf_set_isapprox_rtol)
     const double* sites; const int* n_db; const int* x_index; const double* x; const double* delta;
     const double* glb; const double* gub; const int* flags_in; const int* max_new;
     int* r1; int* n_r1; int* r2; int* n_r2; double* r3_sites; int* n_r3; double* dirs; int* n_dirs; int* flags_out;

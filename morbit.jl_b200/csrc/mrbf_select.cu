@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) select_rounds123_kernel
             n_dirs = zc;
         }
         int n_missing = n - n_r1;
-        const bool approx = fabs(delta - P.delta_max) <= 1.4901161193847656e-08 * fmax(fabs(delta), fabs(P.delta_max));
+        const bool approx = fabs(delta - P.delta_max) <= P.approx_rtol * fmax(fabs(delta), fabs(P.delta_max));
         if (n_missing == 0 || skip_search || ensure_fl || (approx && P.cfg.theta_enlarge_1 == P.cfg.theta_enlarge_2)) {
             fully_linear = true;                 // RbfModel.jl:588-591
         } else {                                 // round 2: box 2, excluding every round-1 candidate

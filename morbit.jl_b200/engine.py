@@ -133,6 +133,11 @@ class Engine:
     def sync(self):
         self._check(self.lib.mrbf_sync(self.ctx))
 
+    def set_isapprox_rtol(self, rtol: float):
+        """rtol of the reference's `Δ ≈ Δ_max` test (RbfModel.jl:588): sqrt(eps(Float64)) by default; a run with the reference's
+        default algorithm config (Float32 literals) uses sqrt(eps(Float32)) -- see mrbf_set_isapprox_rtol in include/morbit_rbf.h."""
+        self._check(self.lib.mrbf_set_isapprox_rtol(self.ctx, float(rtol)))
+
     def profile_enable(self, on: bool = True):
         self._check(self.lib.mrbf_profile_enable(self.ctx, int(on)))
 
@@ -201,7 +206,7 @@ class Engine:
         return res, Prepared(self, handle.value)
 
     def build_prepared(self, cfg, prepared: "Prepared", sites, values, x_index, sel: SelectResult, r3_values=None,
-                       recycle: Optional[ModelBatch] = None):
+                       recycle: Optional[ModelBatch] = None, raise_on_failure: bool = True):
         """update_model from the factorisation kept by select_points_keep (host buffers).  sites / values: the same database
         arrays (B x db_stride x n / k) the selection saw; r3_values: B x n x k values of the new round-3 sites."""
         sites = _np(sites, np.float64); values = _np(values, np.float64)
@@ -214,10 +219,16 @@ class Engine:
         if recycle is not None:
             recycle.handle = None
         ccfg = to_c_cfg(cfg)
-        self._check(self.lib.mrbf_build_prepared(
+        rc = self.lib.mrbf_build_prepared(
             self.ctx, C.byref(ccfg), prepared.handle, k, _ptr(sites), _ptr(values), _ptr(_np(sel.r3_sites, np.float64)), _ptr(r3v),
             _ptr(x_index), _ptr(_np(sel.r1, np.int32)), _ptr(_np(sel.n_r1, np.int32)), _ptr(_np(sel.r2, np.int32)),
-            _ptr(_np(sel.n_r2, np.int32)), _ptr(_np(sel.n_r3, np.int32)), C.byref(handle), _ptr(status)))
+            _ptr(_np(sel.n_r2, np.int32)), _ptr(_np(sel.n_r3, np.int32)), C.byref(handle), _ptr(status))
+        # MRBF_ENUMERIC returns a VALID handle (some instances failed numerically, status[] says which); every other error
+        # has already released it inside the library (include/morbit_rbf.h, ownership rule of mrbf_build*)
+        if rc != 0 and not (rc == _lib.MRBF_ENUMERIC and not raise_on_failure):
+            if rc == _lib.MRBF_ENUMERIC and handle.value:
+                self.lib.mrbf_free_model(self.ctx, handle)
+            self._check(rc)
         return ModelBatch(self, handle.value), status
 
     def round4(self, cfg, sites, n_db, lb2, ub2, found, n_found, extra_sites=None, n_extra=None):
@@ -334,7 +345,7 @@ class Engine:
         rc = self.lib.mrbf_build(self.ctx, C.byref(ccfg), B, n, k, ts, _ptr(N), _ptr(sites), _ptr(values), _ptr(shape_a),
                                  C.byref(handle), _ptr(status))
         if rc != 0 and not (rc == _lib.MRBF_ENUMERIC and not raise_on_failure):
-            if handle.value:
+            if rc == _lib.MRBF_ENUMERIC and handle.value:
                 self.lib.mrbf_free_model(self.ctx, handle)
             self._check(rc)
         return ModelBatch(self, handle.value), status

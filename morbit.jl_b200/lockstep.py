@@ -76,6 +76,9 @@ class AlgorithmConfig:
     armijo_const_shrink: float = 0.75
     min_stepsize: float = 10 * float(np.finfo(np.float64).eps)
     normalize: bool = True
+    # rtol of `Δ ≈ Δ_max` (RbfModel.jl:588): these defaults are the reference's Float32 literals, so Julia compares a Float64
+    # radius with a Float32 delta_max => sqrt(eps(Float32)); 1.4901161193847656e-08 for an AlgorithmConfig{Float64}
+    isapprox_rtol: float = float(np.sqrt(np.float32(np.finfo(np.float32).eps)))
 
 
 def _intersect_box_absmax(torch, x, d, lb, ub):
@@ -145,6 +148,7 @@ class LockstepDriver:
             dev_ = torch.device(device)
             engine = Engine(dev_.index or 0, stream=torch.cuda.current_stream(dev_).cuda_stream)
         self.engine, self.cfg, self.func, self.ac = engine, cfg, func, ac or AlgorithmConfig()
+        self.engine.set_isapprox_rtol(self.ac.isapprox_rtol)
         self.func_on_device, self.record = func_on_device, record
         self.n_func_calls = 0
         self.profile, self.phase_s = profile, {}

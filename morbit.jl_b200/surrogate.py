@@ -192,6 +192,9 @@ class VarScaler:
 class AlgoConfig:
     delta_max: float = float(np.float32(0.5))       # AbstractConfigInterface.jl:31 (Float32 literal)
     max_evals: int = INT_MAX
+    # rtol of `Δ ≈ Δ_max` (RbfModel.jl:588).  Julia: max(sqrt(eps(T))) over the two argument types; the default config's
+    # delta_max is Float32 => sqrt(eps(Float32)).  An AlgorithmConfig{Float64} gives sqrt(eps(Float64)) = 1.4901161193847656e-08.
+    isapprox_rtol: float = float(np.sqrt(np.float32(np.finfo(np.float32).eps)))
 
 
 @dataclass
@@ -294,6 +297,7 @@ def prepare_update_model(mod, meta: RbfMeta, cfg: RbfConfig, func_indices, mop, 
     max_new = int(max(0, min(budget, 2**31 - 1)))
     n_db0 = db.num_entries
     prev = meta._kept[1] if meta._kept is not None else None
+    eng.set_isapprox_rtol(getattr(algo_config, "isapprox_rtol", 1.4901161193847656e-08))
     res, prepared = eng.select_points_keep(cfg_num, db.sites_array()[None], [n_db0], [x_index], x[None], [delta], delta_max,
                                            scal.lb, scal.ub, ensure_fully_linear, force_rebuild, max_new, prepared=prev)
     meta._kept = (res, prepared, n_db0, x_index)

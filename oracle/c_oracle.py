@@ -138,6 +138,40 @@ def select_points_batched(cfg, sites, x_index, x, delta, delta_max, glb, gub, en
                         flags_out[:, 0].astype(bool), flags_out[:, 1].astype(bool), margins)
 
 
+FUNC_IDS = {None: 0, "zdt3": 1, "zdt1": 2, "two_parabolas": 3}
+
+
+def set_isapprox_rtol(rtol: float) -> None:
+    """rtol of `isapprox(delta, delta_max)` (RbfModel.jl:588): sqrt(eps(Float64)) by default, sqrt(eps(Float32)) when the
+    algorithm config holds Float32 radii (the reference's default config)."""
+    lib().orc_set_isapprox_rtol(C.c_double(rtol))
+
+
+def select_and_build_batched(cfg, sites, values, x_index, x, delta, delta_max, glb, gub, ensure_fully_linear=False,
+                             force_rebuild=False, max_new=2**31 - 1, func: Optional[str] = None, nthreads: int = 1):
+    """One whole model build per instance and thread inside the C library (rounds 1-4, training-set gather from the database
+    arrays, objective values of the new round-3 sites, saddle solve): the CPU arm of bench.py.  Returns (N, ids, w, lam, status)."""
+    sites = np.ascontiguousarray(sites, dtype=np.float64); values = np.ascontiguousarray(values, dtype=np.float64)
+    B, n_db, n = sites.shape
+    k = values.shape[2]
+    x = np.ascontiguousarray(x, dtype=np.float64); x_index = np.ascontiguousarray(x_index, dtype=np.int32)
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    glb = np.ascontiguousarray(np.broadcast_to(glb, (n,)), dtype=np.float64)
+    gub = np.ascontiguousarray(np.broadcast_to(gub, (n,)), dtype=np.float64)
+    flags_in = np.ascontiguousarray(np.stack([np.broadcast_to(ensure_fully_linear, (B,)),
+                                              np.broadcast_to(force_rebuild, (B,))], axis=1), dtype=np.int32)
+    max_new = np.ascontiguousarray(np.broadcast_to(max_new, (B,)), dtype=np.int32)
+    ccfg = make_cfg(cfg)
+    p = _poly_dim_c(ccfg, n)
+    ts = max(n + 1, min(max_points(cfg, n), n + n_db))
+    N = np.zeros(B, np.int32); ids = np.zeros((B, ts), np.int32)
+    w = np.zeros((B, ts, k)); lam = np.zeros((B, p, k)); status = np.zeros(B, np.int32)
+    lib().orc_select_and_build_batched(C.byref(ccfg), B, n, k, n_db, _dp(sites), _dp(values), _ip(x_index), _dp(x), _dp(delta),
+                                       C.c_double(delta_max), _dp(glb), _dp(gub), _ip(flags_in), _ip(max_new), FUNC_IDS[func],
+                                       ts, _ip(N), _ip(ids), ts, _dp(w), _dp(lam), _ip(status), nthreads)
+    return N, ids, w, lam, status
+
+
 def round4(cfg, sites, lb2, ub2, found):
     sites = np.ascontiguousarray(sites, dtype=np.float64)
     n_db, n = sites.shape

@@ -77,6 +77,7 @@ class AlgoConfig:
     armijo_const_shrink: float = 0.75
     min_stepsize: float = 10 * O.EPS
     normalize: bool = True
+    isapprox_rtol: float = O.ISAPPROX_RTOL_F32      # `Δ ≈ Δ_max` with a Float32 delta_max (RbfModel.jl:588, AbstractConfigInterface.jl:31)
 
 
 @dataclass
@@ -132,7 +133,8 @@ class Run:
         tf, t4 = O.FilterTrace(), O.Round4Trace()
         self.meta = O.prepare_update_model(self.meta, self.cfg, self.db, self.x, self.x_index, self.delta, self.ac.delta_max,
                                            self.glb, self.gub, ensure_fully_linear=ensure_fully_linear,
-                                           num_objf_evals=self.num_evals, algo_max_evals=self.ac.max_evals, trace=tf, trace4=t4)
+                                           num_objf_evals=self.num_evals, algo_max_evals=self.ac.max_evals, trace=tf, trace4=t4,
+                                           isapprox_rtol=self.ac.isapprox_rtol)
         # decisions taken by less than rounding accuracy (pivot tests of the filter, tau^2 of round 4): a second implementation
         # may legitimately decide the other way, so a comparison has to stop at this state
         self.knife = self.knife or tf.knife_edge() or any(abs(v) < 1e-12 for v in t4.tau2)

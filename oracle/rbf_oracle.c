@@ -50,6 +50,12 @@ typedef struct {
     int32_t optimized_sampling;
 } orc_cfg;
 
+/* rtol of Julia's `isapprox(delta, delta_max)` at RbfModel.jl:588: max(sqrt(eps(T)) over the two argument types) -- sqrt(eps(Float64))
+ * when the algorithm config holds Float64 radii, sqrt(eps(Float32)) = 3.4526698e-4 with the default config, whose delta_max is a
+ * Float32 literal (AbstractConfigInterface.jl:31).  Process-wide setting of the test infrastructure (set once before a run). */
+static double orc_isapprox_rtol = 1.4901161193847656e-08;
+void orc_set_isapprox_rtol(double rtol) { orc_isapprox_rtol = rtol; }
+
 /* ---------------------------------------------------------------- radial functions */
 static double sgn_pow(int e) { return (e & 1) ? -1.0 : 1.0; }
 
@@ -463,7 +469,7 @@ restart:
         *n_dirs = zc;
     }
     int n_missing = n - *n_r1;
-    int approx = fabs(delta - delta_max) <= sqrt(2.220446049250313e-16) * fmax(fabs(delta), fabs(delta_max));
+    int approx = fabs(delta - delta_max) <= orc_isapprox_rtol * fmax(fabs(delta), fabs(delta_max));
     if (n_missing == 0 || skip_search || ensure_fully_linear || (approx && cfg->theta_enlarge_1 == cfg->theta_enlarge_2)) {
         fully_linear = 1;
     } else {
@@ -636,6 +642,77 @@ int orc_build_batched(const orc_cfg* cfg, int B, int n, int k, int N_stride, con
     for (int b = 0; b < B; ++b)
         status[b] = orc_build(cfg, n, k, N[b], sites + (size_t)b * N_stride * n, values + (size_t)b * N_stride * k,
                               w + (size_t)b * N_stride * k, lam + (size_t)b * p * k);
+    return 0;
+}
+
+/* Built-in objectives of the BASELINE configs (the reference evaluates user functions in the thread that runs optimize()).
+ * func_id 1: ZDT3, 2: ZDT1 (both k = 2, inputs clipped to [0,1] like synthetic.py), 3: two parabolas (k = 2). */
+static void orc_objective(int func_id, int n, const double* x, double* y) {
+    if (func_id == 3) {
+        double a = 0, b = 0;
+        for (int i = 0; i < n; ++i) { a += (x[i] - 1.0) * (x[i] - 1.0); b += (x[i] + 1.0) * (x[i] + 1.0); }
+        y[0] = a; y[1] = b;
+        return;
+    }
+    double f1 = fmin(fmax(x[0], 0.0), 1.0), s = 0;
+    for (int i = 1; i < n; ++i) s += fmin(fmax(x[i], 0.0), 1.0);
+    double g = 1.0 + 9.0 * (s / (double)(n - 1));
+    y[0] = f1;
+    if (func_id == 2) y[1] = g * (1.0 - sqrt(f1 / g));
+    else y[1] = g * (1.0 - sqrt(f1 / g) - (f1 / g) * sin(10.0 * 3.14159265358979323846 * f1));
+}
+
+/* One whole model build per instance and thread, nothing between the two halves but the training-set gather
+ * (prepare_update_model -> eval_missing! of the new round-3 sites -> update_model; RbfModel.jl:518-655, 743-767,
+ * Databases.jl:258-277): rounds 1-4, values of [centre; r1; r2; r3; r4] read from the database arrays (round-3 sites are
+ * evaluated with the built-in objective `func_id`, or left 0 when func_id == 0), saddle-system solve.
+ * sites B x n_db x n, values B x n_db x k.  Outputs: N (B), ids (B x ids_stride: training ids, 0 for round-3 sites),
+ * w (B x w_stride x k), lam (B x p x k), status (B).  Returns 0. */
+int orc_select_and_build_batched(const orc_cfg* cfg, int B, int n, int k, int n_db, const double* sites, const double* values,
+                                 const int* x_index, const double* x, const double* delta, double delta_max,
+                                 const double* glb, const double* gub, const int* flags_in, const int* max_new, int func_id,
+                                 int ids_stride, int* N, int* ids, int w_stride, double* w, double* lam, int* status, int nthreads) {
+    const int p = poly_dim(n, eff_degree(cfg));
+    const int mp = cfg->max_model_points <= 0 ? ((n + 1) * (n + 2)) / 2 : cfg->max_model_points;
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+    {
+        int* r1 = (int*)malloc(sizeof(int) * (size_t)(2 * n + mp + 8));
+        int *r2 = r1 + n, *r4 = r2 + n;
+        double* r3 = (double*)malloc(sizeof(double) * ((size_t)n * n * 2 + (size_t)(mp + n + 1) * (n + k)));
+        double* dirs = r3 + (size_t)n * n;
+        double* S = dirs + (size_t)n * n;
+        double* V = S + (size_t)(mp + n + 1) * n;
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; ++b) {
+            const double* sb = sites + (size_t)b * n_db * n;
+            const double* vb = values + (size_t)b * n_db * k;
+            int n1, n2, n3, n4, nd, fl[2];
+            orc_select_points(cfg, n, n_db, sb, x_index[b], x + (size_t)b * n, delta[b], delta_max, glb, gub,
+                              flags_in[2 * b], flags_in[2 * b + 1], max_new[b], r1, &n1, r2, &n2, r3, &n3, r4, &n4, dirs, &nd, fl, 0);
+            int f = 0;
+            int* idb = ids + (size_t)b * ids_stride;
+#define ORC_TAKE(id) do { memcpy(S + (size_t)f * n, sb + (size_t)((id) - 1) * n, sizeof(double) * (size_t)n); \
+                          memcpy(V + (size_t)f * k, vb + (size_t)((id) - 1) * k, sizeof(double) * (size_t)k); \
+                          if (f < ids_stride) idb[f] = (id); ++f; } while (0)
+            ORC_TAKE(x_index[b]);
+            for (int i = 0; i < n1; ++i) ORC_TAKE(r1[i]);
+            for (int i = 0; i < n2; ++i) ORC_TAKE(r2[i]);
+            for (int i = 0; i < n3; ++i) {
+                memcpy(S + (size_t)f * n, r3 + (size_t)i * n, sizeof(double) * (size_t)n);
+                if (func_id > 0 && k == 2) orc_objective(func_id, n, r3 + (size_t)i * n, V + (size_t)f * k);
+                else memset(V + (size_t)f * k, 0, sizeof(double) * (size_t)k);
+                if (f < ids_stride) idb[f] = 0;
+                ++f;
+            }
+            for (int i = 0; i < n4; ++i) ORC_TAKE(r4[i]);
+#undef ORC_TAKE
+            N[b] = f;
+            if (f <= w_stride)
+                status[b] = orc_build(cfg, n, k, f, S, V, w + (size_t)b * w_stride * k, lam + (size_t)b * p * k);
+            else status[b] = -1;
+        }
+        free(r1); free(r3);
+    }
     return 0;
 }
 

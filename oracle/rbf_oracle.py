@@ -4,12 +4,16 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``morbit.jl_b200/`` imports this file; 
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may use it,
 and only as the checker.
 
-PARITY UNPINNED: the reference is pure Julia, no ``julia`` binary exists in this image
-or on the GPU boxes, and the reference ships no golden vectors for this path
+PARITY UNPINNED (by the reference): the reference is pure Julia, no ``julia`` binary exists
+in this image or on the GPU boxes, and the reference ships no golden vectors for this path
 (test/rbf_models.jl holds properties only).  This file is therefore a literal
-restatement of the reference sources, pinned only by the properties of
-test/rbf_models.jl (see tests/test_oracle_properties.py) and by cross-checking against
-the independent C restatement in ``oracle/rbf_oracle.c``.
+restatement of the reference sources, pinned by the properties of test/rbf_models.jl
+(tests/test_oracle_properties.py), by cross-checking against the independent C restatement
+in ``oracle/rbf_oracle.c`` (tests/test_oracle_c_vs_py.py) and -- for the model build and
+evaluation, whose arithmetic lives in the un-vendored dependency -- by an implementation
+written by other people: ``scipy.interpolate.RBFInterpolator`` (tests/test_scipy_pin.py:
+seven radial functions, tails of degree -1/0/1, values to cond * eps, Jacobians against
+finite differences of SciPy's values).
 
 Half of the arithmetic lives in the un-vendored dependency RadialBasisFunctionModels.jl
 (compat "0.3.4", Project.toml:25,50; no Manifest, so no exact pin).  Its published
@@ -420,6 +424,12 @@ def _rbf_round3(db, lb_1, ub_1, x, piv, dirs, max_new, n_missing, ensure_fully_l
 class Round4Trace:
     tau2: List[float] = field(default_factory=list)
     accepted: List[bool] = field(default_factory=list)
+    cid: List[int] = field(default_factory=list)          # candidate id each tau2 belongs to
+    n_points: List[int] = field(default_factory=list)     # model points N when the candidate was tested
+    sigma: List[float] = field(default_factory=list)      # the two terms tau2 = sigma - lv2 is the difference of
+    lv2: List[float] = field(default_factory=list)
+    guard: List[bool] = field(default_factory=list)       # candidate skipped by the rank guard (:433-438); tau2 holds the row norm
+    phi_scale: float = 1.0                                # max |Phi_ij| of the starting kernel matrix (noise scale of tau2)
 
 
 def rbf_round4(db: ArrayDB, lb_2, ub_2, x, delta, found: Sequence[int], cfg: RbfConfig,
@@ -462,16 +472,23 @@ def rbf_round4(db: ArrayDB, lb_2, ub_2, x, delta, found: Sequence[int], cfg: Rbf
             R_xi, G = nullify_last_row(R_xi)                             # :431
             if N < full_rank_dim:
                 if np.linalg.norm(R_xi[-1, :]) <= EPS * 10:             # :434
+                    if trace is not None:
+                        trace.tau2.append(float(np.linalg.norm(R_xi[-1, :]))); trace.accepted.append(False); trace.cid.append(int(cid))
+                        trace.n_points.append(int(N)); trace.sigma.append(0.0); trace.lv2.append(0.0); trace.guard.append(True)
                     continue
             g_t = G.T[:-1, -1]                                           # :442
             g_h = G[-1, -1]                                              # :443
             Qg = Q @ g_t
             v = Z.T @ (Phi @ Qg + phi_xi * g_h)                          # :446
             sigma = Qg @ Phi @ Qg + (2 * g_h) * (phi_xi @ Qg) + g_h ** 2 * phi0   # :447
-            tau2 = sigma - float(np.linalg.norm(Linv @ v)) ** 2          # :449
+            lv2 = float(np.linalg.norm(Linv @ v)) ** 2
+            tau2 = sigma - lv2                                           # :449
             ok = tau2 > chol_pivot ** 2                                  # :452 (squared twice)
             if trace is not None:
                 trace.tau2.append(float(tau2)); trace.accepted.append(bool(ok))
+                trace.cid.append(int(cid)); trace.n_points.append(int(N))
+                trace.sigma.append(float(sigma)); trace.lv2.append(lv2); trace.guard.append(False)
+                trace.phi_scale = max(trace.phi_scale, float(np.max(np.abs(Phi))))
             if ok:
                 r4.append(cid)
                 tau = math.sqrt(tau2)
@@ -492,16 +509,23 @@ def rbf_round4(db: ArrayDB, lb_2, ub_2, x, delta, found: Sequence[int], cfg: Rbf
     return r4
 
 
-def isapprox(a: float, b: float) -> bool:
-    """Julia's default isapprox: rtol = sqrt(eps)."""
-    return abs(a - b) <= math.sqrt(EPS) * max(abs(a), abs(b))
+ISAPPROX_RTOL_F64 = math.sqrt(EPS)
+ISAPPROX_RTOL_F32 = math.sqrt(float(np.finfo(np.float32).eps))      # 3.4526698e-4
+
+
+def isapprox(a: float, b: float, rtol: float = ISAPPROX_RTOL_F64) -> bool:
+    """Julia's default isapprox: rtol = max(sqrt(eps(T)) over the argument types).  At RbfModel.jl:588 the radius is compared with
+    delta_max(algo_config), a Float32 literal in the default config (AbstractConfigInterface.jl:31) => sqrt(eps(Float32));
+    a user-supplied AlgorithmConfig{Float64} gives sqrt(eps(Float64))."""
+    return abs(a - b) <= rtol * max(abs(a), abs(b))
 
 
 def prepare_update_model(meta: RbfMeta, cfg: RbfConfig, db: ArrayDB, x, x_index: int, delta: float,
                          delta_max: float, glb, gub, *, ensure_fully_linear=False, force_rebuild=False,
                          meta_array: Optional[Sequence[Tuple[RbfMeta, ArrayDB]]] = None,
                          num_objf_evals: int = 0, algo_max_evals: int = INT_MAX,
-                         trace: Optional[FilterTrace] = None, trace4: Optional[Round4Trace] = None):
+                         trace: Optional[FilterTrace] = None, trace4: Optional[Round4Trace] = None,
+                         isapprox_rtol: float = ISAPPROX_RTOL_F64):
     """A9, RbfModel.jl:518-655 (state machine of SURVEY App. A.2)."""
     x = np.asarray(x, dtype=np.float64)
     n = len(x)
@@ -538,7 +562,7 @@ def prepare_update_model(meta: RbfMeta, cfg: RbfConfig, db: ArrayDB, x, x_index:
         meta.improving_directions = list(dirs)
         n_missing = n - len(meta.round1_indices)
         if (n_missing == 0 or force_rebuild or not cfg.optimized_sampling or ensure_fully_linear
-                or (isapprox(delta, delta_max) and cfg.theta_enlarge_1 == cfg.theta_enlarge_2)):   # :588
+                or (isapprox(delta, delta_max, isapprox_rtol) and cfg.theta_enlarge_1 == cfg.theta_enlarge_2)):   # :588
             meta.fully_linear = True
             meta.round2_indices = []
         else:
@@ -559,7 +583,7 @@ def prepare_update_model(meta: RbfMeta, cfg: RbfConfig, db: ArrayDB, x, x_index:
                 return prepare_update_model(meta, cfg, db, x, x_index, delta, delta_max, glb, gub,
                                             ensure_fully_linear=True, force_rebuild=True,
                                             num_objf_evals=num_objf_evals, algo_max_evals=algo_max_evals,
-                                            trace=trace, trace4=trace4)  # :634-637
+                                            trace=trace, trace4=trace4, isapprox_rtol=isapprox_rtol)  # :634-637
     meta.round4_indices = []
     if cfg.optimized_sampling:                                           # :647-652
         meta.round4_indices = rbf_round4(db, lb_2, ub_2, x, delta, meta.collect_indices(), cfg, trace4)

@@ -36,3 +36,45 @@ def assert_select_equal(res, ref, B, check_dirs=True):
             kd = ref.n_dirs[b]
             if kd:
                 np.testing.assert_allclose(res.dirs[b, :kd], ref.dirs[b, :kd], rtol=0, atol=1e-11)
+
+
+def literal_round4_verdict(cfg, sites, x, delta, delta_max, glb, gub, efl, max_new, got):
+    """Literal NumPy oracle (oracle/rbf_oracle.py, the reference's own dense operation order) for ONE instance whose round 4 starts
+    under-poised (N0 < n + 1).  `got` = dict with the r1, r2, r4 id lists and n_r3 of the implementation under test.
+
+    Returns ("equal", None) when every list is the literal oracle's, else ("noise", info) when rounds 1-3 agree and the FIRST
+    round-4 decision on which the two differ is one the literal oracle itself took at rounding level -- tau^2 = sigma - |L^-1 v|^2
+    (RbfModel.jl:447-452) cancelled to below 1e-8 of its terms (or below 1e-12 of |Phi|), or the rank guard's row norm (:433-438)
+    was below 1e-12 -- i.e. the reference's own accept/reject there depends on the summation order of its BLAS.  Anything else
+    returns ("mismatch", info)."""
+    from oracle import rbf_oracle as O
+    ocfg = O.RbfConfig(kernel=cfg.kernel, shape_parameter=cfg.shape_parameter, polynomial_degree=cfg.polynomial_degree,
+                       theta_enlarge_1=cfg.theta_enlarge_1, theta_enlarge_2=cfg.theta_enlarge_2, theta_pivot=cfg.theta_pivot,
+                       theta_pivot_cholesky=cfg.theta_pivot_cholesky, max_model_points=cfg.max_model_points)
+    db = O.ArrayDB()
+    for s in sites:
+        db.new_result(s, [0.0])
+    meta = O.RbfMeta(signature=ocfg.signature())
+    t4 = O.Round4Trace()
+    amax = O.INT_MAX if max_new >= 2**31 - 1 else max_new + 1
+    O.prepare_update_model(meta, ocfg, db, np.asarray(x, float), 1, float(delta), delta_max, glb, gub, ensure_fully_linear=efl,
+                           algo_max_evals=amax, trace4=t4)
+    lit = dict(r1=meta.round1_indices, r2=meta.round2_indices, r4=meta.round4_indices, n_r3=len(meta.round3_indices))
+    if [int(v) for v in got["r1"]] != lit["r1"] or [int(v) for v in got["r2"]] != lit["r2"] or int(got["n_r3"]) != lit["n_r3"]:
+        return "mismatch", dict(stage="rounds 1-3", literal=lit)
+    g4 = [int(v) for v in got["r4"]]
+    if g4 == lit["r4"]:
+        return "equal", None
+    gset = set(g4)
+    for i, cid in enumerate(t4.cid):
+        if (cid in gset) != bool(t4.accepted[i]):
+            if t4.guard[i]:
+                noise = t4.tau2[i] <= 1e-12
+            else:
+                terms = max(abs(t4.sigma[i]), abs(t4.lv2[i]))
+                noise = abs(t4.tau2[i]) <= max(1e-8 * terms, 1e-12 * t4.phi_scale)
+            info = dict(candidate=cid, tau2=t4.tau2[i], sigma=t4.sigma[i], lv2=t4.lv2[i], guard=t4.guard[i], n_points=t4.n_points[i],
+                        literal=lit["r4"], got=g4)
+            return ("noise" if noise else "mismatch"), info
+    # identical decisions on every candidate the literal oracle tested, yet different lists: the implementation tested more
+    return "mismatch", dict(stage="candidate walk", literal=lit["r4"], got=g4)

@@ -21,7 +21,7 @@ def test_library_exports_every_header_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in morbit_rbf.h but not exported"
     assert declared == set(mb._lib.SIGNATURES), declared ^ set(mb._lib.SIGNATURES)
-    assert lib.mrbf_abi_version() == 1
+    assert lib.mrbf_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -8,7 +8,7 @@ import pytest
 import morbit_jl_b200 as mb
 from oracle import c_oracle as CO
 from oracle import rbf_oracle as O
-from helpers import random_instances, assert_select_equal
+from helpers import random_instances, assert_select_equal, literal_round4_verdict
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10          # north-star tolerance for values / Jacobians (relative to the largest magnitude)
@@ -448,10 +448,12 @@ def test_large_database_block_kernel_and_streamed_build(engine):
 def test_select_points_randomised_sweep(engine):
     """Seeded random sweep over shapes, kernels, budgets and caps (the register-tiled round-4 kernel takes every database of <= 128
     sites here: 1..127 candidates, partial tile rows, caps that hit inside a pivot block, ragged databases).  Indices, counters and
-    flags must be the oracle's.  A mismatch is accepted only where the oracle itself reports a knife-edge decision margin."""
+    flags must be the oracle's: the C port for the poised instances (no mismatch tolerated on this corpus), the LITERAL NumPy oracle
+    for the instances whose round 4 starts under-poised (N0 < n + 1), where the only accepted difference is a decision the literal
+    oracle's own tau^2 trace proves to be the sign of a rounding residue."""
     rng = np.random.default_rng(20261018)
     kernels = ["cubic", "multiquadric", "gaussian", "inv_multiquadric"]
-    n_cases = n_noise = 0
+    n_cases = n_noise = n_under = n_knife = 0
     for trial in range(48):
         n = int(rng.integers(2, 13))
         n_db = int(rng.integers(1, 129))
@@ -476,21 +478,27 @@ def test_select_points_randomised_sweep(engine):
             same = all(list(getattr(res, nm)[b, :getattr(res, cnt)[b]]) == list(getattr(ref, nm)[0, :getattr(ref, cnt)[0]])
                        for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4"))) and res.n_r3[b] == ref.n_r3[0]
             N0 = 1 + int(ref.n_r1[0]) + int(ref.n_r2[0]) + int(ref.n_r3[0])
-            if not same and N0 < n + 1:
-                # Budget-limited round 3: round 4 starts with fewer points than polynomial basis functions.  Then the reference's own
-                # test quantity tau^2 (RbfModel.jl:447-452) is pure rounding noise (+-1e-17 against a threshold of 1e-28) for most
-                # candidates -- the literal NumPy oracle and its C twin disagree with each other on exactly these instances
-                # (tests/test_oracle_c_vs_py.py::test_round4_below_poised_is_rounding_noise).  Rounds 1-3 must still agree.
-                assert all(list(getattr(res, nm)[b, :getattr(res, cnt)[b]]) == list(getattr(ref, nm)[0, :getattr(ref, cnt)[0]])
-                           for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"))) and res.n_r3[b] == ref.n_r3[0]
-                n_noise += 1
+            if N0 < n + 1:
+                # Budget-limited round 3: round 4 starts with fewer points than polynomial basis functions.  This regime is checked
+                # against the LITERAL oracle (the reference's own dense operation order, oracle/rbf_oracle.py), not the
+                # structure-exploiting C port.  Every list must be the literal oracle's -- except that the reference's test quantity
+                # tau^2 = sigma - |L^-1 v|^2 (RbfModel.jl:447-452) cancels EXACTLY for candidates that do not enlarge the span, so the
+                # literal oracle's own decision there is the sign of a +-1e-17 rounding residue against the threshold 1e-28.  A
+                # difference is accepted only if the FIRST diverging decision is such a proven coin flip (helpers.literal_round4_verdict
+                # re-runs the literal oracle with its tau^2 trace); everything before it, and rounds 1-3, must be identical.
+                got = dict(r1=res.r1[b, :res.n_r1[b]], r2=res.r2[b, :res.n_r2[b]], r4=res.r4[b, :res.n_r4[b]], n_r3=res.n_r3[b])
+                verdict, info = literal_round4_verdict(cfg, sites[b, :n_dbs[b]], x[b], dl[b], 0.5, glb, gub, efl, max_new, got)
+                assert verdict in ("equal", "noise"), (trial, b, n, n_db, kernel, mmp, verdict, info)
+                n_under += 1
+                n_noise += verdict == "noise"
             elif not same:
                 # knife edge: the oracle's smallest decision margin (filter score vs pivot, tau^2 vs threshold) is at rounding level
                 assert np.min(np.abs(ref.margins[0])) < 1e-9, (trial, b, n, n_db, kernel, mmp, ref.margins[0])
+                n_knife += 1
             else:
                 assert bool(res.flags_out[b, 0]) == bool(ref.fully_linear[0])
             n_cases += 1
-    assert n_cases == 48 * 6 and n_noise <= 8
+    assert n_cases == 48 * 6 and n_under >= 40 and n_noise <= 8 and n_knife == 0, (n_cases, n_under, n_noise, n_knife)
 
 
 def test_kept_factorisation_randomised_sweep(engine):

@@ -120,3 +120,36 @@ def test_round4_below_poised_is_rounding_noise():
             if list(res.r4[0, :res.n_r4[0]]) != meta.round4_indices:
                 assert len(tiny) > 0        # a disagreement is always explained by a noise-level tau^2
     assert noise_seen
+
+
+def test_under_poised_round4_c_port_vs_literal_per_case_proof():
+    """The corpus of tests/test_gpu_parity.py::test_select_points_randomised_sweep, with the C port standing in for the GPU: on every
+    instance whose round 4 starts with fewer points than polynomial basis functions the C port either reproduces the literal oracle's
+    lists or first departs from them at a candidate whose tau^2 the literal oracle itself computed as an exact cancellation
+    (|tau^2| <= 1e-8 of its two terms) -- a coin flip in the reference's own operation order."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import random_instances, literal_round4_verdict
+    rng = np.random.default_rng(20261018)
+    kernels = ["cubic", "multiquadric", "gaussian", "inv_multiquadric"]
+    count = {"equal": 0, "noise": 0}
+    for trial in range(48):
+        n = int(rng.integers(2, 13)); n_db = int(rng.integers(1, 129)); B = 6
+        kernel = kernels[trial % 4]
+        mmp = int(rng.choice([-1, -1, n + 2, 2 * n + 1, n + 1 + int(rng.integers(1, 9))]))
+        cfg = O.RbfConfig(kernel=kernel, max_model_points=mmp)
+        spread = float(rng.choice([0.15, 0.6, 1.2]))
+        sites, x, glb, gub = random_instances(rng, B, n, n_db, bool(trial % 3), spread=spread)
+        n_dbs = np.minimum(n_db, rng.integers(1, n_db + 1, size=B)).astype(np.int32); n_dbs[0] = n_db
+        dl = rng.choice([0.02, 0.1, 0.3], size=B)
+        efl = bool(trial % 2)
+        max_new = int(rng.choice([0, 1, 3, 2**31 - 1]))
+        for b in range(B):
+            ref = CO.select_points_batched(cfg, sites[b:b + 1, :n_dbs[b]], [1], x[b:b + 1], dl[b:b + 1], 0.5, glb, gub, efl, False, max_new)
+            if 1 + int(ref.n_r1[0]) + int(ref.n_r2[0]) + int(ref.n_r3[0]) >= n + 1:
+                continue
+            got = dict(r1=ref.r1[0, :ref.n_r1[0]], r2=ref.r2[0, :ref.n_r2[0]], r4=ref.r4[0, :ref.n_r4[0]], n_r3=ref.n_r3[0])
+            verdict, info = literal_round4_verdict(cfg, sites[b, :n_dbs[b]], x[b], dl[b], 0.5, glb, gub, efl, max_new, got)
+            assert verdict in count, (trial, b, verdict, info)
+            count[verdict] += 1
+    assert count["equal"] >= 40 and count["noise"] <= 8, count
