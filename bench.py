@@ -279,6 +279,20 @@ def run_ours(args):
     # ---- final gather of per-instance results (the only collective)
     rows = np.stack([Ntrain, n_r4, status.cpu().numpy()], axis=1).astype(np.float64)
     allrows = gather_results(rows, world * B, rank, world)
+    gather_c_abi = None
+    if world > 1:
+        # the same gather through the C export a Julia host would call (mrbf_comm_init + mrbf_gather: ncclAllGather on the library's
+        # own communicator; the 128-byte NCCL id travels over the host channel, here torch.distributed's store)
+        from morbit_jl_b200.multistart import gather_results_c_abi
+        box = [mb.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = mb.Comm(local, box[0], rank, world)
+        t0g = time.perf_counter()
+        allrows_c = gather_results_c_abi(comm, rows, world * B)
+        gather_c_abi = {"ms": (time.perf_counter() - t0g) * 1e3, "equal_to_torch_distributed": bool(np.array_equal(allrows_c, allrows))}
+        comm.close()
+        if not gather_c_abi["equal_to_torch_distributed"]:
+            raise SystemExit("mrbf_gather disagrees with torch.distributed.all_gather")
 
     # ---- secondary metric: surrogate evals/s and Jacobians/s (config C5)
     secondary = []
@@ -406,7 +420,7 @@ def run_ours(args):
                                 f"snapshot runs behind the kernels of the current one; {args.e2e_outputs} set(s) of result buffers -- a step's result copy "
                                 "runs behind the next step's kernels, the timed region ends when the last copy has landed"},
                 "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
-                "gathered_rows": None if allrows is None else int(allrows.shape[0])}
+                "gathered_rows": None if allrows is None else int(allrows.shape[0]), "gather_c_abi": gather_c_abi}
         emit(line)
     model.free()
     if world > 1:

@@ -256,6 +256,27 @@ int mrbf_db_append_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int32_t d
  * (room for more training points per instance) than `src`. */
 int mrbf_model_scatter_dev(mrbf_ctx* ctx, mrbf_model* dst, const mrbf_model* src, const int32_t* map, int32_t S);
 
+/* ---- multi-GPU: the final gather of per-instance results (the only collective of the path) -----------------
+ * Independent multistart instances / objective blocks shard over the GPUs of a box with NO collective on the data path (the
+ * reference runs them independently under Threads.@threads, examples/large_scale_benchmarks.jl:253).  When the runs are over every
+ * rank (one host process or thread per GPU) contributes its result rows -- x, f(x), stop code, #evals, training ids ... -- and
+ * receives everybody's: one ncclAllGather over NVLink / NVSwitch.  NCCL is loaded at run time (dlopen "libnccl.so.2", or the path in
+ * $MRBF_NCCL_LIB); without it these entry points return MRBF_EUNSUPPORTED and nothing else of the library is affected.
+ *
+ *   mrbf_comm_unique_id   rank 0 creates the 128-byte NCCL id; the host distributes it (Distributed.jl, MPI, a file ...)
+ *   mrbf_comm_init        ncclCommInitRank on `device` (collective: every rank calls it with the same id)
+ *   mrbf_comm_from_nccl   wrap a communicator the host already has (NCCL.jl, torch) -- not destroyed with the handle
+ *   mrbf_gather           rows: count x width doubles of this rank (HOST pointer); all_rows: world x max_count x width doubles,
+ *                         block r holds rank r's rows (zero padded), counts[r] its row count; max_count >= every rank's count and
+ *                         equal on all ranks.  Blocks until the result is in host memory. */
+typedef struct mrbf_comm mrbf_comm;
+int mrbf_comm_unique_id(char* id128);
+int mrbf_comm_init(int device, const char* id128, int32_t rank, int32_t world, mrbf_comm** comm);
+int mrbf_comm_from_nccl(int device, void* nccl_comm, int32_t rank, int32_t world, mrbf_comm** comm);
+void mrbf_comm_destroy(mrbf_comm* comm);
+const char* mrbf_comm_last_error(const mrbf_comm* comm);
+int mrbf_gather(mrbf_comm* comm, const double* rows, int32_t count, int32_t width, int32_t max_count, double* all_rows, int32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ from ._lib import MrbfError, LIB_PATH
 
 _lib.load()
 
-from .engine import Engine, ModelBatch, Prepared, SelectResult, max_model_points, to_c_cfg  # noqa: E402
+from .engine import Engine, Comm, ModelBatch, Prepared, SelectResult, max_model_points, to_c_cfg  # noqa: E402
 from .surrogate import (  # noqa: E402
     RBF_KERNELS, RbfConfig, RbfMeta, RbfModel, ArrayDB, SuperDB, IterData, VarScaler, AlgoConfig, MopStub,
     max_evals, combinable, get_saveable, fully_linear, set_fully_linear, num_outputs, get_sub_db,

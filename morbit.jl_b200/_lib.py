@@ -69,6 +69,12 @@ SIGNATURES = {
     "mrbf_descent_direction_dev": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mrbf_db_append_dev": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mrbf_model_scatter_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i32]),
+    "mrbf_comm_unique_id": (C.c_int, [_vp]),
+    "mrbf_comm_init": (C.c_int, [C.c_int, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "mrbf_comm_from_nccl": (C.c_int, [C.c_int, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "mrbf_comm_destroy": (None, [_vp]),
+    "mrbf_comm_last_error": (C.c_char_p, [_vp]),
+    "mrbf_gather": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
 }
 
 _lib = None

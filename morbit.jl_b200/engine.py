@@ -103,6 +103,53 @@ class Prepared:
             pass
 
 
+class Comm:
+    """NCCL communicator for the final gather of per-instance results (mrbf_comm_*, mrbf_gather: the only collective of the
+    path).  `unique_id()` on rank 0, hand the 128 bytes to every rank (any host channel), then `Comm(device, id, rank, world)`."""
+
+    def __init__(self, device: int, unique_id: bytes, rank: int, world: int):
+        self.lib = _lib.load()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        h = C.c_void_p()
+        rc = self.lib.mrbf_comm_init(self.device, buf, self.rank, self.world, C.byref(h))
+        if rc != 0:
+            raise MrbfError(rc, "mrbf_comm_init failed: " + self.lib.mrbf_comm_last_error(None).decode(errors="replace"))
+        self.handle = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        rc = lib.mrbf_comm_unique_id(buf)
+        if rc != 0:
+            raise MrbfError(rc, "mrbf_comm_unique_id failed: " + lib.mrbf_comm_last_error(None).decode(errors="replace"))
+        return buf.raw
+
+    def gather(self, rows: np.ndarray, max_count: int):
+        """rows: (count, width) float64 of this rank -> list of per-rank arrays (counts[r], width)."""
+        rows = _np(rows, np.float64)
+        rows = rows.reshape(rows.shape[0], -1)
+        count, width = rows.shape
+        out = np.zeros((self.world, int(max_count), width))
+        counts = np.zeros(self.world, np.int32)
+        rc = self.lib.mrbf_gather(self.handle, _ptr(rows), count, width, int(max_count), _ptr(out), _ptr(counts))
+        if rc != 0:
+            raise MrbfError(rc, self.lib.mrbf_comm_last_error(self.handle).decode(errors="replace"))
+        return [out[r, :counts[r]] for r in range(self.world)]
+
+    def close(self):
+        if self.handle:
+            self.lib.mrbf_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, device: int = 0, stream: Optional[int] = None):
         self.lib = _lib.load()

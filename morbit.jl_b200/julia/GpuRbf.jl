@@ -1,15 +1,19 @@
 # GpuRbf.jl -- the Julia side of the drop-in: a `GpuRbfConfig <: AbstractSurrogateConfig` whose methods reach
-# CUDA only through `ccall` into libmorbit_rbf.so (include/morbit_rbf.h).  No CUDA.jl, no kernel DSL.
+# CUDA only through `ccall` into libmorbit_rbf.so (include/morbit_rbf.h).  No CUDA.jl, no kernel DSL, no CPU fallback.
 #
 # This file cannot be executed in the build image (no `julia` binary); it is the binding a Morbit maintainer adds
 # (`include("GpuRbf.jl")` after `models/RbfModel.jl` in src/Morbit.jl:80).  Every method below names the reference
 # method it replaces.  The Python mirror `morbit.jl_b200/surrogate.py` implements exactly the same host logic and is
-# what the parity tests drive.
+# what the parity tests drive; `tests/test_cpu_host.py::test_julia_shim_ccall_signatures_match_header` checks every
+# `ccall` argument tuple in this file against the C header's prototypes.
 #
 # Host logic kept in Julia (as in the reference): database appends (`new_result!`), site matching for
 # `_exploit_other_rbf_metas!`, the evaluation budget, string shape parameters.  Everything numerical is one ccall.
 
 const LIBMRBF = get(ENV, "MORBIT_RBF_LIB", "libmorbit_rbf.so")
+
+const MRBF_OK = Cint(0)
+const MRBF_ENUMERIC = Cint(-5)      # some instances failed numerically: the handle is valid, status[] says which
 
 # struct mrbf_cfg (include/morbit_rbf.h) -- field order and types must match
 struct MrbfCfg
@@ -28,21 +32,40 @@ end
 
 const KERNEL_IDS = Dict(:cubic => 0, :inv_multiquadric => 1, :multiquadric => 2, :thin_plate_spline => 3, :gaussian => 4)
 
-# one context per (Julia thread, device): the reference runs many `optimize` under Threads.@threads
-# (examples/large_scale_benchmarks.jl:253), the library is re-entrant per context
-const _CTX = Dict{Tuple{Int,Int},Ptr{Cvoid}}()
+# ---------------------------------------------------------------------------------------------------------------
+# Contexts.  An mrbf_ctx is NOT thread safe (grow-only workspaces, one stream, one error string), and Julia tasks
+# migrate between threads (`Threads.@threads` is :dynamic; examples/large_scale_benchmarks.jl:253 runs many `optimize`
+# concurrently), so a context can be keyed neither by thread id nor by task.  Instead every device has a POOL of
+# contexts: a call borrows one (creating it when the pool is empty), runs, and puts it back.  Concurrent calls get
+# different contexts and therefore different streams; a model handle may be used with any context of its device
+# (the host-pointer entry points return only after their stream has drained).
+# ---------------------------------------------------------------------------------------------------------------
+const _CTX_POOL = Dict{Int,Vector{Ptr{Cvoid}}}()
 const _CTX_LOCK = ReentrantLock()
-function mrbf_ctx(device::Int = 0)
-    lock(_CTX_LOCK) do
-        get!(_CTX, (Threads.threadid(), device)) do
-            ref = Ref{Ptr{Cvoid}}(C_NULL)
-            rc = ccall((:mrbf_init, LIBMRBF), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ref)
-            rc == 0 || error("mrbf_init failed ($rc): no usable CUDA device; there is no CPU fallback")
-            ref[]
-        end
+
+function _new_ctx(device::Int)
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mrbf_init, LIBMRBF), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ref)
+    rc == MRBF_OK || error("mrbf_init failed ($rc): no usable CUDA device; there is no CPU fallback")
+    return ref[]
+end
+
+"Borrow a context of `device` for the duration of `f(ctx)`."
+function with_ctx(f, device::Int = 0)
+    ctx = lock(_CTX_LOCK) do
+        pool = get!(_CTX_POOL, device) do; Ptr{Cvoid}[]; end
+        isempty(pool) ? C_NULL : pop!(pool)
+    end
+    ctx == C_NULL && (ctx = _new_ctx(device))
+    try
+        return f(ctx)
+    finally
+        lock(_CTX_LOCK) do; push!(_CTX_POOL[device], ctx); end
     end
 end
-_check(ctx, rc) = rc == 0 || error("libmorbit_rbf: " * unsafe_string(ccall((:mrbf_last_error, LIBMRBF), Cstring, (Ptr{Cvoid},), ctx)))
+
+_errmsg(ctx) = unsafe_string(ccall((:mrbf_last_error, LIBMRBF), Cstring, (Ptr{Cvoid},), ctx))
+_check(ctx, rc) = rc == MRBF_OK || error("libmorbit_rbf: " * _errmsg(ctx))
 
 # ---------------------------------------------------------------------------------------------------------------
 # Config / meta / model  (replace RbfConfig, RbfMeta, RbfModel -- src/models/RbfModel.jl:33-38, 66-112, 148-159)
@@ -59,25 +82,47 @@ get_saveable_type(cfg::GpuRbfConfig, x, y) = get_saveable_type(cfg.rbf, x, y)
 requires_update(::GpuRbfConfig) = true
 requires_improve(::GpuRbfConfig) = true
 
-const GpuRbfMeta = RbfMeta          # same bookkeeping fields (center_index, round1..4_indices, fully_linear, improving_directions)
+const GpuRbfMeta = RbfMeta          # same bookkeeping fields, so `other_meta isa RbfMeta` in _exploit_other_rbf_metas! holds
 
 mutable struct GpuRbfModel <: AbstractSurrogate
     handle::Ptr{Cvoid}              # opaque mrbf_model* (device-resident centres, coefficients)
-    ctx::Ptr{Cvoid}
+    device::Int
     n::Int
     k::Int
     fully_linear::Bool
-    function GpuRbfModel(handle, ctx, n, k, fl)
-        m = new(handle, ctx, n, k, fl)
-        finalizer(m) do mm
-            ccall((:mrbf_free_model, LIBMRBF), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}), mm.ctx, mm.handle)
-        end
+    status::Int32                   # 0, or > 0: the reduced kernel matrix was not positive definite (duplicated sites)
+    function GpuRbfModel(handle, device, n, k, fl, status = Int32(0))
+        m = new(handle, device, n, k, fl, status)
+        # finalizers must not take locks or switch tasks: mrbf_free_model accepts a NULL context (plain cudaFree)
+        finalizer(mm -> (mm.handle == C_NULL || ccall((:mrbf_free_model, LIBMRBF), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}), C_NULL, mm.handle); mm.handle = C_NULL), m)
         m
     end
 end
 fully_linear(m::GpuRbfModel) = m.fully_linear
 set_fully_linear!(m::GpuRbfModel, v) = (m.fully_linear = v; nothing)
 num_outputs(m::GpuRbfModel) = m.k
+
+# What the reference throws away between prepare_update_model and update_model and notes it should keep
+# (RbfModel.jl:657-660): the round-4 factorisation (opaque mrbf_prepared*, device resident) and the selection outputs
+# it belongs to.  RbfMeta has no spare field, so the state hangs off the meta object in a weak-keyed side table.
+mutable struct KeptSelection
+    prepared::Ptr{Cvoid}
+    n_db::Int                       # database size the selection saw (ids 1..n_db)
+    x_index::Int32
+    r1::Vector{Int32}; n_r1::Vector{Int32}
+    r2::Vector{Int32}; n_r2::Vector{Int32}
+    r3::Matrix{Float64}; n_r3::Vector{Int32}
+    function KeptSelection(args...)
+        k = new(args...)
+        finalizer(kk -> (kk.prepared == C_NULL || ccall((:mrbf_free_prepared, LIBMRBF), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}), C_NULL, kk.prepared); kk.prepared = C_NULL), k)
+        k
+    end
+end
+const _KEPT = WeakKeyDict{Any,KeptSelection}()
+const _KEPT_LOCK = ReentrantLock()
+_kept(meta) = lock(() -> get(_KEPT, meta, nothing), _KEPT_LOCK)
+_keep!(meta, k) = lock(() -> (_KEPT[meta] = k), _KEPT_LOCK)
+_drop_kept!(meta) = lock(() -> delete!(_KEPT, meta), _KEPT_LOCK)
 
 function _c_cfg(cfg::RbfConfig, Δ)
     sp = cfg.shape_parameter isa String ? parse_shape_param_string(Δ, cfg.shape_parameter) : cfg.shape_parameter
@@ -89,7 +134,7 @@ end
 _site_matrix(db) = reduce(hcat, (Vector{Float64}(get_site(db, id)) for id in get_ids(db)); init = zeros(Float64, length(get_site(db, 1)), 0))
 
 # ---------------------------------------------------------------------------------------------------------------
-# prepare_init_model / prepare_update_model   (RbfModel.jl:506-513, 518-655)  -> mrbf_select_points
+# prepare_init_model / prepare_update_model   (RbfModel.jl:506-513, 518-655)  -> mrbf_select_points_keep
 # ---------------------------------------------------------------------------------------------------------------
 function prepare_init_model(cfg::GpuRbfConfig, func_indices, mop, scal, id, sdb, ac; ensure_fully_linear = true, kwargs...)
     F = eltype(get_x_scaled(id))
@@ -100,9 +145,11 @@ end
 function prepare_update_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cfg::GpuRbfConfig, func_indices, mop, scal,
         iter_data, sdb, algo_config; ensure_fully_linear = false, force_rebuild = false, meta_array = nothing)
     rcfg = cfg.rbf
-    ctx = mrbf_ctx(cfg.device)
     db = get_sub_db(sdb, func_indices)
     Δ = Float64(get_delta(iter_data)); Δ_max = Float64(delta_max(algo_config))
+    # `Δ ≈ Δ_max` at RbfModel.jl:588 compares with the tolerance of the LESS precise argument type (the default config's
+    # delta_max is a Float32 literal, AbstractConfigInterface.jl:31)
+    rtol = Float64(Base.rtoldefault(typeof(get_delta(iter_data)), typeof(delta_max(algo_config)), 0))
     x = Vector{Float64}(get_x_scaled(iter_data)); n = length(x)
     x_index = get_x_index(iter_data, Tuple(func_indices))
     meta.fully_linear = false
@@ -114,17 +161,20 @@ function prepare_update_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cf
     max_points = rcfg.max_model_points <= 0 ? ((n + 1) * (n + 2)) ÷ 2 : rcfg.max_model_points
     r4 = zeros(Int32, max_points); n_r4 = Int32[0]; status = Int32[0]
     if skip                                                               # @goto round4, RbfModel.jl:562
+        _drop_kept!(meta)                  # rounds 1-3 came from another group: from-scratch build (mrbf_build) for this one
         empty!(meta.round4_indices)
         if rcfg.optimized_sampling
             Δ_2 = rcfg.θ_enlarge_2 * Δ_max
-            lb_2 = max.(lb, x .- Δ_2); ub_2 = min.(ub, x .+ Δ_2)
+            lb_2 = Vector{Float64}(max.(lb, x .- Δ_2)); ub_2 = Vector{Float64}(min.(ub, x .+ Δ_2))
             found = Int32.(_collect_indices(meta)); n_found = Int32[length(found)]
-            GC.@preserve sites found lb_2 ub_2 r4 begin
-                _check(ctx, ccall((:mrbf_round4, LIBMRBF), Cint,
-                    (Ptr{Cvoid}, Ref{MrbfCfg}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
-                     Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
-                    ctx, ccfg, 1, n, n_db[1], sites, n_db, lb_2, ub_2, length(found), found, n_found, 0, C_NULL, C_NULL,
-                    max_points, r4, n_r4, status))
+            with_ctx(cfg.device) do ctx
+                GC.@preserve sites found lb_2 ub_2 r4 begin
+                    _check(ctx, ccall((:mrbf_round4, LIBMRBF), Cint,
+                        (Ptr{Cvoid}, Ref{MrbfCfg}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
+                         Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                        ctx, ccfg, 1, n, n_db[1], sites, n_db, lb_2, ub_2, length(found), found, n_found, 0, C_NULL, C_NULL,
+                        max_points, r4, n_r4, status))
+                end
             end
             append!(meta.round4_indices, Int.(r4[1:n_r4[1]]))
         end
@@ -138,14 +188,22 @@ function prepare_update_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cf
     r1 = zeros(Int32, n); r2 = zeros(Int32, n); r3 = zeros(Float64, n, n); dirs = zeros(Float64, n, n)
     n_r1 = Int32[0]; n_r2 = Int32[0]; n_r3 = Int32[0]; n_dirs = Int32[0]; flags_out = zeros(Int32, 2)
     xi = Int32[x_index]; Δv = Float64[Δ]
-    GC.@preserve sites x lb ub r1 r2 r3 r4 dirs begin
-        _check(ctx, ccall((:mrbf_select_points, LIBMRBF), Cint,
-            (Ptr{Cvoid}, Ref{MrbfCfg}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Float64,
-             Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
-             Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
-            ctx, ccfg, 1, n, n_db[1], sites, n_db, xi, x, Δv, Δ_max, Vector{Float64}(lb), Vector{Float64}(ub), flags_in, max_new,
-            r1, n_r1, r2, n_r2, r3, n_r3, max_points, r4, n_r4, dirs, n_dirs, flags_out, status))
+    lbv = Vector{Float64}(lb); ubv = Vector{Float64}(ub)
+    old = _kept(meta)
+    prepared = Ref{Ptr{Cvoid}}(isnothing(old) ? C_NULL : old.prepared)   # an earlier handle is recycled by the library
+    isnothing(old) || (old.prepared = C_NULL)                             # ownership moves through the call
+    with_ctx(cfg.device) do ctx
+        _check(ctx, ccall((:mrbf_set_isapprox_rtol, LIBMRBF), Cint, (Ptr{Cvoid}, Float64), ctx, rtol))
+        GC.@preserve sites x lbv ubv r1 r2 r3 r4 dirs begin
+            _check(ctx, ccall((:mrbf_select_points_keep, LIBMRBF), Cint,
+                (Ptr{Cvoid}, Ref{MrbfCfg}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Float64,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
+                 Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+                ctx, ccfg, 1, n, n_db[1], sites, n_db, xi, x, Δv, Δ_max, lbv, ubv, flags_in, max_new,
+                r1, n_r1, r2, n_r2, r3, n_r3, max_points, r4, n_r4, dirs, n_dirs, flags_out, status, prepared))
+        end
     end
+    _keep!(meta, KeptSelection(prepared[], Int(n_db[1]), Int32(x_index), r1, n_r1, r2, n_r2, r3, n_r3))
     F = eltype(get_x_scaled(iter_data))
     empty!(meta.round1_indices); append!(meta.round1_indices, Int.(r1[1:n_r1[1]]))
     empty!(meta.round2_indices); append!(meta.round2_indices, Int.(r2[1:n_r2[1]]))
@@ -159,31 +217,70 @@ function prepare_update_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cf
     return meta
 end
 
-# prepare_improve_model is n-sized scalar logic on ids and one wall step: the reference method is reused unchanged
-prepare_improve_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cfg::GpuRbfConfig, args...; kwargs...) =
-    prepare_improve_model(nothing, meta, cfg.rbf, args...; kwargs...)      # RbfModel.jl:699-732
+# prepare_improve_model is n-sized scalar logic on ids and one wall step: the reference method is reused unchanged.
+# It may append a site to round1_indices, after which the kept factorisation no longer describes the training set.
+function prepare_improve_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cfg::GpuRbfConfig, args...; kwargs...)
+    n1 = length(meta.round1_indices)
+    meta = prepare_improve_model(nothing, meta, cfg.rbf, args...; kwargs...)      # RbfModel.jl:699-732
+    length(meta.round1_indices) == n1 || _drop_kept!(meta)
+    return meta
+end
 
 # ---------------------------------------------------------------------------------------------------------------
-# init_model / update_model / improve_model   (RbfModel.jl:738-776)  -> mrbf_build
+# init_model / update_model / improve_model   (RbfModel.jl:738-776)  -> mrbf_build_prepared, else mrbf_build
 # ---------------------------------------------------------------------------------------------------------------
 init_model(meta::RbfMeta, cfg::GpuRbfConfig, args...; kwargs...) = update_model(nothing, meta, cfg, args...; kwargs...)
 improve_model(mod, meta::RbfMeta, cfg::GpuRbfConfig, args...; kwargs...) = update_model(mod, meta, cfg, args...; kwargs...)
 
+# the previous model's device buffers are recycled by the library when the shapes match (the container swaps the new
+# model in anyway, SurrogateContainer.jl:376-382): take the handle out of the old object so that its finalizer is a no-op
+_take_handle!(mod::GpuRbfModel) = (h = mod.handle; mod.handle = C_NULL; h)
+_take_handle!(::Nothing) = C_NULL
+
 function update_model(mod::Union{Nothing,GpuRbfModel}, meta::RbfMeta, cfg::GpuRbfConfig, func_indices, mop, scal, iter_data, sdb, ac; kwargs...)
-    ctx = mrbf_ctx(cfg.device)
     db = get_sub_db(sdb, func_indices)
     Δ = Float64(get_delta(iter_data))
+    ccfg = Ref(_c_cfg(cfg.rbf, Δ))
     ids = _collect_indices(meta)                                        # centre, r1, r2, r3, r4 -- RbfModel.jl:178-186
-    sites = reduce(hcat, (Vector{Float64}(get_site(db, i)) for i in ids))      # n x N   (column-major == N x n row-major AoS)
-    values = reduce(hcat, (Vector{Float64}(get_value(db, i)) for i in ids))    # k x N
-    n, N = size(sites); k = size(values, 1)
-    handle = Ref{Ptr{Cvoid}}(C_NULL); status = Int32[0]; Nv = Int32[N]
-    GC.@preserve sites values begin
-        _check(ctx, ccall((:mrbf_build, LIBMRBF), Cint,
-            (Ptr{Cvoid}, Ref{MrbfCfg}, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}, Ptr{Int32}),
-            ctx, Ref(_c_cfg(cfg.rbf, Δ)), 1, n, k, N, Nv, sites, values, C_NULL, handle, status))
+    n = length(get_site(db, ids[1])); k = length(get_value(db, ids[1]))
+    handle = Ref{Ptr{Cvoid}}(_take_handle!(mod)); status = Int32[0]
+    kept = _kept(meta)
+    rc = with_ctx(cfg.device) do ctx
+        if !isnothing(kept) && kept.prepared != C_NULL && !(cfg.rbf.shape_parameter isa String)
+            # round 4 kept its factorisation for exactly this training set: two triangular solves finish the model
+            N0 = kept.n_db
+            sites = reduce(hcat, (Vector{Float64}(get_site(db, i)) for i in 1:N0))                 # n x N0, the arrays the selection saw
+            values = reduce(hcat, (let v = get_value(db, i); isempty(v) ? fill(NaN, k) : Vector{Float64}(v) end for i in 1:N0))   # k x N0
+            r3v = zeros(Float64, k, n)                                                           # values of the new round-3 sites
+            for (j, rid) in enumerate(meta.round3_indices)
+                r3v[:, j] .= get_value(db, rid)
+            end
+            xi = Int32[kept.x_index]
+            GC.@preserve sites values r3v kept begin
+                ccall((:mrbf_build_prepared, LIBMRBF), Cint,
+                    (Ptr{Cvoid}, Ref{MrbfCfg}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32},
+                     Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}, Ptr{Int32}),
+                    ctx, ccfg, kept.prepared, k, sites, values, kept.r3, r3v, xi, kept.r1, kept.n_r1, kept.r2, kept.n_r2, kept.n_r3,
+                    handle, status)
+            end
+        else
+            sites = reduce(hcat, (Vector{Float64}(get_site(db, i)) for i in ids))      # n x N   (column-major == N x n row-major AoS)
+            values = reduce(hcat, (Vector{Float64}(get_value(db, i)) for i in ids))    # k x N
+            N = size(sites, 2); Nv = Int32[N]
+            GC.@preserve sites values begin
+                ccall((:mrbf_build, LIBMRBF), Cint,
+                    (Ptr{Cvoid}, Ref{MrbfCfg}, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}, Ptr{Int32}),
+                    ctx, ccfg, 1, n, k, N, Nv, sites, values, C_NULL, handle, status)
+            end
+        end
     end
-    return GpuRbfModel(handle[], ctx, n, k, meta.fully_linear), meta
+    # MRBF_ENUMERIC: the handle is valid, status[1] > 0 says the reduced kernel matrix was not positive definite (the reference's
+    # `\` would throw SingularException or return garbage on the same duplicated sites); every other error released the handle
+    if rc != MRBF_OK && rc != MRBF_ENUMERIC
+        with_ctx(ctx -> _check(ctx, rc), cfg.device)
+    end
+    rc == MRBF_ENUMERIC && @warn "GpuRbfModel: interpolation system not positive definite (duplicated sites?)" status[1]
+    return GpuRbfModel(handle[], cfg.device, n, k, meta.fully_linear, status[1]), meta
 end
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -193,9 +290,11 @@ function _eval(mod::GpuRbfModel, x̂::Vec; values::Bool, jac::Bool)
     x = Vector{Float64}(x̂)
     Y = values ? zeros(Float64, mod.k) : Float64[]
     J = jac ? zeros(Float64, mod.n, mod.k) : Float64[]          # C layout k x n row-major == Julia n x k column-major
-    GC.@preserve x Y J begin
-        _check(mod.ctx, ccall((:mrbf_eval, LIBMRBF), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            mod.ctx, mod.handle, 1, x, values ? pointer(Y) : C_NULL, jac ? pointer(J) : C_NULL))
+    with_ctx(mod.device) do ctx
+        GC.@preserve x Y J mod begin
+            _check(ctx, ccall((:mrbf_eval, LIBMRBF), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx, mod.handle, 1, x, values ? pointer(Y) : C_NULL, jac ? pointer(J) : C_NULL))
+        end
     end
     return Y, J
 end
@@ -205,40 +304,110 @@ get_jacobian(mod::GpuRbfModel, scal::AbstractVarScaler, x̂::Vec, rows = nothing
     (J = permutedims(_eval(mod, x̂; values = false, jac = true)[2]); isnothing(rows) ? J : J[rows, :])
 get_gradient(mod::GpuRbfModel, scal::AbstractVarScaler, x̂::Vec, ℓ) = vec(get_jacobian(mod, scal, x̂, [ℓ]))
 
-# Armijo backtracking over the surrogate (descent.jl:150-185): one launch for all step sizes instead of <= 118
-# sequential model evaluations.  `_backtrack` gains a method for containers whose objectives are one GpuRbfModel.
-function _backtrack_gpu(mod::GpuRbfModel, x::Vector{Float64}, dir::Vector{Float64}, step_size, ω, cfg::SteepestDescentConfig)
-    n = length(x); k = mod.k
-    idx = Int32[0]; σ = Float64[0]; x₊ = zeros(n); mx = zeros(k); mx₊ = zeros(k)
-    _check(mod.ctx, ccall((:mrbf_backtrack, LIBMRBF), Cint,
-        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Int32, Int32,
-         Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-        mod.ctx, mod.handle, x, dir, Float64[step_size], Float64[ω], cfg.armijo_const_rhs, cfg.armijo_const_shrink,
-        cfg.min_stepsize, cfg.max_loops, cfg.strict_backtracking, idx, σ, x₊, mx, mx₊))
-    return x₊, mx₊, σ[1] .* dir
+# ---------------------------------------------------------------------------------------------------------------
+# Descent hooks.  `compute_descent_step` calls `_backtrack(x_n, d, σ, ω, sc, desc_cfg, scal)` (descent.jl:313) and
+# `get_criticality` calls `_steepest_descent_direction(x_n, ∇m, lb, ub, A_eq, b_eq, A_ineq, b_ineq, normalize)` (:239).
+# The methods below are more specific than the reference's (typed `sc` / typed arrays), so Julia dispatches to them; they take
+# the device path when it applies and `invoke` the reference method otherwise -- no behaviour is lost.
+# ---------------------------------------------------------------------------------------------------------------
+
+# all objective outputs of the container come from ONE GpuRbfModel, in model-output order?
+function _gpu_objective_model(sc::SurrogateContainer)
+    model = nothing; cols = Int[]
+    for ind in get_objective_indices(sc)
+        s = get_surrogates(sc, ind)
+        s isa RefSurrogate || return nothing
+        m = s.model_ref[]
+        (m isa GpuRbfModel && (isnothing(model) || m === model)) || return nothing
+        model = m; append!(cols, s.output_indices)
+    end
+    (isnothing(model) || cols != collect(1:model.k)) && return nothing
+    return model
 end
 
-# Optional fast path for update_model: `prepare_update_model` may call `mrbf_select_points_keep` (same arguments as
-# `mrbf_select_points` plus a `Ref{Ptr{Cvoid}}` for the kept round-4 factorisation, stored in the GpuRbfMeta) and `update_model`
-# then calls `mrbf_build_prepared(ctx, cfg, prepared, k, sites, values, r3_sites, r3_values, x_index, r1, n_r1, r2, n_r2, n_r3,
-# handle, status)` with the database arrays the selection saw and the freshly evaluated round-3 values: the model is finished with
-# two triangular solves instead of a from-scratch factorisation (the reference notes this saving itself, RbfModel.jl:657-660).
-# `prepare_improve_model` appends a site and therefore drops the kept factorisation (falls back to `mrbf_build`).
+# Armijo backtracking over the surrogate (descent.jl:150-185): one launch for all step sizes instead of <= 118 sequential
+# model evaluations; returns the step the sequential loop would have stopped at.
+function _backtrack(x::AbstractVector{F}, dir, step_size, ω, sc::SurrogateContainer, cfg::SteepestDescentConfig, scal::AbstractVarScaler) where F<:AbstractFloat
+    mod = _gpu_objective_model(sc)
+    if isnothing(mod) || F != Float64
+        return invoke(_backtrack, Tuple{AbstractVector{F},Any,Any,Any,Any,Any,Any}, x, dir, step_size, ω, sc, cfg, scal)
+    end
+    n = length(x); k = mod.k
+    xv = Vector{Float64}(x); dv = Vector{Float64}(dir)
+    idx = Int32[0]; σ = Float64[0]; x₊ = zeros(n); mx = zeros(k); mx₊ = zeros(k)
+    s0 = Float64[step_size]; om = Float64[ω]
+    min_step = cfg.min_stepsize >= 0 ? cfg.min_stepsize : eps(Float64)
+    with_ctx(mod.device) do ctx
+        GC.@preserve xv dv s0 om idx σ x₊ mx mx₊ mod begin
+            _check(ctx, ccall((:mrbf_backtrack, LIBMRBF), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Int32, Int32,
+                 Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx, mod.handle, xv, dv, s0, om, cfg.armijo_const_rhs, cfg.armijo_const_shrink,
+                min_step, cfg.max_loops, cfg.strict_backtracking, idx, σ, x₊, mx, mx₊))
+        end
+    end
+    return x₊, mx₊, σ[1] .* dv
+end
 
-# Constrained steepest-descent direction (descent.jl:91-135): the LP that the reference hands to JuMP + OSQP, solved exactly on
-# the device.  Drop-in for `_steepest_descent_direction(x, ∇F, lb, ub, [], [], [], [], normalize)` when the MOP has no linear
-# constraints (descent.jl:239 passes them through; with constraints the reference method stays in charge).
-function _steepest_descent_direction_gpu(ctx::Ptr{Cvoid}, x::Vector{Float64}, ∇F::Matrix{Float64}, lb::Vector{Float64}, ub::Vector{Float64},
-                                         normalize::Bool = true)
+# Constrained steepest-descent direction (descent.jl:91-135): the LP the reference hands to JuMP + OSQP (eps_rel = 1e-5), solved
+# exactly on the device when the MOP has no linear / linearised constraints and at most 8 objectives.
+const GPU_DESCENT_LP = Ref(true)        # set to false to keep OSQP in charge
+const GPU_DESCENT_DEVICE = Ref(0)
+function _steepest_descent_direction(x::Vector{Float64}, ∇F::Matrix{Float64}, lb::Vec, ub::Vec,
+        A_eq = [], b_eq = [], A_ineq = [], b_ineq = [], normalize = true)
     k, n = size(∇F)
+    if !GPU_DESCENT_LP[] || !isempty(A_eq) || !isempty(A_ineq) || k > 8
+        return invoke(_steepest_descent_direction, Tuple{AbstractVector{Float64},Mat,Vec,Vec,Any,Any,Any,Any,Any},
+                      x, ∇F, lb, ub, A_eq, b_eq, A_ineq, b_ineq, normalize)
+    end
     jac = permutedims(∇F)                       # k x n row-major == n x k column-major
+    lbv = Vector{Float64}(lb); ubv = Vector{Float64}(ub)
     d = zeros(n); ω = Float64[0]; iters = Int32[0]; status = Int32[0]
-    _check(ctx, ccall((:mrbf_descent_direction, LIBMRBF), Cint,
-        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
-         Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
-        ctx, 1, n, k, jac, x, lb, ub, normalize, d, ω, iters, status))
+    with_ctx(GPU_DESCENT_DEVICE[]) do ctx
+        GC.@preserve jac x lbv ubv d ω iters status begin
+            _check(ctx, ccall((:mrbf_descent_direction, LIBMRBF), Cint,
+                (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                ctx, 1, n, k, jac, x, lbv, ubv, normalize, d, ω, iters, status))
+        end
+    end
     status[1] == 0 || return zeros(n), -Inf     # descent.jl:129-133
     return d, ω[1]
+end
+
+# ---------------------------------------------------------------------------------------------------------------
+# Multi-GPU: the final gather of per-instance results (SURVEY §8(e)).  One Julia process / thread per GPU runs its shard of the
+# multistart instances with no communication; at the end `gather_results` exchanges the result rows with one ncclAllGather.
+# The 128-byte NCCL id travels over whatever channel the host already has (Distributed.jl `remotecall_fetch`, MPI.bcast, a file).
+# ---------------------------------------------------------------------------------------------------------------
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:mrbf_comm_unique_id, LIBMRBF), Cint, (Ptr{UInt8},), id)
+    rc == MRBF_OK || error("mrbf_comm_unique_id failed ($rc): is libnccl.so.2 loadable (MRBF_NCCL_LIB)?")
+    return id
+end
+
+mutable struct MrbfComm
+    handle::Ptr{Cvoid}; rank::Int; world::Int
+end
+function MrbfComm(device::Int, id::Vector{UInt8}, rank::Int, world::Int)       # rank is 0-based like NCCL's
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mrbf_comm_init, LIBMRBF), Cint, (Cint, Ptr{UInt8}, Int32, Int32, Ref{Ptr{Cvoid}}), device, id, rank, world, ref)
+    rc == MRBF_OK || error("mrbf_comm_init failed ($rc)")
+    c = MrbfComm(ref[], rank, world)
+    finalizer(cc -> (cc.handle == C_NULL || ccall((:mrbf_comm_destroy, LIBMRBF), Cvoid, (Ptr{Cvoid},), cc.handle); cc.handle = C_NULL), c)
+    return c
+end
+
+"`rows`: width x count matrix of this rank (one column per instance) -> vector of per-rank matrices."
+function gather_results(comm::MrbfComm, rows::Matrix{Float64}, max_count::Int)
+    width, count = size(rows)
+    all_rows = zeros(Float64, width, max_count, comm.world); counts = zeros(Int32, comm.world)
+    rc = GC.@preserve rows all_rows counts ccall((:mrbf_gather, LIBMRBF), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Int32}),
+        comm.handle, rows, count, width, max_count, all_rows, counts)
+    rc == MRBF_OK || error("mrbf_gather: " * unsafe_string(ccall((:mrbf_comm_last_error, LIBMRBF), Cstring, (Ptr{Cvoid},), comm.handle)))
+    return [all_rows[:, 1:counts[r], r] for r in 1:comm.world]
 end
 
 # user-facing: add_objective!(mop, f; model_cfg = GpuRbfConfig(rbf = RbfConfig(kernel = :multiquadric)), n_out = 2)

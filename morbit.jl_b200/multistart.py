@@ -217,3 +217,15 @@ def gather_results(local: np.ndarray, total: int, rank: int, world: int) -> Opti
     dist.all_gather(outs, t)
     rows = [o.cpu().numpy()[: counts[r]] for r, o in enumerate(outs)]
     return np.concatenate(rows, axis=0).reshape((total,) + tuple(local.shape[1:]))
+
+
+def gather_results_c_abi(comm, local: np.ndarray, total: int) -> np.ndarray:
+    """The same final gather through the C ABI (mrbf_gather: one ncclAllGather on the library's own communicator) -- what a
+    Julia host calls.  `comm`: engine.Comm; `local`: this rank's rows (shard_range(total, rank, world))."""
+    world, rank = comm.world, comm.rank
+    counts = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+    assert local.shape[0] == counts[rank]
+    parts = comm.gather(local.reshape(local.shape[0], -1), max(counts))
+    for r in range(world):
+        assert parts[r].shape[0] == counts[r], (r, parts[r].shape, counts[r])
+    return np.concatenate(parts, axis=0).reshape((total,) + tuple(local.shape[1:]))

@@ -4,8 +4,16 @@ from __future__ import annotations
 
 import numpy as np
 
-_PRIMES = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 101, 103, 107,
-           109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193, 197, 199, 211, 223, 227, 229]
+def _first_primes(count: int):
+    out, c = [], 2
+    while len(out) < count:
+        if all(c % q for q in out if q * q <= c):
+            out.append(c)
+        c += 1
+    return out
+
+
+_PRIMES = _first_primes(512)
 
 
 def halton(num: int, dim: int, start: int = 1) -> np.ndarray:

@@ -24,6 +24,100 @@ def test_library_exports_every_header_symbol():
     assert lib.mrbf_abi_version() == 2
 
 
+def _header_prototypes():
+    """{name: (ret, [kinds])} parsed from include/morbit_rbf.h; kinds: ptr / i32 / i64 / f64."""
+    header = open(os.path.join(ROOT, "include", "morbit_rbf.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|void|int64_t|const char\s*\*)\s*(mrbf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
+        kinds = []
+        for a in [a.strip() for a in args.split(",")]:
+            if a in ("", "void"):
+                continue
+            if "*" in a:
+                kinds.append("ptr")
+            elif re.match(r"(const\s+)?double\b", a):
+                kinds.append("f64")
+            elif re.match(r"(const\s+)?int64_t\b", a):
+                kinds.append("i64")
+            elif re.match(r"(const\s+)?(int32_t|int)\b", a):
+                kinds.append("i32")
+            else:
+                raise AssertionError(f"unparsed argument {a!r} of {name}")
+        protos[name] = ({"int": "i32", "void": "void", "int64_t": "i64"}.get(ret, "ptr"), kinds)
+    return protos
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """The ctypes table the tests call through (morbit.jl_b200/_lib.py) against the prototypes in include/morbit_rbf.h:
+    same entry points, same number of arguments, pointer / int32 / int64 / double in the same places."""
+    import ctypes as C
+    import morbit_jl_b200 as mb
+    protos = _header_prototypes()
+    assert set(protos) == set(mb._lib.SIGNATURES), set(protos) ^ set(mb._lib.SIGNATURES)
+
+    def kind(t):
+        if t in (C.c_int32, C.c_int):
+            return "i32"
+        if t is C.c_int64:
+            return "i64"
+        if t is C.c_double:
+            return "f64"
+        return "ptr"
+    for name, (res, args) in mb._lib.SIGNATURES.items():
+        ret, kinds = protos[name]
+        assert [kind(a) for a in args] == kinds, (name, [kind(a) for a in args], kinds)
+        assert ("void" if res is None else kind(res)) == ret, (name, res, ret)
+
+
+def test_julia_shim_ccall_signatures_match_header():
+    """Every `ccall((:mrbf_..., LIBMRBF), Ret, (T...), ...)` in morbit.jl_b200/julia/GpuRbf.jl (the binding a Morbit maintainer adds;
+    Julia cannot run in this image) against the header's prototypes: existing symbol, argument count, pointer / Int32 / Int64 /
+    Float64 in the same places, and as many call arguments as declared types."""
+    src = open(os.path.join(ROOT, "morbit.jl_b200", "julia", "GpuRbf.jl")).read()
+    protos = _header_prototypes()
+    calls = list(re.finditer(r"ccall\(\(:(mrbf_\w+), LIBMRBF\),\s*(\w+),\s*\(([^)]*)\)", src, flags=re.S))
+    assert len(calls) >= 14
+    jl_kind = lambda t: ("ptr" if t.startswith(("Ptr{", "Ref{")) or t == "Cstring" else
+                         {"Int32": "i32", "Cint": "i32", "Int64": "i64", "Float64": "f64"}[t])
+    seen = set()
+    for m in calls:
+        name, ret, tup = m.group(1), m.group(2), m.group(3)
+        assert name in protos, f"{name} is not declared in morbit_rbf.h"
+        types = [t.strip() for t in tup.replace("\n", " ").split(",") if t.strip()]
+        assert [jl_kind(t) for t in types] == protos[name][1], (name, types, protos[name][1])
+        assert {"Cint": "i32", "Cvoid": "void", "Cstring": "ptr", "Int64": "i64"}[ret] == protos[name][0], (name, ret)
+        # number of values passed == number of declared types (count top-level commas up to the matching parenthesis)
+        i, depth, nargs, cur = m.end(), 1, 0, ""
+        while depth > 0:
+            ch = src[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    break
+            if ch == "," and depth == 1:
+                nargs += 1 if cur.strip() else 0
+                cur = ""
+            else:
+                cur += ch
+            i += 1
+        nargs += 1 if cur.strip() else 0
+        assert nargs == len(types), (name, nargs, len(types))
+        seen.add(name)
+    # the shim binds the fused path the benchmark measures, the descent hooks and the gather
+    for need in ("mrbf_select_points_keep", "mrbf_build_prepared", "mrbf_build", "mrbf_round4", "mrbf_eval", "mrbf_backtrack",
+                 "mrbf_descent_direction", "mrbf_set_isapprox_rtol", "mrbf_gather", "mrbf_comm_init", "mrbf_free_prepared"):
+        assert need in seen, need
+    # struct MrbfCfg mirrors struct mrbf_cfg field by field
+    header = open(os.path.join(ROOT, "include", "morbit_rbf.h")).read()
+    c_fields = re.findall(r"^\s*(int32_t|double)\s+(\w+);", header[header.index("typedef struct mrbf_cfg {"):header.index("} mrbf_cfg;")], flags=re.M)
+    jl_fields = re.findall(r"^\s*(\w+)::(Int32|Float64)\s*$", src[src.index("struct MrbfCfg"):src.index("const KERNEL_IDS")], flags=re.M)
+    assert [(n, {"int32_t": "Int32", "double": "Float64"}[t]) for t, n in c_fields] == [(n, t) for n, t in jl_fields]
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     import morbit_jl_b200 as mb

@@ -271,10 +271,7 @@ def test_build_error_contract(engine):
     for b in range(B):
         r3v[b, :res.n_r3[b]] = synthetic.zdt3(res.r3_sites[b, :res.n_r3[b]])
     model, status = engine.build_prepared(cfg, prepared, host["sites"], host["values"], host["x_index"], res, r3v, raise_on_failure=False)
-    assert model.handle and status[0] == 0
-    dup_used = (5 in list(res.r4[1, :res.n_r4[1]]) + list(res.r1[1, :res.n_r1[1]])) and (6 in list(res.r4[1, :res.n_r4[1]]) + list(res.r1[1, :res.n_r1[1]]))
-    if dup_used:
-        assert status[1] != 0
+    assert model.handle and status[0] == 0      # (round 4 rejects an exact duplicate itself: tau^2 = 0, so status[1] may well be 0)
     Y, _ = engine.eval(model, host["x"][:, None, :], True, False)
     assert np.abs(Y[0, 0] - synthetic.zdt3(host["x"][0])).max() <= 1e-9
     # an error that is not numerical: kernel mismatch between the kept factorisation and the build -> handle released, NULL back

@@ -299,3 +299,17 @@ def test_reentrant_contexts_from_concurrent_threads():
         for a, b in zip(serial[s_], threaded[s_]):
             for x_, y_ in zip(a, b):
                 assert np.array_equal(x_, y_)
+
+
+def test_c_abi_gather_single_rank():
+    """mrbf_comm_* / mrbf_gather (the C export of the final NCCL gather) with a one-rank communicator; the
+    multi-rank exchange is exercised by bench.py under torchrun (N = 2, 4, 8) where its result is checked against torch.distributed."""
+    import morbit_jl_b200 as mb
+    from morbit_jl_b200.multistart import gather_results_c_abi
+    comm = mb.Comm(0, mb.Comm.unique_id(), 0, 1)
+    rows = np.random.default_rng(0).random((37, 5))
+    out = gather_results_c_abi(comm, rows, 37)
+    np.testing.assert_array_equal(out, rows)
+    out2 = comm.gather(rows[:0], 4)                    # a rank may contribute nothing
+    assert out2[0].shape == (0, 5)
+    comm.close()
