@@ -129,7 +129,8 @@ class Comm:
     def gather(self, rows: np.ndarray, max_count: int):
         """rows: (count, width) float64 of this rank -> list of per-rank arrays (counts[r], width)."""
         rows = _np(rows, np.float64)
-        rows = rows.reshape(rows.shape[0], -1)
+        if rows.ndim != 2:
+            rows = rows.reshape(rows.shape[0], int(np.prod(rows.shape[1:], dtype=np.int64)))   # (0, w, ...) keeps its width
         count, width = rows.shape
         out = np.zeros((self.world, int(max_count), width))
         counts = np.zeros(self.world, np.int32)
