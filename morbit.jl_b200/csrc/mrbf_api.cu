@@ -418,7 +418,14 @@ static int select_points_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int
     S.found = (int*)ctx->ws[5].p; S.n_found = S.found + (size_t)B * S.found_stride;
     const bool dbg123 = getenv("MRBF_DEBUG_CLOCK") != nullptr;
     if (dbg123) { ENSURE(ctx->ws[14], 64 * sizeof(long long)); CK(cudaMemsetAsync(ctx->ws[14].p, 0, 64 * sizeof(long long), ctx->stream)); S.dbg_clock = (long long*)ctx->ws[14].p; }
-    { Timed t_(ctx, 0); CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem, S.st_in_smem ? st_doubles : 0, db_stride), ctx->stream)); }
+    // n <= 32 and <= 128 sites per database (the C3 shape): filter state in registers, scores on the FP64 tensor path
+    static const bool mma_off = getenv("MRBF_SELECT_MMA") && atoi(getenv("MRBF_SELECT_MMA")) == 0;
+    const bool use_mma = !mma_off && !dbg123 && select_mma_eligible(n, db_stride);
+    {
+        Timed t_(ctx, 0);
+        if (use_mma) CK(launch_select_rounds123_mma(S, ctx->stream));
+        else CK(launch_select_rounds123(S, select_smem_bytes(n, S.wz_in_smem, S.st_in_smem ? st_doubles : 0, db_stride), ctx->stream));
+    }
     ctx->launches += 1;
     if (dbg123) {
         long long h[64];

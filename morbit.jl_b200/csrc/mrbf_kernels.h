@@ -153,6 +153,8 @@ size_t build_vec_doubles(int n, int k, int ld, int p);
 size_t build_ws_doubles(int n, int k, int ld, int p);
 
 cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStream_t s);
+bool select_mma_eligible(int n, int db_stride);                       // register/DMMA filter kernel (mrbf_select_mma.cu)
+cudaError_t launch_select_rounds123_mma(const SelectParams& P, cudaStream_t s);
 cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid);
 cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s);
 size_t round4_block_vec_doubles(int T, int n, int NM, int p);

@@ -28,29 +28,6 @@ __device__ __forceinline__ bool in_box(const double* s, const double* lb, const 
     return ok;
 }
 
-// intersect_box(x, d, lb, ub; return_vals = :absmax), src/utilities.jl:126-221.
-__device__ double intersect_box_absmax(int n, const double* x, const double* d, const double* lb, const double* ub) {
-    bool any = false;
-    for (int i = 0; i < n; ++i) any = any || (d[i] != 0.0);
-    if (!any) return INFINITY;
-    double s_pos = 0.0, s_neg = 0.0;
-    bool have_pos = false, have_neg = false;
-    for (int pass = 0; pass < 2; ++pass)
-        for (int i = 0; i < n; ++i) {
-            if (d[i] == 0.0) continue;
-            double tmp = (pass == 0 ? lb[i] : ub[i]) - x[i];
-            double sig;
-            if (tmp != 0.0) sig = tmp / d[i];
-            else if (pass == 0) sig = d[i] > 0.0 ? INFINITY : 0.0;
-            else sig = d[i] < 0.0 ? INFINITY : 0.0;
-            if (sig >= 0.0) { if (!have_pos || sig < s_pos) s_pos = sig; have_pos = true; }
-            else { if (!have_neg || sig > s_neg) s_neg = sig; have_neg = true; }
-        }
-    if (!have_pos) s_pos = 0.0;
-    if (!have_neg) s_neg = 0.0;
-    return fabs(s_pos) >= fabs(s_neg) ? s_pos : s_neg;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Rounds 1-3
 // ------------------------------------------------------------------------------------------------
