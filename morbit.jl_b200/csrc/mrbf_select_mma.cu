@@ -39,12 +39,15 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
                  : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
+constexpr int WTS = 132;         // doubles per k-step of the packed B operand (128 + 4: the column owners' stores spread over the banks)
+
 struct Smem {
     double x[32], lb1[32], ub1[32], lb2[32], ub2[32];
-    double Wt[1024];             // W D^-2 packed [ks][row][4]; row-major scratch copy of W at run boundaries
+    double Wt[8 * WTS];          // W D^-2 packed [ks][row][4]; row-major scratch copy of W at run boundaries
     double cm[NWARP * 32];       // per-warp column maxima of |W|
-    double xw[NWARP * 32];       // per-warp winner: its column of y
-    double wv[NWARP];            // per-warp winner: score
+    double xw[NWARP * 32];       // per-warp winner: the reflector vector v of its column of y
+    double tauw[NWARP];          //                  tau of that reflector
+    double wv[NWARP];            //                  score
     int wi[NWARP];               //                  position (-1: none)
     int cl[NCMAX];               // compacted candidate ids of the current run
     int ctl[8];
@@ -62,60 +65,173 @@ __device__ __forceinline__ double quad_max(double v) {
     v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
     return fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
 }
+__device__ __forceinline__ double quad_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
 
-// Warp arg-max of non-negative scores with first-maximiser tie-breaking, then the block stage: every warp publishes its winner and
-// the winner's column of y; after ONE barrier every thread scans the eight winners.  Returns the block winner (id = -1: none).
-__device__ __forceinline__ ArgMax publish_and_pick(Smem& sm, const Filter& f, double s0, double s1, bool alive0, bool alive1, int pos0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ArgMax m; m.v = 0.0; m.id = -1;
-    if (alive0) { m.v = s0; m.id = pos0; }
-    if (alive1 && (m.id < 0 || s1 > m.v)) { m.v = s1; m.id = pos0 + 8; }
-    const double v = (m.id >= 0) ? m.v : 0.0;
+// Warp arg-max of non-negative scores (first maximiser wins ties); result in every lane.
+__device__ __forceinline__ void warp_argmax_pos(double v, int id, double& bv, int& bid) {
+    if (id < 0) v = 0.0;
     const unsigned vh = (unsigned)__double2hiint(v), vl = (unsigned)__double2loint(v);
     const unsigned mh = __reduce_max_sync(0xffffffffu, vh);
     const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
-    const unsigned mid = __reduce_min_sync(0xffffffffu, (vh == mh && vl == ml && m.id >= 0) ? (unsigned)m.id : 0x7fffffffu);
-    if (mid != 0x7fffffffu) {
-        const int wp = (int)mid;
-        if ((lane >> 2) == (wp & 7)) {           // the quad that owns the winner writes its column of y
-            const bool c1 = ((wp >> 3) & 1) != 0;
-            double* dst = sm.xw + warp * 32 + (lane & 3);
+    const unsigned mid = __reduce_min_sync(0xffffffffu, (vh == mh && vl == ml && id >= 0) ? (unsigned)id : 0x7fffffffu);
+    bv = __hiloint2double((int)mh, (int)ml);
+    bid = (mid == 0x7fffffffu) ? -1 : (int)mid;
+}
+
+// Every warp finds its best candidate and publishes, next to the score, the Householder reflector of that candidate's column of y
+// for the next pivot index jn (LAPACK dlarfg: beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = [1; x / (alpha -
+// beta)]; rows < jn are dead) -- eight reflectors in parallel before the barrier instead of one derived by every thread behind it.
+// After ONE barrier every warp picks the block winner from the eight entries.  KSMIN: k-steps below it are dead.
+template <int KSMIN>
+__device__ __forceinline__ ArgMax publish_and_pick(Smem& sm, const Filter& f, double s0, double s1, bool alive0, bool alive1, int pos0, int jn) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, pq = lane >> 2;
+    double mv = 0.0; int mi = -1;
+    if (alive0) { mv = s0; mi = pos0; }
+    if (alive1 && (mi < 0 || s1 > mv)) { mv = s1; mi = pos0 + 8; }
+    double wbv; int wp;
+    warp_argmax_pos(mv, mi, wbv, wp);
+    if (wp >= 0) {                               // warp-uniform
+        const bool c1 = ((wp >> 3) & 1) != 0;
+        double ys[8];
+        double e = 0.0, al = 0.0;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) dst[4 * ks] = c1 ? f.Y[ks][1] : f.Y[ks][0];
+        for (int ks = KSMIN; ks < 8; ++ks) {
+            const int k = 4 * ks + q;
+            ys[ks] = c1 ? f.Y[ks][1] : f.Y[ks][0];
+            if (k > jn) e = fma(ys[ks], ys[ks], e);
+            if (k == jn) al = ys[ks];
+        }
+        e = quad_sum(e); al = quad_sum(al);      // al: exact, one lane holds the pivot entry
+        double tau = 0.0, sc = 0.0;
+        if (e != 0.0) {
+            const double nn = fma(al, al, e);
+            const double beta = -copysign(nn * fast_rsqrt(nn), al);
+            tau = (beta - al) * fast_rcp(beta);
+            sc = fast_rcp(al - beta);
+        }
+        if (pq == (wp & 7)) {                    // the quad that owns the winner
+            double* dst = sm.xw + warp * 32 + q;
+#pragma unroll
+            for (int ks = KSMIN; ks < 8; ++ks) {
+                const int k = 4 * ks + q;
+                dst[4 * ks] = (k < jn) ? 0.0 : ((k == jn) ? 1.0 : ys[ks] * sc);
+            }
+            if (q == 0) sm.tauw[warp] = tau;
         }
     }
-    if (lane == 0) { sm.wv[warp] = __hiloint2double((int)mh, (int)ml); sm.wi[warp] = (mid == 0x7fffffffu) ? -1 : (int)mid; }
+    if (lane == 0) { sm.wv[warp] = wbv; sm.wi[warp] = wp; }
     __syncthreads();
-    ArgMax r; r.v = 0.0; r.id = -1;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) { ArgMax c_; c_.v = sm.wv[w]; c_.id = sm.wi[w]; r = better(r, c_); }
+    ArgMax r;
+    warp_argmax_pos(lane < NWARP ? sm.wv[lane] : 0.0, lane < NWARP ? sm.wi[lane] : -1, r.v, r.id);
     return r;
 }
 
-// Column maxima of |W| over the live columns -> sm.cm (per warp); the caller puts a barrier behind it.
-__device__ __forceinline__ void colmax_partials(Smem& sm, const Filter& f, int n, int r, int g) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double m[4];
+// One accepted point: position `bpos` becomes pivot j = f.jY (k-step KSJ = j / 4).  Reflector on y and W (registers), column maxima,
+// W D^-2 to shared memory, scores of the remaining candidates on the tensor path, next winner.  `last`: only W is updated.
+template <int KSJ>
+__device__ __forceinline__ ArgMax filter_step(Smem& sm, Filter& f, int n, int bpos, bool last, bool& alive0, bool& alive1, int pos0) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = tid >> 3, g = tid & 7;         // W role: row r, columns 4g..4g+3
+    const int q = lane & 3, pq = lane >> 2;      // score role: k = 4 ks + q, candidates 16 warp + 8 ct + pq
+    const int j = f.jY, bw = bpos >> 4;
+    const double* vcol = sm.xw + bw * 32;
+    const double tau = sm.tauw[bw];
+    if (warp == bw && pq == (bpos & 7)) { if ((bpos >> 3) & 1) alive1 = false; else alive0 = false; }
+    // ---- y <- H y (rows k < j are dead, row j dies now)
+    if (!last && tau != 0.0) {
+        double v[8];
+        double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        m[i] = fabs(f.w[i]);
-        m[i] = fmax(m[i], __shfl_xor_sync(0xffffffffu, m[i], 8));
-        m[i] = fmax(m[i], __shfl_xor_sync(0xffffffffu, m[i], 16));
-    }
-    if (lane < 8) {
-        double2* dst = reinterpret_cast<double2*>(sm.cm + warp * 32 + 4 * g);
-        dst[0] = make_double2(m[0], m[1]); dst[1] = make_double2(m[2], m[3]);
-    }
-    (void)n; (void)r;
-}
-__device__ __forceinline__ void colmax_collect(const Smem& sm, int g, double (&D)[4]) {
-    D[0] = D[1] = D[2] = D[3] = 0.0;
+        for (int ks = KSJ; ks < 8; ++ks) { v[ks] = vcol[4 * ks + q]; g0 = fma(v[ks], f.Y[ks][0], g0); g1 = fma(v[ks], f.Y[ks][1], g1); }
+        g0 = quad_sum(g0) * tau; g1 = quad_sum(g1) * tau;
 #pragma unroll
-    for (int w = 0; w < NWARP; ++w) {
-        const double2* src = reinterpret_cast<const double2*>(sm.cm + w * 32 + 4 * g);
-        const double2 a = src[0], b = src[1];
-        D[0] = fmax(D[0], a.x); D[1] = fmax(D[1], a.y); D[2] = fmax(D[2], b.x); D[3] = fmax(D[3], b.y);
+        for (int ks = KSJ; ks < 8; ++ks) { f.Y[ks][0] = fma(-g0, v[ks], f.Y[ks][0]); f.Y[ks][1] = fma(-g1, v[ks], f.Y[ks][1]); }
     }
+    // ---- W <- W H (row r, columns 4g..4g+3; column groups below KSJ are dead)
+    if (tau != 0.0) {
+        double vc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (g >= KSJ) {
+            const double2* s2 = reinterpret_cast<const double2*>(vcol + 4 * g);
+            const double2 a_ = s2[0], b_ = s2[1];
+            vc[0] = a_.x; vc[1] = a_.y; vc[2] = b_.x; vc[3] = b_.y;
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a = fma(f.w[i], vc[i], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a *= tau;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f.w[i] = fma(-a, vc[i], f.w[i]);
+    }
+    f.jY = j + 1;
+    ArgMax none; none.v = 0.0; none.id = -1;
+    if (last) return none;
+    const int jn = j + 1, ks0 = jn >> 2;         // ks0 is KSJ or KSJ + 1
+    // ---- column maxima of |W|: over the four rows of this warp by shuffles, over the warps through shared memory
+    if (g >= KSJ) {
+        const unsigned gm = 0x01010101u << g;
+        double m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m[i] = fabs(f.w[i]);
+            m[i] = fmax(m[i], __shfl_xor_sync(gm, m[i], 8));
+            m[i] = fmax(m[i], __shfl_xor_sync(gm, m[i], 16));
+        }
+        if (lane < 8) {
+            double2* dst = reinterpret_cast<double2*>(sm.cm + warp * 32 + 4 * g);
+            dst[0] = make_double2(m[0], m[1]); dst[1] = make_double2(m[2], m[3]);
+        }
+    }
+    __syncthreads();
+    // ---- B operand: W D^-2 on the live columns, zero elsewhere.  Lane c of every warp derives 1 / D_c^2, the row owners fetch
+    // their four by shuffle.
+    {
+        double dinv = 0.0;
+        if (lane >= 4 * KSJ) {
+            double D = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) D = fmax(D, sm.cm[w * 32 + lane]);
+            if (lane >= jn && lane < n && D > 0.0) dinv = fast_rcp(D * D);
+        }
+        double o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = f.w[i] * __shfl_sync(0xffffffffu, dinv, 4 * g + i);
+        if (g >= ks0) {
+            double2* dst = reinterpret_cast<double2*>(sm.Wt + g * WTS + r * 4);
+            dst[0] = make_double2(o[0], o[1]); dst[1] = make_double2(o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    // ---- scores^T = y^T (W D^-2)^T on the FP64 tensor path; the thread ends up with rows 8 rt + 2 q + {0,1} of its two candidates
+    double acc[2][4][2];
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) { acc[ct][rt][0] = 0.0; acc[ct][rt][1] = 0.0; }
+#pragma unroll
+    for (int ks = KSJ; ks < 8; ++ks) {
+        if (ks > KSJ || ks0 == KSJ) {
+            const double* bp = sm.Wt + ks * WTS + lane;
+            double bf[4];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) bf[rt] = bp[32 * rt];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) { dmma884(acc[0][rt], f.Y[ks][0], bf[rt]); dmma884(acc[1][rt], f.Y[ks][1], bf[rt]); }
+        }
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int rt = 0; rt < 4; ++rt) {
+        s0 = fmax(s0, fmax(fabs(acc[0][rt][0]), fabs(acc[0][rt][1])));
+        s1 = fmax(s1, fmax(fabs(acc[1][rt][0]), fabs(acc[1][rt][1])));
+    }
+    s0 = quad_max(s0); s1 = quad_max(s1);
+    return publish_and_pick<KSJ>(sm, f, s0, s1, alive0, alive1, pos0, jn);
 }
 
 // One run of the filter over the candidates with (flags & want) == want and !(flags & (CF_USED | avoid)); picks are appended to
@@ -123,8 +239,8 @@ __device__ __forceinline__ void colmax_collect(const Smem& sm, int g, double (&D
 __device__ __forceinline__ int filter_run_mma(Smem& sm, Filter& f, const double* __restrict__ sites, int n, int n_db, unsigned want,
                                               unsigned avoid, double piv, int n_wanted, int* out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r = tid >> 3, g = tid & 7;         // W role: row r, columns 4g..4g+3
-    const int q = lane & 3, pq = lane >> 2;      // score role: k = 4 ks + q, candidates 16 warp + 8 ct + pq
+    const int r = tid >> 3, g = tid & 7;
+    const int q = lane & 3, pq = lane >> 2;
     // ---- compact candidate list (one warp; ascending ids, so "first maximiser" = smallest position)
     if (warp == 0) {
         int base = 0;
@@ -176,111 +292,25 @@ __device__ __forceinline__ int filter_run_mma(Smem& sm, Filter& f, const double*
             }
         }
     }
-    ArgMax best = publish_and_pick(sm, f, s0, s1, alive0, alive1, pos0);
+    ArgMax best = publish_and_pick<0>(sm, f, s0, s1, alive0, alive1, pos0, f.jY);
     int found = 0;
     for (;;) {
         if (best.id < 0) break;                                  // no candidate left
         if (found > 0 && !(best.v > piv)) break;                 // AffinelyIndependentPoints.jl:92 (the first pick is unconditional)
-        // ---- accept position best.id
-        const int bpos = best.id, bw = bpos >> 4, j = f.jY;
-        const double* xcol = sm.xw + bw * 32;                    // its coefficients on the current W (entries >= j are live)
-        if (tid == 0) { const int id = sm.cl[bpos]; sm.fl[id] |= CF_USED; out[found] = id + 1; }
-        if (warp == bw && pq == (bpos & 7)) { if ((bpos >> 3) & 1) alive1 = false; else alive0 = false; }
+        if (tid == 0) { const int id = sm.cl[best.id]; sm.fl[id] |= CF_USED; out[found] = id + 1; }
         found += 1;
         const bool last = (found == n_wanted);
-        // reflector of that column (LAPACK dlarfg: beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta,
-        // v = [1; x / (alpha - beta)]), derived by every thread for itself from broadcast reads
-        double tau = 0.0, sc = 0.0;
-        {
-            double e0 = 0.0, e1 = 0.0;
-            const double2* xc2 = reinterpret_cast<const double2*>(xcol);
-#pragma unroll
-            for (int c2 = 0; c2 < 16; ++c2) {
-                const double2 t = xc2[c2];
-                if (2 * c2 > j) e0 = fma(t.x, t.x, e0);
-                if (2 * c2 + 1 > j) e1 = fma(t.y, t.y, e1);
-            }
-            const double sig = e0 + e1, alpha = xcol[j];
-            if (sig != 0.0) {
-                const double nn = fma(alpha, alpha, sig);
-                const double beta = -copysign(nn * fast_rsqrt(nn), alpha);
-                tau = (beta - alpha) * fast_rcp(beta);
-                sc = fast_rcp(alpha - beta);
-            }
+        switch (f.jY >> 2) {
+        case 0: best = filter_step<0>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        case 1: best = filter_step<1>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        case 2: best = filter_step<2>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        case 3: best = filter_step<3>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        case 4: best = filter_step<4>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        case 5: best = filter_step<5>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        case 6: best = filter_step<6>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
+        default: best = filter_step<7>(sm, f, n, best.id, last, alive0, alive1, pos0); break;
         }
-        // ---- y <- H y (registers; rows k < j are dead, row j dies now)
-        if (!last && tau != 0.0) {
-            double v[8];
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) { const int k = 4 * ks + q; v[ks] = (k < j) ? 0.0 : ((k == j) ? 1.0 : xcol[k] * sc); }
-            double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) { g0 = fma(v[ks], f.Y[ks][0], g0); g1 = fma(v[ks], f.Y[ks][1], g1); }
-            g0 += __shfl_xor_sync(0xffffffffu, g0, 1); g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
-            g0 += __shfl_xor_sync(0xffffffffu, g0, 2); g1 += __shfl_xor_sync(0xffffffffu, g1, 2);
-            g0 *= tau; g1 *= tau;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) { f.Y[ks][0] = fma(-g0, v[ks], f.Y[ks][0]); f.Y[ks][1] = fma(-g1, v[ks], f.Y[ks][1]); }
-        }
-        // ---- W <- W H (registers; row r, columns 4g..4g+3)
-        if (tau != 0.0) {
-            double vc[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const int c = 4 * g + i; vc[i] = (c < j) ? 0.0 : ((c == j) ? 1.0 : xcol[c] * sc); }
-            double a = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a = fma(f.w[i], vc[i], a);
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            a += __shfl_xor_sync(0xffffffffu, a, 4);
-            a *= tau;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) f.w[i] = fma(-a, vc[i], f.w[i]);
-        }
-        f.jY = j + 1;
         if (last) break;
-        colmax_partials(sm, f, n, r, g);
-        __syncthreads();
-        // ---- B operand: W D^-2 on the live columns, zero elsewhere; k-step g, row r
-        const int ks0 = f.jY >> 2;
-        if (g >= ks0) {
-            double D[4];
-            colmax_collect(sm, g, D);
-            double o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = 4 * g + i;
-                o[i] = (c >= f.jY && c < n && D[i] > 0.0) ? f.w[i] * fast_rcp(D[i] * D[i]) : 0.0;
-            }
-            double2* dst = reinterpret_cast<double2*>(sm.Wt + (g * 32 + r) * 4);
-            dst[0] = make_double2(o[0], o[1]); dst[1] = make_double2(o[2], o[3]);
-        }
-        __syncthreads();
-        // ---- scores^T = y^T (W D^-2)^T on the FP64 tensor path; the thread ends up with rows 8 rt + 2 q + {0,1} of its two candidates
-        double acc[2][4][2];
-#pragma unroll
-        for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-            for (int rt = 0; rt < 4; ++rt) { acc[ct][rt][0] = 0.0; acc[ct][rt][1] = 0.0; }
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            if (ks >= ks0) {
-                const double* bp = sm.Wt + ks * 128 + lane;
-                double bf[4];
-#pragma unroll
-                for (int rt = 0; rt < 4; ++rt) bf[rt] = bp[32 * rt];
-#pragma unroll
-                for (int rt = 0; rt < 4; ++rt) { dmma884(acc[0][rt], f.Y[ks][0], bf[rt]); dmma884(acc[1][rt], f.Y[ks][1], bf[rt]); }
-            }
-        }
-        s0 = 0.0; s1 = 0.0;
-#pragma unroll
-        for (int rt = 0; rt < 4; ++rt) {
-            s0 = fmax(s0, fmax(fabs(acc[0][rt][0]), fabs(acc[0][rt][1])));
-            s1 = fmax(s1, fmax(fabs(acc[1][rt][0]), fabs(acc[1][rt][1])));
-        }
-        s0 = quad_max(s0); s1 = quad_max(s1);
-        best = publish_and_pick(sm, f, s0, s1, alive0, alive1, pos0);
     }
     return found;
 }
@@ -345,16 +375,26 @@ __global__ void __launch_bounds__(NTHR, 2) select_rounds123_mma_kernel(SelectPar
             n_r1 = filter_run_mma(sm, f, sites, n, n_db, CF_BOX1, 0, piv, n, r1);
             // improving directions = reverse(eachcol(Z)), Z = live columns of W scaled by their inf-norm (RbfModel.jl:232)
             __syncthreads();
-            colmax_partials(sm, f, n, r, g);
-            __syncthreads();
             {
-                double D[4];
-                colmax_collect(sm, g, D);
+                double m[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int c = 4 * g + i;
-                    if (c >= f.jY && c < n && r < n) dirs[r + (size_t)(n - 1 - c) * n] = f.w[i] / D[i];
+                    m[i] = fabs(f.w[i]);
+                    m[i] = fmax(m[i], __shfl_xor_sync(0xffffffffu, m[i], 8));
+                    m[i] = fmax(m[i], __shfl_xor_sync(0xffffffffu, m[i], 16));
                 }
+                if ((tid & 31) < 8) {
+                    double2* dst = reinterpret_cast<double2*>(sm.cm + (tid >> 5) * 32 + 4 * g);
+                    dst[0] = make_double2(m[0], m[1]); dst[1] = make_double2(m[2], m[3]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = 4 * g + i;
+                double D = 0.0;
+                for (int w = 0; w < NWARP; ++w) D = fmax(D, sm.cm[w * 32 + c]);
+                if (c >= f.jY && c < n && r < n) dirs[r + (size_t)(n - 1 - c) * n] = f.w[i] / D;
             }
             n_dirs = n - f.jY;
         }
