@@ -60,10 +60,20 @@ struct Filter {
     int jY;                      // accepted points so far = first live column
 };
 
+// max of two non-negative, NaN-free doubles.  fmax() costs seven instructions (NaN handling); IEEE doubles >= 0 order like their bit
+// patterns, so this is two integer compares and two selects on the integer pipe -- the FP64 pipe is the contended one here.
+#ifndef MRBF_MAXNN_FP
+__device__ __forceinline__ double maxnn(double a, double b) {
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+    return __longlong_as_double((long long)(ua > ub ? ua : ub));
+}
+#else
+__device__ __forceinline__ double maxnn(double a, double b) { return a > b ? a : b; }
+#endif
 // max over the four lanes of a quad
 __device__ __forceinline__ double quad_max(double v) {
-    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    return fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = maxnn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return maxnn(v, __shfl_xor_sync(0xffffffffu, v, 2));
 }
 __device__ __forceinline__ double quad_sum(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -85,7 +95,7 @@ __device__ __forceinline__ void warp_argmax_pos(double v, int id, double& bv, in
 // for the next pivot index jn (LAPACK dlarfg: beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = [1; x / (alpha -
 // beta)]; rows < jn are dead) -- eight reflectors in parallel before the barrier instead of one derived by every thread behind it.
 // After ONE barrier every warp picks the block winner from the eight entries.  KSMIN: k-steps below it are dead.
-template <int KSMIN>
+template <int KSMIN, bool GEN>
 __device__ __forceinline__ ArgMax publish_and_pick(Smem& sm, const Filter& f, double s0, double s1, bool alive0, bool alive1, int pos0, int jn) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, pq = lane >> 2;
     double mv = 0.0; int mi = -1;
@@ -94,15 +104,26 @@ __device__ __forceinline__ ArgMax publish_and_pick(Smem& sm, const Filter& f, do
     double wbv; int wp;
     warp_argmax_pos(mv, mi, wbv, wp);
     if (wp >= 0) {                               // warp-uniform
-        const bool c1 = ((wp >> 3) & 1) != 0;
         double ys[8];
+        if ((wp >> 3) & 1) {                     // warp-uniform too: which of the thread's two candidates
+#pragma unroll
+            for (int ks = KSMIN; ks < 8; ++ks) ys[ks] = f.Y[ks][1];
+        } else {
+#pragma unroll
+            for (int ks = KSMIN; ks < 8; ++ks) ys[ks] = f.Y[ks][0];
+        }
+        // from a filter step jn lies in [4 KSMIN, 4 KSMIN + 4]: only the first two k-steps can hold dead rows or the pivot
+        constexpr int KSEL = GEN ? 8 : (KSMIN + 2 < 8 ? KSMIN + 2 : 8);
         double e = 0.0, al = 0.0;
 #pragma unroll
         for (int ks = KSMIN; ks < 8; ++ks) {
-            const int k = 4 * ks + q;
-            ys[ks] = c1 ? f.Y[ks][1] : f.Y[ks][0];
-            if (k > jn) e = fma(ys[ks], ys[ks], e);
-            if (k == jn) al = ys[ks];
+            if (ks < KSEL) {
+                const int k = 4 * ks + q;
+                if (k > jn) e = fma(ys[ks], ys[ks], e);
+                if (k == jn) al = ys[ks];
+            } else {
+                e = fma(ys[ks], ys[ks], e);
+            }
         }
         e = quad_sum(e); al = quad_sum(al);      // al: exact, one lane holds the pivot entry
         double tau = 0.0, sc = 0.0;
@@ -116,8 +137,12 @@ __device__ __forceinline__ ArgMax publish_and_pick(Smem& sm, const Filter& f, do
             double* dst = sm.xw + warp * 32 + q;
 #pragma unroll
             for (int ks = KSMIN; ks < 8; ++ks) {
-                const int k = 4 * ks + q;
-                dst[4 * ks] = (k < jn) ? 0.0 : ((k == jn) ? 1.0 : ys[ks] * sc);
+                if (ks < KSEL) {
+                    const int k = 4 * ks + q;
+                    dst[4 * ks] = (k < jn) ? 0.0 : ((k == jn) ? 1.0 : ys[ks] * sc);
+                } else {
+                    dst[4 * ks] = ys[ks] * sc;
+                }
             }
             if (q == 0) sm.tauw[warp] = tau;
         }
@@ -179,8 +204,8 @@ __device__ __forceinline__ ArgMax filter_step(Smem& sm, Filter& f, int n, int bp
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             m[i] = fabs(f.w[i]);
-            m[i] = fmax(m[i], __shfl_xor_sync(gm, m[i], 8));
-            m[i] = fmax(m[i], __shfl_xor_sync(gm, m[i], 16));
+            m[i] = maxnn(m[i], __shfl_xor_sync(gm, m[i], 8));
+            m[i] = maxnn(m[i], __shfl_xor_sync(gm, m[i], 16));
         }
         if (lane < 8) {
             double2* dst = reinterpret_cast<double2*>(sm.cm + warp * 32 + 4 * g);
@@ -195,7 +220,7 @@ __device__ __forceinline__ ArgMax filter_step(Smem& sm, Filter& f, int n, int bp
         if (lane >= 4 * KSJ) {
             double D = 0.0;
 #pragma unroll
-            for (int w = 0; w < NWARP; ++w) D = fmax(D, sm.cm[w * 32 + lane]);
+            for (int w = 0; w < NWARP; ++w) D = maxnn(D, sm.cm[w * 32 + lane]);
             if (lane >= jn && lane < n && D > 0.0) dinv = fast_rcp(D * D);
         }
         double o[4];
@@ -227,11 +252,11 @@ __device__ __forceinline__ ArgMax filter_step(Smem& sm, Filter& f, int n, int bp
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int rt = 0; rt < 4; ++rt) {
-        s0 = fmax(s0, fmax(fabs(acc[0][rt][0]), fabs(acc[0][rt][1])));
-        s1 = fmax(s1, fmax(fabs(acc[1][rt][0]), fabs(acc[1][rt][1])));
+        s0 = maxnn(s0, maxnn(fabs(acc[0][rt][0]), fabs(acc[0][rt][1])));
+        s1 = maxnn(s1, maxnn(fabs(acc[1][rt][0]), fabs(acc[1][rt][1])));
     }
     s0 = quad_max(s0); s1 = quad_max(s1);
-    return publish_and_pick<KSJ>(sm, f, s0, s1, alive0, alive1, pos0, jn);
+    return publish_and_pick<KSJ, false>(sm, f, s0, s1, alive0, alive1, pos0, jn);
 }
 
 // One run of the filter over the candidates with (flags & want) == want and !(flags & (CF_USED | avoid)); picks are appended to
@@ -276,7 +301,7 @@ __device__ __forceinline__ int filter_run_mma(Smem& sm, Filter& f, const double*
                 const double xk = in ? sm.x[k] : 0.0;
                 f.Y[ks][0] = (in && alive0) ? sa[k] - xk : 0.0;
                 f.Y[ks][1] = (in && alive1) ? sb[k] - xk : 0.0;
-                s0 = fmax(s0, fabs(f.Y[ks][0])); s1 = fmax(s1, fabs(f.Y[ks][1]));
+                s0 = maxnn(s0, fabs(f.Y[ks][0])); s1 = maxnn(s1, fabs(f.Y[ks][1]));
             }
             s0 = quad_max(s0); s1 = quad_max(s1);
         } else {
@@ -285,14 +310,14 @@ __device__ __forceinline__ int filter_run_mma(Smem& sm, Filter& f, const double*
             for (int i = 0; i < n; ++i) {
                 const double xi = sm.x[i];
                 const double a = alive0 ? sa[i] - xi : 0.0, b = alive1 ? sb[i] - xi : 0.0;
-                s0 = fmax(s0, fabs(a)); s1 = fmax(s1, fabs(b));
+                s0 = maxnn(s0, fabs(a)); s1 = maxnn(s1, fabs(b));
                 const double* wrow = sm.Wt + i * 32 + q;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) { const double wv_ = wrow[4 * ks]; f.Y[ks][0] = fma(wv_, a, f.Y[ks][0]); f.Y[ks][1] = fma(wv_, b, f.Y[ks][1]); }
             }
         }
     }
-    ArgMax best = publish_and_pick<0>(sm, f, s0, s1, alive0, alive1, pos0, f.jY);
+    ArgMax best = publish_and_pick<0, true>(sm, f, s0, s1, alive0, alive1, pos0, f.jY);
     int found = 0;
     for (;;) {
         if (best.id < 0) break;                                  // no candidate left
