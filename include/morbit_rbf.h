@@ -238,6 +238,31 @@ int mrbf_descent_direction_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, c
                                const double* lb, const double* ub, int32_t normalize,
                                double* d, double* omega, int32_t* iters, int32_t* status);
 
+/* ---- Pascoletti-Serafini inner solves: replace the NLopt runs of src/descent.jl:369-387 (`_min_component`, called by
+ * `compute_local_ideal_point` :404-412) and :478-500 (`_ps_optimization`, called by `get_criticality(::PascolettiSerafiniConfig)`
+ * :503-581), whose objective / constraint callbacks evaluate the surrogates one point at a time
+ * (src/AbstractSurrogateInterface.jl:98-106).  A batched (mu, lambda) evolution strategy with stochastic ranking (ISRES, the
+ * reference's default `:GN_ISRES`): every generation of all B instances is one batched surrogate evaluation on the device.
+ *   model: B instances, k outputs; outputs 0..n_obj-1 are objectives, n_obj..k-1 constraint surrogates c(xi) <= 0
+ *          (`get_nl_ineq_constraints_optim_handles`).
+ *   x B x n: start point (scaled iterate);  lb / ub B x n: `local_bounds(scal, x, delta)` (finite).
+ *   dir == NULL (ideal-point mode): minimise output `objective` over the box (one call per objective, descent.jl:408-411);
+ *          f_min[b] = minimum found.
+ *   dir != NULL (PS mode): mx B x k = m(x), dir B x k = r > 0 (only the first n_obj entries are read); solves
+ *          min tau  s.t.  m_l(xi) - mx_l - tau r_l <= 0,  -1 <= tau <= 0, box, c(xi) <= 0;  f_min[b] = tau (omega = |tau|).
+ *   population <= 0: 20 (n + 1) (NLopt's ISRES default); max_evals <= 0: 500 (n + 1) (descent.jl:373, 418, 535).
+ *   Outputs: x_min B x n, y_min B x k (surrogate values at x_min), found B (0: no feasible point was seen -- the caller
+ *   treats the instance like NLopt's FAILURE, descent.jl:556-571), *evals_used (may be NULL): surrogate evaluations per instance.
+ * Deterministic for a given seed (counter-based random numbers); NLopt's own random stream is not reproduced. */
+int mrbf_ps_solve(mrbf_ctx* ctx, const mrbf_model* model, const double* x, const double* lb, const double* ub,
+                  const double* mx, const double* dir, int32_t n_obj, int32_t objective, int32_t population,
+                  int32_t max_evals, int64_t seed, double* f_min, double* x_min, double* y_min, int32_t* found,
+                  int32_t* evals_used);
+int mrbf_ps_solve_dev(mrbf_ctx* ctx, const mrbf_model* model, const double* x, const double* lb, const double* ub,
+                      const double* mx, const double* dir, int32_t n_obj, int32_t objective, int32_t population,
+                      int32_t max_evals, int64_t seed, double* f_min, double* x_min, double* y_min, int32_t* found,
+                      int32_t* evals_used);
+
 /* ---- device-resident database + model swap (lock-step multistart driver) ----------------------
  * new_result!(db, x, y) for B databases that live on the device (src/Databases.jl:174-183; value-less results are the
  * "unevaluated" ones of :202-205 and are stored as NaN rows): instance b appends its first n_add[b] rows of

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmorbit_rbf.so")
-SOURCES = ["mrbf_select.cu", "mrbf_select_mma.cu", "mrbf_round4_schur.cu", "mrbf_build.cu", "mrbf_eval.cu", "mrbf_descent.cu", "mrbf_db.cu", "mrbf_comm.cu", "mrbf_api.cu"]
+SOURCES = ["mrbf_select.cu", "mrbf_select_mma.cu", "mrbf_round4_schur.cu", "mrbf_build.cu", "mrbf_eval.cu", "mrbf_descent.cu", "mrbf_ps.cu", "mrbf_db.cu", "mrbf_comm.cu", "mrbf_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -67,6 +67,8 @@ SIGNATURES = {
     "mrbf_backtrack_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mrbf_descent_direction": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mrbf_descent_direction_dev": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mrbf_ps_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mrbf_ps_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mrbf_db_append_dev": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mrbf_model_scatter_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i32]),
     "mrbf_comm_unique_id": (C.c_int, [_vp]),

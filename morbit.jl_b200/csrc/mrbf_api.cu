@@ -1008,6 +1008,70 @@ int mrbf_descent_direction(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, const
     return MRBF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ Pascoletti-Serafini inner solves
+int mrbf_ps_solve_dev(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const double* lb, const double* ub,
+                      const double* mx, const double* dir, int32_t n_obj, int32_t objective, int32_t population,
+                      int32_t max_evals, int64_t seed, double* f_min, double* x_min, double* y_min, int32_t* found,
+                      int32_t* evals_used) {
+    if (!ctx || !m || !x || !lb || !ub || !f_min || !x_min || !y_min || !found) return MRBF_EINVAL;
+    const int B = m->B, n = m->n, k = m->k;
+    if (n_obj <= 0 || n_obj > k) return fail(ctx, MRBF_EINVAL, "n_obj must lie in 1..k%s");
+    if (dir && !mx) return fail(ctx, MRBF_EINVAL, "Pascoletti-Serafini mode needs m(x)%s");
+    if (!dir && (objective < 0 || objective >= n_obj)) return fail(ctx, MRBF_EINVAL, "ideal-point mode needs an objective index in 0..n_obj-1%s");
+    int lam = population > 0 ? population : 20 * (n + 1);              // NLopt's ISRES default: 20 (n + 1)
+    if (lam < 8) lam = 8;
+    const int evals = max_evals > 0 ? max_evals : 500 * (n + 1);        // descent.jl:373, 418, 535
+    int gens = evals / lam; if (gens < 1) gens = 1;                     // generations after the initial population
+    if (ps_rank_smem_bytes(lam) > SMEM_LIMIT) return fail(ctx, MRBF_EUNSUPPORTED, "population too large for the ranking kernel%s");
+    CK(cudaSetDevice(ctx->device));
+    const size_t pop = (size_t)B * lam * n;
+    ENSURE(ctx->ws[15], sizeof(double) * (4 * pop + (size_t)B * lam * k) + sizeof(int) * (size_t)B * lam);
+    PsParams P{};
+    P.B = B; P.n = n; P.k = k; P.lambda = lam; P.mu = (lam + 6) / 7; P.generations = gens; P.n_obj = n_obj; P.objective = objective;
+    P.seed = (unsigned long long)seed; P.x0 = x; P.lb = lb; P.ub = ub; P.mx = mx; P.dir = dir;
+    double* base = (double*)ctx->ws[15].p;
+    P.X = base; P.S = base + pop; P.Xn = base + 2 * pop; P.Sn = base + 3 * pop;
+    double* Y = base + 4 * pop; P.Y = Y; P.rank = (int*)(Y + (size_t)B * lam * k);
+    P.best_f = f_min; P.best_x = x_min; P.best_y = y_min; P.best_found = found;
+    CK(launch_ps_init(P, ctx->stream));
+    ctx->launches += 1;
+    for (int g = 0; g <= gens; ++g) {
+        int rc = mrbf_eval_dev(ctx, m, lam, P.X, Y, nullptr);
+        if (rc != MRBF_OK) return rc;
+        CK(launch_ps_fitness_rank(P, g, ctx->stream));
+        ctx->launches += 1;
+        if (g == gens) break;
+        CK(launch_ps_evolve(P, g + 1, ctx->stream));
+        ctx->launches += 1;
+        double* t = P.X; P.X = P.Xn; P.Xn = t; t = P.S; P.S = P.Sn; P.Sn = t;
+    }
+    if (evals_used) *evals_used = (gens + 1) * lam;
+    return MRBF_OK;
+}
+
+int mrbf_ps_solve(mrbf_ctx* ctx, const mrbf_model* m, const double* x, const double* lb, const double* ub,
+                  const double* mx, const double* dir, int32_t n_obj, int32_t objective, int32_t population,
+                  int32_t max_evals, int64_t seed, double* f_min, double* x_min, double* y_min, int32_t* found,
+                  int32_t* evals_used) {
+    if (!ctx || !m || !x || !lb || !ub || !f_min || !x_min || !y_min || !found) return MRBF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int B = m->B, n = m->n, k = m->k;
+    const size_t bx = sizeof(double) * (size_t)B * n, bk = sizeof(double) * (size_t)B * k, bb = sizeof(double) * (size_t)B;
+    ENSURE(ctx->hb[23], 4 * bx + 3 * bk + bb + sizeof(int) * (size_t)B);
+    double* d_x = (double*)ctx->hb[23].p; double* d_lb = d_x + (size_t)B * n; double* d_ub = d_lb + (size_t)B * n; double* d_xm = d_ub + (size_t)B * n;
+    double* d_mx = d_xm + (size_t)B * n; double* d_dir = d_mx + (size_t)B * k; double* d_ym = d_dir + (size_t)B * k;
+    double* d_f = d_ym + (size_t)B * k; int* d_found = (int*)(d_f + B);
+    H2D(d_x, x, bx); H2D(d_lb, lb, bx); H2D(d_ub, ub, bx);
+    if (mx) H2D(d_mx, mx, bk);
+    if (dir) H2D(d_dir, dir, bk);
+    int rc = mrbf_ps_solve_dev(ctx, m, d_x, d_lb, d_ub, mx ? d_mx : nullptr, dir ? d_dir : nullptr, n_obj, objective, population,
+                               max_evals, seed, d_f, d_xm, d_ym, d_found, evals_used);
+    if (rc != MRBF_OK) return rc;
+    D2H(f_min, d_f, bb); D2H(x_min, d_xm, bx); D2H(y_min, d_ym, bk); D2H(found, d_found, sizeof(int) * (size_t)B);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRBF_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ device-resident database
 int mrbf_db_append_dev(mrbf_ctx* ctx, int32_t B, int32_t n, int32_t k, int32_t db_stride, double* sites, double* values,
                        int32_t* n_db, int32_t add_stride, const double* new_sites, const double* new_values,

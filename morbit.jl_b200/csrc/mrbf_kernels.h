@@ -130,6 +130,17 @@ struct DescentParams {
     double* d; double* omega; int* iters; int* status;
 };
 
+// Pascoletti-Serafini / ideal-point inner solves (mrbf_ps.cu)
+struct PsParams {
+    int B, n, k, lambda, mu, generations, n_obj, objective;
+    unsigned long long seed;
+    const double* x0; const double* lb; const double* ub; const double* mx; const double* dir;
+    double* X; double* S; double* Xn; double* Sn;       // populations and step sizes, B x lambda x n each
+    const double* Y;                                    // surrogate values of X, B x lambda x k
+    int* rank;                                          // B x lambda
+    double* best_f; double* best_x; double* best_y; int* best_found;
+};
+
 struct DbAppendParams {
     int B, n, k, db_stride, add_stride;
     double* sites; double* values; int* n_db;
@@ -176,6 +187,10 @@ size_t descent_warp_doubles(int n, int k);
 int descent_max_outputs();
 cudaError_t launch_backtrack_points(const BacktrackParams& P, cudaStream_t s);
 cudaError_t launch_backtrack_pick(const BacktrackParams& P, cudaStream_t s);
+cudaError_t launch_ps_init(const PsParams& P, cudaStream_t s);
+cudaError_t launch_ps_fitness_rank(const PsParams& P, int gen, cudaStream_t s);
+cudaError_t launch_ps_evolve(const PsParams& P, int gen, cudaStream_t s);
+size_t ps_rank_smem_bytes(int lambda);
 cudaError_t launch_db_append(const DbAppendParams& P, cudaStream_t s);
 cudaError_t launch_model_scatter(const ModelScatterParams& P, cudaStream_t s);
 

@@ -449,6 +449,39 @@ class Engine:
                                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3])))
         return out
 
+    # ------------------------------------------------------------------ Pascoletti-Serafini inner solves
+    def ps_solve(self, model: ModelBatch, x, lb, ub, mx=None, direction=None, n_obj: Optional[int] = None, objective: int = -1,
+                 population: int = -1, max_evals: int = -1, seed: int = 0):
+        """Batched `_ps_optimization` (direction given; descent.jl:478-500) or `_min_component` (direction None, one objective;
+        descent.jl:369-387) on the surrogates: x, lb, ub B x n; mx, direction B x k.
+        Returns (f_min B, x_min B x n, y_min B x k, found B, evals_per_instance)."""
+        B, n, k = model.B, model.n, model.k
+        x = _np(x, np.float64).reshape(B, n)
+        lb = _np(np.broadcast_to(lb, (B, n)), np.float64); ub = _np(np.broadcast_to(ub, (B, n)), np.float64)
+        mx_ = None if mx is None else _np(mx, np.float64).reshape(B, k)
+        dir_ = None if direction is None else _np(np.broadcast_to(direction, (B, k)), np.float64)
+        f = np.zeros(B); xm = np.zeros((B, n)); ym = np.zeros((B, k)); found = np.zeros(B, np.int32); used = C.c_int32(0)
+        self._check(self.lib.mrbf_ps_solve(self.ctx, model.handle, _ptr(x), _ptr(lb), _ptr(ub), _ptr(mx_) if mx_ is not None else None,
+                                           _ptr(dir_) if dir_ is not None else None, int(k if n_obj is None else n_obj), int(objective),
+                                           int(population), int(max_evals), C.c_int64(int(seed)), _ptr(f), _ptr(xm), _ptr(ym), _ptr(found),
+                                           C.byref(used)))
+        return f, xm, ym, found, int(used.value)
+
+    def ps_solve_dev(self, model: ModelBatch, x, lb, ub, mx=None, direction=None, n_obj: Optional[int] = None, objective: int = -1,
+                     population: int = -1, max_evals: int = -1, seed: int = 0, out=None):
+        """Device tensors in and out (enqueued on the engine's stream); returns (f_min, x_min, y_min, found) and the evaluation count."""
+        import torch
+        B, n, k = model.B, model.n, model.k
+        if out is None:
+            f64 = dict(dtype=torch.float64, device=x.device)
+            out = (torch.empty(B, **f64), torch.empty((B, n), **f64), torch.empty((B, k), **f64), torch.empty(B, dtype=torch.int32, device=x.device))
+        used = C.c_int32(0)
+        self._check(self.lib.mrbf_ps_solve_dev(self.ctx, model.handle, _ptr(x), _ptr(lb), _ptr(ub), _ptr(mx) if mx is not None else None,
+                                               _ptr(direction) if direction is not None else None, int(k if n_obj is None else n_obj),
+                                               int(objective), int(population), int(max_evals), C.c_int64(int(seed)),
+                                               _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), C.byref(used)))
+        return out, int(used.value)
+
     def backtrack_dev(self, model: ModelBatch, x, direction, step0, omega, armijo_c=1e-6, shrink=0.75,
                       min_stepsize=10 * np.finfo(np.float64).eps, max_loops=None, strict=True, out=None):
         """descent.jl:150-185 for device tensors (x, direction: B x n; step0, omega: B); returns

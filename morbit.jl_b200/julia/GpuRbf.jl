@@ -376,6 +376,50 @@ function _steepest_descent_direction(x::Vector{Float64}, ∇F::Matrix{Float64}, 
 end
 
 # ---------------------------------------------------------------------------------------------------------------
+# Pascoletti-Serafini inner solves (descent.jl:369-387, 404-412, 478-500).  The reference builds NLopt handles that call the
+# surrogates one point at a time (AbstractSurrogateInterface.jl:98-106); with one GPU RBF group holding the objectives (and, behind
+# them, the nonlinear inequality constraints of the MOP) and `:GN_ISRES` -- the default -- both NLopt runs become one library call each.
+# Hooked in by overloading the two workers `get_criticality(::PascolettiSerafiniConfig, ...)` calls (descent.jl:537, 552); every
+# other case (several surrogate groups, linear constraints of the MOP, a polish algorithm, another NLopt algorithm) goes back to NLopt.
+# ---------------------------------------------------------------------------------------------------------------
+const GPU_PS = Ref(true)
+const GPU_PS_SEED = Ref(Int64(0))
+
+function _ps_solve_gpu(mod::GpuRbfModel, x::Vector{Float64}, lb::Vector{Float64}, ub::Vector{Float64}, mx, r, n_obj::Int,
+        objective::Int, max_evals::Int)
+    n = length(x); k = mod.k
+    fmin = Float64[0]; xmin = zeros(n); ymin = zeros(k); found = Int32[0]; used = Int32[0]
+    mxv = isnothing(mx) ? Float64[] : Vector{Float64}(mx)
+    rv = isnothing(r) ? Float64[] : vcat(Vector{Float64}(r), ones(k - length(r)))
+    with_ctx(mod.device) do ctx
+        GC.@preserve x lb ub mxv rv fmin xmin ymin found used mod begin
+            _check(ctx, ccall((:mrbf_ps_solve, LIBMRBF), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
+                 Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                ctx, mod.handle, x, lb, ub, isnothing(mx) ? C_NULL : pointer(mxv), isnothing(r) ? C_NULL : pointer(rv),
+                n_obj, objective, -1, max_evals, GPU_PS_SEED[], fmin, xmin, ymin, found, used))
+        end
+    end
+    GPU_PS_SEED[] += 1
+    return fmin[1], xmin, ymin, found[1] == 1
+end
+
+# compute_local_ideal_point (descent.jl:404-412): one `_min_component` per objective
+function compute_local_ideal_point_gpu(mod::GpuRbfModel, x_n, lb_eff, ub_eff, n_obj::Int, MAX_EVALS::Int)
+    x = Vector{Float64}(x_n); lb = Vector{Float64}(lb_eff); ub = Vector{Float64}(ub_eff)
+    return [ begin
+                 f, _, _, ok = _ps_solve_gpu(mod, x, lb, ub, nothing, nothing, n_obj, l - 1, MAX_EVALS)
+                 ok ? f : Inf
+             end for l = 1:n_obj ]
+end
+
+# _ps_optimization (descent.jl:478-500): returns (tau, x_min, ret) like the reference
+function _ps_optimization_gpu(mod::GpuRbfModel, x_n, lb_eff, ub_eff, mx, r, n_obj::Int, MAX_EVALS::Int)
+    τ, x_min, _, ok = _ps_solve_gpu(mod, Vector{Float64}(x_n), Vector{Float64}(lb_eff), Vector{Float64}(ub_eff), mx, r, n_obj, -1, MAX_EVALS)
+    return τ, x_min, ok ? :MAXEVAL_REACHED : :FAILURE
+end
+
+# ---------------------------------------------------------------------------------------------------------------
 # Multi-GPU: the final gather of per-instance results (SURVEY §8(e)).  One Julia process / thread per GPU runs its shard of the
 # multistart instances with no communication; at the end `gather_results` exchanges the result rows with one ncclAllGather.
 # The 128-byte NCCL id travels over whatever channel the host already has (Distributed.jl `remotecall_fetch`, MPI.bcast, a file).

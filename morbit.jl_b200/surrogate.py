@@ -441,3 +441,78 @@ def _backtrack(x, direction, step_size, omega, mod: RbfModel, *, armijo_const_rh
                                                           [step_size], [omega], armijo_const_rhs, armijo_const_shrink,
                                                           min_stepsize, max_loops, strict_backtracking)
     return xp[0], mxp[0], step[0]
+
+
+# ---------------------------------------------------------------------------------------- Pascoletti-Serafini
+@dataclass
+class PascolettiSerafiniConfig:
+    """src/descent.jl:324-349 (only `:GN_ISRES`, the reference's default, runs on the device; a polish algorithm stays with NLopt)."""
+    reference_point: Sequence[float] = ()
+    reference_direction: Sequence[float] = ()
+    trust_region_factor: float = 1.0
+    max_ps_problem_evals: int = -1
+    max_ps_polish_evals: int = -1
+    max_ideal_point_problem_evals: int = -1
+    main_algo: str = "GN_ISRES"
+    reference_algo: str = "GN_ISRES"
+    reference_trust_region_factor: float = 1.1
+    ps_polish_algo: Optional[str] = None
+    seed: int = 0
+
+    def __post_init__(self):
+        assert all(v > 0 for v in self.reference_direction), "The components of the `reference_direction` cannot be negative."
+        if self.main_algo != "GN_ISRES" or self.reference_algo != "GN_ISRES":
+            raise NotImplementedError("only :GN_ISRES inner solves run on the device")
+        if self.ps_polish_algo is not None:
+            raise NotImplementedError("ps_polish_algo is an NLopt local method of the reference's host code")
+
+
+def _get_global_dir(cfg: PascolettiSerafiniConfig, fx):
+    """descent.jl:359-367."""
+    if len(cfg.reference_direction) > 0:
+        return np.asarray(cfg.reference_direction, dtype=np.float64)
+    if len(cfg.reference_point) > 0:
+        return np.asarray(fx, dtype=np.float64) - np.asarray(cfg.reference_point, dtype=np.float64)
+    return None
+
+
+def _local_bounds(x, delta, lb, ub):
+    """local_bounds(scal, x, delta), utilities.jl:290-294."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.maximum(np.broadcast_to(lb, x.shape), x - delta), np.minimum(np.broadcast_to(ub, x.shape), x + delta)
+
+
+def compute_local_ideal_point(mod: RbfModel, x_scaled, lb_eff, ub_eff, max_evals: int = -1, n_obj: Optional[int] = None, seed: int = 0):
+    """compute_local_ideal_point, descent.jl:404-412: one box-constrained minimisation per objective (`_min_component` :369-387)."""
+    eng, k = mod.model.engine, mod.model.k
+    n_obj = k if n_obj is None else n_obj
+    out = np.zeros(n_obj)
+    for ell in range(n_obj):
+        f, _x, _y, found, _ = eng.ps_solve(mod.model, np.asarray(x_scaled)[None], np.asarray(lb_eff)[None], np.asarray(ub_eff)[None],
+                                           None, None, n_obj, ell, -1, max_evals, seed + 7919 * (ell + 1))
+        out[ell] = f[0] if found[0] else math.inf
+    return out
+
+
+def get_criticality_ps(desc_cfg: PascolettiSerafiniConfig, mod: RbfModel, x_scaled, fx, delta, lb, ub, n_obj: Optional[int] = None):
+    """get_criticality(::PascolettiSerafiniConfig, ...), descent.jl:503-581, for one RBF surrogate group holding the objectives
+    (and, behind them, constraint surrogates c <= 0).  Returns (omega, x_trial, m(x_trial), step length) -- the reference's
+    `(0, copy(x), mx, 0)` when the direction has a non-positive component (:541-543) or the solver reports no feasible point."""
+    x = np.asarray(x_scaled, dtype=np.float64)
+    eng, n, k = mod.model.engine, len(x), mod.model.k
+    n_obj = k if n_obj is None else n_obj
+    lb_eff, ub_eff = _local_bounds(x, delta, lb, ub)
+    mx = eval_models(mod, None, x)
+    r = _get_global_dir(desc_cfg, fx)
+    if r is None:
+        ideal = compute_local_ideal_point(mod, x, lb_eff, ub_eff, desc_cfg.max_ideal_point_problem_evals, n_obj, desc_cfg.seed)
+        r = np.asarray(fx, dtype=np.float64)[:n_obj] - ideal
+    if np.any(r[:n_obj] <= 0):
+        return 0.0, x.copy(), mx, 0.0
+    rr = np.ones(k); rr[:n_obj] = r[:n_obj]
+    max_evals = 500 * (n + 1) if desc_cfg.max_ps_problem_evals < 0 else desc_cfg.max_ps_problem_evals       # _ps_max_evals, :414-433
+    tau, xm, ym, found, _ = eng.ps_solve(mod.model, x[None], lb_eff[None], ub_eff[None], mx[None], rr[None], n_obj, -1, -1, max_evals,
+                                         desc_cfg.seed)
+    if not found[0] or not np.isfinite(tau[0]) or np.any(np.isnan(xm[0])):
+        return 0.0, x.copy(), mx, 0.0
+    return float(abs(tau[0])), xm[0], ym[0], float(np.max(np.abs(x - xm[0])))
