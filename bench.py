@@ -250,6 +250,70 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
 
+    def timed_pipeline(pipe_, nb):
+        for _ in range(max(nb, args.warmup // 2)):          # every buffer / output set used once (allocations)
+            pipe_.step(); pipe_.drain(); stream.synchronize()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(args.steps):
+            _, outs_ = pipe_.step()
+        pipe_.drain()
+        a1.record(stream)
+        stream.synchronize()
+        barrier()
+        ms_ = a0.elapsed_time(a1) / args.steps
+        if world > 1:
+            t_ = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_, int(sum(int((o[-1].numpy() == 0).sum()) for o in outs_))
+
+    # ---- the same end-to-end step with the databases resident on the device: only iterate, radius, flags and
+    # budget travel per step -- what changes between two model updates on one database (criticality loop, algorithm.jl:523-612)
+    del pipe
+    pipe_r = HostPipeline(eng, cfg, DELTA_MAX, host, f"cuda:{local}", stream, chunks=1, buffers=2, outputs=2, resident_db=True)
+    e2e_res_ms, e2e_res_ok = timed_pipeline(pipe_r, 4)
+    e2e_resident = {"value": world * B / (e2e_res_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_res_ms, "builds_ok": e2e_res_ok,
+                    "h2d_bytes_per_step": int(pipe_r.h2d_bytes), "d2h_bytes_per_step": int(pipe_r.d2h_bytes),
+                    "path": "databases uploaded once and kept on the device (mrbf_db_append_dev grows them in a driver); per step: pinned H2D of "
+                            "iterate / radius / flags / budget -> mrbf_select_points_keep_dev + mrbf_build_prepared_dev -> D2H of indices / flags / status"}
+    del pipe_r
+
+    # ---- strong scaling (the 4096 instances of config C3 split [g B / G, (g + 1) B / G) over the ranks)
+    strong = None
+    if world > 1:
+        lo_s, hi_s = rank * B // world, (rank + 1) * B // world
+        host_s = {k_: (v_[lo_s:hi_s] if isinstance(v_, np.ndarray) and v_.ndim >= 1 and v_.shape[0] == B else v_) for k_, v_ in
+                  synthetic.multistart_batch(B, n=N_VARS, n_db=N_DB, delta=DELTA, delta_max=DELTA_MAX, func=synthetic.zdt3).items()}
+        dev_s = upload_batch(host_s, f"cuda:{local}")
+        b_s = MultistartBuilder(eng, cfg, DELTA_MAX)
+        with torch.cuda.stream(stream):
+            m_s = None
+            for _ in range(args.warmup):
+                m_s, _, _ = b_s.step(dev_s, recycle=m_s); stream.synchronize()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for _ in range(args.steps):
+                m_s, _, st_s = b_s.step(dev_s, recycle=m_s)
+            s1.record(stream)
+            stream.synchronize()
+            barrier()
+        ms_s = s0.elapsed_time(s1) / args.steps
+        t_ = torch.tensor([ms_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms_s = float(t_.item())
+        per = hi_s - lo_s
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        strong = {"metric": METRIC, "scaling": "strong", "value": B / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
+                  "instances_total": B, "instances_per_gpu": per,
+                  "limiter": f"one CTA per instance: {per} CTAs on {sms} SMs = {per / (2 * sms):.2f} waves of the rounds-1-3 kernel (2 CTAs/SM), "
+                             f"{per / (4 * sms):.2f} of the panels kernel (4/SM), {per / sms:.2f} of the elimination kernel (1/SM) -- the last, partly "
+                             "filled wave of each kernel is the loss against ideal strong scaling; there is no communication on the data path",
+                  "config": {"workload": f"C3 strong: {B} instances in total, [g B / G, (g + 1) B / G) on rank g"}}
+        m_s.free(); del dev_s, b_s
+
     # ---- per-kernel device times (one extra, untimed-for-the-metric step with event brackets) and roofline
     eng.profile_enable(True)
     with torch.cuda.stream(stream):
@@ -267,7 +331,7 @@ def run_ours(args):
     ach = kflops[dom] / (prof[dom] * 1e-3) / 1e12
     step_total = prof["rounds123"] + prof["round4"] + prof["round4_fallback"] + prof["gather"] + prof["build"] + prof["build_prepared"]
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json"))).get(dom) if B == B_PER_GPU else None
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json"))).get(dom) if B == B_PER_GPU else None
     except Exception:
         traffic = None
     roofline = {"bound": "tensor", "pipe": "fp64 (DFMA; B200 FP64 tensor peak equals the FMA-pipe peak)", "kernel": dom,
@@ -356,6 +420,108 @@ def run_ours(args):
                                                  "for the constrained steepest-descent direction"}})
 
 
+    # ---- secondary metric: Pascoletti-Serafini inner solves on the fitted surrogates (descent.jl:478-581):
+    # one mrbf_ps_solve_dev per batch = 26 generations of 620 individuals per instance, every generation one batched evaluation
+    if args.ps:
+        r_dir = torch.ones((B, K_OUT), dtype=torch.float64, device="cuda")
+        lb_e = torch.clamp(dev.x - DELTA, min=0.0).contiguous(); ub_e = torch.clamp(dev.x + DELTA, max=1.0).contiguous()
+        mx0 = torch.empty((B, 1, K_OUT), dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(stream):
+            eng.eval_dev(model, dev.x.reshape(B, 1, N_VARS).contiguous(), mx0, None)
+            pso, used = eng.ps_solve_dev(model, dev.x, lb_e, ub_e, mx0.view(B, K_OUT), r_dir, K_OUT, -1, -1, -1, 1)      # warm-up (allocations)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stream.synchronize(); l0p = eng.launch_count
+            p0.record(stream)
+            reps_ps = max(1, min(3, args.steps))
+            for i_ in range(reps_ps):
+                pso, used = eng.ps_solve_dev(model, dev.x, lb_e, ub_e, mx0.view(B, K_OUT), r_dir, K_OUT, -1, -1, -1, 2 + i_, out=pso)
+            p1.record(stream)
+            stream.synchronize()
+        ps_ms = p0.elapsed_time(p1) / reps_ps
+        tps = torch.tensor([ps_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tps, op=dist.ReduceOp.MAX)
+        ps_ms = float(tps.item())
+        fe_ps = N_DB * (3 * N_VARS + 1 + 2 * K_OUT) + 2 * (N_VARS + 1) * K_OUT
+        secondary.append({"metric": "ps_solves_per_s", "value": world * B / (ps_ms * 1e-3), "unit": "solves/s", "ms_per_step": ps_ms,
+                          "surrogate_evals_per_s": world * B * used / (ps_ms * 1e-3), "evals_per_solve": int(used),
+                          "gpu_launches_per_solve_batch": int((eng.launch_count - l0p) // reps_ps),
+                          "mean_tau": float(pso[0].mean().item()), "found": int(pso[3].sum().item()),
+                          "fp64_frac_of_peak_eval_only": world * B * used / (ps_ms * 1e-3) / world * fe_ps / 1e12 / peak,
+                          "config": {"workload": f"{B} instances per GPU (the C3 models: n={N_VARS}, k={K_OUT}, {N_DB} centres): Pascoletti-Serafini problem in the "
+                                                 f"trust region box, direction r = 1, population 20 (n + 1) = {20 * (N_VARS + 1)}, budget 500 (n + 1) evaluations "
+                                                 "(the reference's NLopt :GN_ISRES defaults, descent.jl:373, 418)"}})
+
+    # ---- secondary metric: a heterogeneous batch (half of every database inside the trust region, mixed radii and budgets) -- rounds 1,
+    # 2 and 3 all take part, instances differ in their control flow -- and a descent step on it with a step length that makes Armijo backtrack
+    if args.hetero:
+        host_h = synthetic.multistart_batch(B, n=N_VARS, n_db=N_DB, delta=DELTA, delta_max=DELTA_MAX, func=synthetic.zdt3,
+                                            first_instance=rank * B, local_fraction=0.5)
+        rng_h = np.random.default_rng(12345 + rank)
+        host_h["delta"] = DELTA * rng_h.choice([0.25, 0.5, 1.0, 2.0], size=B)
+        host_h["max_new"] = rng_h.choice([0, 2, 2**31 - 1], size=B, p=[0.05, 0.05, 0.9]).astype(np.int32)   # an exhausted budget is the rare case
+        host_h["flags_in"][:, 0] = rng_h.integers(0, 2, size=B)
+        dev_h = upload_batch(host_h, f"cuda:{local}")
+        b_h = MultistartBuilder(eng, cfg, DELTA_MAX)
+        with torch.cuda.stream(stream):
+            m_h = None
+            for _ in range(args.warmup):
+                m_h, sel_h, st_h = b_h.step(dev_h, recycle=m_h); stream.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record(stream)
+            for _ in range(args.steps):
+                m_h, sel_h, st_h = b_h.step(dev_h, recycle=m_h)
+            h1.record(stream)
+            stream.synchronize()
+            h_ms = h0.elapsed_time(h1) / args.steps
+            eng.profile_enable(True)
+            m_h, sel_h, st_h = b_h.step(dev_h, recycle=m_h)
+            prof_h = eng.profile_read()
+            eng.profile_enable(False)
+            # descent on it: Jacobian, LP, Armijo from a step of 4 Delta (longer than the model is good for: the loop has to shrink)
+            Xh = dev_h.x.reshape(B, 1, N_VARS).contiguous()
+            Jh = torch.empty((B, 1, K_OUT, N_VARS), dtype=torch.float64, device="cuda")
+            eng.eval_dev(m_h, Xh, None, Jh)
+            oh = eng.descent_direction_dev(Jh.view(B, K_OUT, N_VARS), dev_h.x, dev_h.glb, dev_h.gub, True, None)
+            dnh = oh[0].abs().amax(dim=1).clamp_min(1e-300)
+            dirh = (oh[0] / dnh[:, None]).contiguous()
+            bth = eng.backtrack_dev(m_h, dev_h.x, dirh, torch.minimum(dnh, 4.0 * dev_h.delta).contiguous(), oh[1])
+            stream.synchronize()
+        th = torch.tensor([h_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        h_ms = float(th.item())
+        cnt = {a: float(getattr(sel_h, a).double().mean().item()) for a in ("n_r1", "n_r2", "n_r3", "n_r4")}
+        secondary.append({"metric": METRIC, "variant": "heterogeneous", "value": world * B / (h_ms * 1e-3), "unit": UNIT, "ms_per_step": h_ms,
+                          "builds_ok": int((st_h == 0).sum().item()), "mean_round_sizes": cnt,
+                          "kernel_ms": {k_: round(v_, 4) for k_, v_ in prof_h.items() if k_ != "eval"},
+                          "fully_linear_fraction": float(sel_h.flags_out[:, 0].double().mean().item()),
+                          "rebuilt_fraction": float(sel_h.flags_out[:, 1].double().mean().item()),
+                          "descent_on_it": {"lp_iterations_mean": float(oh[2].double().mean().item()), "lp_ok": int((oh[3] == 0).sum().item()),
+                                            "mean_backtrack_index": float(bth[0].double().mean().item()),
+                                            "backtracked_fraction": float((bth[0] > 0).double().mean().item())},
+                          "config": {"workload": f"{B} instances per GPU, database snapshots of {N_DB} sites with half of them inside the trust region, radii "
+                                                 "Delta x {1/4, 1/2, 1, 2}, round-3 budgets {0, 2, unlimited} with probabilities {5, 5, 90} % (budget-limited instances start round 4 under-poised and take the literal kernel), ensure_fully_linear on for half of the instances"}})
+        m_h.free(); del dev_h, b_h
+        # the LP alone on a workload where the simplex has to pivot: four conflicting random gradients, iterates partly on the bounds
+        g_l = torch.Generator(device="cuda"); g_l.manual_seed(7 + rank)
+        Jr = torch.randn((B, 4, N_VARS), dtype=torch.float64, device="cuda", generator=g_l)
+        xr = torch.rand((B, N_VARS), dtype=torch.float64, device="cuda", generator=g_l)
+        xr = torch.where(torch.rand((B, N_VARS), device="cuda", generator=g_l) < 0.2, torch.round(xr), xr).contiguous()
+        with torch.cuda.stream(stream):
+            ol = eng.descent_direction_dev(Jr, xr, dev.glb, dev.gub, True, None)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            for _ in range(args.steps):
+                ol = eng.descent_direction_dev(Jr, xr, dev.glb, dev.gub, True, ol)
+            q1.record(stream)
+            stream.synchronize()
+        lp_ms2 = q0.elapsed_time(q1) / args.steps
+        secondary.append({"metric": "descent_lp_per_s", "value": world * B / (lp_ms2 * 1e-3), "unit": "LPs/s", "ms_per_step": lp_ms2,
+                          "lp_iterations_mean": float(ol[2].double().mean().item()), "lp_iterations_max": int(ol[2].max().item()),
+                          "lp_ok": int((ol[3] == 0).sum().item()), "mean_omega": float(ol[1].mean().item()),
+                          "config": {"workload": f"{B} LPs per GPU: n={N_VARS}, k=4 random normal gradients, 20 % of the coordinates of the iterate on a bound"}})
+
     # ---- secondary metric: the whole multistart run in lock-step with device-resident databases:
     # every instance starts from its Halton point with an empty database and runs iterate! (algorithm.jl:615-917) until it stops
     if args.lockstep_iters > 0:
@@ -408,7 +574,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "instances_per_gpu": B, "n_vars": N_VARS, "n_outputs": K_OUT, "db_sites": N_DB,
                            "kernel": KERNEL, "mean_training_points": float(Ntrain.mean()), "builds_ok": ok,
-                           "l2": "per-step working set (sites + seeds + round-4 workspace) ~0.9 GB > 126 MB L2; no flush needed",
+                           "l2": "per-step working set (database sites 126 MB + round-4 panel workspace 0.5 GB + kept factorisations 0.8 GB) > 126 MB L2; no flush needed",
                            "parallelism": f"instances sharded over {world} rank(s), no data-path collective"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -419,6 +585,7 @@ def run_ours(args):
                                 f"{args.e2e_chunks} slice(s) of the batch, {args.e2e_buffers} device buffer(s) per slice -- the upload of the next "
                                 f"snapshot runs behind the kernels of the current one; {args.e2e_outputs} set(s) of result buffers -- a step's result copy "
                                 "runs behind the next step's kernels, the timed region ends when the last copy has landed"},
+                "e2e_resident": e2e_resident, "strong_scaling": strong,
                 "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
                 "gathered_rows": None if allrows is None else int(allrows.shape[0]), "gather_c_abi": gather_c_abi}
         emit(line)
@@ -486,6 +653,8 @@ def main():
     ap.add_argument("--eval-points", type=int, default=10**6, help="C5 trial points for the secondary metric (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-descent", dest="descent", action="store_false", help="skip the steepest-descent secondary metric")
+    ap.add_argument("--no-ps", dest="ps", action="store_false", help="skip the Pascoletti-Serafini secondary metric")
+    ap.add_argument("--no-hetero", dest="hetero", action="store_false", help="skip the heterogeneous-batch secondary metric")
     ap.add_argument("--lockstep-iters", type=int, default=20, help="max_iter of the lock-step multistart run (secondary metric; 0 = skip)")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="slices of the batch in the end-to-end pipeline")
     ap.add_argument("--e2e-outputs", type=int, default=2, help="sets of result buffers (2: a step's result copy runs behind the next step's kernels)")

@@ -125,9 +125,14 @@ class HostPipeline:
     OUTS = ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "flags_out")
 
     def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2, buffers: int = 1,
-                 outputs: int = 1):
+                 outputs: int = 1, resident_db: bool = False):
+        """resident_db: the databases (sites, values) are uploaded ONCE and stay on the device (grown with
+        mrbf_db_append_dev by a driver); a step then uploads only what changes between two model updates on the same database --
+        iterate, radius, flags, budget -- as in the reference's criticality loop (algorithm.jl:523-612), which rebuilds the models
+        for a shrinking radius on an unchanged database."""
         import torch
         self.torch = torch
+        self.resident_db = bool(resident_db)
         self.engine, self.cfg, self.chunks, self.compute = engine, cfg, chunks, compute_stream
         B = host["sites"].shape[0]
         self.bounds = [shard_range(B, c, chunks) for c in range(chunks)]
@@ -153,7 +158,13 @@ class HostPipeline:
         self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
         self.ev_comp = [[torch.cuda.Event() for _ in range(self.buffers)] for _ in range(chunks)]
         self.ev_out = [[torch.cuda.Event() for _ in range(self.outputs)] for _ in range(chunks)]
-        self.h2d_bytes = sum(t.numel() * t.element_size() for pc in self.pinned for t in pc.values())
+        self.step_names = tuple(k for k in self.NAMES if not (self.resident_db and k in ("sites", "values")))
+        if self.resident_db:
+            for c, pc in enumerate(self.pinned):
+                for d in self.dev[c]:
+                    d.sites.copy_(pc["sites"]); d.values.copy_(pc["values"])
+            torch.cuda.synchronize()
+        self.h2d_bytes = sum(pc[k].numel() * pc[k].element_size() for pc in self.pinned for k in self.step_names)
         self.d2h_bytes = 0
 
     def step(self):
@@ -166,7 +177,7 @@ class HostPipeline:
         for c in range(self.chunks):
             with torch.cuda.stream(self.copy_in):
                 self.copy_in.wait_event(self.ev_comp[c][t])       # this device buffer of the slice is free again
-                for k in self.NAMES:
+                for k in self.step_names:
                     getattr(self.dev[c][t], k).copy_(self.pinned[c][k], non_blocking=True)
                 self.ev_in[c].record(self.copy_in)
             with torch.cuda.stream(self.compute):
