@@ -522,6 +522,98 @@ def run_ours(args):
                           "lp_ok": int((ol[3] == 0).sum().item()), "mean_omega": float(ol[1].mean().item()),
                           "config": {"workload": f"{B} LPs per GPU: n={N_VARS}, k=4 random normal gradients, 20 % of the coordinates of the iterate on a bound"}})
 
+    # ---- secondary metric: config C4 (n = 200 convex quadratics; 5 RBF objectives in one group + a nonlinear constraint g(x) = sum x^2 - r^2
+    # as a second RBF group, large_scale_benchmarks.jl:154-160 settings: cubic, 2n + 1 = 401 model points, theta_1 = 2, theta_pivot = 1/4):
+    # per instance and iteration two surrogate updates (SurrogateContainer.jl:334-391), then the Jacobians / values the steepest-descent
+    # step and compute_normal_step read (descent.jl:196, 705-708).  One wave of instances (one per SM).
+    if args.c4_instances > 0:
+        n4, k4, ndb4, B4 = 200, 5, 400, args.c4_instances
+        rng4 = np.random.default_rng(4 + rank)
+        a4 = rng4.random((k4, n4)); D4 = 0.5 + rng4.random((k4, n4))
+        x4 = 0.3 + 0.4 * rng4.random((B4, n4))
+        s4 = np.zeros((B4, ndb4, n4)); s4[:, 0] = x4
+        rad4 = rng4.random((B4, ndb4 - 1, 1)) ** 0.25
+        s4[:, 1:] = np.clip(x4[:, None, :] + (rng4.random((B4, ndb4 - 1, n4)) * 2 - 1) * 0.4 * rad4, 0.0, 1.0)
+        v_obj = np.stack([np.sum(D4[j] * (s4 - a4[j]) ** 2, axis=-1) for j in range(k4)], axis=-1)
+        v_con = (np.sum(s4 ** 2, axis=-1) - 0.33 * n4)[..., None]
+        common = dict(n_db=np.full(B4, ndb4, np.int32), x_index=np.ones(B4, np.int32), x=x4, delta=np.full(B4, 0.1), glb=np.zeros(n4),
+                      gub=np.ones(n4), flags_in=np.tile(np.array([[1, 0]], np.int32), (B4, 1)), max_new=np.full(B4, 2**31 - 1, np.int32))
+        cfg_o = mb.RbfConfig(kernel="cubic", max_model_points=2 * n4 + 1, theta_enlarge_1=2.0, theta_pivot=0.25)
+        cfg_c = mb.RbfConfig(kernel="multiquadric", max_model_points=2 * n4 + 1, theta_enlarge_1=2.0, theta_pivot=0.25)
+        dev_o = upload_batch(dict(sites=s4, values=v_obj, **common), f"cuda:{local}")
+        dev_c = upload_batch(dict(sites=s4, values=v_con, **common), f"cuda:{local}")
+        b_o, b_c = MultistartBuilder(eng, cfg_o, DELTA_MAX), MultistartBuilder(eng, cfg_c, DELTA_MAX)
+        X4 = dev_o.x.reshape(B4, 1, n4).contiguous()
+        Jo = torch.empty((B4, 1, k4, n4), dtype=torch.float64, device="cuda"); Jcn = torch.empty((B4, 1, 1, n4), dtype=torch.float64, device="cuda")
+        Yo = torch.empty((B4, 1, k4), dtype=torch.float64, device="cuda"); Ycn = torch.empty((B4, 1, 1), dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(stream):
+            m_o = m_c = None
+            for _ in range(2):
+                m_o, sel_o, st_o = b_o.step(dev_o, recycle=m_o); m_c, sel_c, st_c = b_c.step(dev_c, recycle=m_c)
+            c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            stream.synchronize()
+            reps4 = max(1, min(3, args.steps))
+            c0.record(stream)
+            for _ in range(reps4):
+                m_o, sel_o, st_o = b_o.step(dev_o, recycle=m_o); m_c, sel_c, st_c = b_c.step(dev_c, recycle=m_c)
+            c1.record(stream)
+            for _ in range(reps4):
+                eng.eval_dev(m_o, X4, Yo, Jo); eng.eval_dev(m_c, X4, Ycn, Jcn)
+                o4 = eng.descent_direction_dev(Jo.view(B4, k4, n4), dev_o.x, dev_o.glb, dev_o.gub, True, None)
+            c2.record(stream)
+            stream.synchronize()
+        ms4, ms4d = c0.elapsed_time(c1) / reps4, c1.elapsed_time(c2) / reps4
+        same_r123 = bool(torch.equal(sel_o.r1, sel_c.r1) and torch.equal(sel_o.r2, sel_c.r2) and torch.equal(sel_o.n_r3, sel_c.n_r3))
+        secondary.append({"metric": "c4_instance_updates_per_s", "value": world * B4 / (ms4 * 1e-3), "unit": "instance updates/s (2 groups each)",
+                          "ms_per_step": ms4, "builds_ok": [int((st_o == 0).sum().item()), int((st_c == 0).sum().item())],
+                          "mean_training_points": [float((1 + sel_o.n_r1 + sel_o.n_r2 + sel_o.n_r3 + sel_o.n_r4).double().mean().item()),
+                                                   float((1 + sel_c.n_r1 + sel_c.n_r2 + sel_c.n_r3 + sel_c.n_r4).double().mean().item())],
+                          "rounds_1_3_equal_across_groups": same_r123, "jacobians_values_lp_ms": ms4d, "lp_ok": int((o4[3] == 0).sum().item()),
+                          "config": {"workload": f"C4: {B4} instances per GPU, n=200, group 1 = 5 cubic RBF objectives, group 2 = 1 multiquadric RBF constraint "
+                                                 "(equal signature: rounds 1-3 coincide, test/rbf_models.jl:158-162), 401 model points, 400-site snapshots"}})
+        m_o.free(); m_c.free(); del dev_o, dev_c, b_o, b_c
+
+    # ---- secondary metric: config C2 (one optimize run: ZDT1 n = 30, k = 2, multiquadric; 61 and 496 model points): B = 1 latencies through
+    # the host-pointer C ABI (what the Julia shim calls), wall clock medians
+    if args.c2 and rank == 0:
+        def med_ms(f, reps=9):
+            f(); ts = []
+            for _ in range(reps):
+                t0_ = time.perf_counter(); f(); ts.append(time.perf_counter() - t0_)
+            return float(np.median(ts)) * 1e3
+        rows2 = []
+        for ndb2, mmp2 in ((128, 61), (600, -1)):
+            cfg2 = mb.RbfConfig(kernel="multiquadric", max_model_points=mmp2)
+            h2 = synthetic.multistart_batch(1, n=N_VARS, n_db=ndb2, delta=DELTA, func=synthetic.zdt1)
+            kept2 = [None, None]
+            def sel2():
+                kept2[0], kept2[1] = eng.select_points_keep(cfg2, h2["sites"], h2["n_db"], h2["x_index"], h2["x"], h2["delta"], h2["delta_max"],
+                                                            h2["glb"], h2["gub"], prepared=kept2[1])
+            sel2()
+            r3v2 = synthetic.zdt1(kept2[0].r3_sites[0])[None]
+            m2 = [None]
+            def bld2():
+                m2[0], _ = eng.build_prepared(cfg2, kept2[1], h2["sites"], h2["values"], h2["x_index"], kept2[0], r3v2, recycle=m2[0])
+            t_s, t_b = med_ms(sel2), med_ms(bld2)
+            x2 = h2["x"][:, None, :]
+            t_j = med_ms(lambda: eng.eval(m2[0], x2, True, True), 21)
+            J2 = eng.eval(m2[0], x2, False, True)[1][:, 0]
+            t_lp = med_ms(lambda: eng.descent_direction(J2, h2["x"], h2["glb"], h2["gub"], True), 21)
+            d2 = np.ones((1, N_VARS)) / np.sqrt(N_VARS)
+            t_bt = med_ms(lambda: eng.backtrack(m2[0], h2["x"], d2, 0.1, 0.5), 15)
+            mx2 = eng.eval(m2[0], x2, True, False)[0][:, 0]
+            lb2_, ub2_ = np.maximum(0.0, h2["x"] - DELTA), np.minimum(1.0, h2["x"] + DELTA)
+            t_ps = med_ms(lambda: eng.ps_solve(m2[0], h2["x"], lb2_, ub2_, mx2, np.ones((1, K_OUT)), K_OUT, -1, -1, -1, 5), 3)
+            Ntr2 = int(1 + kept2[0].n_r1[0] + kept2[0].n_r2[0] + kept2[0].n_r3[0] + kept2[0].n_r4[0])
+            rows2.append({"db_sites": ndb2, "max_model_points": mmp2, "training_points": Ntr2,
+                          "ms": {"prepare_update_model": t_s, "update_model": t_b, "values_and_jacobian_1pt": t_j, "descent_lp": t_lp,
+                                 "backtrack_118pts": t_bt, "pascoletti_serafini_solve_16120_evals": t_ps}})
+            m2[0].free(); kept2[1].free()
+        secondary.append({"metric": "c2_single_instance_latency_ms", "value": rows2[0]["ms"]["prepare_update_model"] + rows2[0]["ms"]["update_model"],
+                          "unit": "ms per model update (61 model points)", "rows": rows2,
+                          "config": {"workload": "C2: one ZDT1 n=30 k=2 instance, multiquadric; per-call wall-clock medians of the host-pointer entry points "
+                                                 "(B = 1: launch-latency-bound by construction, SURVEY 7 'hard parts')"}})
+
     # ---- secondary metric: the whole multistart run in lock-step with device-resident databases:
     # every instance starts from its Halton point with an empty database and runs iterate! (algorithm.jl:615-917) until it stops
     if args.lockstep_iters > 0:
@@ -655,6 +747,8 @@ def main():
     ap.add_argument("--no-descent", dest="descent", action="store_false", help="skip the steepest-descent secondary metric")
     ap.add_argument("--no-ps", dest="ps", action="store_false", help="skip the Pascoletti-Serafini secondary metric")
     ap.add_argument("--no-hetero", dest="hetero", action="store_false", help="skip the heterogeneous-batch secondary metric")
+    ap.add_argument("--c4-instances", type=int, default=148, help="instances of the C4 two-group secondary metric (0 = skip)")
+    ap.add_argument("--no-c2", dest="c2", action="store_false", help="skip the C2 single-instance latency secondary")
     ap.add_argument("--lockstep-iters", type=int, default=20, help="max_iter of the lock-step multistart run (secondary metric; 0 = skip)")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="slices of the batch in the end-to-end pipeline")
     ap.add_argument("--e2e-outputs", type=int, default=2, help="sets of result buffers (2: a step's result copy runs behind the next step's kernels)")

@@ -114,6 +114,64 @@ def test_rounds_1_to_3_shared_between_kernels():
     assert np.allclose(J, fd, rtol=1e-4, atol=1e-5)
 
 
+def test_c4_two_groups_exploit_other_rbf_metas_n200():
+    """BASELINE config C4 through the plugin mirror: n = 200, group 1 = 5 cubic RBF objectives, group 2 = the RBF constraint
+    g(x) = sum x^2 - r^2 with another kernel but the same signature, large_scale_benchmarks.jl:154-160 settings (401 model points,
+    theta_1 = 2, theta_pivot = 1/4).  The second group takes rounds 1-3 from the first one by site (`_exploit_other_rbf_metas!`,
+    RbfModel.jl:311-342, inserting the value-less round-3 sites into its own database) and runs only its own round 4; both training
+    sets equal what the oracle selects for each group on its own, and the constraint surrogate's value and Jacobian at the iterate --
+    what compute_normal_step reads (descent.jl:705-708) -- match the oracle model."""
+    rng = np.random.default_rng(200)
+    n, k, n_db = 200, 5, 260
+    a = rng.random((k, n)); D = 0.5 + rng.random((k, n))
+    fo = lambda x: np.array([np.sum(D[j] * (x - a[j]) ** 2) for j in range(k)])
+    fc = lambda x: np.array([np.sum(x ** 2) - 0.33 * n])
+    kw = dict(max_model_points=2 * n + 1, theta_enlarge_1=2.0, theta_pivot=0.25)
+    cfg1, cfg2 = mb.RbfConfig(kernel="cubic", **kw), mb.RbfConfig(kernel="multiquadric", **kw)
+    assert cfg1.signature() == cfg2.signature() and cfg1 != cfg2
+    x0 = 0.3 + 0.4 * rng.random(n)
+    db1, db2 = mb.ArrayDB(n), mb.ArrayDB(n)
+    i1 = db1.new_result(x0, fo(x0)); i2 = db2.new_result(x0, fc(x0))
+    for _ in range(n_db - 1):
+        xi = np.clip(x0 + (rng.random(n) * 2 - 1) * 0.4 * rng.random() ** 0.25, 0.0, 1.0)
+        db1.new_result(xi, fo(xi)); db2.new_result(xi, fc(xi))
+    sdb = mb.SuperDB({("o",): db1, ("c",): db2})
+    scal = mb.VarScaler(np.zeros(n), np.ones(n))
+    it = mb.IterData(x0, 0.1, {("o",): i1, ("c",): i2})
+    ac = mb.AlgoConfig(max_evals=10**9)
+    mop = mb.MopStub({"o": k, "c": 1})
+    m1 = mb.RbfMeta(signature=cfg1.signature(), func_indices=("o",))
+    m2 = mb.RbfMeta(signature=cfg2.signature(), func_indices=("c",))
+    m1 = mb.prepare_update_model(None, m1, cfg1, ("o",), mop, scal, it, sdb, ac, ensure_fully_linear=True, meta_array=[])
+    m2 = mb.prepare_update_model(None, m2, cfg2, ("c",), mop, scal, it, sdb, ac, ensure_fully_linear=True, meta_array=[m1])
+    for fn in ("round1_indices", "round2_indices", "round3_indices"):
+        a_, b_ = getattr(m1, fn), getattr(m2, fn)
+        assert len(a_) == len(b_) and all(np.array_equal(db1.get_site(i), db2.get_site(j)) for i, j in zip(a_, b_)), fn
+    assert m2.fully_linear == m1.fully_linear and len(m1.round3_indices) > 0
+    # the oracle, each group on its own database (same sites, so the same rounds 1-3; round 4 depends on the kernel)
+    for cfg, meta, db in ((cfg1, m1, db1), (cfg2, m2, db2)):
+        ocfg = O.RbfConfig(kernel=cfg.kernel, **kw)
+        S0 = db.sites_array()[:n_db]
+        ref = CO.select_points_batched(ocfg, S0[None], np.array([1], np.int32), x0[None], np.array([0.1]), 0.5, np.zeros(n), np.ones(n),
+                                       True, False, 2**31 - 1, nthreads=1)
+        assert list(meta.round1_indices) == list(ref.r1[0, :ref.n_r1[0]]) and list(meta.round2_indices) == list(ref.r2[0, :ref.n_r2[0]])
+        assert len(meta.round3_indices) == ref.n_r3[0]
+        # round 4 of the GPU path ran on the database that already holds the round-3 sites; they are no candidates (found set)
+        assert [i for i in meta.round4_indices] == list(ref.r4[0, :ref.n_r4[0]])
+        assert 1 + len(meta.round1_indices) + len(meta.round2_indices) + len(meta.round3_indices) + len(meta.round4_indices) <= 2 * n + 1
+    db1.eval_missing(fo); db2.eval_missing(fc)
+    mod1, _ = mb.update_model(None, m1, cfg1, ("o",), mop, scal, it, sdb, ac)
+    mod2, _ = mb.update_model(None, m2, cfg2, ("c",), mop, scal, it, sdb, ac)
+    ids2 = mb._collect_indices(m2)
+    om2 = O.build_model(np.array([db2.get_site(i) for i in ids2]), np.array([db2.get_value(i) for i in ids2]), O.RbfConfig(kernel="multiquadric", **kw))
+    yc, Jc = mb.eval_models(mod2, scal, x0), mb.get_jacobian(mod2, scal, x0)
+    assert abs(yc[0] - fc(x0)[0]) <= 1e-9 * max(1.0, abs(fc(x0)[0]))                       # interpolation at the centre
+    assert np.abs(yc - om2.eval(x0)).max() <= 1e-9 * max(1.0, np.abs(yc).max())
+    assert np.abs(Jc - om2.jac(x0)).max() <= 1e-8 * max(1.0, np.abs(om2.jac(x0)).max())
+    J1 = mb.get_jacobian(mod1, scal, x0)
+    assert J1.shape == (k, n) and np.all(np.isfinite(J1))
+
+
 def _common_descent(J):
     """Minimum-norm element of the convex hull of the normalised gradients (k <= 2): a descent direction for every output,
     so the Armijo loop stops at a moderate step instead of a rounding-noise decision at the minimum step size."""
