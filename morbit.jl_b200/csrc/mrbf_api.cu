@@ -6,6 +6,8 @@
 
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "mrbf_common.cuh"
 #include "mrbf_kernels.h"
 
@@ -79,10 +81,21 @@ int fail(mrbf_ctx* c, int code, const char* fmt, const char* detail = "") {
     } while (0)
 
 // event bracket around a kernel class (instrumentation only)
+// MRBF_NVTX=1 additionally opens an NVTX range per kernel class (header-only nvtx3; a no-op without an attached tool), so that
+// `ncu --nvtx --nvtx-include "mrbf:round4/"` or a timeline tool can address the phases by name.
+const bool g_nvtx = getenv("MRBF_NVTX") && atoi(getenv("MRBF_NVTX")) != 0;
+const char* const k_phase_names[8] = {"mrbf:rounds123", "mrbf:round4", "mrbf:gather", "mrbf:build", "mrbf:eval", "mrbf:round4_literal",
+                                      "mrbf:build_prepared", "mrbf:other"};
 struct Timed {
     mrbf_ctx* c; int id;
-    Timed(mrbf_ctx* ctx, int i) : c(ctx), id(i) { if (c->prof) cudaEventRecord(c->ev0[id], c->stream); }
-    ~Timed() { if (c->prof) { cudaEventRecord(c->ev1[id], c->stream); c->ev_used[id] = true; } }
+    Timed(mrbf_ctx* ctx, int i) : c(ctx), id(i) {
+        if (g_nvtx) nvtxRangePushA(k_phase_names[id & 7]);
+        if (c->prof) cudaEventRecord(c->ev0[id], c->stream);
+    }
+    ~Timed() {
+        if (c->prof) { cudaEventRecord(c->ev1[id], c->stream); c->ev_used[id] = true; }
+        if (g_nvtx) nvtxRangePop();
+    }
 };
 
 int ensure(mrbf_ctx* ctx, DevBuf& b, size_t bytes) {
