@@ -50,10 +50,10 @@ struct Round4Params {
 // Geometry of the register-tiled round-4 kernel (mrbf_round4_schur.cu): shared-memory offsets and the layout of the
 // kept factorisation, all in doubles.
 struct SchurGeom {
-    int MC, TR, ntiles, nthreads, eligible, two_variants;
-    size_t sm_C, sm_V, sm_Xc, sm_col, sm_red, sm_int, smem_doubles;          // kernel 2 (tiles + elimination)
-    size_t ps_Aq, ps_X0, ps_M0, ps_P00, ps_red, ps_int, ps_doubles;           // kernel 1 (panels)
-    size_t pw_C, pw_V, pw_Xc, pw_clist, pw_meta, pw_doubles;                  // global panel workspace per instance
+    int MC, TR, ntiles, nthreads, eligible, two_variants, LD_small;
+    size_t smem_doubles, smem_small;                                          // kernel 2 (panels + tiles + elimination): full / small launch shape
+    size_t ps_Aq, ps_X0, ps_red, ps_int, ps_doubles;                          // kernel 1 (candidate list, Pi_0^{-1})
+    size_t pw_M0, pw_clist, pw_meta, pw_doubles;                              // global hand-over workspace per instance
     size_t off_M0, off_U, off_C, off_L, off_acc, state_doubles;
 };
 

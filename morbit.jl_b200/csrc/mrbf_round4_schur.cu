@@ -9,21 +9,27 @@
 //   * the reference tests   tau^2 = sigma - ||L^{-1} v||^2 > theta^4   (RbfModel.jl:447-452).  In the basis above
 //         tau^2 = d^2 / (1 + lev),
 //     d^2  = Schur complement of  A = N' Phi N  at xi after eliminating the accepted candidates,
-//     1+lev = Schur complement of W = I + C' C   at xi after eliminating the accepted candidates
+//     lev  = c_xi' (I + C_S C_S')^{-1} c_xi,   C_S = Lagrange coefficients of the accepted candidates
 //     (lev = pi' (Pi' Pi)^{-1} pi is the leverage whose 1/(1+lev) is the product of the Givens cosines of
-//     utilities.jl:437-448; Woodbury turns the Sherman-Morrison updates of (Pi' Pi)^{-1} into an elimination on W).
-//   * so round 4 is ONE symmetric elimination on the pair (A, W) over the candidates in ascending id order, where a
-//     rejected pivot is simply skipped (RbfModel.jl:452 leaves the state untouched).  A and W (mc x mc, mc <= 128
-//     candidates) never touch memory: every thread owns one 4 x 4 tile of each in registers, computed directly from
-//     the shared-memory panels C (Lagrange coefficients), V = B - Phi00 C / 2 and the candidate sites
-//         A_ij = phi(|xi_i - xi_j|) - c_i.v_j - v_i.c_j ,      W_ij = delta_ij + c_i.c_j .
+//     utilities.jl:437-448; 1 + lev is the Schur complement of I + C'C at xi -- push-through identity).
+//   * so round 4 is ONE symmetric elimination on A over the candidates in ascending id order, where a rejected pivot is
+//     simply skipped (RbfModel.jl:452 leaves the state untouched), with the leverages supplied beside it.  A (mc x mc,
+//     mc <= 128 candidates) never touches memory: every tile thread owns one 4 x 4 tile in registers, computed directly
+//     from the shared-memory panels C (Lagrange coefficients), V = B - Phi00 C / 2 and the candidate sites
+//         A_ij = phi(|xi_i - xi_j|) - c_i.v_j - v_i.c_j .
 //     The elimination is blocked, four pivots (one tile column) at a time: the diagonal-tile thread runs the four pivot
 //     tests in registers, the tiles of that tile column publish the pivot panel, every tile to the right applies the
 //     rank-4 update; the hand-overs are split-phase mbarriers.  The Cholesky factor rows (pivot column / d) are streamed
 //     out for mrbf_build_prepared_dev, which finishes the model with two triangular solves per output.
-//   * two kernels: round4_panels_kernel (candidate list, Pi_0^{-1}, panels; four instances per SM) hands the panels over
-//     through an L2-resident workspace to round4_schur_kernel (tiles + elimination; the tiles fill the register file, one
-//     instance per SM, in two launch shapes: <= 100 candidates on 352 threads / 157 registers, else 544 threads).
+//   * the leverages come from ONE extra warp per CTA that keeps M = (I + C_S C_S')^{-1} (p x p, shared memory) and hands the
+//     diagonal-tile thread the 4 x 4 block G = I + C_J' M C_J of the next four candidates J; the thread eliminates G in its
+//     registers beside A's diagonal tile (so every accept pattern inside the block is covered) and returns the multipliers,
+//     from which the warp applies the rank-(#accepted) downdate of M.  That keeps the p x p recursion off the tile threads:
+//     half the registers of an elimination on the pair (A, I + C'C), so TWO instances share an SM and hide each other's
+//     pivot chains.
+//   * two kernels: round4_prep_kernel (candidate list, Pi_0^{-1}; small footprint, several instances per SM) and
+//     round4_elim_kernel (panels in shared memory, tiles, elimination; in two launch shapes: <= 100 candidates on 352 + 32
+//     threads, two CTAs per SM, else 544 + 32 threads).
 //
 // Instances that do not qualify (N0 != p, singular Pi_0) are marked n_r4 = -1 for the literal kernel; batches whose
 // database is larger than 128 sites or whose panels do not fit in shared memory use round4_block_kernel instead.
@@ -75,6 +81,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!done);
 }
 
+// Shared-memory layout of round4_elim_kernel for leading dimension LD (the padded candidate count of the instance, <= the
+// launch's maximum), in doubles; every block starts 32-byte aligned (double4 accesses).
+//   phase "panels":  C (p x LD) | V (p x LD) | Xc (n x LD) || X0 (p x n) | M0 (p x p) | P00 (p x p) || fixed
+//   phase "elim":    C (p x LD) | ring[3] of { colA, colAs : [4][LD] } .... || M (p x PS) | su (p x 4)  || fixed
+// fixed: G blocks [3][16], info [3][28], barriers [9], clist (LD ints)
+struct ElimLayout { int C, V, Xc, ring, X0, M0, P00, Minv, su, gs, inf, bar, clist, total, PS; };
+__host__ __device__ inline ElimLayout elim_layout(int p, int n, int LD) {
+    ElimLayout L;
+    const int pl = p > 0 ? p : 1;
+    const int pg = (pl + 7) & ~7;                    // the leverage warp walks the columns of M in groups of eight
+    L.PS = pg + 1;                                   // odd row stride: a lane per row walks the columns without bank conflicts
+    L.C = 0; L.V = pl * LD; L.Xc = L.V + pl * LD; L.ring = L.V;
+    int regB = (pl + n) * LD; if (regB < 24 * LD) regB = 24 * LD;
+    const int baseC = L.V + regB;
+    L.X0 = baseC; L.M0 = (L.X0 + pl * n + 3) & ~3; L.P00 = (L.M0 + pl * pl + 3) & ~3;
+    int endC1 = L.P00 + pl * pl;
+    L.Minv = baseC; L.su = (L.Minv + pl * L.PS + 3) & ~3;
+    int endC2 = L.su + 4 * pg;
+    int endC = endC1 > endC2 ? endC1 : endC2; endC = (endC + 3) & ~3;
+    L.gs = endC; L.inf = L.gs + 48; L.bar = L.inf + 84; L.clist = L.bar + 12;
+    L.total = L.clist + (LD + 1) / 2 + 2;
+    return L;
+}
+
 SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     SchurGeom g{};
     const int pl = p > 0 ? p : 1;
@@ -82,52 +112,48 @@ SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     if (g.MC < 4) g.MC = 4;
     g.TR = g.MC / 4;
     g.ntiles = schur_tiles(g.TR);
+    g.two_variants = g.ntiles > 352 ? 1 : 0;
     int nt = (g.ntiles + 31) & ~31;
-    if (nt < 256) nt = 256;
-    g.nthreads = nt;
+    if (nt < 64) nt = 64;
+    g.nthreads = nt + 32;                              // tile threads + the leverage warp
+    g.LD_small = g.MC < 104 ? g.MC : 104;                // 26 tile rows = 351 tiles still run in the small shape
+    g.smem_small = (size_t)elim_layout(p, n, g.LD_small).total;
+    g.smem_doubles = (size_t)elim_layout(p, n, g.MC).total;
     auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };          // every block starts 32-byte aligned (double4 accesses)
     const size_t ints = (size_t)g.MC + 32 + ((size_t)db_stride + 3) / 4 + 4;   // clist[MC], wcnt[32], flags[db_stride] bytes
-    // kernel 1 (panels): shared memory
-    g.ps_Aq = 0; g.ps_X0 = up4((size_t)2 * pl * pl); g.ps_M0 = up4(g.ps_X0 + (size_t)pl * n); g.ps_P00 = up4(g.ps_M0 + (size_t)pl * pl);
-    g.ps_red = up4(g.ps_P00 + (size_t)pl * pl); g.ps_int = g.ps_red + 80; g.ps_doubles = g.ps_int + (ints + 1) / 2;
-    // panel workspace (global, per instance): C (p x MC), V (p x MC), Xc (n x MC), clist (MC ints), meta (8)
-    g.pw_C = 0; g.pw_V = (size_t)pl * g.MC; g.pw_Xc = g.pw_V + (size_t)pl * g.MC; g.pw_clist = g.pw_Xc + (size_t)n * g.MC;
+    // kernel 1 (prep): shared memory
+    g.ps_Aq = 0; g.ps_X0 = up4((size_t)2 * pl * pl); g.ps_red = up4(g.ps_X0 + (size_t)pl * n);
+    g.ps_int = g.ps_red + 80; g.ps_doubles = g.ps_int + (ints + 1) / 2;
+    // hand-over workspace (global, per instance): M0 = Pi_0^{-T} (p x p), clist (MC ints), meta (8)
+    g.pw_M0 = 0; g.pw_clist = up4((size_t)pl * pl);
     g.pw_meta = up4(g.pw_clist + (g.MC + 1) / 2); g.pw_doubles = g.pw_meta + 8;
-    // kernel 2 (tiles + elimination): shared memory
-    g.sm_C = 0; g.sm_V = (size_t)pl * g.MC; g.sm_Xc = g.sm_V + (size_t)pl * g.MC;
-    g.sm_col = g.sm_Xc + (size_t)n * g.MC;                              // ring[3] of { colA, colAs, colW, colWs : [4][MC] }, then info[3][24]
-    g.sm_red = g.sm_col + (size_t)48 * g.MC + 3 * 24;
-    g.sm_int = g.sm_red + 80;
-    g.smem_doubles = g.sm_int + ((size_t)g.MC + 1) / 2 + 2;
     // kept state per instance: M0 (p x p), U (p x MC), C (p x MC), L (MC x MC, column q = q-th accepted pivot), accpos (MC), meta (8)
     g.off_M0 = 0; g.off_U = up4((size_t)pl * pl); g.off_C = g.off_U + (size_t)pl * g.MC; g.off_L = g.off_C + (size_t)pl * g.MC;
     g.off_acc = g.off_L + (size_t)g.MC * g.MC; g.state_doubles = up4(g.off_acc + g.MC + 8);
-    g.two_variants = g.ntiles > 352 ? 1 : 0;
-    g.eligible = (p > 0 && g.MC <= 128 && g.nthreads <= 544 && g.smem_doubles * sizeof(double) <= (size_t)225 * 1024 &&
+    g.eligible = (p > 0 && p <= 96 && g.MC <= 128 && g.ntiles <= 544 && g.smem_doubles * sizeof(double) <= (size_t)225 * 1024 &&
                   g.ps_doubles * sizeof(double) <= (size_t)225 * 1024) ? 1 : 0;
     return g;
 }
 
-// Kernel 1 of 2: candidate list, Pi_0^{-1} and the panels C, V, Xc of one instance, written to the global panel workspace
-// (and C, U, M0 to the kept factorisation).  Small footprint (the Gauss-Jordan scratch and three p x p matrices in shared
-// memory, 64 registers), so four to five instances share an SM and hide each other's pivot chains.
-__global__ void __launch_bounds__(256, 4) round4_panels_kernel(Round4Params P, SchurGeom g) {
+#define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+#define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+
+// Kernel 1 of 2: candidate list and Pi_0^{-1} of one instance, written to the hand-over workspace.  Small footprint (the
+// Gauss-Jordan scratch and the found sites in shared memory), so several instances share an SM and hide each other's pivot chains.
+__global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, SchurGeom g) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = poly_dim(n, P.cfg.polynomial_degree), pl = p;
     const int MC = g.MC;
     double* pw = P.panel_ws + (size_t)blockIdx.x * g.pw_doubles;
-    double* Cs = pw + g.pw_C; double* Vs = pw + g.pw_V; double* Xc = pw + g.pw_Xc;      // panels: global (L2-resident) workspace
     double* pmeta = pw + g.pw_meta;
     double* Aq = smem + g.ps_Aq;       // Gauss-Jordan scratch [Pi_0 | I] (p x 2p)
     double* Qx = Aq + pl * pl;
-    double* X0 = smem + g.ps_X0; double* M0 = smem + g.ps_M0; double* P00 = smem + g.ps_P00;
+    double* X0 = smem + g.ps_X0;
     double* red = smem + g.ps_red;
     int* clist = reinterpret_cast<int*>(smem + g.ps_int); int* wcnt = clist + MC;
     unsigned char* cflag = reinterpret_cast<unsigned char*>(wcnt + 32);
 
-#define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
-#define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
     SCHUR_STAMP(0);
     const int n_db = P.n_db[b];
     const double* sites = P.sites + (size_t)b * P.db_stride * n;
@@ -199,17 +225,8 @@ __global__ void __launch_bounds__(256, 4) round4_panels_kernel(Round4Params P, S
     }
     __syncthreads();
     if (mc == 0) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
-    const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
-    // candidate sites, coordinate-major (Xc[k][i]); the padding columns repeat the centre (finite, never a pivot)
-    for (int e = tid; e < MCa * n; e += nt) {
-        const int i = e % MCa, k = e / MCa;
-        Xc[k * MC + i] = (i < mc) ? sites[(size_t)clist[i] * n + k] : X0[k];
-    }
     for (int e = tid; e < p * p; e += nt) {
         const int i = e % p, j = e / p;
-        double r2 = 0.0;
-        for (int k = 0; k < n; ++k) { const double d = X0[i * n + k] - X0[j * n + k]; r2 = fma(d, d, r2); }
-        P00[i + j * pl] = rad_phi(P.rf, r2);
         Aq[i + j * pl] = (j == 0) ? 1.0 : (X0[i * n + j - 1] - X0[j - 1]) * inv_s;
         Qx[i + j * pl] = (i == j) ? 1.0 : 0.0;
     }
@@ -258,68 +275,89 @@ __global__ void __launch_bounds__(256, 4) round4_panels_kernel(Round4Params P, S
         __syncthreads();
     }
     if (red[76] != 0.0) { if (tid == 0) P.n_r4[b] = -1; return; }
-    for (int e = tid; e < p * p; e += nt) { const int r = e % p, c = e / p; M0[r + c * pl] = Qx[c + r * pl]; }   // M0 = Pi_0^{-T}
-    __syncthreads();                                // Gauss-Jordan scratch is dead from here on
-    double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
-    if (keep) for (int e = tid; e < p * p; e += nt) keep[g.off_M0 + e] = M0[e];
-
-    SCHUR_STAMP(2);
-    // ---- panels: C = Pi_0^{-T} pi~ (Lagrange coefficients) and B = Phi(S0, candidates), one (row, 4 candidates) task per thread
-    for (int t = tid; t < p * TRa; t += nt) {
-        const int r = t / TRa, i4 = (t % TRa) * 4;
-        double c0 = M0[r], c1 = c0, c2 = c0, c3 = c0;            // pi~[0] = 1
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double4 x = *reinterpret_cast<const double4*>(Xc + k * MC + i4);
-            if (k + 1 < p) {
-                const double mv = M0[r + (k + 1) * pl] * inv_s, xc = X0[k];
-                c0 = fma(mv, x.x - xc, c0); c1 = fma(mv, x.y - xc, c1); c2 = fma(mv, x.z - xc, c2); c3 = fma(mv, x.w - xc, c3);
-            }
-            const double xr = X0[r * n + k];
-            double e_;
-            e_ = x.x - xr; d0 = fma(e_, e_, d0); e_ = x.y - xr; d1 = fma(e_, e_, d1);
-            e_ = x.z - xr; d2 = fma(e_, e_, d2); e_ = x.w - xr; d3 = fma(e_, e_, d3);
-        }
-        *reinterpret_cast<double4*>(Cs + r * MC + i4) = make_double4(c0, c1, c2, c3);
-        *reinterpret_cast<double4*>(Vs + r * MC + i4) = make_double4(rad_phi(P.rf, d0), rad_phi(P.rf, d1), rad_phi(P.rf, d2), rad_phi(P.rf, d3));
-        if (keep) *reinterpret_cast<double4*>(keep + g.off_C + r * MC + i4) = make_double4(c0, c1, c2, c3);
-    }
-    __syncthreads();
-    // ---- U = B - Phi00 C (kept for the build), V = B - Phi00 C / 2 (in place of B)
-    for (int t = tid; t < p * TRa; t += nt) {
-        const int r = t / TRa, i4 = (t % TRa) * 4;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        for (int c = 0; c < p; ++c) {
-            const double pv = P00[r + c * pl];
-            const double4 cc = *reinterpret_cast<const double4*>(Cs + c * MC + i4);
-            s0 = fma(pv, cc.x, s0); s1 = fma(pv, cc.y, s1); s2 = fma(pv, cc.z, s2); s3 = fma(pv, cc.w, s3);
-        }
-        const double4 bb = *reinterpret_cast<const double4*>(Vs + r * MC + i4);
-        if (keep) *reinterpret_cast<double4*>(keep + g.off_U + r * MC + i4) = make_double4(bb.x - s0, bb.y - s1, bb.z - s2, bb.w - s3);
-        *reinterpret_cast<double4*>(Vs + r * MC + i4) = make_double4(fma(-0.5, s0, bb.x), fma(-0.5, s1, bb.y), fma(-0.5, s2, bb.z), fma(-0.5, s3, bb.w));
-    }
+    for (int e = tid; e < p * p; e += nt) { const int r = e % p, c = e / p; pw[g.pw_M0 + r + c * pl] = Qx[c + r * pl]; }   // M0 = Pi_0^{-T}
     for (int i = tid; i < mc; i += nt) reinterpret_cast<int*>(pw + g.pw_clist)[i] = clist[i];
     if (tid == 0) { pmeta[1] = inv_s; pmeta[2] = (double)N0; pmeta[0] = (double)mc; }
-    SCHUR_STAMP(3);
+    SCHUR_STAMP(2);
 }
 
-// Kernel 2 of 2: the panels come back from the workspace into shared memory, every thread computes its 4 x 4 tiles of A and W and
-// the blocked elimination runs in registers.  One CTA per SM (the tiles fill the register file).
-// Two launch shapes of the same code, every instance is taken by exactly one: SMALL (<= 352 tiles, i.e. <= 100 candidates: 352
-// threads, so the CTA leaves ~28 k registers and 80 KB of shared memory of its SM to CTAs of other streams -- rounds 1-3, the
-// panels kernel or the build of another slice of the batch) and the full shape (544 threads, <= 128 candidates).
-template <bool SMALL>
-__global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Round4Params P, SchurGeom g) {
+// Sum of 16 per-lane values over the warp with 32 shuffles: each exchange step keeps one half of the values and sends the other.
+// Afterwards lane l holds the total of value  8 * bit4(l) + 4 * bit3(l) + 2 * bit2(l) + bit1(l).
+__device__ __forceinline__ double warp_sum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, m = 16; half >= 1; half >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double keep = up ? v[i + half] : v[i];
+            const double send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// One pass of the leverage warp over the rows of M it owns (lane l: rows l, l + 32, ..): downdate  M -= sum_q av_q u_q'  (upd) and
+// U = M C_J, eight columns at a time so that the loads of a group are in flight together.  Columns p .. PS-2 of M are zero padding.
+template <int RPL>
+__device__ __forceinline__ void lev_pass(double* __restrict__ Minv, const double* __restrict__ su, const double* __restrict__ Cj, int LD, int PS,
+                                         int p, int lane, bool upd, const double (&av)[RPL][4], double (&U4)[RPL][4]) {
+    const int pg = (p + 7) & ~7;
+#pragma unroll
+    for (int rr = 0; rr < RPL; ++rr) {
+        const int r = lane + 32 * rr;
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+        if (r < p) {
+            double* mrow = Minv + r * PS;
+            const double a0 = av[rr][0], a1 = av[rr][1], a2 = av[rr][2], a3 = av[rr][3];
+            for (int c0 = 0; c0 < pg; c0 += 8) {
+                double m[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = mrow[c0 + i];
+                if (upd) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double4 s[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s[i] = *reinterpret_cast<const double4*>(su + 4 * (c0 + 4 * h + i));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double a = fma(-a1, s[i].y, fma(-a0, s[i].x, m[4 * h + i]));
+                            const double t = fma(a3, s[i].w, a2 * s[i].z);
+                            m[4 * h + i] = a - t;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mrow[c0 + i] = m[i];
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double4 cj[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const int c = min(c0 + 4 * h + i, p - 1); cj[i] = *reinterpret_cast<const double4*>(Cj + c * LD); }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        u0 = fma(m[4 * h + i], cj[i].x, u0); u1 = fma(m[4 * h + i], cj[i].y, u1);
+                        u2 = fma(m[4 * h + i], cj[i].z, u2); u3 = fma(m[4 * h + i], cj[i].w, u3);
+                    }
+                }
+            }
+        }
+        U4[rr][0] = u0; U4[rr][1] = u1; U4[rr][2] = u2; U4[rr][3] = u3;
+    }
+}
+
+// Kernel 2 of 2: the panels C, V and the candidate sites are computed into shared memory, every tile thread computes its
+// 4 x 4 tile of A and the blocked elimination runs in registers; the last warp supplies the leverage blocks (header comment).
+// Two launch shapes of the same code, every instance is taken by exactly one: SMALL (<= 352 tiles, i.e. <= 100 candidates:
+// 352 + 32 threads, <= 80 registers and < 113 KB of shared memory, so two instances share an SM) and the full shape
+// (544 + 32 threads, <= 128 candidates).  RPL = rows of M per lane of the leverage warp (p <= 32 RPL).
+template <bool SMALL, int RPL>
+__global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_kernel(Round4Params P, SchurGeom g) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = poly_dim(n, P.cfg.polynomial_degree);
     const int MC = g.MC;
-    double* Cs = smem + g.sm_C; double* Vs = smem + g.sm_V; double* Xc = smem + g.sm_Xc;
-    double* ring = smem + g.sm_col; double* info = ring + 48 * MC;
-    double* red = smem + g.sm_red;
-    int* clist = reinterpret_cast<int*>(smem + g.sm_int);
-#define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
-#define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
     SCHUR_STAMP(6);
     const double* pw = P.panel_ws + (size_t)b * g.pw_doubles;
     const double* pmeta = pw + g.pw_meta;
@@ -332,37 +370,97 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
     double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
     const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
     if (g.two_variants && (SMALL != (schur_tiles(TRa) <= 352))) return;      // the other launch shape's instance
+    const int LD = MCa;
+    const ElimLayout L = elim_layout(p, n, LD);
+    double* Cs = smem + L.C; double* Vs = smem + L.V; double* Xc = smem + L.Xc;
+    double* X0 = smem + L.X0; double* M0 = smem + L.M0; double* P00 = smem + L.P00;
+    double* ring = smem + L.ring; double* Minv = smem + L.Minv; double* su = smem + L.su;
+    double* gs = smem + L.gs; double* info = smem + L.inf;
+    unsigned long long* barD = reinterpret_cast<unsigned long long*>(smem + L.bar);      // [3] diagonal tile factorised
+    unsigned long long* barP = barD + 3;                                                 // [3] pivot panel published
+    unsigned long long* barG = barP + 3;                                                 // [3] leverage block ready
+    int* clist = reinterpret_cast<int*>(smem + L.clist);
+    const int PS = L.PS;
+
+    // ---- found sites, Pi_0^{-T}, candidate list and candidate sites (coordinate-major; the padding columns repeat the
+    // centre: finite, never a pivot)
     {
-        const int q4 = MCa >> 2;
-        const double* Cg = pw + g.pw_C; const double* Vg = pw + g.pw_V; const double* Xg = pw + g.pw_Xc;
-        for (int e = tid; e < (2 * p + n) * q4; e += nt) {
-            const int r = e / q4, i4 = (e % q4) * 4;
-            const double* src = (r < p) ? Cg + (size_t)r * MC : ((r < 2 * p) ? Vg + (size_t)(r - p) * MC : Xg + (size_t)(r - 2 * p) * MC);
-            double* dst = (r < p) ? Cs + r * MC : ((r < 2 * p) ? Vs + (r - p) * MC : Xc + (r - 2 * p) * MC);
-            *reinterpret_cast<double4*>(dst + i4) = *reinterpret_cast<const double4*>(src + i4);
+        const double* sites = P.sites + (size_t)b * P.db_stride * n;
+        const int* found = P.found + (size_t)b * P.found_stride;
+        const int nf_ids = P.n_found[b];
+        const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
+        for (int e = tid; e < p * n; e += nt) {
+            const int i = e / n, k = e % n;
+            X0[e] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
         }
-        for (int i = tid; i < mc; i += nt) clist[i] = reinterpret_cast<const int*>(pw + g.pw_clist)[i];
+        for (int e = tid; e < p * p; e += nt) { const double v = pw[g.pw_M0 + e]; M0[e] = v; if (keep) keep[g.off_M0 + e] = v; }
+        const int* cl = reinterpret_cast<const int*>(pw + g.pw_clist);
+        for (int i = tid; i < mc; i += nt) clist[i] = cl[i];
+        for (int e = tid; e < mc * n; e += nt) {
+            const int i = e / n, k = e % n;
+            Xc[k * LD + i] = sites[(size_t)cl[i] * n + k];
+        }
+        if (tid == 0) for (int q = 0; q < 3; ++q) { mbar_init(&barD[q], 1); mbar_init(&barP[q], nwarps - 1); mbar_init(&barG[q], 1); }
+        __syncthreads();
+        for (int e = tid; e < (MCa - mc) * n; e += nt) { const int i = mc + e / n, k = e % n; Xc[k * LD + i] = X0[k]; }
+        for (int e = tid; e < p * p; e += nt) {
+            const int i = e % p, j = e / p;
+            double r2 = 0.0;
+            for (int k = 0; k < n; ++k) { const double d = X0[i * n + k] - X0[j * n + k]; r2 = fma(d, d, r2); }
+            P00[i + j * p] = rad_phi(P.rf, r2);
+        }
+        __syncthreads();
     }
-    // split-phase barriers of the elimination, one pair per slot of the three-deep ring of pivot blocks:
-    //   barD: the diagonal tile of the block has been factorised (one arrival), barP: the whole pivot panel is published
-    //   (one arrival per warp that is still alive).
-    unsigned long long* barD = reinterpret_cast<unsigned long long*>(red + 64);      // [3]
-    unsigned long long* barP = barD + 3;                                             // [3]
-    if (tid == 0) for (int q = 0; q < 3; ++q) { mbar_init(&barD[q], 1); mbar_init(&barP[q], nwarps); }
+    SCHUR_STAMP(100);
+    // ---- panels: C = Pi_0^{-T} pi~ (Lagrange coefficients) and B = Phi(S0, candidates), one (row, 4 candidates) task per thread
+    for (int t = tid; t < p * TRa; t += nt) {
+        const int r = t / TRa, i4 = (t % TRa) * 4;
+        double c0 = M0[r], c1 = c0, c2 = c0, c3 = c0;            // pi~[0] = 1
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double4 x = *reinterpret_cast<const double4*>(Xc + k * LD + i4);
+            if (k + 1 < p) {
+                const double mv = M0[r + (k + 1) * p] * inv_s, xc = X0[k];
+                c0 = fma(mv, x.x - xc, c0); c1 = fma(mv, x.y - xc, c1); c2 = fma(mv, x.z - xc, c2); c3 = fma(mv, x.w - xc, c3);
+            }
+            const double xr = X0[r * n + k];
+            double e_;
+            e_ = x.x - xr; d0 = fma(e_, e_, d0); e_ = x.y - xr; d1 = fma(e_, e_, d1);
+            e_ = x.z - xr; d2 = fma(e_, e_, d2); e_ = x.w - xr; d3 = fma(e_, e_, d3);
+        }
+        *reinterpret_cast<double4*>(Cs + r * LD + i4) = make_double4(c0, c1, c2, c3);
+        *reinterpret_cast<double4*>(Vs + r * LD + i4) = make_double4(rad_phi(P.rf, d0), rad_phi(P.rf, d1), rad_phi(P.rf, d2), rad_phi(P.rf, d3));
+        if (keep) *reinterpret_cast<double4*>(keep + g.off_C + (size_t)r * MC + i4) = make_double4(c0, c1, c2, c3);
+    }
     __syncthreads();
+    // ---- U = B - Phi00 C (kept for the build), V = B - Phi00 C / 2 (in place of B)
+    for (int t = tid; t < p * TRa; t += nt) {
+        const int r = t / TRa, i4 = (t % TRa) * 4;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int c = 0; c < p; ++c) {
+            const double pv = P00[r + c * p];
+            const double4 cc = *reinterpret_cast<const double4*>(Cs + c * LD + i4);
+            s0 = fma(pv, cc.x, s0); s1 = fma(pv, cc.y, s1); s2 = fma(pv, cc.z, s2); s3 = fma(pv, cc.w, s3);
+        }
+        const double4 bb = *reinterpret_cast<const double4*>(Vs + r * LD + i4);
+        if (keep) *reinterpret_cast<double4*>(keep + g.off_U + (size_t)r * MC + i4) = make_double4(bb.x - s0, bb.y - s1, bb.z - s2, bb.w - s3);
+        *reinterpret_cast<double4*>(Vs + r * LD + i4) = make_double4(fma(-0.5, s0, bb.x), fma(-0.5, s1, bb.y), fma(-0.5, s2, bb.z), fma(-0.5, s3, bb.w));
+    }
+    __syncthreads();                                // X0, M0, P00 are dead from here on
 
     SCHUR_STAMP(7);
-    // ---- tiles: thread t owns tile (I, K), I >= K, of A and of W.  Tiles are numbered column by column from the LAST tile
+    // ---- tiles: thread t owns tile (I, K), I >= K, of A.  Tiles are numbered column by column from the LAST tile
     // column, so the tiles that are still live at pivot j (K >= j / 4) are always a prefix of the thread block.
+    const bool lev_warp = warp == nwarps - 1;
     int tI = 0, tK = 0;
     const int ntl = schur_tiles(TRa);
-    const bool has_tile = tid < ntl;
+    const bool has_tile = tid < ntl;                // ntl <= nt - 32: never a thread of the leverage warp
     if (has_tile) {
         int s_ = 0;
         while (((s_ + 1) * (s_ + 2)) / 2 <= tid) ++s_;
         tK = TRa - 1 - s_; tI = tK + (tid - (s_ * (s_ + 1)) / 2);
     }
-    double A[4][4], W[4][4];
+    double A[4][4];
     if (has_tile) {
         const double* xi = Xc + 4 * tI; const double* xk = Xc + 4 * tK;
 #pragma unroll
@@ -370,8 +468,8 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
 #pragma unroll
             for (int c = 0; c < 4; ++c) A[a][c] = 0.0;
         for (int k = 0; k < n; ++k) {
-            const double4 vi = *reinterpret_cast<const double4*>(xi + k * MC);
-            const double4 vk = *reinterpret_cast<const double4*>(xk + k * MC);
+            const double4 vi = *reinterpret_cast<const double4*>(xi + k * LD);
+            const double4 vk = *reinterpret_cast<const double4*>(xk + k * LD);
             const double ri[4] = {vi.x, vi.y, vi.z, vi.w}, rk[4] = {vk.x, vk.y, vk.z, vk.w};
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -381,11 +479,11 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { A[a][c] = rad_phi(P.rf, A[a][c]); W[a][c] = (tI == tK && a == c) ? 1.0 : 0.0; }
+            for (int c = 0; c < 4; ++c) A[a][c] = rad_phi(P.rf, A[a][c]);
         const double* ci_ = Cs + 4 * tI; const double* ck_ = Cs + 4 * tK; const double* vi_ = Vs + 4 * tI; const double* vk_ = Vs + 4 * tK;
         for (int r = 0; r < p; ++r) {
-            const double4 a4 = *reinterpret_cast<const double4*>(ci_ + r * MC), b4 = *reinterpret_cast<const double4*>(ck_ + r * MC);
-            const double4 c4 = *reinterpret_cast<const double4*>(vi_ + r * MC), d4 = *reinterpret_cast<const double4*>(vk_ + r * MC);
+            const double4 a4 = *reinterpret_cast<const double4*>(ci_ + r * LD), b4 = *reinterpret_cast<const double4*>(ck_ + r * LD);
+            const double4 c4 = *reinterpret_cast<const double4*>(vi_ + r * LD), d4 = *reinterpret_cast<const double4*>(vk_ + r * LD);
             const double ci[4] = {a4.x, a4.y, a4.z, a4.w}, ck[4] = {b4.x, b4.y, b4.z, b4.w};
             const double vi[4] = {c4.x, c4.y, c4.z, c4.w}, vk[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -394,40 +492,110 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
                 for (int c = 0; c < 4; ++c) {
                     A[a][c] = fma(-ci[a], vk[c], A[a][c]);
                     A[a][c] = fma(-vi[a], ck[c], A[a][c]);
-                    W[a][c] = fma(ci[a], ck[c], W[a][c]);
                 }
         }
+    } else if (lev_warp) {
+        for (int e = lane; e < p * PS; e += 32) Minv[e] = (e / PS == e % PS) ? 1.0 : 0.0;      // no candidate accepted yet: M = I
+        for (int e = lane; e < 4 * (PS - 1); e += 32) su[e] = 0.0;
     }
+    __syncthreads();                                // V, Xc are dead from here on: the ring of pivot panels takes their place
     SCHUR_STAMP(4);
+
+    const double thr = P.chol_thr;
+    const int cap = min(max_points - N0, P.r4_stride);       // RbfModel.jl:402
+
+    if (lev_warp) {
+        // ---- leverage warp.  Block K: (a) downdate M by the candidates accepted in block K - 1 (multipliers from the diagonal-tile
+        // thread), (b) U = M C_J, (c) G = I + C_J' U  -> diagonal-tile thread.  Lane l owns rows l, l + 32, .. of M.
+        double U4[RPL][4];
+        for (int K = 0; K < TRa; ++K) {
+            const int slot = K % 3, j0 = 4 * K;
+            bool upd = false;
+            double av[RPL][4];
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) { av[rr][0] = 0.0; av[rr][1] = 0.0; av[rr][2] = 0.0; av[rr][3] = 0.0; }
+            if (K > 0) {
+                const int ps = (K - 1) % 3;
+                mbar_wait(&barD[ps], (unsigned)(((K - 1) / 3) & 1));
+                const double* pin = info + ps * 28;
+                if (pin[13] != 0.0) break;          // capacity reached: no further leverage is needed
+                if ((int)pin[12] != 0) {
+                    upd = true;
+                    const double4 rw = *reinterpret_cast<const double4*>(pin + 8);
+                    const double l10 = pin[14], l20 = pin[15], l21 = pin[16], l30 = pin[17], l31 = pin[18], l32 = pin[19];
+#pragma unroll
+                    for (int rr = 0; rr < RPL; ++rr) {
+                        const int r = lane + 32 * rr;
+                        const double u0 = U4[rr][0];
+                        const double u1 = fma(-u0, l10, U4[rr][1]);
+                        const double u2 = fma(-u1, l21, fma(-u0, l20, U4[rr][2]));
+                        const double u3 = fma(-u2, l32, fma(-u1, l31, fma(-u0, l30, U4[rr][3])));
+                        if (r < p) *reinterpret_cast<double4*>(su + 4 * r) = make_double4(u0, u1, u2, u3);
+                        av[rr][0] = rw.x * u0; av[rr][1] = rw.y * u1; av[rr][2] = rw.z * u2; av[rr][3] = rw.w * u3;
+                    }
+                    __syncwarp();
+                }
+            }
+            lev_pass<RPL>(Minv, su, Cs + j0, LD, PS, p, lane, upd, av, U4);
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) {
+                const int r = lane + 32 * rr;
+                if (r < p) {
+                    const double4 cr = *reinterpret_cast<const double4*>(Cs + r * LD + j0);
+                    v[0] = fma(cr.x, U4[rr][0], v[0]);
+                    v[1] = fma(cr.y, U4[rr][0], v[1]); v[2] = fma(cr.y, U4[rr][1], v[2]);
+                    v[3] = fma(cr.z, U4[rr][0], v[3]); v[4] = fma(cr.z, U4[rr][1], v[4]); v[5] = fma(cr.z, U4[rr][2], v[5]);
+                    v[6] = fma(cr.w, U4[rr][0], v[6]); v[7] = fma(cr.w, U4[rr][1], v[7]); v[8] = fma(cr.w, U4[rr][2], v[8]);
+                    v[9] = fma(cr.w, U4[rr][3], v[9]);
+                }
+            }
+            const double tot = warp_sum16(v, lane);
+            const int idx = lane >> 1;              // value held by this lane (pairs of lanes hold the same one)
+            if ((lane & 1) == 0 && idx < 10) gs[slot * 16 + idx] = tot + ((idx == 0 || idx == 2 || idx == 5 || idx == 9) ? 1.0 : 0.0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&barG[slot]);
+        }
+        return;
+    }
+
     // ---- blocked right-looking elimination over the candidates in ascending id order, four pivots (one tile column) per block.
-    //   1. the thread that owns the diagonal tile (K, K) runs the four pivot tests and eliminations inside its registers
-    //      (RbfModel.jl:447-452; a rejected pivot gets a zero multiplier, so nothing downstream branches on it) -> barD
+    //   1. the thread that owns the diagonal tile (K, K) runs the four pivot tests and eliminations inside its registers, on its
+    //      tile of A and on the leverage block G (RbfModel.jl:447-452; a rejected pivot gets a zero multiplier, so nothing
+    //      downstream branches on it) -> barD
     //   2. the other tiles of tile column K finish their four pivot columns against the diagonal tile's multipliers, publish
     //      them (raw and scaled by 1/d^2) and stream the Cholesky factor rows out for mrbf_build_prepared_dev        -> barP
     //   3. every tile to the right applies the rank-4 update.  Tile column K + 1 sits in the lowest live thread ids and its
     //      diagonal tile starts step 1 of the next block as soon as its own update is done; warps without live tiles leave.
-    const double thr = P.chol_thr;
-    const int cap = min(max_points - N0, P.r4_stride);       // RbfModel.jl:402
     int nacc = 0, nacc_diag = -1;
     const int my_last = __shfl_sync(0xffffffffu, has_tile ? tK : -1, 0);             // lane 0 holds this warp's largest tile column
     for (int K = 0; K < TRa; ++K) {
         const int slot = K % 3;
         const unsigned par = (unsigned)((K / 3) & 1);
         const int j0 = 4 * K;
-        double* cA = ring + (size_t)slot * 16 * MC; double* cAs = cA + 4 * MC; double* cW = cAs + 4 * MC; double* cWs = cW + 4 * MC;
-        double* inf = info + slot * 24;              // [0..3] 1/d, [4..7] 1/d^2 (0 if rejected), [8..11] 1/(1+lev) (0 if rejected), [12] mask, [13] stop
+        double* cA = ring + (size_t)slot * 8 * LD; double* cAs = cA + 4 * LD;
+        double* inf = info + slot * 28;              // [4..7] 1/d^2 (0 if rejected), [8..11] 1/(1+lev) (0 if rejected), [12] mask, [13] stop,
+                                                     // [14..19] multipliers of the leverage block, [20..25] multipliers of A's diagonal tile
         if (K < 40) SCHUR_STAMP(8 + 2 * K);
         if (has_tile && tK == K && tI == K) {        // ---- 1. diagonal tile
             if (K < 25) SCHUR_STAMPX(128 + 8 * K);
+            mbar_wait(&barG[slot], par);
+            double W[4][4];
+            {
+                const double* gq = gs + slot * 16;
+                W[0][0] = gq[0]; W[1][0] = gq[1]; W[1][1] = gq[2]; W[2][0] = gq[3]; W[2][1] = gq[4]; W[2][2] = gq[5];
+                W[3][0] = gq[6]; W[3][1] = gq[7]; W[3][2] = gq[8]; W[3][3] = gq[9];
+            }
             int mask = 0, na = nacc;
-            double rdv[4], rav[4], rwv[4];
+            double rav[4], rwv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double dA = A[q][q], dW = W[q][q];
-                const double rw = fast_rcp(dW), rs = fast_rsqrt(fmax(dA, 1e-300));      // independent: their latencies overlap
+                const double rw = fast_rcp(dW), ra = fast_rcp(fmax(dA, 1e-300));        // independent: their latencies overlap
                 const bool ok = (j0 + q < mc) && (na < cap) && (dA * rw > thr);      // d^2 / (1 + lev) == sigma - ||L^-1 v||^2
-                const double rd = ok ? rs : 0.0;
-                rdv[q] = rd; rav[q] = rd * rd; rwv[q] = ok ? rw : 0.0;
+                rav[q] = ok ? ra : 0.0; rwv[q] = ok ? rw : 0.0;
                 if (ok) { mask |= 1 << q; na += 1; }
 #pragma unroll
                 for (int r = q + 1; r < 4; ++r)
@@ -438,19 +606,14 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
                     }
             }
             if (K < 25) SCHUR_STAMPX(128 + 8 * K + 1);
-            *reinterpret_cast<double4*>(inf) = make_double4(rdv[0], rdv[1], rdv[2], rdv[3]);
+            // what the panel tiles and the leverage warp need: 1/d^2, the accept mask, the multipliers of the diagonal blocks
             *reinterpret_cast<double4*>(inf + 4) = make_double4(rav[0], rav[1], rav[2], rav[3]);
             *reinterpret_cast<double4*>(inf + 8) = make_double4(rwv[0], rwv[1], rwv[2], rwv[3]);
             *reinterpret_cast<double2*>(inf + 12) = make_double2((double)mask, (na >= cap || j0 + 4 >= mc) ? 1.0 : 0.0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {           // rows j0..j0+3 of the four pivot columns: zeros on and above the diagonal
-                const double a1 = (q < 1) ? A[1][q] : 0.0, a2 = (q < 2) ? A[2][q] : 0.0, a3 = (q < 3) ? A[3][q] : 0.0;
-                const double w1 = (q < 1) ? W[1][q] : 0.0, w2 = (q < 2) ? W[2][q] : 0.0, w3 = (q < 3) ? W[3][q] : 0.0;
-                *reinterpret_cast<double4*>(cA + q * MC + j0) = make_double4(0.0, a1, a2, a3);
-                *reinterpret_cast<double4*>(cAs + q * MC + j0) = make_double4(0.0, a1 * rav[q], a2 * rav[q], a3 * rav[q]);
-                *reinterpret_cast<double4*>(cW + q * MC + j0) = make_double4(0.0, w1, w2, w3);
-                *reinterpret_cast<double4*>(cWs + q * MC + j0) = make_double4(0.0, w1 * rwv[q], w2 * rwv[q], w3 * rwv[q]);
-            }
+            *reinterpret_cast<double2*>(inf + 14) = make_double2(W[1][0] * rwv[0], W[2][0] * rwv[0]);
+            *reinterpret_cast<double4*>(inf + 16) = make_double4(W[2][1] * rwv[1], W[3][0] * rwv[0], W[3][1] * rwv[1], W[3][2] * rwv[2]);
+            *reinterpret_cast<double4*>(inf + 20) = make_double4(A[1][0] * rav[0], A[2][0] * rav[0], A[2][1] * rav[1], A[3][0] * rav[0]);
+            *reinterpret_cast<double2*>(inf + 24) = make_double2(A[3][1] * rav[1], A[3][2] * rav[2]);
             nacc_diag = na;
             mbar_arrive(&barD[slot]);
             if (K < 25) SCHUR_STAMPX(128 + 8 * K + 2);
@@ -459,28 +622,22 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
         if (has_tile && tK == K && tI > K) {         // ---- 2. the rest of the pivot panel
             mbar_wait(&barD[slot], par);
             if (K < 25 && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 3);
-            const int mask = (int)inf[12];
+            {
+                const double4 m4 = *reinterpret_cast<const double4*>(inf + 20); const double2 m2 = *reinterpret_cast<const double2*>(inf + 24);
+                const double l10 = m4.x, l20 = m4.y, l21 = m4.z, l30 = m4.w, l31 = m2.x, l32 = m2.y;
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int jj = q + 1; jj < 4; ++jj) {
-                    const double la = cAs[q * MC + j0 + jj], lw = cWs[q * MC + j0 + jj];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) { A[a][jj] = fma(-A[a][q], la, A[a][jj]); W[a][jj] = fma(-W[a][q], lw, W[a][jj]); }
+                for (int a = 0; a < 4; ++a) {
+                    A[a][1] = fma(-A[a][0], l10, A[a][1]);
+                    A[a][2] = fma(-A[a][1], l21, fma(-A[a][0], l20, A[a][2]));
+                    A[a][3] = fma(-A[a][2], l32, fma(-A[a][1], l31, fma(-A[a][0], l30, A[a][3])));
                 }
-            int q_out = nacc;
+            }
+            const double4 ra4 = *reinterpret_cast<const double4*>(inf + 4);
+            const double ra[4] = {ra4.x, ra4.y, ra4.z, ra4.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const double rd = inf[q], ra = inf[4 + q], rw = inf[8 + q];
-                *reinterpret_cast<double4*>(cA + q * MC + 4 * tI) = make_double4(A[0][q], A[1][q], A[2][q], A[3][q]);
-                *reinterpret_cast<double4*>(cAs + q * MC + 4 * tI) = make_double4(A[0][q] * ra, A[1][q] * ra, A[2][q] * ra, A[3][q] * ra);
-                *reinterpret_cast<double4*>(cW + q * MC + 4 * tI) = make_double4(W[0][q], W[1][q], W[2][q], W[3][q]);
-                *reinterpret_cast<double4*>(cWs + q * MC + 4 * tI) = make_double4(W[0][q] * rw, W[1][q] * rw, W[2][q] * rw, W[3][q] * rw);
-                if (mask & (1 << q)) {
-                    if (keep) *reinterpret_cast<double4*>(keep + g.off_L + (size_t)q_out * MC + 4 * tI) =
-                                  make_double4(A[0][q] * rd, A[1][q] * rd, A[2][q] * rd, A[3][q] * rd);
-                    q_out += 1;
-                }
+                *reinterpret_cast<double4*>(cA + q * LD + 4 * tI) = make_double4(A[0][q], A[1][q], A[2][q], A[3][q]);
+                *reinterpret_cast<double4*>(cAs + q * LD + 4 * tI) = make_double4(A[0][q] * ra[q], A[1][q] * ra[q], A[2][q] * ra[q], A[3][q] * ra[q]);
             }
         }
         if (K < 25 && has_tile && tK == K && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 4);
@@ -489,6 +646,16 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
         if (lane == 0) {
             if (!leaving) mbar_arrive(&barP[slot]);
             else { mbar_arrive_drop(&barP[slot]); mbar_arrive_drop(&barP[(slot + 1) % 3]); mbar_arrive_drop(&barP[(slot + 2) % 3]); }
+        }
+        if (keep && has_tile && tK == K && tI > K) { // factor rows of the panel tiles (off the critical path)
+            const int mask = (int)inf[12];
+            int q_out = nacc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (mask & (1 << q)) {
+                const double rd = sqrt(inf[4 + q]);      // 1/d from 1/d^2: the factor rows are scaled off the pivot chain
+                *reinterpret_cast<double4*>(keep + g.off_L + (size_t)q_out * MC + 4 * tI) = make_double4(A[0][q] * rd, A[1][q] * rd, A[2][q] * rd, A[3][q] * rd);
+                q_out += 1;
+            }
         }
         if (has_tile && tK == K && tI == K) {        // ids, positions and the diagonal block of the Cholesky factor (off the critical path)
             int q_out = nacc;
@@ -499,7 +666,7 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
                 if (keep) {
                     keep[g.off_acc + q_out] = (double)(j0 + q);
                     double* Lc = keep + g.off_L + (size_t)q_out * MC + j0;
-                    const double rd = inf[q];
+                    const double rd = sqrt(inf[4 + q]);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) if (r >= q && j0 + r < mc) Lc[r] = A[r][q] * rd;
                 }
@@ -514,22 +681,12 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
         if (has_tile && tK > K) {                    // ---- 3. rank-4 update
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                {
-                    const double4 i4 = *reinterpret_cast<const double4*>(cAs + q * MC + 4 * tI), k4 = *reinterpret_cast<const double4*>(cA + q * MC + 4 * tK);
-                    const double ai[4] = {i4.x, i4.y, i4.z, i4.w}, ak[4] = {k4.x, k4.y, k4.z, k4.w};
+                const double4 i4 = *reinterpret_cast<const double4*>(cAs + q * LD + 4 * tI), k4 = *reinterpret_cast<const double4*>(cA + q * LD + 4 * tK);
+                const double ai[4] = {i4.x, i4.y, i4.z, i4.w}, ak[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) A[a][c] = fma(-ai[a], ak[c], A[a][c]);
-                }
-                {
-                    const double4 i4 = *reinterpret_cast<const double4*>(cWs + q * MC + 4 * tI), k4 = *reinterpret_cast<const double4*>(cW + q * MC + 4 * tK);
-                    const double wi[4] = {i4.x, i4.y, i4.z, i4.w}, wk[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) W[a][c] = fma(-wi[a], wk[c], W[a][c]);
-                }
+                    for (int c = 0; c < 4; ++c) A[a][c] = fma(-ai[a], ak[c], A[a][c]);
             }
         }
     }
@@ -546,22 +703,41 @@ __global__ void __launch_bounds__(SMALL ? 352 : 544, 1) round4_schur_kernel(Roun
     }
 }
 
-cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaStream_t s) {
-    const size_t psmem = g.ps_doubles * sizeof(double), smem = g.smem_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(round4_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(round4_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(round4_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    round4_panels_kernel<<<P.B, 256, psmem, s>>>(P, g);
-    if (g.two_variants) {
-        round4_schur_kernel<true><<<P.B, 352, smem, s>>>(P, g);
-        round4_schur_kernel<false><<<P.B, g.nthreads, smem, s>>>(P, g);
-    } else if (g.nthreads <= 352) {
-        round4_schur_kernel<true><<<P.B, g.nthreads, smem, s>>>(P, g);
-    } else {
-        round4_schur_kernel<false><<<P.B, g.nthreads, smem, s>>>(P, g);
+template <bool SMALL>
+static cudaError_t launch_elim(const Round4Params& P, const SchurGeom& g, int nthreads, size_t smem, int rpl, cudaStream_t s) {
+    cudaError_t e;
+#define MRBF_ELIM_CASE(R)                                                                                                          \
+    case R:                                                                                                                        \
+        e = cudaFuncSetAttribute(round4_elim_kernel<SMALL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        if (e != cudaSuccess) return e;                                                                                            \
+        round4_elim_kernel<SMALL, R><<<P.B, nthreads, smem, s>>>(P, g);                                                            \
+        break;
+    switch (rpl) {
+        MRBF_ELIM_CASE(1)
+        MRBF_ELIM_CASE(2)
+        MRBF_ELIM_CASE(3)
+    default: return cudaErrorInvalidValue;
     }
+#undef MRBF_ELIM_CASE
     return cudaGetLastError();
+}
+
+cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaStream_t s) {
+    const int p = poly_dim(P.n, P.cfg.polynomial_degree);
+    const int rpl = (p + 31) / 32;
+    const size_t psmem = g.ps_doubles * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(round4_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    if (e != cudaSuccess) return e;
+    round4_prep_kernel<<<P.B, 256, psmem, s>>>(P, g);
+    if (g.two_variants) {
+        e = launch_elim<true>(P, g, 384, g.smem_small * sizeof(double), rpl, s);
+        if (e == cudaSuccess) e = launch_elim<false>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
+    } else if (g.nthreads <= 384) {
+        e = launch_elim<true>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
+    } else {
+        e = launch_elim<false>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
+    }
+    return e;
 }
 
 }  // namespace mrbf

@@ -92,14 +92,14 @@ def main():
         rec = dict(ret=np.full((len(x0s), T), -1), it_stat=np.full((len(x0s), T), -1), x_index=np.zeros((len(x0s), T), int),
                    n_db=np.zeros((len(x0s), T), int), delta=np.zeros((len(x0s), T)), x=np.zeros((len(x0s), T, n)), fx=np.zeros((len(x0s), T, 2)),
                    rho=np.full((len(x0s), T), np.nan), omega=np.full((len(x0s), T), np.nan), n_train=np.zeros((len(x0s), T), int),
-                   knife=np.zeros((len(x0s), T), bool), n_iter=np.zeros(len(x0s), int))
+                   knife=np.zeros((len(x0s), T), bool), wall_tie=np.zeros((len(x0s), T), bool), n_iter=np.zeros(len(x0s), int))
         for b, x0 in enumerate(x0s):
             run = IO.optimize(f, x0, np.full(n, -np.inf), np.full(n, np.inf), O.RbfConfig(kernel="cubic"), IO.AlgoConfig(max_iter=max_iter))
             rec["n_iter"][b] = len(run.records)
             for t, r in enumerate(run.records):
                 rec["ret"][b, t], rec["it_stat"][b, t], rec["x_index"][b, t], rec["n_db"][b, t] = r.ret_code, r.it_stat, r.x_index, r.n_db
                 rec["delta"][b, t], rec["x"][b, t], rec["fx"][b, t], rec["rho"][b, t], rec["omega"][b, t] = r.delta, r.x, r.fx, r.rho, r.omega
-                rec["n_train"][b, t], rec["knife"][b, t] = len(r.training_ids), r.knife
+                rec["n_train"][b, t], rec["knife"][b, t], rec["wall_tie"][b, t] = len(r.training_ids), r.knife, r.wall_tie
         np.savez(os.path.join(OUT, name + ".npz"), kind="trajectory", x0=x0s, max_iter=max_iter, **rec)
     print("wrote", len(SELECT) + len(BUILD) + len(DESCENT) + len(TRAJ), "fixtures to", OUT)
 

@@ -99,6 +99,7 @@ class IterRecord:
     training_ids: List[int] = field(default_factory=list)
     fully_linear: bool = False
     knife: bool = False          # some threshold decision on the way here was closer than rounding accuracy
+    wall_tie: bool = False       # a model update of THIS iteration placed a site by comparing two equal wall distances (sign = rounding noise)
 
 
 class Run:
@@ -122,6 +123,9 @@ class Run:
         self.iter_counter, self.it_stat, self.ret_code = 1, ACCEPTABLE, CONTINUE
         self.records: List[IterRecord] = []
         self.knife = False
+        # a round-3 / improvement step in a box that is symmetric about the iterate (unbounded problems): `intersect_box(:absmax)`
+        # compared two equal wall distances, so the SIGN of the new site follows the last bits of x and of the direction
+        self.wall_tie = False
         self._update(True)                                                   # init_surrogates: prepare_init_model => ensure_fully_linear
 
     # ------------------------------------------------------------------ surrogates
@@ -131,6 +135,7 @@ class Run:
     def _update(self, ensure_fully_linear: bool):
         """update_surrogates!, SurrogateContainer.jl:339-390 (one group)."""
         tf, t4 = O.FilterTrace(), O.Round4Trace()
+        O.WALL_TIES.clear()
         self.meta = O.prepare_update_model(self.meta, self.cfg, self.db, self.x, self.x_index, self.delta, self.ac.delta_max,
                                            self.glb, self.gub, ensure_fully_linear=ensure_fully_linear,
                                            num_objf_evals=self.num_evals, algo_max_evals=self.ac.max_evals, trace=tf, trace4=t4,
@@ -138,11 +143,14 @@ class Run:
         # decisions taken by less than rounding accuracy (pivot tests of the filter, tau^2 of round 4): a second implementation
         # may legitimately decide the other way, so a comparison has to stop at this state
         self.knife = self.knife or tf.knife_edge() or any(abs(v) < 1e-12 for v in t4.tau2)
+        self.wall_tie = self.wall_tie or bool(O.WALL_TIES)
         self._eval_missing()
         self.model = O.update_model(self.meta, self.cfg, self.db)
 
     def _improve(self):
+        O.WALL_TIES.clear()
         self.meta = O.prepare_improve_model(self.meta, self.cfg, self.db, self.x, self.delta, self.glb, self.gub)
+        self.wall_tie = self.wall_tie or bool(O.WALL_TIES)
         self._eval_missing()
         self.model = O.update_model(self.meta, self.cfg, self.db)
 
@@ -279,7 +287,8 @@ class Run:
     def _record(self, ret, stat, omega=math.nan, rho=math.nan, steplength=math.nan, loops=0):
         self.ret_code, self.it_stat = ret, stat
         r = IterRecord(self.iter_counter, ret, stat, self.x.copy(), self.fx.copy(), self.x_index, self.delta, self.db.num_entries,
-                       self.num_evals, omega, rho, steplength, loops, list(self.meta.collect_indices()), self.meta.fully_linear, self.knife)
+                       self.num_evals, omega, rho, steplength, loops, list(self.meta.collect_indices()), self.meta.fully_linear, self.knife, self.wall_tie)
+        self.wall_tie = False
         self.records.append(r)
         self.iter_counter += 1
         return r

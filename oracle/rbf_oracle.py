@@ -255,6 +255,9 @@ def _intersect_bound_vec(x, b, d, d_nz, sense):
     return np.concatenate((sig, on))
 
 
+WALL_TIES: list = []      # (s_pos, s_neg) of every intersect_box call whose two wall distances agreed to 1e-9 (knife-edge sign); tests clear it
+
+
 def intersect_box_absmax(x, d, lb, ub) -> float:
     """intersect_box(...; return_vals=:absmax) -> _intersect_bounds, utilities.jl:156-221, 285-287."""
     if not np.any(d != 0):
@@ -268,6 +271,8 @@ def intersect_box_absmax(x, d, lb, ub) -> float:
     neg = sig[~(sig >= 0)]
     s_pos = float(pos.min()) if pos.size else 0.0
     s_neg = float(neg.max()) if neg.size else 0.0
+    if pos.size and neg.size and abs(abs(s_pos) - abs(s_neg)) <= 1e-9 * max(abs(s_pos), abs(s_neg)):
+        WALL_TIES.append((s_pos, s_neg))                      # the sign of the step is decided by the last bits of x, d (test hook)
     return s_pos if abs(s_pos) >= abs(s_neg) else s_neg       # positive wins ties, :212-217
 
 

@@ -155,6 +155,11 @@ def test_cuda_lockstep_matches_golden_trajectory(path):
                 # the model values -- the fixture (HiGHS direction, NumPy model) and the GPU path then accept different step lengths.
                 # tests/test_gpu_lockstep.py compares those states with the direction injected; here the comparison stops.
                 break
+            if g["wall_tie"][b, t] and np.abs(tr["x"][b] - g["x"][b, t]).max() > 1e-8:
+                # unbounded problem: the round-3 step of this iteration was placed by `intersect_box(:absmax)` comparing two EQUAL wall
+                # distances ((x + D) - x against x - (x - D)), so the side the new site lands on follows the last bits of the iterate --
+                # rounding noise in the reference too.  The other side gives another (valid) model; the comparison of this run stops.
+                break
             assert (int(tr["ret"][b]), int(tr["it_stat"][b]), int(tr["x_index"][b]), int(tr["n_db"][b])) == \
                    tuple(int(g[k][b, t]) for k in ("ret", "it_stat", "x_index", "n_db")), (b, t)
             assert abs(tr["delta"][b] - g["delta"][b, t]) <= 1e-12 * g["delta"][b, t]
