@@ -239,22 +239,32 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             ENSURE(ctx->ws[13], (size_t)B * geom.pw_doubles * sizeof(double));
             R.panel_ws = (double*)ctx->ws[13].p;
             const bool dbg = getenv("MRBF_DEBUG_CLOCK") != nullptr;
-            if (dbg) { ENSURE(ctx->ws[12], 512 * sizeof(long long)); CK(cudaMemsetAsync(ctx->ws[12].p, 0, 512 * sizeof(long long), ctx->stream)); R.dbg_clock = (long long*)ctx->ws[12].p; }
+            if (dbg) { ENSURE(ctx->ws[12], 1024 * sizeof(long long)); CK(cudaMemsetAsync(ctx->ws[12].p, 0, 1024 * sizeof(long long), ctx->stream)); R.dbg_clock = (long long*)ctx->ws[12].p; }
             {
                 Timed t_(ctx, 1);
                 CK(launch_round4_schur(R, geom, ctx->stream));
             }
             if (dbg) {
-                long long h[512];
+                long long h[1024];
                 CK(cudaMemcpyAsync(h, ctx->ws[12].p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
                 fprintf(stderr, "[mrbf clock] prep: setup %lld GJ %lld | elim: load %lld panels %lld tiles %lld elim %lld | blocks (start->panel published):", h[1] - h[0],
                         h[2] - h[1], h[100] - h[6], h[7] - h[100], h[4] - h[7], h[5] - h[4]);
                 for (int K = 0; K < 40 && h[8 + 2 * K]; ++K) fprintf(stderr, " %lld/%lld", h[8 + 2 * K] - h[4], h[9 + 2 * K] ? h[9 + 2 * K] - h[8 + 2 * K] : -1LL);
-                fprintf(stderr, "\n[mrbf clock] per block: diag pivots / publish+arrive / panel wakes after arrive / panel work:");
+                fprintf(stderr, "\n[mrbf clock] per block: diag pivots / publish+arrive / panel wakes after arrive / panel work / next diag tile: panel published / updated / starts:");
                 for (int K = 0; K < 25 && h[128 + 8 * K]; ++K)
-                    fprintf(stderr, " %lld/%lld/%lld/%lld", h[129 + 8 * K] - h[128 + 8 * K], h[130 + 8 * K] - h[129 + 8 * K], h[131 + 8 * K] - h[130 + 8 * K],
-                            h[132 + 8 * K] - h[131 + 8 * K]);
+                    fprintf(stderr, " %lld/%lld/%lld/%lld/%lld/%lld/%lld", h[129 + 8 * K] - h[128 + 8 * K], h[130 + 8 * K] - h[129 + 8 * K], h[131 + 8 * K] - h[130 + 8 * K],
+                            h[132 + 8 * K] - h[131 + 8 * K], h[133 + 8 * K] - h[132 + 8 * K], h[134 + 8 * K] - h[133 + 8 * K], h[136 + 8 * K] - h[134 + 8 * K]);
+                fprintf(stderr, "\n[mrbf clock] arrival of every warp at the panel barrier, cycles after the diagonal tile's hand-over:");
+                for (int K = 1; K < 25 && h[128 + 8 * K]; ++K) {
+                    fprintf(stderr, " [K=%d", K);
+                    for (int w = 0; w < 12; ++w) if (h[600 + 12 * K + w]) fprintf(stderr, " %lld", h[600 + 12 * K + w] - h[130 + 8 * K]);
+                    fprintf(stderr, "]");
+                }
+                fprintf(stderr, "\n[mrbf clock] leverage warp per block: after diag(K-1) -> u vectors / pass over M / reduce + hand-over; lead over the diagonal tile's start:");
+                for (int K = 1; K < 25 && h[340 + 4 * K]; ++K)
+                    fprintf(stderr, " %lld/%lld/%lld;%lld", h[341 + 4 * K] - h[340 + 4 * K], h[342 + 4 * K] - h[341 + 4 * K], h[343 + 4 * K] - h[342 + 4 * K],
+                            h[128 + 8 * K] - h[343 + 4 * K]);
                 fprintf(stderr, "\n");
             }
         } else {

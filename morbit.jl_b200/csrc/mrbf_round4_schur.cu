@@ -35,6 +35,7 @@
 // database is larger than 128 sites or whose panels do not fit in shared memory use round4_block_kernel instead.
 #include "mrbf_common.cuh"
 #include "mrbf_kernels.h"
+#include <stdlib.h>
 
 namespace mrbf {
 
@@ -297,6 +298,28 @@ __device__ __forceinline__ double warp_sum16(double (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// Results of pivot block K, written from the published panel (ring slot) by threads that have slack -- never by the warp that
+// carries the pivot chain: ids of the accepted candidates, their positions, and the rows of the Cholesky factor (pivot column / d)
+// for mrbf_build_prepared_dev.  Worker w of nw takes the (column q, tile row I) items w, w + nw, ..
+__device__ __forceinline__ void store_pivot_block(const double* cA, const double* inf, int K, int TRa, int LD, int MC, int nacc0, int* r4,
+                                                  const int* clist, double* keep, size_t off_L, size_t off_acc, int w, int nw) {
+    const int mask = (int)inf[12];
+    if (mask == 0) return;
+    const int j0 = 4 * K, items = keep ? 4 * (TRa - K) : 4;
+    for (int e = w; e < items; e += nw) {
+        const int q = e & 3, I = K + (e >> 2);
+        if (!(mask & (1 << q))) continue;
+        const int q_out = nacc0 + __popc((unsigned)(mask & ((1 << q) - 1)));
+        if (I == K) r4[q_out] = clist[j0 + q] + 1;
+        if (keep) {
+            if (I == K) keep[off_acc + q_out] = (double)(j0 + q);
+            const double rd = sqrt(inf[4 + q]);      // 1/d from 1/d^2
+            const double4 v = *reinterpret_cast<const double4*>(cA + q * LD + 4 * I);
+            *reinterpret_cast<double4*>(keep + off_L + (size_t)q_out * MC + 4 * I) = make_double4(v.x * rd, v.y * rd, v.z * rd, v.w * rd);
+        }
+    }
+}
+
 // One pass of the leverage warp over the rows of M it owns (lane l: rows l, l + 32, ..): downdate  M -= sum_q av_q u_q'  (upd) and
 // U = M C_J, eight columns at a time so that the loads of a group are in flight together.  Columns p .. PS-2 of M are zero padding.
 template <int RPL>
@@ -508,7 +531,8 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         // ---- leverage warp.  Block K: (a) downdate M by the candidates accepted in block K - 1 (multipliers from the diagonal-tile
         // thread), (b) U = M C_J, (c) G = I + C_J' U  -> diagonal-tile thread.  Lane l owns rows l, l + 32, .. of M.
         double U4[RPL][4];
-        for (int K = 0; K < TRa; ++K) {
+        int nacc_l = 0;                              // accepted before block K - 1
+        for (int K = 0; K <= TRa; ++K) {
             const int slot = K % 3, j0 = 4 * K;
             bool upd = false;
             double av[RPL][4];
@@ -517,8 +541,16 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             if (K > 0) {
                 const int ps = (K - 1) % 3;
                 mbar_wait(&barD[ps], (unsigned)(((K - 1) / 3) & 1));
+                if (K < 25 && lane == 0) SCHUR_STAMPX(340 + 4 * K);
                 const double* pin = info + ps * 28;
-                if (pin[13] != 0.0) break;          // capacity reached: no further leverage is needed
+                const bool mine = (schur_tiles(max(TRa - (K - 1) - 2, 0)) >> 5) == 0;      // nobody else writes the results of block K - 1
+                if (pin[13] != 0.0) {               // capacity reached or last block: no further leverage is needed
+                    if (mine) {
+                        mbar_wait(&barP[ps], (unsigned)(((K - 1) / 3) & 1));
+                        store_pivot_block(ring + (size_t)ps * 8 * LD, pin, K - 1, TRa, LD, MC, nacc_l, r4, clist, keep, g.off_L, g.off_acc, lane, 32);
+                    }
+                    break;
+                }
                 if ((int)pin[12] != 0) {
                     upd = true;
                     const double4 rw = *reinterpret_cast<const double4*>(pin + 8);
@@ -536,7 +568,9 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                     __syncwarp();
                 }
             }
+            if (K < 25 && lane == 0) SCHUR_STAMPX(341 + 4 * K);
             lev_pass<RPL>(Minv, su, Cs + j0, LD, PS, p, lane, upd, av, U4);
+            if (K < 25 && lane == 0) SCHUR_STAMPX(342 + 4 * K);
             double v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.0;
@@ -557,6 +591,16 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             if ((lane & 1) == 0 && idx < 10) gs[slot * 16 + idx] = tot + ((idx == 0 || idx == 2 || idx == 5 || idx == 9) ? 1.0 : 0.0);
             __syncwarp();
             if (lane == 0) mbar_arrive(&barG[slot]);
+            if (K < 25 && lane == 0) SCHUR_STAMPX(343 + 4 * K);
+            if (K > 0) {                            // results of block K - 1 (the leverage block of K is on its way: this is idle time)
+                const int ps = (K - 1) % 3;
+                const double* pin = info + ps * 28;
+                if ((schur_tiles(max(TRa - (K - 1) - 2, 0)) >> 5) == 0) {
+                    mbar_wait(&barP[ps], (unsigned)(((K - 1) / 3) & 1));
+                    store_pivot_block(ring + (size_t)ps * 8 * LD, pin, K - 1, TRa, LD, MC, nacc_l, r4, clist, keep, g.off_L, g.off_acc, lane, 32);
+                }
+                nacc_l += __popc((unsigned)(int)pin[12]);
+            }
         }
         return;
     }
@@ -614,6 +658,9 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             *reinterpret_cast<double4*>(inf + 16) = make_double4(W[2][1] * rwv[1], W[3][0] * rwv[0], W[3][1] * rwv[1], W[3][2] * rwv[2]);
             *reinterpret_cast<double4*>(inf + 20) = make_double4(A[1][0] * rav[0], A[2][0] * rav[0], A[2][1] * rav[1], A[3][0] * rav[0]);
             *reinterpret_cast<double2*>(inf + 24) = make_double2(A[3][1] * rav[1], A[3][2] * rav[2]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)             // rows j0..j0+3 of the four pivot columns (zeros above the diagonal) for store_pivot_block
+                *reinterpret_cast<double4*>(cA + q * LD + j0) = make_double4(q <= 0 ? A[0][q] : 0.0, q <= 1 ? A[1][q] : 0.0, q <= 2 ? A[2][q] : 0.0, A[3][q]);
             nacc_diag = na;
             mbar_arrive(&barD[slot]);
             if (K < 25) SCHUR_STAMPX(128 + 8 * K + 2);
@@ -644,41 +691,23 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         __syncwarp();
         const bool leaving = my_last <= K;           // no tile of this warp lies to the right of tile column K
         if (lane == 0) {
+            if (K < 25 && warp < 12) SCHUR_STAMPX(600 + 12 * K + warp);
             if (!leaving) mbar_arrive(&barP[slot]);
             else { mbar_arrive_drop(&barP[slot]); mbar_arrive_drop(&barP[(slot + 1) % 3]); mbar_arrive_drop(&barP[(slot + 2) % 3]); }
-        }
-        if (keep && has_tile && tK == K && tI > K) { // factor rows of the panel tiles (off the critical path)
-            const int mask = (int)inf[12];
-            int q_out = nacc;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (mask & (1 << q)) {
-                const double rd = sqrt(inf[4 + q]);      // 1/d from 1/d^2: the factor rows are scaled off the pivot chain
-                *reinterpret_cast<double4*>(keep + g.off_L + (size_t)q_out * MC + 4 * tI) = make_double4(A[0][q] * rd, A[1][q] * rd, A[2][q] * rd, A[3][q] * rd);
-                q_out += 1;
-            }
-        }
-        if (has_tile && tK == K && tI == K) {        // ids, positions and the diagonal block of the Cholesky factor (off the critical path)
-            int q_out = nacc;
-            const int dmask = (int)inf[12];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (dmask & (1 << q)) {
-                r4[q_out] = clist[j0 + q] + 1;
-                if (keep) {
-                    keep[g.off_acc + q_out] = (double)(j0 + q);
-                    double* Lc = keep + g.off_L + (size_t)q_out * MC + j0;
-                    const double rd = sqrt(inf[4 + q]);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) if (r >= q && j0 + r < mc) Lc[r] = A[r][q] * rd;
-                }
-                q_out += 1;
-            }
         }
         if (leaving) break;
         mbar_wait(&barP[slot], par);
         if (K < 40) SCHUR_STAMP(9 + 2 * K);
+        if (K < 25 && has_tile && tK == K + 1 && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 5);
+        {   // results of this block: by the warps whose tiles all lie right of tile column K + 1 (they have arrived long ago and have
+            // slack), or by the leverage warp when no such warp is left
+            const int nfw = schur_tiles(max(TRa - K - 2, 0)) >> 5;
+            if (warp < nfw) store_pivot_block(cA, inf, K, TRa, LD, MC, nacc, r4, clist, keep, g.off_L, g.off_acc, tid, nfw * 32);
+        }
         nacc += __popc((unsigned)(int)inf[12]);
         if (inf[13] != 0.0) break;                   // capacity reached (RbfModel.jl:402) or no candidates left
-        if (has_tile && tK > K) {                    // ---- 3. rank-4 update
+        // ---- 3. rank-4 update
+        if (has_tile && tK > K) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double4 i4 = *reinterpret_cast<const double4*>(cAs + q * LD + 4 * tI), k4 = *reinterpret_cast<const double4*>(cA + q * LD + 4 * tK);
@@ -689,6 +718,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                     for (int c = 0; c < 4; ++c) A[a][c] = fma(-ai[a], ak[c], A[a][c]);
             }
         }
+        if (K < 25 && has_tile && tK == K + 1 && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 6);
     }
     SCHUR_STAMP(5);
     // thread 0 owns the last diagonal tile: it is alive until the end and has seen every accepted pivot
@@ -730,7 +760,7 @@ cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaS
     if (e != cudaSuccess) return e;
     round4_prep_kernel<<<P.B, 256, psmem, s>>>(P, g);
     if (g.two_variants) {
-        e = launch_elim<true>(P, g, 384, g.smem_small * sizeof(double), rpl, s);
+        e = launch_elim<true>(P, g, 384, g.smem_small * sizeof(double) + (getenv("MRBF_R4_PAD") ? (size_t)atoi(getenv("MRBF_R4_PAD")) : 0), rpl, s);
         if (e == cudaSuccess) e = launch_elim<false>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
     } else if (g.nthreads <= 384) {
         e = launch_elim<true>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
