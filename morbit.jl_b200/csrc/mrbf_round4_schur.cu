@@ -82,6 +82,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!done);
 }
 
+// Rows of the shared-memory panels (candidates along the row) are stored in two halves: the candidates 4t, 4t + 1 of tile t at
+// [2t, 2t + 1] and 4t + 2, 4t + 3 at [H + 2t, H + 2t + 1], H = LD / 2.  A thread reads the four values of its tile with two
+// 16-byte loads, and the threads of consecutive tiles touch consecutive 16-byte pieces -- no bank conflicts (32 bytes per thread
+// in one piece would be a two-way conflict on every access).
+__device__ __forceinline__ double4 ld4(const double* row, int t, int H) {
+    const double2 a = *reinterpret_cast<const double2*>(row + 2 * t), b = *reinterpret_cast<const double2*>(row + H + 2 * t);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(double* row, int t, int H, double4 v) {
+    *reinterpret_cast<double2*>(row + 2 * t) = make_double2(v.x, v.y);
+    *reinterpret_cast<double2*>(row + H + 2 * t) = make_double2(v.z, v.w);
+}
+__device__ __forceinline__ int off4(int i, int H) { return ((i >> 2) << 1) + (i & 1) + ((i >> 1) & 1) * H; }
+
 // Shared-memory layout of round4_elim_kernel for leading dimension LD (the padded candidate count of the instance, <= the
 // launch's maximum), in doubles; every block starts 32-byte aligned (double4 accesses).
 //   phase "panels":  C (p x LD) | V (p x LD) | Xc (n x LD) || X0 (p x n) | M0 (p x p) | P00 (p x p) || fixed
@@ -314,7 +328,7 @@ __device__ __forceinline__ void store_pivot_block(const double* cA, const double
         if (keep) {
             if (I == K) keep[off_acc + q_out] = (double)(j0 + q);
             const double rd = sqrt(inf[4 + q]);      // 1/d from 1/d^2
-            const double4 v = *reinterpret_cast<const double4*>(cA + q * LD + 4 * I);
+            const double4 v = ld4(cA + q * LD, I, LD >> 1);
             *reinterpret_cast<double4*>(keep + off_L + (size_t)q_out * MC + 4 * I) = make_double4(v.x * rd, v.y * rd, v.z * rd, v.w * rd);
         }
     }
@@ -323,7 +337,7 @@ __device__ __forceinline__ void store_pivot_block(const double* cA, const double
 // One pass of the leverage warp over the rows of M it owns (lane l: rows l, l + 32, ..): downdate  M -= sum_q av_q u_q'  (upd) and
 // U = M C_J, eight columns at a time so that the loads of a group are in flight together.  Columns p .. PS-2 of M are zero padding.
 template <int RPL>
-__device__ __forceinline__ void lev_pass(double* __restrict__ Minv, const double* __restrict__ su, const double* __restrict__ Cj, int LD, int PS,
+__device__ __forceinline__ void lev_pass(double* __restrict__ Minv, const double* __restrict__ su, const double* __restrict__ Cs, int K, int LD, int PS,
                                          int p, int lane, bool upd, const double (&av)[RPL][4], double (&U4)[RPL][4]) {
     const int pg = (p + 7) & ~7;
 #pragma unroll
@@ -357,7 +371,7 @@ __device__ __forceinline__ void lev_pass(double* __restrict__ Minv, const double
                 for (int h = 0; h < 2; ++h) {
                     double4 cj[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const int c = min(c0 + 4 * h + i, p - 1); cj[i] = *reinterpret_cast<const double4*>(Cj + c * LD); }
+                    for (int i = 0; i < 4; ++i) { const int c = min(c0 + 4 * h + i, p - 1); cj[i] = ld4(Cs + c * LD, K, LD >> 1); }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         u0 = fma(m[4 * h + i], cj[i].x, u0); u1 = fma(m[4 * h + i], cj[i].y, u1);
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
     const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
     if (g.two_variants && (SMALL != (schur_tiles(TRa) <= 352))) return;      // the other launch shape's instance
-    const int LD = MCa;
+    const int LD = MCa, H = LD >> 1;
     const ElimLayout L = elim_layout(p, n, LD);
     double* Cs = smem + L.C; double* Vs = smem + L.V; double* Xc = smem + L.Xc;
     double* X0 = smem + L.X0; double* M0 = smem + L.M0; double* P00 = smem + L.P00;
@@ -421,11 +435,11 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         for (int i = tid; i < mc; i += nt) clist[i] = cl[i];
         for (int e = tid; e < mc * n; e += nt) {
             const int i = e / n, k = e % n;
-            Xc[k * LD + i] = sites[(size_t)cl[i] * n + k];
+            Xc[k * LD + off4(i, H)] = sites[(size_t)cl[i] * n + k];
         }
         if (tid == 0) for (int q = 0; q < 3; ++q) { mbar_init(&barD[q], 1); mbar_init(&barP[q], nwarps - 1); mbar_init(&barG[q], 1); }
         __syncthreads();
-        for (int e = tid; e < (MCa - mc) * n; e += nt) { const int i = mc + e / n, k = e % n; Xc[k * LD + i] = X0[k]; }
+        for (int e = tid; e < (MCa - mc) * n; e += nt) { const int i = mc + e / n, k = e % n; Xc[k * LD + off4(i, H)] = X0[k]; }
         for (int e = tid; e < p * p; e += nt) {
             const int i = e % p, j = e / p;
             double r2 = 0.0;
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         double c0 = M0[r], c1 = c0, c2 = c0, c3 = c0;            // pi~[0] = 1
         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
         for (int k = 0; k < n; ++k) {
-            const double4 x = *reinterpret_cast<const double4*>(Xc + k * LD + i4);
+            const double4 x = ld4(Xc + k * LD, i4 >> 2, H);
             if (k + 1 < p) {
                 const double mv = M0[r + (k + 1) * p] * inv_s, xc = X0[k];
                 c0 = fma(mv, x.x - xc, c0); c1 = fma(mv, x.y - xc, c1); c2 = fma(mv, x.z - xc, c2); c3 = fma(mv, x.w - xc, c3);
@@ -451,8 +465,8 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             e_ = x.x - xr; d0 = fma(e_, e_, d0); e_ = x.y - xr; d1 = fma(e_, e_, d1);
             e_ = x.z - xr; d2 = fma(e_, e_, d2); e_ = x.w - xr; d3 = fma(e_, e_, d3);
         }
-        *reinterpret_cast<double4*>(Cs + r * LD + i4) = make_double4(c0, c1, c2, c3);
-        *reinterpret_cast<double4*>(Vs + r * LD + i4) = make_double4(rad_phi(P.rf, d0), rad_phi(P.rf, d1), rad_phi(P.rf, d2), rad_phi(P.rf, d3));
+        st4(Cs + r * LD, i4 >> 2, H, make_double4(c0, c1, c2, c3));
+        st4(Vs + r * LD, i4 >> 2, H, make_double4(rad_phi(P.rf, d0), rad_phi(P.rf, d1), rad_phi(P.rf, d2), rad_phi(P.rf, d3)));
         if (keep) *reinterpret_cast<double4*>(keep + g.off_C + (size_t)r * MC + i4) = make_double4(c0, c1, c2, c3);
     }
     __syncthreads();
@@ -462,12 +476,12 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         for (int c = 0; c < p; ++c) {
             const double pv = P00[r + c * p];
-            const double4 cc = *reinterpret_cast<const double4*>(Cs + c * LD + i4);
+            const double4 cc = ld4(Cs + c * LD, i4 >> 2, H);
             s0 = fma(pv, cc.x, s0); s1 = fma(pv, cc.y, s1); s2 = fma(pv, cc.z, s2); s3 = fma(pv, cc.w, s3);
         }
-        const double4 bb = *reinterpret_cast<const double4*>(Vs + r * LD + i4);
+        const double4 bb = ld4(Vs + r * LD, i4 >> 2, H);
         if (keep) *reinterpret_cast<double4*>(keep + g.off_U + (size_t)r * MC + i4) = make_double4(bb.x - s0, bb.y - s1, bb.z - s2, bb.w - s3);
-        *reinterpret_cast<double4*>(Vs + r * LD + i4) = make_double4(fma(-0.5, s0, bb.x), fma(-0.5, s1, bb.y), fma(-0.5, s2, bb.z), fma(-0.5, s3, bb.w));
+        st4(Vs + r * LD, i4 >> 2, H, make_double4(fma(-0.5, s0, bb.x), fma(-0.5, s1, bb.y), fma(-0.5, s2, bb.z), fma(-0.5, s3, bb.w)));
     }
     __syncthreads();                                // X0, M0, P00 are dead from here on
 
@@ -485,14 +499,13 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     }
     double A[4][4];
     if (has_tile) {
-        const double* xi = Xc + 4 * tI; const double* xk = Xc + 4 * tK;
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int c = 0; c < 4; ++c) A[a][c] = 0.0;
         for (int k = 0; k < n; ++k) {
-            const double4 vi = *reinterpret_cast<const double4*>(xi + k * LD);
-            const double4 vk = *reinterpret_cast<const double4*>(xk + k * LD);
+            const double4 vi = ld4(Xc + k * LD, tI, H);
+            const double4 vk = ld4(Xc + k * LD, tK, H);
             const double ri[4] = {vi.x, vi.y, vi.z, vi.w}, rk[4] = {vk.x, vk.y, vk.z, vk.w};
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -503,10 +516,9 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int c = 0; c < 4; ++c) A[a][c] = rad_phi(P.rf, A[a][c]);
-        const double* ci_ = Cs + 4 * tI; const double* ck_ = Cs + 4 * tK; const double* vi_ = Vs + 4 * tI; const double* vk_ = Vs + 4 * tK;
         for (int r = 0; r < p; ++r) {
-            const double4 a4 = *reinterpret_cast<const double4*>(ci_ + r * LD), b4 = *reinterpret_cast<const double4*>(ck_ + r * LD);
-            const double4 c4 = *reinterpret_cast<const double4*>(vi_ + r * LD), d4 = *reinterpret_cast<const double4*>(vk_ + r * LD);
+            const double4 a4 = ld4(Cs + r * LD, tI, H), b4 = ld4(Cs + r * LD, tK, H);
+            const double4 c4 = ld4(Vs + r * LD, tI, H), d4 = ld4(Vs + r * LD, tK, H);
             const double ci[4] = {a4.x, a4.y, a4.z, a4.w}, ck[4] = {b4.x, b4.y, b4.z, b4.w};
             const double vi[4] = {c4.x, c4.y, c4.z, c4.w}, vk[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -569,7 +581,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                 }
             }
             if (K < 25 && lane == 0) SCHUR_STAMPX(341 + 4 * K);
-            lev_pass<RPL>(Minv, su, Cs + j0, LD, PS, p, lane, upd, av, U4);
+            lev_pass<RPL>(Minv, su, Cs, K, LD, PS, p, lane, upd, av, U4);
             if (K < 25 && lane == 0) SCHUR_STAMPX(342 + 4 * K);
             double v[16];
 #pragma unroll
@@ -578,7 +590,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             for (int rr = 0; rr < RPL; ++rr) {
                 const int r = lane + 32 * rr;
                 if (r < p) {
-                    const double4 cr = *reinterpret_cast<const double4*>(Cs + r * LD + j0);
+                    const double4 cr = ld4(Cs + r * LD, K, H);
                     v[0] = fma(cr.x, U4[rr][0], v[0]);
                     v[1] = fma(cr.y, U4[rr][0], v[1]); v[2] = fma(cr.y, U4[rr][1], v[2]);
                     v[3] = fma(cr.z, U4[rr][0], v[3]); v[4] = fma(cr.z, U4[rr][1], v[4]); v[5] = fma(cr.z, U4[rr][2], v[5]);
@@ -660,7 +672,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             *reinterpret_cast<double2*>(inf + 24) = make_double2(A[3][1] * rav[1], A[3][2] * rav[2]);
 #pragma unroll
             for (int q = 0; q < 4; ++q)             // rows j0..j0+3 of the four pivot columns (zeros above the diagonal) for store_pivot_block
-                *reinterpret_cast<double4*>(cA + q * LD + j0) = make_double4(q <= 0 ? A[0][q] : 0.0, q <= 1 ? A[1][q] : 0.0, q <= 2 ? A[2][q] : 0.0, A[3][q]);
+                st4(cA + q * LD, K, H, make_double4(q <= 0 ? A[0][q] : 0.0, q <= 1 ? A[1][q] : 0.0, q <= 2 ? A[2][q] : 0.0, A[3][q]));
             nacc_diag = na;
             mbar_arrive(&barD[slot]);
             if (K < 25) SCHUR_STAMPX(128 + 8 * K + 2);
@@ -683,8 +695,8 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             const double ra[4] = {ra4.x, ra4.y, ra4.z, ra4.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                *reinterpret_cast<double4*>(cA + q * LD + 4 * tI) = make_double4(A[0][q], A[1][q], A[2][q], A[3][q]);
-                *reinterpret_cast<double4*>(cAs + q * LD + 4 * tI) = make_double4(A[0][q] * ra[q], A[1][q] * ra[q], A[2][q] * ra[q], A[3][q] * ra[q]);
+                st4(cA + q * LD, tI, H, make_double4(A[0][q], A[1][q], A[2][q], A[3][q]));
+                st4(cAs + q * LD, tI, H, make_double4(A[0][q] * ra[q], A[1][q] * ra[q], A[2][q] * ra[q], A[3][q] * ra[q]));
             }
         }
         if (K < 25 && has_tile && tK == K && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 4);
@@ -710,7 +722,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         if (has_tile && tK > K) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const double4 i4 = *reinterpret_cast<const double4*>(cAs + q * LD + 4 * tI), k4 = *reinterpret_cast<const double4*>(cA + q * LD + 4 * tK);
+                const double4 i4 = ld4(cAs + q * LD, tI, H), k4 = ld4(cA + q * LD, tK, H);
                 const double ai[4] = {i4.x, i4.y, i4.z, i4.w}, ak[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
