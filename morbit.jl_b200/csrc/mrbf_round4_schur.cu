@@ -35,7 +35,6 @@
 // database is larger than 128 sites or whose panels do not fit in shared memory use round4_block_kernel instead.
 #include "mrbf_common.cuh"
 #include "mrbf_kernels.h"
-#include <stdlib.h>
 
 namespace mrbf {
 
@@ -240,6 +239,69 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
     }
     __syncthreads();
     if (mc == 0) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
+    if (p <= 32 && nwarps == 8) {
+        // ---- Pi_0^{-1} by Gauss-Jordan on [Pi_0 | I] held in REGISTERS: lane i owns row i, warp w the columns w, w + 8, ..  The pivot
+        // row of a step is never moved (its index is remembered instead of a row swap: row k of the inverse is row r_k of the right
+        // half), the pivot-row entries travel by shuffle and the multiplier column through a double-buffered shared-memory column,
+        // ONE barrier per step.  The warp that owns column k + 1 looks for the next pivot right after its own update.
+        double a[8];
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) {
+            const int c = warp + 8 * sl;
+            double v = 0.0;
+            if (lane < p) {
+                if (c < p) v = (c == 0) ? 1.0 : (X0[lane * n + c - 1] - X0[c - 1]) * inv_s;
+                else if (c < 2 * p) v = (c - p == lane) ? 1.0 : 0.0;
+            }
+            a[sl] = v;
+        }
+        double* fb = Aq;                               // [2][32] multiplier columns
+        double* rpb = Aq + 64;                         // [2] reciprocal pivots
+        int* ib = reinterpret_cast<int*>(Aq + 66);     // [2] pivot rows (-1: singular)
+        bool used = lane >= p;
+        int mystep = -1;
+#pragma unroll
+        for (int so = 0; so < 4; ++so)               // column kk lives in slot so = kk / 8 (compile-time: the array stays in registers)
+        for (int kk = 8 * so; kk < min(p, 8 * so + 8); ++kk) {
+            const int par = kk & 1;
+            if (warp == (kk & 7)) {
+                const double v = a[so];
+                const double av = used ? 0.0 : fabs(v);
+                const unsigned vh = (unsigned)__double2hiint(av), vl = (unsigned)__double2loint(av);
+                const unsigned mh = __reduce_max_sync(0xffffffffu, vh);
+                const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
+                const unsigned win = __ballot_sync(0xffffffffu, vh == mh && vl == ml && !used);
+                const double mv = __hiloint2double((int)mh, (int)ml);
+                const int r = (mv > 1e-12 && win) ? (__ffs(win) - 1) : -1;
+                const double pv = __shfl_sync(0xffffffffu, v, r < 0 ? 0 : r);
+                fb[par * 32 + lane] = v;
+                if (lane == 0) { ib[par] = r; rpb[par] = (r < 0) ? 0.0 : fast_rcp(pv); }
+            }
+            __syncthreads();
+            const int r = ib[par];
+            if (r < 0) { if (tid == 0) P.n_r4[b] = -1; return; }       // Pi_0 (scaled to O(1)) is rank deficient
+            const double rp = rpb[par], f = fb[par * 32 + lane];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) {
+                const double pv = __shfl_sync(0xffffffffu, a[sl], r) * rp;
+                a[sl] = (lane == r) ? pv : fma(-f, pv, a[sl]);
+            }
+            if (lane == r) { used = true; mystep = kk; }
+        }
+        // row r_k of the right half is row k of Pi_0^{-1};  M0 = Pi_0^{-T}:  M0[j + k * p] = inverse[k][j]
+        if (lane < p) {
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) {
+                const int c = warp + 8 * sl;
+                if (c >= p && c < 2 * p) pw[g.pw_M0 + (c - p) + mystep * pl] = a[sl];
+            }
+        }
+        for (int i = tid; i < mc; i += nt) reinterpret_cast<int*>(pw + g.pw_clist)[i] = clist[i];
+        if (tid == 0) { pmeta[1] = inv_s; pmeta[2] = (double)N0; pmeta[0] = (double)mc; }
+        SCHUR_STAMP(1);
+        SCHUR_STAMP(2);
+        return;
+    }
     for (int e = tid; e < p * p; e += nt) {
         const int i = e % p, j = e / p;
         Aq[i + j * pl] = (j == 0) ? 1.0 : (X0[i * n + j - 1] - X0[j - 1]) * inv_s;
@@ -772,7 +834,7 @@ cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaS
     if (e != cudaSuccess) return e;
     round4_prep_kernel<<<P.B, 256, psmem, s>>>(P, g);
     if (g.two_variants) {
-        e = launch_elim<true>(P, g, 384, g.smem_small * sizeof(double) + (getenv("MRBF_R4_PAD") ? (size_t)atoi(getenv("MRBF_R4_PAD")) : 0), rpl, s);
+        e = launch_elim<true>(P, g, 384, g.smem_small * sizeof(double), rpl, s);
         if (e == cudaSuccess) e = launch_elim<false>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
     } else if (g.nthreads <= 384) {
         e = launch_elim<true>(P, g, g.nthreads, g.smem_doubles * sizeof(double), rpl, s);
