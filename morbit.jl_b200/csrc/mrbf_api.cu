@@ -34,7 +34,7 @@ struct mrbf_ctx {
     double isapprox_rtol = 1.4901161193847656e-08;   // sqrt(eps(Float64)); see mrbf_set_isapprox_rtol
     cudaEvent_t ev0[8] = {nullptr}, ev1[8] = {nullptr};
     bool ev_used[8] = {false};
-    DevBuf ws[16];      // kernel workspaces (grow-only)
+    DevBuf ws[24];      // kernel workspaces (grow-only)
     DevBuf hb[32];      // staging for the host-pointer entry points
 };
 
@@ -719,6 +719,48 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     }
     if (e == cudaSuccess) e = cudaMemsetAsync(m->w, 0, sizeof(double) * (size_t)B * train_stride * k, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->lam, 0, sizeof(double) * (size_t)B * pl * k, ctx->stream);
+    // 0. no kept factorisation: the reduced-system route on the register-tiled round-4 kernels in BUILD MODE (found set = the first p
+    //    training points, every other point a candidate that must be accepted: Pi_0^{-1}, panels, blocked Cholesky of N' Phi N in
+    //    registers, then the two triangular solves of build_schur_kernel).  Instances that do not qualify (N <= p, more than 128
+    //    reduced unknowns, ill-conditioned first p points, reduced matrix not positive definite) are left to the general kernel.
+    const SchurGeom bgeom = (p > 0 && train_stride > p) ? round4_schur_geom(n, p, train_stride - p) : SchurGeom{};
+    const char* bg_env = getenv("MRBF_BUILD_GENERAL");
+    const bool reduced_route = !kp && e == cudaSuccess && bgeom.eligible && !(bg_env && atoi(bg_env) != 0) &&
+                               build_schur_smem_doubles(k, bgeom.MC, p) * sizeof(double) <= SMEM_LIMIT;
+    if (reduced_route) {
+        const size_t ni = (size_t)B * 4 + (size_t)B * p + (size_t)B * bgeom.MC;
+        int r_ = ensure(ctx, ctx->ws[16], (size_t)B * bgeom.state_doubles * sizeof(double));
+        if (r_ == MRBF_OK) r_ = ensure(ctx, ctx->ws[17], ni * sizeof(int));
+        if (r_ == MRBF_OK) r_ = ensure(ctx, ctx->ws[13], (size_t)B * bgeom.pw_doubles * sizeof(double));
+        if (r_ != MRBF_OK) { mrbf_free_model(ctx, m); return r_; }
+        int* b_elig = (int*)ctx->ws[17].p; int* b_nfound = b_elig + B; int* b_nr4 = b_nfound + B; int* b_done = b_nr4 + B;
+        int* b_found = b_done + B; int* b_r4 = b_found + (size_t)B * p;
+        Round4Params R{};
+        R.B = B; R.n = n; R.db_stride = train_stride; R.found_stride = p; R.extra_stride = 0; R.r4_stride = bgeom.MC;
+        R.NM = train_stride; R.max_points = 1 << 30;
+        R.cfg.polynomial_degree = deg; R.cfg.optimized_sampling = 1;
+        R.rf = rf; R.chol_thr = 0.0;
+        R.sites = sites; R.n_db = N; R.r4 = b_r4; R.n_r4 = b_nr4; R.status = nullptr;
+        R.keep_fs = (double*)ctx->ws[16].p; R.fs_stride = bgeom.state_doubles; R.elig = b_elig;
+        R.panel_ws = (double*)ctx->ws[13].p;
+        R.build_mode = 1; R.shape_arr = shape; R.alpha_default = alpha; R.alpha2_out = m->alpha2;
+        R.found_out = b_found; R.n_found_out = b_nfound;
+        e = cudaMemsetAsync(b_done, 0, sizeof(int) * (size_t)B, ctx->stream);
+        if (e == cudaSuccess) { Timed t_(ctx, 1); e = launch_round4_schur(R, bgeom, ctx->stream); ctx->launches += 1; }
+        if (e == cudaSuccess) {
+            SchurBuildParams Q{};
+            Q.B = B; Q.n = n; Q.k = k; Q.p = p; Q.deg = deg; Q.db_stride = train_stride; Q.found_stride = p;
+            Q.r4_stride = bgeom.MC; Q.train_stride = train_stride; Q.MC = bgeom.MC; Q.fs_stride = bgeom.state_doubles;
+            Q.off_M0 = bgeom.off_M0; Q.off_U = bgeom.off_U; Q.off_C = bgeom.off_C; Q.off_L = bgeom.off_L; Q.off_acc = bgeom.off_acc;
+            Q.fs = R.keep_fs; Q.elig = b_elig; Q.found = b_found; Q.n_found = b_nfound; Q.r4 = b_r4;
+            Q.sites = sites; Q.values = values; Q.r3_sites = nullptr; Q.r3_values = nullptr; Q.alpha2 = -1.0;
+            Q.centers = m->centers; Q.w = m->w; Q.lam = m->lam; Q.alpha2_out = m->alpha2; Q.N = m->N; Q.status = status; Q.done = b_done;
+            Timed t_(ctx, 6);
+            e = launch_build_schur(Q, build_schur_smem_doubles(k, bgeom.MC, p) * sizeof(double), ctx->stream);
+            ctx->launches += 1;
+            Pb.skip = b_done;
+        }
+    }
     if (e == cudaSuccess && kp && kp->kind == 1 && kp->cfg_degree == deg && kp->p > 0) {
         // 1'. factorisation kept by round4_schur_kernel: two triangular solves per output
         SchurBuildParams Q{};

@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(64, 16) build_schur_kernel(SchurBuildParams P)
         else val = sv[e] * inv_s;
         lam_out[e] = val;
     }
-    if (tid == 0) { P.N[b] = N; P.alpha2_out[b] = P.alpha2; P.status[b] = 0; P.done[b] = 1; }
+    if (tid == 0) { P.N[b] = N; if (P.alpha2 >= 0.0) P.alpha2_out[b] = P.alpha2; P.status[b] = 0; P.done[b] = 1; }
 }
 
 size_t build_schur_smem_doubles(int k, int MC, int p) {

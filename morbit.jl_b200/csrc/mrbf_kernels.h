@@ -45,6 +45,12 @@ struct Round4Params {
     double* keep_fs; int* elig;                     // kept factorisation (mrbf_prepared) or NULL
     double* panel_ws;                               // round4_panels_kernel -> round4_schur_kernel hand-over (B x SchurGeom::pw_doubles)
     long long* dbg_clock;                           // instrumentation (MRBF_DEBUG_CLOCK): phase time stamps of CTA 0, or NULL
+    // build mode of the register-tiled kernels (mrbf_build without a kept factorisation): `sites` are the training sets
+    // (B x db_stride x n, n_db = N), the found set is the first p training points, every other point is a candidate that MUST be
+    // accepted (plain Cholesky of the reduced kernel matrix, no leverages); instances that do not qualify get n_r4 = -1
+    int build_mode;
+    const double* shape_arr; double alpha_default; double* alpha2_out;   // per-instance shape parameter (NaN: default) or NULL
+    int* found_out; int* n_found_out;               // build mode: the found ids 1..p are written here for build_schur_kernel
 };
 
 // Geometry of the register-tiled round-4 kernel (mrbf_round4_schur.cu): shared-memory offsets and the layout of the
@@ -94,7 +100,7 @@ struct SchurBuildParams {
     size_t fs_stride, off_M0, off_U, off_C, off_L, off_acc;
     const double* fs; const int* elig; const int* found; const int* n_found; const int* r4;
     const double* sites; const double* values; const double* r3_sites; const double* r3_values;
-    double alpha2;
+    double alpha2;        // < 0: alpha2_out has already been written per instance (build mode)
     double* centers; double* w; double* lam; double* alpha2_out; int* N; int* status; int* done;
 };
 

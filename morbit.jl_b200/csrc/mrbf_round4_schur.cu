@@ -169,24 +169,34 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
     unsigned char* cflag = reinterpret_cast<unsigned char*>(wcnt + 32);
 
     SCHUR_STAMP(0);
+    const bool bm = P.build_mode != 0;
     const int n_db = P.n_db[b];
     const double* sites = P.sites + (size_t)b * P.db_stride * n;
-    const double* lb2 = P.lb2 + (size_t)b * n;
-    const double* ub2 = P.ub2 + (size_t)b * n;
-    const int* found = P.found + (size_t)b * P.found_stride;
-    const int nf_ids = P.n_found[b];
+    const double* lb2 = bm ? nullptr : P.lb2 + (size_t)b * n;
+    const double* ub2 = bm ? nullptr : P.ub2 + (size_t)b * n;
+    const int* found = bm ? nullptr : P.found + (size_t)b * P.found_stride;
+    const int nf_ids = bm ? p : P.n_found[b];
     const int n_extra = P.n_extra ? P.n_extra[b] : 0;
     const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
     const int N0 = nf_ids + n_extra;
     const int max_points = P.max_points;
     if (tid == 0 && P.elig) P.elig[b] = 0;
     if (tid == 0) pmeta[0] = 0.0;                  // [0] number of candidates handed to kernel 2 (0: nothing to do)
-    if (!(N0 < max_points)) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
-    if (N0 != p || n_db > MC) { if (tid == 0) P.n_r4[b] = -1; return; }      // literal kernel takes over
+    if (bm) {
+        // build mode: found set = the first p training points, candidates = all the others; too few / too many points: general kernel
+        if (n_db <= p || n_db - p > MC) { if (tid == 0) P.n_r4[b] = -1; return; }
+        for (int i = tid; i < p; i += nt) P.found_out[(size_t)b * P.found_stride + i] = i + 1;
+        if (tid == 0) P.n_found_out[b] = p;
+    } else {
+        if (!(N0 < max_points)) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
+        if (N0 != p || n_db > MC) { if (tid == 0) P.n_r4[b] = -1; return; }      // literal kernel takes over
+    }
 
     // ---- candidates: results_in_box_indices(db, lb_2, ub_2, found) in ascending id order (RbfModel.jl:360).  After rounds
     // 1-3 the box-2 flags and the picked ids are already in the flag bytes of select_rounds123_kernel.
-    if (P.cflags) {
+    if (bm) {
+        // nothing to scan
+    } else if (P.cflags) {
         const unsigned char* cf = P.cflags + (size_t)b * P.db_stride;
         for (int id = tid; id < n_db; id += nt) { const unsigned f = cf[id]; cflag[id] = ((f & 2u) && !(f & 4u)) ? 1 : 0; }
     } else {
@@ -201,12 +211,15 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
     }
     for (int e = tid; e < p * n; e += nt) {
         const int i = e / n, k = e % n;
-        X0[e] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
+        X0[e] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k]);
     }
     if (tid == 0) red[76] = 0.0;
     __syncthreads();
     int mc = 0;
-    {
+    if (bm) {
+        mc = n_db - p;
+        for (int i = tid; i < mc; i += nt) clist[i] = p + i;
+    } else {
         const int nseg = (n_db + 31) >> 5;         // <= 4 segments of 32 ids
         if (warp < nseg) {
             const int id = warp * 32 + lane;
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
                 const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
                 const unsigned win = __ballot_sync(0xffffffffu, vh == mh && vl == ml && !used);
                 const double mv = __hiloint2double((int)mh, (int)ml);
-                const int r = (mv > 1e-12 && win) ? (__ffs(win) - 1) : -1;
+                const int r = (mv > (bm ? 1e-6 : 1e-12) && win) ? (__ffs(win) - 1) : -1;      // build mode: an ill-conditioned Pi_0 goes to the QR-based kernel
                 const double pv = __shfl_sync(0xffffffffu, v, r < 0 ? 0 : r);
                 fb[par * 32 + lane] = v;
                 if (lane == 0) { ib[par] = r; rpb[par] = (r < 0) ? 0.0 : fast_rcp(pv); }
@@ -470,6 +483,12 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
     if (g.two_variants && (SMALL != (schur_tiles(TRa) <= 352))) return;      // the other launch shape's instance
     const int LD = MCa, H = LD >> 1;
+    const bool bm = P.build_mode != 0;
+    RadFn rf = P.rf;
+    if (P.shape_arr) {                              // per-instance shape parameter (NaN: the configuration's default)
+        double a_ = P.alpha_default; const double sp = P.shape_arr[b]; if (sp == sp) a_ = sp;
+        rf.alpha2 = a_ * a_;
+    }
     const ElimLayout L = elim_layout(p, n, LD);
     double* Cs = smem + L.C; double* Vs = smem + L.V; double* Xc = smem + L.Xc;
     double* X0 = smem + L.X0; double* M0 = smem + L.M0; double* P00 = smem + L.P00;
@@ -485,12 +504,12 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     // centre: finite, never a pivot)
     {
         const double* sites = P.sites + (size_t)b * P.db_stride * n;
-        const int* found = P.found + (size_t)b * P.found_stride;
-        const int nf_ids = P.n_found[b];
+        const int* found = bm ? nullptr : P.found + (size_t)b * P.found_stride;
+        const int nf_ids = bm ? p : P.n_found[b];
         const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
         for (int e = tid; e < p * n; e += nt) {
             const int i = e / n, k = e % n;
-            X0[e] = (i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k];
+            X0[e] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k]);
         }
         for (int e = tid; e < p * p; e += nt) { const double v = pw[g.pw_M0 + e]; M0[e] = v; if (keep) keep[g.off_M0 + e] = v; }
         const int* cl = reinterpret_cast<const int*>(pw + g.pw_clist);
@@ -506,7 +525,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             const int i = e % p, j = e / p;
             double r2 = 0.0;
             for (int k = 0; k < n; ++k) { const double d = X0[i * n + k] - X0[j * n + k]; r2 = fma(d, d, r2); }
-            P00[i + j * p] = rad_phi(P.rf, r2);
+            P00[i + j * p] = rad_phi(rf, r2);
         }
         __syncthreads();
     }
@@ -528,7 +547,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             e_ = x.z - xr; d2 = fma(e_, e_, d2); e_ = x.w - xr; d3 = fma(e_, e_, d3);
         }
         st4(Cs + r * LD, i4 >> 2, H, make_double4(c0, c1, c2, c3));
-        st4(Vs + r * LD, i4 >> 2, H, make_double4(rad_phi(P.rf, d0), rad_phi(P.rf, d1), rad_phi(P.rf, d2), rad_phi(P.rf, d3)));
+        st4(Vs + r * LD, i4 >> 2, H, make_double4(rad_phi(rf, d0), rad_phi(rf, d1), rad_phi(rf, d2), rad_phi(rf, d3)));
         if (keep) *reinterpret_cast<double4*>(keep + g.off_C + (size_t)r * MC + i4) = make_double4(c0, c1, c2, c3);
     }
     __syncthreads();
@@ -577,7 +596,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) A[a][c] = rad_phi(P.rf, A[a][c]);
+            for (int c = 0; c < 4; ++c) A[a][c] = rad_phi(rf, A[a][c]);
         for (int r = 0; r < p; ++r) {
             const double4 a4 = ld4(Cs + r * LD, tI, H), b4 = ld4(Cs + r * LD, tK, H);
             const double4 c4 = ld4(Vs + r * LD, tI, H), d4 = ld4(Vs + r * LD, tK, H);
@@ -625,7 +644,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                     }
                     break;
                 }
-                if ((int)pin[12] != 0) {
+                if (!bm && (int)pin[12] != 0) {
                     upd = true;
                     const double4 rw = *reinterpret_cast<const double4*>(pin + 8);
                     const double l10 = pin[14], l20 = pin[15], l21 = pin[16], l30 = pin[17], l31 = pin[18], l32 = pin[19];
@@ -641,6 +660,18 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                     }
                     __syncwarp();
                 }
+            }
+            if (bm) {                               // no leverages in build mode: only the result stores of the late blocks
+                if (K > 0) {
+                    const int ps = (K - 1) % 3;
+                    const double* pin = info + ps * 28;
+                    if ((schur_tiles(max(TRa - (K - 1) - 2, 0)) >> 5) == 0) {
+                        mbar_wait(&barP[ps], (unsigned)(((K - 1) / 3) & 1));
+                        store_pivot_block(ring + (size_t)ps * 8 * LD, pin, K - 1, TRa, LD, MC, nacc_l, r4, clist, keep, g.off_L, g.off_acc, lane, 32);
+                    }
+                    nacc_l += __popc((unsigned)(int)pin[12]);
+                }
+                continue;
             }
             if (K < 25 && lane == 0) SCHUR_STAMPX(341 + 4 * K);
             lev_pass<RPL>(Minv, su, Cs, K, LD, PS, p, lane, upd, av, U4);
@@ -688,6 +719,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     //   3. every tile to the right applies the rank-4 update.  Tile column K + 1 sits in the lowest live thread ids and its
     //      diagonal tile starts step 1 of the next block as soon as its own update is done; warps without live tiles leave.
     int nacc = 0, nacc_diag = -1;
+    bool bm_failed = false;
     const int my_last = __shfl_sync(0xffffffffu, has_tile ? tK : -1, 0);             // lane 0 holds this warp's largest tile column
     for (int K = 0; K < TRa; ++K) {
         const int slot = K % 3;
@@ -699,14 +731,18 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         if (K < 40) SCHUR_STAMP(8 + 2 * K);
         if (has_tile && tK == K && tI == K) {        // ---- 1. diagonal tile
             if (K < 25) SCHUR_STAMPX(128 + 8 * K);
-            mbar_wait(&barG[slot], par);
             double W[4][4];
-            {
+            if (bm) {                               // plain Cholesky: no leverage, every candidate must be accepted
+                W[0][0] = 1.0; W[1][0] = 0.0; W[1][1] = 1.0; W[2][0] = 0.0; W[2][1] = 0.0; W[2][2] = 1.0;
+                W[3][0] = 0.0; W[3][1] = 0.0; W[3][2] = 0.0; W[3][3] = 1.0;
+            } else {
+                mbar_wait(&barG[slot], par);
                 const double* gq = gs + slot * 16;
                 W[0][0] = gq[0]; W[1][0] = gq[1]; W[1][1] = gq[2]; W[2][0] = gq[3]; W[2][1] = gq[4]; W[2][2] = gq[5];
                 W[3][0] = gq[6]; W[3][1] = gq[7]; W[3][2] = gq[8]; W[3][3] = gq[9];
             }
             int mask = 0, na = nacc;
+            bool failed = false;
             double rav[4], rwv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -715,6 +751,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                 const bool ok = (j0 + q < mc) && (na < cap) && (dA * rw > thr);      // d^2 / (1 + lev) == sigma - ||L^-1 v||^2
                 rav[q] = ok ? ra : 0.0; rwv[q] = ok ? rw : 0.0;
                 if (ok) { mask |= 1 << q; na += 1; }
+                else if (bm && j0 + q < mc) failed = true;       // reduced kernel matrix not positive definite: the general kernel reports it
 #pragma unroll
                 for (int r = q + 1; r < 4; ++r)
 #pragma unroll
@@ -727,7 +764,8 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             // what the panel tiles and the leverage warp need: 1/d^2, the accept mask, the multipliers of the diagonal blocks
             *reinterpret_cast<double4*>(inf + 4) = make_double4(rav[0], rav[1], rav[2], rav[3]);
             *reinterpret_cast<double4*>(inf + 8) = make_double4(rwv[0], rwv[1], rwv[2], rwv[3]);
-            *reinterpret_cast<double2*>(inf + 12) = make_double2((double)mask, (na >= cap || j0 + 4 >= mc) ? 1.0 : 0.0);
+            *reinterpret_cast<double2*>(inf + 12) = make_double2((double)mask, (na >= cap || j0 + 4 >= mc || failed) ? 1.0 : 0.0);
+            inf[26] = failed ? 1.0 : 0.0;
             *reinterpret_cast<double2*>(inf + 14) = make_double2(W[1][0] * rwv[0], W[2][0] * rwv[0]);
             *reinterpret_cast<double4*>(inf + 16) = make_double4(W[2][1] * rwv[1], W[3][0] * rwv[0], W[3][1] * rwv[1], W[3][2] * rwv[2]);
             *reinterpret_cast<double4*>(inf + 20) = make_double4(A[1][0] * rav[0], A[2][0] * rav[0], A[2][1] * rav[1], A[3][0] * rav[0]);
@@ -779,6 +817,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             if (warp < nfw) store_pivot_block(cA, inf, K, TRa, LD, MC, nacc, r4, clist, keep, g.off_L, g.off_acc, tid, nfw * 32);
         }
         nacc += __popc((unsigned)(int)inf[12]);
+        if (inf[26] != 0.0) bm_failed = true;
         if (inf[13] != 0.0) break;                   // capacity reached (RbfModel.jl:402) or no candidates left
         // ---- 3. rank-4 update
         if (has_tile && tK > K) {
@@ -797,8 +836,10 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     SCHUR_STAMP(5);
     // thread 0 owns the last diagonal tile: it is alive until the end and has seen every accepted pivot
     if (nacc_diag >= 0) nacc = nacc_diag;
+    if (tid == 0 && bm && (bm_failed || nacc != mc)) { P.n_r4[b] = -1; return; }      // build mode: the general kernel takes the instance
     if (tid == 0) {
         P.n_r4[b] = nacc; if (P.status) P.status[b] = 0;
+        if (bm && P.alpha2_out) P.alpha2_out[b] = rf.alpha2;
         if (keep) {
             keep[g.off_acc + MC + 0] = inv_s; keep[g.off_acc + MC + 1] = (double)N0; keep[g.off_acc + MC + 2] = (double)nacc;
             keep[g.off_acc + MC + 3] = (double)mc;
