@@ -723,7 +723,8 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     //    training points, every other point a candidate that must be accepted: Pi_0^{-1}, panels, blocked Cholesky of N' Phi N in
     //    registers, then the two triangular solves of build_schur_kernel).  Instances that do not qualify (N <= p, more than 128
     //    reduced unknowns, ill-conditioned first p points, reduced matrix not positive definite) are left to the general kernel.
-    const SchurGeom bgeom = (p > 0 && train_stride > p) ? round4_schur_geom(n, p, train_stride - p) : SchurGeom{};
+    // (the geometry covers at most 128 reduced unknowns; an instance with more falls back on its own)
+    const SchurGeom bgeom = (p > 0 && train_stride > p) ? round4_schur_geom(n, p, train_stride - p < 128 ? train_stride - p : 128) : SchurGeom{};
     const char* bg_env = getenv("MRBF_BUILD_GENERAL");
     const bool reduced_route = !kp && e == cudaSuccess && bgeom.eligible && !(bg_env && atoi(bg_env) != 0) &&
                                build_schur_smem_doubles(k, bgeom.MC, p) * sizeof(double) <= SMEM_LIMIT;
@@ -965,6 +966,16 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
     }
     EvalParams E{};
     fill_eval(E, m, M, X, Y, J);       // with J the same pass also produces the values
+    if (E.pack && M > 8 && m->n <= 64 && m->B <= 65535 && m->k <= 16) {
+        // grids below one wave of the tensor-path sweep (Armijo / PS batches of a single run, the low end of the C5 sweep): split the
+        // centre tiles over several CTAs per point tile; partial sums are added in a fixed order by eval_split_reduce_kernel
+        const int z = eval_split_factor(M, m->B, m->pack_nt);
+        if (z > 1) {
+            const size_t ny = (size_t)m->B * M * m->k, nj = J ? ny * m->n : 0;
+            ENSURE(ctx->ws[18], sizeof(double) * (size_t)z * (ny + nj));
+            E.zsplit = z; E.partY = (double*)ctx->ws[18].p; E.partJ = J ? E.partY + (size_t)z * ny : nullptr;
+        }
+    }
     { Timed t_(ctx, 4); CK(launch_eval(E, ctx->stream, &nl)); }
     ctx->launches += nl;
     return MRBF_OK;

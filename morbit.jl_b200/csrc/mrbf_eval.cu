@@ -467,6 +467,16 @@ __host__ __device__ inline int pack_stride(int n) {
     while ((s & 15) != 4 && (s & 15) != 12) s += 4;
     return s;
 }
+int eval_split_factor(long long M, int B, int pack_nt) {
+    // CTAs of the tensor-path sweep: ceil(M / 128) x B, one per SM.  Below one wave the centre tiles are split so that ~one wave runs.
+    const long long ctas = ((M + DM_TM - 1) / DM_TM) * (long long)B;
+    if (ctas >= 148 || pack_nt < 2) return 1;
+    long long z = 148 / ctas;                       // never more than one wave: a second, nearly empty wave costs more than it gains
+    if (z < 1) z = 1;
+    if (z > pack_nt) z = pack_nt;
+    return (int)z;
+}
+
 int eval_pack_stride(int n) { return pack_stride(n); }
 
 __global__ void eval_pack_kernel(PackParams P) {
@@ -522,6 +532,8 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0)
     const long long m0 = (long long)blockIdx.x * DM_TM;
     const int N = P.N[b];
     const int ntiles = (N + DM_TN - 1) / DM_TN;
+    const int Z = (int)gridDim.z, zz = (int)blockIdx.z;                                   // centre tiles [t_lo, t_hi) of this CTA
+    const int t_lo = (int)(((long long)ntiles * zz) / Z), t_hi = (int)(((long long)ntiles * (zz + 1)) / Z);
     const double* centers = P.centers + (size_t)b * P.train_stride * n;
     const double* X = P.X + (size_t)b * P.M * n;
     const double* pack = P.pack + (size_t)b * P.pack_nt * P.pack_tile_doubles;
@@ -535,10 +547,10 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[1])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (ntiles > 0) {                        // tile 0 -> buffer 0
+        if (t_hi > t_lo) {                       // first tile -> buffer 0
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(tile_bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(buf0)), "l"(pack), "r"(tile_bytes), "r"(smem_u32(&bar[0])) : "memory");
+                         :: "r"(smem_u32(buf0)), "l"(pack + (size_t)t_lo * tile_d), "r"(tile_bytes), "r"(smem_u32(&bar[0])) : "memory");
         }
     }
     // X' tile: rows centred at the first centre, zero padded to the row stride
@@ -563,9 +575,9 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0)
     const int ksteps = ((n + 3) & ~3) >> 2;
     const double* xa = Xs + (32 * wm + qr) * s + qc;
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int cur = t & 1;
-        if (tid == 0 && t + 1 < ntiles) {        // prefetch tile t+1 into the other buffer (its readers passed the barrier below)
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int it = t - t_lo, cur = it & 1;
+        if (tid == 0 && t + 1 < t_hi) {          // prefetch tile t+1 into the other buffer (its readers passed the barrier below)
             const int nb = cur ^ 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(tile_bytes) : "memory");
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0)
                          :: "r"(smem_u32(nb ? buf1 : buf0)), "l"(pack + (size_t)(t + 1) * tile_d), "r"(tile_bytes), "r"(smem_u32(&bar[nb])) : "memory");
         }
         {                                        // wait for tile t
-            const unsigned parity = (unsigned)((t >> 1) & 1);
+            const unsigned parity = (unsigned)((it >> 1) & 1);
             unsigned ok = 0;
             while (!ok) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
@@ -638,6 +650,7 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0)
         if (mi < P.M) {
             for (int l = 0; l < kk; ++l) {
                 double v = Yp[tid * 4 + l] + Yp[(DM_TM + tid) * 4 + l];
+                if (Z > 1) { P.partY[(((size_t)zz * P.B + b) * P.M + mi) * k + l0 + l] = v; continue; }     // tail added by the reduction
                 if (P.deg >= 0) v += lam[l0 + l];
                 if (P.deg >= 1) {
                     double tsum = 0.0;
@@ -673,7 +686,7 @@ static cudaError_t launch_dmma(const EvalParams& P, cudaStream_t s, int* n_launc
     const int rk = rad_kind(P.kernel, P.ibeta);
     for (int l0 = 0; l0 < P.k; l0 += 4) {
         const int kk = (P.k - l0) < 4 ? (P.k - l0) : 4;
-        dim3 grid((unsigned)tiles, (unsigned)P.B);
+        dim3 grid((unsigned)tiles, (unsigned)P.B, (unsigned)(P.zsplit > 1 ? P.zsplit : 1));
         cudaError_t e;
         switch (rk) {
         case RK_CUBIC3: e = launch_dmma_k<RK_CUBIC3>(P, s, l0, kk, smem, grid); break;
@@ -702,6 +715,8 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
     const long long m0 = (long long)blockIdx.x * DM_TM;
     const int N = P.N[b];
     const int ntiles = (N + DM_TN - 1) / DM_TN;
+    const int Z = (int)gridDim.z, zz = (int)blockIdx.z;                                   // centre tiles [t_lo, t_hi) of this CTA
+    const int t_lo = (int)(((long long)ntiles * zz) / Z), t_hi = (int)(((long long)ntiles * (zz + 1)) / Z);
     const double* centers = P.centers + (size_t)b * P.train_stride * n;
     const double* X = P.X + (size_t)b * P.M * n;
     const double* pack = P.pack + (size_t)b * P.pack_nt * P.pack_tile_doubles;
@@ -716,10 +731,10 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[1])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (ntiles > 0) {
+        if (t_hi > t_lo) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[0])), "r"(tile_bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(buf0)), "l"(pack), "r"(tile_bytes), "r"(smem_u32(&bar[0])) : "memory");
+                         :: "r"(smem_u32(buf0)), "l"(pack + (size_t)t_lo * tile_d), "r"(tile_bytes), "r"(smem_u32(&bar[0])) : "memory");
         }
     }
     for (int e = tid; e < DM_TM * s; e += 256) {
@@ -747,9 +762,9 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
     const int ksteps = ((n + 3) & ~3) >> 2;
     const double* xa = Xs + (row0 + qr) * s + qc;
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int cur = t & 1;
-        if (tid == 0 && t + 1 < ntiles) {
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int it = t - t_lo, cur = it & 1;
+        if (tid == 0 && t + 1 < t_hi) {
             const int nb = cur ^ 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar[nb])), "r"(tile_bytes) : "memory");
@@ -757,7 +772,7 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
                          :: "r"(smem_u32(nb ? buf1 : buf0)), "l"(pack + (size_t)(t + 1) * tile_d), "r"(tile_bytes), "r"(smem_u32(&bar[nb])) : "memory");
         }
         {
-            const unsigned parity = (unsigned)((t >> 1) & 1);
+            const unsigned parity = (unsigned)((it >> 1) & 1);
             unsigned ok = 0;
             while (!ok) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
@@ -847,6 +862,18 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_jac_kernel(EvalParams P, int
 #pragma unroll
         for (int o = 0; o < KO; ++o) {
             const int lo_ = l0 + o;
+            if (Z > 1) {
+                if (P.Y && qc == 0) P.partY[(((size_t)zz * P.B + b) * P.M + mi) * k + lo_] = ysum[o][a];
+                double* Jp = P.partJ + ((((size_t)zz * P.B + b) * P.M + mi) * k + lo_) * n;
+#pragma unroll
+                for (int cbk = 0; cbk < 8; ++cbk)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * cbk + 2 * qc + e;
+                        if (cbk < ncb && col < n) Jp[col] = fma(Xs[row * s + col], gsum[o][a], -jacc[o][a][cbk][e]);
+                    }
+                continue;
+            }
             if (P.Y && qc == 0) {
                 double v = ysum[o][a];
                 if (P.deg >= 0) v += lam[lo_];
@@ -882,7 +909,7 @@ static cudaError_t launch_dmma_jac_t(const EvalParams& P, cudaStream_t s, int* n
     if (e != cudaSuccess) return e;
     const long long tiles = (P.M + DM_TM - 1) / DM_TM;
     for (int l0 = 0; l0 < P.k;) {                // two outputs per pass while there are two left
-        dim3 grid((unsigned)tiles, (unsigned)P.B);
+        dim3 grid((unsigned)tiles, (unsigned)P.B, (unsigned)(P.zsplit > 1 ? P.zsplit : 1));
         if (l0 + 1 < P.k) { eval_dmma_jac_kernel<RK, 2><<<grid, 256, smem, s>>>(P, l0); l0 += 2; }
         else { eval_dmma_jac_kernel<RK, 1><<<grid, 256, smem, s>>>(P, l0); l0 += 1; }
         if (n_launches) ++*n_launches;
@@ -940,6 +967,37 @@ static cudaError_t launch_wide(const EvalParams& P, cudaStream_t s, int* n_launc
     return cudaSuccess;
 }
 
+
+// Sum of the zsplit partial results in a fixed order, plus the polynomial tail (values: lambda_0 + lambda' x, Jacobian: lambda).
+__global__ void eval_split_reduce_kernel(EvalParams P) {
+    const int n = P.n, k = P.k, pl = P.p > 0 ? P.p : 1;
+    const size_t ny = (size_t)P.B * P.M * k, nj = P.J ? ny * n : 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < ny + nj; e += (size_t)gridDim.x * blockDim.x) {
+        if (e < ny) {
+            if (!P.Y) continue;
+            const int l = (int)(e % k); const size_t pm = e / k; const int b = (int)(pm / P.M);
+            double v = 0.0;
+            for (int z = 0; z < P.zsplit; ++z) v += P.partY[(size_t)z * ny + e];
+            const double* lam = P.lam + (size_t)b * pl * k;
+            if (P.deg >= 0) v += lam[l];
+            if (P.deg >= 1) {
+                const double* x = P.X + pm * n;
+                double tsum = 0.0;
+                for (int c = 0; c < n; ++c) tsum = fma(lam[(size_t)(c + 1) * k + l], x[c], tsum);
+                v += tsum;
+            }
+            P.Y[e] = v;
+        } else {
+            const size_t f = e - ny;
+            const int col = (int)(f % n); const size_t pml = f / n; const int l = (int)(pml % k); const int b = (int)(pml / k / P.M);
+            double v = 0.0;
+            for (int z = 0; z < P.zsplit; ++z) v += P.partJ[(size_t)z * nj + f];
+            if (P.deg >= 1) v += P.lam[(size_t)b * pl * k + (size_t)(col + 1) * k + l];
+            P.J[f] = v;
+        }
+    }
+}
+
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
     if (P.M <= 0 || P.B <= 0) return cudaSuccess;
     const bool want_j = P.J != nullptr;
@@ -955,7 +1013,17 @@ cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
             return cudaGetLastError();
         }
     }
-    if (P.pack && P.n <= 64 && P.B <= 65535 && P.k <= 16) return want_j ? launch_dmma_jac(P, s, n_launches) : launch_dmma(P, s, n_launches);
+    if (P.pack && P.n <= 64 && P.B <= 65535 && P.k <= 16) {
+        cudaError_t e = want_j ? launch_dmma_jac(P, s, n_launches) : launch_dmma(P, s, n_launches);
+        if (e == cudaSuccess && P.zsplit > 1) {
+            const size_t tot = (size_t)P.B * P.M * P.k * (want_j ? (size_t)(P.n + 1) : 1);
+            const unsigned blocks = (unsigned)((tot + 255) / 256 < 4096 ? (tot + 255) / 256 : 4096);
+            eval_split_reduce_kernel<<<blocks, 256, 0, s>>>(P);
+            if (n_launches) ++*n_launches;
+            e = cudaGetLastError();
+        }
+        return e;
+    }
     if (P.n <= 64 && P.B <= 65535) {
         const int cq = (P.n + 15) / 16;
         if (want_j) {

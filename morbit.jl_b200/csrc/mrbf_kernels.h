@@ -113,6 +113,9 @@ struct EvalParams {
     // tiled, centred copy of the model for the DMMA kernel (built once per model): per instance nt tiles of
     // [64 x s centre rows | 64 squared norms | k x 64 coefficients]
     const double* pack; int pack_s, pack_nt; size_t pack_tile_doubles;
+    // small grids (few trial points x few instances): the centre tiles are split over gridDim.z CTAs per point tile, partial sums
+    // go to partY / partJ (zsplit x the output shapes) and eval_split_reduce_kernel adds them in a fixed order plus the tail
+    int zsplit; double* partY; double* partJ;
 };
 
 struct PackParams {
@@ -188,6 +191,7 @@ size_t build_schur_smem_doubles(int k, int MC, int p);
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches);
 cudaError_t launch_eval_pack(const PackParams& P, cudaStream_t s);
 int eval_pack_stride(int n);
+int eval_split_factor(long long M, int B, int pack_nt);
 cudaError_t launch_descent_direction(const DescentParams& P, cudaStream_t s);
 size_t descent_warp_doubles(int n, int k);
 int descent_max_outputs();
