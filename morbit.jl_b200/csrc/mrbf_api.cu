@@ -250,6 +250,7 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
                 CK(cudaStreamSynchronize(ctx->stream));
                 fprintf(stderr, "[mrbf clock] prep: setup %lld GJ %lld | elim: load %lld panels %lld tiles %lld elim %lld | blocks (start->panel published):", h[1] - h[0],
                         h[2] - h[1], h[100] - h[6], h[7] - h[100], h[4] - h[7], h[5] - h[4]);
+                fprintf(stderr, " [tiles: distances %lld phi %lld C.V %lld]", h[101] - h[7], h[102] - h[101], h[4] - h[102]);
                 for (int K = 0; K < 40 && h[8 + 2 * K]; ++K) fprintf(stderr, " %lld/%lld", h[8 + 2 * K] - h[4], h[9 + 2 * K] ? h[9 + 2 * K] - h[8 + 2 * K] : -1LL);
                 fprintf(stderr, "\n[mrbf clock] per block: diag pivots / publish+arrive / panel wakes after arrive / panel work / next diag tile: panel published / updated / starts:");
                 for (int K = 0; K < 25 && h[128 + 8 * K]; ++K)

@@ -593,10 +593,12 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { const double d = ri[a] - rk[c]; A[a][c] = fma(d, d, A[a][c]); }
         }
+        SCHUR_STAMP(101);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int c = 0; c < 4; ++c) A[a][c] = rad_phi(rf, A[a][c]);
+        SCHUR_STAMP(102);
         for (int r = 0; r < p; ++r) {
             const double4 a4 = ld4(Cs + r * LD, tI, H), b4 = ld4(Cs + r * LD, tK, H);
             const double4 c4 = ld4(Vs + r * LD, tI, H), d4 = ld4(Vs + r * LD, tK, H);
