@@ -309,7 +309,7 @@ def run_ours(args):
         strong = {"metric": METRIC, "scaling": "strong", "value": B / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
                   "instances_total": B, "instances_per_gpu": per,
                   "limiter": f"one CTA per instance: {per} CTAs on {sms} SMs = {per / (2 * sms):.2f} waves of the rounds-1-3 kernel (2 CTAs/SM), "
-                             f"{per / (4 * sms):.2f} of the panels kernel (4/SM), {per / sms:.2f} of the elimination kernel (1/SM) -- the last, partly "
+                             f"{per / (4 * sms):.2f} of the round-4 pre-kernel (4/SM), {per / (2 * sms):.2f} of the elimination kernel (2/SM) -- the last, partly "
                              "filled wave of each kernel is the loss against ideal strong scaling; there is no communication on the data path",
                   "config": {"workload": f"C3 strong: {B} instances in total, [g B / G, (g + 1) B / G) on rank g"}}
         m_s.free(); del dev_s, b_s
@@ -666,7 +666,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "instances_per_gpu": B, "n_vars": N_VARS, "n_outputs": K_OUT, "db_sites": N_DB,
                            "kernel": KERNEL, "mean_training_points": float(Ntrain.mean()), "builds_ok": ok,
-                           "l2": "per-step working set (database sites 126 MB + round-4 panel workspace 0.5 GB + kept factorisations 0.8 GB) > 126 MB L2; no flush needed",
+                           "l2": "per-step working set (database sites 126 MB + kept factorisations 0.8 GB) > 126 MB L2; no flush needed",
                            "parallelism": f"instances sharded over {world} rank(s), no data-path collective"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
