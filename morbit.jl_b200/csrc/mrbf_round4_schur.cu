@@ -149,12 +149,14 @@ SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     return g;
 }
 
-#define SCHUR_STAMPX(i) do { if (P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
-#define SCHUR_STAMP(i) do { if (P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+// clock64 stamps of CTA 0 (MRBF_DEBUG_CLOCK=1); the elimination kernel is instantiated without them for production launches
+#define SCHUR_STAMPX(i) do { if (SCHUR_DBG && P.dbg_clock && b == 0) P.dbg_clock[(i)] = clock64(); } while (0)
+#define SCHUR_STAMP(i) do { if (SCHUR_DBG && P.dbg_clock && b == 0 && tid == 0) P.dbg_clock[(i)] = clock64(); } while (0)
 
 // Kernel 1 of 2: candidate list and Pi_0^{-1} of one instance, written to the hand-over workspace.  Small footprint (the
 // Gauss-Jordan scratch and the found sites in shared memory), so several instances share an SM and hide each other's pivot chains.
 __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, SchurGeom g) {
+    constexpr bool SCHUR_DBG = true;
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = poly_dim(n, P.cfg.polynomial_degree), pl = p;
@@ -464,7 +466,7 @@ __device__ __forceinline__ void lev_pass(double* __restrict__ Minv, const double
 // Two launch shapes of the same code, every instance is taken by exactly one: SMALL (<= 352 tiles, i.e. <= 100 candidates:
 // 352 + 32 threads, <= 80 registers and < 113 KB of shared memory, so two instances share an SM) and the full shape
 // (544 + 32 threads, <= 128 candidates).  RPL = rows of M per lane of the leverage warp (p <= 32 RPL).
-template <bool SMALL, int RPL>
+template <bool SMALL, int RPL, bool SCHUR_DBG>
 __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_kernel(Round4Params P, SchurGeom g) {
     extern __shared__ double smem[];
     const int b = blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -855,9 +857,15 @@ static cudaError_t launch_elim(const Round4Params& P, const SchurGeom& g, int nt
     cudaError_t e;
 #define MRBF_ELIM_CASE(R)                                                                                                          \
     case R:                                                                                                                        \
-        e = cudaFuncSetAttribute(round4_elim_kernel<SMALL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-        if (e != cudaSuccess) return e;                                                                                            \
-        round4_elim_kernel<SMALL, R><<<P.B, nthreads, smem, s>>>(P, g);                                                            \
+        if (P.dbg_clock) {                                                                                                         \
+            e = cudaFuncSetAttribute(round4_elim_kernel<SMALL, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            if (e != cudaSuccess) return e;                                                                                        \
+            round4_elim_kernel<SMALL, R, true><<<P.B, nthreads, smem, s>>>(P, g);                                                  \
+        } else {                                                                                                                   \
+            e = cudaFuncSetAttribute(round4_elim_kernel<SMALL, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                                        \
+            round4_elim_kernel<SMALL, R, false><<<P.B, nthreads, smem, s>>>(P, g);                                                 \
+        }                                                                                                                          \
         break;
     switch (rpl) {
         MRBF_ELIM_CASE(1)
