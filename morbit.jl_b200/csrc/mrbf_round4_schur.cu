@@ -109,7 +109,7 @@ __host__ __device__ inline ElimLayout elim_layout(int p, int n, int LD) {
     L.C = 0; L.V = pl * LD; L.Xc = L.V + pl * LD; L.ring = L.V;
     int regB = (pl + n) * LD; if (regB < 24 * LD) regB = 24 * LD;
     const int baseC = L.V + regB;
-    L.X0 = baseC; L.M0 = (L.X0 + pl * n + 3) & ~3; L.P00 = (L.M0 + pl * pl + 3) & ~3;
+    L.X0 = baseC; L.M0 = (L.X0 + pl * (n | 1) + 3) & ~3; L.P00 = (L.M0 + pl * pl + 3) & ~3;     // X0: odd row stride (no bank conflicts)
     int endC1 = L.P00 + pl * pl;
     L.Minv = baseC; L.su = (L.Minv + pl * L.PS + 3) & ~3;
     int endC2 = L.su + 4 * pg;
@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     unsigned long long* barG = barP + 3;                                                 // [3] leverage block ready
     int* clist = reinterpret_cast<int*>(smem + L.clist);
     const int PS = L.PS;
+    const int nx = n | 1;                           // row stride of X0
 
     // ---- found sites, Pi_0^{-T}, candidate list and candidate sites (coordinate-major; the padding columns repeat the
     // centre: finite, never a pivot)
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
         for (int e = tid; e < p * n; e += nt) {
             const int i = e / n, k = e % n;
-            X0[e] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k]);
+            X0[i * nx + k] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k]);
         }
         for (int e = tid; e < p * p; e += nt) { const double v = pw[g.pw_M0 + e]; M0[e] = v; if (keep) keep[g.off_M0 + e] = v; }
         const int* cl = reinterpret_cast<const int*>(pw + g.pw_clist);
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         for (int e = tid; e < p * p; e += nt) {
             const int i = e % p, j = e / p;
             double r2 = 0.0;
-            for (int k = 0; k < n; ++k) { const double d = X0[i * n + k] - X0[j * n + k]; r2 = fma(d, d, r2); }
+            for (int k = 0; k < n; ++k) { const double d = X0[i * nx + k] - X0[j * nx + k]; r2 = fma(d, d, r2); }
             P00[i + j * p] = rad_phi(rf, r2);
         }
         __syncthreads();
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                 const double mv = M0[r + (k + 1) * p] * inv_s, xc = X0[k];
                 c0 = fma(mv, x.x - xc, c0); c1 = fma(mv, x.y - xc, c1); c2 = fma(mv, x.z - xc, c2); c3 = fma(mv, x.w - xc, c3);
             }
-            const double xr = X0[r * n + k];
+            const double xr = X0[r * nx + k];
             double e_;
             e_ = x.x - xr; d0 = fma(e_, e_, d0); e_ = x.y - xr; d1 = fma(e_, e_, d1);
             e_ = x.z - xr; d2 = fma(e_, e_, d2); e_ = x.w - xr; d3 = fma(e_, e_, d3);
