@@ -620,13 +620,21 @@ __global__ void __launch_bounds__(64, 16) build_schur_kernel(SchurBuildParams P)
         y0[e] = (i < nf) ? values[(size_t)(found[i] - 1) * k + o] : (r3v ? r3v[(size_t)(i - nf) * k + o] : 0.0);
     }
     double* centers = P.centers + (size_t)b * P.train_stride * n;
-    for (int e = tid; e < N * n; e += nt) {
-        const int i = e / n, c = e % n;
-        double v;
-        if (i < nf) v = sites[(size_t)(found[i] - 1) * n + c];
-        else if (i < N0) v = r3s[(size_t)(i - nf) * n + c];
-        else v = sites[(size_t)(r4[i - N0] - 1) * n + c];
-        centers[e] = v;
+    // centres = [found; round-3 sites; accepted candidates]: a warp per row, four rows in flight (id lookup, coalesced row read, store)
+    for (int i0 = 4 * warp; i0 < N; i0 += 4 * nwarps) {
+        const double* src[4];
+#pragma unroll
+        for (int u_ = 0; u_ < 4; ++u_) {
+            const int i = i0 + u_;
+            src[u_] = (i >= N) ? nullptr : ((i < nf) ? sites + (size_t)(found[i] - 1) * n : ((i < N0) ? r3s + (size_t)(i - nf) * n : sites + (size_t)(r4[i - N0] - 1) * n));
+        }
+        for (int c = lane; c < n; c += 32) {
+            double v[4];
+#pragma unroll
+            for (int u_ = 0; u_ < 4; ++u_) v[u_] = src[u_] ? src[u_][c] : 0.0;
+#pragma unroll
+            for (int u_ = 0; u_ < 4; ++u_) if (src[u_]) centers[(size_t)(i0 + u_) * n + c] = v[u_];
+        }
     }
     __syncthreads();
     for (int e = tid; e < m * k; e += nt) {      // r = Y_acc - C_acc' Y_0, stored by candidate position
@@ -706,13 +714,31 @@ __global__ void __launch_bounds__(64, 16) build_schur_kernel(SchurBuildParams P)
     double* w_out = P.w + (size_t)b * P.train_stride * k;
     double* lam_out = P.lam + (size_t)b * p * k;
     for (int e = tid; e < m * k; e += nt) { const int q = e / k, o = e % k; w_out[(size_t)(p + q) * k + o] = rv[o * MC + accpos[q]]; }
-    for (int e = warp; e < p * k; e += nwarps) { // w_0 = -C_acc u ; t0 = Y_0 - U_acc u   (warp per entry, lanes over the accepted points)
-        const int r = e / k, o = e % k;
+    // w_0 = -C_acc u ; t0 = Y_0 - U_acc u : a warp takes four rows of C and U at a time (lanes over the accepted points), so eight row
+    // reads are in flight and the eight reductions overlap -- one (row, output) entry per pass was a chain of DRAM latencies
+    const int nrc = (p + 3) >> 2;
+    for (int e = warp; e < nrc * k; e += nwarps) {
+        const int r0 = 4 * (e / k), o = e % k;
         const double* u = rv + o * MC;
-        double a = 0.0, g = 0.0;
-        for (int q = lane; q < m; q += 32) { const int pos = accpos[q]; a = fma(Cg[(size_t)r * MC + pos], u[pos], a); g = fma(Ug[(size_t)r * MC + pos], u[pos], g); }
-        a = warp_sum(a); g = warp_sum(g);
-        if (lane == 0) { w_out[(size_t)r * k + o] = -a; t0[e] = y0[e] - g; }
+        double a[4] = {0.0, 0.0, 0.0, 0.0}, g_[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int q = lane; q < m; q += 32) {
+            const int pos = accpos[q];
+            const double uv = u[pos];
+#pragma unroll
+            for (int u_ = 0; u_ < 4; ++u_) {
+                const int r = min(r0 + u_, p - 1);
+                a[u_] = fma(Cg[(size_t)r * MC + pos], uv, a[u_]); g_[u_] = fma(Ug[(size_t)r * MC + pos], uv, g_[u_]);
+            }
+        }
+#pragma unroll
+        for (int u_ = 0; u_ < 4; ++u_) { a[u_] = warp_sum(a[u_]); g_[u_] = warp_sum(g_[u_]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int u_ = 0; u_ < 4; ++u_) {
+                const int r = r0 + u_;
+                if (r < p) { w_out[(size_t)r * k + o] = -a[u_]; t0[r * k + o] = y0[r * k + o] - g_[u_]; }
+            }
+        }
     }
     __syncthreads();
     for (int e = tid; e < p * k; e += nt) {      // lambda~ = Pi_0^{-1} t0 = M0' t0
