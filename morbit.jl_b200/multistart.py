@@ -125,11 +125,14 @@ class HostPipeline:
     OUTS = ("r1", "n_r1", "r2", "n_r2", "n_r3", "r4", "n_r4", "flags_out")
 
     def __init__(self, engine: Engine, cfg, delta_max: float, host: dict, device: str, compute_stream, chunks: int = 2, buffers: int = 1,
-                 outputs: int = 1, resident_db: bool = False):
+                 outputs: int = 1, resident_db: bool = False, append_rows: int = 0):
         """resident_db: the databases (sites, values) are uploaded ONCE and stay on the device (grown with
         mrbf_db_append_dev by a driver); a step then uploads only what changes between two model updates on the same database --
         iterate, radius, flags, budget -- as in the reference's criticality loop (algorithm.jl:523-612), which rebuilds the models
-        for a shrinking radius on an unchanged database."""
+        for a shrinking radius on an unchanged database.
+        append_rows (with resident_db): every step additionally uploads the LAST `append_rows` rows of every database (site + values: the
+        evaluations an iteration adds, Databases.jl:390-401) and appends them on the device with mrbf_db_append_dev -- the resident
+        databases hold the rows before them, `n_db - append_rows` travels as the per-step size; the result of a step is unchanged."""
         import torch
         self.torch = torch
         self.resident_db = bool(resident_db)
@@ -159,12 +162,29 @@ class HostPipeline:
         self.ev_comp = [[torch.cuda.Event() for _ in range(self.buffers)] for _ in range(chunks)]
         self.ev_out = [[torch.cuda.Event() for _ in range(self.outputs)] for _ in range(chunks)]
         self.step_names = tuple(k for k in self.NAMES if not (self.resident_db and k in ("sites", "values")))
+        self.append_rows = int(append_rows) if self.resident_db else 0
+        self.new_pinned, self.new_dev, self.n_add = [], [], []
+        if self.append_rows > 0:
+            a = self.append_rows
+            for c, (lo, hi) in enumerate(self.bounds):
+                nd = np.asarray(host["n_db"][lo:hi]).astype(np.int64)
+                assert np.all(nd >= a), "append_rows larger than a database"
+                rows = (nd[:, None] - a + np.arange(a)[None, :])                                 # the last a rows of every database
+                ns = np.take_along_axis(np.asarray(host["sites"][lo:hi]), rows[:, :, None], axis=1)
+                nv = np.take_along_axis(np.asarray(host["values"][lo:hi]), rows[:, :, None], axis=1)
+                self.new_pinned.append((torch.from_numpy(np.ascontiguousarray(ns)).to(f64).pin_memory(),
+                                        torch.from_numpy(np.ascontiguousarray(nv)).to(f64).pin_memory()))
+                self.new_dev.append([(torch.empty_like(self.new_pinned[c][0], device=device), torch.empty_like(self.new_pinned[c][1], device=device))
+                                     for _ in range(self.buffers)])
+                self.n_add.append(torch.full((hi - lo,), a, dtype=i32, device=device))
+                self.pinned[c]["n_db"] = (self.pinned[c]["n_db"] - a).pin_memory()               # size before this step's evaluations arrive
         if self.resident_db:
             for c, pc in enumerate(self.pinned):
                 for d in self.dev[c]:
                     d.sites.copy_(pc["sites"]); d.values.copy_(pc["values"])
             torch.cuda.synchronize()
         self.h2d_bytes = sum(pc[k].numel() * pc[k].element_size() for pc in self.pinned for k in self.step_names)
+        self.h2d_bytes += sum(t_.numel() * t_.element_size() for pair in self.new_pinned for t_ in pair)
         self.d2h_bytes = 0
 
     def step(self):
@@ -179,10 +199,16 @@ class HostPipeline:
                 self.copy_in.wait_event(self.ev_comp[c][t])       # this device buffer of the slice is free again
                 for k in self.step_names:
                     getattr(self.dev[c][t], k).copy_(self.pinned[c][k], non_blocking=True)
+                if self.append_rows > 0:
+                    self.new_dev[c][t][0].copy_(self.new_pinned[c][0], non_blocking=True)
+                    self.new_dev[c][t][1].copy_(self.new_pinned[c][1], non_blocking=True)
                 self.ev_in[c].record(self.copy_in)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self.ev_in[c])
                 self.compute.wait_event(self.ev_out[c][u])        # the last result copy out of this set of output buffers has left
+                if self.append_rows > 0:                          # new_result! of this step's evaluations, on the device
+                    d_ = self.dev[c][t]
+                    self.engine.db_append_dev(d_.sites, d_.values, d_.n_db, self.new_dev[c][t][0], self.new_dev[c][t][1], self.n_add[c])
                 self.models[c][u], sel, status = self.builders[c][u].step(self.dev[c][t], recycle=self.models[c][u])
                 self.ev_comp[c][t].record(self.compute)
             outs = [getattr(sel, k) for k in self.OUTS] + [status]

@@ -363,6 +363,41 @@ def test_host_pipeline_overlapped_copies_match_oracle(engine, chunks, buffers, o
         m.free()
 
 
+@pytest.mark.parametrize("append_rows,chunks", [(0, 1), (1, 1), (3, 2)])
+def test_host_pipeline_resident_databases_with_appended_rows(engine, append_rows, chunks):
+    """HostPipeline(resident_db=True, append_rows=a): the databases stay on the device, every step uploads the last `a` rows of every
+    database (the evaluations an iteration adds) and appends them with mrbf_db_append_dev, `n_db - a` travels as the size.  Ragged
+    databases; the indices must be the oracle's on the full databases, step after step (the append lands in the same rows)."""
+    import torch
+    from morbit_jl_b200 import synthetic
+    from morbit_jl_b200.multistart import HostPipeline
+    B, n, n_db = 17, 10, 48
+    cfg = mb.RbfConfig(kernel="cubic")
+    host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=0.1, func=synthetic.zdt3, local_fraction=0.5)
+    host["n_db"] = np.maximum(8, n_db - np.arange(B)).astype(np.int32)                      # ragged
+    ref = [CO.select_points_batched(cfg, host["sites"][b:b + 1, :host["n_db"][b]], host["x_index"][b:b + 1], host["x"][b:b + 1], host["delta"][b:b + 1],
+                                    host["delta_max"], host["glb"], host["gub"], False, False, host["max_new"][b:b + 1], nthreads=1) for b in range(B)]
+    stream = torch.cuda.Stream()
+    eng = mb.Engine(0, stream=stream.cuda_stream)
+    pipe = HostPipeline(eng, cfg, host["delta_max"], host, "cuda:0", stream, chunks=chunks, buffers=2, outputs=2, resident_db=True,
+                        append_rows=append_rows)
+    snap_bytes = host["sites"].nbytes + host["values"].nbytes
+    assert pipe.h2d_bytes < snap_bytes / 4
+    for _ in range(4):
+        models, outs = pipe.step()
+        pipe.drain()
+        stream.synchronize()
+        for c, (lo, hi) in enumerate(pipe.bounds):
+            o = dict(zip(HostPipeline.OUTS + ("status",), (t.numpy() for t in outs[c])))
+            assert np.all(o["status"] == 0)
+            for b in range(lo, hi):
+                for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+                    assert list(o[nm][b - lo, :o[cnt][b - lo]]) == list(getattr(ref[b], nm)[0, :getattr(ref[b], cnt)[0]]), (b, nm)
+                assert o["n_r3"][b - lo] == ref[b].n_r3[0]
+    for m in models:
+        m.free()
+
+
 def test_c3_full_size_properties(engine):
     """BASELINE config C3 at full size (4096 instances, n = 30, k = 2, 128 database sites): size-independent properties of the
     whole batch plus exact parity with the oracle on a sample of instances."""

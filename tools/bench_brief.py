@@ -8,7 +8,8 @@ for line in open(sys.argv[1]):
         print(d); continue
     print(f"{d.get('impl', 'gpu')}: {d['value']:.0f} {d['unit']}  {d['ms_per_step']:.3f} ms/step  n_gpus={d['n_gpus']}")
     e = d.get("e2e") or {}
-    print("  e2e", round(e.get("value", 0)), "resident", round((d.get("e2e_resident") or {}).get("value", 0)))
+    print("  e2e", round(e.get("value", 0)), "h2d", e.get("h2d_bytes_per_step"), "snapshot", round((d.get("e2e_snapshot") or {}).get("value", 0)),
+          "resident", round((d.get("e2e_resident") or {}).get("value", 0)))
     r = d.get("roofline") or {}
     print("  roofline", r.get("kernel"), round(r.get("frac", 0), 4), "kernel_ms", r.get("kernel_ms"))
     c = d.get("cpu_baseline") or {}
