@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         double U4[RPL][4];
         int nacc_l = 0;                              // accepted before block K - 1
         for (int K = 0; K <= TRa; ++K) {
-            const int slot = K % 3, j0 = 4 * K;
+            const int slot = K % 3;
             bool upd = false;
             double av[RPL][4];
 #pragma unroll
