@@ -119,6 +119,17 @@ __host__ __device__ inline ElimLayout elim_layout(int p, int n, int LD) {
     return L;
 }
 
+// the same wait for warps that have slack: sleep between the polls instead of competing for issue slots with the pivot chain
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
+
 SchurGeom round4_schur_geom(int n, int p, int db_stride) {
     SchurGeom g{};
     const int pl = p > 0 ? p : 1;
@@ -813,7 +824,8 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
             else { mbar_arrive_drop(&barP[slot]); mbar_arrive_drop(&barP[(slot + 1) % 3]); mbar_arrive_drop(&barP[(slot + 2) % 3]); }
         }
         if (leaving) break;
-        mbar_wait(&barP[slot], par);
+        if (__any_sync(0xffffffffu, has_tile && tK == K + 1)) mbar_wait(&barP[slot], par);      // next tile column: on the pivot chain
+        else mbar_wait_relaxed(&barP[slot], par);
         if (K < 40) SCHUR_STAMP(9 + 2 * K);
         if (K < 25 && has_tile && tK == K + 1 && tI == K + 1) SCHUR_STAMPX(128 + 8 * K + 5);
         {   // results of this block: by the warps whose tiles all lie right of tile column K + 1 (they have arrived long ago and have
