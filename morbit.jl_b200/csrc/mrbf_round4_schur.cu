@@ -100,6 +100,7 @@ __device__ __forceinline__ int off4(int i, int H) { return ((i >> 2) << 1) + (i 
 //   phase "panels":  C (p x LD) | V (p x LD) | Xc (n x LD) || X0 (p x n) | M0 (p x p) | P00 (p x p) || fixed
 //   phase "elim":    C (p x LD) | ring[3] of { colA, colAs : [4][LD] } .... || M (p x PS) | su (p x 4)  || fixed
 // fixed: G blocks [3][16], info [3][28], barriers [9], clist (LD ints)
+constexpr int LEV_MS = 36;      // row stride of M for the tensor-path leverage warp: rows 32 bytes apart modulo 128 (fragment loads without bank conflicts)
 struct ElimLayout { int C, V, Xc, ring, X0, M0, P00, Minv, su, gs, inf, bar, clist, total, PS; };
 __host__ __device__ inline ElimLayout elim_layout(int p, int n, int LD) {
     ElimLayout L;
@@ -113,6 +114,7 @@ __host__ __device__ inline ElimLayout elim_layout(int p, int n, int LD) {
     int endC1 = L.P00 + pl * pl;
     L.Minv = baseC; L.su = (L.Minv + pl * L.PS + 3) & ~3;
     int endC2 = L.su + 4 * pg;
+    if (pl <= 32) { L.su = L.Minv + 32 * LEV_MS; endC2 = L.su + 3 * 128; }     // tensor-path leverage warp: M 32 x LEV_MS, u~, -u~/(1+lev), U (32 x 4 each)
     int endC = endC1 > endC2 ? endC1 : endC2; endC = (endC + 3) & ~3;
     L.gs = endC; L.inf = L.gs + 48; L.bar = L.inf + 84; L.clist = L.bar + 12;
     L.total = L.clist + (LD + 1) / 2 + 2;
@@ -472,6 +474,11 @@ __device__ __forceinline__ void lev_pass(double* __restrict__ Minv, const double
     }
 }
 
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {      // D (8 x 8) += A (8 x 4) B (4 x 8), FP64 tensor path
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
 // Kernel 2 of 2: the panels C, V and the candidate sites are computed into shared memory, every tile thread computes its
 // 4 x 4 tile of A and the blocked elimination runs in registers; the last warp supplies the leverage blocks (header comment).
 // Two launch shapes of the same code, every instance is taken by exactly one: SMALL (<= 352 tiles, i.e. <= 100 candidates:
@@ -627,8 +634,13 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                 }
         }
     } else if (lev_warp) {
-        for (int e = lane; e < p * PS; e += 32) Minv[e] = (e / PS == e % PS) ? 1.0 : 0.0;      // no candidate accepted yet: M = I
-        for (int e = lane; e < 4 * (PS - 1); e += 32) su[e] = 0.0;
+        if (RPL == 1) {                             // tensor-path layout: M 32 x LEV_MS (zero beyond p), u~ / -u~/(1+lev) / U 32 x 4
+            for (int e = lane; e < 32 * LEV_MS; e += 32) Minv[e] = (e / LEV_MS == e % LEV_MS && e / LEV_MS < p) ? 1.0 : 0.0;
+            for (int e = lane; e < 3 * 128; e += 32) su[e] = 0.0;
+        } else {
+            for (int e = lane; e < p * PS; e += 32) Minv[e] = (e / PS == e % PS) ? 1.0 : 0.0;      // no candidate accepted yet: M = I
+            for (int e = lane; e < 4 * (PS - 1); e += 32) su[e] = 0.0;
+        }
     }
     __syncthreads();                                // V, Xc are dead from here on: the ring of pivot panels takes their place
     SCHUR_STAMP(4);
@@ -664,6 +676,15 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                     upd = true;
                     const double4 rw = *reinterpret_cast<const double4*>(pin + 8);
                     const double l10 = pin[14], l20 = pin[15], l21 = pin[16], l30 = pin[17], l31 = pin[18], l32 = pin[19];
+                    if (RPL == 1) {                 // tensor path: U of the previous block comes from shared memory, lane = row
+                        const double4 Uv = *reinterpret_cast<const double4*>(su + 256 + 4 * lane);
+                        const double u0 = Uv.x;
+                        const double u1 = fma(-u0, l10, Uv.y);
+                        const double u2 = fma(-u1, l21, fma(-u0, l20, Uv.z));
+                        const double u3 = fma(-u2, l32, fma(-u1, l31, fma(-u0, l30, Uv.w)));
+                        *reinterpret_cast<double4*>(su + 4 * lane) = make_double4(u0, u1, u2, u3);
+                        *reinterpret_cast<double4*>(su + 128 + 4 * lane) = make_double4(-rw.x * u0, -rw.y * u1, -rw.z * u2, -rw.w * u3);
+                    } else
 #pragma unroll
                     for (int rr = 0; rr < RPL; ++rr) {
                         const int r = lane + 32 * rr;
@@ -690,6 +711,69 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
                 continue;
             }
             if (K < 25 && lane == 0) SCHUR_STAMPX(341 + 4 * K);
+            if (RPL == 1) {
+                // ---- p <= 32: the three products of the block on the FP64 tensor path (mma.m8n8k4): a tenth of the instructions of the
+                // lane-per-row pass below, which made this warp -- one serial resource per instance -- the pace setter of the elimination
+                //   M -= (u~ / (1 + lev)) u~'     16 tiles, accumulator fragments loaded from / stored to shared memory
+                //   U  = M C_J                    32 x 8 (4 used), A fragments of M from shared memory
+                //   G  = I + C_J' U               8 x 8 (4 x 4 used), U through shared memory as the B operand
+                const int fg = lane >> 2, ft = lane & 3;
+                double* ub = su; double* nb = su + 128; double* Ub = su + 256;
+                if (upd) {                          // (u~ and -u~ / (1 + lev) were written below, before this point, by lane = row)
+                    double af[4], bf[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) { af[mt] = nb[(8 * mt + fg) * 4 + ft]; bf[mt] = ub[(8 * mt + fg) * 4 + ft]; }
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt_ = 0; nt_ < 4; ++nt_) {
+                            double2* mp = reinterpret_cast<double2*>(Minv + (8 * mt + fg) * LEV_MS + 8 * nt_ + 2 * ft);
+                            const double2 c2 = *mp;
+                            double d[2] = {c2.x, c2.y};
+                            dmma884(d, af[mt], bf[nt_]);
+                            *mp = make_double2(d[0], d[1]);
+                        }
+                    __syncwarp();
+                }
+                double cf[8];                       // C[4 ks + ft][j0 + fg]: B fragment of U = M C_J and A fragment of G = C_J' U
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) { const int k = 4 * ks + ft; cf[ks] = (fg < 4 && k < p) ? Cs[k * LD + off4(4 * K + fg, H)] : 0.0; }
+                double Ua[4][2];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) { Ua[mt][0] = 0.0; Ua[mt][1] = 0.0; }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) dmma884(Ua[mt], Minv[(8 * mt + fg) * LEV_MS + 4 * ks + ft], cf[ks]);
+                if (ft < 2) {
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) *reinterpret_cast<double2*>(Ub + (8 * mt + fg) * 4 + 2 * ft) = make_double2(Ua[mt][0], Ua[mt][1]);
+                }
+                __syncwarp();
+                double Gd[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) dmma884(Gd, cf[ks], (fg < 4) ? Ub[(4 * ks + ft) * 4 + fg] : 0.0);
+                if (fg < 4 && ft < 2) {             // G(a = fg, b = 2 ft + e), lower triangle, index a (a + 1) / 2 + b
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int gb = 2 * ft + e;
+                        if (gb <= fg) gs[slot * 16 + (fg * (fg + 1)) / 2 + gb] = Gd[e] + (gb == fg ? 1.0 : 0.0);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&barG[slot]);
+                if (K < 25 && lane == 0) SCHUR_STAMPX(343 + 4 * K);
+                if (K > 0) {                        // results of block K - 1 (the leverage block of K is on its way: this is idle time)
+                    const int ps = (K - 1) % 3;
+                    const double* pin = info + ps * 28;
+                    if ((schur_tiles(max(TRa - (K - 1) - 2, 0)) >> 5) == 0) {
+                        mbar_wait(&barP[ps], (unsigned)(((K - 1) / 3) & 1));
+                        store_pivot_block(ring + (size_t)ps * 8 * LD, pin, K - 1, TRa, LD, MC, nacc_l, r4, clist, keep, g.off_L, g.off_acc, lane, 32);
+                    }
+                    nacc_l += __popc((unsigned)(int)pin[12]);
+                }
+                continue;
+            }
             lev_pass<RPL>(Minv, su, Cs, K, LD, PS, p, lane, upd, av, U4);
             if (K < 25 && lane == 0) SCHUR_STAMPX(342 + 4 * K);
             double v[16];
