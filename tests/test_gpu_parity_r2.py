@@ -285,3 +285,38 @@ def test_build_error_contract(engine):
     assert rc == mb._lib.MRBF_EINVAL and not handle.value
     assert b"kernel/shape" in engine.lib.mrbf_last_error(engine.ctx)
     prepared.free()
+
+
+def test_build_routes_agree_and_fall_back_per_instance(engine):
+    """mrbf_build picks its route per instance: the reduced system on the first p training points, or the QR-based kernel
+    when those points are not poised / the set is too small or too large.  One batch with all the cases; every instance must match the
+    oracle, and the forced QR route (MRBF_BUILD_GENERAL=1) must agree with the default one."""
+    import os
+    rng = np.random.default_rng(77)
+    n, k, ts = 4, 2, 150
+    cfg = mb.RbfConfig(kernel="cubic")
+    Ns = np.array([40, 5, 3, 140, 40, 12], np.int32)            # 5 = p (no reduced unknowns), 3 < p, 140 - p > 128 (too large)
+    B = len(Ns)
+    S = rng.random((B, ts, n)); 
+    S[4, :5] = np.linspace(0.1, 0.9, 5)[:, None] * np.ones(n)   # first p points collinear: Pi_0 singular -> QR route
+    S[5, :5] = S[4, :5] + 1e-7 * rng.standard_normal((5, n))     # first p points affinely dependent up to 1e-7 (well separated): pivot guard -> QR route
+    V = np.stack([np.sum(S ** 2, -1), np.sum(np.sin(3 * S), -1)], -1)
+    X = rng.random((B, 9, n))
+    out = {}
+    for env in ("0", "1"):
+        os.environ["MRBF_BUILD_GENERAL"] = env
+        try:
+            model, status = engine.build(cfg, S, V, Ns)
+            assert np.all(status == 0), status
+            out[env] = engine.eval(model, X, True, True)
+            model.free()
+        finally:
+            os.environ["MRBF_BUILD_GENERAL"] = "0"
+    wr, lr, st = CO.build_batched(cfg, S, V, Ns, nthreads=2)
+    for b in range(B):
+        N = int(Ns[b])
+        Yr = CO.eval_points(cfg, S[b, :N], wr[b, :N], lr[b], X[b]); Jr = CO.jac_points(cfg, S[b, :N], wr[b, :N], lr[b], X[b])
+        for env in ("0", "1"):
+            Y, J = out[env]
+            assert np.abs(Y[b] - Yr).max() <= RTOL * np.abs(Yr).max(), (b, env, np.abs(Y[b] - Yr).max() / np.abs(Yr).max())
+            assert np.abs(J[b] - Jr).max() <= 1e-9 * np.abs(Jr).max(), (b, env, np.abs(J[b] - Jr).max() / np.abs(Jr).max())
