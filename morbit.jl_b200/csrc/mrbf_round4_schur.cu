@@ -26,7 +26,8 @@
 //     registers beside A's diagonal tile (so every accept pattern inside the block is covered) and returns the multipliers,
 //     from which the warp applies the rank-(#accepted) downdate of M.  That keeps the p x p recursion off the tile threads:
 //     half the registers of an elimination on the pair (A, I + C'C), so TWO instances share an SM and hide each other's
-//     pivot chains.
+//     pivot chains.  For p <= 32 the warp's three products per block (downdate of M, M C_J, C_J' M C_J) are mma.m8n8k4.f64
+//     instructions: the warp is one serial resource per instance and its instruction count sets the pace of the elimination.
 //   * two kernels: round4_prep_kernel (candidate list, Pi_0^{-1}; small footprint, several instances per SM) and
 //     round4_elim_kernel (panels in shared memory, tiles, elimination; in two launch shapes: <= 100 candidates on 352 + 32
 //     threads, two CTAs per SM, else 544 + 32 threads).
