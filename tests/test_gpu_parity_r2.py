@@ -320,3 +320,32 @@ def test_build_routes_agree_and_fall_back_per_instance(engine):
             Y, J = out[env]
             assert np.abs(Y[b] - Yr).max() <= RTOL * np.abs(Yr).max(), (b, env, np.abs(Y[b] - Yr).max() / np.abs(Yr).max())
             assert np.abs(J[b] - Jr).max() <= 1e-9 * np.abs(Jr).max(), (b, env, np.abs(J[b] - Jr).max() / np.abs(Jr).max())
+
+
+@pytest.mark.parametrize("n,n_db,kernel", [(3, 40, "gaussian"), (6, 100, "inv_multiquadric"), (10, 128, "multiquadric")])
+def test_round4_register_kernels_with_a_constant_tail(engine, n, n_db, kernel):
+    """polynomial_degree = 0 and no budget for round 3: the found set is the centre alone, which is exactly poised for the constant tail
+    (p = 1), so round 4 runs on the register-tiled kernels with a 1 x 1 Pi_0 and a 1 x 1 leverage matrix (tensor-path leverage warp with
+    31 rows of padding).  Indices as the oracle's; the model built from the kept factorisation interpolates."""
+    rng = np.random.default_rng(n * 1000 + n_db)
+    cfg = mb.RbfConfig(kernel=kernel, polynomial_degree=0)
+    B = 5
+    sites, x, glb, gub = random_instances(rng, B, n, n_db, True, spread=0.6)
+    xi = np.ones(B, np.int32); dl = np.full(B, 0.2)
+    ref = CO.select_points_batched(cfg, sites, xi, x, dl, 0.5, glb, gub, False, False, 0, nthreads=2)
+    res, prep = engine.select_points_keep(cfg, sites, np.full(B, n_db), xi, x, dl, 0.5, glb, gub, False, False, 0)
+    assert np.all(res.status == 0)
+    for b in range(B):
+        for nm, cnt in (("r1", "n_r1"), ("r2", "n_r2"), ("r4", "n_r4")):
+            assert list(getattr(res, nm)[b, :getattr(res, cnt)[b]]) == list(getattr(ref, nm)[b, :getattr(ref, cnt)[b]]), (b, nm)
+        assert res.n_r3[b] == ref.n_r3[b]
+    V = np.stack([np.sum(sites ** 2, -1), np.sum(np.sin(3 * sites), -1)], -1)
+    model, status = engine.build_prepared(cfg, prep, sites, V, xi, res, np.zeros((B, n, 2)))
+    assert np.all(status == 0)
+    for b in range(B):
+        ids = [1] + list(res.r1[b, :res.n_r1[b]]) + list(res.r2[b, :res.n_r2[b]]) + list(res.r4[b, :res.n_r4[b]])
+        if res.n_r3[b] == 0:
+            P = sites[b, np.array(ids) - 1]
+            Y, _ = engine.eval(model, np.repeat(P[None, :4], B, axis=0), True, False)
+            assert np.abs(Y[b] - V[b, np.array(ids[:4]) - 1]).max() <= 1e-8 * max(1.0, np.abs(V[b]).max())
+    prep.free(); model.free()
