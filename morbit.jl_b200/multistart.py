@@ -59,8 +59,12 @@ def upload_batch(host: dict, device: str = "cuda:0", pin: bool = False) -> Devic
 class MultistartBuilder:
     """select (rounds 1-4) -> gather -> build for a device-resident batch; buffers are reused across steps."""
 
-    def __init__(self, engine: Engine, cfg, delta_max: float):
-        self.engine, self.cfg, self.delta_max = engine, cfg, float(delta_max)
+    def __init__(self, engine: Engine, cfg, delta_max: float, func=None):
+        """func (optional): the objective, (M, n) sites -> (M, k) values on the host.  Round 3 can create NEW sites (RbfModel.jl:269-307)
+        whose values the build needs (eval_missing!, Databases.jl:258-277): with `func` the fused step evaluates them between the two
+        phases -- one host round trip, only when some instance has new sites; without it their values are taken as zero, which is only
+        right for batches that create none (e.g. the headline snapshots: every direction is covered by database sites)."""
+        self.engine, self.cfg, self.delta_max, self.func = engine, cfg, float(delta_max), func
         self._sel: Optional[SelectResult] = None
         self._train = None
         self._r3_values = None
@@ -110,6 +114,12 @@ class MultistartBuilder:
             self._r3_values = torch.zeros((B, n, k), dtype=torch.float64, device=d.sites.device)
         if self._status is None or self._status.shape[0] != B:
             self._status = torch.zeros(B, dtype=torch.int32, device=d.sites.device)
+        if self.func is not None:
+            new = torch.arange(n, device=d.sites.device)[None, :] < self._sel.n_r3[:, None]       # rows of r3_sites that are new sites
+            if bool(new.any()):
+                vals = np.asarray(self.func(self._sel.r3_sites[new].cpu().numpy()), dtype=np.float64).reshape(-1, k)
+                self._r3_values.zero_()
+                self._r3_values[new] = torch.from_numpy(vals).to(d.sites.device)
         model, status = self.engine.build_prepared_dev(self.cfg, prepared, d.sites, d.values, d.x_index, self._sel,
                                                        self._r3_values, self._status, recycle=recycle)
         return model, self._sel, status

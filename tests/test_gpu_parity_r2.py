@@ -349,3 +349,28 @@ def test_round4_register_kernels_with_a_constant_tail(engine, n, n_db, kernel):
             Y, _ = engine.eval(model, np.repeat(P[None, :4], B, axis=0), True, False)
             assert np.abs(Y[b] - V[b, np.array(ids[:4]) - 1]).max() <= 1e-8 * max(1.0, np.abs(V[b]).max())
     prep.free(); model.free()
+
+
+def test_multistart_builder_evaluates_new_round3_sites(engine):
+    """Sparse databases: round 3 creates new sites (RbfModel.jl:269-307).  MultistartBuilder(func=...) evaluates them between the
+    selection and the build from the kept factorisation, so the model interpolates the objective AT the new sites too."""
+    import torch
+    from morbit_jl_b200.multistart import MultistartBuilder, upload_batch
+    B, n, n_db = 12, 6, 4                                       # fewer sites than directions: round 3 has to create some
+    cfg = mb.RbfConfig(kernel="cubic")
+    host = synthetic.multistart_batch(B, n=n, n_db=n_db, delta=0.1, func=synthetic.zdt3, local_fraction=0.5)
+    dev = upload_batch(host, "cuda:0")
+    builder = MultistartBuilder(engine, cfg, host["delta_max"], func=synthetic.zdt3)
+    model, sel, status = builder.step(dev)
+    engine.sync()
+    assert np.all(status.cpu().numpy() == 0)
+    n_r3 = sel.n_r3.cpu().numpy(); r3 = sel.r3_sites.cpu().numpy()
+    assert n_r3.sum() > 0, "corpus creates no new sites"
+    X = np.zeros((B, n, n)); X[:] = host["x"][:, None, :]
+    for b in range(B):
+        X[b, :n_r3[b]] = r3[b, :n_r3[b]]
+    Y, _ = engine.eval(model, X, True, False)
+    for b in range(B):
+        for i in range(n_r3[b]):
+            assert np.abs(Y[b, i] - synthetic.zdt3(r3[b, i][None])[0]).max() <= 1e-8, (b, i)
+    model.free()

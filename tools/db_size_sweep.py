@@ -21,7 +21,7 @@ def main():
         B = 4096 if len(sys.argv) < 3 else int(sys.argv[2])
         host = synthetic.multistart_batch(B, n=30, n_db=n_db, delta=0.1, delta_max=0.5, func=synthetic.zdt3)
         dev = upload_batch(host, "cuda:0")
-        builder = MultistartBuilder(eng, cfg, 0.5)
+        builder = MultistartBuilder(eng, cfg, 0.5, func=synthetic.zdt3)          # new round-3 sites get their true values
         model = None
         with torch.cuda.stream(stream):
             for _ in range(2):
