@@ -44,7 +44,7 @@ enum mrbf_status {
     MRBF_EINVAL = -1,        /* bad argument */
     MRBF_ECUDA = -2,         /* CUDA runtime error */
     MRBF_ENOMEM = -3,
-    MRBF_EUNSUPPORTED = -4,  /* e.g. use_max_points (random sampling), polynomial degree > 1 */
+    MRBF_EUNSUPPORTED = -4,  /* e.g. use_max_points (random sampling), a kernel that needs a polynomial tail of degree > 2 */
     MRBF_ENUMERIC = -5       /* at least one instance failed numerically; see status[] */
 };
 

@@ -662,7 +662,7 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     if (rc != MRBF_OK) return rc;
     int deg = cfg->polynomial_degree;
     if (deg < cpd - 1) deg = cpd - 1;           // degree raised to cpd_order - 1 (assumption U4)
-    if (deg > 1) return fail(ctx, MRBF_EUNSUPPORTED, "kernel needs a polynomial tail of degree > 1%s");
+    if (deg > 2) return fail(ctx, MRBF_EUNSUPPORTED, "kernel needs a polynomial tail of degree > 2%s");
     const int p = poly_dim(n, deg), pl = p > 0 ? p : 1;
     mrbf_model* m = nullptr;
     cudaError_t e = cudaSuccess;
@@ -679,7 +679,7 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
         if (e == cudaSuccess) e = cudaMalloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
         if (e == cudaSuccess) e = cudaMalloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
         if (e == cudaSuccess) e = cudaMalloc(&m->alpha2, sizeof(double) * (size_t)B);
-        if (e == cudaSuccess && n <= 64 && k <= 16) {   // geometry of the tiled copy; the buffer itself is allocated on first use
+        if (e == cudaSuccess && n <= 64 && k <= 16 && deg <= 1) {   // geometry of the tiled copy; the buffer itself is allocated on first use
             m->pack_s = eval_pack_stride(n); m->pack_nt = (train_stride + 63) / 64;
             m->pack_tile_doubles = (size_t)64 * m->pack_s + 64 + (size_t)k * 64;
         }
@@ -725,7 +725,7 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
     //    registers, then the two triangular solves of build_schur_kernel).  Instances that do not qualify (N <= p, more than 128
     //    reduced unknowns, ill-conditioned first p points, reduced matrix not positive definite) are left to the general kernel.
     // (the geometry covers at most 128 reduced unknowns; an instance with more falls back on its own)
-    const SchurGeom bgeom = (p > 0 && train_stride > p) ? round4_schur_geom(n, p, train_stride - p < 128 ? train_stride - p : 128) : SchurGeom{};
+    const SchurGeom bgeom = (p > 0 && deg <= 1 && train_stride > p) ? round4_schur_geom(n, p, train_stride - p < 128 ? train_stride - p : 128) : SchurGeom{};
     const char* bg_env = getenv("MRBF_BUILD_GENERAL");
     const bool reduced_route = !kp && e == cudaSuccess && bgeom.eligible && !(bg_env && atoi(bg_env) != 0) &&
                                build_schur_smem_doubles(k, bgeom.MC, p) * sizeof(double) <= SMEM_LIMIT;

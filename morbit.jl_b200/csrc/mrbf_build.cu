@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT) build_kernel(BuildParams P) {
         }
         __syncthreads();                                      // the staging area may be reused below
     }
-    for (int e = tid; e < N * p; e += nt) { const int i = e % N, c = e / N; Pm[i + (size_t)c * ld] = (c == 0) ? 1.0 : sites[(size_t)i * n + c - 1]; }
+    for (int e = tid; e < N * p; e += nt) { const int i = e % N, c = e / N; Pm[i + (size_t)c * ld] = poly_basis_at(sites + (size_t)i * n, n, c); }
     for (int e = tid; e < N * k; e += nt) { const int i = e % N, q = e / N; Yv[i + (size_t)q * ld] = values[(size_t)i * k + q]; }
     __syncthreads();
 

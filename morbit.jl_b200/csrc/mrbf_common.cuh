@@ -176,7 +176,18 @@ __device__ inline double intersect_box_absmax(int n, const double* x, const doub
     return fabs(s_pos) >= fabs(s_neg) ? s_pos : s_neg;
 }
 
-__host__ __device__ inline int poly_dim(int n, int deg) { return deg < 0 ? 0 : (deg == 0 ? 1 : n + 1); }
+// dimension of the polynomial tail: none, constants, linear, or full quadratic (monomials 1, x_1..x_n, x_i x_j with i <= j, i outer).
+// Degree 2 only arises when a kernel's order of conditional positive definiteness raises the configured degree (thin plate spline
+// k = 2, cubic beta = 5): the build and the generic evaluation kernel handle it, round 4 always works with the configured degree.
+__host__ __device__ inline int poly_dim(int n, int deg) { return deg < 0 ? 0 : (deg == 0 ? 1 : (deg == 1 ? n + 1 : ((n + 1) * (n + 2)) / 2)); }
+// value of basis function c (0-based) of the degree-<= 2 monomial basis at x
+__device__ __forceinline__ double poly_basis_at(const double* x, int n, int c) {
+    if (c == 0) return 1.0;
+    if (c <= n) return x[c - 1];
+    int a = 0, rem = c - (n + 1);
+    while (rem >= n - a) { rem -= n - a; ++a; }
+    return x[a] * x[a + rem];
+}
 
 // ---- block-wide reductions (deterministic order) ----------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -442,6 +442,16 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(EvalParams P) {
                 s += t;
                 if (J) { double* Jl = J + (size_t)(l0 + l) * n; for (int r = 0; r < n; ++r) Jl[r] += lam[(size_t)(r + 1) * k + l0 + l]; }
             }
+            if (P.deg >= 2) {                      // quadratic monomials x_a x_b, a <= b (a outer), behind the linear ones
+                int q = n + 1;
+                double* Jl = J ? J + (size_t)(l0 + l) * n : nullptr;
+                for (int a = 0; a < n; ++a)
+                    for (int bb = a; bb < n; ++bb, ++q) {
+                        const double lq = lam[(size_t)q * k + l0 + l];
+                        s = fma(lq, x[a] * x[bb], s);
+                        if (Jl) { Jl[a] = fma(lq, x[bb], Jl[a]); Jl[bb] = fma(lq, x[a], Jl[bb]); }
+                    }
+            }
             if (Y) Y[l0 + l] = s;
         }
     }
@@ -1001,6 +1011,13 @@ __global__ void eval_split_reduce_kernel(EvalParams P) {
 cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
     if (P.M <= 0 || P.B <= 0) return cudaSuccess;
     const bool want_j = P.J != nullptr;
+    if (P.deg >= 2) {                              // quadratic tail (kernels of cpd order 3): the generic kernel only
+        if (P.B > 65535) return cudaErrorInvalidValue;
+        dim3 grid((unsigned)((P.M + 127) / 128), (unsigned)P.B);
+        eval_generic_kernel<<<grid, 128, 0, s>>>(P);
+        if (n_launches) ++*n_launches;
+        return cudaGetLastError();
+    }
     {   // a handful of points per instance: one warp per point
         const int wd = P.n + P.train_stride * P.k;
         const long long q = (long long)P.B * P.M;

@@ -158,16 +158,38 @@ def get_radial_function(cfg: RbfConfig, shape: Optional[float] = None) -> Radial
 
 
 def poly_basis(x: np.ndarray, degree: int) -> np.ndarray:
-    """Canonical monomial basis of total degree <= degree: [], [1] or [1, x_1..x_n]  (U4)."""
+    """Canonical monomial basis of total degree <= degree: [], [1], [1, x_1..x_n] or [1, x_1..x_n, x_i x_j (i <= j, i outer)]  (U4).
+    Degree 2 only arises when a kernel's order of conditional positive definiteness raises it (thin plate spline k = 2, cubic beta = 5):
+    the configuration itself allows -1..1 (RbfModel.jl:78)."""
     if degree < 0:
         return np.zeros(0)
     if degree == 0:
         return np.ones(1)
-    return np.concatenate(([1.0], x))
+    if degree == 1:
+        return np.concatenate(([1.0], x))
+    n = len(x)
+    quad = [x[i] * x[j] for i in range(n) for j in range(i, n)]
+    return np.concatenate(([1.0], x, quad))
+
+
+def poly_jac(x: np.ndarray, degree: int) -> np.ndarray:
+    """d poly_basis / d x : (dim, n)."""
+    n = len(x)
+    if degree < 0:
+        return np.zeros((0, n))
+    if degree == 0:
+        return np.zeros((1, n))
+    rows = [np.zeros(n)] + [np.eye(n)[i] for i in range(n)]
+    if degree >= 2:
+        for i in range(n):
+            for j in range(i, n):
+                g = np.zeros(n); g[i] += x[j]; g[j] += x[i]
+                rows.append(g)
+    return np.array(rows)
 
 
 def poly_dim(n: int, degree: int) -> int:
-    return 0 if degree < 0 else (1 if degree == 0 else n + 1)
+    return 0 if degree < 0 else (1 if degree == 0 else (n + 1 if degree == 1 else ((n + 1) * (n + 2)) // 2))
 
 
 # --------------------------------------------------------------------------------------
@@ -646,8 +668,10 @@ class RbfModel:
         diff = x[None, :] - self.centers
         rho = np.sqrt((diff ** 2).sum(-1))
         J = (self.w * self.rf.psi(rho)[:, None]).T @ diff                # k x n
-        if self.degree >= 1:
+        if self.degree == 1:
             J = J + self.lam[1:, :].T
+        elif self.degree >= 2:
+            J = J + self.lam.T @ poly_jac(x, self.degree)
         return J if rows is None else J[np.asarray(rows) - 1, :]
 
     def grad(self, x, ell: int):
@@ -668,8 +692,8 @@ def build_model(sites: np.ndarray, values: np.ndarray, cfg: RbfConfig, shape: Op
     N, n = sites.shape
     rf = get_radial_function(cfg, shape)
     deg = max(cfg.polynomial_degree, rf.cpd_order - 1)
-    if deg > 1:
-        raise NotImplementedError("polynomial tails of degree > 1 are outside the hot path")
+    if deg > 2:
+        raise NotImplementedError("polynomial tails of degree > 2 (thin plate splines of order >= 3, cubic exponents >= 7) are not built")
     p = poly_dim(n, deg)
     Phi = rf.phi(np.sqrt(((sites[:, None, :] - sites[None, :, :]) ** 2).sum(-1)))
     Pi = np.array([poly_basis(s, deg) for s in sites]).reshape(N, p)

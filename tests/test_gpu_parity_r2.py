@@ -120,7 +120,8 @@ def test_thin_plate_spline_order1_build_and_eval(engine, n, N, k, deg):
 @pytest.mark.parametrize("n,n_db,shape", [(3, 40, 1.0), (6, 90, 1.0), (5, 60, float("nan"))])
 def test_thin_plate_spline_point_search(engine, n, n_db, shape):
     """Rounds 1-4 with the thin-plate spline (round 4 uses phi with the CONFIGURED polynomial degree, RbfModel.jl:374-375); the default
-    order k = 2 selects points too, only its model build needs a quadratic tail (MRBF_EUNSUPPORTED)."""
+    order k = 2 selects points too; its model build raises the tail to degree 2 (test_quadratic_tail_for_kernels_of_cpd_order_three),
+    order 3 would need a cubic tail (MRBF_EUNSUPPORTED)."""
     rng = np.random.default_rng(n * 1000 + n_db)
     B = 8
     cfg = mb.RbfConfig(kernel="thin_plate_spline", shape_parameter=shape)
@@ -130,9 +131,12 @@ def test_thin_plate_spline_point_search(engine, n, n_db, shape):
     res = engine.select_points(cfg, sites, np.full(B, n_db), xi, x, dl, 0.5, glb, gub, False, False, 2**31 - 1)
     assert np.all(res.status == 0)
     assert_select_equal(res, ref, B)
-    if shape != shape:          # default order 2
+    if shape != shape:          # default order 2 builds (quadratic tail); order 3 is the first unsupported one
+        model, status = engine.build(cfg, sites[:, :30], np.sum(sites[:, :30] ** 2, -1, keepdims=True), [30] * B)
+        assert np.all(status == 0)
+        model.free()
         with pytest.raises(mb.MrbfError) as ei:
-            engine.build(cfg, sites[:, :20], np.zeros((B, 20, 1)), [20] * B)
+            engine.build(mb.RbfConfig(kernel="thin_plate_spline", shape_parameter=3.0), sites[:, :30], np.zeros((B, 30, 1)), [30] * B)
         assert ei.value.code == mb._lib.MRBF_EUNSUPPORTED
 
 
@@ -373,4 +377,33 @@ def test_multistart_builder_evaluates_new_round3_sites(engine):
     for b in range(B):
         for i in range(n_r3[b]):
             assert np.abs(Y[b, i] - synthetic.zdt3(r3[b, i][None])[0]).max() <= 1e-8, (b, i)
+    model.free()
+
+
+@pytest.mark.parametrize("kernel,shape,n,N", [("thin_plate_spline", float("nan"), 2, 12), ("thin_plate_spline", float("nan"), 5, 40),
+                                              ("thin_plate_spline", 2.0, 3, 30), ("cubic", 5.0, 4, 40), ("cubic", 5.0, 2, 6)])
+def test_quadratic_tail_for_kernels_of_cpd_order_three(engine, kernel, shape, n, N):
+    """The default :thin_plate_spline (k = 2, rho^4 log rho) and cubic with beta = 5 are conditionally positive definite of order 3: the
+    tail is raised to degree 2 (assumption U4; the reference's test sweeps the default thin plate spline, test/rbf_models.jl:27-30).
+    Build (QR route) + generic evaluation kernel against the oracle, whose degree-2 tail is pinned by SciPy's quintic / degree = 2
+    (tests/test_scipy_pin.py).  Values, Jacobians, the Armijo batch and interpolation at the sites."""
+    rng = np.random.default_rng(n * 97 + N)
+    cfg = mb.RbfConfig(kernel=kernel, shape_parameter=shape)
+    B, k = 3, 2
+    S = rng.random((B, N, n))
+    V = np.stack([np.sum(S ** 2, -1) + S[..., 0], np.sum(np.sin(3 * S), -1)], -1)
+    model, status = engine.build(cfg, S, V, [N] * B)
+    assert np.all(status == 0)
+    X = np.concatenate((rng.random((B, 21, n)), S[:, :3]), axis=1)
+    Y, J = engine.eval(model, X, True, True)
+    Y2, _ = engine.eval(model, X[:, :5], True, False)          # few points: must not take the one-warp-per-point kernel's linear tail
+    for b in range(B):
+        om = O.build_model(S[b], V[b], O.RbfConfig(kernel=kernel, shape_parameter=shape))
+        assert om.degree == 2
+        Yr = np.array([om.eval(x) for x in X[b]]); Jr = np.array([om.jac(x) for x in X[b]])
+        tol = max(RTOL, 20 * om.cond * np.finfo(float).eps)
+        assert np.abs(Y[b] - Yr).max() <= tol * np.abs(Yr).max(), (b, np.abs(Y[b] - Yr).max() / np.abs(Yr).max(), om.cond)
+        assert np.abs(Y2[b] - Yr[:5]).max() <= tol * np.abs(Yr).max()
+        assert np.abs(J[b] - Jr).max() <= 10 * tol * np.abs(Jr).max(), (b, np.abs(J[b] - Jr).max() / np.abs(Jr).max(), om.cond)
+        assert np.abs(Y[b, -3:] - V[b, :3]).max() <= 1e3 * tol * max(1.0, np.abs(V[b]).max())     # interpolation
     model.free()

@@ -96,3 +96,20 @@ def test_degree_is_raised_to_cpd_minus_one_like_scipy_requires():
     ref = RBFInterpolator(S, V, kernel="cubic", degree=1)
     X = rng.random((10, 3))
     assert np.abs(np.array([m.eval(x) for x in X]) - ref(X)).max() <= 1e-9
+
+
+@pytest.mark.parametrize("n,N", [(2, 15), (4, 40)])
+def test_quadratic_tail_matches_scipy_quintic(n, N):
+    """cubic with exponent 5 is SciPy's `quintic` (-rho^5), conditionally positive definite of order 3: the oracle raises the tail to
+    degree 2 (U4) -- the same saddle system as RBFInterpolator(kernel="quintic", degree=2).  Pins the quadratic tail and the sign."""
+    from scipy.interpolate import RBFInterpolator
+    rng = np.random.default_rng(n + N)
+    S = rng.random((N, n)); V = np.stack([np.sum(S ** 2, -1), np.sum(np.sin(3 * S), -1)], -1); X = rng.random((9, n))
+    m = O.build_model(S, V, O.RbfConfig(kernel="cubic", shape_parameter=5.0))
+    assert m.degree == 2 and m.lam.shape[0] == (n + 1) * (n + 2) // 2
+    Yo = np.array([m.eval(x) for x in X])
+    Ys = RBFInterpolator(S, V, kernel="quintic", degree=2)(X)
+    assert np.abs(Yo - Ys).max() <= 1e-9 * np.abs(Ys).max()
+    h = 1e-6
+    Jfd = np.array([(m.eval(X[0] + h * np.eye(n)[i]) - m.eval(X[0] - h * np.eye(n)[i])) / (2 * h) for i in range(n)]).T
+    assert np.abs(m.jac(X[0]) - Jfd).max() <= 1e-6 * max(1.0, np.abs(Jfd).max())
