@@ -30,7 +30,7 @@ def _initialize(cfg, n, constrained, rng, algo_max_evals=mb.surrogate.INT_MAX):
 
 
 @pytest.mark.parametrize("n", [2, 5, 10])
-@pytest.mark.parametrize("kernel", ["cubic", "inv_multiquadric", "multiquadric", "gaussian"])
+@pytest.mark.parametrize("kernel", ["cubic", "inv_multiquadric", "multiquadric", "thin_plate_spline", "gaussian"])     # Morbit.RbfKernels, RbfModel.jl:48-54
 @pytest.mark.parametrize("deg", [-1, 0, 1])
 @pytest.mark.parametrize("constrained", [True, False])
 def test_rbf_models_jl(n, kernel, deg, constrained):
