@@ -72,6 +72,8 @@ typedef struct mrbf_model mrbf_model;   /* device-resident batch of fitted model
 int mrbf_abi_version(void);
 int mrbf_init(int device, mrbf_ctx** ctx);                 /* creates a private non-blocking stream */
 int mrbf_set_stream(mrbf_ctx* ctx, void* cuda_stream);     /* run on the caller's cudaStream_t instead */
+int mrbf_get_stream(const mrbf_ctx* ctx, void** cuda_stream);  /* the cudaStream_t the *_dev entry points enqueue on: a caller whose device
+                                                              buffers are produced on another stream orders the two with events */
 int mrbf_sync(mrbf_ctx* ctx);
 /* rtol of the reference's `Δ ≈ Δ_max` test that skips round 2 (src/models/RbfModel.jl:588).  Julia's isapprox uses
  * max(sqrt(eps(T))) over the two argument types, and delta_max(algo_config) of the DEFAULT config is a Float32 literal

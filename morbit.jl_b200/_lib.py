@@ -35,6 +35,7 @@ SIGNATURES = {
     "mrbf_abi_version": (C.c_int, []),
     "mrbf_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "mrbf_set_stream": (C.c_int, [_vp, _vp]),
+    "mrbf_get_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "mrbf_sync": (C.c_int, [_vp]),
     "mrbf_set_isapprox_rtol": (C.c_int, [_vp, _f64]),
     "mrbf_destroy": (None, [_vp]),

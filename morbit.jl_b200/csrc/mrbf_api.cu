@@ -4,7 +4,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -12,6 +15,23 @@
 #include "mrbf_kernels.h"
 
 using namespace mrbf;
+
+namespace mrbf {
+cudaError_t raise_dyn_smem_impl(const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> limit;      // (function, device) -> what the attribute was last raised to
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> guard(mu);
+    size_t& cur = limit[std::make_pair(kernel, dev)];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
+}  // namespace mrbf
 
 namespace {
 
@@ -98,12 +118,23 @@ struct Timed {
     }
 };
 
+// Every device allocation of the library goes through here.  MRBF_POISON=<byte> (debugging aid, stands in for compute-sanitizer's
+// initcheck) fills fresh allocations with that byte -- 255 gives NaN doubles / -1 ints, 127 gives 1.4e306 / 2139062143 -- so that a
+// kernel consuming workspace it has not written shows up as a wrong result instead of depending on what the allocator handed back.
+static cudaError_t dev_malloc(void** p, size_t bytes) {
+    static const int poison = getenv("MRBF_POISON") ? atoi(getenv("MRBF_POISON")) : -1;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess && poison >= 0) { e = cudaMemset(*p, poison & 255, bytes); if (e == cudaSuccess) e = cudaDeviceSynchronize(); }
+    return e;
+}
+template <class T> static cudaError_t dev_malloc(T** p, size_t bytes) { return dev_malloc((void**)p, bytes); }
+
 int ensure(mrbf_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes == 0) bytes = 16;
     if (b.cap >= bytes) return MRBF_OK;
     if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8;
-    cudaError_t e = cudaMalloc(&b.p, want);
+    cudaError_t e = dev_malloc(&b.p, want);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();        // the failure is reported here; do not leave it for the next launch check to trip over
         b.p = nullptr; return fail(ctx, MRBF_ENOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -175,8 +206,8 @@ int ensure_prepared(mrbf_ctx* ctx, mrbf_prepared** keep_out, const mrbf_cfg* cfg
     kp->r4_stride = r4_stride; kp->cfg_degree = cfg->polynomial_degree; kp->kernel = cfg->kernel; kp->shape = cfg->shape_parameter;
     kp->fs_stride = fsd; kp->kind = kind; kp->geom = geom;
     const size_t ni = (size_t)B * 4 + (size_t)B * found_stride + (size_t)B * r4_stride;
-    cudaError_t e1 = cudaMalloc(&kp->fs, (size_t)B * (fsd ? fsd : 1) * sizeof(double));
-    cudaError_t e2 = (e1 == cudaSuccess) ? cudaMalloc(&kp->ints, ni * sizeof(int)) : e1;
+    cudaError_t e1 = dev_malloc(&kp->fs, (size_t)B * (fsd ? fsd : 1) * sizeof(double));
+    cudaError_t e2 = (e1 == cudaSuccess) ? dev_malloc(&kp->ints, ni * sizeof(int)) : e1;
     if (e2 != cudaSuccess) {
         (void)cudaGetLastError();
         cudaFree(kp->fs); delete kp;
@@ -353,6 +384,12 @@ int mrbf_set_stream(mrbf_ctx* ctx, void* s) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
     ctx->stream = (cudaStream_t)s;
+    return MRBF_OK;
+}
+
+int mrbf_get_stream(const mrbf_ctx* ctx, void** s) {
+    if (!ctx || !s) return MRBF_EINVAL;
+    *s = (void*)ctx->stream;
     return MRBF_OK;
 }
 
@@ -674,11 +711,11 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
         m = new (std::nothrow) mrbf_model();
         if (!m) return fail(ctx, MRBF_ENOMEM, "out of host memory%s");
         m->B = B; m->n = n; m->k = k; m->train_stride = train_stride; m->p = p; m->deg = deg;
-        if (e == cudaSuccess) e = cudaMalloc(&m->N, sizeof(int) * (size_t)B);
-        if (e == cudaSuccess) e = cudaMalloc(&m->centers, sizeof(double) * (size_t)B * train_stride * n);
-        if (e == cudaSuccess) e = cudaMalloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
-        if (e == cudaSuccess) e = cudaMalloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
-        if (e == cudaSuccess) e = cudaMalloc(&m->alpha2, sizeof(double) * (size_t)B);
+        if (e == cudaSuccess) e = dev_malloc(&m->N, sizeof(int) * (size_t)B);
+        if (e == cudaSuccess) e = dev_malloc(&m->centers, sizeof(double) * (size_t)B * train_stride * n);
+        if (e == cudaSuccess) e = dev_malloc(&m->w, sizeof(double) * (size_t)B * train_stride * k);
+        if (e == cudaSuccess) e = dev_malloc(&m->lam, sizeof(double) * (size_t)B * pl * k);
+        if (e == cudaSuccess) e = dev_malloc(&m->alpha2, sizeof(double) * (size_t)B);
         if (e == cudaSuccess && n <= 64 && k <= 16 && deg <= 1) {   // geometry of the tiled copy; the buffer itself is allocated on first use
             m->pack_s = eval_pack_stride(n); m->pack_nt = (train_stride + 63) / 64;
             m->pack_tile_doubles = (size_t)64 * m->pack_s + 64 + (size_t)k * 64;
@@ -953,7 +990,7 @@ int mrbf_eval_dev(mrbf_ctx* ctx, const mrbf_model* m, int64_t M, const double* X
         // first evaluation of this model: re-tile it once for the tensor-path sweep (the handle is logically const)
         mrbf_model* mm = const_cast<mrbf_model*>(m);
         if (!mm->pack) {
-            cudaError_t e = cudaMalloc(&mm->pack, sizeof(double) * (size_t)m->B * m->pack_nt * m->pack_tile_doubles);
+            cudaError_t e = dev_malloc(&mm->pack, sizeof(double) * (size_t)m->B * m->pack_nt * m->pack_tile_doubles);
             if (e != cudaSuccess) { (void)cudaGetLastError(); mm->pack = nullptr; mm->pack_tile_doubles = 0; }   // handled: fall back to the tile kernels
         }
         if (mm->pack) {

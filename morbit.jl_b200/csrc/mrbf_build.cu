@@ -553,7 +553,7 @@ size_t build_prepared_stream_smem_doubles(int n, int k, int NM, int p) {
     return (size_t)NM * k + 2 * (size_t)MM * k + (size_t)pl * k + 8 * (size_t)MM * k + 8;
 }
 cudaError_t launch_build_prepared_stream(const PreparedBuildParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(build_prepared_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(build_prepared_stream_kernel, smem);
     if (e != cudaSuccess) return e;
     build_prepared_stream_kernel<<<P.B, 256, smem, s>>>(P);
     return cudaGetLastError();
@@ -564,7 +564,7 @@ size_t build_prepared_smem_doubles(int n, int k, int NM, int p) {
     return (size_t)NM * k + 2 * (size_t)MM * k + (size_t)pl * k + (size_t)MM * (MM + 1) / 2 + 2 * (size_t)pb * MM;
 }
 cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(build_prepared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(build_prepared_kernel, smem);
     if (e != cudaSuccess) return e;
     build_prepared_kernel<<<P.B, 256, smem, s>>>(P);
     return cudaGetLastError();
@@ -762,7 +762,7 @@ size_t build_schur_smem_doubles(int k, int MC, int p) {
     return 3 * (size_t)p * k + (size_t)MC * k + MC + MC + 2;
 }
 cudaError_t launch_build_schur(const SchurBuildParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(build_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(build_schur_kernel, smem);
     if (e != cudaSuccess) return e;
     build_schur_kernel<<<P.B, 64, smem, s>>>(P);
     return cudaGetLastError();
@@ -773,7 +773,7 @@ size_t build_ws_doubles(int n, int k, int ld, int p) { int pl = p > 0 ? p : 1; r
 
 template <int NT>
 static cudaError_t launch_build_nt(const BuildParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(build_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(build_kernel<NT>, smem);
     if (e != cudaSuccess) return e;
     build_kernel<NT><<<P.B, NT, smem, s>>>(P);
     return cudaGetLastError();

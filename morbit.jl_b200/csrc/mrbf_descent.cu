@@ -193,7 +193,7 @@ int descent_max_outputs() { return DK; }
 cudaError_t launch_descent_direction(const DescentParams& P, cudaStream_t s) {
     const int wpb = 4;
     const size_t smem = wpb * P.warp_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(descent_direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(descent_direction_kernel, smem);
     if (e != cudaSuccess) return e;
     descent_direction_kernel<<<(P.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(P);
     return cudaGetLastError();

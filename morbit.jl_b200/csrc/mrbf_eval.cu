@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256, 1) eval_dmma_kernel(EvalParams P, int l0)
 
 template <int RK, int KK>
 static cudaError_t launch_dmma_t(const EvalParams& P, cudaStream_t s, int l0, size_t smem, dim3 grid) {
-    cudaError_t e = cudaFuncSetAttribute(eval_dmma_kernel<RK, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(eval_dmma_kernel<RK, KK>, smem);
     if (e != cudaSuccess) return e;
     eval_dmma_kernel<RK, KK><<<grid, 256, smem, s>>>(P, l0);
     return cudaGetLastError();
@@ -914,8 +914,8 @@ template <int RK>
 static cudaError_t launch_dmma_jac_t(const EvalParams& P, cudaStream_t s, int* n_launches) {
     const int st = P.pack_s;
     const size_t smem = 128 + sizeof(double) * (2 * P.pack_tile_doubles + (size_t)DM_TM * st + DM_TM);
-    cudaError_t e = cudaFuncSetAttribute(eval_dmma_jac_kernel<RK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_dmma_jac_kernel<RK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(eval_dmma_jac_kernel<RK, 1>, smem);
+    if (e == cudaSuccess) e = raise_dyn_smem(eval_dmma_jac_kernel<RK, 2>, smem);
     if (e != cudaSuccess) return e;
     const long long tiles = (P.M + DM_TM - 1) / DM_TM;
     for (int l0 = 0; l0 < P.k;) {                // two outputs per pass while there are two left
@@ -941,7 +941,7 @@ template <int CQ, bool WANT_J>
 static cudaError_t launch_tile(const EvalParams& P, cudaStream_t s, int* n_launches) {
     constexpr int ND = 16 * CQ, KG = WANT_J ? 2 : 4;
     const size_t smem = sizeof(double) * ((size_t)ND * TM + (size_t)ND * TN + (size_t)TN * ND + (size_t)TM * GLD + TM + TN + KG * TN + ND);
-    cudaError_t e = cudaFuncSetAttribute(eval_tile_kernel<CQ, WANT_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(eval_tile_kernel<CQ, WANT_J>, smem);
     if (e != cudaSuccess) return e;
     const long long tiles = (P.M + TM - 1) / TM;
     for (int l0 = 0; l0 < P.k; l0 += KG) {
@@ -963,7 +963,7 @@ static size_t eval_wide_smem(int npad) {
 static cudaError_t launch_wide(const EvalParams& P, cudaStream_t s, int* n_launches) {
     const int npad = ((P.n + WC - 1) / WC) * WC;
     const size_t smem = eval_wide_smem(npad);
-    cudaError_t e = cudaFuncSetAttribute(eval_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(eval_wide_kernel, smem);
     if (e != cudaSuccess) return e;
     const long long tiles = (P.M + TM - 1) / TM;
     for (int l0 = 0; l0 < P.k; l0 += 4) {
@@ -1023,7 +1023,7 @@ cudaError_t launch_eval(const EvalParams& P, cudaStream_t s, int* n_launches) {
         const long long q = (long long)P.B * P.M;
         if (P.M <= 8 && (size_t)4 * wd * sizeof(double) <= 96 * 1024 && (q + 3) / 4 < 2147483647LL) {
             const size_t smem = (size_t)4 * wd * sizeof(double);
-            cudaError_t e = cudaFuncSetAttribute(eval_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = raise_dyn_smem(eval_small_kernel, smem);
             if (e != cudaSuccess) return e;
             eval_small_kernel<<<(unsigned)((q + 3) / 4), 128, smem, s>>>(P, wd);
             if (n_launches) ++*n_launches;

@@ -165,6 +165,13 @@ struct ModelScatterParams {
 };
 
 size_t select_smem_bytes(int n, bool wz_in_smem, int st_doubles, int db_stride);
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION, process-wide: two host threads that launch the same kernel with
+// different shared-memory sizes through their own contexts (the reference's benchmark driver runs optimize() under Threads.@threads,
+// examples/large_scale_benchmarks.jl:253) must not lower each other's limit between the set and the launch.  The limit is therefore
+// only ever raised, under a mutex (mrbf_api.cu); sizes within the 48 KB default need no call at all.
+cudaError_t raise_dyn_smem_impl(const void* kernel, size_t bytes);
+template <class... A> inline cudaError_t raise_dyn_smem(void (*kernel)(A...), size_t bytes) { return raise_dyn_smem_impl((const void*)kernel, bytes); }
+
 size_t round4_vec_doubles(int n, int NM, int p);
 size_t round4_ws_doubles(int n, int NM, int p);
 size_t round4_fast_state_doubles(int n, int NM, int p);

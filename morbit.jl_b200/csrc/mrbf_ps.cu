@@ -176,7 +176,7 @@ cudaError_t launch_ps_init(const PsParams& P, cudaStream_t s) {
 }
 cudaError_t launch_ps_fitness_rank(const PsParams& P, int gen, cudaStream_t s) {
     const size_t smem = ps_rank_smem_bytes(P.lambda);
-    cudaError_t e = cudaFuncSetAttribute(ps_fitness_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(ps_fitness_rank_kernel, smem);
     if (e != cudaSuccess) return e;
     ps_fitness_rank_kernel<<<P.B, 256, smem, s>>>(P, gen);
     return cudaGetLastError();

@@ -956,11 +956,11 @@ static cudaError_t launch_elim(const Round4Params& P, const SchurGeom& g, int nt
 #define MRBF_ELIM_CASE(R)                                                                                                          \
     case R:                                                                                                                        \
         if (P.dbg_clock) {                                                                                                         \
-            e = cudaFuncSetAttribute(round4_elim_kernel<SMALL, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            e = raise_dyn_smem(round4_elim_kernel<SMALL, R, true>, smem);  \
             if (e != cudaSuccess) return e;                                                                                        \
             round4_elim_kernel<SMALL, R, true><<<P.B, nthreads, smem, s>>>(P, g);                                                  \
         } else {                                                                                                                   \
-            e = cudaFuncSetAttribute(round4_elim_kernel<SMALL, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = raise_dyn_smem(round4_elim_kernel<SMALL, R, false>, smem); \
             if (e != cudaSuccess) return e;                                                                                        \
             round4_elim_kernel<SMALL, R, false><<<P.B, nthreads, smem, s>>>(P, g);                                                 \
         }                                                                                                                          \
@@ -979,7 +979,7 @@ cudaError_t launch_round4_schur(const Round4Params& P, const SchurGeom& g, cudaS
     const int p = poly_dim(P.n, P.cfg.polynomial_degree);
     const int rpl = (p + 31) / 32;
     const size_t psmem = g.ps_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(round4_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    cudaError_t e = raise_dyn_smem(round4_prep_kernel, psmem);
     if (e != cudaSuccess) return e;
     round4_prep_kernel<<<P.B, 256, psmem, s>>>(P, g);
     if (g.two_variants) {

@@ -1205,7 +1205,7 @@ size_t round4_ws_doubles(int n, int NM, int p) {
 
 template <bool WZS, bool STS, int NT>
 static cudaError_t launch_select_t(const SelectParams& P, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(select_rounds123_kernel<WZS, STS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(select_rounds123_kernel<WZS, STS, NT>, smem);
     if (e != cudaSuccess) return e;
     select_rounds123_kernel<WZS, STS, NT><<<P.B, NT, smem, s>>>(P);
     return cudaGetLastError();
@@ -1218,7 +1218,7 @@ cudaError_t launch_select_rounds123(const SelectParams& P, size_t smem, cudaStre
     return launch_select_t<false, false, 512>(P, smem, s);
 }
 cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, int grid) {
-    cudaError_t e = cudaFuncSetAttribute(round4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dyn_smem(round4_kernel, smem);
     if (e != cudaSuccess) return e;
     round4_kernel<<<grid, 256, smem, s>>>(P);
     return cudaGetLastError();
@@ -1231,11 +1231,11 @@ template <int T>
 static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream_t s) {
     cudaError_t e;
     if (P.fs_in_smem) {
-        e = cudaFuncSetAttribute(round4_block_kernel<T, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = raise_dyn_smem(round4_block_kernel<T, true, 256>, smem);
         if (e != cudaSuccess) return e;
         round4_block_kernel<T, true, 256><<<P.B, 256, smem, s>>>(P);
     } else {
-        e = cudaFuncSetAttribute(round4_block_kernel<T, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = raise_dyn_smem(round4_block_kernel<T, false, 1024>, smem);
         if (e != cudaSuccess) return e;
         round4_block_kernel<T, false, 1024><<<P.B, 1024, smem, s>>>(P);
     }
@@ -1243,7 +1243,7 @@ static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream
 }
 cudaError_t launch_round4_block(const Round4Params& P, int T, size_t smem, cudaStream_t s) {
     if (T == 16) {      // global-memory state, many accepted points: 16 candidates per pass over the packed L^{-1} (half the L2 / HBM traffic)
-        cudaError_t e = cudaFuncSetAttribute(round4_block_kernel<16, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = raise_dyn_smem(round4_block_kernel<16, false, 512>, smem);
         if (e != cudaSuccess) return e;
         round4_block_kernel<16, false, 512><<<P.B, 512, smem, s>>>(P);
         return cudaGetLastError();

@@ -151,17 +151,62 @@ class Comm:
             pass
 
 
+class _StreamOrderedLib:
+    """The library as an Engine sees it.  `*_dev` entry points take torch tensors, which torch produces (and will consume) on ITS current
+    stream; when that is not the stream the context enqueues on -- an Engine created without `stream=` runs on the library's private
+    non-blocking stream -- every such call is bracketed by two event waits: the engine's stream waits for what torch has enqueued so
+    far (e.g. the zero fill of freshly allocated outputs), and torch's stream waits for the call's kernels afterwards.  Nothing is
+    added when both are the same stream (bench.py, lockstep).  Every other symbol is passed through untouched."""
+
+    def __init__(self, lib, engine):
+        import weakref
+        self._lib, self._engine = lib, weakref.ref(engine)
+
+    def __getattr__(self, name):
+        f = getattr(self._lib, name)
+        if not name.endswith("_dev"):
+            return f
+
+        def ordered(*args):
+            eng = self._engine()
+            ext = eng._foreign_stream() if eng is not None else None
+            if ext is None:
+                return f(*args)
+            import torch
+            cur = torch.cuda.current_stream(eng.device)
+            ext.wait_stream(cur)
+            rc = f(*args)
+            cur.wait_stream(ext)
+            return rc
+
+        self.__dict__[name] = ordered
+        return ordered
+
+
 class Engine:
     def __init__(self, device: int = 0, stream: Optional[int] = None):
-        self.lib = _lib.load()
+        self.lib = _StreamOrderedLib(_lib.load(), self)
         ctx = C.c_void_p()
         rc = self.lib.mrbf_init(int(device), C.byref(ctx))
         if rc != 0:
             raise MrbfError(rc, f"mrbf_init(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
         self.ctx = ctx
         self.device = device
+        self._ext = None
         if stream is not None:
             self._check(self.lib.mrbf_set_stream(self.ctx, C.c_void_p(stream)))
+        h = C.c_void_p()
+        self._check(self.lib.mrbf_get_stream(self.ctx, C.byref(h)))
+        self._stream = int(h.value or 0)
+
+    def _foreign_stream(self):
+        """torch's view of the context's stream when it differs from torch's current stream on this device, else None."""
+        import torch
+        if torch.cuda.current_stream(self.device).cuda_stream == self._stream:
+            return None
+        if self._ext is None:
+            self._ext = torch.cuda.ExternalStream(self._stream, device=self.device)
+        return self._ext
 
     def close(self):
         if self.ctx:

@@ -407,3 +407,66 @@ def test_quadratic_tail_for_kernels_of_cpd_order_three(engine, kernel, shape, n,
         assert np.abs(J[b] - Jr).max() <= 10 * tol * np.abs(Jr).max(), (b, np.abs(J[b] - Jr).max() / np.abs(Jr).max(), om.cond)
         assert np.abs(Y[b, -3:] - V[b, :3]).max() <= 1e3 * tol * max(1.0, np.abs(V[b]).max())     # interpolation
     model.free()
+
+
+def test_dev_entry_points_are_ordered_with_torchs_stream():
+    """An Engine created without `stream=` enqueues on the library's private non-blocking stream while torch allocates (and zero-fills)
+    the outputs of a `*_dev` call on its own current stream.  The Python layer brackets such calls with event waits
+    (engine._StreamOrderedLib, mrbf_get_stream): with torch's stream held busy, the fill of the fresh outputs is still pending when the
+    call is made -- the results must nevertheless be the ones of the host-buffer path, and readable from torch's stream right after."""
+    import torch
+    from morbit_jl_b200.multistart import upload_batch
+    eng = mb.Engine(0)
+    assert eng._stream != torch.cuda.current_stream().cuda_stream
+    cfg = mb.RbfConfig(kernel="multiquadric")
+    host = synthetic.multistart_batch(64, n=12, n_db=70, func=synthetic.zdt3, local_fraction=0.5)
+    ref = eng.select_points(cfg, host["sites"], host["n_db"], host["x_index"], host["x"], host["delta"], host["delta_max"],
+                            host["glb"], host["gub"])
+    dev = upload_batch(host, "cuda:0")
+    torch.cuda.synchronize()
+    torch.cuda._sleep(400_000_000)                       # ~0.2 s of work in front of everything torch enqueues from here on
+    sel = eng.select_points_dev(cfg, dev.sites, dev.n_db, dev.x_index, dev.x, dev.delta, host["delta_max"], dev.glb, dev.gub,
+                                dev.flags_in, dev.max_new)
+    got = [t.cpu().numpy() for t in (sel.n_r1, sel.n_r2, sel.n_r3, sel.n_r4, sel.r4)]        # no eng.sync(): torch's stream waits
+    for a, b in zip(got[:4], (ref.n_r1, ref.n_r2, ref.n_r3, ref.n_r4)):
+        assert np.array_equal(a, b)
+    assert ref.n_r4.sum() > 0
+    for b in range(64):
+        assert np.array_equal(got[4][b, :ref.n_r4[b]], ref.r4[b, :ref.n_r4[b]])
+    eng.close()
+
+
+def test_concurrent_contexts_with_different_shapes_share_the_kernels():
+    """Two host threads, each with its own context, launch the SAME kernel instantiations with very different dynamic shared-memory
+    sizes (n = 6 vs n = 30: a few KB vs ~100 KB for the round-4 elimination).  The per-function shared-memory limit is process-wide;
+    the library only ever raises it (raise_dyn_smem, mrbf_api.cu), so neither thread can see its launch refused -- or served with
+    another thread's smaller limit -- in the window between the other thread's set and launch.  Results equal the serial ones."""
+    import threading
+    shapes = {0: dict(n=6, n_db=40), 1: dict(n=30, n_db=128)}
+
+    def run(eng, which, rep):
+        cfg = mb.RbfConfig(kernel="multiquadric")
+        h = synthetic.multistart_batch(8, func=synthetic.zdt3, first_instance=10 * rep, **shapes[which])
+        res = eng.select_points(cfg, h["sites"], h["n_db"], h["x_index"], h["x"], h["delta"], h["delta_max"], h["glb"], h["gub"])
+        return np.concatenate([res.n_r2, res.n_r4] + [res.r4[b, :res.n_r4[b]] for b in range(8)])
+
+    eng = mb.Engine(0)
+    serial = {(w, r): run(eng, w, r) for w in shapes for r in range(3)}
+    eng.close()
+    errors, out = [], {}
+
+    def work(which):
+        try:
+            e = mb.Engine(0)
+            for it in range(40):
+                out[(which, it)] = run(e, which, it % 3)
+            e.close()
+        except Exception as ex:            # an exception in a thread would otherwise only be printed
+            errors.append(repr(ex))
+
+    ths = [threading.Thread(target=work, args=(w,)) for w in shapes]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    assert not errors, errors
+    for (w, it), v in out.items():
+        assert np.array_equal(v, serial[(w, it % 3)]), (w, it)

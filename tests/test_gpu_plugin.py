@@ -347,16 +347,25 @@ def test_reentrant_contexts_from_concurrent_threads():
         out[seed] = res_all
         eng.close()
 
-    serial, threaded = {}, {}
+    serial, threaded, errors = {}, {}, []
     for s_ in (1, 2):
         work(s_, serial)
-    ths = [threading.Thread(target=work, args=(s_, threaded)) for s_ in (1, 2)]
+
+    def guarded(s_):
+        try:
+            work(s_, threaded)
+        except Exception as ex:            # an exception in a thread would otherwise only be printed
+            errors.append((s_, repr(ex)))
+
+    ths = [threading.Thread(target=guarded, args=(s_,)) for s_ in (1, 2)]
     for t in ths: t.start()
     for t in ths: t.join()
+    assert not errors, errors
     for s_ in (1, 2):
-        for a, b in zip(serial[s_], threaded[s_]):
-            for x_, y_ in zip(a, b):
-                assert np.array_equal(x_, y_)
+        for rep, (a, b) in enumerate(zip(serial[s_], threaded[s_])):
+            for part, x_, y_ in zip(("r1", "r2", "r4", "n_r4", "values", "jacobians"), a, b):
+                assert np.array_equal(x_, y_), (s_, rep, part, np.abs(np.asarray(x_, float) - np.asarray(y_, float)).max()
+                                                if np.shape(x_) == np.shape(y_) else (np.shape(x_), np.shape(y_)))
 
 
 def test_c_abi_gather_single_rank():
