@@ -692,6 +692,15 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
+// D (8 x 8) += A (8 x 4) B (4 x 8) on the FP64 tensor path: lane l holds A[l / 4][l % 4], B[l % 4][l / 4], D[l / 4][2 (l % 4) + {0, 1}]
+__device__ __forceinline__ void dmma884_sel(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+// Row stride of the block's a- and t-vectors in shared memory: = 4 (mod 16) doubles, so that the 8 rows x 4 columns a tensor-path operand
+// load touches fall into 2 x 16 distinct banks (two wavefronts, the minimum for 256 bytes)
+__host__ __device__ __forceinline__ int round4_block_row_stride(int MM) { return ((MM + 11) / 16) * 16 + 4; }
+
 template <int T, bool SMEM, int NT>
 __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
     // Blocked variant of the shared-memory round 4: T candidates are evaluated together against the factorisation as it was
@@ -709,15 +718,16 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
     const int p = poly_dim(n, deg);
     const int pl = p > 0 ? p : 1, pb = pl | 1;
     const int MM = (NM - p) > 1 ? (NM - p) : 1;
+    const int MS = round4_block_row_stride(MM);     // row stride of AV / TV
     // block buffers
     double* XI = smem;                 // T x n    candidate sites
     double* PH = XI + T * n;           // T x NM   kernel columns against the current centres
     double* CV = PH + T * NM;          // T x pl   c_xi
     double* UB = CV + T * pl;          // T x pl   u_xi = b_xi - Phi00 c_xi
     double* HV = UB + T * pl;          // T x pl   H pi_xi
-    double* AV = HV + T * pl;          // T x MM   a_xi
-    double* TV = AV + T * MM;          // T x MM   t_xi = L^{-1} a_xi
-    double* Kx = TV + T * MM;          // T x T    phi(xi_i, xi_j)
+    double* AV = HV + T * pl;          // T x MS   a_xi
+    double* TV = AV + T * MS;          // T x MS   t_xi = L^{-1} a_xi
+    double* Kx = TV + T * MS;          // T x T    phi(xi_i, xi_j)
     double* Ax = Kx + T * T;           // T x T    A_ij (i < j), A_jj on the diagonal
     double* Dx = Ax + T * T;           // T x T    t_i . t_j
     double* Sx = Dx + T * T;           // T x T    pi_i' H pi_j (i < j), leverage on the diagonal
@@ -951,7 +961,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
                     for (int j = 0; j < T; ++j) acc[j] = fma(gv, CV[j * pl + c], fma(cv_, PH[j * NM + c], acc[j]));
                 }
 #pragma unroll
-                for (int j = 0; j < T; ++j) if (j < tb) AV[j * MM + eta] = PH[j * NM + base + eta] - acc[j];
+                for (int j = 0; j < T; ++j) if (j < tb) AV[j * MS + eta] = PH[j * NM + base + eta] - acc[j];
             }
         }
         if (tid >= nt - 32 && lane < tb) {         // leverages by the last warp
@@ -964,7 +974,57 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         // ---- P3: t_j = L^{-1} a_j for all block members at once (G threads per row share the row of L^{-1})
         const int G = (!SMEM) ? 8 : ((m > 64) ? 2 : ((m > 32) ? 4 : 8));   // state in global memory: eight lanes read a 64-byte piece of a row of L^{-1}
         const int rows_per_pass = nt / G;
-        {
+        if constexpr (!SMEM) {
+            // State in global memory (large systems): T = L^{-1} A' as FP64 tensor-path tiles.  A warp owns 8 rows of L^{-1} at a time
+            // (mma.m8n8k4: the 8 x 4 piece of L^{-1} straight from L2 / HBM as the A operand, 4 x 8 pieces of the block's a-vectors from
+            // shared memory as B) -- one shared-memory operand per 256 FMA where the lane-per-column loop below reads one per FMA, which
+            // is what bounded this phase (ncu: 29 % of the kernel's shared-memory wavefronts).  Row tiles are dealt to the warps in a
+            // snake so that the triangular row lengths balance.
+            constexpr int NJT = (T + 7) / 8;
+            const int lr = lane >> 2, lk = lane & 3;
+            const int ntile = (m + 7) >> 3;
+            double tn2[NJT][2];
+#pragma unroll
+            for (int jt = 0; jt < NJT; ++jt) tn2[jt][0] = tn2[jt][1] = 0.0;
+            for (int i = 0; i * nwarps < ntile; ++i) {
+                const int t = i * nwarps + ((i & 1) ? (nwarps - 1 - warp) : warp);
+                if (t >= ntile) continue;
+                const int r = (t << 3) + lr;
+                const bool rok = r < m;
+                const double* lrow = Li + tri(rok ? r : 0);
+                const int cend = min((t << 3) + 8, m);
+                double d[NJT][2];
+#pragma unroll
+                for (int jt = 0; jt < NJT; ++jt) d[jt][0] = d[jt][1] = 0.0;
+#pragma unroll 4
+                for (int c0 = 0; c0 < cend; c0 += 4) {
+                    const int c = c0 + lk;
+                    const double a = (rok && c <= r) ? lrow[c] : 0.0;
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt) {
+                        const double bv = (c < m && jt * 8 + lr < T) ? AV[(jt * 8 + lr) * MS + c] : 0.0;
+                        dmma884_sel(d[jt], a, bv);
+                    }
+                }
+#pragma unroll
+                for (int jt = 0; jt < NJT; ++jt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = jt * 8 + 2 * lk + e;
+                        if (j < T && rok) TV[j * MS + r] = d[jt][e];
+                        tn2[jt][e] = fma(d[jt][e], d[jt][e], tn2[jt][e]);          // rows beyond m carry zeros
+                    }
+            }
+#pragma unroll
+            for (int jt = 0; jt < NJT; ++jt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double v = tn2[jt][e];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    const int j = jt * 8 + 2 * lk + e;
+                    if (lr == 0 && j < T) tnp[warp * T + j] = v;
+                }
+        } else {
             double tn[T];
 #pragma unroll
             for (int j = 0; j < T; ++j) tn[j] = 0.0;
@@ -979,14 +1039,14 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
                     for (int c = l; c <= r; c += G) {
                         const double lv = lr[c];
 #pragma unroll
-                        for (int j = 0; j < T; ++j) acc[j] = fma(lv, AV[j * MM + c], acc[j]);
+                        for (int j = 0; j < T; ++j) acc[j] = fma(lv, AV[j * MS + c], acc[j]);
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < T; ++j) {
                     double a = acc[j];
                     for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                    if (r < m && l == 0) { TV[j * MM + r] = a; tn[j] = fma(a, a, tn[j]); }
+                    if (r < m && l == 0) { TV[j * MS + r] = a; tn[j] = fma(a, a, tn[j]); }
                 }
             }
 #pragma unroll
@@ -1009,7 +1069,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
                             a0 = fma(CV[i * pl + c], PH[j * NM + c], a0);
                             a2 = fma(HV[i * pl + c], PT[j * pl + c], a2);
                         }
-                        for (int r = l8; r < m; r += 8) a1 = fma(TV[i * MM + r], TV[j * MM + r], a1);
+                        for (int r = l8; r < m; r += 8) a1 = fma(TV[i * MS + r], TV[j * MS + r], a1);
                     } else {
                         for (int c = l8; c < p; c += 8) a0 = fma(CV[j * pl + c], PH[j * NM + c] + UB[j * pl + c], a0);
                     }
@@ -1083,6 +1143,57 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         // ---- P6: append the accepted members
         if (na > 0) {
             // new rows of L^{-1}: columns < m from  -P_^{-1} (T_ L^{-1}),  columns >= m from P_^{-1}
+            if constexpr (!SMEM) {
+                // tensor-path twin of the loop below: a warp owns 8 columns of L^{-1}; A = the accepted members' t-vectors (shared memory),
+                // B = 4 x 8 pieces of L^{-1} below the diagonal; the T x T triangular factor P_^{-1} is applied from registers through
+                // shuffles (lane (q, cpair) collects column pair cpair of every row q2 <= q)
+                constexpr int NJT = (T + 7) / 8;
+                const int lr = lane >> 2, lk = lane & 3;
+                const int ntile = (m + 7) >> 3;
+                int jq[NJT];
+#pragma unroll
+                for (int jt = 0; jt < NJT; ++jt) jq[jt] = (jt * 8 + lr < na) ? ib[2 * T + jt * 8 + lr] : -1;
+                for (int i = 0; i * nwarps < ntile; ++i) {
+                    const int t = i * nwarps + ((i & 1) ? (nwarps - 1 - warp) : warp);
+                    if (t >= ntile) continue;
+                    const int c0 = t << 3, c = c0 + lr;
+                    double d[NJT][2];
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt) d[jt][0] = d[jt][1] = 0.0;
+#pragma unroll 4
+                    for (int r0 = c0; r0 < m; r0 += 4) {
+                        const int r = r0 + lk;
+                        const bool rok = r < m;
+                        const double bv = (rok && c <= r) ? Li[tri(r) + c] : 0.0;        // (c <= r < m implies c < m)
+#pragma unroll
+                        for (int jt = 0; jt < NJT; ++jt) {
+                            const double a = (rok && jq[jt] >= 0) ? TV[jq[jt] * MS + r] : 0.0;
+                            dmma884_sel(d[jt], a, bv);
+                        }
+                    }
+                    double v[NJT][2];
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt) v[jt][0] = v[jt][1] = 0.0;
+#pragma unroll
+                    for (int q2 = 0; q2 < T; ++q2) {
+                        const int src = ((q2 & 7) << 2) | lk;
+                        const double x0 = __shfl_sync(0xffffffffu, d[q2 >> 3][0], src), x1 = __shfl_sync(0xffffffffu, d[q2 >> 3][1], src);
+#pragma unroll
+                        for (int jt = 0; jt < NJT; ++jt) {
+                            const int q = jt * 8 + lr;
+                            if (q2 <= q && q < na) { const double pv = Px[q * T + q2]; v[jt][0] = fma(pv, x0, v[jt][0]); v[jt][1] = fma(pv, x1, v[jt][1]); }
+                        }
+                    }
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt) {
+                        const int q = jt * 8 + lr;
+                        if (q < na) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { const int cc = c0 + 2 * lk + e; if (cc < m) Li[tri(m + q) + cc] = -v[jt][e]; }
+                        }
+                    }
+                }
+            } else
             for (int c0 = 0; c0 < m; c0 += rows_per_pass) {
                 const int c = c0 + tid / G, l = tid % G;
                 double acc[T];
@@ -1093,7 +1204,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
                     for (int r = c + l; r < m; r += G) {
                         const double lv = Li[tri(r) + c];
 #pragma unroll
-                        for (int q = 0; q < T; ++q) if (q < na) acc[q] = fma(TV[ib[2 * T + q] * MM + r], lv, acc[q]);
+                        for (int q = 0; q < T; ++q) if (q < na) acc[q] = fma(TV[ib[2 * T + q] * MS + r], lv, acc[q]);
                     }
 #pragma unroll
                 for (int q = 0; q < T; ++q) for (int o = G >> 1; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
@@ -1225,7 +1336,7 @@ cudaError_t launch_round4(const Round4Params& P, size_t smem, cudaStream_t s, in
 }
 size_t round4_block_vec_doubles(int T, int n, int NM, int p) {
     int pl = p > 0 ? p : 1; int MM = (NM - p) > 1 ? (NM - p) : 1;
-    return (size_t)T * n + (size_t)T * NM + 4 * (size_t)T * pl + 2 * (size_t)T * MM + 7 * (size_t)T * T + 33 * (size_t)T + pl + 80 + 2 * T + 4 + 16;
+    return (size_t)T * n + (size_t)T * NM + 4 * (size_t)T * pl + 2 * (size_t)T * round4_block_row_stride(MM) + 7 * (size_t)T * T + 33 * (size_t)T + pl + 80 + 2 * T + 4 + 16;
 }
 template <int T>
 static cudaError_t launch_block_t(const Round4Params& P, size_t smem, cudaStream_t s) {
