@@ -1088,6 +1088,44 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         // ---- P5: panel (one warp, lane = block member): resolve the dependence on accepted block members.
         // Lane i decides once every accepted l < i has been folded into its pivot and leverage; the lanes j > i then
         // fold member i into theirs (the recurrences of a left-looking Cholesky / of successive Sherman-Morrison updates).
+        // (state in global memory) While warp 0 walks the panel, the other warps already form the products  t_j' L^{-1}  of ALL block
+        // members -- they do not depend on which members get accepted -- and park them in the rows m + j of L^{-1}, which are free
+        // until the block is appended; after the barrier a thread per column applies the accepted part of P_^{-1} in place.  Needs the
+        // rows m .. m + tb - 1 to exist, i.e. not within tb of the cap; otherwise the products are formed after the panel (P6 below).
+        bool early = false;
+        if constexpr (!SMEM) early = (m > 0) && (m + tb <= MM);
+        if (warp != 0 && early) {
+            if constexpr (!SMEM) {
+                constexpr int NJT = (T + 7) / 8;
+                const int lr = lane >> 2, lk = lane & 3, nw = nwarps - 1, wi = warp - 1;
+                const int ntile = (m + 7) >> 3;
+                for (int i = 0; i * nw < ntile; ++i) {
+                    const int t = i * nw + ((i & 1) ? (nw - 1 - wi) : wi);
+                    if (t >= ntile) continue;
+                    const int c0 = t << 3, c = c0 + lr;
+                    double d[NJT][2];
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt) d[jt][0] = d[jt][1] = 0.0;
+#pragma unroll 4
+                    for (int r0 = c0; r0 < m; r0 += 4) {
+                        const int r = r0 + lk;
+                        const bool rok = r < m;
+                        const double bv = (rok && c <= r) ? Li[tri(r) + c] : 0.0;
+#pragma unroll
+                        for (int jt = 0; jt < NJT; ++jt) {
+                            const double a = (rok && jt * 8 + lr < tb) ? TV[(jt * 8 + lr) * MS + r] : 0.0;
+                            dmma884_sel(d[jt], a, bv);
+                        }
+                    }
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt)
+                        if (jt * 8 + lr < tb) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { const int cc = c0 + 2 * lk + e; if (cc < m) Li[tri(m + jt * 8 + lr) + cc] = d[jt][e]; }
+                        }
+                }
+            }
+        }
         if (warp == 0) {
             const int j = lane;
             double dj2 = 0.0, lev = 0.0;
@@ -1143,7 +1181,20 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         // ---- P6: append the accepted members
         if (na > 0) {
             // new rows of L^{-1}: columns < m from  -P_^{-1} (T_ L^{-1}),  columns >= m from P_^{-1}
-            if constexpr (!SMEM) {
+            if (early) {
+                for (int c = tid; c < m; c += nt) {
+                    double xs[T];
+#pragma unroll
+                    for (int q2 = 0; q2 < T; ++q2) xs[q2] = (q2 < na) ? Li[tri(m + ib[2 * T + q2]) + c] : 0.0;     // all reads of the column first
+#pragma unroll
+                    for (int q = 0; q < T; ++q) if (q < na) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int q2 = 0; q2 < T; ++q2) if (q2 <= q) v = fma(Px[q * T + q2], xs[q2], v);
+                        Li[tri(m + q) + c] = -v;
+                    }
+                }
+            } else if constexpr (!SMEM) {
                 // tensor-path twin of the loop below: a warp owns 8 columns of L^{-1}; A = the accepted members' t-vectors (shared memory),
                 // B = 4 x 8 pieces of L^{-1} below the diagonal; the T x T triangular factor P_^{-1} is applied from registers through
                 // shuffles (lane (q, cpair) collects column pair cpair of every row q2 <= q)
