@@ -938,7 +938,41 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
         }
         __syncthreads();
         // ---- P2: u_j = b_j - Phi00 c_j ; a_j[eta] = phi(eta, xi_j) - g_eta.c_j - c_eta.b_j ; leverage l_j = pi_j.h_j
-        for (int r = tid; r < p + m; r += nt) {
+        if constexpr (!SMEM) {
+            // a_j[eta] for 8 values of eta per warp on the FP64 tensor path: K runs over the p entries of g_eta (against c_j) and the p
+            // entries of c_eta (against b_j = the first p kernel values of member j)
+            constexpr int NJT = (T + 7) / 8;
+            const int lr = lane >> 2, lk = lane & 3;
+            const int ntile = (m + 7) >> 3;
+            for (int t = warp; t < ntile; t += nwarps) {
+                const int eta = (t << 3) + lr;
+                const bool eok = eta < m;
+                const double* ge = Gm + (eok ? eta : 0) * pb; const double* ce = Cm + (eok ? eta : 0) * pb;
+                double d[NJT][2];
+#pragma unroll
+                for (int jt = 0; jt < NJT; ++jt) d[jt][0] = d[jt][1] = 0.0;
+#pragma unroll 2
+                for (int c0 = 0; c0 < p; c0 += 4) {
+                    const int c = c0 + lk;
+                    const bool cok = c < p;
+                    const double ag = (eok && cok) ? ge[c] : 0.0, ac = (eok && cok) ? ce[c] : 0.0;
+#pragma unroll
+                    for (int jt = 0; jt < NJT; ++jt) {
+                        const bool jok = cok && (jt * 8 + lr < T);
+                        dmma884_sel(d[jt], ag, jok ? CV[(jt * 8 + lr) * pl + c] : 0.0);
+                        dmma884_sel(d[jt], ac, jok ? PH[(jt * 8 + lr) * NM + c] : 0.0);
+                    }
+                }
+#pragma unroll
+                for (int jt = 0; jt < NJT; ++jt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = jt * 8 + 2 * lk + e;
+                        if (j < tb && eok) AV[j * MS + eta] = PH[j * NM + base + eta] - d[jt][e];
+                    }
+            }
+        }
+        for (int r = tid; r < (SMEM ? p + m : p); r += nt) {
             double acc[T];
 #pragma unroll
             for (int j = 0; j < T; ++j) acc[j] = 0.0;
