@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
                 double d[NJT][2];
 #pragma unroll
                 for (int jt = 0; jt < NJT; ++jt) d[jt][0] = d[jt][1] = 0.0;
-#pragma unroll 4
+#pragma unroll 8
                 for (int c0 = 0; c0 < cend; c0 += 4) {
                     const int c = c0 + lk;
                     const double a = (rok && c <= r) ? lrow[c] : 0.0;
@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(NT) round4_block_kernel(Round4Params P) {
                     double d[NJT][2];
 #pragma unroll
                     for (int jt = 0; jt < NJT; ++jt) d[jt][0] = d[jt][1] = 0.0;
-#pragma unroll 4
+#pragma unroll 8
                     for (int r0 = c0; r0 < m; r0 += 4) {
                         const int r = r0 + lk;
                         const bool rok = r < m;
