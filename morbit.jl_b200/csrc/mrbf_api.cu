@@ -17,7 +17,28 @@
 using namespace mrbf;
 
 namespace mrbf {
+// MRBF_POISON=<byte> (debugging aid; see dev_malloc below for the global-memory half): before every kernel of the library the shared
+// memory of every SM is filled with that byte -- a kernel whose result depends on shared memory it has not written (typically a padded
+// operand multiplied by zero: 0 x NaN) then fails its test instead of depending on what ran on that SM before.  Serialises the device.
+static const int g_poison = getenv("MRBF_POISON") ? atoi(getenv("MRBF_POISON")) : -1;
+__global__ void poison_smem_kernel(unsigned long long pattern, int words) {
+    extern __shared__ unsigned long long poison_sm[];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) poison_sm[i] = pattern;
+}
+static void poison_shared_memory() {
+    if (g_poison < 0) return;
+    int dev = 0, sms = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    unsigned long long pat = (unsigned long long)(g_poison & 255); pat |= pat << 8; pat |= pat << 16; pat |= pat << 32;
+    cudaDeviceSynchronize();
+    cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    poison_smem_kernel<<<4 * sms, 256, optin>>>(pat, optin / 8);      // a CTA takes a whole SM: every SM gets (at least) one
+    cudaDeviceSynchronize();
+}
 cudaError_t raise_dyn_smem_impl(const void* kernel, size_t bytes) {
+    poison_shared_memory();
     if (bytes <= 48 * 1024) return cudaSuccess;
     static std::mutex mu;
     static std::map<std::pair<const void*, int>, size_t> limit;      // (function, device) -> what the attribute was last raised to
@@ -109,6 +130,7 @@ const char* const k_phase_names[8] = {"mrbf:rounds123", "mrbf:round4", "mrbf:gat
 struct Timed {
     mrbf_ctx* c; int id;
     Timed(mrbf_ctx* ctx, int i) : c(ctx), id(i) {
+        mrbf::poison_shared_memory();         // (MRBF_POISON only; kernels with static shared memory do not pass raise_dyn_smem)
         if (g_nvtx) nvtxRangePushA(k_phase_names[id & 7]);
         if (c->prof) cudaEventRecord(c->ev0[id], c->stream);
     }
