@@ -289,6 +289,18 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
             R.keep_fs = (*keep_out)->fs; R.elig = (*keep_out)->elig;
         }
         if (schur) {
+            // Under-poised instances (N0 < p) first: the literal kernel walks them until the point set is poised and hands them over to
+            // the register kernels below (Round4Params::hyb).  Regular instances leave that launch at once.
+            const size_t lvec = round4_vec_doubles(n, NM, p), lws = round4_ws_doubles(n, NM, p);
+            if (p > 0 && (lvec + lws) * sizeof(double) <= SMEM_LIMIT) {
+                ENSURE(ctx->ws[19], sizeof(int) * 3 * (size_t)B);
+                R.hyb = (int*)ctx->ws[19].p; R.pre_cnt = R.hyb + B; R.pre_min = R.pre_cnt + B;
+                Round4Params Rp = R;
+                Rp.prefix_mode = 1; Rp.only_marked = 0; Rp.ws_in_smem = 1; Rp.ws = nullptr; Rp.ws_stride = 0; Rp.b0 = 0;
+                Timed t_(ctx, 5);
+                CK(launch_round4(Rp, (lvec + lws) * sizeof(double), ctx->stream, B));
+                ctx->launches += 1;
+            }
             ENSURE(ctx->ws[13], (size_t)B * geom.pw_doubles * sizeof(double));
             R.panel_ws = (double*)ctx->ws[13].p;
             const bool dbg = getenv("MRBF_DEBUG_CLOCK") != nullptr;

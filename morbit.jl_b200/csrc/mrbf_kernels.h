@@ -50,7 +50,13 @@ struct Round4Params {
     // accepted (plain Cholesky of the reduced kernel matrix, no leverages); instances that do not qualify get n_r4 = -1
     int build_mode;
     const double* shape_arr; double alpha_default; double* alpha2_out;   // per-instance shape parameter (NaN: default) or NULL
-    int* found_out; int* n_found_out;               // build mode: the found ids 1..p are written here for build_schur_kernel
+    int* found_out; int* n_found_out;               // build mode: the found ids 1..p are written here for build_schur_kernel    // Hand-over of under-poised instances (N0 < p: budget-limited round 3).  The literal kernel, launched first in `prefix_mode`, walks
+    // such an instance only until the point set is poised (N = p: the rank guard of RbfModel.jl:433-438 no longer applies and Z is empty
+    // again -- exactly the start state of the register kernels), leaves its acceptances in r4[0 .. pre_cnt) and the first untried id in
+    // pre_min; the register kernels then continue with found set = found | extra | r4[0 .. pre_cnt) and the candidates >= pre_min.
+    // hyb[b]: 0 regular instance, 1 hand-over pending, 2 finished by the literal kernel (never became poised).  All NULL: old behaviour.
+    int prefix_mode;
+    int* hyb; int* pre_cnt; int* pre_min;
 };
 
 // Geometry of the register-tiled round-4 kernel (mrbf_round4_schur.cu): shared-memory offsets and the layout of the

@@ -194,17 +194,22 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
     const int nf_ids = bm ? p : P.n_found[b];
     const int n_extra = P.n_extra ? P.n_extra[b] : 0;
     const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
-    const int N0 = nf_ids + n_extra;
+    // hand-over from the literal kernel's prefix run (Round4Params::hyb): npre accepted round-4 points complete the found set
+    const int hyb = (!bm && P.hyb) ? P.hyb[b] : 0;
+    const int npre = (hyb == 1) ? P.pre_cnt[b] : 0, min_id = (hyb == 1) ? P.pre_min[b] : 0;
+    const int* r4pre = P.r4 + (size_t)b * P.r4_stride;
+    const int N0 = nf_ids + n_extra + npre;
     const int max_points = P.max_points;
+    if (tid == 0) { pmeta[0] = 0.0; pmeta[3] = (double)npre; }      // [0] number of candidates handed to kernel 2 (0: nothing to do)
     if (tid == 0 && P.elig) P.elig[b] = 0;
-    if (tid == 0) pmeta[0] = 0.0;                  // [0] number of candidates handed to kernel 2 (0: nothing to do)
+    if (hyb == 2) return;                          // finished by the literal kernel: results are in place
     if (bm) {
         // build mode: found set = the first p training points, candidates = all the others; too few / too many points: general kernel
         if (n_db <= p || n_db - p > MC) { if (tid == 0) P.n_r4[b] = -1; return; }
         for (int i = tid; i < p; i += nt) P.found_out[(size_t)b * P.found_stride + i] = i + 1;
         if (tid == 0) P.n_found_out[b] = p;
     } else {
-        if (!(N0 < max_points)) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
+        if (!(N0 < max_points)) { if (tid == 0) { P.n_r4[b] = npre; if (P.status) P.status[b] = 0; } return; }
         if (N0 != p || n_db > MC) { if (tid == 0) P.n_r4[b] = -1; return; }      // literal kernel takes over
     }
 
@@ -214,9 +219,9 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
         // nothing to scan
     } else if (P.cflags) {
         const unsigned char* cf = P.cflags + (size_t)b * P.db_stride;
-        for (int id = tid; id < n_db; id += nt) { const unsigned f = cf[id]; cflag[id] = ((f & 2u) && !(f & 4u)) ? 1 : 0; }
+        for (int id = tid; id < n_db; id += nt) { const unsigned f = cf[id]; cflag[id] = ((f & 2u) && !(f & 4u) && id >= min_id) ? 1 : 0; }
     } else {
-        for (int id = tid; id < n_db; id += nt) cflag[id] = 1;
+        for (int id = tid; id < n_db; id += nt) cflag[id] = (id >= min_id) ? 1 : 0;
         __syncthreads();
         for (int e = tid; e < n_db * n; e += nt) {
             const int id = e / n, k = e % n;
@@ -227,7 +232,8 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
     }
     for (int e = tid; e < p * n; e += nt) {
         const int i = e / n, k = e % n;
-        X0[e] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k]);
+        X0[e] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k]
+                                 : ((i < nf_ids + n_extra) ? extra[(size_t)(i - nf_ids) * n + k] : sites[(size_t)(r4pre[i - nf_ids - n_extra] - 1) * n + k]));
     }
     if (tid == 0) red[76] = 0.0;
     __syncthreads();
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
         inv_s = mx > 0.0 ? 1.0 / mx : 1.0;
     }
     __syncthreads();
-    if (mc == 0) { if (tid == 0) { P.n_r4[b] = 0; if (P.status) P.status[b] = 0; } return; }
+    if (mc == 0) { if (tid == 0) { P.n_r4[b] = npre; if (P.status) P.status[b] = 0; } return; }
     if (p <= 32 && nwarps == 8) {
         // ---- Pi_0^{-1} by Gauss-Jordan on [Pi_0 | I] held in REGISTERS: lane i owns row i, warp w the columns w, w + 8, ..  The pivot
         // row of a step is never moved (its index is remembered instead of a row swap: row k of the inverse is row r_k of the right
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(256, 4) round4_prep_kernel(Round4Params P, Sch
                 const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
                 const unsigned win = __ballot_sync(0xffffffffu, vh == mh && vl == ml && !used);
                 const double mv = __hiloint2double((int)mh, (int)ml);
-                const int r = (mv > (bm ? 1e-6 : 1e-12) && win) ? (__ffs(win) - 1) : -1;      // build mode: an ill-conditioned Pi_0 goes to the QR-based kernel
+                const int r = (mv > ((bm || npre > 0) ? 1e-6 : 1e-12) && win) ? (__ffs(win) - 1) : -1;      // build mode: an ill-conditioned Pi_0 goes to the QR-based kernel
                 const double pv = __shfl_sync(0xffffffffu, v, r < 0 ? 0 : r);
                 fb[par * 32 + lane] = v;
                 if (lane == 0) { ib[par] = r; rpb[par] = (r < 0) ? 0.0 : fast_rcp(pv); }
@@ -498,9 +504,10 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     if (mc == 0) return;                            // kernel 1 has already written n_r4 (0, or -1 for the literal kernel)
     const double inv_s = pmeta[1];
     const int N0 = (int)pmeta[2];
+    const int npre = (int)pmeta[3];                 // round-4 points the literal kernel accepted before the hand-over (part of S0 here)
     const int max_points = P.max_points;
-    int* r4 = P.r4 + (size_t)b * P.r4_stride;
-    double* keep = P.keep_fs ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;
+    int* r4 = P.r4 + (size_t)b * P.r4_stride + npre;
+    double* keep = (P.keep_fs && npre == 0) ? P.keep_fs + (size_t)b * P.fs_stride : nullptr;    // a handed-over instance keeps no factorisation (elig stays 0)
     const int TRa = (mc + 3) >> 2, MCa = TRa * 4;   // tile rows / padded candidate count actually in use
     if (g.two_variants && (SMALL != (schur_tiles(TRa) <= 352))) return;      // the other launch shape's instance
     const int LD = MCa, H = LD >> 1;
@@ -531,7 +538,8 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
         const double* extra = P.extra_sites ? P.extra_sites + (size_t)b * P.extra_stride * n : nullptr;
         for (int e = tid; e < p * n; e += nt) {
             const int i = e / n, k = e % n;
-            X0[i * nx + k] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k] : extra[(size_t)(i - nf_ids) * n + k]);
+            X0[i * nx + k] = bm ? sites[e] : ((i < nf_ids) ? sites[(size_t)(found[i] - 1) * n + k]
+                                              : ((i < p - npre) ? extra[(size_t)(i - nf_ids) * n + k] : sites[(size_t)(r4[i - p] - 1) * n + k]));   // r4[-npre .. -1]: the literal kernel's prefix
         }
         for (int e = tid; e < p * p; e += nt) { const double v = pw[g.pw_M0 + e]; M0[e] = v; if (keep) keep[g.off_M0 + e] = v; }
         const int* cl = reinterpret_cast<const int*>(pw + g.pw_clist);
@@ -647,7 +655,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     SCHUR_STAMP(4);
 
     const double thr = P.chol_thr;
-    const int cap = min(max_points - N0, P.r4_stride);       // RbfModel.jl:402
+    const int cap = min(max_points - N0, P.r4_stride - npre);       // RbfModel.jl:402
 
     if (lev_warp) {
         // ---- leverage warp.  Block K: (a) downdate M by the candidates accepted in block K - 1 (multipliers from the diagonal-tile
@@ -940,7 +948,7 @@ __global__ void __launch_bounds__(SMALL ? 384 : 576, SMALL ? 2 : 1) round4_elim_
     if (nacc_diag >= 0) nacc = nacc_diag;
     if (tid == 0 && bm && (bm_failed || nacc != mc)) { P.n_r4[b] = -1; return; }      // build mode: the general kernel takes the instance
     if (tid == 0) {
-        P.n_r4[b] = nacc; if (P.status) P.status[b] = 0;
+        P.n_r4[b] = npre + nacc; if (P.status) P.status[b] = 0;
         if (bm && P.alpha2_out) P.alpha2_out[b] = rf.alpha2;
         if (keep) {
             keep[g.off_acc + MC + 0] = inv_s; keep[g.off_acc + MC + 1] = (double)N0; keep[g.off_acc + MC + 2] = (double)nacc;

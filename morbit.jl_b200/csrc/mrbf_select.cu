@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
     extern __shared__ double smem[];
     const int b = P.b0 + blockIdx.x, n = P.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     if (P.only_marked && P.n_r4[b] != -1) return;      // handled by the shared-memory fast path
+    const bool prefix = P.prefix_mode != 0;            // walk under-poised instances until N = p only (see Round4Params::hyb)
+    if (prefix) {
+        const int N0_ = P.n_found[b] + (P.n_extra ? P.n_extra[b] : 0);
+        if (tid == 0) { P.hyb[b] = 0; P.pre_cnt[b] = 0; P.pre_min[b] = 0; }
+        if (!(N0_ < poly_dim(P.n, P.cfg.polynomial_degree)) || !(N0_ < P.max_points) || N0_ > P.NM) return;     // regular instance
+    }
     const int NM = P.NM, MM = P.NM;
     const int deg = P.cfg.polynomial_degree;
     const int p = poly_dim(n, deg);
@@ -547,7 +553,9 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
     const int full_rank_dim = deg < 0 ? 0 : p;
     const double thr = P.chol_thr;                 // (theta_pivot_cholesky^2)^2, RbfModel.jl:370, 452
 
-    for (int id = 0; id < n_db && N < max_points && nr4 < P.r4_stride; ++id) {
+    int id_next = 0;
+    for (int id = 0; id < n_db && N < max_points && nr4 < P.r4_stride && !(prefix && N >= p); ++id) {
+        id_next = id + 1;
         if (!cand[id]) continue;                   // block-uniform: in box 2 and not in the found set
         __syncthreads();
         for (int k = tid; k < n; k += nt) xi[k] = sites[(size_t)id * n + k];
@@ -670,7 +678,14 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
         N += 1; m += 1; nr4 += 1;
         __syncthreads();
     }
-    if (tid == 0) { P.n_r4[b] = nr4; if (P.status) P.status[b] = 0; }
+    if (tid == 0) {
+        if (prefix && N >= p && id_next < n_db && N < max_points && nr4 < P.r4_stride) {
+            P.hyb[b] = 1; P.pre_cnt[b] = nr4; P.pre_min[b] = id_next;       // poised now: the register kernels continue (n_r4 is theirs to write)
+        } else {
+            P.n_r4[b] = nr4; if (P.status) P.status[b] = 0;
+            if (prefix) P.hyb[b] = 2;
+        }
+    }
 }
 
 
