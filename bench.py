@@ -342,7 +342,8 @@ def run_ours(args):
               "build": float(np.sum(build_flops(Ntrain, N_VARS, K_OUT))), "build_prepared": float(np.sum(build_flops(Ntrain, N_VARS, K_OUT)))}
     dom = max(("rounds123", "round4", "build", "build_prepared"), key=lambda k: prof[k])
     ach = kflops[dom] / (prof[dom] * 1e-3) / 1e12
-    step_total = prof["rounds123"] + prof["round4"] + prof["round4_fallback"] + prof["gather"] + prof["build"] + prof["build_prepared"]
+    step_total = (prof["rounds123"] + prof["round4"] + prof["round4_fallback"] + prof.get("round4_prefix", 0.0) + prof["gather"] + prof["build"]
+                  + prof["build_prepared"])
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json"))).get(dom) if B == B_PER_GPU else None
     except Exception:

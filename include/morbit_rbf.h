@@ -89,7 +89,7 @@ int64_t mrbf_launch_count(const mrbf_ctx* ctx);
  * events on the context's stream.  mrbf_profile_read synchronises and returns the device time in ms of the LAST
  * launch of each kernel class: ms[0] rounds 1-3, ms[1] round 4, ms[2] training-set gather, ms[3] build,
  * ms[4] eval/Jacobian (all passes of the last call), ms[5] round-4 fallback kernel, ms[6] build from a kept
- * factorisation, ms[7] reserved (0). */
+ * factorisation, ms[7] round-4 literal prefix run of under-poised instances (until they are poised). */
 int mrbf_profile_enable(mrbf_ctx* ctx, int32_t on);
 int mrbf_profile_read(mrbf_ctx* ctx, double* ms8);
 

@@ -126,7 +126,7 @@ int fail(mrbf_ctx* c, int code, const char* fmt, const char* detail = "") {
 // `ncu --nvtx --nvtx-include "mrbf:round4/"` or a timeline tool can address the phases by name.
 const bool g_nvtx = getenv("MRBF_NVTX") && atoi(getenv("MRBF_NVTX")) != 0;
 const char* const k_phase_names[8] = {"mrbf:rounds123", "mrbf:round4", "mrbf:gather", "mrbf:build", "mrbf:eval", "mrbf:round4_literal",
-                                      "mrbf:build_prepared", "mrbf:other"};
+                                      "mrbf:build_prepared", "mrbf:round4_prefix"};
 struct Timed {
     mrbf_ctx* c; int id;
     Timed(mrbf_ctx* ctx, int i) : c(ctx), id(i) {
@@ -291,13 +291,15 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
         if (schur) {
             // Under-poised instances (N0 < p) first: the literal kernel walks them until the point set is poised and hands them over to
             // the register kernels below (Round4Params::hyb).  Regular instances leave that launch at once.
-            const size_t lvec = round4_vec_doubles(n, NM, p), lws = round4_ws_doubles(n, NM, p);
+            // The prefix run never holds more than p points: with NM = p its whole state (Phi, Q, R, Z, L^-1) lives in shared memory.
+            const size_t lvec = round4_vec_doubles(n, p, p), lws = round4_ws_doubles(n, p, p);
             if (p > 0 && (lvec + lws) * sizeof(double) <= SMEM_LIMIT) {
                 ENSURE(ctx->ws[19], sizeof(int) * 3 * (size_t)B);
                 R.hyb = (int*)ctx->ws[19].p; R.pre_cnt = R.hyb + B; R.pre_min = R.pre_cnt + B;
                 Round4Params Rp = R;
+                Rp.NM = p;
                 Rp.prefix_mode = 1; Rp.only_marked = 0; Rp.ws_in_smem = 1; Rp.ws = nullptr; Rp.ws_stride = 0; Rp.b0 = 0;
-                Timed t_(ctx, 5);
+                Timed t_(ctx, 7);
                 CK(launch_round4(Rp, (lvec + lws) * sizeof(double), ctx->stream, B));
                 ctx->launches += 1;
             }

@@ -238,7 +238,7 @@ class Engine:
         ms = (C.c_double * 8)()
         self._check(self.lib.mrbf_profile_read(self.ctx, ms))
         return dict(rounds123=ms[0], round4=ms[1], gather=ms[2], build=ms[3], eval=ms[4], round4_fallback=ms[5],
-                    build_prepared=ms[6])
+                    build_prepared=ms[6], round4_prefix=ms[7])
 
     @property
     def launch_count(self) -> int:
