@@ -291,9 +291,16 @@ int run_round4(mrbf_ctx* ctx, const mrbf_cfg* cfg, int B, int n, int db_stride, 
         if (schur) {
             // Under-poised instances (N0 < p) first: the literal kernel walks them until the point set is poised and hands them over to
             // the register kernels below (Round4Params::hyb).  Regular instances leave that launch at once.
+            // Only for kernels that are conditionally positive definite of order <= 1 (Gaussian, inverse multiquadric, multiquadric,
+            // cubic with exponent 1).  The reference appends a column to Z on EVERY acceptance (RbfModel.jl:464-467), also while N < p,
+            // so at N = p its Z holds p - N0 directions that are orthogonal to the constants (the first column of Q spans them) but not to
+            // the linear polynomials.  For order <= 1 the reduced kernel matrix is positive definite on any such Z: tau^2 > 0 for every
+            // candidate that is not a duplicate, exactly like the walk that starts afresh from the poised set -- same decisions.  For
+            // order 2 (cubic, thin plate spline) it is indefinite there and the reference goes on rejecting candidates a fresh walk
+            // accepts (tests/test_handover_property.py holds the counterexample): those stay on the literal kernel for the whole walk.
             // The prefix run never holds more than p points: with NM = p its whole state (Phi, Q, R, Z, L^-1) lives in shared memory.
             const size_t lvec = round4_vec_doubles(n, p, p), lws = round4_ws_doubles(n, p, p);
-            if (p > 0 && (lvec + lws) * sizeof(double) <= SMEM_LIMIT) {
+            if (p > 0 && cpd <= 1 && (lvec + lws) * sizeof(double) <= SMEM_LIMIT) {
                 ENSURE(ctx->ws[19], sizeof(int) * 3 * (size_t)B);
                 R.hyb = (int*)ctx->ws[19].p; R.pre_cnt = R.hyb + B; R.pre_min = R.pre_cnt + B;
                 Round4Params Rp = R;

@@ -51,9 +51,10 @@ struct Round4Params {
     int build_mode;
     const double* shape_arr; double alpha_default; double* alpha2_out;   // per-instance shape parameter (NaN: default) or NULL
     int* found_out; int* n_found_out;               // build mode: the found ids 1..p are written here for build_schur_kernel    // Hand-over of under-poised instances (N0 < p: budget-limited round 3).  The literal kernel, launched first in `prefix_mode`, walks
-    // such an instance only until the point set is poised (N = p: the rank guard of RbfModel.jl:433-438 no longer applies and Z is empty
-    // again -- exactly the start state of the register kernels), leaves its acceptances in r4[0 .. pre_cnt) and the first untried id in
-    // pre_min; the register kernels then continue with found set = found | extra | r4[0 .. pre_cnt) and the candidates >= pre_min.
+    // such an instance only until the point set is poised (N = p: the rank guard of RbfModel.jl:433-438 no longer applies), leaves its
+    // acceptances in r4[0 .. pre_cnt) and the first untried id in pre_min; the register kernels then continue with found set =
+    // found | extra | r4[0 .. pre_cnt) and the candidates >= pre_min.  Decision-equivalent to the reference's walk only for kernels of
+    // cpd order <= 1 (run_round4 in mrbf_api.cu explains why and enables it only for those).
     // hyb[b]: 0 regular instance, 1 hand-over pending, 2 finished by the literal kernel (never became poised).  All NULL: old behaviour.
     int prefix_mode;
     int* hyb; int* pre_cnt; int* pre_min;

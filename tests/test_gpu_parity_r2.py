@@ -470,3 +470,20 @@ def test_concurrent_contexts_with_different_shapes_share_the_kernels():
     assert not errors, errors
     for (w, it), v in out.items():
         assert np.array_equal(v, serial[(w, it % 3)]), (w, it)
+
+
+@pytest.mark.parametrize("kernel", ["multiquadric", "gaussian", "cubic"])
+def test_under_poised_round4_with_and_without_hand_over(engine, kernel):
+    """Explicit under-poised found sets through mrbf_round4 on the instances of tests/test_handover_property.py: kernels of cpd order <= 1
+    are handed over from the literal kernel's prefix run to the register kernels once they are poised, cubic (order 2: the reference goes
+    on rejecting what a fresh walk would accept) stays on the literal kernel -- either way the ids are the oracle's."""
+    import test_handover_property as H
+    for n, n_db, n_found in [(3, 40, 2), (5, 60, 1), (8, 90, 3), (12, 120, 1)]:
+        rng = np.random.default_rng(100 * n + n_db + n_found)
+        for rep in range(4):
+            sites, lb2, ub2 = H._instance(rng, n, n_db)
+            found0 = H._found0(rng, sites, lb2, ub2, n_found)
+            cfg = mb.RbfConfig(kernel=kernel)
+            ref, _ = CO.round4(O.RbfConfig(kernel=kernel), sites, lb2, ub2, found0)
+            r4, n_r4, status = engine.round4(cfg, sites[None], [n_db], lb2[None], ub2[None], np.array([found0]), [len(found0)])
+            assert status[0] == 0 and [int(v) for v in r4[0, :n_r4[0]]] == [int(v) for v in ref], (n, rep, found0)
