@@ -515,7 +515,7 @@ def run_ours(args):
                                             "mean_backtrack_index": float(bth[0].double().mean().item()),
                                             "backtracked_fraction": float((bth[0] > 0).double().mean().item())},
                           "config": {"workload": f"{B} instances per GPU, database snapshots of {N_DB} sites with half of them inside the trust region, radii "
-                                                 "Delta x {1/4, 1/2, 1, 2}, round-3 budgets {0, 2, unlimited} with probabilities {5, 5, 90} % (budget-limited instances start round 4 under-poised and take the literal kernel), ensure_fully_linear on for half of the instances"}})
+                                                 "Delta x {1/4, 1/2, 1, 2}, round-3 budgets {0, 2, unlimited} with probabilities {5, 5, 90} % (budget-limited instances start round 4 under-poised: the literal kernel walks them until they are poised, then the register kernels continue), ensure_fully_linear on for half of the instances"}})
         m_h.free(); del dev_h, b_h
         # the LP alone on a workload where the simplex has to pivot: four conflicting random gradients, iterates partly on the bounds
         g_l = torch.Generator(device="cuda"); g_l.manual_seed(7 + rank)
