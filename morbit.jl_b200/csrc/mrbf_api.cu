@@ -86,7 +86,7 @@ struct mrbf_prepared {
     double* fs = nullptr;
     int* ints = nullptr;        // elig[B], n_found[B], n_extra[B], n_r4[B], found[B*found_stride], r4[B*r4_stride]
     int *elig, *n_found, *n_extra, *n_r4, *found, *r4;
-    int kind = 0;               // 0: round4_block_kernel layout (round4_fast_state_layout), 1: round4_schur_kernel layout,
+    int kind = 0;               // 0: round4_block_kernel layout (round4_fast_state_layout), 1: round4_elim_kernel layout,
                                 // 2: no factorisation at all (optimized_sampling = false): every instance takes the general route
     SchurGeom geom{};
 };
@@ -844,7 +844,7 @@ static int build_impl(mrbf_ctx* ctx, const mrbf_cfg* cfg, int32_t B, int32_t n, 
         }
     }
     if (e == cudaSuccess && kp && kp->kind == 1 && kp->cfg_degree == deg && kp->p > 0) {
-        // 1'. factorisation kept by round4_schur_kernel: two triangular solves per output
+        // 1'. factorisation kept by round4_elim_kernel: two triangular solves per output
         SchurBuildParams Q{};
         const SchurGeom& g = kp->geom;
         Q.B = B; Q.n = n; Q.k = k; Q.p = kp->p; Q.deg = deg; Q.db_stride = kp->db_stride; Q.found_stride = kp->found_stride;

@@ -572,7 +572,7 @@ cudaError_t launch_build_prepared(const PreparedBuildParams& P, size_t smem, cud
 
 
 // ------------------------------------------------------------------------------------------------
-// Build from the factorisation kept by round4_schur_kernel (mrbf_round4_schur.cu).
+// Build from the factorisation kept by round4_elim_kernel (mrbf_round4_schur.cu).
 //
 // That kernel leaves, per instance: M0 = Pi_0^{-T}, the panels C (Lagrange coefficients) and U = Phi(S0, .) - Phi00 C over
 // the candidate positions, and the Cholesky factor L of A = N' Phi N over the accepted candidates (column q = q-th accepted

@@ -43,7 +43,7 @@ struct Round4Params {
     int only_marked;              // literal kernel: process only instances the fast kernel marked (n_r4 == -1)
     double* fs; size_t fs_stride; int fs_in_smem;   // fast-path state
     double* keep_fs; int* elig;                     // kept factorisation (mrbf_prepared) or NULL
-    double* panel_ws;                               // round4_panels_kernel -> round4_schur_kernel hand-over (B x SchurGeom::pw_doubles)
+    double* panel_ws;                               // round4_prep_kernel -> round4_elim_kernel hand-over (B x SchurGeom::pw_doubles)
     long long* dbg_clock;                           // instrumentation (MRBF_DEBUG_CLOCK): phase time stamps of CTA 0, or NULL
     // build mode of the register-tiled kernels (mrbf_build without a kept factorisation): `sites` are the training sets
     // (B x db_stride x n, n_db = N), the found set is the first p training points, every other point is a candidate that MUST be
@@ -101,7 +101,7 @@ struct PreparedBuildParams {
     double* centers; double* w; double* lam; double* alpha2_out; int* N; int* status; int* done;
 };
 
-// Build from the factorisation kept by round4_schur_kernel (layout: SchurGeom::off_*).
+// Build from the factorisation kept by round4_elim_kernel (layout: SchurGeom::off_*).
 struct SchurBuildParams {
     int B, n, k, p, deg, db_stride, found_stride, r4_stride, train_stride, MC;
     size_t fs_stride, off_M0, off_U, off_C, off_L, off_acc;

@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(256) round4_kernel(Round4Params P) {
 
 // ------------------------------------------------------------------------------------------------
 // Round 4, Lagrange-basis formulation for the regular case N0 == p (found set = centre + n poised points): the blocked
-// left-looking kernel for large databases (round4_schur_kernel in mrbf_round4_schur.cu takes databases of <= 128 sites).
+// left-looking kernel for large databases (round4_elim_kernel in mrbf_round4_schur.cu takes databases of <= 128 sites).
 //
 // Same decisions as RbfModel.jl:420-452, different basis.  Let S0 be the found set (Pi_0 = Pi(S0) is p x p and
 // non-singular).  Every later point xi has the null vector  n_xi = e_xi - sum_{s in S0} c_xi[s] e_s,
