@@ -220,3 +220,43 @@ def test_gather_results_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
+
+
+def test_stream_ordered_lib_brackets_only_the_device_entry_points():
+    """engine._StreamOrderedLib: symbols that do not end in `_dev` are the library's own; `_dev` calls are bracketed by stream waits only
+    when the context's stream differs from torch's current one (exercised on the GPU by
+    test_dev_entry_points_are_ordered_with_torchs_stream; here the control flow with stand-ins)."""
+    from morbit_jl_b200.engine import _StreamOrderedLib
+
+    class FakeLib:
+        def __init__(self): self.calls = []
+        def mrbf_sync(self, *a): self.calls.append(("mrbf_sync", a)); return 0
+        def mrbf_eval_dev(self, *a): self.calls.append(("mrbf_eval_dev", a)); return 7
+
+    class FakeStream:
+        def __init__(self, log, name): self.log, self.name = log, name
+        def wait_stream(self, other): self.log.append((self.name, "waits for", other.name))
+
+    class FakeEngine:
+        device = 0
+        def __init__(self): self.ext = None
+        def _foreign_stream(self): return self.ext
+
+    lib, eng = FakeLib(), FakeEngine()
+    proxy = _StreamOrderedLib(lib, eng)
+    assert proxy.mrbf_sync.__self__ is lib and proxy.mrbf_sync(1) == 0            # passed through untouched
+    assert proxy.mrbf_eval_dev(1, 2) == 7 and lib.calls[-1] == ("mrbf_eval_dev", (1, 2))     # same stream: a plain call
+    # a foreign stream: engine stream waits for torch's, then torch's waits for the engine's -- needs torch only for current_stream()
+    import torch
+    log = []
+    eng.ext = FakeStream(log, "engine")
+    cur = FakeStream(log, "torch")
+    orig = torch.cuda.current_stream
+    torch.cuda.current_stream = lambda device=None: cur
+    try:
+        assert proxy.mrbf_eval_dev(3) == 7
+    finally:
+        torch.cuda.current_stream = orig
+    assert log == [("engine", "waits for", "torch"), ("torch", "waits for", "engine")] and lib.calls[-1] == ("mrbf_eval_dev", (3,))
+    with pytest.raises(AttributeError):
+        proxy.mrbf_no_such_symbol
